@@ -1,0 +1,307 @@
+"""CPU oracle for the vectorised Eagle/Firefly acquisition optimiser and its driver.
+
+TEST INFRASTRUCTURE ONLY (see oracle/gp_oracle.py header for the rules).
+
+Restates, in NumPy, the continuous-feature path of
+  vizier/_src/algorithms/optimizers/eagle_strategy.py   (a12-a14 in SURVEY 8a)
+  vizier/_src/algorithms/optimizers/vectorized_base.py  (a11)
+  vizier/_src/algorithms/optimizers/random_vectorized_optimizer.py
+with n_parallel == 1.
+
+Randomness.  The reference draws from JAX threefry (`jax.random.uniform`,
+`laplace`, `split`); bit-matching it is out of scope.  Parity is
+stage-wise with INJECTED draws: every function takes its random numbers as
+arrays.  For whole-loop comparisons the product and this oracle share one
+counter-based generator, Philox4x32-10 (`philox_uniform` below, validated
+against the Random123 known-answer vectors in tests/test_philox.py).
+
+With n_parallel == 1 the reference's normalised Laplace noise
+(eagle_strategy.py:1033-1044: noise / max|noise| over axis=1) is exactly
+sign(noise) = +-1 per coordinate, so only a sign bit per coordinate is drawn.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable, Optional
+
+import numpy as np
+
+# EagleStrategyConfig defaults, eagle_strategy.py:139-167.
+@dataclasses.dataclass(frozen=True)
+class EagleConfig:
+  visibility: float = 0.45
+  gravity: float = 1.5
+  negative_gravity: float = 0.008
+  perturbation: float = 0.16
+  perturbation_lower_bound: float = 7e-5
+  penalize_factor: float = 0.7
+  pool_size_exponent: float = 1.2
+  pool_size: int = 0
+  max_pool_size: int = 100
+  normalization_scale: float = 0.5
+  prior_trials_pool_pct: float = 0.96
+
+
+def default_pool_size(n_features: int, batch_size: Optional[int], cfg: EagleConfig) -> int:
+  """eagle_strategy.py:376-386."""
+  pool = cfg.pool_size
+  if pool == 0:
+    pool = 10 + int(0.5 * n_features + n_features**cfg.pool_size_exponent)
+    pool = min(pool, cfg.max_pool_size)
+    if batch_size is not None:
+      pool = int(np.ceil(pool / batch_size) * batch_size)
+  return pool
+
+
+# ----------------------------------------------------------------------------
+# Philox4x32-10 (Salmon et al. 2011), shared with vizier_b200/csrc/philox.cuh
+# ----------------------------------------------------------------------------
+_M0 = np.uint64(0xD2511F53)
+_M1 = np.uint64(0xCD9E8D57)
+_W0 = np.uint32(0x9E3779B9)
+_W1 = np.uint32(0xBB67AE85)
+
+STREAM_INIT_POOL = 0
+STREAM_PERTURB_SIGN = 1
+STREAM_TRIM = 2
+STREAM_RANDOM_POOL = 3  # RandomVectorizedStrategy candidate pool
+
+
+def philox4x32(counter: np.ndarray, key: np.ndarray) -> np.ndarray:
+  """counter [...,4] uint32, key [2] uint32 -> [...,4] uint32 (10 rounds)."""
+  c = np.array(counter, dtype=np.uint32, copy=True)
+  c0, c1, c2, c3 = (c[..., i].copy() for i in range(4))
+  k0 = np.uint32(key[0])
+  k1 = np.uint32(key[1])
+  with np.errstate(over='ignore'):
+    for _ in range(10):
+      p0 = _M0 * c0.astype(np.uint64)
+      p1 = _M1 * c2.astype(np.uint64)
+      hi0 = (p0 >> np.uint64(32)).astype(np.uint32)
+      lo0 = (p0 & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+      hi1 = (p1 >> np.uint64(32)).astype(np.uint32)
+      lo1 = (p1 & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+      c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+      k0 = np.uint32(k0 + _W0)
+      k1 = np.uint32(k1 + _W1)
+  return np.stack([c0, c1, c2, c3], axis=-1)
+
+
+def philox_uniform(seed: int, stream: int, iteration: int, n: int) -> np.ndarray:
+  """n doubles in [0,1): element e uses counter (e, iteration, stream, 0).
+
+  u = ((w0 >> 5) * 2^26 + (w1 >> 6)) / 2^53 from output words w0, w1.
+  """
+  e = np.arange(n, dtype=np.uint32)
+  ctr = np.stack([
+      e,
+      np.full(n, iteration, np.uint32),
+      np.full(n, stream, np.uint32),
+      np.zeros(n, np.uint32),
+  ], axis=-1)
+  key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+  out = philox4x32(ctr, key)
+  a = (out[..., 0] >> np.uint32(5)).astype(np.float64)
+  b = (out[..., 1] >> np.uint32(6)).astype(np.float64)
+  return (a * 67108864.0 + b) / 9007199254740992.0
+
+
+def philox_signs(seed: int, iteration: int, n: int) -> np.ndarray:
+  """+-1 per coordinate: +1 if u >= 0.5 else -1."""
+  u = philox_uniform(seed, STREAM_PERTURB_SIGN, iteration, n)
+  return np.where(u >= 0.5, 1.0, -1.0)
+
+
+# ----------------------------------------------------------------------------
+# Strategy state and steps
+# ----------------------------------------------------------------------------
+@dataclasses.dataclass
+class EagleState:
+  iterations: int
+  features: np.ndarray  # [P, D]
+  rewards: np.ndarray  # [P]
+  best_reward: float
+  perturbations: np.ndarray  # [P]
+
+  def copy(self) -> 'EagleState':
+    return EagleState(self.iterations, self.features.copy(), self.rewards.copy(),
+                      self.best_reward, self.perturbations.copy())
+
+
+def features_dist_squared(batch: np.ndarray, pool: np.ndarray) -> np.ndarray:
+  """Direct sum (a-b)^2 as in eagle_strategy_test.py:89-104 (`_create_features_simple`).
+
+  The library code (eagle_strategy.py:451-455) uses |a|^2+|b|^2-2ab; both agree
+  to ~1e-15 on [0,1]^D and the reference tests one against the other.
+  """
+  diff = batch[:, None, :] - pool[None, :, :]
+  return np.sum(diff * diff, axis=-1)
+
+
+def mask_flip(prior_features: np.ndarray, prior_rewards: np.ndarray):
+  """eagle_strategy.py:472-496: valid entries newest-first, -inf ones last."""
+  mask = ~np.isneginf(prior_rewards)
+  idx = np.flip(np.argsort(np.where(mask, np.arange(prior_rewards.shape[0]), -1), kind='stable'))
+  return prior_features[idx], prior_rewards[idx]
+
+
+def populate_pool_with_prior_trials(
+    random_pool: np.ndarray, prior_features: np.ndarray, prior_rewards: np.ndarray,
+    cfg: EagleConfig,
+) -> np.ndarray:
+  """eagle_strategy.py:568-713.  random_pool [P, D] are the injected uniform draws."""
+  pool_size = random_pool.shape[0]
+  flipped_f, flipped_r = mask_flip(prior_features, prior_rewards)
+  n_random = int(pool_size * (1 - cfg.prior_trials_pool_pct))
+  init_features = random_pool[:n_random]
+  left = pool_size - n_random
+  random_features = random_pool[n_random:]
+  features = flipped_f[:left].copy()
+  rewards = flipped_r[:left].copy()
+  for i in range(left, prior_rewards.shape[0]):
+    d = features_dist_squared(flipped_f[i][None, :], features)[0]
+    ind = int(np.argmin(d))
+    if rewards[ind] < flipped_r[i]:
+      features[ind] = flipped_f[i]
+      rewards[ind] = flipped_r[i]
+  chosen = rewards.shape[0]
+  features = np.where(np.isneginf(rewards)[:, None], random_features[:chosen], features)
+  features = np.concatenate([features, random_features[chosen:]], axis=0)
+  return np.concatenate([init_features, features], axis=0)
+
+
+def init_state(
+    random_pool: np.ndarray, cfg: EagleConfig,
+    prior_features: Optional[np.ndarray] = None, prior_rewards: Optional[np.ndarray] = None,
+) -> EagleState:
+  """eagle_strategy.py:527-565."""
+  pool_size = random_pool.shape[0]
+  if prior_features is not None and prior_rewards is not None and prior_features.shape[0] > 0:
+    feats = populate_pool_with_prior_trials(random_pool, prior_features, prior_rewards, cfg)
+  else:
+    feats = random_pool.copy()
+  return EagleState(0, feats, np.full(pool_size, -np.inf), -np.inf,
+                    np.full(pool_size, cfg.perturbation))
+
+
+def create_features(
+    pool: np.ndarray, rewards: np.ndarray, batch: np.ndarray, rewards_batch: np.ndarray,
+    perturbations: np.ndarray, cfg: EagleConfig,
+) -> np.ndarray:
+  """eagle_strategy.py:784-952, MEAN normalisation, ADDITIVE perturbation.
+
+  perturbations [B, D] already = sign * perturbation_i.
+  """
+  n_features = pool.shape[1]
+  dists = features_dist_squared(batch, pool)
+  with np.errstate(invalid='ignore'):
+    directions = rewards[None, :] - rewards_batch[:, None]
+  scaled_dir = np.where(directions >= 0.0, cfg.gravity, -cfg.negative_gravity)
+  force = np.exp(-cfg.visibility * dists / n_features * 10.0)
+  scaled_force = scaled_dir * force * np.isfinite(rewards).astype(np.float64)[None, :]
+  pulls = np.maximum(scaled_force, 0.0)
+  push = np.minimum(scaled_force, 0.0)
+  with np.errstate(invalid='ignore', divide='ignore'):
+    npull = cfg.normalization_scale * np.nan_to_num(
+        pulls / np.sum(pulls > 0.0, axis=1, keepdims=True), nan=0.0)
+    npush = cfg.normalization_scale * np.nan_to_num(
+        push / np.sum(push < 0.0, axis=1, keepdims=True), nan=0.0)
+  scale = npull + npush
+  change = scale @ pool - batch * np.sum(scale, axis=-1, keepdims=True)
+  return batch + change + perturbations
+
+
+def suggest(state: EagleState, batch_size: int, signs: np.ndarray, cfg: EagleConfig) -> np.ndarray:
+  """eagle_strategy.py:720-782 incl. DefaultProjection clip to [0,1] (:257-268)."""
+  pool_size = state.features.shape[0]
+  nb = pool_size // batch_size
+  start = (state.iterations % nb) * batch_size
+  fb = state.features[start : start + batch_size]
+  if state.iterations < nb:
+    new = fb.copy()
+  else:
+    rb = state.rewards[start : start + batch_size]
+    pb = state.perturbations[start : start + batch_size]
+    new = create_features(state.features, state.rewards, fb, rb, signs * pb[:, None], cfg)
+  return np.clip(new, 0.0, 1.0)
+
+
+def update(
+    state: EagleState, batch_size: int, batch_features: np.ndarray, batch_rewards: np.ndarray,
+    random_features: np.ndarray, cfg: EagleConfig,
+) -> EagleState:
+  """eagle_strategy.py:1075-1247 (update, _update_pool_features_and_rewards, _trim_pool)."""
+  pool_size = state.features.shape[0]
+  nb = pool_size // batch_size
+  new_best = max(state.best_reward, float(np.max(batch_rewards)))
+  start = (state.iterations % nb) * batch_size
+  sl = slice(start, start + batch_size)
+  pert = state.perturbations[sl]
+  if state.iterations < nb:
+    nf, nr, npert = batch_features, batch_rewards, pert
+  else:
+    prev_f, prev_r = state.features[sl], state.rewards[sl]
+    improve = batch_rewards > prev_r
+    nf = np.where(improve[:, None], batch_features, prev_f)
+    nr = np.where(improve, batch_rewards, prev_r)
+    npert = np.where(improve, pert, pert * cfg.penalize_factor)
+    trim = (npert < cfg.perturbation_lower_bound) & (nr != new_best)
+    nf = np.where(trim[:, None], random_features, nf)
+    npert = np.where(trim, cfg.perturbation, npert)
+    nr = np.where(trim, -np.inf, nr)
+  out = state.copy()
+  out.iterations = state.iterations + 1
+  out.features[sl] = nf
+  out.rewards[sl] = nr
+  out.perturbations[sl] = npert
+  out.best_reward = new_best
+  return out
+
+
+# ----------------------------------------------------------------------------
+# Driver (vectorized_base.py:324-587)
+# ----------------------------------------------------------------------------
+def update_best(best_f, best_r, best_id, new_f, new_r, new_id, count):
+  """Top-`count` of (new U best); ties -> smaller evaluation id (earlier)."""
+  f = np.concatenate([new_f, best_f], axis=0)
+  r = np.concatenate([new_r, best_r], axis=0)
+  ids = np.concatenate([new_id, best_id], axis=0)
+  rr = np.where(np.isnan(r), -np.inf, r)
+  order = np.lexsort((ids, -rr))[:count]
+  return f[order], r[order], ids[order]
+
+
+def run_eagle_optimizer(
+    score_fn: Callable[[np.ndarray], np.ndarray], *, dim: int, pool_size: int, batch_size: int,
+    max_evaluations: int, count: int, seed: int, cfg: EagleConfig = EagleConfig(),
+    prior_features: Optional[np.ndarray] = None,
+):
+  """VectorizedOptimizer.__call__ with the eagle strategy and Philox draws."""
+  prior_rewards = None
+  if prior_features is not None and prior_features.shape[0] > 0:
+    prior_rewards = score_fn(prior_features)
+  random_pool = philox_uniform(seed, STREAM_INIT_POOL, 0, pool_size * dim).reshape(pool_size, dim)
+  state = init_state(random_pool, cfg, prior_features, prior_rewards)
+  best_f = np.zeros((count, dim))
+  best_r = np.full(count, -np.inf)
+  best_id = np.full(count, np.iinfo(np.int64).max, dtype=np.int64)
+  n_steps = (max_evaluations - 1) // batch_size + 1
+  for t in range(n_steps):
+    signs = philox_signs(seed, t, batch_size * dim).reshape(batch_size, dim)
+    x = suggest(state, batch_size, signs, cfg)
+    r = score_fn(x)
+    rnd = philox_uniform(seed, STREAM_TRIM, t, batch_size * dim).reshape(batch_size, dim)
+    state = update(state, batch_size, x, r, rnd, cfg)
+    ids = np.arange(batch_size, dtype=np.int64) + t * batch_size
+    best_f, best_r, best_id = update_best(best_f, best_r, best_id, x, r, ids, count)
+  return best_f, best_r, state
+
+
+def run_random_optimizer(score_fn, *, dim: int, num_candidates: int, count: int, seed: int):
+  """RandomVectorizedStrategy with batch = max_evaluations = M (SURVEY 8a note)."""
+  xs = philox_uniform(seed, STREAM_RANDOM_POOL, 0, num_candidates * dim).reshape(num_candidates, dim)
+  r = score_fn(xs)
+  rr = np.where(np.isnan(r), -np.inf, r)
+  order = np.lexsort((np.arange(num_candidates), -rr))[:count]
+  return xs[order], r[order], order

@@ -1,0 +1,139 @@
+"""Validates the oracle's GP arithmetic independently of the reference:
+scipy.stats mvn for the NLL, 50-digit mpmath for kernel/Cholesky/posterior,
+central finite differences for the gradient, analytic identities."""
+import math
+
+import mpmath as mp
+import numpy as np
+import pytest
+import scipy.stats as st
+
+from oracle import gp_oracle as go
+
+
+def _problem(n=12, d=3, seed=0, noise=1e-3):
+  rng = np.random.default_rng(seed)
+  x = rng.uniform(size=(n, d))
+  y = -np.sum((x - 0.3) ** 2, axis=1) + 0.05 * rng.normal(size=n)
+  p = go.GPParams(1.3, 0.5 * (1 + np.arange(d) / d), noise)
+  return x, y, p
+
+
+def test_nll_matches_scipy_mvn():
+  x, y, p = _problem(20, 4)
+  ky = go.kernel_matrix(p, x)
+  want = -st.multivariate_normal(mean=np.zeros(20), cov=ky).logpdf(y)
+  assert abs(go.nll(p, x, y) - want) < 1e-9
+
+
+def test_kernel_chol_posterior_vs_mpmath():
+  mp.mp.dps = 50
+  x, y, p = _problem(8, 3, seed=1, noise=1e-3)
+  xs = np.random.default_rng(5).uniform(size=(3, 3))
+  n = 8
+  ls2 = [mp.mpf(v) for v in p.continuous_length_scale_squared]
+
+  def k(a, b):
+    d2 = sum((mp.mpf(float(a[i])) - mp.mpf(float(b[i]))) ** 2 / ls2[i] for i in range(3))
+    s = mp.sqrt(5 * d2)
+    return mp.mpf(p.signal_variance) * (1 + s + s * s / 3) * mp.exp(-s)
+
+  K = mp.matrix(n, n)
+  for i in range(n):
+    for j in range(n):
+      K[i, j] = k(x[i], x[j]) + (mp.mpf(p.observation_noise_variance) if i == j else 0)
+  L = mp.cholesky(K)
+  alpha = mp.lu_solve(K, mp.matrix([mp.mpf(float(v)) for v in y]))
+  pred = go.precompute_predictive(p, x, y)
+  got_k = go.kernel_matrix(p, x)
+  for i in range(n):
+    for j in range(n):
+      assert abs(got_k[i, j] - float(K[i, j])) < 1e-14
+      if j <= i:
+        assert abs(pred.chol[i, j] - float(L[i, j])) < 1e-12
+    assert abs(pred.alpha[i] - float(alpha[i])) < 1e-9 * max(1.0, abs(float(alpha[i])))
+  mu, sd = go.predict(pred, xs)
+  for m in range(3):
+    ks = mp.matrix([k(xs[m], x[i]) for i in range(n)])
+    mu_m = sum(ks[i] * alpha[i] for i in range(n))
+    sol = mp.lu_solve(K, ks)
+    var = mp.mpf(p.signal_variance) - sum(ks[i] * sol[i] for i in range(n)) + mp.mpf(p.observation_noise_variance)
+    assert abs(mu[m] - float(mu_m)) < 1e-11
+    assert abs(sd[m] - float(mp.sqrt(var))) < 1e-11
+
+
+@pytest.mark.parametrize('noise', [1e-3, 1e-6])
+def test_gradient_vs_finite_differences(noise):
+  x, y, p = _problem(15, 3, seed=2, noise=noise)
+  theta = p.to_vector()
+  val, grad = go.loss_and_grad(theta, x, y)
+  assert abs(val - go.loss(p, x, y)) < 1e-10
+  for i in range(theta.shape[0]):
+    h = 1e-6 * theta[i]
+    tp, tm = theta.copy(), theta.copy()
+    tp[i] += h; tm[i] -= h
+    fd = (go.loss_and_grad(tp, x, y)[0] - go.loss_and_grad(tm, x, y)[0]) / (2 * h)
+    assert abs(fd - grad[i]) < 1e-5 * max(1.0, abs(grad[i])), (i, fd, grad[i])
+
+
+def test_gradient_with_categorical_and_masks():
+  rng = np.random.default_rng(3)
+  n = 10
+  x = rng.uniform(size=(n, 3)); z = rng.integers(0, 3, size=(n, 2)); y = rng.normal(size=n)
+  valid = np.ones(n, bool); valid[-2:] = False
+  cvalid = np.array([True, True, False])
+  p = go.GPParams(0.8, [0.4, 0.9, 2.0], 1e-2, [0.7, 1.5])
+  theta = p.to_vector()
+  val, grad = go.loss_and_grad(theta, x, y, z, valid, cvalid, None)
+  for i in range(theta.shape[0]):
+    h = 1e-6 * theta[i]
+    tp, tm = theta.copy(), theta.copy()
+    tp[i] += h; tm[i] -= h
+    fd = (go.loss_and_grad(tp, x, y, z, valid, cvalid)[0] - go.loss_and_grad(tm, x, y, z, valid, cvalid)[0]) / (2 * h)
+    assert abs(fd - grad[i]) < 1e-5 * max(1.0, abs(grad[i])), (i, fd, grad[i])
+  # masking invariance (tuned_gp_models_test.py:171-245): loss independent of fill values
+  x2 = x.copy(); x2[:, 2] = 123.0; x2[-2:] = -7.0
+  y2 = y.copy(); y2[-2:] = 99.0
+  val2, grad2 = go.loss_and_grad(theta, x2, y2, z, valid, cvalid, None)
+  assert val2 == pytest.approx(val, abs=1e-12)
+  np.testing.assert_allclose(grad2, grad, atol=1e-12)
+  # padded rows add exactly nothing: compare with the unpadded problem
+  val3, _ = go.loss_and_grad(theta, x[:-2], y[:-2], z[:-2], None, cvalid, None)
+  assert val3 == pytest.approx(val, abs=1e-11)
+
+
+def test_posterior_interpolates_as_noise_vanishes():
+  x, y, p = _problem(10, 2, seed=4, noise=1e-10)
+  pred = go.precompute_predictive(p, x, y)
+  mu, sd = go.predict(pred, x)
+  np.testing.assert_allclose(mu, y, atol=1e-6)
+  assert np.all(sd < 1e-3)
+
+
+def test_retrying_cholesky():
+  a = np.array([[1.0, 1.0], [1.0, 1.0 - 1e-6]])  # indefinite by 1e-6
+  l, shift, it = go.retrying_cholesky(a)
+  assert it == 1 and shift == 1e-4 and np.all(np.isfinite(l))
+  a = np.array([[1.0, 2.0], [2.0, 1.0]])  # needs shift >= 1 -> 1e-4..1 = 5 tries
+  l, shift, it = go.retrying_cholesky(a)
+  assert it == 5 and shift == pytest.approx(1.0)
+  l, shift, it = go.retrying_cholesky(np.eye(3))
+  assert it == 0 and shift == 0.0
+
+
+def test_ard_fit_weak_pin_tuned_gp_models_dataset():
+  # tuned_gp_models_test.py:300-319 asserts min loss over restarts < -0.2 on its fixture;
+  # we use a same-shaped smooth synthetic problem and check that ARD improves on its inits.
+  rng = np.random.default_rng(0)
+  x = rng.uniform(size=(10, 6)); y = np.sin(3 * x[:, 0]) + 0.5 * x[:, 1]
+  inits = np.stack([go.log_uniform_init(rng, 6, 0) for _ in range(4)])
+  best, losses = go.ard_fit(x, y, init_thetas=inits)
+  init_losses = [go.loss_and_grad(t, x, y)[0] for t in inits]
+  assert losses.min() < min(init_losses)
+  lo, hi = go.param_bounds(6, 0)
+  assert np.all(best >= lo) and np.all(best <= hi)
+
+
+def test_top_k_ordering():
+  s = np.array([1.0, 3.0, 3.0, -np.inf, 2.0])
+  assert go.top_k(s, 3).tolist() == [1, 2, 4]
