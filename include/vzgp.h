@@ -1,0 +1,189 @@
+/*
+ * vzgp.h -- C ABI of libvzgp.so: the B200 (sm_100a) GP-Bandit hot path.
+ *
+ * The reference (google/vizier @ b0651861) has NO native/FFI layer: its
+ * GP-bandit arithmetic is reached through JAX/TFP Python calls.  Each entry
+ * point below replaces one of those Python call sites (cited as
+ * file:line under /root/reference); the Python host (vizier_b200/) binds them
+ * with ctypes, and INTEGRATION.md shows the stub a Vizier maintainer would
+ * add to vizier/_src/algorithms/designers/gp_bandit.py.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++/torch types.
+ *  - Every function returns int: 0 = ok, <0 = argument/CUDA error (message via
+ *    vzgp_last_error()), >0 = numeric event documented per function.  Nothing
+ *    throws.
+ *  - All matrices are row-major fp64.  "device" pointers are caller-owned CUDA
+ *    device memory (e.g. torch.Tensor.data_ptr()); "host" pointers are ordinary
+ *    host memory.  Small hyper-parameter vectors are always host memory.
+ *  - A handle owns workspaces and the fitted model (X, L, L^-1, alpha).  A
+ *    handle is bound to one device and one stream and must not be used from
+ *    two threads at once; different handles are independent (the Vizier
+ *    service runs different studies concurrently, vizier_service.py:297).
+ *  - Work is enqueued on the handle's stream.  Functions that return values
+ *    to HOST memory synchronise the stream before returning; the others do
+ *    not.
+ *  - Categorical features (int32, Hamming term of the kernel) are accepted by
+ *    every entry point through (Z, Dk); pass NULL / 0 when absent.
+ */
+#ifndef VZGP_H_
+#define VZGP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vzgp_handle vzgp_handle;
+
+/* Status codes (<0). */
+#define VZGP_OK 0
+#define VZGP_ERR_ARG (-1)
+#define VZGP_ERR_CUDA (-2)
+#define VZGP_ERR_STATE (-3)  /* e.g. scoring before fit */
+#define VZGP_ERR_UNSUPPORTED (-4)
+
+/* Hyper-parameters of VizierGaussianProcess (tuned_gp_models.py:161-271).
+ * All host memory. */
+typedef struct vzgp_params {
+  double signal_variance;             /* sigma_f^2  in [1e-3, 10]   */
+  double observation_noise_variance;  /* sigma_n^2  in [1e-10, 1]   */
+  const double* continuous_length_scale_squared;  /* [Dc], in [1e-2, 1e2] */
+  const double* categorical_length_scale_squared; /* [Dk] or NULL         */
+} vzgp_params;
+
+/* Acquisition + trust-region parameters (acquisitions.py:213-225, :152-174,
+ * :691-820).  trust_radius > 0.5 disables the region exactly like the
+ * reference (:160-166); pass use_trust_region = 0 for trust_region=None. */
+typedef struct vzgp_acq {
+  double ucb_coefficient;       /* 1.8 by default (acquisitions.py:217) */
+  int use_trust_region;
+  double trust_radius;          /* TrustRegion.trust_radius, computed by the host */
+  const uint8_t* tr_dim_mask;   /* host [Dc]: 1 = dimension takes part; NULL = all */
+} vzgp_acq;
+
+const char* vzgp_last_error(void);       /* thread-local message of the last failure */
+int vzgp_version(void);                  /* ABI version, currently 1 */
+int vzgp_device_count(void);
+
+/* device: CUDA ordinal.  stream: a cudaStream_t cast to void*, or NULL for a
+ * private non-blocking stream created (and destroyed) by the handle. */
+int vzgp_create(int device, void* stream, vzgp_handle** out);
+int vzgp_destroy(vzgp_handle* h);
+int vzgp_synchronize(vzgp_handle* h);
+/* Number of kernels this library has launched through `h` so far. */
+int64_t vzgp_launch_count(const vzgp_handle* h);
+
+/* ---- stage-wise entry points (parity tests call these one by one) -------- */
+
+/* K = K_theta(X,X) + diag_add*I, both triangles, K is [N x ldk] device.
+ * Rows/cols >= n_valid are replaced by identity (padded observations,
+ * stochastic_process_model.py:962-964).  Replaces the tfd.GaussianProcess
+ * covariance build at tuned_gp_models.py:307-313. */
+int vzgp_kernel_matrix(vzgp_handle* h, const double* X, const int32_t* Z, int N, int Dc, int Dk,
+                       int n_valid, const vzgp_params* p, double diag_add, double* K, int ldk);
+
+/* Ks[m, n] = k_theta(Xs[m], X[n]), Ks is [M x ldks] device.  Replaces the
+ * kernel.matrix(x*, X) inside prior.posterior_predictive,
+ * stochastic_process_model.py:830-832. */
+int vzgp_cross_kernel(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const double* X,
+                      const int32_t* Z, int N, int Dc, int Dk, const vzgp_params* p, double* Ks,
+                      int ldks);
+
+/* L = chol(A) with TFP retrying_cholesky semantics (tuned_gp_models.py:272-280):
+ * on failure add jitter0, 10*jitter0, ... to the diagonal, at most max_iters
+ * times.  A [N x lda] device (lower triangle read, not modified); L [N x ldl]
+ * device (upper triangle zeroed).  Returns the number of retries (>= 0); if
+ * the last attempt still fails returns max_iters+1 and L holds NaNs.
+ * *shift_out (host, optional) receives the diagonal shift finally used. */
+int vzgp_cholesky_retry(vzgp_handle* h, const double* A, int N, int lda, double jitter0,
+                        int max_iters, double* L, int ldl, double* shift_out);
+
+/* Linv = L^-1 for lower-triangular L (both [N x ld] device, upper zeroed). */
+int vzgp_tri_inverse(vzgp_handle* h, const double* L, int N, int ldl, double* Linv, int ldi);
+
+/* ---- model: fit, loss, score --------------------------------------------- */
+
+/* precompute_predictive (stochastic_process_model.py:968-997): builds K_y,
+ * factors it (retrying), forms L^-1 and alpha = K_y^-1 y, and keeps X, L,
+ * L^-1, alpha in the handle.  X [N x Dc], Z [N x Dk], y [N] device.  Returns
+ * the number of Cholesky retries (>=0). */
+int vzgp_fit(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
+             int Dk, int n_valid, const vzgp_params* p);
+
+/* Copy the fitted factor / alpha out (device destinations). */
+int vzgp_get_cholesky(vzgp_handle* h, double* L, int ldl);
+int vzgp_get_alpha(vzgp_handle* h, double* alpha);
+
+/* loss_with_aux + its gradient (stochastic_process_model.py:940-966, called
+ * through jaxopt at jaxopt_wrappers.py:139-152): loss = -log N(y;0,K_y) +
+ * regularisers; grad in the order [categorical ls2 (Dk), continuous ls2 (Dc),
+ * noise variance, signal variance] (jaxopt's sorted-key flattening).
+ * loss_out [1], grad_out [Dk+Dc+2] are HOST.  Returns Cholesky retries. */
+int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
+                  int Dk, int n_valid, const vzgp_params* p, double* loss_out, double* grad_out);
+
+/* BayesianScoringFunction.score / score_with_aux (acquisitions.py:177-207)
+ * on the fitted model: mu = K* alpha, var = sf2 - ||L^-1 K*^T||^2 + sn2
+ * (clamped at 0), score = UCB then trust region.  Xs [M x Dc], Zs [M x Dk]
+ * device.  score [M] device (required); mu, sigma, linf [M] device, each
+ * optional (NULL).  Asynchronous on the handle's stream.  The number of candidates
+ * whose variance round-off went negative and was clamped (the reference would
+ * yield NaN there) accumulates in the handle; read it with vzgp_clamped_count. */
+int vzgp_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+               double* score, double* mu, double* sigma, double* linf);
+
+/* Synchronises, returns the clamp counter accumulated since the last call and resets it. */
+int vzgp_clamped_count(vzgp_handle* h, int64_t* count_out);
+
+/* Same as vzgp_score but with HOST buffers: copies Xs to the device, scores,
+ * copies the requested outputs back (this is the call bench.py's e2e times). */
+int vzgp_score_host(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
+                    const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf);
+
+/* Top-`count` of score[0..M) (device), descending, ties -> lowest index, NaN
+ * treated as -inf (vectorized_base.py:580,598).  idx_out [count] int64 and
+ * val_out [count] are HOST. */
+int vzgp_topk(vzgp_handle* h, const double* score, int64_t M, int count, int64_t* idx_out,
+              double* val_out);
+
+/* ---- acquisition optimisers (device-resident loops) ---------------------- */
+
+/* EagleStrategyConfig (eagle_strategy.py:111-167), continuous features. */
+typedef struct vzgp_eagle_config {
+  double visibility, gravity, negative_gravity;
+  double perturbation, perturbation_lower_bound, penalize_factor;
+  double normalization_scale, prior_trials_pool_pct;
+  int pool_size;        /* P, multiple of batch_size */
+  int batch_size;       /* B */
+  int max_evaluations;  /* steps = (max_evaluations-1)/B + 1 */
+} vzgp_eagle_config;
+
+/* VectorizedOptimizer.__call__ with VectorizedEagleStrategy
+ * (vectorized_base.py:324-542; eagle_strategy.py:527-1247) scoring against
+ * the fitted model.  prior [n_prior x Dc] device (may be NULL/0) are the
+ * observed trials in creation order.  best_x [count x Dc], best_score [count]
+ * are HOST outputs, best first.  Randomness: Philox4x32-10 keyed by `seed`. */
+int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
+                   const double* prior, int n_prior, int count, uint64_t seed, double* best_x,
+                   double* best_score);
+
+/* RandomVectorizedStrategy with batch = max_evaluations = M
+ * (random_vectorized_optimizer.py:32-123): generates M uniform candidates on
+ * the device (Philox), scores them, returns the top `count` (HOST outputs).
+ * index_base offsets the Philox element counter so ranks can generate
+ * disjoint shards of one global pool: candidate g = index_base + m. */
+int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp_acq* acq,
+                       int count, uint64_t seed, double* best_x, double* best_score,
+                       int64_t* best_index);
+
+/* Fill X [M x Dc] (device) with the same Philox uniforms vzgp_random_search
+ * uses (stream STREAM_RANDOM_POOL), for parity tests and the benchmark. */
+int vzgp_random_pool(vzgp_handle* h, int64_t M, int Dc, int64_t index_base, uint64_t seed,
+                     double* X);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VZGP_H_ */

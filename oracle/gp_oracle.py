@@ -138,11 +138,14 @@ def scaled_sq_dist(
   ls2 = np.asarray(ls2, np.float64)
   d2 = np.zeros((x1.shape[0], x2.shape[0]), np.float64)
   dc = x1.shape[1]
+  diff = np.empty_like(d2)
   for d in range(dc):
     if cont_dim_valid is not None and not cont_dim_valid[d]:
       continue
-    diff = x1[:, d][:, None] - x2[:, d][None, :]
-    d2 += diff * diff / ls2[d]
+    np.subtract(x1[:, d][:, None], x2[:, d][None, :], out=diff)
+    np.multiply(diff, diff, out=diff)
+    diff /= ls2[d]
+    d2 += diff
   if z1 is not None and z1.shape[1] > 0:
     for k in range(z1.shape[1]):
       if cat_dim_valid is not None and not cat_dim_valid[k]:
@@ -153,8 +156,16 @@ def scaled_sq_dist(
 
 def matern52_from_d2(d2: np.ndarray, signal_variance: float) -> np.ndarray:
   """k = sf2*(1+s+s^2/3)*exp(-s), s=sqrt(5*d2); TFP form exp(log1p(s+s^2/3)-s)."""
-  s = SQRT5 * np.sqrt(d2)
-  return signal_variance * np.exp(np.log1p(s + s * s / 3.0) - s)
+  s = np.sqrt(d2)
+  s *= SQRT5
+  poly = s * s
+  poly /= 3.0
+  poly += s
+  np.log1p(poly, out=poly)
+  poly -= s
+  np.exp(poly, out=poly)
+  poly *= signal_variance
+  return poly
 
 
 def kernel(
@@ -446,11 +457,20 @@ def min_linf_distance(
   trusted = np.asarray(trusted, np.float64)
   if trusted.size == 0 or xs.shape[-1] == 0:
     return -np.inf * np.ones(xs.shape[:-1])
-  dist = np.abs(trusted - xs[..., None, :])
-  dist = np.where(np.asarray(dim_mask, bool), dist, 0.0)
+  # Same arithmetic as the reference's broadcasted (..., N, D) array, evaluated one feature
+  # dimension at a time so the CPU baseline does not pay for a 3-D temporary.
+  flat = xs.reshape(-1, xs.shape[-1])
+  linf = np.zeros((flat.shape[0], trusted.shape[0]), np.float64)
+  tmp = np.empty_like(linf)
+  for d in range(flat.shape[1]):
+    if not dim_mask[d]:
+      continue
+    np.subtract(flat[:, d][:, None], trusted[:, d][None, :], out=tmp)
+    np.abs(tmp, out=tmp)
+    np.maximum(linf, tmp, out=linf)
   if row_valid is not None:
-    dist = np.where(~np.asarray(row_valid, bool)[:, None], np.inf, dist)
-  return np.min(np.max(dist, axis=-1), axis=-1)
+    linf[:, ~np.asarray(row_valid, bool)] = np.inf
+  return np.min(linf, axis=-1).reshape(xs.shape[:-1])
 
 
 def apply_trust_region(acq: np.ndarray, distance: np.ndarray, radius: float) -> np.ndarray:

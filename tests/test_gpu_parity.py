@@ -1,0 +1,260 @@
+"""GPU parity: every C-ABI entry point against the oracle on the same seeded inputs.
+
+Tolerances (fp64 path): 1e-10 absolute on well-conditioned hyper-parameters
+(north-star bar).  The oracle is a restatement validated by mpmath/scipy, not a
+live TFP run ("parity unpinned" at the TFP boundary, see oracle/gp_oracle.py).
+Integer/index results (top-k indices, Philox draws, retry counts) are bit-exact.
+"""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import eagle_oracle as eo  # noqa: E402
+from oracle import gp_oracle as go  # noqa: E402
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope='module')
+def dev():
+  if not torch.cuda.is_available():
+    pytest.skip('no CUDA device')
+  from vizier_b200 import gp
+  d = gp.DeviceGP(0)
+  yield d
+  d.close()
+
+
+def _gp():
+  from vizier_b200 import gp
+  return gp
+
+
+def _problem(n, d, seed=0, dk=0):
+  rng = np.random.default_rng(seed)
+  x = rng.uniform(size=(n, d))
+  y = -np.sum((x - 0.3) ** 2, axis=1) + 0.05 * rng.normal(size=n)
+  z = rng.integers(0, 4, size=(n, dk)).astype(np.int32) if dk else None
+  return x, y, z
+
+
+def _params(d, dk=0, sf2=1.0, sn2=1e-3, ls=None):
+  ls2 = 0.5 * (1 + np.arange(d) / d) if ls is None else np.full(d, ls)
+  lk = np.linspace(0.6, 1.4, dk) if dk else None
+  return go.GPParams(sf2, ls2, sn2, lk), _gp().GPHyperParams(sf2, ls2, sn2, lk)
+
+
+@pytest.mark.parametrize('n,d,dk', [(1, 1, 0), (50, 4, 0), (100, 5, 2), (200, 20, 0), (64, 3, 0)])
+def test_kernel_matrix(dev, n, d, dk):
+  x, _, z = _problem(n, d, 1, dk)
+  po, pg = _params(d, dk)
+  nv = max(1, n - 3)
+  want = go.kernel_matrix(po, x, z, row_valid=np.arange(n) < nv)
+  got = dev.kernel_matrix(x, pg, z=z, n_valid=nv, diag_add=po.observation_noise_variance).cpu().numpy()
+  np.testing.assert_allclose(got, want, atol=1e-13, rtol=0)
+  np.testing.assert_array_equal(got, got.T)
+
+
+def test_cross_kernel(dev):
+  x, _, z = _problem(130, 7, 2, 3)
+  xs, _, zs = _problem(257, 7, 3, 3)
+  po, pg = _params(7, 3)
+  want = go.kernel(po, xs, x, zs, z)
+  got = dev.cross_kernel(xs, x, pg, zs=zs, z=z).cpu().numpy()
+  np.testing.assert_allclose(got, want, atol=1e-13, rtol=0)
+
+
+@pytest.mark.parametrize('n', [1, 17, 64, 65, 200, 448])
+def test_cholesky_and_inverse(dev, n):
+  x, _, _ = _problem(n, 4, 4)
+  po, _ = _params(4)
+  a = go.kernel_matrix(po, x)
+  l, shift, retries = dev.cholesky_retry(a)
+  assert retries == 0 and shift == 0.0
+  want = np.linalg.cholesky(a)
+  np.testing.assert_allclose(l.cpu().numpy(), want, atol=1e-12, rtol=0)
+  linv = dev.tri_inverse(want).cpu().numpy()
+  np.testing.assert_allclose(linv, sla.solve_triangular(want, np.eye(n), lower=True), atol=1e-9, rtol=1e-9)
+  assert np.all(np.triu(linv, 1) == 0)
+
+
+def test_cholesky_retry_semantics(dev):
+  # indefinite by 1e-6 -> one retry with shift 1e-4 (tuned_gp_models.py:272-280 semantics)
+  a = np.array([[1.0, 1.0], [1.0, 1.0 - 1e-6]])
+  l, shift, retries = dev.cholesky_retry(a)
+  lo, so, ro = go.retrying_cholesky(a)
+  assert retries == ro == 1 and shift == so == 1e-4
+  np.testing.assert_allclose(l.cpu().numpy(), lo, atol=1e-14)
+  a = np.array([[1.0, 2.0], [2.0, 1.0]])
+  l, shift, retries = dev.cholesky_retry(a)
+  assert retries == 5 and shift == pytest.approx(1.0)
+  a = np.array([[1.0, 5.0], [5.0, 1.0]])  # never succeeds within 5 retries
+  l, shift, retries = dev.cholesky_retry(a)
+  assert retries == 6 and np.isnan(l.cpu().numpy()).any()
+
+
+@pytest.mark.parametrize('n,d,dk,nv', [(50, 4, 0, 50), (200, 6, 0, 200), (150, 5, 2, 140), (333, 20, 0, 333)])
+def test_fit_factor_and_alpha(dev, n, d, dk, nv):
+  x, y, z = _problem(n, d, 5, dk)
+  po, pg = _params(d, dk)
+  valid = np.arange(n) < nv
+  pred = go.precompute_predictive(po, x, y, z, row_valid=valid)
+  retries = dev.fit(x, y, pg, z=z, n_valid=nv)
+  assert retries == 0
+  np.testing.assert_allclose(dev.cholesky().cpu().numpy(), pred.chol, atol=1e-11, rtol=0)
+  alpha = dev.alpha().cpu().numpy()
+  np.testing.assert_allclose(alpha, pred.alpha, atol=1e-8 * np.max(np.abs(pred.alpha)), rtol=0)
+  # residual of the solve is at round-off level (the property that matters for mu)
+  ky = go.kernel_matrix(po, x, z, row_valid=valid)
+  yv = np.where(valid, y, 0.0)
+  assert np.max(np.abs(ky @ alpha - yv)) < 1e-11
+
+
+@pytest.mark.parametrize('n,d,dk,m,tr', [(20, 3, 0, 100, True), (50, 4, 0, 513, True), (96, 5, 2, 300, True),
+                                        (300, 20, 0, 1000, True), (300, 20, 0, 1000, False)])
+def test_score_with_aux(dev, n, d, dk, m, tr):
+  x, y, z = _problem(n, d, 6, dk)
+  xs, _, zs = _problem(m, d, 7, dk)
+  xs[:5] = x[:5]  # include observed points (sigma ~ sqrt(2*sn2), distance 0)
+  if zs is not None:
+    zs[:5] = z[:5]
+  po, pg = _params(d, dk)
+  pred = go.precompute_predictive(po, x, y, z)
+  mask = np.ones(d, bool)
+  if d > 2:
+    mask[1] = False
+  want, aux = go.score_with_aux(pred, xs, zs, tr_dim_mask=mask, categorical_dof=dk, use_trust_region=tr)
+  radius = go.trust_radius(n, int(mask.sum()), dk)
+  dev.fit(x, y, pg, z=z)
+  acq = _gp().Acquisition(1.8, tr, radius, mask)
+  out = dev.score(xs, acq, zs=zs, with_aux=True)
+  dev.synchronize()
+  mu_w, sd_w = go.predict(pred, xs, zs)
+  np.testing.assert_allclose(out['mean'].cpu().numpy(), mu_w, atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['stddev'].cpu().numpy(), sd_w, atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['score'].cpu().numpy(), want, atol=TOL, rtol=0)
+  dist = go.min_linf_distance(xs, x, mask)
+  np.testing.assert_array_equal(out['linf_distance'].cpu().numpy(), dist)  # max/min of exact differences
+  if tr and radius <= 0.5:
+    assert np.any(want < -1e3)  # the trust region really was active in this case
+  # score-only path (no aux outputs) gives bit-identical scores
+  out2 = dev.score(xs, acq, zs=zs, with_aux=False)
+  dev.synchronize()
+  np.testing.assert_array_equal(out2['score'].cpu().numpy(), out['score'].cpu().numpy())
+
+
+def test_score_hard_conditioning_scaled_tolerance(dev):
+  # sn2=1e-8, ls2=0.05: cond(K_y) ~ 1e10; both sides lose digits ~ eps*cond(L)*|v|.
+  n, d, m = 200, 6, 400
+  x, y, _ = _problem(n, d, 8)
+  xs, _, _ = _problem(m, d, 9)
+  po, pg = _params(d, sn2=1e-8, ls=0.05)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  out = dev.score(xs, _gp().Acquisition(1.8, False, 1.0), with_aux=True)
+  dev.synchronize()
+  mu_w, sd_w = go.predict(pred, xs)
+  np.testing.assert_allclose(out['mean'].cpu().numpy(), mu_w, atol=1e-7, rtol=0)
+  np.testing.assert_allclose(out['stddev'].cpu().numpy(), sd_w, atol=1e-7, rtol=0)
+
+
+@pytest.mark.parametrize('n,d,dk,nv', [(40, 3, 0, 40), (130, 6, 2, 120), (256, 20, 0, 256)])
+def test_nll_grad(dev, n, d, dk, nv):
+  x, y, z = _problem(n, d, 10, dk)
+  po, pg = _params(d, dk, sf2=0.7, sn2=2e-3)
+  valid = np.arange(n) < nv
+  want_l, want_g = go.loss_and_grad(po.to_vector(), x, y, z, valid)
+  xt = torch.from_numpy(x).cuda(); yt = torch.from_numpy(y).cuda()
+  zt = torch.from_numpy(z).cuda() if z is not None else None
+  loss, grad, retries = dev.loss_and_grad(xt, yt, pg, z=zt, n_valid=nv)
+  assert retries == 0
+  assert abs(loss - want_l) < 1e-9 * max(1.0, abs(want_l))
+  np.testing.assert_allclose(grad, want_g, atol=1e-8 * max(1.0, np.max(np.abs(want_g))), rtol=0)
+
+
+def test_topk_ties_nan_and_order(dev):
+  rng = np.random.default_rng(11)
+  s = rng.normal(size=5000)
+  s[[10, 4000, 77]] = s.max() + 1.0  # three-way tie for the top
+  s[5] = np.nan
+  s[6] = -np.inf
+  idx, val = dev.topk(torch.from_numpy(s).cuda(), 7)
+  want = go.top_k(np.where(np.isnan(s), -np.inf, s), 7)
+  np.testing.assert_array_equal(idx, want)
+  np.testing.assert_array_equal(val, s[want])
+  idx, _ = dev.topk(torch.from_numpy(np.array([3.0, 1.0])).cuda(), 2)
+  np.testing.assert_array_equal(idx, [0, 1])
+
+
+def test_random_pool_matches_philox_oracle(dev):
+  got = dev.random_pool(1000, 7, seed=0x1234ABCD5678, index_base=5).cpu().numpy()
+  want = eo.philox_uniform(0x1234ABCD5678, eo.STREAM_RANDOM_POOL, 0, 1005 * 7).reshape(1005, 7)[5:]
+  np.testing.assert_array_equal(got, want)
+
+
+def test_random_search_matches_oracle(dev):
+  n, d, m = 120, 6, 5000
+  x, y, _ = _problem(n, d, 12)
+  po, pg = _params(d)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  radius = go.trust_radius(n, d, 0)
+  bx, bs, bi = dev.random_search(m, _gp().Acquisition(1.8, True, radius), count=3, seed=99)
+  wx, ws, wi = eo.run_random_optimizer(lambda q: go.score_with_aux(pred, q)[0], dim=d, num_candidates=m, count=3, seed=99)
+  np.testing.assert_array_equal(bi, wi)
+  np.testing.assert_array_equal(bx, wx)
+  np.testing.assert_allclose(bs, ws, atol=TOL)
+
+
+@pytest.mark.parametrize('n,d,pool,batch,steps', [(30, 4, 25, 25, 6), (60, 5, 20, 5, 14), (130, 3, 50, 25, 7)])
+def test_eagle_run_matches_oracle(dev, n, d, pool, batch, steps):
+  x, y, _ = _problem(n, d, 13)
+  po, pg = _params(d)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  radius = go.trust_radius(n, d, 0)
+  score_fn = lambda q: go.score_with_aux(pred, q)[0]
+  cfg_o = eo.EagleConfig()
+  wx, wr, st = eo.run_eagle_optimizer(score_fn, dim=d, pool_size=pool, batch_size=batch,
+                                      max_evaluations=steps * batch, count=3, seed=7, cfg=cfg_o, prior_features=x)
+  from vizier_b200 import _lib
+  cfg = _lib.EagleConfig(cfg_o.visibility, cfg_o.gravity, cfg_o.negative_gravity, cfg_o.perturbation,
+                         cfg_o.perturbation_lower_bound, cfg_o.penalize_factor, cfg_o.normalization_scale,
+                         cfg_o.prior_trials_pool_pct, pool, batch, steps * batch)
+  bx, br = dev.eagle_run(cfg, _gp().Acquisition(1.8, True, radius), count=3, seed=7, prior=x)
+  np.testing.assert_allclose(br, wr, atol=1e-9)
+  np.testing.assert_allclose(bx, wx, atol=1e-9)
+
+
+def test_c2_full_size_properties(dev):
+  """BASELINE C2 (N=1000, D=20, M=100k): spot parity on a sample + size-independent properties."""
+  n, d, m = 1000, 20, 100_000
+  x, y, _ = _problem(n, d, 0)
+  po, pg = _params(d)
+  dev.fit(x, y, pg)
+  xs = dev.random_pool(m, d, seed=2024)
+  acq = _gp().Acquisition(1.8, True, go.trust_radius(n, d, 0))
+  out = dev.score(xs, acq, with_aux=True)
+  dev.synchronize()
+  sc = out['score'].cpu().numpy()
+  assert np.all(np.isfinite(sc)) and dev.clamped_count() == 0
+  # (1) sample parity against the oracle
+  pred = go.precompute_predictive(po, x, y)
+  sel = np.random.default_rng(1).choice(m, 512, replace=False)
+  want, _ = go.score_with_aux(pred, xs[torch.from_numpy(sel).cuda()].cpu().numpy())
+  np.testing.assert_allclose(sc[sel], want, atol=TOL, rtol=0)
+  # (2) position independence: the same candidates scored alone give bit-identical values
+  sub = xs[torch.from_numpy(sel).cuda()].contiguous()
+  out2 = dev.score(sub, acq)
+  dev.synchronize()
+  np.testing.assert_array_equal(out2['score'].cpu().numpy(), sc[sel])
+  # (3) posterior sanity: 0 <= var <= sf2 + sn2, and UCB identity
+  sd = out['stddev'].cpu().numpy(); mu = out['mean'].cpu().numpy()
+  assert sd.min() >= 0 and sd.max() <= np.sqrt(1.0 + 1e-3) + 1e-12
+  np.testing.assert_allclose(sc, mu + 1.8 * sd, atol=1e-12)
+  # (4) top-k agrees with a host sort
+  idx, val = dev.topk(out['score'], 5)
+  np.testing.assert_array_equal(idx, go.top_k(sc, 5))

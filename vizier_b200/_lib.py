@@ -1,0 +1,132 @@
+"""ctypes binding of libvzgp.so (the C ABI in include/vzgp.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or a call
+fails, an exception is raised.  PyTorch is used only as a device-memory handle
+(`tensor.data_ptr()`), never for arithmetic on this path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_lib', 'libvzgp.so')
+
+VZGP_ERR_ARG = -1
+VZGP_ERR_CUDA = -2
+VZGP_ERR_STATE = -3
+VZGP_ERR_UNSUPPORTED = -4
+
+
+class VzgpError(RuntimeError):
+  """A libvzgp call returned a negative status."""
+
+  def __init__(self, fn: str, status: int, message: str):
+    super().__init__(f'{fn} failed with status {status}: {message}')
+    self.status = status
+
+
+class Params(C.Structure):
+  _fields_ = [
+      ('signal_variance', C.c_double),
+      ('observation_noise_variance', C.c_double),
+      ('continuous_length_scale_squared', C.POINTER(C.c_double)),
+      ('categorical_length_scale_squared', C.POINTER(C.c_double)),
+  ]
+
+
+class Acq(C.Structure):
+  _fields_ = [
+      ('ucb_coefficient', C.c_double),
+      ('use_trust_region', C.c_int),
+      ('trust_radius', C.c_double),
+      ('tr_dim_mask', C.POINTER(C.c_uint8)),
+  ]
+
+
+class EagleConfig(C.Structure):
+  _fields_ = [
+      ('visibility', C.c_double),
+      ('gravity', C.c_double),
+      ('negative_gravity', C.c_double),
+      ('perturbation', C.c_double),
+      ('perturbation_lower_bound', C.c_double),
+      ('penalize_factor', C.c_double),
+      ('normalization_scale', C.c_double),
+      ('prior_trials_pool_pct', C.c_double),
+      ('pool_size', C.c_int),
+      ('batch_size', C.c_int),
+      ('max_evaluations', C.c_int),
+  ]
+
+
+_vp = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_u64 = C.c_uint64
+_d = C.c_double
+_pd = C.POINTER(C.c_double)
+_pi64 = C.POINTER(C.c_int64)
+_pP = C.POINTER(Params)
+_pA = C.POINTER(Acq)
+_pE = C.POINTER(EagleConfig)
+
+# name -> (restype, argtypes).  Must list every symbol declared in include/vzgp.h
+# (tests/test_abi.py checks this against the header).
+SIGNATURES = {
+    'vzgp_last_error': (C.c_char_p, []),
+    'vzgp_version': (_i, []),
+    'vzgp_device_count': (_i, []),
+    'vzgp_create': (_i, [_i, _vp, C.POINTER(_vp)]),
+    'vzgp_destroy': (_i, [_vp]),
+    'vzgp_synchronize': (_i, [_vp]),
+    'vzgp_launch_count': (_i64, [_vp]),
+    'vzgp_kernel_matrix': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _pP, _d, _vp, _i]),
+    'vzgp_cross_kernel': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _pP, _vp, _i]),
+    'vzgp_cholesky_retry': (_i, [_vp, _vp, _i, _i, _d, _i, _vp, _i, _pd]),
+    'vzgp_tri_inverse': (_i, [_vp, _vp, _i, _i, _vp, _i]),
+    'vzgp_fit': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _pP]),
+    'vzgp_get_cholesky': (_i, [_vp, _vp, _i]),
+    'vzgp_get_alpha': (_i, [_vp, _vp]),
+    'vzgp_nll_grad': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _pP, _pd, _pd]),
+    'vzgp_score': (_i, [_vp, _vp, _vp, _i, _pA, _vp, _vp, _vp, _vp]),
+    'vzgp_clamped_count': (_i, [_vp, _pi64]),
+    'vzgp_score_host': (_i, [_vp, _vp, _vp, _i, _pA, _vp, _vp, _vp, _vp]),
+    'vzgp_topk': (_i, [_vp, _vp, _i64, _i, _pi64, _pd]),
+    'vzgp_eagle_run': (_i, [_vp, _pE, _pA, _vp, _i, _i, _u64, _pd, _pd]),
+    'vzgp_random_search': (_i, [_vp, _i64, _i64, _pA, _i, _u64, _pd, _pd, _pi64]),
+    'vzgp_random_pool': (_i, [_vp, _i64, _i, _i64, _u64, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> C.CDLL:
+  """Loads libvzgp.so (once).  Raises ImportError loudly if it is not built."""
+  global _lib
+  with _lock:
+    if _lib is not None:
+      return _lib
+    if not os.path.exists(LIB_PATH):
+      raise ImportError(
+          f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; '
+          'g.build()"` (or `make -C vizier_b200/csrc`).  vizier_b200 has no CPU fallback.'
+      )
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+      fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+      fn.restype = res
+      fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(fn: str, status: int) -> int:
+  """Raises VzgpError for negative statuses; returns non-negative ones."""
+  if status < 0:
+    msg = load().vzgp_last_error()
+    raise VzgpError(fn, status, msg.decode('utf-8', 'replace') if msg else '')
+  return status

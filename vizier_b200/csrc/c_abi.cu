@@ -1,0 +1,515 @@
+// extern "C" surface of libvzgp.so (see include/vzgp.h for the contract of each entry point).
+#include <climits>
+#include <cstdarg>
+#include <cstring>
+
+#include "launchers.h"
+
+namespace vzgp {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+
+// Layout of handle->small (device, 64 KiB).
+constexpr size_t kSmallBytes = 65536;
+constexpr size_t kOffClamp = 0;      // int
+constexpr size_t kOffFlag = 8;       // int
+constexpr size_t kOffLogdet = 64;    // double[2]
+constexpr size_t kOffGrad = 128;     // double[<=98]
+constexpr size_t kOffTopIdx = 1024;  // long long[256]
+constexpr size_t kOffTopVal = 3072;  // double[256]
+constexpr size_t kOffPartial = 8192; // ArgMax[<=2048]
+constexpr int kMaxTopk = 256;
+
+struct Guard {
+  int prev = -1;
+  explicit Guard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~Guard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+static int ensure_model_buffers(vzgp_handle* h, int np, int dc, int dk) {
+  VZ_TRY(h->X.reserve(sizeof(double) * (size_t)np * (dc > 0 ? dc : 1)));
+  VZ_TRY(h->Z.reserve(sizeof(int32_t) * (size_t)np * (dk > 0 ? dk : 1)));
+  VZ_TRY(h->L.reserve(sizeof(double) * (size_t)np * np));
+  VZ_TRY(h->Linv.reserve(sizeof(double) * (size_t)np * np));
+  VZ_TRY(h->Kws.reserve(sizeof(double) * (size_t)np * np));
+  VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)np * np));
+  VZ_TRY(h->alpha.reserve(sizeof(double) * (size_t)np));
+  VZ_TRY(h->ypad.reserve(sizeof(double) * (size_t)np * 4));  // y, w, r, tmp
+  return 0;
+}
+
+// Factor A (np x np device, lower read) into h-independent buffers with retry semantics.
+// L, Linv: [np x np].  Returns retries, or max_iters+1 on final failure, or <0.
+static int cholesky_retry_padded(vzgp_handle* h, const double* A, int lda, int n_src, int np,
+                                 double jitter0, int max_iters, double* L, double* Linv,
+                                 double* shift_out) {
+  int* flag = reinterpret_cast<int*>(h->small.as<char>() + kOffFlag);
+  double shift = 0.0;
+  int attempt = 0;
+  for (;;) {
+    VZ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+    VZ_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)np * np, h->stream));
+    VZ_TRY(launch_copy_lower_shift(h, A, lda, n_src, np, shift, L, np));
+    VZ_TRY(potrf_blocked(h, L, np, Linv, np, np, flag));
+    int bad = 0;
+    VZ_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    VZ_CUDA(cudaStreamSynchronize(h->stream));
+    if (!bad) break;
+    if (attempt >= max_iters) {
+      if (shift_out) *shift_out = shift;
+      return max_iters + 1;
+    }
+    shift = (shift == 0.0) ? jitter0 : shift * 10.0;
+    ++attempt;
+  }
+  if (shift_out) *shift_out = shift;
+  return attempt;
+}
+
+// Shared front half of fit / nll_grad: pads inputs, builds K_y, factors, inverts, solves alpha.
+// On return: h->X/Z padded copies, Kws = K_y (unshifted), L, Linv, alpha valid; ypad[0..np) = y,
+// ypad[np..2np) = w = Linv y.
+static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N,
+                      int dc, int dk, int n_valid, const vzgp_params* p, double* shift_used) {
+  VZ_ARG(h != nullptr, "handle");
+  VZ_ARG(N >= 1, "N >= 1");
+  VZ_ARG(n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
+  VZ_ARG(X != nullptr || dc == 0, "X");
+  VZ_ARG(Z != nullptr || dk == 0, "Z");
+  VZ_ARG(y != nullptr, "y");
+  KernelParams kp;
+  VZ_TRY(fill_kernel_params(p, dc, dk, &kp));
+  const int np = round_up(N, kBlk);
+  VZ_TRY(ensure_model_buffers(h, np, dc, dk));
+  h->fitted = false;
+  h->n = N; h->np = np; h->dc = dc; h->dk = dk; h->n_valid = n_valid;
+  h->kp = kp; h->sn2 = p->observation_noise_variance;
+  double* yp = h->ypad.as<double>();
+  double* w = yp + np;
+  double* r = yp + 2 * np;
+  double* tmp = yp + 3 * np;
+  if (dc > 0) VZ_TRY(launch_pad_rows(h, X, N, dc, np, h->X.as<double>()));
+  if (dk > 0) VZ_TRY(launch_pad_rows_i32(h, Z, N, dk, np, h->Z.as<int32_t>()));
+  VZ_TRY(launch_pad_vector(h, y, N, n_valid, np, yp));
+  VZ_TRY(launch_kernel_matrix(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, h->sn2,
+                              h->Kws.as<double>(), np));
+  double shift = 0.0;
+  int retries = cholesky_retry_padded(h, h->Kws.as<double>(), np, np, np, 1e-4, 5,
+                                      h->L.as<double>(), h->Linv.as<double>(), &shift);
+  if (retries < 0) return retries;
+  if (shift_used) *shift_used = shift;
+  VZ_TRY(trtri_doubling(h, h->L.as<double>(), np, h->Linv.as<double>(), np, h->Tws.as<double>(), np, np));
+  // alpha = Linv^T (Linv y), then one step of iterative refinement against K_y (+shift).
+  double* alpha = h->alpha.as<double>();
+  VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
+  VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, w, alpha));
+  VZ_TRY(launch_residual(h, h->Kws.as<double>(), np, np, yp, alpha, r));
+  if (shift != 0.0) VZ_TRY(launch_axpy(h, np, -shift, alpha, r));
+  VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, r, tmp, 1));
+  VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, tmp, r));
+  VZ_TRY(launch_axpy(h, np, 1.0, r, alpha));
+  return retries;
+}
+
+}  // namespace vzgp
+
+using namespace vzgp;
+
+extern "C" {
+
+const char* vzgp_last_error(void) { return g_err; }
+int vzgp_version(void) { return 1; }
+
+int vzgp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int vzgp_create(int device, void* stream, vzgp_handle** out) {
+  VZ_ARG(out != nullptr, "out");
+  *out = nullptr;
+  int n = 0;
+  VZ_CUDA(cudaGetDeviceCount(&n));
+  VZ_ARG(device >= 0 && device < n, "device ordinal");
+  Guard g(device);
+  vzgp_handle* h = new vzgp_handle();
+  h->device = device;
+  if (stream) {
+    h->stream = reinterpret_cast<cudaStream_t>(stream);
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+      delete h;
+      return VZGP_ERR_CUDA;
+    }
+    h->own_stream = true;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  int s = h->small.reserve(kSmallBytes);
+  if (s < 0) { delete h; return s; }
+  cudaMemsetAsync(h->small.ptr, 0, kSmallBytes, h->stream);
+  *out = h;
+  return 0;
+}
+
+int vzgp_destroy(vzgp_handle* h) {
+  if (!h) return 0;
+  Guard g(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : {&h->X, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv,
+                    &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle})
+    b->release();
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int vzgp_synchronize(vzgp_handle* h) {
+  VZ_ARG(h != nullptr, "handle");
+  Guard g(h->device);
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t vzgp_launch_count(const vzgp_handle* h) { return h ? h->launches : 0; }
+
+int vzgp_kernel_matrix(vzgp_handle* h, const double* X, const int32_t* Z, int N, int Dc, int Dk,
+                       int n_valid, const vzgp_params* p, double diag_add, double* K, int ldk) {
+  VZ_ARG(h && K, "handle / K");
+  VZ_ARG(N >= 1 && ldk >= N, "N, ldk");
+  VZ_ARG(n_valid >= 0 && n_valid <= N, "n_valid");
+  Guard g(h->device);
+  KernelParams kp;
+  VZ_TRY(fill_kernel_params(p, Dc, Dk, &kp));
+  return launch_kernel_matrix(h, X, Z, N, n_valid, kp, diag_add, K, ldk);
+}
+
+int vzgp_cross_kernel(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const double* X,
+                      const int32_t* Z, int N, int Dc, int Dk, const vzgp_params* p, double* Ks,
+                      int ldks) {
+  VZ_ARG(h && Ks, "handle / Ks");
+  VZ_ARG(M >= 1 && N >= 1 && ldks >= N, "M, N, ldks");
+  Guard g(h->device);
+  KernelParams kp;
+  VZ_TRY(fill_kernel_params(p, Dc, Dk, &kp));
+  return launch_cross_kernel(h, Xs, Zs, M, X, Z, N, N, kp, Ks, ldks);
+}
+
+// Copies the top-left [N x N] lower part of a padded [np x np] matrix into a user matrix.
+__global__ void k_unpad_lower(const double* __restrict__ src, int np, int N, double* __restrict__ dst,
+                              int ld) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j < N) dst[(size_t)i * ld + j] = (j <= i) ? src[(size_t)i * np + j] : 0.0;
+}
+
+int vzgp_cholesky_retry(vzgp_handle* h, const double* A, int N, int lda, double jitter0,
+                        int max_iters, double* L, int ldl, double* shift_out) {
+  VZ_ARG(h && A && L, "handle / A / L");
+  VZ_ARG(N >= 1 && lda >= N && ldl >= N, "N, lda, ldl");
+  VZ_ARG(max_iters >= 0, "max_iters");
+  Guard g(h->device);
+  const int np = round_up(N, kBlk);
+  VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * 2));
+  double* Lp = h->Kinv.as<double>();
+  double* Li = Lp + (size_t)np * np;
+  int retries = cholesky_retry_padded(h, A, lda, N, np, jitter0, max_iters, Lp, Li, shift_out);
+  if (retries < 0) return retries;
+  k_unpad_lower<<<dim3((N + 255) / 256, N), 256, 0, h->stream>>>(Lp, np, N, L, ldl);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  return retries;
+}
+
+int vzgp_tri_inverse(vzgp_handle* h, const double* L, int N, int ldl, double* Linv, int ldi) {
+  VZ_ARG(h && L && Linv, "handle / L / Linv");
+  VZ_ARG(N >= 1 && ldl >= N && ldi >= N, "N, ldl, ldi");
+  Guard g(h->device);
+  const int np = round_up(N, kBlk);
+  VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * 3));
+  double* Lp = h->Kinv.as<double>();
+  double* Li = Lp + (size_t)np * np;
+  double* T = Li + (size_t)np * np;
+  VZ_TRY(launch_copy_lower_shift(h, L, ldl, N, np, 0.0, Lp, np));
+  VZ_CUDA(cudaMemsetAsync(Li, 0, sizeof(double) * (size_t)np * np, h->stream));
+  VZ_TRY(launch_diag_inv(h, Lp, np, Li, np, np));
+  VZ_TRY(trtri_doubling(h, Lp, np, Li, np, T, np, np));
+  k_unpad_lower<<<dim3((N + 255) / 256, N), 256, 0, h->stream>>>(Li, np, N, Linv, ldi);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+
+int vzgp_fit(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
+             int Dk, int n_valid, const vzgp_params* p) {
+  VZ_ARG(h != nullptr, "handle");
+  Guard g(h->device);
+  int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, nullptr);
+  if (retries < 0) return retries;
+  h->fitted = true;
+  return retries;
+}
+
+int vzgp_get_cholesky(vzgp_handle* h, double* L, int ldl) {
+  VZ_ARG(h && L, "handle / L");
+  if (!h->fitted) { set_error("vzgp_get_cholesky: model not fitted"); return VZGP_ERR_STATE; }
+  VZ_ARG(ldl >= h->n, "ldl");
+  Guard g(h->device);
+  k_unpad_lower<<<dim3((h->n + 255) / 256, h->n), 256, 0, h->stream>>>(h->L.as<double>(), h->np, h->n, L, ldl);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+
+int vzgp_get_alpha(vzgp_handle* h, double* alpha) {
+  VZ_ARG(h && alpha, "handle / alpha");
+  if (!h->fitted) { set_error("vzgp_get_alpha: model not fitted"); return VZGP_ERR_STATE; }
+  Guard g(h->device);
+  VZ_CUDA(cudaMemcpyAsync(alpha, h->alpha.ptr, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
+                  int Dk, int n_valid, const vzgp_params* p, double* loss_out, double* grad_out) {
+  VZ_ARG(h && loss_out && grad_out, "handle / outputs");
+  Guard g(h->device);
+  double shift = 0.0;
+  int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, &shift);
+  if (retries < 0) return retries;
+  const int np = h->np, nq = Dc + Dk + 2;
+  VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np));
+  double* out2 = reinterpret_cast<double*>(h->small.as<char>() + kOffLogdet);
+  double* gout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);
+  double* w = h->ypad.as<double>() + np;
+  VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, w, out2));
+  VZ_TRY(launch_lauum(h, h->Linv.as<double>(), np, h->Kinv.as<double>(), np, np));
+  VZ_TRY(launch_nll_grad_tiles(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, h->kp,
+                               h->Kinv.as<double>(), np, h->alpha.as<double>(), h->Tws.as<double>(), gout));
+  double host2[2];
+  double hostg[kMaxDc + kMaxDk + 2];
+  VZ_CUDA(cudaMemcpyAsync(host2, out2, sizeof(host2), cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(hostg, gout, sizeof(double) * nq, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  // Regularisers: tuned_gp_models.py:167,180,192,269 -> 0.01*log(x/c)^2, derivative 0.02*log(x/c)/x.
+  const double sf2 = p->signal_variance, sn2 = p->observation_noise_variance;
+  auto reg = [](double x, double c) { double l = std::log(x / c); return 0.01 * l * l; };
+  auto dreg = [](double x, double c) { return 0.02 * std::log(x / c) / x; };
+  double loss = host2[1] + host2[0] + 0.5 * n_valid * std::log(2.0 * M_PI);
+  loss += reg(sf2, 0.039) + reg(sn2, 0.0039);
+  for (int k = 0; k < Dk; ++k) {
+    const double l = p->categorical_length_scale_squared[k];
+    loss += reg(l, 0.5);
+    grad_out[k] = -0.5 * hostg[k] / (l * l) + dreg(l, 0.5);
+  }
+  for (int d = 0; d < Dc; ++d) {
+    const double l = p->continuous_length_scale_squared[d];
+    loss += reg(l, 0.5);
+    grad_out[Dk + d] = -0.5 * hostg[Dk + d] / (l * l) + dreg(l, 0.5);
+  }
+  grad_out[Dk + Dc] = 0.5 * hostg[Dk + Dc] + dreg(sn2, 0.0039);
+  grad_out[Dk + Dc + 1] = 0.5 * hostg[Dk + Dc + 1] / sf2 + dreg(sf2, 0.039);
+  *loss_out = loss;
+  return retries;
+}
+
+static int check_scoring(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
+                         const vzgp_acq* acq, const double* score) {
+  VZ_ARG(h != nullptr, "handle");
+  if (!h->fitted) { set_error("scoring requested before vzgp_fit"); return VZGP_ERR_STATE; }
+  VZ_ARG(M >= 0, "M");
+  VZ_ARG(acq != nullptr, "acq");
+  VZ_ARG(score != nullptr, "score");
+  VZ_ARG(Xs != nullptr || h->dc == 0, "Xs");
+  VZ_ARG(Zs != nullptr || h->dk == 0, "Zs");
+  return 0;
+}
+
+int vzgp_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+               double* score, double* mu, double* sigma, double* linf) {
+  VZ_TRY(check_scoring(h, Xs, Zs, M, acq, score));
+  Guard g(h->device);
+  return launch_score(h, Xs, Zs, M, acq, score, mu, sigma, linf);
+}
+
+int vzgp_clamped_count(vzgp_handle* h, int64_t* count_out) {
+  VZ_ARG(h && count_out, "handle / out");
+  Guard g(h->device);
+  int c = 0;
+  int* d = reinterpret_cast<int*>(h->small.as<char>() + kOffClamp);
+  VZ_CUDA(cudaMemcpyAsync(&c, d, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemsetAsync(d, 0, sizeof(int), h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  *count_out = c;
+  return 0;
+}
+
+int vzgp_score_host(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
+                    const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf) {
+  VZ_TRY(check_scoring(h, Xs, Zs, M, acq, score));
+  if (M == 0) return 0;
+  Guard g(h->device);
+  const size_t xb = sizeof(double) * (size_t)M * h->dc, zb = sizeof(int32_t) * (size_t)M * h->dk;
+  VZ_TRY(h->xs_dev.reserve(xb + zb + 64));
+  VZ_TRY(h->out_dev.reserve(sizeof(double) * (size_t)M * 4));
+  double* dX = h->xs_dev.as<double>();
+  int32_t* dZ = reinterpret_cast<int32_t*>(h->xs_dev.as<char>() + ((xb + 15) / 16) * 16);
+  if (h->dc > 0) VZ_CUDA(cudaMemcpyAsync(dX, Xs, xb, cudaMemcpyHostToDevice, h->stream));
+  if (h->dk > 0) VZ_CUDA(cudaMemcpyAsync(dZ, Zs, zb, cudaMemcpyHostToDevice, h->stream));
+  double* o = h->out_dev.as<double>();
+  VZ_TRY(launch_score(h, dX, h->dk > 0 ? dZ : nullptr, M, acq, o, mu ? o + M : nullptr,
+                      sigma ? o + 2 * (size_t)M : nullptr, linf ? o + 3 * (size_t)M : nullptr));
+  const size_t ob = sizeof(double) * (size_t)M;
+  VZ_CUDA(cudaMemcpyAsync(score, o, ob, cudaMemcpyDeviceToHost, h->stream));
+  if (mu) VZ_CUDA(cudaMemcpyAsync(mu, o + M, ob, cudaMemcpyDeviceToHost, h->stream));
+  if (sigma) VZ_CUDA(cudaMemcpyAsync(sigma, o + 2 * (size_t)M, ob, cudaMemcpyDeviceToHost, h->stream));
+  if (linf) VZ_CUDA(cudaMemcpyAsync(linf, o + 3 * (size_t)M, ob, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int topk_to_device(vzgp_handle* h, const double* score, int64_t M, int count,
+                          long long** d_idx, double** d_val) {
+  VZ_ARG(count >= 1 && count <= kMaxTopk, "1 <= count <= 256");
+  *d_idx = reinterpret_cast<long long*>(h->small.as<char>() + kOffTopIdx);
+  *d_val = reinterpret_cast<double*>(h->small.as<char>() + kOffTopVal);
+  ArgMax* part = reinterpret_cast<ArgMax*>(h->small.as<char>() + kOffPartial);
+  int64_t nb = (M + 2047) / 2048;
+  if (nb < 1) nb = 1;
+  if (nb > 2048) nb = 2048;
+  return launch_topk_device(h, score, M, count, *d_idx, *d_val, part, (int)nb);
+}
+
+int vzgp_topk(vzgp_handle* h, const double* score, int64_t M, int count, int64_t* idx_out,
+              double* val_out) {
+  VZ_ARG(h && score && idx_out && val_out, "handle / pointers");
+  VZ_ARG(M >= 1, "M");
+  Guard g(h->device);
+  long long* d_idx; double* d_val;
+  VZ_TRY(topk_to_device(h, score, M, count, &d_idx, &d_val));
+  long long hidx[kMaxTopk];
+  VZ_CUDA(cudaMemcpyAsync(hidx, d_idx, sizeof(long long) * count, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(val_out, d_val, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < count; ++c) idx_out[c] = (hidx[c] == LLONG_MAX) ? -1 : (int64_t)hidx[c];
+  return 0;
+}
+
+int vzgp_random_pool(vzgp_handle* h, int64_t M, int Dc, int64_t index_base, uint64_t seed, double* X) {
+  VZ_ARG(h && X, "handle / X");
+  VZ_ARG(M >= 0 && Dc >= 1, "M, Dc");
+  Guard g(h->device);
+  return launch_random_fill(h, X, M * Dc, index_base * Dc, seed, 3u, 0u);
+}
+
+int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp_acq* acq, int count,
+                       uint64_t seed, double* best_x, double* best_score, int64_t* best_index) {
+  VZ_ARG(h && acq && best_x && best_score, "handle / pointers");
+  if (!h->fitted) { set_error("vzgp_random_search before vzgp_fit"); return VZGP_ERR_STATE; }
+  VZ_ARG(h->dk == 0, "random search supports continuous features only");
+  VZ_ARG(M >= 1 && M <= INT_MAX, "1 <= M < 2^31 per call");
+  Guard g(h->device);
+  const int dc = h->dc;
+  VZ_TRY(h->xs_dev.reserve(sizeof(double) * (size_t)M * dc));
+  VZ_TRY(h->out_dev.reserve(sizeof(double) * ((size_t)M + (size_t)kMaxTopk * dc)));
+  double* dX = h->xs_dev.as<double>();
+  double* dS = h->out_dev.as<double>();
+  double* dBest = dS + M;
+  VZ_TRY(launch_random_fill(h, dX, M * dc, index_base * dc, seed, 3u, 0u));
+  VZ_TRY(launch_score(h, dX, nullptr, (int)M, acq, dS, nullptr, nullptr, nullptr));
+  long long* d_idx; double* d_val;
+  VZ_TRY(topk_to_device(h, dS, M, count, &d_idx, &d_val));
+  VZ_TRY(launch_gather_rows(h, dX, dc, d_idx, count, M, dBest));
+  long long hidx[kMaxTopk];
+  VZ_CUDA(cudaMemcpyAsync(hidx, d_idx, sizeof(long long) * count, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(best_score, d_val, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(best_x, dBest, sizeof(double) * (size_t)count * dc, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  if (best_index)
+    for (int c = 0; c < count; ++c)
+      best_index[c] = (hidx[c] == LLONG_MAX) ? -1 : (int64_t)hidx[c] + index_base;
+  return 0;
+}
+
+int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
+                   const double* prior, int n_prior, int count, uint64_t seed, double* best_x,
+                   double* best_score) {
+  VZ_ARG(h && cfg && acq && best_x && best_score, "handle / pointers");
+  if (!h->fitted) { set_error("vzgp_eagle_run before vzgp_fit"); return VZGP_ERR_STATE; }
+  VZ_ARG(h->dk == 0, "eagle supports continuous features only (categorical: next)");
+  VZ_ARG(cfg->pool_size >= 1 && cfg->batch_size >= 1, "pool/batch size");
+  VZ_ARG(cfg->pool_size % cfg->batch_size == 0, "pool_size must be a multiple of batch_size");
+  VZ_ARG(cfg->pool_size <= 3000, "pool_size <= 3000");
+  VZ_ARG(cfg->batch_size <= 8192, "batch_size <= 8192");
+  VZ_ARG(count >= 1 && count <= kMaxTopk, "count");
+  VZ_ARG(cfg->max_evaluations >= 1, "max_evaluations");
+  VZ_ARG(n_prior >= 0 && (n_prior == 0 || prior != nullptr), "prior");
+  Guard g(h->device);
+  const int P = cfg->pool_size, B = cfg->batch_size, D = h->dc;
+  // carve the eagle buffer
+  size_t nd = (size_t)P * D + 2 * (size_t)P + 8 + (size_t)B * D + B + 2 * ((size_t)count * D + count) +
+              (size_t)(n_prior > 0 ? n_prior : 1) + (size_t)P;
+  size_t bytes = nd * sizeof(double) + 2 * (size_t)count * sizeof(long long) + 64 +
+                 (size_t)(n_prior > 0 ? n_prior : 1) * sizeof(int) + 64;
+  VZ_TRY(h->eagle.reserve(bytes));
+  double* p = h->eagle.as<double>();
+  EagleDev e;
+  e.pool = p; p += (size_t)P * D;
+  e.rewards = p; p += P;
+  e.pert = p; p += P;
+  e.best_reward = p; p += 8;
+  e.batch = p; p += (size_t)B * D;
+  e.batch_r = p; p += B;
+  e.best_x = p; p += (size_t)count * D;
+  e.best_r = p; p += count;
+  e.tmp_x = p; p += (size_t)count * D;
+  e.tmp_r = p; p += count;
+  double* prior_r = p; p += (n_prior > 0 ? n_prior : 1);
+  double* chosen_r = p; p += P;
+  long long* lp = reinterpret_cast<long long*>(p);
+  e.best_id = lp; lp += count;
+  e.tmp_id = lp; lp += count;
+  int* ip = reinterpret_cast<int*>(lp);
+  e.iter = ip; ip += 16;
+  int* ord = ip;
+  e.P = P; e.B = B; e.D = D; e.count = count; e.cfg = *cfg; e.seed = seed;
+  VZ_TRY(eagle_prepare(e));
+  VZ_TRY(launch_eagle_init(h, e));
+  if (n_prior > 0) {
+    VZ_TRY(launch_score(h, prior, nullptr, n_prior, acq, prior_r, nullptr, nullptr, nullptr));
+    VZ_TRY(launch_eagle_seed_priors(h, e, prior, prior_r, n_prior, ord, chosen_r));
+  }
+  const int steps = (cfg->max_evaluations - 1) / B + 1;
+  for (int t = 0; t < steps; ++t) {
+    VZ_TRY(launch_eagle_suggest(h, e));
+    VZ_TRY(launch_score(h, e.batch, nullptr, B, acq, e.batch_r, nullptr, nullptr, nullptr));
+    VZ_TRY(launch_eagle_update(h, e));
+  }
+  VZ_CUDA(cudaMemcpyAsync(best_x, e.best_x, sizeof(double) * (size_t)count * D, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(best_score, e.best_r, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // extern "C"

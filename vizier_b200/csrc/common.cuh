@@ -1,0 +1,128 @@
+// Shared declarations for libvzgp: handle, error plumbing, small device helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/vzgp.h"
+
+namespace vzgp {
+
+constexpr int kBlk = 64;       // padding / factorisation block size
+constexpr int kMaxDc = 64;     // continuous feature dims supported by the tile kernels
+constexpr int kMaxDk = 32;     // categorical feature dims
+
+void set_error(const char* fmt, ...);
+
+#define VZ_CUDA(expr)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      ::vzgp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,              \
+                        cudaGetErrorString(_e));                                   \
+      return VZGP_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+#define VZ_CHECK_LAUNCH()                                                          \
+  do {                                                                             \
+    cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) {                                                       \
+      ::vzgp::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,          \
+                        cudaGetErrorString(_e));                                   \
+      return VZGP_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+#define VZ_ARG(cond, msg)                                                          \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      ::vzgp::set_error("%s:%d: bad argument: %s (%s)", __FILE__, __LINE__, msg,   \
+                        #cond);                                                    \
+      return VZGP_ERR_ARG;                                                         \
+    }                                                                              \
+  } while (0)
+
+#define VZ_TRY(expr)                                                               \
+  do {                                                                             \
+    int _s = (expr);                                                               \
+    if (_s < 0) return _s;                                                         \
+  } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Growable device buffer owned by a handle.
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t n) {
+    if (n <= bytes) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, n);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+      return VZGP_ERR_CUDA;
+    }
+    bytes = n;
+    return 0;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// Kernel hyper-parameters in the form the kernels consume (device constant-ish,
+// passed by value in kernel arguments; <= 4 KB parameter space is fine).
+struct KernelParams {
+  int dc;
+  int dk;
+  double sf2;
+  double inv_ls2_c[kMaxDc];
+  double inv_ls2_k[kMaxDk];
+};
+
+}  // namespace vzgp
+
+struct vzgp_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int64_t launches = 0;
+
+  // Fitted model (all padded to np = round_up(n, 64); pad rows are identity/zero).
+  bool fitted = false;
+  int n = 0, np = 0, dc = 0, dk = 0, n_valid = 0;
+  vzgp::KernelParams kp;
+  double sn2 = 0.0;
+  vzgp::DevBuf X;      // [np x dc]
+  vzgp::DevBuf Z;      // [np x dk] int32
+  vzgp::DevBuf L;      // [np x np]
+  vzgp::DevBuf Linv;   // [np x np]
+  vzgp::DevBuf alpha;  // [np]
+  vzgp::DevBuf ypad;   // [np]
+
+  // Workspaces.
+  vzgp::DevBuf Kws;     // [np x np] kernel matrix / temporaries
+  vzgp::DevBuf Tws;     // [np x np] second temporary
+  vzgp::DevBuf Kinv;    // [np x np]
+  vzgp::DevBuf scratch; // per-CTA K* tiles for the score kernel
+  vzgp::DevBuf small;   // flags, partial reductions
+  vzgp::DevBuf xs_dev;  // staging for *_host entry points
+  vzgp::DevBuf out_dev;
+  vzgp::DevBuf eagle;   // eagle state
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};

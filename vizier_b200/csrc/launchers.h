@@ -1,0 +1,74 @@
+// Internal prototypes of the per-file launch helpers (all return 0 or a negative vzgp status).
+#pragma once
+#include "common.cuh"
+
+namespace vzgp {
+
+int fill_kernel_params(const vzgp_params* p, int dc, int dk, KernelParams* kp);
+int launch_kernel_matrix(vzgp_handle* h, const double* X, const int32_t* Z, int n, int n_valid,
+                         const KernelParams& kp, double diag_add, double* K, int ldk);
+int launch_cross_kernel(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const double* X,
+                        const int32_t* Z, int n, int n_valid, const KernelParams& kp, double* Ks,
+                        int ldks);
+int potrf_blocked(vzgp_handle* h, double* L, int ld, double* Linv, int ldi, int np, int* flag);
+int trtri_doubling(vzgp_handle* h, const double* L, int ld, double* Linv, int ldi, double* T, int ldt,
+                   int np);
+int launch_lauum(vzgp_handle* h, const double* Linv, int ldi, double* Kinv, int ldk, int np);
+int launch_copy_lower_shift(vzgp_handle* h, const double* A, int lda, int n_src, int np, double shift,
+                            double* L, int ldl);
+int launch_diag_inv(vzgp_handle* h, const double* L, int ld, double* Linv, int ldi, int np);
+int launch_gemv_rows(vzgp_handle* h, const double* M, int ld, int np, const double* v, double* out,
+                     int lower_only);
+int launch_gemv_lower_T(vzgp_handle* h, const double* M, int ld, int np, const double* v, double* out);
+int launch_residual(vzgp_handle* h, const double* Ky, int ld, int np, const double* y, const double* a,
+                    double* r);
+int launch_axpy(vzgp_handle* h, int n, double a, const double* x, double* y);
+int launch_pad_vector(vzgp_handle* h, const double* src, int n, int n_valid, int np, double* dst);
+int launch_pad_rows(vzgp_handle* h, const double* src, int n, int d, int np, double* dst);
+int launch_pad_rows_i32(vzgp_handle* h, const int32_t* src, int n, int d, int np, int32_t* dst);
+int launch_logdet_quad(vzgp_handle* h, const double* L, int ld, int n_valid, const double* w, double* out);
+
+int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
+                          const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,
+                          double* partial, double* out);
+
+int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                 double* score, double* mu, double* sigma, double* linf);
+int launch_random_fill(vzgp_handle* h, double* X, int64_t total, int64_t elem_base, uint64_t seed,
+                       uint32_t stream, uint32_t iteration);
+struct ArgMax {
+  double v;
+  long long i;
+};
+int launch_topk_device(vzgp_handle* h, const double* score, int64_t M, int count, long long* d_idx,
+                       double* d_val, ArgMax* d_partial, int nblocks);
+int launch_gather_rows(vzgp_handle* h, const double* X, int dc, const long long* idx, int count,
+                       int64_t M, double* out);
+
+// Device-resident eagle optimiser state (pointers into handle->eagle).
+struct EagleDev {
+  double* pool;         // [P x D]
+  double* rewards;      // [P]
+  double* pert;         // [P]
+  double* best_reward;  // [1]
+  int* iter;            // [1]
+  double* batch;        // [B x D] candidates of the current step
+  double* batch_r;      // [B] their scores
+  double* best_x;       // [count x D]
+  double* best_r;       // [count]
+  long long* best_id;   // [count] evaluation ids (t*B + b), tie-break
+  double* tmp_x;
+  double* tmp_r;
+  long long* tmp_id;
+  int P, B, D, count;
+  vzgp_eagle_config cfg;
+  uint64_t seed;
+};
+int launch_eagle_init(vzgp_handle* h, const EagleDev& e);
+int launch_eagle_seed_priors(vzgp_handle* h, const EagleDev& e, const double* prior,
+                             const double* prior_r, int n, int* ord, double* chosen_r);
+int eagle_prepare(const EagleDev& e);
+int launch_eagle_suggest(vzgp_handle* h, const EagleDev& e);
+int launch_eagle_update(vzgp_handle* h, const EagleDev& e);
+
+}  // namespace vzgp

@@ -1,0 +1,128 @@
+// Gradient of the GP negative log marginal likelihood w.r.t. the ARD hyper-parameters.
+//
+// Replaces the JAX autodiff of loss_with_aux (vizier/_src/jax/stochastic_process_model.py:
+// 940-966, differentiated at vizier/_src/jax/optimizers/jaxopt_wrappers.py:149-151) by the
+// closed form:  G = K_y^-1 - alpha alpha^T,  dNLL/dp = 0.5 * sum_ij G_ij dK_ij/dp,
+//   dK/d ls2_d = -E_ij * diff_ijd^2 / ls2_d^2,  dK/d sf2 = K/sf2,  dK_y/d sn2 = I,
+//   E_ij = dk/d(d2) = -(5/6) sf2 (1+s) exp(-s).
+#include "launchers.h"
+#include "tiles.cuh"
+
+namespace vzgp {
+
+using G64 = GemmCfg<64, 64, 16, 4, 4>;
+
+// One CTA per lower-triangular 64x64 tile (off-diagonal tiles count twice).  Writes
+// partial[tile][0..dk) = sum G*E*neq_k, [dk..dk+dc) = sum G*E*diff_d^2, [dk+dc] = trace part of G,
+// [dk+dc+1] = sum G*K.
+__global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict__ X,
+                                                        const int32_t* __restrict__ Z, int np,
+                                                        int n_valid, KernelParams kp,
+                                                        const double* __restrict__ Kinv, int ldk,
+                                                        const double* __restrict__ alpha,
+                                                        double* __restrict__ partial, int nb) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  extern __shared__ double smem[];
+  constexpr int LD = 66;
+  const int dc = kp.dc, dk = kp.dk, np_out = dc + dk + 2;
+  double* sa = smem;
+  double* sb = sa + dc * LD;
+  double* s_part = sb + dc * LD;                                   // [8 warps][np_out]
+  int32_t* za = reinterpret_cast<int32_t*>(s_part + 8 * np_out);
+  int32_t* zb = za + dk * LD;
+  stage_rows_T(X, np, dc, bi * 64, 64, sa, LD);
+  stage_rows_T(X, np, dc, bj * 64, 64, sb, LD);
+  if (dk > 0) {
+    stage_rows_T_i32(Z, np, dk, bi * 64, 64, za, LD);
+    stage_rows_T_i32(Z, np, dk, bj * 64, 64, zb, LD);
+  }
+  __syncthreads();
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16, warp = tid / 32, lane = tid % 32;
+  double d2[4][4], unused[4][4];
+  tile_d2<G64, 4, 4, false>(sa, LD, sb, LD, za, LD, zb, LD, kp, nullptr, ty, tx, d2, unused);
+  double ge[4][4];
+  double sum_gk = 0.0, sum_tr = 0.0;
+  const double wgt = (bi == bj) ? 1.0 : 2.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = bi * 64 + G64::row_of(ty, i), gj = bj * 64 + G64::col_of(tx, j);
+      double g = 0.0, kv = 0.0, ev = 0.0;
+      if (gi < n_valid && gj < n_valid) {
+        g = wgt * (Kinv[(size_t)gi * ldk + gj] - alpha[gi] * alpha[gj]);
+        matern52_with_grad(d2[i][j], kp.sf2, kv, ev);
+        if (gi == gj) sum_tr += g;
+      }
+      ge[i][j] = g * ev;
+      sum_gk = fma(g, kv, sum_gk);
+    }
+  auto warp_store = [&](double v, int slot) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[warp * np_out + slot] = v;
+  };
+  for (int k = 0; k < dk; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int av = za[k * LD + G64::row_of(ty, i)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t += (av != zb[k * LD + G64::col_of(tx, j)]) ? ge[i][j] : 0.0;
+    }
+    warp_store(t, k);
+  }
+  for (int d = 0; d < dc; ++d) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double av = sa[d * LD + G64::row_of(ty, i)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double diff = av - sb[d * LD + G64::col_of(tx, j)];
+        t = fma(ge[i][j], diff * diff, t);
+      }
+    }
+    warp_store(t, dk + d);
+  }
+  warp_store(sum_tr, dk + dc);
+  warp_store(sum_gk, dk + dc + 1);
+  __syncthreads();
+  // tile index in row-major lower-triangular enumeration
+  const int tile = bi * (bi + 1) / 2 + bj;
+  if (tid < np_out) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_part[w * np_out + tid];
+    partial[(size_t)tile * np_out + tid] = s;
+  }
+}
+
+// out[q] = sum over tiles (fixed order) of partial[tile][q].
+__global__ void k_reduce_partials(const double* __restrict__ partial, int ntiles, int nq,
+                                  double* __restrict__ out) {
+  __shared__ double red[32];
+  const int q = blockIdx.x;
+  double s = 0.0;
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) s += partial[(size_t)t * nq + q];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[q] = s;
+}
+
+int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
+                          const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,
+                          double* partial, double* out) {
+  const int nb = np / 64, nq = kp.dc + kp.dk + 2, ntiles = nb * (nb + 1) / 2;
+  size_t sm = sizeof(double) * (kp.dc * 2 * 66 + 8 * nq) + sizeof(int32_t) * kp.dk * 2 * 66;
+  VZ_CUDA(cudaFuncSetAttribute(k_nll_grad_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_nll_grad_tiles<<<dim3(nb, nb), 256, sm, h->stream>>>(X, Z, np, n_valid, kp, Kinv, ldk, alpha,
+                                                         partial, nb);
+  VZ_CHECK_LAUNCH();
+  k_reduce_partials<<<nq, 256, 0, h->stream>>>(partial, ntiles, nq, out);
+  VZ_CHECK_LAUNCH();
+  h->launches += 2;
+  return 0;
+}
+
+}  // namespace vzgp

@@ -1,0 +1,331 @@
+"""Device GP: thin Python object over a libvzgp handle.
+
+Mirrors the pieces of the reference's GP stack that `VizierGPBandit` touches:
+  * `GPHyperParams`  <-> the parameter dict of `VizierGaussianProcess`
+    (vizier/_src/jax/models/tuned_gp_models.py:161-271),
+  * `DeviceGP.fit`   <-> `StochasticProcessWithCoroutine.precompute_predictive`
+    (vizier/_src/jax/stochastic_process_model.py:968-997),
+  * `DeviceGP.loss_and_grad` <-> `loss_with_aux` + autodiff (:940-966),
+  * `DeviceGP.score` <-> `BayesianScoringFunction.score_with_aux`
+    (vizier/_src/algorithms/designers/gp/acquisitions.py:177-207).
+All arithmetic runs in the CUDA library; torch tensors are device-memory handles.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from vizier_b200 import _lib
+
+# Bounds / regulariser centres of the reference model (tuned_gp_models.py:147-159).
+BOUNDARY_EPS = 1e-12
+SIGNAL_VARIANCE_BOUNDS = (1e-3 - BOUNDARY_EPS, 10.0 + BOUNDARY_EPS)
+LENGTH_SCALE_SQUARED_BOUNDS = (1e-2 - BOUNDARY_EPS, 1e2 + BOUNDARY_EPS)
+NOISE_VARIANCE_BOUNDS = (1e-10 - BOUNDARY_EPS, 1.0 + BOUNDARY_EPS)
+
+
+@dataclasses.dataclass
+class GPHyperParams:
+  signal_variance: float
+  continuous_length_scale_squared: np.ndarray
+  observation_noise_variance: float
+  categorical_length_scale_squared: Optional[np.ndarray] = None
+
+  def __post_init__(self):
+    self.continuous_length_scale_squared = np.ascontiguousarray(
+        np.asarray(self.continuous_length_scale_squared, np.float64).reshape(-1))
+    if self.categorical_length_scale_squared is None:
+      self.categorical_length_scale_squared = np.zeros((0,), np.float64)
+    self.categorical_length_scale_squared = np.ascontiguousarray(
+        np.asarray(self.categorical_length_scale_squared, np.float64).reshape(-1))
+
+  # jaxopt's sorted-key flattening: categorical ls2, continuous ls2, noise, signal.
+  def to_vector(self) -> np.ndarray:
+    return np.concatenate([
+        self.categorical_length_scale_squared, self.continuous_length_scale_squared,
+        [self.observation_noise_variance], [self.signal_variance]])
+
+  @classmethod
+  def from_vector(cls, v: np.ndarray, dc: int, dk: int) -> 'GPHyperParams':
+    v = np.asarray(v, np.float64)
+    return cls(signal_variance=float(v[dk + dc + 1]),
+               continuous_length_scale_squared=v[dk:dk + dc].copy(),
+               observation_noise_variance=float(v[dk + dc]),
+               categorical_length_scale_squared=v[:dk].copy())
+
+  def _c(self) -> _lib.Params:
+    p = _lib.Params()
+    p.signal_variance = float(self.signal_variance)
+    p.observation_noise_variance = float(self.observation_noise_variance)
+    p.continuous_length_scale_squared = self.continuous_length_scale_squared.ctypes.data_as(
+        C.POINTER(C.c_double))
+    p.categorical_length_scale_squared = (
+        self.categorical_length_scale_squared.ctypes.data_as(C.POINTER(C.c_double))
+        if self.categorical_length_scale_squared.size else None)
+    return p
+
+
+def param_bounds(dc: int, dk: int) -> tuple[np.ndarray, np.ndarray]:
+  lo = np.concatenate([np.full(dk, LENGTH_SCALE_SQUARED_BOUNDS[0]), np.full(dc, LENGTH_SCALE_SQUARED_BOUNDS[0]),
+                       [NOISE_VARIANCE_BOUNDS[0]], [SIGNAL_VARIANCE_BOUNDS[0]]])
+  hi = np.concatenate([np.full(dk, LENGTH_SCALE_SQUARED_BOUNDS[1]), np.full(dc, LENGTH_SCALE_SQUARED_BOUNDS[1]),
+                       [NOISE_VARIANCE_BOUNDS[1]], [SIGNAL_VARIANCE_BOUNDS[1]]])
+  return lo, hi
+
+
+@dataclasses.dataclass
+class Acquisition:
+  """UCB coefficient + trust region (acquisitions.py:213-225, :691-820)."""
+
+  ucb_coefficient: float = 1.8
+  use_trust_region: bool = True
+  trust_radius: float = 1.0
+  tr_dim_mask: Optional[np.ndarray] = None  # bool [Dc]
+
+  def _c(self):
+    a = _lib.Acq()
+    a.ucb_coefficient = float(self.ucb_coefficient)
+    a.use_trust_region = 1 if self.use_trust_region else 0
+    a.trust_radius = float(self.trust_radius)
+    keep = None
+    if self.tr_dim_mask is not None:
+      keep = np.ascontiguousarray(np.asarray(self.tr_dim_mask).astype(np.uint8))
+      a.tr_dim_mask = keep.ctypes.data_as(C.POINTER(C.c_uint8))
+    else:
+      a.tr_dim_mask = None
+    return a, keep
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class DeviceGP:
+  """One libvzgp handle = one study's GP on one GPU."""
+
+  def __init__(self, device: int = 0):
+    self._lib = _lib.load()
+    if not torch.cuda.is_available():
+      raise RuntimeError('vizier_b200 needs a CUDA device; there is no CPU fallback.')
+    self.device = torch.device('cuda', device)
+    torch.cuda.init()
+    with torch.cuda.device(self.device):
+      torch.zeros(1, device=self.device)  # make sure the primary context exists
+    self._stream = torch.cuda.Stream(device=self.device)
+    h = C.c_void_p()
+    _lib.check('vzgp_create', self._lib.vzgp_create(device, C.c_void_p(self._stream.cuda_stream), C.byref(h)))
+    self._h = h
+    self.dc = self.dk = self.n = 0
+
+  def close(self):
+    if getattr(self, '_h', None):
+      self._lib.vzgp_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  @property
+  def stream(self) -> torch.cuda.Stream:
+    return self._stream
+
+  def synchronize(self):
+    _lib.check('vzgp_synchronize', self._lib.vzgp_synchronize(self._h))
+
+  @property
+  def launch_count(self) -> int:
+    return int(self._lib.vzgp_launch_count(self._h))
+
+  # -- helpers -------------------------------------------------------------
+  def _dev(self, a, dtype) -> Optional[torch.Tensor]:
+    if a is None:
+      return None
+    if isinstance(a, torch.Tensor):
+      t = a.to(device=self.device, dtype=dtype).contiguous()
+    else:
+      t = torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype={torch.float64: np.float64, torch.int32: np.int32}[dtype])).to(self.device)
+    # tensors created on torch's current stream must be complete before our stream reads them
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    return t
+
+  def _xz(self, x, z):
+    xt = self._dev(x, torch.float64)
+    zt = self._dev(z, torch.int32) if z is not None and np.prod(tuple(z.shape)) > 0 else None
+    if zt is not None and zt.shape[1] == 0:
+      zt = None
+    return xt, zt
+
+  # -- stage-wise entry points -------------------------------------------------
+  def kernel_matrix(self, x, params: GPHyperParams, z=None, n_valid=None, diag_add=0.0) -> torch.Tensor:
+    xt, zt = self._xz(x, z)
+    n, dc = xt.shape
+    dk = 0 if zt is None else zt.shape[1]
+    out = torch.empty((n, n), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    p = params._c()
+    _lib.check('vzgp_kernel_matrix', self._lib.vzgp_kernel_matrix(
+        self._h, _ptr(xt), _ptr(zt), n, dc, dk, n if n_valid is None else n_valid, C.byref(p),
+        float(diag_add), _ptr(out), n))
+    self.synchronize()
+    return out
+
+  def cross_kernel(self, xs, x, params: GPHyperParams, zs=None, z=None) -> torch.Tensor:
+    xst, zst = self._xz(xs, zs)
+    xt, zt = self._xz(x, z)
+    m, dc = xst.shape
+    n = xt.shape[0]
+    dk = 0 if zt is None else zt.shape[1]
+    out = torch.empty((m, n), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    p = params._c()
+    _lib.check('vzgp_cross_kernel', self._lib.vzgp_cross_kernel(
+        self._h, _ptr(xst), _ptr(zst), m, _ptr(xt), _ptr(zt), n, dc, dk, C.byref(p), _ptr(out), n))
+    self.synchronize()
+    return out
+
+  def cholesky_retry(self, a, jitter: float = 1e-4, max_iters: int = 5):
+    at = self._dev(a, torch.float64)
+    n = at.shape[0]
+    out = torch.empty((n, n), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    shift = C.c_double(0.0)
+    retries = _lib.check('vzgp_cholesky_retry', self._lib.vzgp_cholesky_retry(
+        self._h, _ptr(at), n, n, float(jitter), int(max_iters), _ptr(out), n, C.byref(shift)))
+    return out, float(shift.value), retries
+
+  def tri_inverse(self, l) -> torch.Tensor:
+    lt = self._dev(l, torch.float64)
+    n = lt.shape[0]
+    out = torch.empty((n, n), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_tri_inverse', self._lib.vzgp_tri_inverse(self._h, _ptr(lt), n, n, _ptr(out), n))
+    self.synchronize()
+    return out
+
+  # -- model ---------------------------------------------------------------
+  def fit(self, x, y, params: GPHyperParams, z=None, n_valid=None) -> int:
+    xt, zt = self._xz(x, z)
+    yt = self._dev(np.asarray(y).reshape(-1) if not isinstance(y, torch.Tensor) else y.reshape(-1), torch.float64)
+    n, dc = xt.shape
+    dk = 0 if zt is None else zt.shape[1]
+    p = params._c()
+    retries = _lib.check('vzgp_fit', self._lib.vzgp_fit(
+        self._h, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, n if n_valid is None else n_valid, C.byref(p)))
+    self.synchronize()  # inputs may be freed by the caller after return
+    self.n, self.dc, self.dk = n, dc, dk
+    return retries
+
+  def cholesky(self) -> torch.Tensor:
+    out = torch.empty((self.n, self.n), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_get_cholesky', self._lib.vzgp_get_cholesky(self._h, _ptr(out), self.n))
+    self.synchronize()
+    return out
+
+  def alpha(self) -> torch.Tensor:
+    out = torch.empty((self.n,), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_get_alpha', self._lib.vzgp_get_alpha(self._h, _ptr(out)))
+    self.synchronize()
+    return out
+
+  def loss_and_grad(self, x, y, params: GPHyperParams, z=None, n_valid=None):
+    """x, y (and z) should be device tensors kept alive by the caller across ARD iterations."""
+    xt, zt = self._xz(x, z)
+    yt = self._dev(y, torch.float64).reshape(-1)
+    n, dc = xt.shape
+    dk = 0 if zt is None else zt.shape[1]
+    p = params._c()
+    loss = C.c_double(0.0)
+    grad = np.zeros(dc + dk + 2, np.float64)
+    retries = _lib.check('vzgp_nll_grad', self._lib.vzgp_nll_grad(
+        self._h, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, n if n_valid is None else n_valid,
+        C.byref(p), C.byref(loss), grad.ctypes.data_as(C.POINTER(C.c_double))))
+    return float(loss.value), grad, retries
+
+  def score(self, xs, acq: Acquisition, zs=None, with_aux: bool = False, out: Optional[dict] = None) -> dict:
+    """Asynchronous on self.stream; returns device tensors {'score', ['mean','stddev','linf_distance']}."""
+    xst, zst = self._xz(xs, zs)
+    m = xst.shape[0]
+    res = out if out is not None else {}
+    if 'score' not in res:
+      res['score'] = torch.empty((m,), dtype=torch.float64, device=self.device)
+      if with_aux:
+        for k in ('mean', 'stddev', 'linf_distance'):
+          res[k] = torch.empty((m,), dtype=torch.float64, device=self.device)
+      self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    a, keep = acq._c()
+    _lib.check('vzgp_score', self._lib.vzgp_score(
+        self._h, _ptr(xst), _ptr(zst), m, C.byref(a), _ptr(res['score']), _ptr(res.get('mean')),
+        _ptr(res.get('stddev')), _ptr(res.get('linf_distance'))))
+    res['_inputs'] = (xst, zst, keep)  # keep alive until the caller synchronises
+    return res
+
+  def clamped_count(self) -> int:
+    c = C.c_int64(0)
+    _lib.check('vzgp_clamped_count', self._lib.vzgp_clamped_count(self._h, C.byref(c)))
+    return int(c.value)
+
+  def score_host(self, xs: np.ndarray, acq: Acquisition, *, score_out: np.ndarray,
+                 zs: Optional[np.ndarray] = None, mean_out=None, stddev_out=None, linf_out=None):
+    """HOST buffers in, HOST buffers out (pinned memory recommended).  Synchronous."""
+    a, keep = acq._c()
+    m = xs.shape[0]
+
+    def hp(arr):
+      if arr is None:
+        return None
+      if isinstance(arr, torch.Tensor):
+        return C.c_void_p(arr.data_ptr())
+      return C.c_void_p(arr.ctypes.data)
+
+    _lib.check('vzgp_score_host', self._lib.vzgp_score_host(
+        self._h, hp(xs), hp(zs), m, C.byref(a), hp(score_out), hp(mean_out), hp(stddev_out), hp(linf_out)))
+    del keep
+
+  def topk(self, score: torch.Tensor, count: int):
+    idx = np.zeros(count, np.int64)
+    val = np.zeros(count, np.float64)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_topk', self._lib.vzgp_topk(
+        self._h, _ptr(score), score.numel(), count, idx.ctypes.data_as(C.POINTER(C.c_int64)),
+        val.ctypes.data_as(C.POINTER(C.c_double))))
+    return idx, val
+
+  def random_pool(self, m: int, dc: int, seed: int, index_base: int = 0) -> torch.Tensor:
+    out = torch.empty((m, dc), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_random_pool', self._lib.vzgp_random_pool(self._h, m, dc, index_base, seed, _ptr(out)))
+    self.synchronize()
+    return out
+
+  def random_search(self, m: int, acq: Acquisition, count: int, seed: int, index_base: int = 0):
+    a, keep = acq._c()
+    bx = np.zeros((count, self.dc), np.float64)
+    bs = np.zeros(count, np.float64)
+    bi = np.zeros(count, np.int64)
+    _lib.check('vzgp_random_search', self._lib.vzgp_random_search(
+        self._h, m, index_base, C.byref(a), count, seed, bx.ctypes.data_as(C.POINTER(C.c_double)),
+        bs.ctypes.data_as(C.POINTER(C.c_double)), bi.ctypes.data_as(C.POINTER(C.c_int64))))
+    del keep
+    return bx, bs, bi
+
+  def eagle_run(self, cfg: '_lib.EagleConfig', acq: Acquisition, count: int, seed: int,
+                prior: Optional[Sequence] = None):
+    a, keep = acq._c()
+    pt = self._dev(prior, torch.float64) if prior is not None and len(prior) > 0 else None
+    bx = np.zeros((count, self.dc), np.float64)
+    bs = np.zeros(count, np.float64)
+    _lib.check('vzgp_eagle_run', self._lib.vzgp_eagle_run(
+        self._h, C.byref(cfg), C.byref(a), _ptr(pt), 0 if pt is None else pt.shape[0], count, seed,
+        bx.ctypes.data_as(C.POINTER(C.c_double)), bs.ctypes.data_as(C.POINTER(C.c_double))))
+    del keep
+    return bx, bs
