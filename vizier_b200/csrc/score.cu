@@ -8,13 +8,14 @@
 // source of RandomVectorizedStrategy (random_vectorized_optimizer.py:78-100) and the top-k
 // bookkeeping of vectorized_base.py:544-587.
 //
-// One persistent CTA per SM walks 128-candidate tiles:
-//   phase 1  K* tile [128 x np] = Matern(x*, X) built 64 columns at a time from shared-memory
+// One persistent CTA per SM walks 64-candidate tiles:
+//   phase 1  K* tile [64 x np] = Matern(x*, X) built 64 columns at a time from shared-memory
 //            staged rows; mu = K* alpha and the L-inf trust-region distance are reduced on the
 //            fly; the tile goes to a CTA-private scratch (L2 resident, never re-read by others).
-//   phase 2  W = K* . Linv^T by 128x64 register-tiled fp64 GEMM blocks, exploiting that Linv is
-//            lower triangular (k <= j); each block is squared and row-summed in registers, W is
-//            never stored.
+//   phase 2  W = K* . Linv^T in 64 x 128 blocks on the FP64 tensor pipe (mma.sync m8n8k4 f64;
+//            tcgen05 has no f64 kind), operands staged by a 4-deep cp.async ring, exploiting that
+//            Linv is lower triangular (k <= j, all-zero fragments skipped); each block is squared
+//            and row-summed in registers, W is never stored.
 //   epilogue var = sf2 + sn2 - sum W^2 (clamped at 0), sigma, UCB, trust region, outputs.
 #include <climits>
 
@@ -23,7 +24,7 @@
 
 namespace vzgp {
 
-using GS = GemmCfg<128, 64, 16, 8, 4>;
+using G64 = GemmCfg<64, 64, 16, 4, 4>;  // phase-1 thread mapping (4x4 outputs per thread)
 
 struct ScoreArgs {
   const double* Xs;
@@ -42,7 +43,7 @@ struct ScoreArgs {
   int apply_tr;     // trust region modifies the score
   double radius;
   uint8_t tr_mask[kMaxDc];
-  double* scratch;  // [gridDim.x][128][np]
+  double* scratch;  // [gridDim.x][64][np]
   double* score;
   double* mu;
   double* sigma;
@@ -50,108 +51,198 @@ struct ScoreArgs {
   int* clamp_count;
 };
 
+// ---- cp.async / DMMA primitives -------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;  // src-size 0 -> destination is zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// D(8x8) += A(8x4, row) * B(4x8, col); lane l holds A[l/4][l%4], B[k=l%4][n=l/4],
+// D[l/4][2*(l%4)+{0,1}]  (PTX ISA, mma.m8n8k4 .f64 fragment layout).
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 16, 4-stage cp.async
+// ring.  8 warps as 4 (M) x 2 (N): each warp owns a 16 x 64 block = 2 x 8 DMMA tiles.
+constexpr int kTM = 64;          // candidates per tile
+constexpr int kBN = 128;         // output columns per pass
+constexpr int kBK = 16;          // k-slab
+constexpr int kStages = 4;
+constexpr int kLds = kBK + 4;    // smem row stride (doubles): 160 B rows, conflict-free fragment reads
+constexpr int kStageDoubles = (kTM + kBN) * kLds;
+
 template <bool WITH_LINF>
 __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
   extern __shared__ double smem[];
-  constexpr int LDA = 130, LDB = 66;
+  constexpr int LD = 66;
   const int dc = a.kp.dc, dk = a.kp.dk, np = a.np;
-  double* gemm_smem = smem;                              // GS::kSmemDoubles
-  double* sa = gemm_smem + GS::kSmemDoubles;             // [dc][LDA]
-  double* sb = sa + dc * LDA;                            // [dc][LDB]
-  double* s_alpha = sb + dc * LDB;                       // [64]
-  double* s_mu = s_alpha + 64;                           // [128]
-  double* s_linf = s_mu + 128;                           // [128]
-  int32_t* za = reinterpret_cast<int32_t*>(s_linf + 128);  // [dk][LDA]
-  int32_t* zb = za + dk * LDA;                           // [dk][LDB]
-  uint8_t* s_mask = reinterpret_cast<uint8_t*>(zb + dk * LDB);  // [kMaxDc]
+  double* ring = smem;                                   // [kStages][kTM + kBN][kLds]
+  double* sa = ring + kStages * kStageDoubles;           // [dc][LD]   candidate features (transposed)
+  double* sb = sa + dc * LD;                             // [dc][LD]   trial features
+  double* s_alpha = sb + dc * LD;                        // [64]
+  double* s_mu = s_alpha + 64;                           // [64]
+  double* s_linf = s_mu + 64;                            // [64]
+  double* s_rowsq = s_linf + 64;                         // [2][64]
+  int32_t* za = reinterpret_cast<int32_t*>(s_rowsq + 128);  // [dk][LD]
+  int32_t* zb = za + dk * LD;                            // [dk][LD]
+  uint8_t* s_mask = reinterpret_cast<uint8_t*>(zb + dk * LD);  // [kMaxDc]
 
-  const int tid = threadIdx.x;
-  const int ty = tid / 16, tx = tid % 16;
-  double* scr = a.scratch + (size_t)blockIdx.x * 128 * np;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid / 16, tx = tid % 16;      // phase-1 mapping
+  const int wm = warp >> 1, wn = warp & 1;     // phase-2 warp grid 4 x 2
+  const int fr = lane >> 2, fk = lane & 3;     // fragment row / k within a DMMA tile
+  double* scr = a.scratch + (size_t)blockIdx.x * kTM * np;
   if (tid < kMaxDc) s_mask[tid] = a.tr_mask[tid];
   int clamped = 0;
 
-  const int ntiles = (a.M + 127) / 128;
+  const int ntiles = (a.M + kTM - 1) / kTM;
+  const int nblocks = (np + kBN - 1) / kBN;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int m0 = tile * 128;
-    __syncthreads();  // previous tile's readers of sa / s_mu are done
-    stage_rows_T(a.Xs, a.M, dc, m0, 128, sa, LDA);
-    if (dk > 0) stage_rows_T_i32(a.Zs, a.M, dk, m0, 128, za, LDA);
+    const int m0 = tile * kTM;
+    __syncthreads();  // previous tile fully consumed (sa, s_mu, s_rowsq, ring)
+    stage_rows_T(a.Xs, a.M, dc, m0, kTM, sa, LD);
+    if (dk > 0) stage_rows_T_i32(a.Zs, a.M, dk, m0, kTM, za, LD);
 
     // ---------------- phase 1: K* tile, mean, trust-region distance ----------------
-    double mu_part[8], lmin[8];
+    double mu_part[4], lmin[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { mu_part[i] = 0.0; lmin[i] = INFINITY; }
+    for (int i = 0; i < 4; ++i) { mu_part[i] = 0.0; lmin[i] = INFINITY; }
     for (int jb = 0; jb < np / 64; ++jb) {
-      __syncthreads();  // sb / s_alpha free (and sa staged on the first pass)
-      stage_rows_T(a.X, np, dc, jb * 64, 64, sb, LDB);
-      if (dk > 0) stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LDB);
+      __syncthreads();
+      stage_rows_T(a.X, np, dc, jb * 64, 64, sb, LD);
+      if (dk > 0) stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD);
       if (tid < 64) s_alpha[tid] = a.alpha[jb * 64 + tid];
       __syncthreads();
-      double d2[8][4], lf[8][4];
-      tile_d2<GS, 8, 4, WITH_LINF>(sa, LDA, sb, LDB, za, LDA, zb, LDB, a.kp, s_mask, ty, tx, d2,
-                                   lf);
+      double d2[4][4], lf[4][4];
+      tile_d2<G64, 4, 4, WITH_LINF>(sa, LD, sb, LD, za, LD, zb, LD, a.kp, s_mask, ty, tx, d2, lf);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         double kv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int cj = GS::col_of(tx, j);
+          const int cj = G64::col_of(tx, j);
           const bool valid = (jb * 64 + cj) < a.n_valid;
           kv[j] = valid ? matern52(d2[i][j], a.kp.sf2) : 0.0;
           mu_part[i] = fma(kv[j], s_alpha[cj], mu_part[i]);
           if (WITH_LINF && valid) lmin[i] = fmin(lmin[i], lf[i][j]);
         }
-        double* dst = scr + (size_t)GS::row_of(ty, i) * np + jb * 64;
-        *reinterpret_cast<double2*>(dst + GS::col_of(tx, 0)) = make_double2(kv[0], kv[1]);
-        *reinterpret_cast<double2*>(dst + GS::col_of(tx, 2)) = make_double2(kv[2], kv[3]);
+        double* dst = scr + (size_t)G64::row_of(ty, i) * np + jb * 64;
+        *reinterpret_cast<double2*>(dst + G64::col_of(tx, 0)) = make_double2(kv[0], kv[1]);
+        *reinterpret_cast<double2*>(dst + G64::col_of(tx, 2)) = make_double2(kv[2], kv[3]);
       }
     }
-    // reduce over the 16 lanes (tx) that share the same rows
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {
         mu_part[i] += __shfl_xor_sync(0xffffffffu, mu_part[i], o);
         if (WITH_LINF) lmin[i] = fmin(lmin[i], __shfl_xor_sync(0xffffffffu, lmin[i], o));
       }
       if (tx == 0) {
-        s_mu[GS::row_of(ty, i)] = mu_part[i];
-        s_linf[GS::row_of(ty, i)] = lmin[i];
+        s_mu[G64::row_of(ty, i)] = mu_part[i];
+        s_linf[G64::row_of(ty, i)] = lmin[i];
       }
     }
-    __syncthreads();  // scratch tile written by this CTA is visible to all its threads
+    __syncthreads();  // this CTA's scratch tile is complete and visible to all its threads
 
-    // ---------------- phase 2: row sums of (K* Linv^T)^2 ----------------
-    double rowsq[8];
+    // ---------------- phase 2: row sums of (K* Linv^T)^2 on the DMMA pipe ----------------
+    // Slab (jb, ks): A = scratch[0:64, ks*16 : +16], B = Linv[jb*128 : +128, ks*16 : +16];
+    // block jb needs ks < min(np, (jb+1)*128)/16 because Linv is lower triangular.  The slab
+    // stream is flattened over blocks so the cp.async ring never drains between blocks.
+    auto slabs_in = [&](int jb) { int kend = (jb + 1) * kBN; if (kend > np) kend = np; return kend / kBK; };
+    auto issue = [&](int jb, int ks, int stage) {
+      double* As = ring + stage * kStageDoubles;
+      double* Bs = As + kTM * kLds;
+      const int k0 = ks * kBK;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) rowsq[i] = 0.0;
-    for (int jb = 0; jb < np / 64; ++jb) {
-      double acc[8][4];
+      for (int c = tid; c < kTM * 8; c += 256) {         // 64 rows x 8 chunks of 16 B
+        const int r = c >> 3, q = c & 7;
+        cp_async16(As + r * kLds + q * 2, scr + (size_t)r * np + k0 + q * 2, true);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int c = tid; c < kBN * 8; c += 256) {         // 128 rows x 8 chunks
+        const int r = c >> 3, q = c & 7;
+        const int gr = jb * kBN + r;
+        const bool ok = gr < np;
+        cp_async16(Bs + r * kLds + q * 2, a.Linv + (size_t)(ok ? gr : 0) * a.ldi + k0 + q * 2, ok);
+      }
+    };
+    int ljb = 0, lks = 0;  // load cursor
+    auto advance = [&]() { if (++lks == slabs_in(ljb)) { lks = 0; ++ljb; } };
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-      gemm_mainloop<128, 64, 16, 8, 4, false, false>(scr, np, 0, a.Linv, a.ldi, jb * 64, 0,
-                                                     (jb + 1) * 64, acc, gemm_smem);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rowsq[i] = fma(acc[i][j], acc[i][j], rowsq[i]);
+    for (int s = 0; s < kStages - 1; ++s) {
+      if (ljb < nblocks) { issue(ljb, lks, s); advance(); }
+      cp_async_commit();
     }
+    double rowsq[2] = {0.0, 0.0};
+    int stage = 0;
+    for (int jb = 0; jb < nblocks; ++jb) {
+      double acc[2][8][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+      for (int f = 0; f < 2; ++f)
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) rowsq[i] += __shfl_xor_sync(0xffffffffu, rowsq[i], o);
+        for (int g = 0; g < 8; ++g) { acc[f][g][0] = 0.0; acc[f][g][1] = 0.0; }
+      const int nsl = slabs_in(jb);
+      const int col_base = jb * kBN + wn * 64;   // first output column of this warp
+      for (int ks = 0; ks < nsl; ++ks) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        {  // refill the stage consumed in the previous iteration
+          int ps = stage + kStages - 1; if (ps >= kStages) ps -= kStages;
+          if (ljb < nblocks) { issue(ljb, lks, ps); advance(); }
+          cp_async_commit();
+        }
+        const double* As = ring + stage * kStageDoubles + (wm * 16 + fr) * kLds + fk;
+        const double* Bs = ring + stage * kStageDoubles + kTM * kLds + (wn * 64 + fr) * kLds + fk;
+        const int k0 = ks * kBK;
+        // columns of this warp that can be non-zero for this slab: Linv[c, k] = 0 for k > c
+        const bool diag = (k0 + kBK - 1) > col_base;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double a0 = As[q * 4], a1 = As[8 * kLds + q * 4];
+          double b[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) b[g] = Bs[g * 8 * kLds + q * 4];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (diag && (k0 + q * 4) > (col_base + g * 8 + 7)) continue;  // all-zero B fragment
+            dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0, b[g]);
+            dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1, b[g]);
+          }
+        }
+        if (++stage == kStages) stage = 0;
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          rowsq[f] = fma(acc[f][g][0], acc[f][g][0], rowsq[f]);
+          rowsq[f] = fma(acc[f][g][1], acc[f][g][1], rowsq[f]);
+        }
     }
+    cp_async_wait<0>();
+    // combine the 4 lanes that share a fragment row, then the two N-warps through smem
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      rowsq[f] += __shfl_xor_sync(0xffffffffu, rowsq[f], 1);
+      rowsq[f] += __shfl_xor_sync(0xffffffffu, rowsq[f], 2);
+      if (fk == 0) s_rowsq[wn * 64 + wm * 16 + f * 8 + fr] = rowsq[f];
+    }
+    __syncthreads();
     // ---------------- epilogue ----------------
-    if (tx == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = GS::row_of(ty, i);
-        const int m = m0 + r;
-        if (m >= a.M) continue;
-        double var = a.kp.sf2 - rowsq[i] + a.sn2;
+    if (tid < kTM) {
+      const int r = tid, m = m0 + r;
+      if (m < a.M) {
+        const double rs = s_rowsq[r] + s_rowsq[64 + r];
+        double var = a.kp.sf2 - rs + a.sn2;
         if (var < 0.0) { var = 0.0; ++clamped; }
         const double sd = sqrt(var);
         const double mean = s_mu[r];
@@ -172,17 +263,16 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
 }
 
 size_t score_smem_bytes(int dc, int dk) {
-  return sizeof(double) * (GS::kSmemDoubles + dc * (130 + 66) + 64 + 128 + 128) +
-         sizeof(int32_t) * dk * (130 + 66) + kMaxDc;
+  return sizeof(double) * (kStages * kStageDoubles + dc * 2 * 66 + 64 * 3 + 128) +
+         sizeof(int32_t) * dk * 2 * 66 + kMaxDc;
 }
 
 int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                  double* score, double* mu, double* sigma, double* linf) {
   if (M <= 0) return 0;
-  const int ntiles = (M + 127) / 128;
+  const int ntiles = (M + kTM - 1) / kTM;
   const int grid = ntiles < h->sm_count ? ntiles : h->sm_count;
-  VZ_TRY(h->scratch.reserve((size_t)grid * 128 * h->np * sizeof(double)));
-  VZ_TRY(h->small.reserve(4096));
+  VZ_TRY(h->scratch.reserve((size_t)grid * kTM * h->np * sizeof(double)));
   ScoreArgs a;
   a.Xs = Xs; a.Zs = Zs; a.M = M;
   a.X = h->X.as<double>(); a.Z = h->Z.as<int32_t>();
