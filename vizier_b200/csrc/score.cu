@@ -24,7 +24,8 @@
 
 namespace vzgp {
 
-using G64 = GemmCfg<64, 64, 16, 4, 4>;  // phase-1 thread mapping (4x4 outputs per thread)
+using GP1 = GemmCfg<64, 64, 16, 2, 4>;  // phase-1 thread mapping: 512 threads, 2x4 outputs each
+constexpr int kThreads = 512;
 
 struct ScoreArgs {
   const double* Xs;
@@ -71,7 +72,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 }
 
 // Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 16, 4-stage cp.async
-// ring.  8 warps as 4 (M) x 2 (N): each warp owns a 16 x 64 block = 2 x 8 DMMA tiles.
+// ring.  16 warps as 4 (M) x 4 (N): each warp owns a 16 x 32 block = 2 x 4 DMMA tiles.
 constexpr int kTM = 64;          // candidates per tile
 constexpr int kBN = 128;         // output columns per pass
 constexpr int kBK = 16;          // k-slab
@@ -80,7 +81,7 @@ constexpr int kLds = kBK + 4;    // smem row stride (doubles): 160 B rows, confl
 constexpr int kStageDoubles = (kTM + kBN) * kLds;
 
 template <bool WITH_LINF>
-__global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
   extern __shared__ double smem[];
   constexpr int LD = 66;
   const int dc = a.kp.dc, dk = a.kp.dk, np = a.np;
@@ -90,14 +91,14 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
   double* s_alpha = sb + dc * LD;                        // [64]
   double* s_mu = s_alpha + 64;                           // [64]
   double* s_linf = s_mu + 64;                            // [64]
-  double* s_rowsq = s_linf + 64;                         // [2][64]
-  int32_t* za = reinterpret_cast<int32_t*>(s_rowsq + 128);  // [dk][LD]
+  double* s_rowsq = s_linf + 64;                         // [4][64]
+  int32_t* za = reinterpret_cast<int32_t*>(s_rowsq + 256);  // [dk][LD]
   int32_t* zb = za + dk * LD;                            // [dk][LD]
   uint8_t* s_mask = reinterpret_cast<uint8_t*>(zb + dk * LD);  // [kMaxDc]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ty = tid / 16, tx = tid % 16;      // phase-1 mapping
-  const int wm = warp >> 1, wn = warp & 1;     // phase-2 warp grid 4 x 2
+  const int ty = tid / 16, tx = tid % 16;      // phase-1 mapping (32 x 16 threads)
+  const int wm = warp & 3, wn = warp >> 2;     // phase-2 warp grid 4 (M) x 2 (N); each SM sub-partition gets one warp of each N half
   const int fr = lane >> 2, fk = lane & 3;     // fragment row / k within a DMMA tile
   double* scr = a.scratch + (size_t)blockIdx.x * kTM * np;
   if (tid < kMaxDc) s_mask[tid] = a.tr_mask[tid];
@@ -112,43 +113,43 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
     if (dk > 0) stage_rows_T_i32(a.Zs, a.M, dk, m0, kTM, za, LD);
 
     // ---------------- phase 1: K* tile, mean, trust-region distance ----------------
-    double mu_part[4], lmin[4];
+    double mu_part[2], lmin[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { mu_part[i] = 0.0; lmin[i] = INFINITY; }
+    for (int i = 0; i < 2; ++i) { mu_part[i] = 0.0; lmin[i] = INFINITY; }
     for (int jb = 0; jb < np / 64; ++jb) {
       __syncthreads();
       stage_rows_T(a.X, np, dc, jb * 64, 64, sb, LD);
       if (dk > 0) stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD);
       if (tid < 64) s_alpha[tid] = a.alpha[jb * 64 + tid];
       __syncthreads();
-      double d2[4][4], lf[4][4];
-      tile_d2<G64, 4, 4, WITH_LINF>(sa, LD, sb, LD, za, LD, zb, LD, a.kp, s_mask, ty, tx, d2, lf);
+      double d2[2][4], lf[2][4];
+      tile_d2<GP1, 2, 4, WITH_LINF>(sa, LD, sb, LD, za, LD, zb, LD, a.kp, s_mask, ty, tx, d2, lf);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         double kv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int cj = G64::col_of(tx, j);
+          const int cj = GP1::col_of(tx, j);
           const bool valid = (jb * 64 + cj) < a.n_valid;
           kv[j] = valid ? matern52(d2[i][j], a.kp.sf2) : 0.0;
           mu_part[i] = fma(kv[j], s_alpha[cj], mu_part[i]);
           if (WITH_LINF && valid) lmin[i] = fmin(lmin[i], lf[i][j]);
         }
-        double* dst = scr + (size_t)G64::row_of(ty, i) * np + jb * 64;
-        *reinterpret_cast<double2*>(dst + G64::col_of(tx, 0)) = make_double2(kv[0], kv[1]);
-        *reinterpret_cast<double2*>(dst + G64::col_of(tx, 2)) = make_double2(kv[2], kv[3]);
+        double* dst = scr + (size_t)GP1::row_of(ty, i) * np + jb * 64;
+        *reinterpret_cast<double2*>(dst + GP1::col_of(tx, 0)) = make_double2(kv[0], kv[1]);
+        *reinterpret_cast<double2*>(dst + GP1::col_of(tx, 2)) = make_double2(kv[2], kv[3]);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {
         mu_part[i] += __shfl_xor_sync(0xffffffffu, mu_part[i], o);
         if (WITH_LINF) lmin[i] = fmin(lmin[i], __shfl_xor_sync(0xffffffffu, lmin[i], o));
       }
       if (tx == 0) {
-        s_mu[G64::row_of(ty, i)] = mu_part[i];
-        s_linf[G64::row_of(ty, i)] = lmin[i];
+        s_mu[GP1::row_of(ty, i)] = mu_part[i];
+        s_linf[GP1::row_of(ty, i)] = lmin[i];
       }
     }
     __syncthreads();  // this CTA's scratch tile is complete and visible to all its threads
@@ -163,12 +164,12 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
       double* Bs = As + kTM * kLds;
       const int k0 = ks * kBK;
 #pragma unroll
-      for (int c = tid; c < kTM * 8; c += 256) {         // 64 rows x 8 chunks of 16 B
+      for (int c = tid; c < kTM * 8; c += kThreads) {         // 64 rows x 8 chunks of 16 B
         const int r = c >> 3, q = c & 7;
         cp_async16(As + r * kLds + q * 2, scr + (size_t)r * np + k0 + q * 2, true);
       }
 #pragma unroll
-      for (int c = tid; c < kBN * 8; c += 256) {         // 128 rows x 8 chunks
+      for (int c = tid; c < kBN * 8; c += kThreads) {         // 128 rows x 8 chunks
         const int r = c >> 3, q = c & 7;
         const int gr = jb * kBN + r;
         const bool ok = gr < np;
@@ -185,13 +186,13 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
     double rowsq[2] = {0.0, 0.0};
     int stage = 0;
     for (int jb = 0; jb < nblocks; ++jb) {
-      double acc[2][8][2];
+      double acc[2][4][2];
 #pragma unroll
       for (int f = 0; f < 2; ++f)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) { acc[f][g][0] = 0.0; acc[f][g][1] = 0.0; }
+        for (int g = 0; g < 4; ++g) { acc[f][g][0] = 0.0; acc[f][g][1] = 0.0; }
       const int nsl = slabs_in(jb);
-      const int col_base = jb * kBN + wn * 64;   // first output column of this warp
+      const int col_base = jb * kBN + wn * 32;   // first output column of this warp
       for (int ks = 0; ks < nsl; ++ks) {
         cp_async_wait<kStages - 2>();
         __syncthreads();
@@ -201,21 +202,22 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
           cp_async_commit();
         }
         const double* As = ring + stage * kStageDoubles + (wm * 16 + fr) * kLds + fk;
-        const double* Bs = ring + stage * kStageDoubles + kTM * kLds + (wn * 64 + fr) * kLds + fk;
+        const double* Bs = ring + stage * kStageDoubles + kTM * kLds + (wn * 32 + fr) * kLds + fk;
         const int k0 = ks * kBK;
-        // columns of this warp that can be non-zero for this slab: Linv[c, k] = 0 for k > c
-        const bool diag = (k0 + kBK - 1) > col_base;
+        // Linv[c, k] = 0 for k > c: a slab entirely right of this warp's 32 columns contributes
+        // nothing (warp-uniform skip; happens only inside the diagonal 128-block).
+        if (k0 <= col_base + 31) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const double a0 = As[q * 4], a1 = As[8 * kLds + q * 4];
-          double b[8];
+          for (int q = 0; q < 4; ++q) {
+            const double a0 = As[q * 4], a1 = As[8 * kLds + q * 4];
+            double b[4];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) b[g] = Bs[g * 8 * kLds + q * 4];
+            for (int g = 0; g < 4; ++g) b[g] = Bs[g * 8 * kLds + q * 4];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (diag && (k0 + q * 4) > (col_base + g * 8 + 7)) continue;  // all-zero B fragment
-            dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0, b[g]);
-            dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1, b[g]);
+            for (int g = 0; g < 4; ++g) {
+              dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0, b[g]);
+              dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1, b[g]);
+            }
           }
         }
         if (++stage == kStages) stage = 0;
@@ -223,13 +225,13 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
 #pragma unroll
       for (int f = 0; f < 2; ++f)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           rowsq[f] = fma(acc[f][g][0], acc[f][g][0], rowsq[f]);
           rowsq[f] = fma(acc[f][g][1], acc[f][g][1], rowsq[f]);
         }
     }
     cp_async_wait<0>();
-    // combine the 4 lanes that share a fragment row, then the two N-warps through smem
+    // combine the 4 lanes that share a fragment row, then the four N-warps through smem
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       rowsq[f] += __shfl_xor_sync(0xffffffffu, rowsq[f], 1);
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
     if (tid < kTM) {
       const int r = tid, m = m0 + r;
       if (m < a.M) {
-        const double rs = s_rowsq[r] + s_rowsq[64 + r];
+        const double rs = (s_rowsq[r] + s_rowsq[64 + r]) + (s_rowsq[128 + r] + s_rowsq[192 + r]);
         double var = a.kp.sf2 - rs + a.sn2;
         if (var < 0.0) { var = 0.0; ++clamped; }
         const double sd = sqrt(var);
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(256, 1) k_score(const ScoreArgs a) {
 }
 
 size_t score_smem_bytes(int dc, int dk) {
-  return sizeof(double) * (kStages * kStageDoubles + dc * 2 * 66 + 64 * 3 + 128) +
+  return sizeof(double) * (kStages * kStageDoubles + dc * 2 * 66 + 64 * 3 + 256) +
          sizeof(int32_t) * dk * 2 * 66 + kMaxDc;
 }
 
@@ -292,10 +294,10 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
   const size_t sm = score_smem_bytes(h->dc, h->dk);
   if (need_linf) {
     VZ_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_score<true><<<grid, 256, sm, h->stream>>>(a);
+    k_score<true><<<grid, kThreads, sm, h->stream>>>(a);
   } else {
     VZ_CUDA(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_score<false><<<grid, 256, sm, h->stream>>>(a);
+    k_score<false><<<grid, kThreads, sm, h->stream>>>(a);
   }
   VZ_CHECK_LAUNCH();
   h->launches++;
