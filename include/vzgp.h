@@ -142,6 +142,13 @@ int vzgp_clamped_count(vzgp_handle* h, int64_t* count_out);
 int vzgp_score_host(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
                     const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf);
 
+/* Joint posterior over M query points (Predictor.predict/sample, gp_bandit.py:562-627;
+ * acquisitions.sample_from_predictive): mean [M] and covariance [M x ldc] (device outputs),
+ * cov = K** - (K* Linv^T)(K* Linv^T)^T (+ sn2 on the diagonal if add_noise, the TFP
+ * posterior_predictive default).  Asynchronous on the handle's stream. */
+int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,
+                   double* mean, double* cov, int ldc);
+
 /* Top-`count` of score[0..M) (device), descending, ties -> lowest index, NaN
  * treated as -inf (vectorized_base.py:580,598).  idx_out [count] int64 and
  * val_out [count] are HOST. */

@@ -1,0 +1,75 @@
+"""CPU tests of the designer's host logic (no GPU): converters, seeding, validation."""
+import numpy as np
+import pytest
+
+from vizier_b200 import converters, vz
+from vizier_b200 import acquisitions as acq_lib
+
+
+def _problem():
+  p = vz.ProblemStatement()
+  r = p.search_space.root
+  r.add_float_param('lr', 1e-4, 1e-1, scale_type=vz.ScaleType.LOG)
+  r.add_float_param('x', -5.0, 5.0)
+  r.add_float_param('rl', 1.0, 10.0, scale_type=vz.ScaleType.REVERSE_LOG)
+  r.add_int_param('layers', 1, 5)
+  r.add_discrete_param('bs', [16, 32, 128])
+  r.add_categorical_param('opt', ['adam', 'sgd'])
+  p.metric_information.append(vz.MetricInformation(name='obj', goal=vz.ObjectiveMetricGoal.MINIMIZE))
+  return p
+
+
+def test_converter_scaling_and_round_trip():
+  p = _problem()
+  c = converters.TrialToModelInputConverter.from_problem(p)
+  assert (c.n_continuous, c.n_categorical) == (5, 1)
+  t = vz.Trial(parameters={'lr': 1e-3, 'x': 0.0, 'rl': 10.0, 'layers': 3, 'bs': 32, 'opt': 'sgd'})
+  t.complete(vz.Measurement({'obj': 2.0}))
+  bad = vz.Trial(parameters={'lr': 1e-1, 'x': 5.0, 'rl': 1.0, 'layers': 5, 'bs': 128, 'opt': 'unknown'})
+  bad.complete(vz.Measurement(), infeasibility_reason='diverged')
+  (cont, cat), y = c.to_xy([t, bad])
+  # LOG: (log x - log lo)/(log hi - log lo);  LINEAR; REVERSE_LOG: 1 - (log(lo+hi-x) - log lo)/(...)
+  np.testing.assert_allclose(cont[0], [1 / 3, 0.5, 1.0, 0.5, (32 - 16) / (128 - 16)], rtol=1e-12)
+  np.testing.assert_allclose(cont[1], [1.0, 1.0, 0.0, 1.0, 1.0], atol=1e-12)
+  assert cat.dtype == np.int32 and cat[:, 0].tolist() == [1, 2]  # 'sgd' -> 1, unknown -> len(feasible)
+  np.testing.assert_array_equal(y[:, 0], [-2.0, np.nan])      # sign flipped for MINIMIZE; infeasible -> NaN
+  back = c.to_parameters(cont, cat)
+  assert back[0].as_dict() == pytest.approx({'lr': 1e-3, 'x': 0.0, 'rl': 10.0, 'layers': 3, 'bs': 32.0, 'opt': 'sgd'})
+  assert 'opt' not in back[1].as_dict()  # out-of-vocabulary index maps to no value
+  # continuified values round to the nearest feasible value and DOUBLEs are clipped
+  q = c.to_parameters(np.array([[0.5, 1.3, 0.5, 0.6, 0.2]]), np.array([[0]], np.int32))[0].as_dict()
+  assert q['layers'] == 3 and q['bs'] == 32.0 and q['x'] == 5.0 and q['opt'] == 'adam'
+
+
+def test_continuous_feasible_values_and_trust_region_mask():
+  p = _problem()
+  c = converters.TrialToModelInputConverter.from_problem(p)
+  fv = c.continuous_feasible_values(1000)
+  assert [len(v) for v in fv] == [0, 0, 0, 5, 3]
+  mask = acq_lib.trust_region_dim_mask(fv)
+  # ints 1..5 scaled have gaps 0.25 > 0.2 -> excluded; bs has a gap of 0.857 -> excluded
+  assert mask.tolist() == [True, True, True, False, False]
+  a = acq_lib.make_acquisition(10, fv, 5, 1)
+  assert a.trust_radius == pytest.approx(0.2 + 0.3 * 10 / (5 * (3 + 1 + 1)))
+
+
+def test_designer_validation_errors_need_no_gpu():
+  from vizier_b200.designers import gp_bandit
+  with pytest.raises(ValueError):
+    gp_bandit.VizierGPBandit(vz.ProblemStatement())
+  p = _problem()
+  p.metric_information.append(vz.MetricInformation(name='m2', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  with pytest.raises(NotImplementedError):
+    gp_bandit.VizierGPBandit(p)
+
+
+def test_seed_trials_centre_then_quasi_random():
+  from vizier_b200.designers import gp_bandit
+  d = gp_bandit.VizierGPBandit.from_problem(_problem(), seed=1, num_seed_trials=3)
+  s = d.suggest(3)
+  assert len(s) == 3
+  centre = s[0].parameters.as_dict()
+  assert centre['x'] == 0.0 and centre['layers'] == 3 and s[0].metadata['seeded'] == 'center'
+  space = _problem().search_space
+  for sug in s:
+    assert space.contains(sug.parameters)

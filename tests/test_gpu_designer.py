@@ -1,0 +1,105 @@
+"""GPU tests of the drop-in designer, modelled on the reference's gp_bandit_test.py:
+runs (`:130-235`), prediction accuracy (`:373-379`), convergence (`:513-544`)."""
+import json
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from vizier_b200 import optimizers as vb  # noqa: E402
+from vizier_b200 import profiler, vz  # noqa: E402
+from vizier_b200.designers import gp_bandit  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _need_cuda():
+  if not torch.cuda.is_available():
+    pytest.skip('no CUDA device')
+
+
+def _problem(d=4, lo=-5.0, hi=5.0, goal=vz.ObjectiveMetricGoal.MAXIMIZE):
+  p = vz.ProblemStatement()
+  for i in range(d):
+    p.search_space.root.add_float_param(f'x{i}', lo, hi)
+  p.metric_information.append(vz.MetricInformation(name='obj', goal=goal))
+  return p
+
+
+def _complete(suggestions, f, start_id):
+  out = []
+  for i, s in enumerate(suggestions):
+    t = s.to_trial(start_id + i)
+    x = np.array([t.parameters[k].value for k in sorted(t.parameters)])
+    t.complete(vz.Measurement({'obj': float(f(x))}))
+    out.append(t)
+  return out
+
+
+small_opt = vb.VectorizedOptimizerFactory(strategy_factory=vb.VectorizedEagleStrategyFactory(),
+                                          max_evaluations=2000, suggestion_batch_size=25)
+
+
+def test_suggest_update_loop_and_metadata():
+  p = _problem(4)
+  d = gp_bandit.VizierGPBandit.from_problem(p, seed=0, acquisition_optimizer_factory=small_opt)
+  f = lambda x: -np.sum((x - 1.0) ** 2)
+  tid = 1
+  with profiler.collect_events() as ev:
+    for _ in range(6):
+      sugg = d.suggest(2)
+      assert len(sugg) == 2
+      for s in sugg:
+        assert p.search_space.contains(s.parameters)
+      trials = _complete(sugg, f, tid); tid += len(trials)
+      d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  assert 'VizierGPBandit.suggest' in ev and 'VizierGPBandit._update_gp' in ev
+  md = sugg[0].metadata
+  info = json.loads(md.ns('devinfo')['acquisition_optimization'])
+  for k in ('acquisition', 'mean', 'stddev', 'raw_acquisition', 'linf_distance', 'radius'):
+    assert k in info and np.isfinite(info[k])
+  assert 'time_spent' in md.ns('oss_gp_bandit').ns('devinfo')
+
+
+def test_prediction_accuracy_on_quadratic():
+  # gp_bandit_test.py:373-379: 100 quasi-random points of f(x)=x^2 on [-1,1]; |mu(0) - f(0)| < 2e-2
+  p = _problem(1, -1.0, 1.0)
+  d = gp_bandit.VizierGPBandit.from_problem(p, seed=1, acquisition_optimizer_factory=small_opt)
+  xs = (np.arange(100) + 0.5) / 100 * 2 - 1
+  trials = [vz.Trial(parameters={'x0': float(x)}, id=i + 1).complete(vz.Measurement({'obj': float(x * x)})) for i, x in enumerate(xs)]
+  d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  pred = d.predict([vz.TrialSuggestion({'x0': 0.0}), vz.TrialSuggestion({'x0': 0.5})], num_samples=2000)
+  assert pred.mean.shape == (2,) and pred.stddev.shape == (2,)
+  assert abs(pred.mean[0] - 0.0) < 2e-2
+  assert abs(pred.mean[1] - 0.25) < 3e-2
+  s = d.sample([vz.TrialSuggestion({'x0': 0.0})], num_samples=7)
+  assert s.shape == (7, 1) and np.all(np.isfinite(s))
+
+
+def test_minimisation_converges_faster_than_random():
+  p = _problem(3, 0.0, 1.0, goal=vz.ObjectiveMetricGoal.MINIMIZE)
+  f = lambda x: np.sum((x - 0.7) ** 2)
+  d = gp_bandit.VizierGPBandit.from_problem(p, seed=3, acquisition_optimizer_factory=small_opt)
+  best = np.inf
+  tid = 1
+  for _ in range(15):
+    trials = _complete(d.suggest(1), f, tid); tid += 1
+    best = min(best, trials[0].final_measurement.metrics['obj'].value)
+    d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  rng = np.random.default_rng(0)
+  rand_best = min(f(rng.uniform(size=3)) for _ in range(15))
+  assert best < 0.02 and best < rand_best
+
+
+def test_random_pool_optimizer_factory():
+  # the C2 shape through the designer API: score one M-candidate uniform pool, take the top `count`
+  p = _problem(5, 0.0, 1.0)
+  opt = vb.VectorizedOptimizerFactory(strategy_factory=vb.random_strategy_factory, max_evaluations=20_000, suggestion_batch_size=20_000)
+  d = gp_bandit.VizierGPBandit.from_problem(p, seed=5, acquisition_optimizer_factory=opt)
+  rng = np.random.default_rng(2)
+  trials = [vz.Trial(parameters={f'x{j}': float(v) for j, v in enumerate(x)}, id=i + 1).complete(
+      vz.Measurement({'obj': float(-np.sum((x - 0.4) ** 2))})) for i, x in enumerate(rng.uniform(size=(30, 5)))]
+  d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  sugg = d.suggest(3)
+  assert len(sugg) == 3 and len({tuple(sorted(s.parameters.as_dict().items())) for s in sugg}) == 3

@@ -512,4 +512,35 @@ int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq*
   return 0;
 }
 
+int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,
+                   double* mean, double* cov, int ldc) {
+  VZ_ARG(h && mean && cov, "handle / outputs");
+  if (!h->fitted) { set_error("vzgp_posterior before vzgp_fit"); return VZGP_ERR_STATE; }
+  VZ_ARG(M >= 1 && ldc >= M, "M, ldc");
+  VZ_ARG(Xs != nullptr || h->dc == 0, "Xs");
+  Guard g(h->device);
+  const int np = h->np, mp = round_up(M, kBlk);
+  // layout in Kinv buffer: Ks [mp x np] | W [mp x np] | C [mp x mp] | Xs padded [mp x dc] | mean [mp]
+  const size_t nks = (size_t)mp * np, nc = (size_t)mp * mp, nx = (size_t)mp * (h->dc > 0 ? h->dc : 1);
+  VZ_TRY(h->Kinv.reserve(sizeof(double) * (2 * nks + nc + nx + mp) + sizeof(int32_t) * (size_t)mp * (h->dk > 0 ? h->dk : 1)));
+  double* Ks = h->Kinv.as<double>();
+  double* W = Ks + nks;
+  double* C = W + nks;
+  double* Xp = C + nc;
+  double* mu = Xp + nx;
+  int32_t* Zp = reinterpret_cast<int32_t*>(mu + mp);
+  VZ_CUDA(cudaMemsetAsync(Ks, 0, sizeof(double) * nks, h->stream));
+  if (h->dc > 0) VZ_TRY(launch_pad_rows(h, Xs, M, h->dc, mp, Xp));
+  if (h->dk > 0) VZ_TRY(launch_pad_rows_i32(h, Zs, M, h->dk, mp, Zp));
+  VZ_TRY(launch_cross_kernel(h, Xp, Zp, M, h->X.as<double>(), h->Z.as<int32_t>(), np, h->n_valid, h->kp, Ks, np));
+  VZ_TRY(launch_cross_kernel(h, Xp, Zp, mp, Xp, Zp, mp, mp, h->kp, C, mp));
+  VZ_TRY(launch_gemm_nt_tri(h, Ks, np, mp, h->Linv.as<double>(), np, np, W, np));
+  VZ_TRY(launch_cov_update(h, W, np, np, mp, C, mp, add_noise ? h->sn2 : 0.0));
+  VZ_TRY(launch_gemv_rows(h, Ks, np, mp, h->alpha.as<double>(), mu, 0, np));
+  VZ_CUDA(cudaMemcpy2DAsync(cov, sizeof(double) * ldc, C, sizeof(double) * mp, sizeof(double) * M, M,
+                            cudaMemcpyDeviceToDevice, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(mean, mu, sizeof(double) * M, cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
 }  // extern "C"

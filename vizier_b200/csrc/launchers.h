@@ -18,7 +18,7 @@ int launch_copy_lower_shift(vzgp_handle* h, const double* A, int lda, int n_src,
                             double* L, int ldl);
 int launch_diag_inv(vzgp_handle* h, const double* L, int ld, double* Linv, int ldi, int np);
 int launch_gemv_rows(vzgp_handle* h, const double* M, int ld, int np, const double* v, double* out,
-                     int lower_only);
+                     int lower_only, int ncols = 0);
 int launch_gemv_lower_T(vzgp_handle* h, const double* M, int ld, int np, const double* v, double* out);
 int launch_residual(vzgp_handle* h, const double* Ky, int ld, int np, const double* y, const double* a,
                     double* r);
@@ -27,6 +27,11 @@ int launch_pad_vector(vzgp_handle* h, const double* src, int n, int n_valid, int
 int launch_pad_rows(vzgp_handle* h, const double* src, int n, int d, int np, double* dst);
 int launch_pad_rows_i32(vzgp_handle* h, const int32_t* src, int n, int d, int np, int32_t* dst);
 int launch_logdet_quad(vzgp_handle* h, const double* L, int ld, int n_valid, const double* w, double* out);
+
+int launch_gemm_nt_tri(vzgp_handle* h, const double* A, int lda, int mp, const double* B, int ldb, int np,
+                       double* C, int ldc);
+int launch_cov_update(vzgp_handle* h, const double* W, int ldw, int kdim, int mp, double* C, int ldc,
+                      double diag_add);
 
 int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
                           const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,

@@ -293,12 +293,12 @@ __global__ void __launch_bounds__(256) k_lauum(const double* __restrict__ Linv, 
 // Matrix-vector helpers (one warp per row), used for alpha = Linv^T (Linv y) and refinement.
 // ---------------------------------------------------------------------------
 // out[i] = sum_{j in [j_lo(i), j_hi(i))} M[i,j] * v[j];  mode 0: full row [0,np); 1: j <= i.
-__global__ void k_gemv_rows(const double* __restrict__ M, int ld, int np, const double* __restrict__ v,
-                            double* __restrict__ out, int lower_only) {
+__global__ void k_gemv_rows(const double* __restrict__ M, int ld, int nrows, int ncols,
+                            const double* __restrict__ v, double* __restrict__ out, int lower_only) {
   int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x & 31;
-  if (row >= np) return;
-  int hi = lower_only ? row + 1 : np;
+  if (row >= nrows) return;
+  int hi = lower_only ? row + 1 : ncols;
   double s = 0.0;
   for (int j = lane; j < hi; j += 32) s = fma(M[(size_t)row * ld + j], v[j], s);
 #pragma unroll
@@ -512,8 +512,8 @@ int launch_diag_inv(vzgp_handle* h, const double* L, int ld, double* Linv, int l
 }
 
 int launch_gemv_rows(vzgp_handle* h, const double* M, int ld, int np, const double* v, double* out,
-                     int lower_only) {
-  k_gemv_rows<<<(np + 7) / 8, 256, 0, h->stream>>>(M, ld, np, v, out, lower_only);
+                     int lower_only, int ncols) {
+  k_gemv_rows<<<(np + 7) / 8, 256, 0, h->stream>>>(M, ld, np, ncols > 0 ? ncols : np, v, out, lower_only);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;
@@ -562,6 +562,60 @@ int launch_pad_rows_i32(vzgp_handle* h, const int32_t* src, int n, int d, int np
 int launch_logdet_quad(vzgp_handle* h, const double* L, int ld, int n_valid, const double* w,
                        double* out) {
   k_logdet_quad<<<1, 256, 0, h->stream>>>(L, ld, n_valid, w, out);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------
+// Joint posterior over a few query points (predict/sample path, not the hot loop):
+//   W = K* Linv^T  (triangular: k <= j),   cov = K** - W W^T.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gemm_nt_tri(const double* __restrict__ A, int lda,
+                                                     const double* __restrict__ B, int ldb,
+                                                     double* __restrict__ C, int ldc) {
+  extern __shared__ double smem[];
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  double acc[4][4] = {};
+  gemm_mainloop<64, 64, 16, 4, 4, false, false>(A, lda, i0, B, ldb, j0, 0, j0 + 64, acc, smem);
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; j += 2)
+      *reinterpret_cast<double2*>(C + (size_t)(i0 + G64::row_of(ty, i)) * ldc + j0 + G64::col_of(tx, j)) =
+          make_double2(acc[i][j], acc[i][j + 1]);
+}
+
+// C[i,j] = C[i,j] - sum_k W[i,k] W[j,k] + diag_add*[i==j]
+__global__ void __launch_bounds__(256) k_cov_update(const double* __restrict__ W, int ldw, int kdim,
+                                                    double* __restrict__ C, int ldc, double diag_add) {
+  extern __shared__ double smem[];
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  double acc[4][4] = {};
+  gemm_mainloop<64, 64, 16, 4, 4, false, false>(W, ldw, i0, W, ldw, j0, 0, kdim, acc, smem);
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = i0 + G64::row_of(ty, i), gj = j0 + G64::col_of(tx, j);
+      double* p = C + (size_t)gi * ldc + gj;
+      *p = *p - acc[i][j] + (gi == gj ? diag_add : 0.0);
+    }
+}
+
+int launch_gemm_nt_tri(vzgp_handle* h, const double* A, int lda, int mp, const double* B, int ldb,
+                       int np, double* C, int ldc) {
+  k_gemm_nt_tri<<<dim3(np / 64, mp / 64), 256, G64::kSmemBytes, h->stream>>>(A, lda, B, ldb, C, ldc);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+int launch_cov_update(vzgp_handle* h, const double* W, int ldw, int kdim, int mp, double* C, int ldc,
+                      double diag_add) {
+  k_cov_update<<<dim3(mp / 64, mp / 64), 256, G64::kSmemBytes, h->stream>>>(W, ldw, kdim, C, ldc, diag_add);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;

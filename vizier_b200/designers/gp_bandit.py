@@ -1,0 +1,248 @@
+"""`VizierGPBandit`: the GP-UCB designer, with the GP stack running in libvzgp (CUDA, sm_100a).
+
+Drop-in for vizier/_src/algorithms/designers/gp_bandit.py:88-641 on the single-metric default
+path: same constructor keywords, `update` / `suggest` / `predict` / `sample` / `from_problem`,
+same metadata keys, same errors for unsupported search spaces.  What runs where:
+
+  host (NumPy, O(N*D))   trials -> scaled features (converters.py), label warping
+                         (output_warpers.py), SciPy L-BFGS-B driver (ard.py)
+  device (libvzgp)       kernel matrix, Cholesky (+retry), L^-1, alpha, NLL + gradient,
+                         posterior mean/variance + UCB + trust region, Eagle / random acquisition
+                         optimisation, top-k
+
+Not implemented (the reference supports them; SURVEY 8f "next"): multi-metric scalarised UCB,
+`ensemble_size > 1`, `linear_coef`, transfer-learning priors (`set_priors`), parallel (q-)
+acquisitions, feature padding schedules.  Each raises NotImplementedError / ValueError instead of
+silently doing something else.
+"""
+
+from __future__ import annotations
+
+import copy
+import datetime
+import json
+import random
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from vizier_b200 import acquisitions as acq_lib
+from vizier_b200 import ard
+from vizier_b200 import converters
+from vizier_b200 import gp
+from vizier_b200 import optimizers as vb
+from vizier_b200 import output_warpers
+from vizier_b200 import profiler
+from vizier_b200 import vz
+
+# gp_bandit.py:57
+_MAX_NUM_FEASIBLE_VALUES_FOR_TRUST_REGION = 1000
+
+# gp_bandit.py:60-66
+default_acquisition_optimizer_factory = vb.VectorizedOptimizerFactory(
+    strategy_factory=vb.VectorizedEagleStrategyFactory(eagle_config=vb.EagleStrategyConfig()),
+    max_evaluations=75_000,
+    suggestion_batch_size=25,
+)
+
+
+def _seed_from(rng: Any) -> int:
+  """Accepts an int, a NumPy Generator or a JAX-style uint32[2] key."""
+  if rng is None:
+    return random.getrandbits(32)
+  if isinstance(rng, (int, np.integer)):
+    return int(rng)
+  if isinstance(rng, np.random.Generator):
+    return int(rng.integers(2**62))
+  arr = np.asarray(rng).reshape(-1)
+  return int(arr[-1]) if arr.size else 0
+
+
+def _halton(index: int, base: int) -> float:
+  f, r = 1.0, 0.0
+  while index > 0:
+    f /= base
+    r += f * (index % base)
+    index //= base
+  return r
+
+
+_PRIMES = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97,
+           101, 103, 107, 109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173, 179, 181, 191, 193,
+           197, 199, 211, 223, 227, 229, 233, 239, 241, 251, 257, 263, 269, 271, 277, 281, 283, 293, 307, 311]
+
+
+class VizierGPBandit:
+  """GP-Bandit designer; see module docstring."""
+
+  def __init__(self, problem, *, acquisition_optimizer_factory: vb.VectorizedOptimizerFactory = default_acquisition_optimizer_factory,
+               ard_optimizer: Optional[ard.ScipyLbfgsB] = None, ard_random_restarts: int = ard.DEFAULT_RANDOM_RESTARTS,
+               num_seed_trials: int = 1, linear_coef: Optional[float] = None, scoring_function_factory=None,
+               scoring_function_is_parallel: bool = False, padding_schedule=None, use_trust_region: bool = True,
+               rng: Any = None, ensemble_size: Optional[int] = 1, output_warper=None, num_scalarizations: int = 1000,
+               ref_scaling: float = 0.01, multitask_type=None, ucb_coefficient: float = acq_lib.DEFAULT_UCB_COEFFICIENT,
+               device: int = 0):
+    # gp_bandit.py:179-186
+    if problem.search_space.is_conditional:
+      raise ValueError(f'{type(self)} does not support conditional search.')
+    if problem.search_space.num_parameters() == 0:
+      raise ValueError('SearchSpace should contain at least one parameter config.')
+    if len(problem.metric_information) != 1:
+      raise NotImplementedError('vizier_b200.VizierGPBandit implements the single-metric path only.')
+    if linear_coef is not None:
+      raise NotImplementedError('linear_coef (Matern + linear kernel) is not implemented.')
+    if (ensemble_size or 1) != 1:
+      raise NotImplementedError('ensemble_size > 1 is not implemented.')
+    if scoring_function_is_parallel or scoring_function_factory is not None:
+      raise NotImplementedError('custom / parallel scoring functions are not implemented (UCB only).')
+    del padding_schedule, num_scalarizations, ref_scaling, multitask_type
+    self._problem = problem
+    self._acquisition_optimizer_factory = acquisition_optimizer_factory
+    self._ard_optimizer = ard_optimizer or ard.ScipyLbfgsB()
+    self._ard_random_restarts = ard_random_restarts
+    self._num_seed_trials = num_seed_trials
+    self._use_trust_region = use_trust_region
+    self._ucb_coefficient = ucb_coefficient
+    self._metadata_ns = 'oss_gp_bandit'
+    self._output_warper = output_warper or output_warpers.create_default_warper()
+    self._rng = np.random.default_rng(_seed_from(rng))
+    self._converter = converters.TrialToModelInputConverter.from_problem(problem)
+    self._acquisition_optimizer = acquisition_optimizer_factory(self._converter)
+    self._halton_offset = int(self._rng.integers(0, 2**16))
+    self._halton_count = 0
+    self._trials: list = []
+    self._incorporated_trials_count = 0
+    self._device_index = device
+    self._dev: Optional[gp.DeviceGP] = None
+    self._last_params: Optional[gp.GPHyperParams] = None
+
+  # ------------------------------------------------------------------ API
+  def update(self, completed, all_active=None) -> None:
+    """gp_bandit.py:282-287."""
+    del all_active
+    self._trials.extend(copy.deepcopy(list(completed.trials)))
+
+  def set_priors(self, prior_studies) -> None:
+    raise NotImplementedError('transfer-learning priors are not implemented (reference tests skip them too).')
+
+  @classmethod
+  def from_problem(cls, problem, seed: Optional[int] = None, **kwargs) -> 'VizierGPBandit':
+    """gp_bandit.py:629-641."""
+    return cls(problem, rng=random.getrandbits(32) if seed is None else seed, **kwargs)
+
+  # ------------------------------------------------------------------ internals
+  def _device(self) -> gp.DeviceGP:
+    if self._dev is None:
+      self._dev = gp.DeviceGP(self._device_index)
+    return self._dev
+
+  @profiler.record_runtime
+  def _generate_seed_trials(self, count: int) -> Sequence[Any]:
+    """gp_bandit.py:326-364: search-space centre first, quasi-random afterwards."""
+    out = []
+    dc, dk = self._converter.n_continuous, self._converter.n_categorical
+    if not self._trials:
+      params = self._converter.to_parameters(0.5 * np.ones((1, dc)), np.zeros((1, dk), np.int32))[0]
+      out.append(vz.TrialSuggestion(params, metadata=vz.Metadata({'seeded': 'center'})))
+    with profiler.timeit('quasi_random_sampler_seed_trials'):
+      while len(out) < count:
+        self._halton_count += 1
+        idx = self._halton_offset + self._halton_count
+        cont = np.array([[_halton(idx, _PRIMES[j % len(_PRIMES)]) for j in range(dc)]])
+        cat = np.array([[int(_halton(idx, _PRIMES[(dc + j) % len(_PRIMES)]) * (s - 1)) for j, s in enumerate(self._converter.categorical_sizes)]], np.int32).reshape(1, dk)
+        out.append(vz.TrialSuggestion(self._converter.to_parameters(cont, cat)[0]))
+    return out
+
+  def _warp_labels(self, labels: np.ndarray) -> np.ndarray:
+    return np.concatenate([self._output_warper.warp(labels[:, i:i + 1]) for i in range(labels.shape[1])], axis=-1)
+
+  @profiler.record_runtime
+  def _trials_to_data(self, trials):
+    (cont, cat), labels = self._converter.to_xy(trials)
+    return cont, cat, self._warp_labels(labels)
+
+  @profiler.record_runtime
+  def _update_gp(self, cont, cat, labels) -> gp.DeviceGP:
+    """gp_bandit.py:449-479: ARD + precompute, skipped when no new trial arrived."""
+    dev = self._device()
+    if len(self._trials) == self._incorporated_trials_count and self._last_params is not None:
+      return dev
+    self._incorporated_trials_count = len(self._trials)
+    ard_rng = np.random.default_rng(int(self._rng.integers(2**62)))
+    z = cat if cat.shape[1] else None
+    best, _ = ard.train_gp(dev, cont, labels[:, 0], z, rng=ard_rng, random_restarts=self._ard_random_restarts,
+                           ensemble_size=1, optimizer=self._ard_optimizer)
+    self._last_params = best[0]
+    dev.fit(cont, labels[:, 0], self._last_params, z=z)
+    return dev
+
+  def _acquisition(self, n_obs: int) -> gp.Acquisition:
+    return acq_lib.make_acquisition(
+        n_obs, self._converter.continuous_feasible_values(_MAX_NUM_FEASIBLE_VALUES_FOR_TRUST_REGION),
+        self._converter.n_continuous, self._converter.n_categorical, use_trust_region=self._use_trust_region,
+        ucb_coefficient=self._ucb_coefficient)
+
+  @profiler.record_runtime
+  def _optimize_acquisition(self, dev: gp.DeviceGP, acq: gp.Acquisition, count: int):
+    """gp_bandit.py:482-521 + vectorized_base.best_candidates_to_trials (:591-651)."""
+    prior = converters.trials_to_sorted_features(self._trials, self._converter)
+    seed = int(self._rng.integers(2**62))
+    res = self._acquisition_optimizer(dev, acq, count=count, prior_features=None if prior is None else prior[0], seed=seed)
+    trials = []
+    order = np.argsort(-res.rewards, kind='stable')
+    for ind in order:
+      params = self._converter.to_parameters(res.features[ind:ind + 1])[0]
+      trial = vz.Trial(parameters=params)
+      md = trial.metadata.ns('devinfo')
+      aux = {k: float(v[ind]) for k, v in res.aux.items()}
+      md['acquisition_optimization'] = json.dumps({'acquisition': float(res.rewards[ind])} | aux)
+      if not np.isfinite([res.rewards[ind], *aux.values()]).all() and np.isnan([res.rewards[ind], *aux.values()]).any():
+        md['acquisition_optimization_warning'] = (
+            'NaNs encountered in acquisition optimization. See the "acquisition_optimization" field in the '
+            'metadata for more details.')
+      trial.complete(vz.Measurement({'acquisition': float(res.rewards[ind])}))
+      trials.append(trial)
+    return trials
+
+  # ------------------------------------------------------------------ suggest / predict / sample
+  @profiler.record_runtime
+  def suggest(self, count: int = 1) -> Sequence[Any]:
+    """gp_bandit.py:523-559."""
+    if len(self._trials) < self._num_seed_trials:
+      return self._generate_seed_trials(count)
+    start = datetime.datetime.now()
+    cont, cat, labels = self._trials_to_data(self._trials)
+    dev = self._update_gp(cont, cat, labels)
+    acq = self._acquisition(cont.shape[0])
+    best = self._optimize_acquisition(dev, acq, count)
+    out = []
+    for t in best:
+      t.metadata.ns(self._metadata_ns).ns('devinfo')['time_spent'] = f'{datetime.datetime.now() - start}'
+      out.append(vz.TrialSuggestion(parameters=t.parameters, metadata=t.metadata))
+    return out
+
+  @profiler.record_runtime
+  def sample(self, trials: Sequence[Any], rng: Any = None, num_samples: int = 1000) -> np.ndarray:
+    """gp_bandit.py:561-602: unwarped joint posterior samples, shape (num_samples, num_trials)."""
+    if not trials:
+      return np.zeros((num_samples, 0))
+    cont, cat, labels = self._trials_to_data(self._trials)
+    dev = self._update_gp(cont, cat, labels)
+    xs, zs = self._converter.to_features(trials)
+    xs = np.nan_to_num(xs, nan=0.0)
+    mean, cov = dev.posterior(xs, zs if zs.shape[1] else None, add_noise=True)
+    # Cholesky of the (small) posterior covariance on the device as well; the retry adds a tiny
+    # jitter only if round-off made it indefinite.
+    m = mean.shape[0]
+    chol, _, _ = dev.cholesky_retry(cov, jitter=1e-10, max_iters=8)
+    chol = chol.cpu().numpy()
+    mean = mean.cpu().numpy()
+    g = np.random.default_rng(_seed_from(rng) if rng is not None else 0)
+    samples = mean[None, :] + g.standard_normal((num_samples, m)) @ chol.T
+    return np.vstack([self._output_warper.unwarp(samples[i][:, None]).reshape(-1) for i in range(num_samples)])
+
+  @profiler.record_runtime
+  def predict(self, trials: Sequence[Any], rng: Any = None, num_samples: Optional[int] = 1000):
+    """gp_bandit.py:604-627: empirical mean / stddev of unwarped samples."""
+    s = self.sample(trials, rng, num_samples or 1000)
+    return vz.Prediction(mean=np.mean(s, axis=0), stddev=np.std(s, axis=0))

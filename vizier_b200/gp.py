@@ -291,6 +291,18 @@ class DeviceGP:
         self._h, hp(xs), hp(zs), m, C.byref(a), hp(score_out), hp(mean_out), hp(stddev_out), hp(linf_out)))
     del keep
 
+  def posterior(self, xs, zs=None, add_noise: bool = True):
+    """Joint posterior mean [M] and covariance [M, M] (device tensors)."""
+    xst, zst = self._xz(xs, zs)
+    m = xst.shape[0]
+    mean = torch.empty((m,), dtype=torch.float64, device=self.device)
+    cov = torch.empty((m, m), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_posterior', self._lib.vzgp_posterior(
+        self._h, _ptr(xst), _ptr(zst), m, 1 if add_noise else 0, _ptr(mean), _ptr(cov), m))
+    self.synchronize()
+    return mean, cov
+
   def topk(self, score: torch.Tensor, count: int):
     idx = np.zeros(count, np.int64)
     val = np.zeros(count, np.float64)

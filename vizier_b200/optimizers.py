@@ -1,0 +1,123 @@
+"""Acquisition optimisers: the host-side factories of the reference, executing on the device.
+
+Mirrors
+  * `VectorizedOptimizerFactory` / `VectorizedOptimizer` / `VectorizedStrategyResults`
+    (vizier/_src/algorithms/optimizers/vectorized_base.py:668-710, :278-542, :125-131),
+  * `EagleStrategyConfig` / `VectorizedEagleStrategyFactory`
+    (vizier/_src/algorithms/optimizers/eagle_strategy.py:111-167, :325-407),
+  * `random_strategy_factory` (random_vectorized_optimizer.py:114-123).
+Calling the optimiser runs the whole ask-evaluate-tell loop inside libvzgp
+(`vzgp_eagle_run` / `vzgp_random_search`); only the `count` winners come back to the host.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Callable, Dict, Optional, Union
+
+import numpy as np
+
+from vizier_b200 import _lib, gp
+
+
+@dataclasses.dataclass(frozen=True)
+class EagleStrategyConfig:
+  visibility: float = 0.45
+  gravity: float = 1.5
+  negative_gravity: float = 0.008
+  perturbation: float = 0.16
+  categorical_perturbation_factor: float = 1.0
+  pure_categorical_perturbation_factor: float = 30
+  prob_same_category_without_perturbation: float = 0.98
+  perturbation_lower_bound: float = 7e-5
+  penalize_factor: float = 7e-1
+  pool_size_exponent: float = 1.2
+  pool_size: int = 0
+  max_pool_size: int = 100
+  normalization_scale: float = 0.5
+  prior_trials_pool_pct: float = 0.96
+
+
+@dataclasses.dataclass(frozen=True)
+class VectorizedEagleStrategyFactory:
+  eagle_config: EagleStrategyConfig = EagleStrategyConfig()
+
+  def pool_size(self, n_features: int, suggestion_batch_size: Optional[int]) -> int:
+    """eagle_strategy.py:376-386."""
+    cfg = self.eagle_config
+    pool = cfg.pool_size
+    if pool == 0:
+      pool = 10 + int(0.5 * n_features + n_features ** cfg.pool_size_exponent)
+      pool = min(pool, cfg.max_pool_size)
+      if suggestion_batch_size is not None:
+        pool = int(math.ceil(pool / suggestion_batch_size) * suggestion_batch_size)
+    return pool
+
+
+class _RandomStrategyFactory:
+  """Marker for RandomVectorizedStrategy (uniform candidates, no state)."""
+
+  def __repr__(self):
+    return 'random_strategy_factory'
+
+
+random_strategy_factory = _RandomStrategyFactory()
+
+
+@dataclasses.dataclass
+class VectorizedStrategyResults:
+  features: np.ndarray             # [count, Dc]
+  rewards: np.ndarray              # [count]
+  aux: Dict[str, np.ndarray] = dataclasses.field(default_factory=dict)
+
+
+@dataclasses.dataclass
+class VectorizedOptimizer:
+  strategy_factory: Union[VectorizedEagleStrategyFactory, _RandomStrategyFactory]
+  n_continuous: int
+  n_categorical: int
+  suggestion_batch_size: int = 25
+  max_evaluations: int = 75_000
+
+  def __call__(self, dev: gp.DeviceGP, acq: gp.Acquisition, *, count: int = 1,
+               prior_features: Optional[np.ndarray] = None, seed: int = 0) -> VectorizedStrategyResults:
+    if self.n_categorical:
+      raise NotImplementedError('categorical features in the device optimisers are not implemented yet')
+    if isinstance(self.strategy_factory, _RandomStrategyFactory):
+      # one uniform batch per step; the device scores all max_evaluations candidates in one pass
+      n = (self.max_evaluations - 1) // self.suggestion_batch_size + 1
+      m = n * self.suggestion_batch_size
+      bx, bs, _ = dev.random_search(m, acq, count, seed)
+    else:
+      f = self.strategy_factory
+      pool = f.pool_size(self.n_continuous + self.n_categorical, self.suggestion_batch_size)
+      c = f.eagle_config
+      cfg = _lib.EagleConfig(c.visibility, c.gravity, c.negative_gravity, c.perturbation,
+                             c.perturbation_lower_bound, c.penalize_factor, c.normalization_scale,
+                             c.prior_trials_pool_pct, pool, self.suggestion_batch_size, self.max_evaluations)
+      bx, bs = dev.eagle_run(cfg, acq, count, seed, prior=prior_features)
+    # score_with_aux on the winners (vectorized_base.py:504-526)
+    out = dev.score(bx, acq, with_aux=True)
+    dev.synchronize()
+    aux = {
+        'mean': out['mean'].cpu().numpy(), 'stddev': out['stddev'].cpu().numpy(),
+        'linf_distance': out['linf_distance'].cpu().numpy(),
+        'radius': np.full(count, acq.trust_radius),
+    }
+    aux['raw_acquisition'] = aux['mean'] + acq.ucb_coefficient * aux['stddev']
+    if not acq.use_trust_region:
+      aux = {}
+    return VectorizedStrategyResults(bx, bs, aux)
+
+
+@dataclasses.dataclass
+class VectorizedOptimizerFactory:
+  strategy_factory: Union[VectorizedEagleStrategyFactory, _RandomStrategyFactory] = VectorizedEagleStrategyFactory()
+  max_evaluations: int = 75_000
+  suggestion_batch_size: int = 25
+  use_fori: bool = True  # accepted for API compatibility; the loop always runs on the device
+
+  def __call__(self, converter) -> VectorizedOptimizer:
+    return VectorizedOptimizer(self.strategy_factory, converter.n_continuous, converter.n_categorical,
+                               self.suggestion_batch_size, self.max_evaluations)
