@@ -258,3 +258,39 @@ def test_c2_full_size_properties(dev):
   # (4) top-k agrees with a host sort
   idx, val = dev.topk(out['score'], 5)
   np.testing.assert_array_equal(idx, go.top_k(sc, 5))
+
+
+def test_ard_fit_matches_oracle_driver(dev):
+  """Same inits + same SciPy L-BFGS-B driver: CUDA loss/grad vs oracle loss/grad (SURVEY A.4:
+  compare fits by final loss, trajectories are not bit-reproducible across gradient implementations)."""
+  from vizier_b200 import ard
+  n, d = 60, 4
+  x, y, _ = _problem(n, d, 21)
+  y = (y - y.mean()) / y.std()
+  inits = ard.log_uniform_init(np.random.default_rng(5), d, 0, 4)
+  want_theta, want_losses = go.ard_fit(x, y, init_thetas=inits)
+  xt = torch.from_numpy(x).cuda(); yt = torch.from_numpy(y).cuda()
+  lo, hi = _gp().param_bounds(d, 0)
+
+  def f(theta):
+    loss, grad, _ = dev.loss_and_grad(xt, yt, _gp().GPHyperParams.from_vector(theta, d, 0))
+    return loss, grad
+
+  best, losses = ard.ScipyLbfgsB()(inits, f, list(zip(lo, hi)), best_n=1)
+  np.testing.assert_allclose(np.sort(losses), np.sort(want_losses), rtol=1e-5, atol=1e-5)
+  assert abs(losses.min() - want_losses.min()) < 1e-6
+
+
+def test_posterior_covariance(dev):
+  n, d, m = 150, 5, 70
+  x, y, _ = _problem(n, d, 22)
+  xs, _, _ = _problem(m, d, 23)
+  po, pg = _params(d)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  mean, cov = dev.posterior(xs)
+  ks = go.kernel(po, xs, x)
+  v = sla.solve_triangular(pred.chol, ks.T, lower=True)
+  want_cov = go.kernel(po, xs, xs) - v.T @ v + po.observation_noise_variance * np.eye(m)
+  np.testing.assert_allclose(cov.cpu().numpy(), want_cov, atol=TOL, rtol=0)
+  np.testing.assert_allclose(mean.cpu().numpy(), ks @ pred.alpha, atol=TOL, rtol=0)
