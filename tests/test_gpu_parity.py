@@ -140,10 +140,11 @@ def test_score_with_aux(dev, n, d, dk, m, tr):
   np.testing.assert_array_equal(out['linf_distance'].cpu().numpy(), dist)  # max/min of exact differences
   if tr and radius <= 0.5:
     assert np.any(want < -1e3)  # the trust region really was active in this case
-  # score-only path (no aux outputs) gives bit-identical scores
+  # score-only path (no aux outputs; features pre-divided by the length scale when the trust
+  # region is inactive) agrees to round-off
   out2 = dev.score(xs, acq, zs=zs, with_aux=False)
   dev.synchronize()
-  np.testing.assert_array_equal(out2['score'].cpu().numpy(), out['score'].cpu().numpy())
+  np.testing.assert_allclose(out2['score'].cpu().numpy(), out['score'].cpu().numpy(), atol=1e-12, rtol=0)
 
 
 def test_score_hard_conditioning_scaled_tolerance(dev):
@@ -246,11 +247,16 @@ def test_c2_full_size_properties(dev):
   sel = np.random.default_rng(1).choice(m, 512, replace=False)
   want, _ = go.score_with_aux(pred, xs[torch.from_numpy(sel).cuda()].cpu().numpy())
   np.testing.assert_allclose(sc[sel], want, atol=TOL, rtol=0)
-  # (2) position independence: the same candidates scored alone give bit-identical values
+  # (2) position independence: the same candidates scored alone (small-pool path: column blocks
+  # split across CTAs, row sums reduced in a different fixed order) agree to round-off, and
+  # repeated evaluation is bit-reproducible
   sub = xs[torch.from_numpy(sel).cuda()].contiguous()
   out2 = dev.score(sub, acq)
   dev.synchronize()
-  np.testing.assert_array_equal(out2['score'].cpu().numpy(), sc[sel])
+  np.testing.assert_allclose(out2['score'].cpu().numpy(), sc[sel], atol=1e-12, rtol=0)
+  out3 = dev.score(xs, acq)
+  dev.synchronize()
+  np.testing.assert_array_equal(out3['score'].cpu().numpy(), sc)
   # (3) posterior sanity: 0 <= var <= sf2 + sn2, and UCB identity
   sd = out['stddev'].cpu().numpy(); mu = out['mean'].cpu().numpy()
   assert sd.min() >= 0 and sd.max() <= np.sqrt(1.0 + 1e-3) + 1e-12

@@ -43,6 +43,7 @@ struct Guard {
 
 static int ensure_model_buffers(vzgp_handle* h, int np, int dc, int dk) {
   VZ_TRY(h->X.reserve(sizeof(double) * (size_t)np * (dc > 0 ? dc : 1)));
+  VZ_TRY(h->XT.reserve(sizeof(double) * 2 * (size_t)np * (dc > 0 ? dc : 1)));
   VZ_TRY(h->Z.reserve(sizeof(int32_t) * (size_t)np * (dk > 0 ? dk : 1)));
   VZ_TRY(h->L.reserve(sizeof(double) * (size_t)np * np));
   VZ_TRY(h->Linv.reserve(sizeof(double) * (size_t)np * np));
@@ -104,6 +105,7 @@ static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const d
   double* r = yp + 2 * np;
   double* tmp = yp + 3 * np;
   if (dc > 0) VZ_TRY(launch_pad_rows(h, X, N, dc, np, h->X.as<double>()));
+  if (dc > 0) VZ_TRY(launch_transpose_scale(h, h->X.as<double>(), np, dc, kp, h->XT.as<double>()));
   if (dk > 0) VZ_TRY(launch_pad_rows_i32(h, Z, N, dk, np, h->Z.as<int32_t>()));
   VZ_TRY(launch_pad_vector(h, y, N, n_valid, np, yp));
   VZ_TRY(launch_kernel_matrix(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, h->sn2,
@@ -177,7 +179,7 @@ int vzgp_destroy(vzgp_handle* h) {
   if (!h) return 0;
   Guard g(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->X, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv,
+  for (DevBuf* b : {&h->X, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->XT,
                     &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);

@@ -90,6 +90,7 @@ struct KernelParams {
   int dk;
   double sf2;
   double inv_ls2_c[kMaxDc];
+  double inv_ls_c[kMaxDc];   // sqrt(inv_ls2_c): the reference's FeatureScaled divides by the length scale
   double inv_ls2_k[kMaxDk];
 };
 
@@ -108,6 +109,7 @@ struct vzgp_handle {
   vzgp::KernelParams kp;
   double sn2 = 0.0;
   vzgp::DevBuf X;      // [np x dc]
+  vzgp::DevBuf XT;     // [2][dc x np]: transposed trials, scaled by 1/ls (first) and unscaled (second)
   vzgp::DevBuf Z;      // [np x dk] int32
   vzgp::DevBuf L;      // [np x np]
   vzgp::DevBuf Linv;   // [np x np]

@@ -348,6 +348,17 @@ __global__ void k_pad_rows(const double* __restrict__ src, int n, int d, int np,
   dst[e] = e < (size_t)n * d ? src[e] : 0.0;
 }
 
+// XT[0][d][i] = X[i][d] * inv_ls[d],  XT[1][d][i] = X[i][d]   (X is [np x dc], already padded)
+__global__ void k_transpose_scale(const double* __restrict__ X, int np, int dc, KernelParams kp,
+                                  double* __restrict__ XT) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)np * dc) return;
+  int d = (int)(e / np), i = (int)(e % np);
+  double v = X[(size_t)i * dc + d];
+  XT[e] = v * kp.inv_ls_c[d];
+  XT[(size_t)np * dc + e] = v;
+}
+
 __global__ void k_pad_rows_i32(const int32_t* __restrict__ src, int n, int d, int np,
                                int32_t* __restrict__ dst) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,8 +397,10 @@ int fill_kernel_params(const vzgp_params* p, int dc, int dk, KernelParams* kp) {
   kp->dc = dc;
   kp->dk = dk;
   kp->sf2 = p->signal_variance;
-  for (int d = 0; d < kMaxDc; ++d)
+  for (int d = 0; d < kMaxDc; ++d) {
     kp->inv_ls2_c[d] = d < dc ? 1.0 / p->continuous_length_scale_squared[d] : 0.0;
+    kp->inv_ls_c[d] = d < dc ? 1.0 / std::sqrt(p->continuous_length_scale_squared[d]) : 0.0;
+  }
   for (int d = 0; d < kMaxDk; ++d)
     kp->inv_ls2_k[d] = d < dk ? 1.0 / p->categorical_length_scale_squared[d] : 0.0;
   return 0;
@@ -547,6 +560,15 @@ int launch_pad_rows(vzgp_handle* h, const double* src, int n, int d, int np, dou
   size_t tot = (size_t)np * d;
   if (tot == 0) return 0;
   k_pad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(src, n, d, np, dst);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+int launch_transpose_scale(vzgp_handle* h, const double* X, int np, int dc, const KernelParams& kp,
+                           double* XT) {
+  size_t tot = (size_t)np * dc;
+  if (tot == 0) return 0;
+  k_transpose_scale<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(X, np, dc, kp, XT);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;

@@ -31,7 +31,7 @@ struct ScoreArgs {
   const double* Xs;
   const int32_t* Zs;
   int M;
-  const double* X;
+  const double* XT;   // [2][dc][np]: scaled / unscaled transposed trials
   const int32_t* Z;
   int np;
   int n_valid;
@@ -45,6 +45,9 @@ struct ScoreArgs {
   double radius;
   uint8_t tr_mask[kMaxDc];
   double* scratch;  // [gridDim.x][64][np]
+  int nsplit;       // > 1: output column blocks of one tile are shared by nsplit CTAs (small M)
+  double* part;     // nsplit > 1: [nsplit + 2][Mpad] partial row sums, then mu, then linf
+  int mpad;
   double* score;
   double* mu;
   double* sigma;
@@ -79,17 +82,38 @@ constexpr int kBK = 16;          // k-slab
 constexpr int kStages = 4;
 constexpr int kLds = kBK + 4;    // smem row stride (doubles): 160 B rows, conflict-free fragment reads
 constexpr int kStageDoubles = (kTM + kBN) * kLds;
+constexpr int kLD1 = 66;         // phase-1 smem row stride (64 rows/cols + 2)
+
+// Final score from the reduced pieces (shared by the fused epilogue and the split finalize kernel).
+__device__ __forceinline__ void emit_score(const ScoreArgs& a, int m, double rs, double mean, double dist,
+                                           int& clamped) {
+  double var = a.kp.sf2 - rs + a.sn2;
+  if (var < 0.0) { var = 0.0; ++clamped; }
+  const double sd = sqrt(var);
+  double sc = fma(a.coef, sd, mean);
+  if (a.apply_tr) {
+    const bool inside = (dist <= a.radius) || (a.radius > 0.5);
+    sc = inside ? sc : (-1e4 - dist);
+  }
+  a.score[m] = sc;
+  if (a.mu) a.mu[m] = mean;
+  if (a.sigma) a.sigma[m] = sd;
+  if (a.linf) a.linf[m] = dist;
+}
 
 template <bool WITH_LINF>
 __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
   extern __shared__ double smem[];
-  constexpr int LD = 66;
+  constexpr int LD = kLD1;
   const int dc = a.kp.dc, dk = a.kp.dk, np = a.np;
   double* ring = smem;                                   // [kStages][kTM + kBN][kLds]
-  double* sa = ring + kStages * kStageDoubles;           // [dc][LD]   candidate features (transposed)
-  double* sb = sa + dc * LD;                             // [dc][LD]   trial features
-  double* s_alpha = sb + dc * LD;                        // [64]
-  double* s_mu = s_alpha + 64;                           // [64]
+  // Without the trust-region distance the features are pre-divided by the length scale (the
+  // reference's FeatureScaled form, 2 flops per dimension).  With it, unscaled features are staged
+  // so that |a-b| is exact, and the scaling is applied to the squared difference.
+  double* sa = ring + kStages * kStageDoubles;           // [dc][LD]     candidates (transposed)
+  double* sb = sa + dc * LD;                             // [2][dc][LD]  trials, double buffered
+  double* s_alpha = sb + 2 * dc * LD;                    // [2][64]
+  double* s_mu = s_alpha + 128;                          // [64]
   double* s_linf = s_mu + 64;                            // [64]
   double* s_rowsq = s_linf + 64;                         // [4][64]
   int32_t* za = reinterpret_cast<int32_t*>(s_rowsq + 256);  // [dk][LD]
@@ -98,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = tid / 16, tx = tid % 16;      // phase-1 mapping (32 x 16 threads)
-  const int wm = warp & 3, wn = warp >> 2;     // phase-2 warp grid 4 (M) x 2 (N); each SM sub-partition gets one warp of each N half
+  const int wm = warp & 3, wn = warp >> 2;     // phase-2 warp grid 4 (M) x 4 (N)
   const int fr = lane >> 2, fk = lane & 3;     // fragment row / k within a DMMA tile
   double* scr = a.scratch + (size_t)blockIdx.x * kTM * np;
   if (tid < kMaxDc) s_mask[tid] = a.tr_mask[tid];
@@ -106,24 +130,93 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
 
   const int ntiles = (a.M + kTM - 1) / kTM;
   const int nblocks = (np + kBN - 1) / kBN;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int nsplit = a.nsplit;
+  const double* XTs = a.XT;
+  const double* XTu = a.XT + (size_t)dc * np;
+
+  for (int work = blockIdx.x; work < ntiles * nsplit; work += gridDim.x) {
+    const int tile = work / nsplit, split = work - tile * nsplit;
     const int m0 = tile * kTM;
     __syncthreads();  // previous tile fully consumed (sa, s_mu, s_rowsq, ring)
-    stage_rows_T(a.Xs, a.M, dc, m0, kTM, sa, LD);
+    // candidate tile, transposed; scaled by 1/ls like the reference's FeatureScaled kernel
+    for (int e = tid; e < kTM * dc; e += kThreads) {
+      const int r = e / dc, d = e - r * dc;
+      const int gr = m0 + r;
+      const double v = gr < a.M ? __ldg(a.Xs + (size_t)gr * dc + d) : 0.0;
+      sa[d * LD + r] = WITH_LINF ? v : v * a.kp.inv_ls_c[d];
+    }
     if (dk > 0) stage_rows_T_i32(a.Zs, a.M, dk, m0, kTM, za, LD);
 
     // ---------------- phase 1: K* tile, mean, trust-region distance ----------------
+    // Trial rows arrive pre-transposed and pre-scaled (XT), 64 columns per step, through a
+    // two-deep cp.async buffer so the copy of block jb+1 overlaps the math of block jb.
+    auto stage_trials = [&](int jb, int buf) {
+      double* dst = sb + buf * dc * LD;
+      const double* src = WITH_LINF ? XTu : XTs;
+      for (int c = tid; c < dc * 32; c += kThreads) {       // dc rows x 32 chunks of 16 B
+        const int d = c >> 5, q = c & 31;
+        cp_async16(dst + d * LD + q * 2, src + (size_t)d * np + jb * 64 + q * 2, true);
+      }
+      if (tid < 32) cp_async16(s_alpha + buf * 64 + tid * 2, a.alpha + jb * 64 + tid * 2, true);
+    };
     double mu_part[2], lmin[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) { mu_part[i] = 0.0; lmin[i] = INFINITY; }
-    for (int jb = 0; jb < np / 64; ++jb) {
+    const int nj = np / 64;
+    stage_trials(0, 0);
+    cp_async_commit();
+    for (int jb = 0; jb < nj; ++jb) {
+      const int buf = jb & 1;
+      if (jb + 1 < nj) stage_trials(jb + 1, buf ^ 1);   // buffer buf^1 was released by the barrier below
+      cp_async_commit();
+      cp_async_wait<1>();
       __syncthreads();
-      stage_rows_T(a.X, np, dc, jb * 64, 64, sb, LD);
-      if (dk > 0) stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD);
-      if (tid < 64) s_alpha[tid] = a.alpha[jb * 64 + tid];
-      __syncthreads();
+      if (dk > 0) {  // categorical rows are rare: staged synchronously
+        stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD);
+        __syncthreads();
+      }
+      const double* sbj = sb + buf * dc * LD;
+      const double* alj = s_alpha + buf * 64;
       double d2[2][4], lf[2][4];
-      tile_d2<GP1, 2, 4, WITH_LINF>(sa, LD, sb, LD, za, LD, zb, LD, a.kp, s_mask, ty, tx, d2, lf);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { d2[i][j] = 0.0; lf[i][j] = 0.0; }
+      for (int d = 0; d < dc; ++d) {
+        const double2 av = *reinterpret_cast<const double2*>(sa + d * LD + GP1::row_of(ty, 0));
+        const double2 b0 = *reinterpret_cast<const double2*>(sbj + d * LD + GP1::col_of(tx, 0));
+        const double2 b1 = *reinterpret_cast<const double2*>(sbj + d * LD + GP1::col_of(tx, 2));
+        const double aa[2] = {av.x, av.y}, bb[4] = {b0.x, b0.y, b1.x, b1.y};
+        if (WITH_LINF) {
+          const double w = a.kp.inv_ls2_c[d];
+          const bool in_tr = s_mask[d] != 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double df = aa[i] - bb[j];
+              d2[i][j] = fma(df * df, w, d2[i][j]);
+              if (in_tr) lf[i][j] = fmax(lf[i][j], fabs(df));
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double df = aa[i] - bb[j];
+              d2[i][j] = fma(df, df, d2[i][j]);
+            }
+        }
+      }
+      for (int k = 0; k < dk; ++k) {
+        const double w = a.kp.inv_ls2_k[k];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int avz = za[k * LD + GP1::row_of(ty, i)];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d2[i][j] += (avz != zb[k * LD + GP1::col_of(tx, j)]) ? w : 0.0;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         double kv[4];
@@ -132,14 +225,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
           const int cj = GP1::col_of(tx, j);
           const bool valid = (jb * 64 + cj) < a.n_valid;
           kv[j] = valid ? matern52(d2[i][j], a.kp.sf2) : 0.0;
-          mu_part[i] = fma(kv[j], s_alpha[cj], mu_part[i]);
+          mu_part[i] = fma(kv[j], alj[cj], mu_part[i]);
           if (WITH_LINF && valid) lmin[i] = fmin(lmin[i], lf[i][j]);
         }
         double* dst = scr + (size_t)GP1::row_of(ty, i) * np + jb * 64;
         *reinterpret_cast<double2*>(dst + GP1::col_of(tx, 0)) = make_double2(kv[0], kv[1]);
         *reinterpret_cast<double2*>(dst + GP1::col_of(tx, 2)) = make_double2(kv[2], kv[3]);
       }
+      __syncthreads();  // everyone is done with buffer `buf` (and zb) before it is refilled
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
 #pragma unroll
@@ -158,6 +253,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
     // Slab (jb, ks): A = scratch[0:64, ks*16 : +16], B = Linv[jb*128 : +128, ks*16 : +16];
     // block jb needs ks < min(np, (jb+1)*128)/16 because Linv is lower triangular.  The slab
     // stream is flattened over blocks so the cp.async ring never drains between blocks.
+    // With nsplit > 1 this CTA takes blocks {split, nblocks-1-split} (balanced triangular work).
+    const int nq = (nsplit == 1) ? nblocks : ((split == nblocks - 1 - split) ? 1 : 2);
+    auto block_of = [&](int q) { return (nsplit == 1) ? q : (q == 0 ? split : nblocks - 1 - split); };
     auto slabs_in = [&](int jb) { int kend = (jb + 1) * kBN; if (kend > np) kend = np; return kend / kBK; };
     auto issue = [&](int jb, int ks, int stage) {
       double* As = ring + stage * kStageDoubles;
@@ -176,16 +274,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
         cp_async16(Bs + r * kLds + q * 2, a.Linv + (size_t)(ok ? gr : 0) * a.ldi + k0 + q * 2, ok);
       }
     };
-    int ljb = 0, lks = 0;  // load cursor
-    auto advance = [&]() { if (++lks == slabs_in(ljb)) { lks = 0; ++ljb; } };
+    int lq = 0, lks = 0;  // load cursor
+    auto advance = [&]() { if (++lks == slabs_in(block_of(lq))) { lks = 0; ++lq; } };
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
-      if (ljb < nblocks) { issue(ljb, lks, s); advance(); }
+      if (lq < nq) { issue(block_of(lq), lks, s); advance(); }
       cp_async_commit();
     }
     double rowsq[2] = {0.0, 0.0};
     int stage = 0;
-    for (int jb = 0; jb < nblocks; ++jb) {
+    for (int q = 0; q < nq; ++q) {
+      const int jb = block_of(q);
       double acc[2][4][2];
 #pragma unroll
       for (int f = 0; f < 2; ++f)
@@ -198,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
         __syncthreads();
         {  // refill the stage consumed in the previous iteration
           int ps = stage + kStages - 1; if (ps >= kStages) ps -= kStages;
-          if (ljb < nblocks) { issue(ljb, lks, ps); advance(); }
+          if (lq < nq) { issue(block_of(lq), lks, ps); advance(); }
           cp_async_commit();
         }
         const double* As = ring + stage * kStageDoubles + (wm * 16 + fr) * kLds + fk;
@@ -208,11 +307,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
         // nothing (warp-uniform skip; happens only inside the diagonal 128-block).
         if (k0 <= col_base + 31) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double a0 = As[q * 4], a1 = As[8 * kLds + q * 4];
+          for (int qq = 0; qq < 4; ++qq) {
+            const double a0 = As[qq * 4], a1 = As[8 * kLds + qq * 4];
             double b[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) b[g] = Bs[g * 8 * kLds + q * 4];
+            for (int g = 0; g < 4; ++g) b[g] = Bs[g * 8 * kLds + qq * 4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0, b[g]);
@@ -244,40 +343,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
       const int r = tid, m = m0 + r;
       if (m < a.M) {
         const double rs = (s_rowsq[r] + s_rowsq[64 + r]) + (s_rowsq[128 + r] + s_rowsq[192 + r]);
-        double var = a.kp.sf2 - rs + a.sn2;
-        if (var < 0.0) { var = 0.0; ++clamped; }
-        const double sd = sqrt(var);
-        const double mean = s_mu[r];
-        double sc = fma(a.coef, sd, mean);
-        const double dist = s_linf[r];
-        if (a.apply_tr) {
-          const bool inside = (dist <= a.radius) || (a.radius > 0.5);
-          sc = inside ? sc : (-1e4 - dist);
+        if (nsplit == 1) {
+          emit_score(a, m, rs, s_mu[r], s_linf[r], clamped);
+        } else {
+          a.part[(size_t)split * a.mpad + m] = rs;
+          if (split == 0) {
+            a.part[(size_t)nsplit * a.mpad + m] = s_mu[r];
+            a.part[(size_t)(nsplit + 1) * a.mpad + m] = s_linf[r];
+          }
         }
-        a.score[m] = sc;
-        if (a.mu) a.mu[m] = mean;
-        if (a.sigma) a.sigma[m] = sd;
-        if (a.linf) a.linf[m] = dist;
       }
     }
   }
   if (clamped) atomicAdd(a.clamp_count, clamped);
 }
 
-size_t score_smem_bytes(int dc, int dk) {
-  return sizeof(double) * (kStages * kStageDoubles + dc * 2 * 66 + 64 * 3 + 256) +
-         sizeof(int32_t) * dk * 2 * 66 + kMaxDc;
+// nsplit > 1: sums the partial row sums in a fixed order and emits the scores.
+__global__ void k_score_finalize(const ScoreArgs a) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  int clamped = 0;
+  if (m < a.M) {
+    double rs = 0.0;
+    for (int s = 0; s < a.nsplit; ++s) rs += a.part[(size_t)s * a.mpad + m];
+    emit_score(a, m, rs, a.part[(size_t)a.nsplit * a.mpad + m], a.part[(size_t)(a.nsplit + 1) * a.mpad + m], clamped);
+  }
+  if (clamped) atomicAdd(a.clamp_count, clamped);
+}
+
+size_t score_smem_bytes(int dc, int dk, bool with_linf) {
+  (void)with_linf;
+  return sizeof(double) * (kStages * kStageDoubles + dc * kLD1 * 3 + 128 + 64 * 2 + 256) +
+         sizeof(int32_t) * dk * 2 * kLD1 + kMaxDc;
 }
 
 int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                  double* score, double* mu, double* sigma, double* linf) {
   if (M <= 0) return 0;
   const int ntiles = (M + kTM - 1) / kTM;
-  const int grid = ntiles < h->sm_count ? ntiles : h->sm_count;
+  const int nblocks = (h->np + kBN - 1) / kBN;
+  // Small pools cannot fill the GPU with one CTA per tile: share each tile's output column
+  // blocks between nsplit CTAs (each recomputes the cheap K* tile).
+  int nsplit = 1;
+  if (ntiles * 2 <= h->sm_count && nblocks >= 2) nsplit = (nblocks + 1) / 2;
+  const int nwork = ntiles * nsplit;
+  const int grid = nwork < h->sm_count ? nwork : h->sm_count;
   VZ_TRY(h->scratch.reserve((size_t)grid * kTM * h->np * sizeof(double)));
   ScoreArgs a;
   a.Xs = Xs; a.Zs = Zs; a.M = M;
-  a.X = h->X.as<double>(); a.Z = h->Z.as<int32_t>();
+  a.XT = h->XT.as<double>(); a.Z = h->Z.as<int32_t>();
   a.np = h->np; a.n_valid = h->n_valid;
   a.Linv = h->Linv.as<double>(); a.ldi = h->np;
   a.alpha = h->alpha.as<double>();
@@ -288,10 +401,21 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
   for (int d = 0; d < kMaxDc; ++d)
     a.tr_mask[d] = (d < h->dc) ? (acq->tr_dim_mask ? (acq->tr_dim_mask[d] ? 1 : 0) : 1) : 0;
   a.scratch = h->scratch.as<double>();
+  a.nsplit = nsplit;
+  a.mpad = ntiles * kTM;
+  a.part = nullptr;
+  if (nsplit > 1) {
+    VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)(nsplit + 2) * a.mpad));
+    a.part = h->Tws.as<double>();
+  }
   a.score = score; a.mu = mu; a.sigma = sigma; a.linf = linf;
   a.clamp_count = h->small.as<int>();  // slot 0
   const bool need_linf = (linf != nullptr) || (a.apply_tr && a.radius <= 0.5);
-  const size_t sm = score_smem_bytes(h->dc, h->dk);
+  const size_t sm = score_smem_bytes(h->dc, h->dk, need_linf);
+  if (sm > 227 * 1024) {
+    set_error("score kernel needs %zu bytes of shared memory (Dc=%d with trust-region distance)", sm, h->dc);
+    return VZGP_ERR_UNSUPPORTED;
+  }
   if (need_linf) {
     VZ_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_score<true><<<grid, kThreads, sm, h->stream>>>(a);
@@ -301,6 +425,11 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
   }
   VZ_CHECK_LAUNCH();
   h->launches++;
+  if (nsplit > 1) {
+    k_score_finalize<<<(M + 255) / 256, 256, 0, h->stream>>>(a);
+    VZ_CHECK_LAUNCH();
+    h->launches++;
+  }
   return 0;
 }
 
