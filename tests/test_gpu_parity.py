@@ -254,9 +254,16 @@ def test_c2_full_size_properties(dev):
   out2 = dev.score(sub, acq)
   dev.synchronize()
   np.testing.assert_allclose(out2['score'].cpu().numpy(), sc[sel], atol=1e-12, rtol=0)
-  out3 = dev.score(xs, acq)
+  out3 = dev.score(xs, acq, with_aux=True)
   dev.synchronize()
   np.testing.assert_array_equal(out3['score'].cpu().numpy(), sc)
+  out4, out5 = dev.score(xs, acq), None
+  dev.synchronize()
+  first = out4['score'].cpu().numpy().copy()
+  out5 = dev.score(xs, acq)
+  dev.synchronize()
+  np.testing.assert_array_equal(out5['score'].cpu().numpy(), first)
+  np.testing.assert_allclose(first, sc, atol=1e-12, rtol=0)  # scaled-feature path vs difference-first path
   # (3) posterior sanity: 0 <= var <= sf2 + sn2, and UCB identity
   sd = out['stddev'].cpu().numpy(); mu = out['mean'].cpu().numpy()
   assert sd.min() >= 0 and sd.max() <= np.sqrt(1.0 + 1e-3) + 1e-12

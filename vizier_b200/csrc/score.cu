@@ -74,13 +74,13 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
                : "d"(a), "d"(b));
 }
 
-// Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 16, 4-stage cp.async
+// Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 32, 3-stage cp.async
 // ring.  16 warps as 4 (M) x 4 (N): each warp owns a 16 x 32 block = 2 x 4 DMMA tiles.
 constexpr int kTM = 64;          // candidates per tile
 constexpr int kBN = 128;         // output columns per pass
-constexpr int kBK = 16;          // k-slab
-constexpr int kStages = 4;
-constexpr int kLds = kBK + 4;    // smem row stride (doubles): 160 B rows, conflict-free fragment reads
+constexpr int kBK = 32;          // k-slab
+constexpr int kStages = 3;
+constexpr int kLds = kBK + 4;    // smem row stride (doubles): 288 B rows, conflict-free 16-byte fragment reads
 constexpr int kStageDoubles = (kTM + kBN) * kLds;
 constexpr int kLD1 = 66;         // phase-1 smem row stride (64 rows/cols + 2)
 
@@ -110,9 +110,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
   // Without the trust-region distance the features are pre-divided by the length scale (the
   // reference's FeatureScaled form, 2 flops per dimension).  With it, unscaled features are staged
   // so that |a-b| is exact, and the scaling is applied to the squared difference.
-  double* sa = ring + kStages * kStageDoubles;           // [dc][LD]     candidates (transposed)
+  // Phase 1 and phase 2 never overlap in time, so the phase-1 staging buffers alias the ring.
+  double* sa = ring;                                     // [dc][LD]     candidates (transposed)
   double* sb = sa + dc * LD;                             // [2][dc][LD]  trials, double buffered
-  double* s_alpha = sb + 2 * dc * LD;                    // [2][64]
+  double* s_alpha = ring + (kStages * kStageDoubles > 3 * kMaxDc * kLD1 ? kStages * kStageDoubles : 3 * kMaxDc * kLD1);  // [2][64]
   double* s_mu = s_alpha + 128;                          // [64]
   double* s_linf = s_mu + 64;                            // [64]
   double* s_rowsq = s_linf + 64;                         // [4][64]
@@ -262,13 +263,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
       double* Bs = As + kTM * kLds;
       const int k0 = ks * kBK;
 #pragma unroll
-      for (int c = tid; c < kTM * 8; c += kThreads) {         // 64 rows x 8 chunks of 16 B
-        const int r = c >> 3, q = c & 7;
+      for (int c = tid; c < kTM * (kBK / 2); c += kThreads) {  // 64 rows x 16 chunks of 16 B
+        const int r = c >> 4, q = c & 15;
         cp_async16(As + r * kLds + q * 2, scr + (size_t)r * np + k0 + q * 2, true);
       }
 #pragma unroll
-      for (int c = tid; c < kBN * 8; c += kThreads) {         // 128 rows x 8 chunks
-        const int r = c >> 3, q = c & 7;
+      for (int c = tid; c < kBN * (kBK / 2); c += kThreads) {  // 128 rows x 16 chunks
+        const int r = c >> 4, q = c & 15;
         const int gr = jb * kBN + r;
         const bool ok = gr < np;
         cp_async16(Bs + r * kLds + q * 2, a.Linv + (size_t)(ok ? gr : 0) * a.ldi + k0 + q * 2, ok);
@@ -300,22 +301,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
           if (lq < nq) { issue(block_of(lq), lks, ps); advance(); }
           cp_async_commit();
         }
-        const double* As = ring + stage * kStageDoubles + (wm * 16 + fr) * kLds + fk;
-        const double* Bs = ring + stage * kStageDoubles + kTM * kLds + (wn * 32 + fr) * kLds + fk;
+        // Fragment loads are 16 bytes: lane (fr, fk) takes k = 8h + 2fk and 8h + 2fk + 1 of each
+        // 8-wide k group h, i.e. the operands of two DMMA k-steps (the k order inside a slab is
+        // irrelevant as long as A and B agree).
+        const double* As = ring + stage * kStageDoubles + (wm * 16 + fr) * kLds + 2 * fk;
+        const double* Bs = ring + stage * kStageDoubles + kTM * kLds + (wn * 32 + fr) * kLds + 2 * fk;
         const int k0 = ks * kBK;
-        // Linv[c, k] = 0 for k > c: a slab entirely right of this warp's 32 columns contributes
-        // nothing (warp-uniform skip; happens only inside the diagonal 128-block).
-        if (k0 <= col_base + 31) {
+        // Linv[c, k] = 0 for k > c.  k0 and col_base are multiples of 32: slabs right of this
+        // warp's 32 columns contribute nothing; in the diagonal slab (k0 == col_base) the k group
+        // h only reaches column fragments g >= h (static pattern, no predication).
+        if (k0 < col_base) {
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const double a0 = As[qq * 4], a1 = As[8 * kLds + qq * 4];
-            double b[4];
+          for (int h = 0; h < 4; ++h) {
+            const double2 a0 = *reinterpret_cast<const double2*>(As + 8 * h);
+            const double2 a1 = *reinterpret_cast<const double2*>(As + 8 * kLds + 8 * h);
+            double2 b[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) b[g] = Bs[g * 8 * kLds + qq * 4];
+            for (int g = 0; g < 4; ++g) b[g] = *reinterpret_cast<const double2*>(Bs + g * 8 * kLds + 8 * h);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0, b[g]);
-              dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1, b[g]);
+              dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0.x, b[g].x);
+              dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1.x, b[g].x);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0.y, b[g].y);
+              dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1.y, b[g].y);
+            }
+          }
+        } else if (k0 == col_base) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const double2 a0 = *reinterpret_cast<const double2*>(As + 8 * h);
+            const double2 a1 = *reinterpret_cast<const double2*>(As + 8 * kLds + 8 * h);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g < h) continue;  // compile-time: columns of fragment g lie left of k group h
+              const double2 bg = *reinterpret_cast<const double2*>(Bs + g * 8 * kLds + 8 * h);
+              dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0.x, bg.x);
+              dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1.x, bg.x);
+              dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0.y, bg.y);
+              dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1.y, bg.y);
             }
           }
         }
@@ -371,8 +397,9 @@ __global__ void k_score_finalize(const ScoreArgs a) {
 }
 
 size_t score_smem_bytes(int dc, int dk, bool with_linf) {
-  (void)with_linf;
-  return sizeof(double) * (kStages * kStageDoubles + dc * kLD1 * 3 + 128 + 64 * 2 + 256) +
+  (void)with_linf; (void)dc;
+  const size_t big = kStages * kStageDoubles > 3 * kMaxDc * kLD1 ? kStages * kStageDoubles : 3 * kMaxDc * kLD1;
+  return sizeof(double) * (big + 128 + 64 * 2 + 256) +
          sizeof(int32_t) * dk * 2 * kLD1 + kMaxDc;
 }
 
