@@ -87,7 +87,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(
-          ['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+          ['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20'],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
@@ -241,7 +241,6 @@ def run_gpu(args):
   torch.cuda.synchronize()
   if dist is not None:
     dist.barrier()
-  clocks = sampler.stop() if rank == 0 else None
   launches = dev.launch_count - l0
   total_ms = t_start.elapsed_time(t_end)
   kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
@@ -261,6 +260,7 @@ def run_gpu(args):
     dev.score_host(host_x[i % 2], acq, score_out=host_s)
   torch.cuda.synchronize()
   e2e_s = time.perf_counter() - t0
+  clocks = sampler.stop() if rank == 0 else None
 
   if dist is not None:
     t = torch.tensor([total_ms, kern_ms, e2e_s * 1e3], dtype=torch.float64, device=dev.device)
@@ -280,10 +280,14 @@ def run_gpu(args):
   hbm_peak, hbm_src = hbm_peak_gbs()
   hbm_ach = algorithmic_bytes_per_candidate(DIM) * M_POOL / (kern_ms * 1e-3) * 1e-9
   traffic = None
-  tp = os.path.join(ROOT, 'profiles', 'score_kernel_traffic_r01.json')
-  if os.path.exists(tp):
+  tp = os.path.join(ROOT, 'profiles', 'score_kernel_ncu_r01_latest.json')
+  if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one k_score launch (ncu --set full)
     try:
-      traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+      j = json.load(open(tp))
+      def _b(k):
+        v, u = float(j[k]['value']), j[k]['unit'].lower()
+        return v * {'gbyte': 1e9, 'mbyte': 1e6, 'kbyte': 1e3, 'byte': 1.0}[u]
+      traffic = _b('dram__bytes_read.sum') + _b('dram__bytes_write.sum')
     except Exception:  # pylint: disable=broad-except
       pass
   cpu_v, cpu_dt, cores = (None, None, None)
@@ -320,7 +324,7 @@ def run_gpu(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=50)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   args = ap.parse_args()

@@ -110,65 +110,112 @@ __global__ void k_copy_lower_shift(const double* __restrict__ A, int lda, int n_
   L[(size_t)i * ldl + j] = v;
 }
 
+// Inverse of the lower-triangular 64x64 matrix a (shared memory, row stride 66) into x (same
+// layout): column c is owned by 4 adjacent lanes (k-split), combined with two shuffles, so the 64
+// dependent row steps need no block-wide barrier.  256 threads.
+__device__ __forceinline__ void tri_inverse_64(const double* a, double* x) {
+  const int tid = threadIdx.x, c = tid >> 2, q = tid & 3;
+  for (int i = 0; i < 64; ++i) {
+    double s = 0.0;
+    for (int k = c + q; k < i; k += 4) s = fma(a[i * 66 + k], x[k * 66 + c], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (q == 0) x[i * 66 + c] = (c <= i) ? ((i == c ? 1.0 : 0.0) - s) / a[i * 66 + i] : 0.0;
+    __syncwarp();
+  }
+}
+
 // Factor the 64x64 diagonal block kb in place (lower), zero its upper triangle, and write
 // its inverse into the same block of Linv.  flag[0] is set to 1 if a pivot is not a
 // positive finite number (the factor then holds NaN, like jnp.linalg.cholesky).
+// The block lives in registers (thread (ti,tj) owns a 4x4 sub-block); each of the 64 column
+// steps broadcasts the raw pivot column through shared memory and costs one barrier:
+//   a[i][k] -= a[i][j]*a[k][j]/a[j][j]   (k > j),   l[i][j] = a[i][j]/sqrt(a[j][j]).
 __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ L, int ld, int kb,
                                                    double* __restrict__ Linv, int ldi,
                                                    int* __restrict__ flag) {
   extern __shared__ double smem[];
-  double (*a)[65] = reinterpret_cast<double (*)[65]>(smem);
-  double (*x)[65] = reinterpret_cast<double (*)[65]>(smem + 64 * 65);
-  double (*part)[64] = reinterpret_cast<double (*)[64]>(smem + 2 * 64 * 65);
-  __shared__ int bad;
+  double* a = smem;             // [64][66]
+  double* x = smem + 64 * 66;   // [64][66]
+  __shared__ double col[2][64];
   double* blk = L + (size_t)kb * 64 * ld + kb * 64;
-  const int tid = threadIdx.x;
-  if (tid == 0) bad = 0;
-  for (int e = tid; e < 64 * 64; e += 256) {
-    int i = e >> 6, j = e & 63;
-    a[i][j] = blk[(size_t)i * ld + j];
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+  double r[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const double2 v0 = *reinterpret_cast<const double2*>(blk + (size_t)(4 * ti + p) * ld + 4 * tj);
+    const double2 v1 = *reinterpret_cast<const double2*>(blk + (size_t)(4 * ti + p) * ld + 4 * tj + 2);
+    r[p][0] = v0.x; r[p][1] = v0.y; r[p][2] = v1.x; r[p][3] = v1.y;
+  }
+  bool bad = false;
+  double* lc = x;  // [64] scaled pivot column (x is free until the inverse starts)
+  for (int j = 0; j < 64; ++j) {
+    const int jb = j >> 2, jq = j & 3;
+    double* cb = col[j & 1];
+    if (tj == jb) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        double v = r[p][0];
+        if (jq == 1) v = r[p][1];
+        if (jq == 2) v = r[p][2];
+        if (jq == 3) v = r[p][3];
+        cb[4 * ti + p] = v;
+      }
+    }
+    __syncthreads();
+    const double djj = cb[j];
+    if (!(djj > 0.0) || !isfinite(djj)) bad = true;
+    // LAPACK-style arithmetic: l = a / sqrt(d), then a -= l_i * l_k (keeps retry decisions on
+    // exactly singular inputs identical to a host potrf).
+    if (tj == jb) {
+      const double sd = bad ? nan("") : sqrt(djj);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int i = 4 * ti + p;
+        const double v = (i == j) ? sd : cb[i] / sd;
+        lc[(j & 1) * 64 + i] = v;
+        if (i >= j) {
+          if (jq == 0) r[p][0] = v;
+          if (jq == 1) r[p][1] = v;
+          if (jq == 2) r[p][2] = v;
+          if (jq == 3) r[p][3] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (ti >= tj) {
+      const double* lj = lc + (j & 1) * 64;
+      double li[4], lk[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) { li[p] = lj[4 * ti + p]; lk[p] = lj[4 * tj + p]; }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int i = 4 * ti + p, k = 4 * tj + qq;
+          if (k > j && i >= k) r[p][qq] = fma(-li[p], lk[qq], r[p][qq]);
+        }
+    }
   }
   __syncthreads();
-  for (int j = 0; j < 64; ++j) {
-    if (tid == 0) {
-      double d = a[j][j];
-      if (!(d > 0.0) || !isfinite(d)) { bad = 1; a[j][j] = nan(""); }
-      else a[j][j] = sqrt(d);
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int i = 4 * ti + p, k = 4 * tj + qq;
+      a[i * 66 + k] = (k <= i) ? r[p][qq] : 0.0;
     }
-    __syncthreads();
-    const double dj = a[j][j];
-    if (tid > j && tid < 64) a[tid][j] = a[tid][j] / dj;
-    __syncthreads();
-    // trailing update of the block: a[i][k] -= a[i][j]*a[k][j] for j < k <= i
-    for (int e = tid; e < 64 * 64; e += 256) {
-      int i = e >> 6, k = e & 63;
-      if (k > j && i >= k) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
-    }
-    __syncthreads();
-  }
-  // Inverse by forward substitution, row by row: X[i][c] = (delta_ic - sum_{k<i} a[i][k] X[k][c]) / a[i][i].
-  // Thread (c, q): column c = tid % 64, k-split q = tid / 64 (4-way); partials combined via smem.
-  const int c = tid & 63, q = tid >> 6;
-  for (int i = 0; i < 64; ++i) {
-    double s = 0.0;
-    for (int k = c + q; k < i; k += 4) s = fma(a[i][k], x[k][c], s);  // X[k][c] = 0 for k < c
-    part[q][c] = s;
-    __syncthreads();
-    if (q == 0) {
-      double tot = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
-      double v = 0.0;
-      if (c <= i) v = ((i == c ? 1.0 : 0.0) - tot) / a[i][i];
-      x[i][c] = v;
-    }
-    __syncthreads();
-  }
+  __syncthreads();
+  tri_inverse_64(a, x);
+  __syncthreads();
   double* iblk = Linv + (size_t)kb * 64 * ldi + kb * 64;
-  for (int e = tid; e < 64 * 64; e += 256) {
-    int i = e >> 6, j = e & 63;
-    blk[(size_t)i * ld + j] = (j <= i) ? a[i][j] : 0.0;
-    iblk[(size_t)i * ldi + j] = (j <= i) ? x[i][j] : 0.0;
+  for (int e = tid; e < 64 * 32; e += 256) {
+    const int i = e >> 5, j2 = (e & 31) * 2;
+    *reinterpret_cast<double2*>(blk + (size_t)i * ld + j2) = make_double2(a[i * 66 + j2], a[i * 66 + j2 + 1]);
+    *reinterpret_cast<double2*>(iblk + (size_t)i * ldi + j2) =
+        make_double2(j2 <= i ? x[i * 66 + j2] : 0.0, j2 + 1 <= i ? x[i * 66 + j2 + 1] : 0.0);
   }
-  if (tid == 0 && bad) flag[0] = 1;
+  if (bad && tid == 0) flag[0] = 1;
 }
 
 // Panel solve as a GEMM with the inverted diagonal block:
@@ -306,15 +353,26 @@ __global__ void k_gemv_rows(const double* __restrict__ M, int ld, int nrows, int
   if (lane == 0) out[row] = s;
 }
 
-// out[j] = sum_{i >= j} M[i,j] * v[i]   (M lower triangular: out = M^T v).  One thread per column,
-// rows walked in order so accesses are coalesced across the warp.
-__global__ void k_gemv_lower_T(const double* __restrict__ M, int ld, int np,
-                               const double* __restrict__ v, double* __restrict__ out) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= np) return;
+// out[j] = sum_{i >= j} M[i,j] * v[i]   (M lower triangular: out = M^T v).  One CTA per 64
+// columns; 16 row groups of 64 threads stride the rows (coalesced 512-byte row segments), then a
+// fixed-order shared-memory reduction.
+__global__ void __launch_bounds__(1024) k_gemv_lower_T(const double* __restrict__ M, int ld, int np,
+                                                       const double* __restrict__ v,
+                                                       double* __restrict__ out) {
+  __shared__ double part[16][64];
+  const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + c;
   double s = 0.0;
-  for (int i = j; i < np; ++i) s = fma(M[(size_t)i * ld + j], v[i], s);
-  out[j] = s;
+  for (int i = blockIdx.x * 64 + g; i < np; i += 16)
+    if (i >= j) s = fma(M[(size_t)i * ld + j], v[i], s);
+  part[g][c] = s;
+  __syncthreads();
+  if (g == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t += part[k][c];
+    out[j] = t;
+  }
 }
 
 // r = y - Ky * a  (Ky symmetric, full storage)
@@ -431,7 +489,7 @@ int launch_cross_kernel(vzgp_handle* h, const double* Xs, const int32_t* Zs, int
 
 // Factor `L` in place (already holds the shifted lower triangle, np % 64 == 0) and fill the
 // diagonal blocks of Linv.  flag (device int) is raised on a bad pivot.
-constexpr size_t kDiagSmem = sizeof(double) * (2 * 64 * 65 + 4 * 64);
+constexpr size_t kDiagSmem = sizeof(double) * (2 * 64 * 66);
 
 int potrf_blocked(vzgp_handle* h, double* L, int ld, double* Linv, int ldi, int np, int* flag) {
   const int nb = np / 64;
@@ -490,29 +548,18 @@ int launch_copy_lower_shift(vzgp_handle* h, const double* A, int lda, int n_src,
 __global__ void __launch_bounds__(256) k_diag_inv(const double* __restrict__ L, int ld,
                                                   double* __restrict__ Linv, int ldi) {
   extern __shared__ double smem[];
-  double (*a)[65] = reinterpret_cast<double (*)[65]>(smem);
-  double (*x)[65] = reinterpret_cast<double (*)[65]>(smem + 64 * 65);
-  double (*part)[64] = reinterpret_cast<double (*)[64]>(smem + 2 * 64 * 65);
+  double* a = smem;
+  double* x = smem + 64 * 66;
   const int kb = blockIdx.x, tid = threadIdx.x;
   const double* blk = L + (size_t)kb * 64 * ld + kb * 64;
-  for (int e = tid; e < 64 * 64; e += 256) a[e >> 6][e & 63] = blk[(size_t)(e >> 6) * ld + (e & 63)];
+  for (int e = tid; e < 64 * 64; e += 256) a[(e >> 6) * 66 + (e & 63)] = blk[(size_t)(e >> 6) * ld + (e & 63)];
   __syncthreads();
-  const int c = tid & 63, q = tid >> 6;
-  for (int i = 0; i < 64; ++i) {
-    double s = 0.0;
-    for (int k = c + q; k < i; k += 4) s = fma(a[i][k], x[k][c], s);
-    part[q][c] = s;
-    __syncthreads();
-    if (q == 0) {
-      double tot = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
-      x[i][c] = c <= i ? ((i == c ? 1.0 : 0.0) - tot) / a[i][i] : 0.0;
-    }
-    __syncthreads();
-  }
+  tri_inverse_64(a, x);
+  __syncthreads();
   double* iblk = Linv + (size_t)kb * 64 * ldi + kb * 64;
   for (int e = tid; e < 64 * 64; e += 256) {
     int i = e >> 6, j = e & 63;
-    iblk[(size_t)i * ldi + j] = (j <= i) ? x[i][j] : 0.0;
+    iblk[(size_t)i * ldi + j] = (j <= i) ? x[i * 66 + j] : 0.0;
   }
 }
 
@@ -532,7 +579,7 @@ int launch_gemv_rows(vzgp_handle* h, const double* M, int ld, int np, const doub
   return 0;
 }
 int launch_gemv_lower_T(vzgp_handle* h, const double* M, int ld, int np, const double* v, double* out) {
-  k_gemv_lower_T<<<(np + 127) / 128, 128, 0, h->stream>>>(M, ld, np, v, out);
+  k_gemv_lower_T<<<np / 64, 1024, 0, h->stream>>>(M, ld, np, v, out);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;
