@@ -199,7 +199,7 @@ def run_gpu(args):
   x, y, th = make_problem()
   params = gp.GPHyperParams(th['sf2'], th['ls2'], th['sn2'])
   dev.fit(x, y, params)  # every rank recomputes the (deterministic) factorisation: no broadcast needed
-  from vizier_b200.multi_gpu import trust_radius, global_topk
+  from vizier_b200.multi_gpu import trust_radius, TopkExchange
   acq = gp.Acquisition(1.8, True, trust_radius(N_TRIALS, DIM, 0))
 
   # rotating candidate pools: 10 x 16 MB = 160 MB > 126 MB L2, so no step re-reads inputs from L2
@@ -208,12 +208,13 @@ def run_gpu(args):
            for i in range(n_pools)]
   outs = [{'score': torch.empty(M_POOL, dtype=torch.float64, device=dev.device)} for _ in range(2)]
   stream = dev.stream
+  exchange = TopkExchange(dist, dev.device, DIM, 1) if dist is not None else None
 
   def step(i):
     res = dev.score(pools[i % n_pools], acq, out=outs[i % 2])
     idx, val = dev.topk(res['score'], 1)  # device top-1 + 16-byte readback (syncs the stream)
     if dist is not None:
-      global_topk(dist, idx + rank * M_POOL, val, pools[i % n_pools][idx[0]:idx[0] + 1], 1)
+      exchange(idx + rank * M_POOL, val, pools[i % n_pools][idx[0]].cpu().numpy())
     return idx, val
 
   for i in range(args.warmup):
@@ -236,7 +237,7 @@ def run_gpu(args):
     ev[i][1].record(stream)
     idx, val = dev.topk(res['score'], 1)
     if dist is not None:
-      global_topk(dist, idx + rank * M_POOL, val, pools[i % n_pools][idx[0]:idx[0] + 1], 1)
+      exchange(idx + rank * M_POOL, val, pools[i % n_pools][idx[0]].cpu().numpy())
   t_end.record(stream)
   torch.cuda.synchronize()
   if dist is not None:

@@ -503,10 +503,47 @@ int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq*
     VZ_TRY(launch_eagle_seed_priors(h, e, prior, prior_r, n_prior, ord, chosen_r));
   }
   const int steps = (cfg->max_evaluations - 1) / B + 1;
-  for (int t = 0; t < steps; ++t) {
+  auto one_step = [&]() -> int {
     VZ_TRY(launch_eagle_suggest(h, e));
     VZ_TRY(launch_score(h, e.batch, nullptr, B, acq, e.batch_r, nullptr, nullptr, nullptr));
     VZ_TRY(launch_eagle_update(h, e));
+    return 0;
+  };
+  // Step 0 runs eagerly (it sizes every workspace); the remaining steps replay one captured
+  // CUDA graph of the suggest -> score -> update sequence: the iteration counter and all state
+  // live in device memory, so the launches are identical and the host only enqueues graphs.
+  VZ_TRY(one_step());
+  if (steps > 1) {
+    const int64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    VZ_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    int st = one_step();
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (st < 0 || ce != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      if (st >= 0) set_error("eagle: stream capture failed: %s", cudaGetErrorString(ce));
+      return st < 0 ? st : VZGP_ERR_CUDA;
+    }
+    const int64_t per_step = h->launches - l0;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      set_error("eagle: cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+      return VZGP_ERR_CUDA;
+    }
+    h->launches = l0;  // the capture itself executed nothing
+    for (int t = 1; t < steps; ++t) {
+      ce = cudaGraphLaunch(exec, h->stream);
+      if (ce != cudaSuccess) break;
+      h->launches += per_step;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      set_error("eagle: cudaGraphLaunch: %s", cudaGetErrorString(ce));
+      return VZGP_ERR_CUDA;
+    }
   }
   VZ_CUDA(cudaMemcpyAsync(best_x, e.best_x, sizeof(double) * (size_t)count * D, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaMemcpyAsync(best_score, e.best_r, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));

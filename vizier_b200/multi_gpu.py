@@ -21,20 +21,49 @@ def merge_topk(indices: np.ndarray, values: np.ndarray, features: np.ndarray, co
   return indices[order], values[order], features[order]
 
 
+class TopkExchange:
+  """Reusable buffers for the per-suggest collective: one pinned host staging array, one device
+  payload, one device gather target.  Per call: 1 H2D (count*(D+2) doubles), 1 NCCL all-gather,
+  1 D2H of world*count*(D+2) doubles."""
+
+  def __init__(self, dist, device, dim: int, count: int):
+    import torch
+    self.dist, self.count, self.dim = dist, count, dim
+    self.world = dist.get_world_size()
+    self.host = torch.empty((count, dim + 2), dtype=torch.float64).pin_memory()
+    self.payload = torch.empty((count, dim + 2), dtype=torch.float64, device=device)
+    self.gathered = torch.empty((self.world * count, dim + 2), dtype=torch.float64, device=device)
+    self.host_out = torch.empty((self.world * count, dim + 2), dtype=torch.float64).pin_memory()
+
+  def __call__(self, idx: np.ndarray, val: np.ndarray, x_host: np.ndarray):
+    h = self.host.numpy()
+    h[:, 0] = val
+    h[:, 1] = idx          # global indices < 2^53 are exact in fp64
+    h[:, 2:] = x_host
+    self.payload.copy_(self.host, non_blocking=True)
+    self.dist.all_gather_into_tensor(self.gathered, self.payload)
+    self.host_out.copy_(self.gathered, non_blocking=False)
+    g = self.host_out.numpy()
+    return merge_topk(g[:, 1].astype(np.int64), g[:, 0], g[:, 2:], self.count)
+
+
 def global_topk(dist, idx: np.ndarray, val: np.ndarray, x, count: int):
   """All-gathers each rank's local top-`count` (global indices, scores, feature rows) and merges.
 
-  idx/val: host arrays [count]; x: torch device tensor [count, D].  Returns host arrays.
+  idx/val: host arrays [count]; x: torch tensor [count, D] (device or host).  Returns host arrays.
   """
   import torch
+  dev = x.device if x.is_cuda else torch.device('cpu')
+  ex = TopkExchange(dist, dev, x.shape[1], count) if x.is_cuda else None
+  if ex is not None:
+    return ex(np.asarray(idx), np.asarray(val), x.cpu().numpy())
   world = dist.get_world_size()
   d = x.shape[1]
-  payload = torch.empty((count, d + 2), dtype=torch.float64, device=x.device)
-  payload[:, 0] = torch.from_numpy(np.asarray(val, np.float64)).to(x.device)
-  # global indices < 2^53 are exact in fp64
-  payload[:, 1] = torch.from_numpy(np.asarray(idx, np.float64)).to(x.device)
+  payload = torch.empty((count, d + 2), dtype=torch.float64)
+  payload[:, 0] = torch.from_numpy(np.asarray(val, np.float64))
+  payload[:, 1] = torch.from_numpy(np.asarray(idx, np.float64))
   payload[:, 2:] = x
-  gathered = torch.empty((world * count, d + 2), dtype=torch.float64, device=x.device)
+  gathered = torch.empty((world * count, d + 2), dtype=torch.float64)
   dist.all_gather_into_tensor(gathered, payload)
-  g = gathered.cpu().numpy()
+  g = gathered.numpy()
   return merge_topk(g[:, 1].astype(np.int64), g[:, 0], g[:, 2:], count)
