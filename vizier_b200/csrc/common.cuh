@@ -121,6 +121,7 @@ struct vzgp_handle {
   vzgp::DevBuf Tws;     // [np x np] second temporary
   vzgp::DevBuf Kinv;    // [np x np]
   vzgp::DevBuf scratch; // per-CTA K* tiles for the score kernel
+  void* scratch_window = nullptr;  // base of the L2 persisting window currently installed
   vzgp::DevBuf small;   // flags, partial reductions
   vzgp::DevBuf xs_dev;  // staging for *_host entry points
   vzgp::DevBuf out_dev;

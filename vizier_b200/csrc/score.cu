@@ -18,6 +18,7 @@
 //            and row-summed in registers, W is never stored.
 //   epilogue var = sf2 + sn2 - sum W^2 (clamped at 0), sigma, UCB, trust region, outputs.
 #include <climits>
+#include <cstring>
 
 #include "launchers.h"
 #include "tiles.cuh"
@@ -414,7 +415,31 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
   if (ntiles * 2 <= h->sm_count && nblocks >= 2) nsplit = (nblocks + 1) / 2;
   const int nwork = ntiles * nsplit;
   const int grid = nwork < h->sm_count ? nwork : h->sm_count;
-  VZ_TRY(h->scratch.reserve((size_t)grid * kTM * h->np * sizeof(double)));
+  const size_t scratch_bytes = (size_t)grid * kTM * h->np * sizeof(double);
+  if (scratch_bytes > h->scratch.bytes || h->scratch_window != h->scratch.ptr) {
+    VZ_TRY(h->scratch.reserve(scratch_bytes));
+    // The K* scratch is written and re-read by the same CTA tile after tile: pin it in L2
+    // (persisting access-policy window) so its dirty lines are overwritten in place instead of
+    // being evicted to HBM.  Best effort: failures only cost DRAM write-backs.
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+      size_t want = h->scratch.bytes;
+      if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      size_t win = h->scratch.bytes;
+      if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
+      attr.accessPolicyWindow.base_ptr = h->scratch.ptr;
+      attr.accessPolicyWindow.num_bytes = win;
+      attr.accessPolicyWindow.hitRatio = win > 0 ? (float)((double)want / (double)win > 1.0 ? 1.0 : (double)want / (double)win) : 0.f;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
+    h->scratch_window = h->scratch.ptr;
+  }
   ScoreArgs a;
   a.Xs = Xs; a.Zs = Zs; a.M = M;
   a.XT = h->XT.as<double>(); a.Z = h->Z.as<int32_t>();
