@@ -17,6 +17,8 @@
 //            Linv is lower triangular (k <= j, all-zero fragments skipped); each block is squared
 //            and row-summed in registers, W is never stored.
 //   epilogue var = sf2 + sn2 - sum W^2 (clamped at 0), sigma, UCB, trust region, outputs.
+#include <cuda.h>
+
 #include <climits>
 #include <cstring>
 
@@ -26,9 +28,13 @@
 namespace vzgp {
 
 using GP1 = GemmCfg<64, 64, 16, 2, 4>;  // phase-1 thread mapping: 512 threads, 2x4 outputs each
-constexpr int kThreads = 512;
+constexpr int kThreads = 512;        // consumer threads (16 math warps)
+constexpr int kBlockThreads = 544;   // + one TMA producer warp
 
 struct ScoreArgs {
+  // TMA descriptors (must stay first: 64-byte alignment inside the __grid_constant__ parameter).
+  alignas(64) CUtensorMap mapA;  // scratch  as [gridDim.x*64 rows][np], box 64 x 16, SWIZZLE_128B
+  alignas(64) CUtensorMap mapB;  // Linv     as [np rows][np],           box 128 x 16, SWIZZLE_128B
   const double* Xs;
   const int32_t* Zs;
   int M;
@@ -75,14 +81,45 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
                : "d"(a), "d"(b));
 }
 
+// ---- mbarrier / TMA (cp.async.bulk.tensor) primitives --------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 2-D tile load: box origin (c0 = column / innermost, c1 = row); completion bytes land on `bar`.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
 // Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 32, 3-stage cp.async
 // ring.  16 warps as 4 (M) x 4 (N): each warp owns a 16 x 32 block = 2 x 4 DMMA tiles.
 constexpr int kTM = 64;          // candidates per tile
 constexpr int kBN = 128;         // output columns per pass
-constexpr int kBK = 32;          // k-slab
-constexpr int kStages = 3;
-constexpr int kLds = kBK + 4;    // smem row stride (doubles): 288 B rows, conflict-free 16-byte fragment reads
-constexpr int kStageDoubles = (kTM + kBN) * kLds;
+constexpr int kBK = 32;          // k-slab = two TMA boxes of 16 doubles (one 128-byte swizzle atom per row)
+constexpr int kStages = 4;
+// One stage: A half0 | A half1 | B half0 | B half1, each a dense [rows][16] box written by TMA with
+// the 128-byte swizzle (16-byte chunk c of row r lands at chunk c ^ (r & 7)).
+constexpr int kAHalf = kTM * 16;                 // doubles
+constexpr int kBHalf = kBN * 16;
+constexpr int kStageDoubles = 2 * (kAHalf + kBHalf);   // 6144 doubles = 48 KB
+constexpr unsigned kStageBytes = kStageDoubles * sizeof(double);
 constexpr int kLD1 = 66;         // phase-1 smem row stride (64 rows/cols + 2)
 
 // Final score from the reduced pieces (shared by the fused epilogue and the split finalize kernel).
@@ -103,11 +140,13 @@ __device__ __forceinline__ void emit_score(const ScoreArgs& a, int m, double rs,
 }
 
 template <bool WITH_LINF>
-__global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
-  extern __shared__ double smem[];
+__global__ void __launch_bounds__(kBlockThreads, 1) k_score(const __grid_constant__ ScoreArgs a) {
+  extern __shared__ double smem_raw[];
+  // the swizzled TMA boxes need a 1024-byte aligned base
+  double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int LD = kLD1;
   const int dc = a.kp.dc, dk = a.kp.dk, np = a.np;
-  double* ring = smem;                                   // [kStages][kTM + kBN][kLds]
+  double* ring = smem;                                   // [kStages][kStageDoubles]
   // Without the trust-region distance the features are pre-divided by the length scale (the
   // reference's FeatureScaled form, 2 flops per dimension).  With it, unscaled features are staged
   // so that |a-b| is exact, and the scaling is applied to the squared difference.
@@ -118,7 +157,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
   double* s_mu = s_alpha + 128;                          // [64]
   double* s_linf = s_mu + 64;                            // [64]
   double* s_rowsq = s_linf + 64;                         // [4][64]
-  int32_t* za = reinterpret_cast<int32_t*>(s_rowsq + 256);  // [dk][LD]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_rowsq + 256);  // [kStages] TMA bytes landed
+  uint64_t* empty_bar = full_bar + kStages;                         // [kStages] all 16 math warps released the stage
+  int32_t* za = reinterpret_cast<int32_t*>(full_bar + 8);  // [dk][LD]
   int32_t* zb = za + dk * LD;                            // [dk][LD]
   uint8_t* s_mask = reinterpret_cast<uint8_t*>(zb + dk * LD);  // [kMaxDc]
 
@@ -128,7 +169,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
   const int fr = lane >> 2, fk = lane & 3;     // fragment row / k within a DMMA tile
   double* scr = a.scratch + (size_t)blockIdx.x * kTM * np;
   if (tid < kMaxDc) s_mask[tid] = a.tr_mask[tid];
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
   int clamped = 0;
+  unsigned slab_n = 0;   // slabs issued (producer) / consumed (math warps) since kernel start: ring position and phase
+  const bool is_producer = warp == kThreads / 32;
+  auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(kThreads) : "memory"); };
 
   const int ntiles = (a.M + kTM - 1) / kTM;
   const int nblocks = (np + kBN - 1) / kBN;
@@ -139,7 +188,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
   for (int work = blockIdx.x; work < ntiles * nsplit; work += gridDim.x) {
     const int tile = work / nsplit, split = work - tile * nsplit;
     const int m0 = tile * kTM;
-    __syncthreads();  // previous tile fully consumed (sa, s_mu, s_rowsq, ring)
+    // Work split of this tile's phase 2 (identical for producer and consumers).
+    const int nq = (nsplit == 1) ? nblocks : ((split == nblocks - 1 - split) ? 1 : 2);
+    auto block_of = [&](int q) { return (nsplit == 1) ? q : (q == 0 ? split : nblocks - 1 - split); };
+    auto slabs_in = [&](int jb) { int kend = (jb + 1) * kBN; if (kend > np) kend = np; return kend / kBK; };
+    if (is_producer) {
+      // ---- TMA producer warp: waits for phase 1 of this tile, then streams every slab of the
+      // tile through the ring, gated only by the per-stage empty barriers.
+      __syncthreads();
+      if (lane == 0) {
+        for (int q = 0; q < nq; ++q) {
+          const int jb = block_of(q), nsl = slabs_in(jb);
+          for (int ks = 0; ks < nsl; ++ks) {
+            const int stage = slab_n % kStages;
+            mbar_wait(empty_bar + stage, ((slab_n / kStages) & 1) ^ 1);
+            double* base = ring + stage * kStageDoubles;
+            const int k0 = ks * kBK;
+            mbar_expect_tx(full_bar + stage, kStageBytes);
+            tma_load_2d(base, &a.mapA, k0, (int)blockIdx.x * kTM, full_bar + stage);
+            tma_load_2d(base + kAHalf, &a.mapA, k0 + 16, (int)blockIdx.x * kTM, full_bar + stage);
+            tma_load_2d(base + 2 * kAHalf, &a.mapB, k0, jb * kBN, full_bar + stage);          // rows >= np: zero fill
+            tma_load_2d(base + 2 * kAHalf + kBHalf, &a.mapB, k0 + 16, jb * kBN, full_bar + stage);
+            ++slab_n;
+          }
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    consumer_sync();  // previous tile fully consumed by the math warps (sa, s_mu, s_rowsq, ring)
     // candidate tile, transposed; scaled by 1/ls like the reference's FeatureScaled kernel
     for (int e = tid; e < kTM * dc; e += kThreads) {
       const int r = e / dc, d = e - r * dc;
@@ -147,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
       const double v = gr < a.M ? __ldg(a.Xs + (size_t)gr * dc + d) : 0.0;
       sa[d * LD + r] = WITH_LINF ? v : v * a.kp.inv_ls_c[d];
     }
-    if (dk > 0) stage_rows_T_i32(a.Zs, a.M, dk, m0, kTM, za, LD);
+    if (dk > 0) stage_rows_T_i32(a.Zs, a.M, dk, m0, kTM, za, LD, kThreads);
 
     // ---------------- phase 1: K* tile, mean, trust-region distance ----------------
     // Trial rows arrive pre-transposed and pre-scaled (XT), 64 columns per step, through a
@@ -172,10 +249,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
       if (jb + 1 < nj) stage_trials(jb + 1, buf ^ 1);   // buffer buf^1 was released by the barrier below
       cp_async_commit();
       cp_async_wait<1>();
-      __syncthreads();
+      consumer_sync();
       if (dk > 0) {  // categorical rows are rare: staged synchronously
-        stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD);
-        __syncthreads();
+        stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD, kThreads);
+        consumer_sync();
       }
       const double* sbj = sb + buf * dc * LD;
       const double* alj = s_alpha + buf * 64;
@@ -234,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
         *reinterpret_cast<double2*>(dst + GP1::col_of(tx, 0)) = make_double2(kv[0], kv[1]);
         *reinterpret_cast<double2*>(dst + GP1::col_of(tx, 2)) = make_double2(kv[2], kv[3]);
       }
-      __syncthreads();  // everyone is done with buffer `buf` (and zb) before it is refilled
+      consumer_sync();  // everyone is done with buffer `buf` (and zb) before it is refilled
     }
     cp_async_wait<0>();
 #pragma unroll
@@ -249,42 +326,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
         s_linf[GP1::row_of(ty, i)] = lmin[i];
       }
     }
-    __syncthreads();  // this CTA's scratch tile is complete and visible to all its threads
+    fence_proxy_async();  // generic-proxy writes (scratch tile, aliased smem) before async-proxy (TMA) accesses
+    __syncthreads();      // this CTA's scratch tile is complete and visible
 
     // ---------------- phase 2: row sums of (K* Linv^T)^2 on the DMMA pipe ----------------
     // Slab (jb, ks): A = scratch[0:64, ks*16 : +16], B = Linv[jb*128 : +128, ks*16 : +16];
     // block jb needs ks < min(np, (jb+1)*128)/16 because Linv is lower triangular.  The slab
     // stream is flattened over blocks so the cp.async ring never drains between blocks.
     // With nsplit > 1 this CTA takes blocks {split, nblocks-1-split} (balanced triangular work).
-    const int nq = (nsplit == 1) ? nblocks : ((split == nblocks - 1 - split) ? 1 : 2);
-    auto block_of = [&](int q) { return (nsplit == 1) ? q : (q == 0 ? split : nblocks - 1 - split); };
-    auto slabs_in = [&](int jb) { int kend = (jb + 1) * kBN; if (kend > np) kend = np; return kend / kBK; };
-    auto issue = [&](int jb, int ks, int stage) {
-      double* As = ring + stage * kStageDoubles;
-      double* Bs = As + kTM * kLds;
-      const int k0 = ks * kBK;
-#pragma unroll
-      for (int c = tid; c < kTM * (kBK / 2); c += kThreads) {  // 64 rows x 16 chunks of 16 B
-        const int r = c >> 4, q = c & 15;
-        cp_async16(As + r * kLds + q * 2, scr + (size_t)r * np + k0 + q * 2, true);
-      }
-#pragma unroll
-      for (int c = tid; c < kBN * (kBK / 2); c += kThreads) {  // 128 rows x 16 chunks
-        const int r = c >> 4, q = c & 15;
-        const int gr = jb * kBN + r;
-        const bool ok = gr < np;
-        cp_async16(Bs + r * kLds + q * 2, a.Linv + (size_t)(ok ? gr : 0) * a.ldi + k0 + q * 2, ok);
-      }
-    };
-    int lq = 0, lks = 0;  // load cursor
-    auto advance = [&]() { if (++lks == slabs_in(block_of(lq))) { lks = 0; ++lq; } };
-#pragma unroll
-    for (int s = 0; s < kStages - 1; ++s) {
-      if (lq < nq) { issue(block_of(lq), lks, s); advance(); }
-      cp_async_commit();
-    }
     double rowsq[2] = {0.0, 0.0};
-    int stage = 0;
     for (int q = 0; q < nq; ++q) {
       const int jb = block_of(q);
       double acc[2][4][2];
@@ -295,18 +345,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
       const int nsl = slabs_in(jb);
       const int col_base = jb * kBN + wn * 32;   // first output column of this warp
       for (int ks = 0; ks < nsl; ++ks) {
-        cp_async_wait<kStages - 2>();
-        __syncthreads();
-        {  // refill the stage consumed in the previous iteration
-          int ps = stage + kStages - 1; if (ps >= kStages) ps -= kStages;
-          if (lq < nq) { issue(block_of(lq), lks, ps); advance(); }
-          cp_async_commit();
-        }
+        const int stage = slab_n % kStages;
+        mbar_wait(full_bar + stage, (slab_n / kStages) & 1);   // TMA bytes of this slab have landed
+        ++slab_n;
         // Fragment loads are 16 bytes: lane (fr, fk) takes k = 8h + 2fk and 8h + 2fk + 1 of each
         // 8-wide k group h, i.e. the operands of two DMMA k-steps (the k order inside a slab is
-        // irrelevant as long as A and B agree).
-        const double* As = ring + stage * kStageDoubles + (wm * 16 + fr) * kLds + 2 * fk;
-        const double* Bs = ring + stage * kStageDoubles + kTM * kLds + (wn * 32 + fr) * kLds + 2 * fk;
+        // irrelevant as long as A and B agree).  Row r = ... + fr, so the swizzle XOR is fr.
+        const double* stg = ring + stage * kStageDoubles;
+        const double* Arow0 = stg + (wm * 16 + fr) * 16;            // + half*kAHalf + chunk*2
+        const double* Brow0 = stg + 2 * kAHalf + (wn * 32 + fr) * 16;
         const int k0 = ks * kBK;
         // Linv[c, k] = 0 for k > c.  k0 and col_base are multiples of 32: slabs right of this
         // warp's 32 columns contribute nothing; in the diagonal slab (k0 == col_base) the k group
@@ -314,11 +361,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
         if (k0 < col_base) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const double2 a0 = *reinterpret_cast<const double2*>(As + 8 * h);
-            const double2 a1 = *reinterpret_cast<const double2*>(As + 8 * kLds + 8 * h);
+            const int co = ((((h & 1) * 4 + fk) ^ fr) * 2);   // swizzled 16-byte chunk, in doubles
+            const double2 a0 = *reinterpret_cast<const double2*>(Arow0 + (h >> 1) * kAHalf + co);
+            const double2 a1 = *reinterpret_cast<const double2*>(Arow0 + (h >> 1) * kAHalf + 8 * 16 + co);
             double2 b[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) b[g] = *reinterpret_cast<const double2*>(Bs + g * 8 * kLds + 8 * h);
+            for (int g = 0; g < 4; ++g) b[g] = *reinterpret_cast<const double2*>(Brow0 + (h >> 1) * kBHalf + g * 8 * 16 + co);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0.x, b[g].x);
@@ -333,12 +381,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
         } else if (k0 == col_base) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const double2 a0 = *reinterpret_cast<const double2*>(As + 8 * h);
-            const double2 a1 = *reinterpret_cast<const double2*>(As + 8 * kLds + 8 * h);
+            const int co = ((((h & 1) * 4 + fk) ^ fr) * 2);
+            const double2 a0 = *reinterpret_cast<const double2*>(Arow0 + (h >> 1) * kAHalf + co);
+            const double2 a1 = *reinterpret_cast<const double2*>(Arow0 + (h >> 1) * kAHalf + 8 * 16 + co);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (g < h) continue;  // compile-time: columns of fragment g lie left of k group h
-              const double2 bg = *reinterpret_cast<const double2*>(Bs + g * 8 * kLds + 8 * h);
+              const double2 bg = *reinterpret_cast<const double2*>(Brow0 + (h >> 1) * kBHalf + g * 8 * 16 + co);
               dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0.x, bg.x);
               dmma_8x8x4(acc[1][g][0], acc[1][g][1], a1.x, bg.x);
               dmma_8x8x4(acc[0][g][0], acc[0][g][1], a0.y, bg.y);
@@ -346,7 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
             }
           }
         }
-        if (++stage == kStages) stage = 0;
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(empty_bar + stage)) : "memory");
       }
 #pragma unroll
       for (int f = 0; f < 2; ++f)
@@ -364,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score(const ScoreArgs a) {
       rowsq[f] += __shfl_xor_sync(0xffffffffu, rowsq[f], 2);
       if (fk == 0) s_rowsq[wn * 64 + wm * 16 + f * 8 + fr] = rowsq[f];
     }
-    __syncthreads();
+    consumer_sync();
     // ---------------- epilogue ----------------
     if (tid < kTM) {
       const int r = tid, m = m0 + r;
@@ -397,10 +447,45 @@ __global__ void k_score_finalize(const ScoreArgs a) {
   if (clamped) atomicAdd(a.clamp_count, clamped);
 }
 
+// ---- host side: TMA descriptors ------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// fp64 matrix [rows x cols] with row pitch ld (elements); box = box_rows x 16 doubles, 128-byte swizzle.
+static int make_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return VZGP_ERR_CUDA; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(double)};
+  cuuint32_t box[2] = {16, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return VZGP_ERR_CUDA; }
+  return 0;
+}
+
 size_t score_smem_bytes(int dc, int dk, bool with_linf) {
   (void)with_linf; (void)dc;
   const size_t big = kStages * kStageDoubles > 3 * kMaxDc * kLD1 ? kStages * kStageDoubles : 3 * kMaxDc * kLD1;
-  return sizeof(double) * (big + 128 + 64 * 2 + 256) +
+  return 1024 + sizeof(double) * (big + 128 + 64 * 2 + 256 + 8) +
          sizeof(int32_t) * dk * 2 * kLD1 + kMaxDc;
 }
 
@@ -453,6 +538,8 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
   for (int d = 0; d < kMaxDc; ++d)
     a.tr_mask[d] = (d < h->dc) ? (acq->tr_dim_mask ? (acq->tr_dim_mask[d] ? 1 : 0) : 1) : 0;
   a.scratch = h->scratch.as<double>();
+  VZ_TRY(make_map(&a.mapA, a.scratch, (uint64_t)grid * kTM, (uint64_t)h->np, (uint64_t)h->np, kTM));
+  VZ_TRY(make_map(&a.mapB, a.Linv, (uint64_t)h->np, (uint64_t)h->np, (uint64_t)h->np, kBN));
   a.nsplit = nsplit;
   a.mpad = ntiles * kTM;
   a.part = nullptr;
@@ -470,10 +557,10 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
   }
   if (need_linf) {
     VZ_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_score<true><<<grid, kThreads, sm, h->stream>>>(a);
+    k_score<true><<<grid, kBlockThreads, sm, h->stream>>>(a);
   } else {
     VZ_CUDA(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_score<false><<<grid, kThreads, sm, h->stream>>>(a);
+    k_score<false><<<grid, kBlockThreads, sm, h->stream>>>(a);
   }
   VZ_CHECK_LAUNCH();
   h->launches++;

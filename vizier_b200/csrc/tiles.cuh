@@ -18,9 +18,11 @@ __device__ __forceinline__ void stage_rows_T(const double* __restrict__ X, int n
 }
 
 __device__ __forceinline__ void stage_rows_T_i32(const int32_t* __restrict__ Z, int nrows, int dk,
-                                                 int row0, int rows, int32_t* s, int lds) {
+                                                 int row0, int rows, int32_t* s, int lds,
+                                                 int nthreads = 0) {
   const int total = rows * dk;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+  const int stride = nthreads > 0 ? nthreads : (int)blockDim.x;
+  for (int e = threadIdx.x; e < total; e += stride) {
     int r = e / dk, d = e - r * dk;
     int gr = row0 + r;
     s[d * lds + r] = gr < nrows ? __ldg(Z + (size_t)gr * dk + d) : -1;
