@@ -143,7 +143,8 @@ template <bool WITH_LINF>
 __global__ void __launch_bounds__(kBlockThreads, 1) k_score(const __grid_constant__ ScoreArgs a) {
   extern __shared__ double smem_raw[];
   // the swizzled TMA boxes need a 1024-byte aligned base
-  double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared-space pointer so the compiler keeps LDS/STS addressing)
+  double* smem = smem_raw + (((1024u - (static_cast<unsigned>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u) >> 3);
   constexpr int LD = kLD1;
   const int dc = a.kp.dc, dk = a.kp.dk, np = a.np;
   double* ring = smem;                                   // [kStages][kStageDoubles]
