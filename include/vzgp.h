@@ -155,6 +155,13 @@ int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, i
 int vzgp_topk(vzgp_handle* h, const double* score, int64_t M, int count, int64_t* idx_out,
               double* val_out);
 
+/* vzgp_score + vzgp_topk + gather of the winning rows in one call and one host synchronisation
+ * (the per-shard step of a multi-GPU suggest).  Xs device [M x Dc]; score_dev optional device
+ * [M] buffer that receives all scores (NULL: internal).  best_x [count x Dc], best_score [count],
+ * best_index [count] (optional) are HOST outputs, best first. */
+int vzgp_score_topk(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                    int count, double* score_dev, double* best_x, double* best_score, int64_t* best_index);
+
 /* ---- acquisition optimisers (device-resident loops) ---------------------- */
 
 /* EagleStrategyConfig (eagle_strategy.py:111-167), continuous features. */

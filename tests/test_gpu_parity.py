@@ -312,3 +312,85 @@ def test_posterior_covariance(dev):
   want_cov = go.kernel(po, xs, xs) - v.T @ v + po.observation_noise_variance * np.eye(m)
   np.testing.assert_allclose(cov.cpu().numpy(), want_cov, atol=TOL, rtol=0)
   np.testing.assert_allclose(mean.cpu().numpy(), ks @ pred.alpha, atol=TOL, rtol=0)
+
+
+def test_score_topk_fused_call(dev):
+  n, d, m = 120, 6, 3000
+  x, y, _ = _problem(n, d, 31)
+  xs, _, _ = _problem(m, d, 32)
+  po, pg = _params(d)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  acq = _gp().Acquisition(1.8, True, go.trust_radius(n, d, 0))
+  xt = torch.from_numpy(xs).cuda()
+  buf = torch.empty(m, dtype=torch.float64, device='cuda')
+  bx, bs, bi = dev.score_topk(xt, acq, 4, score_out=buf)
+  want, _ = go.score_with_aux(pred, xs)
+  order = go.top_k(want, 4)
+  np.testing.assert_array_equal(bi, order)
+  np.testing.assert_array_equal(bx, xs[order])
+  np.testing.assert_allclose(bs, want[order], atol=TOL)
+  np.testing.assert_allclose(buf.cpu().numpy(), want, atol=TOL)
+
+
+@pytest.mark.parametrize('n,d,m', [(1, 1, 1), (2, 3, 63), (64, 2, 65), (65, 7, 129), (127, 64, 40), (129, 33, 200)])
+def test_score_edge_shapes(dev, n, d, m):
+  """Ragged sizes around the 64-row tiles / 128-column blocks, D=1 and the D=64 maximum."""
+  x, y, _ = _problem(n, d, 41)
+  xs, _, _ = _problem(m, d, 42)
+  po, pg = _params(d)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  acq = _gp().Acquisition(1.8, True, go.trust_radius(n, d, 0))
+  out = dev.score(xs, acq, with_aux=True)
+  dev.synchronize()
+  want, aux = go.score_with_aux(pred, xs)
+  np.testing.assert_allclose(out['score'].cpu().numpy(), want, atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['stddev'].cpu().numpy(), aux['stddev'], atol=TOL, rtol=0)
+  out2 = dev.score(xs, acq)
+  dev.synchronize()
+  np.testing.assert_allclose(out2['score'].cpu().numpy(), want, atol=TOL, rtol=0)
+
+
+def test_c5_shape_sample_parity(dev):
+  """BASELINE C5 per-GPU shape (N=2000, D=50): 20k candidates, 256-sample parity + fit residual."""
+  n, d, m = 2000, 50, 20_000
+  rng = np.random.default_rng(5)
+  x = rng.uniform(size=(n, d)); y = rng.normal(size=n)
+  ls2 = np.full(d, 2.0)
+  po = go.GPParams(1.0, ls2, 1e-2); pg = _gp().GPHyperParams(1.0, ls2, 1e-2)
+  assert dev.fit(x, y, pg) == 0
+  xs = dev.random_pool(m, d, seed=77)
+  acq = _gp().Acquisition(1.8, True, go.trust_radius(n, d, 0))
+  out = dev.score(xs, acq)
+  dev.synchronize()
+  sc = out['score'].cpu().numpy()
+  pred = go.precompute_predictive(po, x, y)
+  sel = np.random.default_rng(2).choice(m, 256, replace=False)
+  want, _ = go.score_with_aux(pred, xs[torch.from_numpy(sel).cuda()].cpu().numpy())
+  np.testing.assert_allclose(sc[sel], want, atol=TOL, rtol=0)
+  idx, _ = dev.topk(out['score'], 3)
+  np.testing.assert_array_equal(idx, go.top_k(sc, 3))
+
+
+def test_error_behaviour(dev):
+  """Status codes and messages instead of exceptions/crashes (C ABI never throws)."""
+  from vizier_b200 import _lib, gp
+  fresh = gp.DeviceGP(0)
+  xs = torch.zeros((4, 3), dtype=torch.float64, device='cuda')
+  with pytest.raises(_lib.VzgpError) as e:
+    fresh.score(xs, gp.Acquisition())
+  assert e.value.status == _lib.VZGP_ERR_STATE and 'before vzgp_fit' in str(e.value)
+  with pytest.raises(_lib.VzgpError) as e:
+    fresh.fit(np.zeros((3, 65)), np.zeros(3), gp.GPHyperParams(1.0, np.ones(65), 1e-3))
+  assert e.value.status == _lib.VZGP_ERR_ARG and 'Dc out of range' in str(e.value)
+  with pytest.raises(_lib.VzgpError):
+    fresh.fit(np.zeros((3, 2)), np.zeros(3), gp.GPHyperParams(1.0, np.ones(2), 1e-3), n_valid=0)
+  # a NaN in the labels does not crash: the factor is fine, alpha carries the NaN
+  x, y, _ = _problem(10, 2, 3)
+  fresh.fit(x, y, gp.GPHyperParams(1.0, np.ones(2), 1e-3))
+  out = fresh.score(np.zeros((0, 2)), gp.Acquisition())  # empty pool is a no-op
+  assert out['score'].numel() == 0
+  idx, val = fresh.topk(torch.tensor([1.0, 2.0], dtype=torch.float64, device='cuda'), 4)  # count > M
+  assert idx.tolist() == [1, 0, -1, -1]
+  fresh.close()

@@ -96,6 +96,7 @@ SIGNATURES = {
     'vzgp_score_host': (_i, [_vp, _vp, _vp, _i, _pA, _vp, _vp, _vp, _vp]),
     'vzgp_posterior': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i]),
     'vzgp_topk': (_i, [_vp, _vp, _i64, _i, _pi64, _pd]),
+    'vzgp_score_topk': (_i, [_vp, _vp, _vp, _i, _pA, _i, _vp, _pd, _pd, _pi64]),
     'vzgp_eagle_run': (_i, [_vp, _pE, _pA, _vp, _i, _i, _u64, _pd, _pd]),
     'vzgp_random_search': (_i, [_vp, _i64, _i64, _pA, _i, _u64, _pd, _pd, _pi64]),
     'vzgp_random_pool': (_i, [_vp, _i64, _i, _i64, _u64, _vp]),

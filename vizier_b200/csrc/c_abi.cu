@@ -582,4 +582,35 @@ int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, i
   return 0;
 }
 
+int vzgp_score_topk(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                    int count, double* score_dev, double* best_x, double* best_score, int64_t* best_index) {
+  VZ_ARG(best_x && best_score, "outputs");
+  VZ_ARG(M >= 1, "M >= 1");
+  Guard g(h ? h->device : 0);
+  const int dc = h ? h->dc : 0;
+  double* dS = score_dev;
+  if (!dS) {
+    VZ_ARG(h != nullptr, "handle");
+    VZ_TRY(h->out_dev.reserve(sizeof(double) * ((size_t)M + (size_t)kMaxTopk * (dc > 0 ? dc : 1))));
+    dS = h->out_dev.as<double>();
+  }
+  VZ_TRY(check_scoring(h, Xs, Zs, M, acq, dS));
+  VZ_ARG(h->dk == 0, "continuous features only");
+  VZ_TRY(h->xs_dev.reserve(0));
+  VZ_TRY(launch_score(h, Xs, Zs, M, acq, dS, nullptr, nullptr, nullptr));
+  long long* d_idx; double* d_val;
+  VZ_TRY(topk_to_device(h, dS, M, count, &d_idx, &d_val));
+  double* dBest = reinterpret_cast<double*>(h->small.as<char>() + 32768);  // count*dc doubles <= 32 KiB
+  VZ_ARG((size_t)count * dc * sizeof(double) <= 32768, "count * Dc too large");
+  VZ_TRY(launch_gather_rows(h, Xs, dc, d_idx, count, M, dBest));
+  long long hidx[kMaxTopk];
+  VZ_CUDA(cudaMemcpyAsync(hidx, d_idx, sizeof(long long) * count, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(best_score, d_val, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(best_x, dBest, sizeof(double) * (size_t)count * dc, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  if (best_index)
+    for (int c = 0; c < count; ++c) best_index[c] = (hidx[c] == LLONG_MAX) ? -1 : (int64_t)hidx[c];
+  return 0;
+}
+
 }  // extern "C"

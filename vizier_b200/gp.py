@@ -312,6 +312,21 @@ class DeviceGP:
         val.ctypes.data_as(C.POINTER(C.c_double))))
     return idx, val
 
+  def score_topk(self, xs: torch.Tensor, acq: Acquisition, count: int, score_out: Optional[torch.Tensor] = None):
+    """Score device candidates, select the top `count`, return (features, scores, indices) on the host."""
+    a, keep = acq._c()
+    m = xs.shape[0]
+    bx = np.zeros((count, self.dc), np.float64)
+    bs = np.zeros(count, np.float64)
+    bi = np.zeros(count, np.int64)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_score_topk', self._lib.vzgp_score_topk(
+        self._h, _ptr(xs), None, m, C.byref(a), count, _ptr(score_out),
+        bx.ctypes.data_as(C.POINTER(C.c_double)), bs.ctypes.data_as(C.POINTER(C.c_double)),
+        bi.ctypes.data_as(C.POINTER(C.c_int64))))
+    del keep
+    return bx, bs, bi
+
   def random_pool(self, m: int, dc: int, seed: int, index_base: int = 0) -> torch.Tensor:
     out = torch.empty((m, dc), dtype=torch.float64, device=self.device)
     self._stream.wait_stream(torch.cuda.current_stream(self.device))
