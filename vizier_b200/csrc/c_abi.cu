@@ -350,6 +350,7 @@ static int check_scoring(vzgp_handle* h, const double* Xs, const int32_t* Zs, in
 
 int vzgp_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                double* score, double* mu, double* sigma, double* linf) {
+  if (h != nullptr && h->fitted && M == 0) return 0;  // empty pool: nothing to do
   VZ_TRY(check_scoring(h, Xs, Zs, M, acq, score));
   Guard g(h->device);
   return launch_score(h, Xs, Zs, M, acq, score, mu, sigma, linf);
