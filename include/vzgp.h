@@ -172,16 +172,22 @@ typedef struct vzgp_eagle_config {
   int pool_size;        /* P, multiple of batch_size */
   int batch_size;       /* B */
   int max_evaluations;  /* steps = (max_evaluations-1)/B + 1 */
+  /* categorical mutation (eagle_strategy.py:149-151) */
+  double categorical_perturbation_factor;       /* 1.0  */
+  double pure_categorical_perturbation_factor;  /* 30.0 (no continuous feature) */
+  double prob_same_category_without_perturbation; /* 0.98 */
 } vzgp_eagle_config;
 
 /* VectorizedOptimizer.__call__ with VectorizedEagleStrategy
  * (vectorized_base.py:324-542; eagle_strategy.py:527-1247) scoring against
- * the fitted model.  prior [n_prior x Dc] device (may be NULL/0) are the
- * observed trials in creation order.  best_x [count x Dc], best_score [count]
- * are HOST outputs, best first.  Randomness: Philox4x32-10 keyed by `seed`. */
+ * the fitted model.  prior [n_prior x Dc] / prior_z [n_prior x Dk] device (may
+ * be NULL/0) are the observed trials in creation order.  cat_sizes (host, [Dk])
+ * = number of categories of each categorical feature (<= 64).  best_x
+ * [count x Dc], best_z [count x Dk], best_score [count] are HOST outputs, best
+ * first.  Randomness: Philox4x32-10 keyed by `seed`. */
 int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
-                   const double* prior, int n_prior, int count, uint64_t seed, double* best_x,
-                   double* best_score);
+                   const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
+                   int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score);
 
 /* RandomVectorizedStrategy with batch = max_evaluations = M
  * (random_vectorized_optimizer.py:32-123): generates M uniform candidates on
@@ -189,13 +195,16 @@ int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq*
  * index_base offsets the Philox element counter so ranks can generate
  * disjoint shards of one global pool: candidate g = index_base + m. */
 int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp_acq* acq,
-                       int count, uint64_t seed, double* best_x, double* best_score,
-                       int64_t* best_index);
+                       const int32_t* cat_sizes, int count, uint64_t seed, double* best_x,
+                       int32_t* best_z, double* best_score, int64_t* best_index);
 
 /* Fill X [M x Dc] (device) with the same Philox uniforms vzgp_random_search
  * uses (stream STREAM_RANDOM_POOL), for parity tests and the benchmark. */
 int vzgp_random_pool(vzgp_handle* h, int64_t M, int Dc, int64_t index_base, uint64_t seed,
                      double* X);
+/* Categorical counterpart: Z [M x Dk] int32 device, uniform over [0, cat_sizes[k]). */
+int vzgp_random_pool_cat(vzgp_handle* h, int64_t M, int Dk, const int32_t* cat_sizes,
+                         int64_t index_base, uint64_t seed, int32_t* Z);
 
 #ifdef __cplusplus
 }

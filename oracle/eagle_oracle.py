@@ -41,6 +41,9 @@ class EagleConfig:
   max_pool_size: int = 100
   normalization_scale: float = 0.5
   prior_trials_pool_pct: float = 0.96
+  categorical_perturbation_factor: float = 1.0
+  pure_categorical_perturbation_factor: float = 30.0
+  prob_same_category_without_perturbation: float = 0.98
 
 
 def default_pool_size(n_features: int, batch_size: Optional[int], cfg: EagleConfig) -> int:
@@ -66,6 +69,11 @@ STREAM_INIT_POOL = 0
 STREAM_PERTURB_SIGN = 1
 STREAM_TRIM = 2
 STREAM_RANDOM_POOL = 3  # RandomVectorizedStrategy candidate pool
+STREAM_INIT_CAT = 4        # categorical features of the initial pool
+STREAM_CAT_LAPLACE = 5     # categorical logit perturbation
+STREAM_CAT_GUMBEL = 6      # Gumbel-max sampling of the mutated categories
+STREAM_TRIM_CAT = 7        # categorical features of re-seeded flies
+STREAM_RANDOM_POOL_CAT = 8
 
 
 def philox4x32(counter: np.ndarray, key: np.ndarray) -> np.ndarray:
@@ -305,3 +313,152 @@ def run_random_optimizer(score_fn, *, dim: int, num_candidates: int, count: int,
   rr = np.where(np.isnan(r), -np.inf, r)
   order = np.lexsort((np.arange(num_candidates), -rr))[:count]
   return xs[order], r[order], order
+
+
+# ----------------------------------------------------------------------------
+# Categorical features (eagle_strategy.py:936-1011, :1046-1073, :293-311)
+# ----------------------------------------------------------------------------
+def laplace_from_uniform(u: np.ndarray) -> np.ndarray:
+  """Standard Laplace draw from u in [0,1) (inverse CDF; shared with csrc/eagle.cu)."""
+  v = u - 0.5
+  return -np.sign(v) * np.log(np.maximum(1.0 - 2.0 * np.abs(v), 1.1102230246251565e-16))
+
+
+def gumbel_from_uniform(u: np.ndarray) -> np.ndarray:
+  return -np.log(-np.log(np.maximum(u, 1e-300)))
+
+
+def uniform_categories(u: np.ndarray, sizes: np.ndarray) -> np.ndarray:
+  """DefaultRandomSampler: uniform over the valid categories of each feature (u [..., Dk])."""
+  return np.minimum((u * sizes).astype(np.int32), np.asarray(sizes, np.int32) - 1)
+
+
+def features_dist_squared_cat(batch, pool, batch_z, pool_z) -> np.ndarray:
+  """eagle_strategy.py:458-468: squared distance + unweighted Hamming distance."""
+  d = features_dist_squared(batch, pool) if batch.shape[1] else np.zeros((batch_z.shape[0], pool_z.shape[0]))
+  if batch_z.shape[1]:
+    d = d + np.sum(batch_z[:, None, :] != pool_z[None, :, :], axis=-1)
+  return d
+
+
+def force_scale(pool, rewards, batch, rewards_batch, cfg: EagleConfig, pool_z=None, batch_z=None) -> np.ndarray:
+  """The normalised force matrix `scale` [B, P] of _create_features (:811-899), MEAN mode."""
+  dk = 0 if pool_z is None else pool_z.shape[1]
+  n_features = pool.shape[1] + dk
+  if dk:
+    dists = features_dist_squared_cat(batch, pool, batch_z, pool_z)
+  else:
+    dists = features_dist_squared(batch, pool)
+  with np.errstate(invalid='ignore'):
+    directions = rewards[None, :] - rewards_batch[:, None]
+  scaled_dir = np.where(directions >= 0.0, cfg.gravity, -cfg.negative_gravity)
+  force = np.exp(-cfg.visibility * dists / n_features * 10.0)
+  scaled_force = scaled_dir * force * np.isfinite(rewards).astype(np.float64)[None, :]
+  pulls = np.maximum(scaled_force, 0.0)
+  push = np.minimum(scaled_force, 0.0)
+  with np.errstate(invalid='ignore', divide='ignore'):
+    npull = cfg.normalization_scale * np.nan_to_num(pulls / np.sum(pulls > 0.0, axis=1, keepdims=True), nan=0.0)
+    npush = cfg.normalization_scale * np.nan_to_num(push / np.sum(push < 0.0, axis=1, keepdims=True), nan=0.0)
+  return npull + npush
+
+
+def categorical_logits(pool_z, batch_z, scale, sizes, cfg: EagleConfig) -> np.ndarray:
+  """_create_logits_vector (:954-985) for every batch member and feature -> [B, Dk, max_size]."""
+  b, dk = batch_z.shape
+  max_size = int(max(sizes)) if dk else 0
+  out = np.full((b, dk, max_size), -np.inf)
+  log_same = np.log(cfg.prob_same_category_without_perturbation)
+  for k in range(dk):
+    s_k = int(sizes[k])
+    with np.errstate(divide='ignore'):
+      log_diff = np.log((1.0 - cfg.prob_same_category_without_perturbation) / (s_k - 1.0)) if s_k > 1 else np.inf
+    for i in range(b):
+      lg = np.array([np.sum(np.where(pool_z[:, k] == c, scale[i], 0.0)) for c in range(max_size)]) + log_diff
+      lg = np.where(np.arange(max_size) < s_k, lg, -np.inf)
+      lg[batch_z[i, k]] += -np.sum(scale[i]) + log_same - log_diff
+      out[i, k] = lg
+  return out
+
+
+def create_features_mixed(pool, pool_z, rewards, batch, batch_z, rewards_batch, perturbations, cat_noise,
+                          gumbel, sizes, cfg: EagleConfig):
+  """_create_features with categorical features.  perturbations [B, Dc] (already scaled),
+  cat_noise [B, Dk, max_size] = laplace * factor * perturbation_i, gumbel [B, Dk, max_size]."""
+  scale = force_scale(pool, rewards, batch, rewards_batch, cfg, pool_z, batch_z)
+  change = scale @ pool - batch * np.sum(scale, axis=-1, keepdims=True)
+  new_c = batch + change + perturbations
+  logits = categorical_logits(pool_z, batch_z, scale, sizes, cfg) + cat_noise
+  new_z = np.zeros_like(batch_z)
+  for k in range(batch_z.shape[1]):
+    s_k = int(sizes[k])
+    if s_k == 1:
+      new_z[:, k] = 0
+    else:
+      new_z[:, k] = np.argmax(logits[:, k, :s_k] + gumbel[:, k, :s_k], axis=-1)  # Gumbel-max = Categorical.sample
+  return new_c, new_z
+
+
+def run_eagle_optimizer_mixed(score_fn, *, dim: int, sizes, pool_size: int, batch_size: int, max_evaluations: int,
+                              count: int, seed: int, cfg: EagleConfig = EagleConfig(), prior_c=None, prior_z=None):
+  """VectorizedOptimizer + eagle strategy with continuous AND categorical features, Philox draws.
+
+  score_fn(xc [B,Dc], xz [B,Dk]) -> [B].  Element numbering of the draws is the contract shared
+  with csrc/eagle.cu (see STREAM_* above): init (p*Dk+k), laplace/gumbel ((b*Dk+k)*Smax+c), trim (b*Dk+k).
+  """
+  sizes = np.asarray(sizes, np.int64)
+  dk = sizes.shape[0]
+  smax = int(sizes.max()) if dk else 0
+  factor = cfg.categorical_perturbation_factor if dim > 0 else cfg.pure_categorical_perturbation_factor
+  pool_c = philox_uniform(seed, STREAM_INIT_POOL, 0, pool_size * dim).reshape(pool_size, dim)
+  pool_z = uniform_categories(philox_uniform(seed, STREAM_INIT_CAT, 0, pool_size * dk).reshape(pool_size, dk), sizes)
+  if prior_c is not None and prior_c.shape[0] > 0:
+    prior_r = score_fn(prior_c, prior_z)
+    order = np.flip(np.arange(prior_r.shape[0]))        # no padded priors here: newest first
+    fc, fz, fr = prior_c[order], prior_z[order], prior_r[order]
+    n_random = int(pool_size * (1 - cfg.prior_trials_pool_pct))
+    left = pool_size - n_random
+    cc, cz, cr = fc[:left].copy(), fz[:left].copy(), fr[:left].copy()
+    for i in range(left, fr.shape[0]):
+      d = features_dist_squared_cat(fc[i][None, :], cc, fz[i][None, :], cz)[0]
+      ind = int(np.argmin(d))
+      if cr[ind] < fr[i]:
+        cc[ind], cz[ind], cr[ind] = fc[i], fz[i], fr[i]
+    n = cr.shape[0]
+    pool_c[n_random:n_random + n] = cc
+    pool_z[n_random:n_random + n] = cz
+  rewards = np.full(pool_size, -np.inf)
+  perts = np.full(pool_size, cfg.perturbation)
+  best_reward = -np.inf
+  best_c = np.zeros((count, dim)); best_z = np.zeros((count, dk), np.int32)
+  best_r = np.full(count, -np.inf); best_id = np.full(count, np.iinfo(np.int64).max, dtype=np.int64)
+  nb = pool_size // batch_size
+  for t in range((max_evaluations - 1) // batch_size + 1):
+    start = (t % nb) * batch_size
+    sl = slice(start, start + batch_size)
+    bc, bz = pool_c[sl].copy(), pool_z[sl].copy()
+    if t >= nb:
+      signs = philox_signs(seed, t, batch_size * dim).reshape(batch_size, dim)
+      lap = laplace_from_uniform(philox_uniform(seed, STREAM_CAT_LAPLACE, t, batch_size * dk * smax)).reshape(batch_size, dk, smax)
+      gum = gumbel_from_uniform(philox_uniform(seed, STREAM_CAT_GUMBEL, t, batch_size * dk * smax)).reshape(batch_size, dk, smax)
+      bc, bz = create_features_mixed(pool_c, pool_z, rewards, bc, bz, rewards[sl], signs * perts[sl][:, None],
+                                     lap * factor * perts[sl][:, None, None], gum, sizes, cfg)
+    bc = np.clip(bc, 0.0, 1.0)
+    r = score_fn(bc, bz)
+    new_best = max(best_reward, float(np.max(r)))
+    if t < nb:
+      pool_c[sl], pool_z[sl], rewards[sl] = bc, bz, r
+    else:
+      improve = r > rewards[sl]
+      nc = np.where(improve[:, None], bc, pool_c[sl]); nz = np.where(improve[:, None], bz, pool_z[sl])
+      nr = np.where(improve, r, rewards[sl]); npert = np.where(improve, perts[sl], perts[sl] * cfg.penalize_factor)
+      trim = (npert < cfg.perturbation_lower_bound) & (nr != new_best)
+      rc = philox_uniform(seed, STREAM_TRIM, t, batch_size * dim).reshape(batch_size, dim)
+      rz = uniform_categories(philox_uniform(seed, STREAM_TRIM_CAT, t, batch_size * dk).reshape(batch_size, dk), sizes)
+      pool_c[sl] = np.where(trim[:, None], rc, nc); pool_z[sl] = np.where(trim[:, None], rz, nz)
+      rewards[sl] = np.where(trim, -np.inf, nr); perts[sl] = np.where(trim, cfg.perturbation, npert)
+    best_reward = new_best
+    ids = np.arange(batch_size, dtype=np.int64) + t * batch_size
+    f = np.concatenate([bc, best_c]); z = np.concatenate([bz, best_z]); rr = np.concatenate([r, best_r]); ii = np.concatenate([ids, best_id])
+    order = np.lexsort((ii, -np.where(np.isnan(rr), -np.inf, rr)))[:count]
+    best_c, best_z, best_r, best_id = f[order], z[order], rr[order], ii[order]
+  return best_c, best_z, best_r

@@ -103,3 +103,35 @@ def test_random_pool_optimizer_factory():
   d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
   sugg = d.suggest(3)
   assert len(sugg) == 3 and len({tuple(sorted(s.parameters.as_dict().items())) for s in sugg}) == 3
+
+
+def test_all_parameter_types_search_space():
+  """gp_bandit_test.py:130-235 runs the designer on `flat_space_with_all_types`; same idea here."""
+  p = vz.ProblemStatement()
+  r = p.search_space.root
+  r.add_float_param('lr', 1e-4, 1e-1, scale_type=vz.ScaleType.LOG)
+  r.add_float_param('x', -1.0, 1.0)
+  r.add_int_param('layers', 1, 6)
+  r.add_discrete_param('bs', [16, 32, 64, 128])
+  r.add_categorical_param('opt', ['adam', 'sgd', 'lion'])
+  r.add_categorical_param('norm', ['bn', 'ln'])
+  p.metric_information.append(vz.MetricInformation(name='obj', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+
+  def f(t):
+    v = t.parameters
+    return (-(np.log10(v['lr'].value) + 2.5) ** 2 - v['x'].value ** 2 - 0.1 * (v['layers'].value - 4) ** 2
+            + (0.5 if v['opt'].value == 'lion' else 0.0) + (0.2 if v['norm'].value == 'ln' else 0.0))
+
+  d = gp_bandit.VizierGPBandit.from_problem(p, seed=7, acquisition_optimizer_factory=small_opt)
+  tid, best = 1, -np.inf
+  for _ in range(12):
+    sugg = d.suggest(2)
+    trials = []
+    for s in sugg:
+      assert p.search_space.contains(s.parameters), s.parameters
+      t = s.to_trial(tid); tid += 1
+      t.complete(vz.Measurement({'obj': float(f(t))}))
+      best = max(best, t.final_measurement.metrics['obj'].value)
+      trials.append(t)
+    d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  assert best > -0.6

@@ -203,7 +203,7 @@ def test_random_search_matches_oracle(dev):
   pred = go.precompute_predictive(po, x, y)
   dev.fit(x, y, pg)
   radius = go.trust_radius(n, d, 0)
-  bx, bs, bi = dev.random_search(m, _gp().Acquisition(1.8, True, radius), count=3, seed=99)
+  bx, _, bs, bi = dev.random_search(m, _gp().Acquisition(1.8, True, radius), count=3, seed=99)
   wx, ws, wi = eo.run_random_optimizer(lambda q: go.score_with_aux(pred, q)[0], dim=d, num_candidates=m, count=3, seed=99)
   np.testing.assert_array_equal(bi, wi)
   np.testing.assert_array_equal(bx, wx)
@@ -225,7 +225,7 @@ def test_eagle_run_matches_oracle(dev, n, d, pool, batch, steps):
   cfg = _lib.EagleConfig(cfg_o.visibility, cfg_o.gravity, cfg_o.negative_gravity, cfg_o.perturbation,
                          cfg_o.perturbation_lower_bound, cfg_o.penalize_factor, cfg_o.normalization_scale,
                          cfg_o.prior_trials_pool_pct, pool, batch, steps * batch)
-  bx, br = dev.eagle_run(cfg, _gp().Acquisition(1.8, True, radius), count=3, seed=7, prior=x)
+  bx, _, br = dev.eagle_run(cfg, _gp().Acquisition(1.8, True, radius), count=3, seed=7, prior=x)
   np.testing.assert_allclose(br, wr, atol=1e-9)
   np.testing.assert_allclose(bx, wx, atol=1e-9)
 
@@ -394,3 +394,52 @@ def test_error_behaviour(dev):
   idx, val = fresh.topk(torch.tensor([1.0, 2.0], dtype=torch.float64, device='cuda'), 4)  # count > M
   assert idx.tolist() == [1, 0, -1, -1]
   fresh.close()
+
+
+@pytest.mark.parametrize('n,d,sizes,pool,batch,steps', [(40, 3, (2, 4), 20, 5, 16), (70, 0, (3, 5, 2), 25, 25, 6), (90, 2, (7,), 50, 25, 9)])
+def test_eagle_mixed_features_matches_oracle(dev, n, d, sizes, pool, batch, steps):
+  """Continuous + categorical (and purely categorical) eagle trajectories against the oracle with the
+  shared Philox draws (laplace / gumbel-max categorical mutation, eagle_strategy.py:936-1011)."""
+  rng = np.random.default_rng(51)
+  sizes = np.asarray(sizes)
+  dk = sizes.shape[0]
+  x = rng.uniform(size=(n, d))
+  z = np.stack([rng.integers(0, s, size=n) for s in sizes], axis=1).astype(np.int32)
+  y = -np.sum((x - 0.3) ** 2, axis=1) - 0.3 * (z[:, 0] != 1) + 0.05 * rng.normal(size=n)
+  po, pg = _params(d, dk)
+  pred = go.precompute_predictive(po, x, y, z)
+  dev.fit(x, y, pg, z=z)
+  mask = np.ones(d, bool)
+  radius = go.trust_radius(n, d, dk)
+  score_fn = lambda xc, xz: go.score_with_aux(pred, xc, xz, tr_dim_mask=mask, categorical_dof=dk)[0]
+  cfg_o = eo.EagleConfig()
+  wc, wz, wr = eo.run_eagle_optimizer_mixed(score_fn, dim=d, sizes=sizes, pool_size=pool, batch_size=batch,
+                                            max_evaluations=steps * batch, count=3, seed=11, cfg=cfg_o, prior_c=x, prior_z=z)
+  from vizier_b200 import _lib
+  cfg = _lib.EagleConfig(cfg_o.visibility, cfg_o.gravity, cfg_o.negative_gravity, cfg_o.perturbation,
+                         cfg_o.perturbation_lower_bound, cfg_o.penalize_factor, cfg_o.normalization_scale,
+                         cfg_o.prior_trials_pool_pct, pool, batch, steps * batch)
+  bx, bz, br = dev.eagle_run(cfg, _gp().Acquisition(1.8, True, radius, mask), count=3, seed=11, prior=x, prior_z=z, cat_sizes=sizes)
+  np.testing.assert_array_equal(bz, wz)
+  np.testing.assert_allclose(br, wr, atol=1e-9)
+  np.testing.assert_allclose(bx, wc, atol=1e-9)
+
+
+def test_random_search_with_categoricals(dev):
+  rng = np.random.default_rng(52)
+  n, d, sizes, m = 80, 3, np.array([3, 6]), 4000
+  x = rng.uniform(size=(n, d)); z = np.stack([rng.integers(0, s, size=n) for s in sizes], axis=1).astype(np.int32)
+  y = rng.normal(size=n)
+  po, pg = _params(d, 2)
+  pred = go.precompute_predictive(po, x, y, z)
+  dev.fit(x, y, pg, z=z)
+  acq = _gp().Acquisition(1.8, True, go.trust_radius(n, d, 2))
+  bx, bz, bs, bi = dev.random_search(m, acq, 2, seed=5, cat_sizes=sizes)
+  xc = eo.philox_uniform(5, eo.STREAM_RANDOM_POOL, 0, m * d).reshape(m, d)
+  xz = eo.uniform_categories(eo.philox_uniform(5, eo.STREAM_RANDOM_POOL_CAT, 0, m * 2).reshape(m, 2), sizes)
+  want = go.score_with_aux(pred, xc, xz, categorical_dof=2)[0]
+  order = go.top_k(want, 2)
+  np.testing.assert_array_equal(bi, order)
+  np.testing.assert_array_equal(bz, xz[order])
+  np.testing.assert_array_equal(bx, xc[order])
+  np.testing.assert_allclose(bs, want[order], atol=TOL)

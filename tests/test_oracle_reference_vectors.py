@@ -150,3 +150,37 @@ def test_default_pool_size():
   assert eo.default_pool_size(20, 25, cfg) == 75     # D=20
   assert eo.default_pool_size(100, 5, eo.EagleConfig(max_pool_size=50)) == 50
   assert eo.default_pool_size(100, None, eo.EagleConfig(max_pool_size=10)) == 10
+
+
+def test_categorical_logits_match_reference_restatement():
+  """eagle_strategy_test.py:38-71 (`_create_logits_vector_simple`, one-hot matmul form) vs the
+  library form (`_create_logits_vector`, eagle_strategy.py:954-985) restated in the oracle."""
+  rng = np.random.default_rng(1)
+  cfg = eo.EagleConfig()
+  p, b = 9, 4
+  sizes = np.array([2, 3, 5])
+  pool_z = np.stack([rng.integers(0, s, size=p) for s in sizes], axis=1)
+  batch_z = pool_z[:b].copy()
+  scale = rng.normal(size=(b, p)) * 0.1
+  got = eo.categorical_logits(pool_z, batch_z, scale, sizes, cfg)
+  max_size = 5
+  for i, s in enumerate(sizes):
+    oh_f = np.zeros((p, s)); oh_f[np.arange(p), pool_z[:, i]] = 1
+    oh_b = np.zeros((b, s)); oh_b[np.arange(b), batch_z[:, i]] = 1
+    change = scale @ oh_f - oh_b * np.sum(scale, axis=-1, keepdims=True)
+    diff_logit = np.log((1.0 - cfg.prob_same_category_without_perturbation) / (s - 1))
+    want = np.zeros((b, max_size)) + diff_logit
+    want[:, s:] = -np.inf
+    want[np.arange(b), batch_z[:, i]] = np.log(cfg.prob_same_category_without_perturbation)
+    want[:, :s] = want[:, :s] + change
+    np.testing.assert_allclose(got[:, i, :], want, atol=1e-14)
+
+
+def test_noise_transforms():
+  u = eo.philox_uniform(3, eo.STREAM_CAT_LAPLACE, 0, 200000)
+  lap = eo.laplace_from_uniform(u)
+  assert abs(lap.mean()) < 2e-2 and abs(lap.var() - 2.0) < 5e-2      # Laplace(0,1): var 2
+  g = eo.gumbel_from_uniform(eo.philox_uniform(3, eo.STREAM_CAT_GUMBEL, 0, 200000))
+  assert abs(g.mean() - 0.5772156649) < 1e-2
+  z = eo.uniform_categories(u[:3000].reshape(1000, 3), np.array([2, 3, 7]))
+  assert z.min() == 0 and z[:, 0].max() == 1 and z[:, 2].max() == 6

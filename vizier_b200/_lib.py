@@ -59,7 +59,19 @@ class EagleConfig(C.Structure):
       ('pool_size', C.c_int),
       ('batch_size', C.c_int),
       ('max_evaluations', C.c_int),
+      ('categorical_perturbation_factor', C.c_double),
+      ('pure_categorical_perturbation_factor', C.c_double),
+      ('prob_same_category_without_perturbation', C.c_double),
   ]
+
+  def __init__(self, *args, **kwargs):
+    super().__init__(*args, **kwargs)
+    if len(args) < 12 and 'categorical_perturbation_factor' not in kwargs:
+      self.categorical_perturbation_factor = 1.0
+    if len(args) < 13 and 'pure_categorical_perturbation_factor' not in kwargs:
+      self.pure_categorical_perturbation_factor = 30.0
+    if len(args) < 14 and 'prob_same_category_without_perturbation' not in kwargs:
+      self.prob_same_category_without_perturbation = 0.98
 
 
 _vp = C.c_void_p
@@ -69,6 +81,7 @@ _u64 = C.c_uint64
 _d = C.c_double
 _pd = C.POINTER(C.c_double)
 _pi64 = C.POINTER(C.c_int64)
+_pi32 = C.POINTER(C.c_int32)
 _pP = C.POINTER(Params)
 _pA = C.POINTER(Acq)
 _pE = C.POINTER(EagleConfig)
@@ -97,9 +110,10 @@ SIGNATURES = {
     'vzgp_posterior': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i]),
     'vzgp_topk': (_i, [_vp, _vp, _i64, _i, _pi64, _pd]),
     'vzgp_score_topk': (_i, [_vp, _vp, _vp, _i, _pA, _i, _vp, _pd, _pd, _pi64]),
-    'vzgp_eagle_run': (_i, [_vp, _pE, _pA, _vp, _i, _i, _u64, _pd, _pd]),
-    'vzgp_random_search': (_i, [_vp, _i64, _i64, _pA, _i, _u64, _pd, _pd, _pi64]),
+    'vzgp_eagle_run': (_i, [_vp, _pE, _pA, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
+    'vzgp_random_search': (_i, [_vp, _i64, _i64, _pA, _pi32, _i, _u64, _pd, _pi32, _pd, _pi64]),
     'vzgp_random_pool': (_i, [_vp, _i64, _i, _i64, _u64, _vp]),
+    'vzgp_random_pool_cat': (_i, [_vp, _i64, _i, _pi32, _i64, _u64, _vp]),
 }
 
 _lock = threading.Lock()

@@ -48,8 +48,9 @@ class _CategoricalSpec:
 
   @property
   def size(self) -> int:
-    # bounds[1] of the reference's DISCRETE spec: number of categories + 1 out-of-vocabulary slot
-    return len(self.feasible_values) + 1
+    # bounds[1] of the reference's DISCRETE spec (core.py:183-191) = number of categories; the
+    # optimisers sample indices in [0, size) (eagle_strategy.py:209-211, :293-302)
+    return len(self.feasible_values)
 
 
 def _make_scaler(low: float, high: float, scale: Optional[str]):
@@ -155,10 +156,15 @@ class TrialToModelInputConverter:
 
   # -- arrays -> parameters ------------------------------------------------------
   def to_parameters(self, continuous: np.ndarray, categorical: Optional[np.ndarray] = None) -> List[Any]:
-    continuous = np.asarray(continuous, dtype=np.float64).reshape(-1, self.n_continuous)
-    n = continuous.shape[0]
+    if self.n_continuous:
+      continuous = np.asarray(continuous, dtype=np.float64).reshape(-1, self.n_continuous)
+      n = continuous.shape[0]
+    else:
+      n = 0 if categorical is None else np.asarray(categorical).reshape(-1, self.n_categorical).shape[0]
+      continuous = np.zeros((n, 0))
     if categorical is None:
       categorical = np.zeros((n, self.n_categorical), dtype=np.int32)
+    categorical = np.asarray(categorical).reshape(n, self.n_categorical)
     out = []
     for i in range(n):
       pd = vz.ParameterDict()

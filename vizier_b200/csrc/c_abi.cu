@@ -426,28 +426,64 @@ int vzgp_random_pool(vzgp_handle* h, int64_t M, int Dc, int64_t index_base, uint
   return launch_random_fill(h, X, M * Dc, index_base * Dc, seed, 3u, 0u);
 }
 
-int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp_acq* acq, int count,
-                       uint64_t seed, double* best_x, double* best_score, int64_t* best_index) {
-  VZ_ARG(h && acq && best_x && best_score, "handle / pointers");
-  if (!h->fitted) { set_error("vzgp_random_search before vzgp_fit"); return VZGP_ERR_STATE; }
-  VZ_ARG(h->dk == 0, "random search supports continuous features only");
-  VZ_ARG(M >= 1 && M <= INT_MAX, "1 <= M < 2^31 per call");
+static int check_cat_sizes(const vzgp_handle* h, const int32_t* cat_sizes, int* sizes, int* smax) {
+  *smax = 0;
+  for (int k = 0; k < kMaxDk; ++k) sizes[k] = 1;
+  if (h->dk == 0) return 0;
+  VZ_ARG(cat_sizes != nullptr, "cat_sizes is required when the model has categorical features");
+  for (int k = 0; k < h->dk; ++k) {
+    VZ_ARG(cat_sizes[k] >= 1 && cat_sizes[k] <= 64, "1 <= cat_sizes[k] <= 64");
+    sizes[k] = cat_sizes[k];
+    if (sizes[k] > *smax) *smax = sizes[k];
+  }
+  return 0;
+}
+
+int vzgp_random_pool_cat(vzgp_handle* h, int64_t M, int Dk, const int32_t* cat_sizes, int64_t index_base,
+                         uint64_t seed, int32_t* Z) {
+  VZ_ARG(h && Z && cat_sizes, "handle / Z / cat_sizes");
+  VZ_ARG(M >= 0 && Dk >= 1 && Dk <= kMaxDk, "M, Dk");
   Guard g(h->device);
-  const int dc = h->dc;
-  VZ_TRY(h->xs_dev.reserve(sizeof(double) * (size_t)M * dc));
-  VZ_TRY(h->out_dev.reserve(sizeof(double) * ((size_t)M + (size_t)kMaxTopk * dc)));
+  int sizes[kMaxDk];
+  for (int k = 0; k < Dk; ++k) {
+    VZ_ARG(cat_sizes[k] >= 1, "cat_sizes[k] >= 1");
+    sizes[k] = cat_sizes[k];
+  }
+  return launch_random_fill_cat(h, Z, M, Dk, sizes, index_base, seed, 8u);
+}
+
+int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp_acq* acq,
+                       const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
+                       double* best_score, int64_t* best_index) {
+  VZ_ARG(h && acq && best_score, "handle / pointers");
+  if (!h->fitted) { set_error("vzgp_random_search before vzgp_fit"); return VZGP_ERR_STATE; }
+  VZ_ARG(M >= 1 && M <= INT_MAX, "1 <= M < 2^31 per call");
+  VZ_ARG(best_x != nullptr || h->dc == 0, "best_x");
+  VZ_ARG(best_z != nullptr || h->dk == 0, "best_z");
+  Guard g(h->device);
+  const int dc = h->dc, dk = h->dk;
+  int sizes[kMaxDk], smax;
+  VZ_TRY(check_cat_sizes(h, cat_sizes, sizes, &smax));
+  const size_t xb = sizeof(double) * (size_t)M * (dc > 0 ? dc : 1);
+  VZ_TRY(h->xs_dev.reserve(xb + sizeof(int32_t) * (size_t)M * (dk > 0 ? dk : 1) + 64));
+  VZ_TRY(h->out_dev.reserve(sizeof(double) * ((size_t)M + (size_t)kMaxTopk * (dc + dk + 1))));
   double* dX = h->xs_dev.as<double>();
+  int32_t* dZ = reinterpret_cast<int32_t*>(h->xs_dev.as<char>() + ((xb + 15) / 16) * 16);
   double* dS = h->out_dev.as<double>();
   double* dBest = dS + M;
-  VZ_TRY(launch_random_fill(h, dX, M * dc, index_base * dc, seed, 3u, 0u));
-  VZ_TRY(launch_score(h, dX, nullptr, (int)M, acq, dS, nullptr, nullptr, nullptr));
+  int32_t* dBestZ = reinterpret_cast<int32_t*>(dBest + (size_t)kMaxTopk * (dc > 0 ? dc : 1));
+  if (dc > 0) VZ_TRY(launch_random_fill(h, dX, M * dc, index_base * dc, seed, 3u, 0u));
+  if (dk > 0) VZ_TRY(launch_random_fill_cat(h, dZ, M, dk, sizes, index_base, seed, 8u));
+  VZ_TRY(launch_score(h, dX, dk > 0 ? dZ : nullptr, (int)M, acq, dS, nullptr, nullptr, nullptr));
   long long* d_idx; double* d_val;
   VZ_TRY(topk_to_device(h, dS, M, count, &d_idx, &d_val));
-  VZ_TRY(launch_gather_rows(h, dX, dc, d_idx, count, M, dBest));
+  if (dc > 0) VZ_TRY(launch_gather_rows(h, dX, dc, d_idx, count, M, dBest));
+  if (dk > 0) VZ_TRY(launch_gather_rows_i32(h, dZ, dk, d_idx, count, M, dBestZ));
   long long hidx[kMaxTopk];
   VZ_CUDA(cudaMemcpyAsync(hidx, d_idx, sizeof(long long) * count, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaMemcpyAsync(best_score, d_val, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
-  VZ_CUDA(cudaMemcpyAsync(best_x, dBest, sizeof(double) * (size_t)count * dc, cudaMemcpyDeviceToHost, h->stream));
+  if (dc > 0) VZ_CUDA(cudaMemcpyAsync(best_x, dBest, sizeof(double) * (size_t)count * dc, cudaMemcpyDeviceToHost, h->stream));
+  if (dk > 0) VZ_CUDA(cudaMemcpyAsync(best_z, dBestZ, sizeof(int32_t) * (size_t)count * dk, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaStreamSynchronize(h->stream));
   if (best_index)
     for (int c = 0; c < count; ++c)
@@ -455,29 +491,33 @@ int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp
   return 0;
 }
 
-int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
-                   const double* prior, int n_prior, int count, uint64_t seed, double* best_x,
-                   double* best_score) {
-  VZ_ARG(h && cfg && acq && best_x && best_score, "handle / pointers");
+int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq, const double* prior,
+                   const int32_t* prior_z, int n_prior, const int32_t* cat_sizes, int count, uint64_t seed,
+                   double* best_x, int32_t* best_z, double* best_score) {
+  VZ_ARG(h && cfg && acq && best_score, "handle / pointers");
   if (!h->fitted) { set_error("vzgp_eagle_run before vzgp_fit"); return VZGP_ERR_STATE; }
-  VZ_ARG(h->dk == 0, "eagle supports continuous features only (categorical: next)");
+  VZ_ARG(best_x != nullptr || h->dc == 0, "best_x");
+  VZ_ARG(best_z != nullptr || h->dk == 0, "best_z");
   VZ_ARG(cfg->pool_size >= 1 && cfg->batch_size >= 1, "pool/batch size");
   VZ_ARG(cfg->pool_size % cfg->batch_size == 0, "pool_size must be a multiple of batch_size");
   VZ_ARG(cfg->pool_size <= 3000, "pool_size <= 3000");
   VZ_ARG(cfg->batch_size <= 8192, "batch_size <= 8192");
   VZ_ARG(count >= 1 && count <= kMaxTopk, "count");
   VZ_ARG(cfg->max_evaluations >= 1, "max_evaluations");
-  VZ_ARG(n_prior >= 0 && (n_prior == 0 || prior != nullptr), "prior");
+  VZ_ARG(n_prior >= 0, "n_prior");
+  VZ_ARG(n_prior == 0 || prior != nullptr || h->dc == 0, "prior");
+  VZ_ARG(n_prior == 0 || prior_z != nullptr || h->dk == 0, "prior_z");
   Guard g(h->device);
-  const int P = cfg->pool_size, B = cfg->batch_size, D = h->dc;
-  // carve the eagle buffer
-  size_t nd = (size_t)P * D + 2 * (size_t)P + 8 + (size_t)B * D + B + 2 * ((size_t)count * D + count) +
-              (size_t)(n_prior > 0 ? n_prior : 1) + (size_t)P;
-  size_t bytes = nd * sizeof(double) + 2 * (size_t)count * sizeof(long long) + 64 +
-                 (size_t)(n_prior > 0 ? n_prior : 1) * sizeof(int) + 64;
-  VZ_TRY(h->eagle.reserve(bytes));
-  double* p = h->eagle.as<double>();
+  const int P = cfg->pool_size, B = cfg->batch_size, D = h->dc, Dk = h->dk;
   EagleDev e;
+  VZ_TRY(check_cat_sizes(h, cat_sizes, e.sizes, &e.smax));
+  // carve the eagle buffer: doubles | long longs | ints
+  const size_t np1 = (size_t)(n_prior > 0 ? n_prior : 1);
+  const size_t nd = (size_t)P * D + 2 * (size_t)P + 8 + (size_t)B * D + B + 2 * ((size_t)count * D + count) + np1 + P;
+  const size_t nl = 2 * (size_t)count;
+  const size_t ni = 16 + np1 + (size_t)P * Dk + (size_t)B * Dk + 2 * (size_t)count * Dk;
+  VZ_TRY(h->eagle.reserve(nd * sizeof(double) + nl * sizeof(long long) + ni * sizeof(int32_t) + 64));
+  double* p = h->eagle.as<double>();
   e.pool = p; p += (size_t)P * D;
   e.rewards = p; p += P;
   e.pert = p; p += P;
@@ -488,25 +528,29 @@ int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq*
   e.best_r = p; p += count;
   e.tmp_x = p; p += (size_t)count * D;
   e.tmp_r = p; p += count;
-  double* prior_r = p; p += (n_prior > 0 ? n_prior : 1);
+  double* prior_r = p; p += np1;
   double* chosen_r = p; p += P;
   long long* lp = reinterpret_cast<long long*>(p);
   e.best_id = lp; lp += count;
   e.tmp_id = lp; lp += count;
-  int* ip = reinterpret_cast<int*>(lp);
+  int32_t* ip = reinterpret_cast<int32_t*>(lp);
   e.iter = ip; ip += 16;
-  int* ord = ip;
-  e.P = P; e.B = B; e.D = D; e.count = count; e.cfg = *cfg; e.seed = seed;
+  int* ord = ip; ip += np1;
+  e.pool_z = ip; ip += (size_t)P * Dk;
+  e.batch_z = ip; ip += (size_t)B * Dk;
+  e.best_z = ip; ip += (size_t)count * Dk;
+  e.tmp_z = ip; ip += (size_t)count * Dk;
+  e.P = P; e.B = B; e.D = D; e.Dk = Dk; e.count = count; e.cfg = *cfg; e.seed = seed;
   VZ_TRY(eagle_prepare(e));
   VZ_TRY(launch_eagle_init(h, e));
   if (n_prior > 0) {
-    VZ_TRY(launch_score(h, prior, nullptr, n_prior, acq, prior_r, nullptr, nullptr, nullptr));
-    VZ_TRY(launch_eagle_seed_priors(h, e, prior, prior_r, n_prior, ord, chosen_r));
+    VZ_TRY(launch_score(h, prior, Dk > 0 ? prior_z : nullptr, n_prior, acq, prior_r, nullptr, nullptr, nullptr));
+    VZ_TRY(launch_eagle_seed_priors(h, e, prior, prior_z, prior_r, n_prior, ord, chosen_r));
   }
   const int steps = (cfg->max_evaluations - 1) / B + 1;
   auto one_step = [&]() -> int {
     VZ_TRY(launch_eagle_suggest(h, e));
-    VZ_TRY(launch_score(h, e.batch, nullptr, B, acq, e.batch_r, nullptr, nullptr, nullptr));
+    VZ_TRY(launch_score(h, e.batch, Dk > 0 ? e.batch_z : nullptr, B, acq, e.batch_r, nullptr, nullptr, nullptr));
     VZ_TRY(launch_eagle_update(h, e));
     return 0;
   };
@@ -546,7 +590,8 @@ int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq*
       return VZGP_ERR_CUDA;
     }
   }
-  VZ_CUDA(cudaMemcpyAsync(best_x, e.best_x, sizeof(double) * (size_t)count * D, cudaMemcpyDeviceToHost, h->stream));
+  if (D > 0) VZ_CUDA(cudaMemcpyAsync(best_x, e.best_x, sizeof(double) * (size_t)count * D, cudaMemcpyDeviceToHost, h->stream));
+  if (Dk > 0) VZ_CUDA(cudaMemcpyAsync(best_z, e.best_z, sizeof(int32_t) * (size_t)count * Dk, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaMemcpyAsync(best_score, e.best_r, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaStreamSynchronize(h->stream));
   return 0;

@@ -1,13 +1,17 @@
 // Vectorised Eagle/Firefly acquisition optimiser: device-resident population state and the
-// suggest / update / trim / top-k steps (continuous features, n_parallel == 1).
+// suggest / update / trim / top-k steps (continuous + categorical features, n_parallel == 1).
 //
 // Replaces (reference): VectorizedEagleStrategy.init_state/_populate_pool_with_prior_trials
 // (vizier/_src/algorithms/optimizers/eagle_strategy.py:527-713), suggest/_create_features/
-// _create_random_perturbations (:720-952, :1013-1073), update/_update_pool_features_and_rewards/
-// _trim_pool (:1075-1247) and VectorizedOptimizer._update_best_results
+// _create_random_perturbations/_create_categorical_feature_logits (:720-1073),
+// update/_update_pool_features_and_rewards/_trim_pool (:1075-1247), DefaultRandomSampler
+// (:271-322) and VectorizedOptimizer._update_best_results
 // (vizier/_src/algorithms/optimizers/vectorized_base.py:544-587).
 // Randomness is Philox4x32-10 (see device.cuh); with n_parallel == 1 the reference's normalised
-// Laplace perturbation is exactly +-1 per coordinate (eagle_strategy.py:1033-1044).
+// Laplace perturbation of continuous features is exactly +-1 per coordinate
+// (eagle_strategy.py:1033-1044); categorical logits get real Laplace noise and are sampled by
+// Gumbel-max (= tfd.Categorical(logits).sample).  Element numbering of the draws is the contract
+// shared with oracle/eagle_oracle.py.
 #include <climits>
 
 #include "device.cuh"
@@ -15,16 +19,29 @@
 
 namespace vzgp {
 
+constexpr uint32_t kStreamInitCat = 4, kStreamCatLaplace = 5, kStreamCatGumbel = 6, kStreamTrimCat = 7;
+
+__device__ __forceinline__ double laplace_from_uniform(double u) {
+  const double v = u - 0.5;
+  const double l = -log(fmax(1.0 - 2.0 * fabs(v), 1.1102230246251565e-16));
+  return v > 0.0 ? l : (v < 0.0 ? -l : 0.0);
+}
+__device__ __forceinline__ double gumbel_from_uniform(double u) { return -log(-log(fmax(u, 1e-300))); }
+__device__ __forceinline__ int uniform_category(double u, int size) {
+  const int c = (int)(u * (double)size);
+  return c < size - 1 ? c : size - 1;
+}
 
 // ---------------------------------------------------------------------------
 // init: pool <- Philox uniforms; rewards=-inf; perturbations=cfg.perturbation; best=-inf.
 // ---------------------------------------------------------------------------
 __global__ void k_eagle_init(EagleDev e) {
   const int64_t total = (int64_t)e.P * e.D;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x)
-    e.pool[i] = philox_uniform(e.seed, kStreamInitPool, 0, (uint64_t)i);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.P; i += gridDim.x * blockDim.x) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < total; i += nth) e.pool[i] = philox_uniform(e.seed, kStreamInitPool, 0, (uint64_t)i);
+  for (int64_t i = tid; i < (int64_t)e.P * e.Dk; i += nth)
+    e.pool_z[i] = uniform_category(philox_uniform(e.seed, kStreamInitCat, 0, (uint64_t)i), e.sizes[i % e.Dk]);
+  for (int64_t i = tid; i < e.P; i += nth) {
     e.rewards[i] = -INFINITY;
     e.pert[i] = e.cfg.perturbation;
   }
@@ -34,22 +51,36 @@ __global__ void k_eagle_init(EagleDev e) {
       e.best_id[c] = LLONG_MAX;
     }
     for (int c = threadIdx.x; c < e.count * e.D; c += blockDim.x) e.best_x[c] = 0.0;
+    for (int c = threadIdx.x; c < e.count * e.Dk; c += blockDim.x) e.best_z[c] = 0;
     if (threadIdx.x == 0) { *e.best_reward = -INFINITY; *e.iter = 0; }
   }
 }
 
+// squared distance + Hamming distance (eagle_strategy.py:421-469)
+__device__ __forceinline__ double fly_distance(const double* a, const double* b, int D, const int32_t* za,
+                                               const int32_t* zb, int Dk) {
+  double s = 0.0;
+  for (int d = 0; d < D; ++d) {
+    const double df = a[d] - b[d];
+    s = fma(df, df, s);
+  }
+  for (int k = 0; k < Dk; ++k) s += (za[k] != zb[k]) ? 1.0 : 0.0;
+  return s;
+}
+
 // ---------------------------------------------------------------------------
 // Prior-trial seeding (single CTA; the reference loop is sequential too).
-// prior [n x D] in creation order, prior_r [n] their acquisition values.
+// prior [n x D] / prior_z [n x Dk] in creation order, prior_r [n] their acquisition values.
 // ord [n] int workspace, chosen_r [left] workspace.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_eagle_seed_priors(EagleDev e, const double* __restrict__ prior,
-                                                           const double* __restrict__ prior_r,
-                                                           int n, int* __restrict__ ord,
+                                                           const int32_t* __restrict__ prior_z,
+                                                           const double* __restrict__ prior_r, int n,
+                                                           int* __restrict__ ord,
                                                            double* __restrict__ chosen_r) {
   __shared__ double sv[256];
   __shared__ int si[256];
-  const int tid = threadIdx.x, D = e.D;
+  const int tid = threadIdx.x, D = e.D, Dk = e.Dk;
   const int n_random = (int)(e.P * (1.0 - e.cfg.prior_trials_pool_pct));
   const int left = e.P - n_random;
   // _mask_flip: valid entries newest first, then the -inf ones (eagle_strategy.py:472-496).
@@ -62,32 +93,28 @@ __global__ void __launch_bounds__(256) k_eagle_seed_priors(EagleDev e, const dou
   }
   __syncthreads();
   const int chosen = n < left ? n : left;
-  double* feat = e.pool + (size_t)n_random * D;  // chosen set lives directly in the pool
-  // Save the random rows that chosen entries may have to fall back to: they are simply the
-  // current pool contents, so only overwrite when the chosen reward is finite (done at the end).
-  // Work on a staging copy in tmp area = e.batch is too small in general, so keep chosen features
-  // in the pool and remember which stay random via chosen_r == -inf.
+  double* feat = e.pool + (size_t)n_random * D;      // the chosen set lives directly in the pool
+  int32_t* featz = e.pool_z + (size_t)n_random * Dk;
   for (int c = tid; c < chosen; c += 256) chosen_r[c] = prior_r[ord[c]];
   __syncthreads();
-  // Stage chosen features into the pool rows, but keep the original random rows for -inf ones.
+  // Entries whose reward is -inf (padded priors) keep the random row already in the pool
+  // (eagle_strategy.py:693-702).
   for (int idx = tid; idx < chosen * D; idx += 256) {
-    int c = idx / D, d = idx % D;
+    const int c = idx / D, d = idx % D;
     if (!(isinf(chosen_r[c]) && chosen_r[c] < 0)) feat[(size_t)c * D + d] = prior[(size_t)ord[c] * D + d];
+  }
+  for (int idx = tid; idx < chosen * Dk; idx += 256) {
+    const int c = idx / Dk, d = idx % Dk;
+    if (!(isinf(chosen_r[c]) && chosen_r[c] < 0)) featz[(size_t)c * Dk + d] = prior_z[(size_t)ord[c] * Dk + d];
   }
   __syncthreads();
   for (int i = left; i < n; ++i) {
     const double* x = prior + (size_t)ord[i] * D;
+    const int32_t* z = prior_z + (size_t)ord[i] * Dk;
     double bv = INFINITY;
     int bi = INT_MAX;
     for (int c = tid; c < left; c += 256) {
-      // distance to chosen member c; members with -inf reward hold random rows in the pool but
-      // the reference compares against the *prior* feature there; this only happens for padded
-      // priors, which sort last and never enter the chosen set before valid ones run out.
-      double s = 0.0;
-      for (int d = 0; d < D; ++d) {
-        double df = x[d] - feat[(size_t)c * D + d];
-        s = fma(df, df, s);
-      }
+      const double s = fly_distance(x, feat + (size_t)c * D, D, z, featz + (size_t)c * Dk, Dk);
       if (s < bv || (s == bv && c < bi)) { bv = s; bi = c; }
     }
     sv[tid] = bv; si[tid] = bi;
@@ -106,6 +133,7 @@ __global__ void __launch_bounds__(256) k_eagle_seed_priors(EagleDev e, const dou
     __syncthreads();
     if (repl) {
       for (int d = tid; d < D; d += 256) feat[(size_t)ind * D + d] = x[d];
+      for (int d = tid; d < Dk; d += 256) featz[(size_t)ind * Dk + d] = z[d];
       if (tid == 0) chosen_r[ind] = ri;
     }
     __syncthreads();
@@ -114,12 +142,12 @@ __global__ void __launch_bounds__(256) k_eagle_seed_priors(EagleDev e, const dou
 
 // ---------------------------------------------------------------------------
 // suggest: one warp per batch fly, 8 flies per CTA.  Dynamic smem: 8*P doubles (forces) +
-// 8*D doubles (the flies' own features).
+// 8*D doubles (the flies' own continuous features) + 8*Dk ints.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_eagle_suggest(EagleDev e) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int P = e.P, B = e.B, D = e.D;
+  const int P = e.P, B = e.B, D = e.D, Dk = e.Dk;
   const int t = *e.iter;
   const int nb = P / B;
   const int start = (t % nb) * B;
@@ -128,23 +156,22 @@ __global__ void __launch_bounds__(256) k_eagle_suggest(EagleDev e) {
   const int i = start + b;
   double* s_f = smem + (size_t)warp * P;
   double* s_x = smem + (size_t)8 * P + warp * D;
+  int32_t* s_z = reinterpret_cast<int32_t*>(smem + (size_t)8 * P + 8 * D) + warp * Dk;
   for (int d = lane; d < D; d += 32) s_x[d] = e.pool[(size_t)i * D + d];
+  for (int d = lane; d < Dk; d += 32) s_z[d] = e.pool_z[(size_t)i * Dk + d];
   __syncwarp();
   double* out = e.batch + (size_t)b * D;
+  int32_t* outz = e.batch_z + (size_t)b * Dk;
   if (t < nb) {  // still initialising: return the pool features (projected)
     for (int d = lane; d < D; d += 32) out[d] = fmin(fmax(s_x[d], 0.0), 1.0);
+    for (int d = lane; d < Dk; d += 32) outz[d] = s_z[d];
     return;
   }
   const double ri = e.rewards[i];
-  const double cexp = -e.cfg.visibility / (double)D * 10.0;
+  const double cexp = -e.cfg.visibility / (double)(D + Dk) * 10.0;
   int npull = 0, npush = 0;
   for (int j = lane; j < P; j += 32) {
-    const double* pj = e.pool + (size_t)j * D;
-    double d2 = 0.0;
-    for (int d = 0; d < D; ++d) {
-      double df = s_x[d] - pj[d];
-      d2 = fma(df, df, d2);
-    }
+    const double d2 = fly_distance(s_x, e.pool + (size_t)j * D, D, s_z, e.pool_z + (size_t)j * Dk, Dk);
     const double rj = e.rewards[j];
     const double dir = rj - ri;
     const double sd = (dir >= 0.0) ? e.cfg.gravity : -e.cfg.negative_gravity;
@@ -161,12 +188,17 @@ __global__ void __launch_bounds__(256) k_eagle_suggest(EagleDev e) {
   __syncwarp();
   const double wpull = npull > 0 ? e.cfg.normalization_scale / (double)npull : 0.0;
   const double wpush = npush > 0 ? e.cfg.normalization_scale / (double)npush : 0.0;
-  // lane handles dims lane and lane+32
+  // convert the forces to the normalised scale in place
+  for (int j = lane; j < P; j += 32) {
+    const double f = s_f[j];
+    s_f[j] = f > 0.0 ? f * wpull : (f < 0.0 ? f * wpush : 0.0);
+  }
+  __syncwarp();
+  // ---- continuous features: lane handles dims lane and lane+32 ----
   double acc0 = 0.0, acc1 = 0.0, ssum = 0.0;
   const int d0 = lane, d1 = lane + 32;
   for (int j = 0; j < P; ++j) {
-    const double f = s_f[j];
-    const double sc = f > 0.0 ? f * wpull : (f < 0.0 ? f * wpush : 0.0);
+    const double sc = s_f[j];
     ssum += sc;
     const double* pj = e.pool + (size_t)j * D;
     if (d0 < D) acc0 = fma(sc, pj[d0], acc0);
@@ -174,19 +206,53 @@ __global__ void __launch_bounds__(256) k_eagle_suggest(EagleDev e) {
   }
   const double pert = e.pert[i];
   if (d0 < D) {
-    double u = philox_uniform(e.seed, kStreamPerturbSign, (uint32_t)t, (uint64_t)b * D + d0);
-    double v = s_x[d0] + (acc0 - s_x[d0] * ssum) + (u >= 0.5 ? pert : -pert);
+    const double u = philox_uniform(e.seed, kStreamPerturbSign, (uint32_t)t, (uint64_t)b * D + d0);
+    const double v = s_x[d0] + (acc0 - s_x[d0] * ssum) + (u >= 0.5 ? pert : -pert);
     out[d0] = fmin(fmax(v, 0.0), 1.0);
   }
   if (d1 < D) {
-    double u = philox_uniform(e.seed, kStreamPerturbSign, (uint32_t)t, (uint64_t)b * D + d1);
-    double v = s_x[d1] + (acc1 - s_x[d1] * ssum) + (u >= 0.5 ? pert : -pert);
+    const double u = philox_uniform(e.seed, kStreamPerturbSign, (uint32_t)t, (uint64_t)b * D + d1);
+    const double v = s_x[d1] + (acc1 - s_x[d1] * ssum) + (u >= 0.5 ? pert : -pert);
     out[d1] = fmin(fmax(v, 0.0), 1.0);
+  }
+  // ---- categorical features (eagle_strategy.py:936-1011): lane = category (and lane+32) ----
+  const double factor = D > 0 ? e.cfg.categorical_perturbation_factor : e.cfg.pure_categorical_perturbation_factor;
+  const double log_same = log(e.cfg.prob_same_category_without_perturbation);
+  for (int k = 0; k < Dk; ++k) {
+    const int size = e.sizes[k];
+    if (size <= 1) {
+      if (lane == 0) outz[k] = 0;
+      continue;
+    }
+    const double log_diff = log((1.0 - e.cfg.prob_same_category_without_perturbation) / ((double)size - 1.0));
+    double best_v = -INFINITY;
+    int best_c = INT_MAX;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int c = lane + 32 * half;
+      if (c < size) {
+        double lg = 0.0;
+        for (int j = 0; j < P; ++j) lg += (e.pool_z[(size_t)j * Dk + k] == c) ? s_f[j] : 0.0;
+        lg += log_diff;
+        if (c == s_z[k]) lg += -ssum + log_same - log_diff;
+        const uint64_t el = ((uint64_t)b * Dk + k) * e.smax + c;
+        lg += laplace_from_uniform(philox_uniform(e.seed, kStreamCatLaplace, (uint32_t)t, el)) * factor * pert;
+        lg += gumbel_from_uniform(philox_uniform(e.seed, kStreamCatGumbel, (uint32_t)t, el));
+        if (lg > best_v || (lg == best_v && c < best_c)) { best_v = lg; best_c = c; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+      if (ov > best_v || (ov == best_v && oc < best_c)) { best_v = ov; best_c = oc; }
+    }
+    if (lane == 0) outz[k] = best_c;
   }
 }
 
 // ---------------------------------------------------------------------------
-// update + trim + top-count bookkeeping: single CTA.  Dynamic smem: (B+count) doubles + ints.
+// update + trim + top-count bookkeeping: single CTA.  Dynamic smem: (B+count) doubles + flags.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ bool rank_better(double v, long long id, double bv, long long bid) {
   return (v > bv) || (v == bv && id < bid);
@@ -198,7 +264,7 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
   __shared__ long long si[256];
   __shared__ int sp[256];
   const int tid = threadIdx.x;
-  const int P = e.P, B = e.B, D = e.D, count = e.count;
+  const int P = e.P, B = e.B, D = e.D, Dk = e.Dk, count = e.count;
   const int t = *e.iter;
   const int nb = P / B;
   const int start = (t % nb) * B;
@@ -246,7 +312,9 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
     __syncthreads();
     if (q >= 0) {
       const double* src = q < B ? e.batch + (size_t)q * D : e.best_x + (size_t)(q - B) * D;
+      const int32_t* srcz = q < B ? e.batch_z + (size_t)q * Dk : e.best_z + (size_t)(q - B) * Dk;
       for (int d = tid; d < D; d += 256) e.tmp_x[(size_t)c * D + d] = src[d];
+      for (int d = tid; d < Dk; d += 256) e.tmp_z[(size_t)c * Dk + d] = srcz[d];
       if (tid == 0) {
         e.tmp_r[c] = q < B ? e.batch_r[q] : e.best_r[q - B];
         e.tmp_id[c] = qid;
@@ -256,6 +324,7 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
     __syncthreads();
   }
   for (int q = tid; q < count * D; q += 256) e.best_x[q] = e.tmp_x[q];
+  for (int q = tid; q < count * Dk; q += 256) e.best_z[q] = e.tmp_z[q];
   for (int c = tid; c < count; c += 256) { e.best_r[c] = e.tmp_r[c]; e.best_id[c] = e.tmp_id[c]; }
 
   // ---- pool update ----
@@ -265,6 +334,7 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
     double pert = e.pert[i];
     if (t < nb) {
       for (int d = 0; d < D; ++d) e.pool[(size_t)i * D + d] = e.batch[(size_t)b * D + d];
+      for (int d = 0; d < Dk; ++d) e.pool_z[(size_t)i * Dk + d] = e.batch_z[(size_t)b * Dk + d];
       e.rewards[i] = rb;
     } else {
       const double prev = e.rewards[i];
@@ -274,12 +344,15 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
       const bool trim = (pert < e.cfg.perturbation_lower_bound) && (nr != new_best);
       if (trim) {
         for (int d = 0; d < D; ++d)
-          e.pool[(size_t)i * D + d] =
-              philox_uniform(e.seed, kStreamTrim, (uint32_t)t, (uint64_t)b * D + d);
+          e.pool[(size_t)i * D + d] = philox_uniform(e.seed, kStreamTrim, (uint32_t)t, (uint64_t)b * D + d);
+        for (int d = 0; d < Dk; ++d)
+          e.pool_z[(size_t)i * Dk + d] = uniform_category(
+              philox_uniform(e.seed, kStreamTrimCat, (uint32_t)t, (uint64_t)b * Dk + d), e.sizes[d]);
         pert = e.cfg.perturbation;
         nr = -INFINITY;
       } else if (improve) {
         for (int d = 0; d < D; ++d) e.pool[(size_t)i * D + d] = e.batch[(size_t)b * D + d];
+        for (int d = 0; d < Dk; ++d) e.pool_z[(size_t)i * Dk + d] = e.batch_z[(size_t)b * Dk + d];
       }
       e.rewards[i] = nr;
       e.pert[i] = pert;
@@ -289,6 +362,25 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
   if (tid == 0) { *e.best_reward = new_best; *e.iter = t + 1; }
 }
 
+// Z[m, k] = uniform category of feature k for candidate index_base+m (RandomVectorizedStrategy).
+struct CatSizes { int v[kMaxDk]; };
+__global__ void k_random_pool_cat(int32_t* __restrict__ Z, int64_t total, int dk, CatSizes sizes,
+                                  int64_t elem_base, uint64_t seed, uint32_t stream) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < total; e += stride)
+    Z[e] = uniform_category(philox_uniform(seed, stream, 0, (uint64_t)(elem_base + e)), sizes.v[(elem_base + e) % dk]);
+}
+
+__global__ void k_gather_rows_i32(const int32_t* __restrict__ Z, int dk, const long long* __restrict__ idx,
+                                  int count, int64_t M, int32_t* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count * dk) return;
+  int c = e / dk, d = e % dk;
+  long long i = idx[c];
+  out[e] = (i >= 0 && i < M) ? Z[(size_t)i * dk + d] : 0;
+}
+
 // ---------------------------------------------------------------------------
 int launch_eagle_init(vzgp_handle* h, const EagleDev& e) {
   k_eagle_init<<<64, 256, 0, h->stream>>>(e);
@@ -296,14 +388,16 @@ int launch_eagle_init(vzgp_handle* h, const EagleDev& e) {
   h->launches++;
   return 0;
 }
-int launch_eagle_seed_priors(vzgp_handle* h, const EagleDev& e, const double* prior,
+int launch_eagle_seed_priors(vzgp_handle* h, const EagleDev& e, const double* prior, const int32_t* prior_z,
                              const double* prior_r, int n, int* ord, double* chosen_r) {
-  k_eagle_seed_priors<<<1, 256, 0, h->stream>>>(e, prior, prior_r, n, ord, chosen_r);
+  k_eagle_seed_priors<<<1, 256, 0, h->stream>>>(e, prior, prior_z, prior_r, n, ord, chosen_r);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;
 }
-size_t eagle_suggest_smem(const EagleDev& e) { return sizeof(double) * (size_t)8 * (e.P + e.D); }
+size_t eagle_suggest_smem(const EagleDev& e) {
+  return sizeof(double) * (size_t)8 * (e.P + e.D) + sizeof(int32_t) * 8 * (size_t)(e.Dk + 2);
+}
 size_t eagle_update_smem(const EagleDev& e) {
   return sizeof(double) * (size_t)(e.B + e.count) + (size_t)(e.B + e.count) + 16;
 }
@@ -322,6 +416,27 @@ int launch_eagle_suggest(vzgp_handle* h, const EagleDev& e) {
 }
 int launch_eagle_update(vzgp_handle* h, const EagleDev& e) {
   k_eagle_update<<<1, 256, eagle_update_smem(e), h->stream>>>(e);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+int launch_random_fill_cat(vzgp_handle* h, int32_t* Z, int64_t M, int dk, const int* sizes, int64_t index_base,
+                           uint64_t seed, uint32_t stream) {
+  const int64_t total = M * dk;
+  if (total <= 0) return 0;
+  CatSizes cs;
+  for (int k = 0; k < kMaxDk; ++k) cs.v[k] = k < dk ? sizes[k] : 1;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
+  k_random_pool_cat<<<(unsigned)blocks, 256, 0, h->stream>>>(Z, total, dk, cs, index_base * dk, seed, stream);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+int launch_gather_rows_i32(vzgp_handle* h, const int32_t* Z, int dk, const long long* idx, int count, int64_t M,
+                           int32_t* out) {
+  if (count * dk == 0) return 0;
+  k_gather_rows_i32<<<(count * dk + 255) / 256, 256, 0, h->stream>>>(Z, dk, idx, count, M, out);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;

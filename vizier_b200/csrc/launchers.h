@@ -66,13 +66,23 @@ struct EagleDev {
   double* tmp_x;
   double* tmp_r;
   long long* tmp_id;
-  int P, B, D, count;
+  // categorical features (Dk may be 0)
+  int32_t* pool_z;   // [P x Dk]
+  int32_t* batch_z;  // [B x Dk]
+  int32_t* best_z;   // [count x Dk]
+  int32_t* tmp_z;    // [count x Dk]
+  int P, B, D, Dk, smax, count;
+  int sizes[kMaxDk];
   vzgp_eagle_config cfg;
   uint64_t seed;
 };
 int launch_eagle_init(vzgp_handle* h, const EagleDev& e);
-int launch_eagle_seed_priors(vzgp_handle* h, const EagleDev& e, const double* prior,
+int launch_eagle_seed_priors(vzgp_handle* h, const EagleDev& e, const double* prior, const int32_t* prior_z,
                              const double* prior_r, int n, int* ord, double* chosen_r);
+int launch_random_fill_cat(vzgp_handle* h, int32_t* Z, int64_t M, int dk, const int* sizes, int64_t index_base,
+                           uint64_t seed, uint32_t stream);
+int launch_gather_rows_i32(vzgp_handle* h, const int32_t* Z, int dk, const long long* idx, int count, int64_t M,
+                           int32_t* out);
 int eagle_prepare(const EagleDev& e);
 int launch_eagle_suggest(vzgp_handle* h, const EagleDev& e);
 int launch_eagle_update(vzgp_handle* h, const EagleDev& e);

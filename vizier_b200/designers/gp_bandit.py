@@ -12,7 +12,7 @@ same metadata keys, same errors for unsupported search spaces.  What runs where:
 
 Not implemented (the reference supports them; SURVEY 8f "next"): multi-metric scalarised UCB,
 `ensemble_size > 1`, `linear_coef`, transfer-learning priors (`set_priors`), parallel (q-)
-acquisitions, feature padding schedules.  Each raises NotImplementedError / ValueError instead of
+acquisitions, feature padding schedules.  Categorical parameters ARE supported end to end.  Each raises NotImplementedError / ValueError instead of
 silently doing something else.
 """
 
@@ -149,7 +149,7 @@ class VizierGPBandit:
         self._halton_count += 1
         idx = self._halton_offset + self._halton_count
         cont = np.array([[_halton(idx, _PRIMES[j % len(_PRIMES)]) for j in range(dc)]])
-        cat = np.array([[int(_halton(idx, _PRIMES[(dc + j) % len(_PRIMES)]) * (s - 1)) for j, s in enumerate(self._converter.categorical_sizes)]], np.int32).reshape(1, dk)
+        cat = np.array([[min(int(_halton(idx, _PRIMES[(dc + j) % len(_PRIMES)]) * s), s - 1) for j, s in enumerate(self._converter.categorical_sizes)]], np.int32).reshape(1, dk)
         out.append(vz.TrialSuggestion(self._converter.to_parameters(cont, cat)[0]))
     return out
 
@@ -187,11 +187,13 @@ class VizierGPBandit:
     """gp_bandit.py:482-521 + vectorized_base.best_candidates_to_trials (:591-651)."""
     prior = converters.trials_to_sorted_features(self._trials, self._converter)
     seed = int(self._rng.integers(2**62))
-    res = self._acquisition_optimizer(dev, acq, count=count, prior_features=None if prior is None else prior[0], seed=seed)
+    res = self._acquisition_optimizer(dev, acq, count=count, prior_features=None if prior is None else prior[0],
+                                      prior_categorical=None if prior is None else prior[1], seed=seed)
     trials = []
     order = np.argsort(-res.rewards, kind='stable')
     for ind in order:
-      params = self._converter.to_parameters(res.features[ind:ind + 1])[0]
+      params = self._converter.to_parameters(
+          res.features[ind:ind + 1], None if res.categorical is None else res.categorical[ind:ind + 1])[0]
       trial = vz.Trial(parameters=params)
       md = trial.metadata.ns('devinfo')
       aux = {k: float(v[ind]) for k, v in res.aux.items()}

@@ -334,25 +334,45 @@ class DeviceGP:
     self.synchronize()
     return out
 
-  def random_search(self, m: int, acq: Acquisition, count: int, seed: int, index_base: int = 0):
+  def random_pool_cat(self, m: int, cat_sizes, seed: int, index_base: int = 0) -> torch.Tensor:
+    sizes = np.ascontiguousarray(np.asarray(cat_sizes, np.int32))
+    out = torch.empty((m, sizes.shape[0]), dtype=torch.int32, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_random_pool_cat', self._lib.vzgp_random_pool_cat(
+        self._h, m, sizes.shape[0], sizes.ctypes.data_as(C.POINTER(C.c_int32)), index_base, seed, _ptr(out)))
+    self.synchronize()
+    return out
+
+  def random_search(self, m: int, acq: Acquisition, count: int, seed: int, index_base: int = 0, cat_sizes=None):
+    """Returns (best_x [count,Dc], best_z [count,Dk], best_score [count], best_index [count])."""
     a, keep = acq._c()
     bx = np.zeros((count, self.dc), np.float64)
+    bz = np.zeros((count, self.dk), np.int32)
     bs = np.zeros(count, np.float64)
     bi = np.zeros(count, np.int64)
+    sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
     _lib.check('vzgp_random_search', self._lib.vzgp_random_search(
-        self._h, m, index_base, C.byref(a), count, seed, bx.ctypes.data_as(C.POINTER(C.c_double)),
+        self._h, m, index_base, C.byref(a), sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes.size else None,
+        count, seed, bx.ctypes.data_as(C.POINTER(C.c_double)), bz.ctypes.data_as(C.POINTER(C.c_int32)),
         bs.ctypes.data_as(C.POINTER(C.c_double)), bi.ctypes.data_as(C.POINTER(C.c_int64))))
     del keep
-    return bx, bs, bi
+    return bx, bz, bs, bi
 
   def eagle_run(self, cfg: '_lib.EagleConfig', acq: Acquisition, count: int, seed: int,
-                prior: Optional[Sequence] = None):
+                prior: Optional[Sequence] = None, prior_z: Optional[Sequence] = None, cat_sizes=None):
+    """Returns (best_x [count,Dc], best_z [count,Dk], best_score [count])."""
     a, keep = acq._c()
-    pt = self._dev(prior, torch.float64) if prior is not None and len(prior) > 0 else None
+    n_prior = 0 if prior is None else len(prior)
+    pt = self._dev(prior, torch.float64) if n_prior > 0 and self.dc > 0 else None
+    pz = self._dev(prior_z, torch.int32) if n_prior > 0 and self.dk > 0 else None
     bx = np.zeros((count, self.dc), np.float64)
+    bz = np.zeros((count, self.dk), np.int32)
     bs = np.zeros(count, np.float64)
+    sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
     _lib.check('vzgp_eagle_run', self._lib.vzgp_eagle_run(
-        self._h, C.byref(cfg), C.byref(a), _ptr(pt), 0 if pt is None else pt.shape[0], count, seed,
-        bx.ctypes.data_as(C.POINTER(C.c_double)), bs.ctypes.data_as(C.POINTER(C.c_double))))
+        self._h, C.byref(cfg), C.byref(a), _ptr(pt), _ptr(pz), n_prior,
+        sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes.size else None, count, seed,
+        bx.ctypes.data_as(C.POINTER(C.c_double)), bz.ctypes.data_as(C.POINTER(C.c_int32)),
+        bs.ctypes.data_as(C.POINTER(C.c_double))))
     del keep
-    return bx, bs
+    return bx, bz, bs

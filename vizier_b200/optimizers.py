@@ -70,6 +70,7 @@ class VectorizedStrategyResults:
   features: np.ndarray             # [count, Dc]
   rewards: np.ndarray              # [count]
   aux: Dict[str, np.ndarray] = dataclasses.field(default_factory=dict)
+  categorical: Optional[np.ndarray] = None   # [count, Dk] int32
 
 
 @dataclasses.dataclass
@@ -79,26 +80,29 @@ class VectorizedOptimizer:
   n_categorical: int
   suggestion_batch_size: int = 25
   max_evaluations: int = 75_000
+  categorical_sizes: tuple = ()
 
   def __call__(self, dev: gp.DeviceGP, acq: gp.Acquisition, *, count: int = 1,
-               prior_features: Optional[np.ndarray] = None, seed: int = 0) -> VectorizedStrategyResults:
-    if self.n_categorical:
-      raise NotImplementedError('categorical features in the device optimisers are not implemented yet')
+               prior_features: Optional[np.ndarray] = None, prior_categorical: Optional[np.ndarray] = None,
+               seed: int = 0) -> VectorizedStrategyResults:
+    sizes = list(self.categorical_sizes)
     if isinstance(self.strategy_factory, _RandomStrategyFactory):
       # one uniform batch per step; the device scores all max_evaluations candidates in one pass
       n = (self.max_evaluations - 1) // self.suggestion_batch_size + 1
       m = n * self.suggestion_batch_size
-      bx, bs, _ = dev.random_search(m, acq, count, seed)
+      bx, bz, bs, _ = dev.random_search(m, acq, count, seed, cat_sizes=sizes)
     else:
       f = self.strategy_factory
       pool = f.pool_size(self.n_continuous + self.n_categorical, self.suggestion_batch_size)
       c = f.eagle_config
       cfg = _lib.EagleConfig(c.visibility, c.gravity, c.negative_gravity, c.perturbation,
                              c.perturbation_lower_bound, c.penalize_factor, c.normalization_scale,
-                             c.prior_trials_pool_pct, pool, self.suggestion_batch_size, self.max_evaluations)
-      bx, bs = dev.eagle_run(cfg, acq, count, seed, prior=prior_features)
+                             c.prior_trials_pool_pct, pool, self.suggestion_batch_size, self.max_evaluations,
+                             c.categorical_perturbation_factor, c.pure_categorical_perturbation_factor,
+                             c.prob_same_category_without_perturbation)
+      bx, bz, bs = dev.eagle_run(cfg, acq, count, seed, prior=prior_features, prior_z=prior_categorical, cat_sizes=sizes)
     # score_with_aux on the winners (vectorized_base.py:504-526)
-    out = dev.score(bx, acq, with_aux=True)
+    out = dev.score(bx, acq, zs=bz if self.n_categorical else None, with_aux=True)
     dev.synchronize()
     aux = {
         'mean': out['mean'].cpu().numpy(), 'stddev': out['stddev'].cpu().numpy(),
@@ -108,7 +112,7 @@ class VectorizedOptimizer:
     aux['raw_acquisition'] = aux['mean'] + acq.ucb_coefficient * aux['stddev']
     if not acq.use_trust_region:
       aux = {}
-    return VectorizedStrategyResults(bx, bs, aux)
+    return VectorizedStrategyResults(bx, bs, aux, categorical=bz)
 
 
 @dataclasses.dataclass
@@ -120,4 +124,4 @@ class VectorizedOptimizerFactory:
 
   def __call__(self, converter) -> VectorizedOptimizer:
     return VectorizedOptimizer(self.strategy_factory, converter.n_continuous, converter.n_categorical,
-                               self.suggestion_batch_size, self.max_evaluations)
+                               self.suggestion_batch_size, self.max_evaluations, tuple(converter.categorical_sizes))
