@@ -443,3 +443,27 @@ def test_random_search_with_categoricals(dev):
   np.testing.assert_array_equal(bz, xz[order])
   np.testing.assert_array_equal(bx, xc[order])
   np.testing.assert_allclose(bs, want[order], atol=TOL)
+
+
+@pytest.mark.parametrize('m', [1, 5000, 60_000])
+def test_score_host_matches_device_path(dev, m):
+  """The HOST-buffer entry point (chunked H2D pipelined against scoring) returns exactly what the
+  device-buffer entry point returns."""
+  n, d = 200, 8
+  x, y, _ = _problem(n, d, 61)
+  po, pg = _params(d)
+  dev.fit(x, y, pg)
+  acq = _gp().Acquisition(1.8, True, go.trust_radius(n, d, 0))
+  xs = np.random.default_rng(62).uniform(size=(m, d))
+  out = dev.score(xs, acq, with_aux=True)
+  dev.synchronize()
+  score = np.empty(m); mean = np.empty(m); sd = np.empty(m); linf = np.empty(m)
+  dev.score_host(xs, acq, score_out=score, mean_out=mean, stddev_out=sd, linf_out=linf)
+  np.testing.assert_allclose(score, out['score'].cpu().numpy(), atol=1e-12, rtol=0)
+  np.testing.assert_allclose(mean, out['mean'].cpu().numpy(), atol=1e-12, rtol=0)
+  np.testing.assert_allclose(sd, out['stddev'].cpu().numpy(), atol=1e-12, rtol=0)
+  np.testing.assert_array_equal(linf, out['linf_distance'].cpu().numpy())
+  pinned = torch.from_numpy(xs).pin_memory(); s2 = torch.empty(m, dtype=torch.float64).pin_memory()
+  dev.score_host(pinned, acq, score_out=s2)
+  want, _ = go.score_with_aux(go.precompute_predictive(po, x, y), xs[:256])
+  np.testing.assert_allclose(s2.numpy()[:256], want, atol=TOL, rtol=0)

@@ -183,6 +183,10 @@ int vzgp_destroy(vzgp_handle* h) {
                     &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->copy_stream) {
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(h->copy_ev[i]);
+    cudaStreamDestroy(h->copy_stream);
+  }
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -378,11 +382,38 @@ int vzgp_score_host(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
   VZ_TRY(h->out_dev.reserve(sizeof(double) * (size_t)M * 4));
   double* dX = h->xs_dev.as<double>();
   int32_t* dZ = reinterpret_cast<int32_t*>(h->xs_dev.as<char>() + ((xb + 15) / 16) * 16);
-  if (h->dc > 0) VZ_CUDA(cudaMemcpyAsync(dX, Xs, xb, cudaMemcpyHostToDevice, h->stream));
-  if (h->dk > 0) VZ_CUDA(cudaMemcpyAsync(dZ, Zs, zb, cudaMemcpyHostToDevice, h->stream));
   double* o = h->out_dev.as<double>();
-  VZ_TRY(launch_score(h, dX, h->dk > 0 ? dZ : nullptr, M, acq, o, mu ? o + M : nullptr,
-                      sigma ? o + 2 * (size_t)M : nullptr, linf ? o + 3 * (size_t)M : nullptr));
+  // The host->device copy is pipelined against the scoring: candidates go over in up to three
+  // chunks sized in whole waves of 64-row tiles (1 wave, 3 waves, rest) on a copy stream, and the
+  // score launch of chunk c only waits for the event of chunk c.
+  if (!h->copy_stream) {
+    VZ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) VZ_CUDA(cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
+  }
+  const int wave = h->sm_count * 64;
+  int bounds[4] = {0, 0, 0, 0};
+  int nchunk = 0;
+  {
+    int pos = 0;
+    const int plan[2] = {wave, 3 * wave};
+    for (int i = 0; i < 2 && M - pos > 2 * plan[i]; ++i) { pos += plan[i]; bounds[++nchunk] = pos; }
+    bounds[++nchunk] = M;
+  }
+  VZ_CUDA(cudaEventRecord(h->copy_ev[3], h->stream));          // previous users of the staging buffers
+  VZ_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[3], 0));
+  for (int c = 0; c < nchunk; ++c) {
+    const size_t lo = bounds[c], n = bounds[c + 1] - bounds[c];
+    if (h->dc > 0) VZ_CUDA(cudaMemcpyAsync(dX + lo * h->dc, Xs + lo * h->dc, sizeof(double) * n * h->dc, cudaMemcpyHostToDevice, h->copy_stream));
+    if (h->dk > 0) VZ_CUDA(cudaMemcpyAsync(dZ + lo * h->dk, Zs + lo * h->dk, sizeof(int32_t) * n * h->dk, cudaMemcpyHostToDevice, h->copy_stream));
+    VZ_CUDA(cudaEventRecord(h->copy_ev[c], h->copy_stream));
+  }
+  for (int c = 0; c < nchunk; ++c) {
+    const size_t lo = bounds[c];
+    const int n = bounds[c + 1] - bounds[c];
+    VZ_CUDA(cudaStreamWaitEvent(h->stream, h->copy_ev[c], 0));
+    VZ_TRY(launch_score(h, dX + lo * h->dc, h->dk > 0 ? dZ + lo * h->dk : nullptr, n, acq, o + lo, mu ? o + M + lo : nullptr,
+                        sigma ? o + 2 * (size_t)M + lo : nullptr, linf ? o + 3 * (size_t)M + lo : nullptr));
+  }
   const size_t ob = sizeof(double) * (size_t)M;
   VZ_CUDA(cudaMemcpyAsync(score, o, ob, cudaMemcpyDeviceToHost, h->stream));
   if (mu) VZ_CUDA(cudaMemcpyAsync(mu, o + M, ob, cudaMemcpyDeviceToHost, h->stream));

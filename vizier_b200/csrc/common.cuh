@@ -128,4 +128,6 @@ struct vzgp_handle {
   vzgp::DevBuf eagle;   // eagle state
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  cudaStream_t copy_stream = nullptr;   // H2D staging of vzgp_score_host, overlapped with scoring
+  cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
