@@ -467,3 +467,29 @@ def test_score_host_matches_device_path(dev, m):
   dev.score_host(pinned, acq, score_out=s2)
   want, _ = go.score_with_aux(go.precompute_predictive(po, x, y), xs[:256])
   np.testing.assert_allclose(s2.numpy()[:256], want, atol=TOL, rtol=0)
+
+
+def test_nll_grad_d50_multiblock(dev):
+  """C4-like shape (D=50, several 64-blocks) against the oracle, plus a directional finite
+  difference at the full C4 size (N=2000) using the device loss only."""
+  n, d = 600, 50
+  rng = np.random.default_rng(71)
+  x = rng.uniform(size=(n, d)); y = rng.normal(size=n)
+  ls2 = np.exp(rng.uniform(np.log(0.3), np.log(5.0), size=d))
+  po = go.GPParams(0.9, ls2, 3e-2); pg = _gp().GPHyperParams(0.9, ls2, 3e-2)
+  want_l, want_g = go.loss_and_grad(po.to_vector(), x, y)
+  xt = torch.from_numpy(x).cuda(); yt = torch.from_numpy(y).cuda()
+  loss, grad, _ = dev.loss_and_grad(xt, yt, pg)
+  assert abs(loss - want_l) < 1e-8 * abs(want_l)
+  np.testing.assert_allclose(grad, want_g, atol=1e-7 * np.max(np.abs(want_g)), rtol=0)
+  n = 2000
+  x = rng.uniform(size=(n, d)); y = rng.normal(size=n)
+  xt = torch.from_numpy(x).cuda(); yt = torch.from_numpy(y).cuda()
+  theta = pg.to_vector()
+  l0, g0, _ = dev.loss_and_grad(xt, yt, pg)
+  direction = rng.normal(size=theta.shape) * theta
+  h = 1e-6
+  lp, _, _ = dev.loss_and_grad(xt, yt, _gp().GPHyperParams.from_vector(theta + h * direction, d, 0))
+  lm, _, _ = dev.loss_and_grad(xt, yt, _gp().GPHyperParams.from_vector(theta - h * direction, d, 0))
+  fd = (lp - lm) / (2 * h)
+  assert abs(fd - g0 @ direction) < 1e-4 * max(1.0, abs(fd))
