@@ -61,7 +61,29 @@ typedef struct vzgp_acq {
   int use_trust_region;
   double trust_radius;          /* TrustRegion.trust_radius, computed by the host */
   const uint8_t* tr_dim_mask;   /* host [Dc]: 1 = dimension takes part; NULL = all */
+  int tr_rows;                  /* trusted points = first tr_rows rows of the model's X; 0 = all valid rows */
+  int tr_strict;                /* 0: inside if dist <= radius (acquisitions.py:160-166);
+                                   1: inside if dist <  radius (gp_ucb_pe.py:236-241) */
 } vzgp_acq;
+
+/* GP-UCB-PE acquisition (vizier/_src/algorithms/designers/gp_ucb_pe.py:282-492) built from two
+ * fitted models: A = completed trials (mean, stddev), B = completed + pending trials
+ * (stddev_from_all; its labels are irrelevant).
+ *   mode 0 (UCBScoreFunction, :344-381): mean_A + ucb_coefficient * stddev_B
+ *   mode 1 (PEScoreFunction,  :434-492): stddev_B + penalty_coefficient *
+ *                                         min(mean_A + explore_coefficient*stddev_A - threshold, 0)
+ * followed by the strict trust region of :221-242 measured against the first tr_rows rows of B. */
+typedef struct vzgp_pe_params {
+  int mode;
+  double ucb_coefficient;       /* 1.8  (mode 0) */
+  double explore_coefficient;   /* 0.5  (mode 1) */
+  double penalty_coefficient;   /* 10.0 (mode 1) */
+  double threshold;             /* _compute_ucb_threshold (:175-218), computed by the host */
+  int use_trust_region;
+  double trust_radius;
+  const uint8_t* tr_dim_mask;   /* host [Dc] or NULL */
+  int tr_rows;                  /* 0 = all rows of B */
+} vzgp_pe_params;
 
 const char* vzgp_last_error(void);       /* thread-local message of the last failure */
 int vzgp_version(void);                  /* ABI version, currently 1 */
@@ -176,6 +198,8 @@ typedef struct vzgp_eagle_config {
   double categorical_perturbation_factor;       /* 1.0  */
   double pure_categorical_perturbation_factor;  /* 30.0 (no continuous feature) */
   double prob_same_category_without_perturbation; /* 0.98 */
+  int mutate_normalization_type;  /* 0 = MEAN (default), 1 = RANDOM (eagle_strategy.py:858-885; the
+                                     GP-UCB-PE default, gp_ucb_pe.py:678-692) */
 } vzgp_eagle_config;
 
 /* VectorizedOptimizer.__call__ with VectorizedEagleStrategy
@@ -188,6 +212,17 @@ typedef struct vzgp_eagle_config {
 int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
                    const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
                    int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score);
+
+/* GP-UCB-PE scoring of M device candidates with models hA / hB (same device and stream).
+ * score [M] required; mu, sigma (model A) and sigma_all (model B) optional; all device. */
+int vzgp_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
+                  const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
+
+/* vzgp_eagle_run with the GP-UCB-PE acquisition as the scoring function (gp_ucb_pe.py:1006-1155). */
+int vzgp_eagle_run_pe(vzgp_handle* hA, vzgp_handle* hB, const vzgp_eagle_config* cfg,
+                      const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,
+                      const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
+                      double* best_score);
 
 /* RandomVectorizedStrategy with batch = max_evaluations = M
  * (random_vectorized_optimizer.py:32-123): generates M uniform candidates on

@@ -44,6 +44,7 @@ class EagleConfig:
   categorical_perturbation_factor: float = 1.0
   pure_categorical_perturbation_factor: float = 30.0
   prob_same_category_without_perturbation: float = 0.98
+  mutate_normalization_type: int = 0   # 0 MEAN, 1 RANDOM (MutateNormalizationType, eagle_strategy.py:86-98)
 
 
 def default_pool_size(n_features: int, batch_size: Optional[int], cfg: EagleConfig) -> int:
@@ -74,6 +75,8 @@ STREAM_CAT_LAPLACE = 5     # categorical logit perturbation
 STREAM_CAT_GUMBEL = 6      # Gumbel-max sampling of the mutated categories
 STREAM_TRIM_CAT = 7        # categorical features of re-seeded flies
 STREAM_RANDOM_POOL_CAT = 8
+STREAM_PULL_RAND = 9        # RANDOM force normalisation weights (eagle_strategy.py:862-877)
+STREAM_PUSH_RAND = 10
 
 
 def philox4x32(counter: np.ndarray, key: np.ndarray) -> np.ndarray:
@@ -341,8 +344,14 @@ def features_dist_squared_cat(batch, pool, batch_z, pool_z) -> np.ndarray:
   return d
 
 
-def force_scale(pool, rewards, batch, rewards_batch, cfg: EagleConfig, pool_z=None, batch_z=None) -> np.ndarray:
-  """The normalised force matrix `scale` [B, P] of _create_features (:811-899), MEAN mode."""
+def force_scale(pool, rewards, batch, rewards_batch, cfg: EagleConfig, pool_z=None, batch_z=None,
+                pull_u=None, push_u=None) -> np.ndarray:
+  """The normalised force matrix `scale` [B, P] of _create_features (:811-899).
+
+  MEAN mode, or RANDOM mode (:858-885) with injected uniform draws pull_u / push_u [B, P].  In RANDOM
+  mode the reference masks both weight matrices with (pull > 0) - pushes get zero weight - and a
+  fly without pulls gets 0/0 = NaN weights; we use zero weights there (deliberate deviation shared
+  with the CUDA kernel)."""
   dk = 0 if pool_z is None else pool_z.shape[1]
   n_features = pool.shape[1] + dk
   if dk:
@@ -356,6 +365,13 @@ def force_scale(pool, rewards, batch, rewards_batch, cfg: EagleConfig, pool_z=No
   scaled_force = scaled_dir * force * np.isfinite(rewards).astype(np.float64)[None, :]
   pulls = np.maximum(scaled_force, 0.0)
   push = np.minimum(scaled_force, 0.0)
+  if cfg.mutate_normalization_type == 1:
+    pos = (pulls > 0.0).astype(np.float64)
+    r1, r2 = pull_u * pos, push_u * pos
+    s1, s2 = r1.sum(axis=1, keepdims=True), r2.sum(axis=1, keepdims=True)
+    w1 = np.where(s1 > 0, r1 / np.where(s1 > 0, s1, 1.0), 0.0)
+    w2 = np.where(s2 > 0, r2 / np.where(s2 > 0, s2, 1.0), 0.0)
+    return cfg.normalization_scale * pulls * w1 + cfg.normalization_scale * push * w2
   with np.errstate(invalid='ignore', divide='ignore'):
     npull = cfg.normalization_scale * np.nan_to_num(pulls / np.sum(pulls > 0.0, axis=1, keepdims=True), nan=0.0)
     npush = cfg.normalization_scale * np.nan_to_num(push / np.sum(push < 0.0, axis=1, keepdims=True), nan=0.0)
@@ -381,10 +397,10 @@ def categorical_logits(pool_z, batch_z, scale, sizes, cfg: EagleConfig) -> np.nd
 
 
 def create_features_mixed(pool, pool_z, rewards, batch, batch_z, rewards_batch, perturbations, cat_noise,
-                          gumbel, sizes, cfg: EagleConfig):
+                          gumbel, sizes, cfg: EagleConfig, pull_u=None, push_u=None):
   """_create_features with categorical features.  perturbations [B, Dc] (already scaled),
   cat_noise [B, Dk, max_size] = laplace * factor * perturbation_i, gumbel [B, Dk, max_size]."""
-  scale = force_scale(pool, rewards, batch, rewards_batch, cfg, pool_z, batch_z)
+  scale = force_scale(pool, rewards, batch, rewards_batch, cfg, pool_z, batch_z, pull_u, push_u)
   change = scale @ pool - batch * np.sum(scale, axis=-1, keepdims=True)
   new_c = batch + change + perturbations
   logits = categorical_logits(pool_z, batch_z, scale, sizes, cfg) + cat_noise
@@ -440,8 +456,10 @@ def run_eagle_optimizer_mixed(score_fn, *, dim: int, sizes, pool_size: int, batc
       signs = philox_signs(seed, t, batch_size * dim).reshape(batch_size, dim)
       lap = laplace_from_uniform(philox_uniform(seed, STREAM_CAT_LAPLACE, t, batch_size * dk * smax)).reshape(batch_size, dk, smax)
       gum = gumbel_from_uniform(philox_uniform(seed, STREAM_CAT_GUMBEL, t, batch_size * dk * smax)).reshape(batch_size, dk, smax)
+      pu = philox_uniform(seed, STREAM_PULL_RAND, t, batch_size * pool_size).reshape(batch_size, pool_size)
+      qu = philox_uniform(seed, STREAM_PUSH_RAND, t, batch_size * pool_size).reshape(batch_size, pool_size)
       bc, bz = create_features_mixed(pool_c, pool_z, rewards, bc, bz, rewards[sl], signs * perts[sl][:, None],
-                                     lap * factor * perts[sl][:, None, None], gum, sizes, cfg)
+                                     lap * factor * perts[sl][:, None, None], gum, sizes, cfg, pu, qu)
     bc = np.clip(bc, 0.0, 1.0)
     r = score_fn(bc, bz)
     new_best = max(best_reward, float(np.max(r)))

@@ -511,3 +511,34 @@ def top_k(scores: np.ndarray, count: int) -> np.ndarray:
   scores = np.asarray(scores, np.float64)
   order = np.lexsort((np.arange(scores.shape[0]), -scores))
   return order[:count]
+
+
+# ----------------------------------------------------------------------------
+# GP-UCB-PE acquisition (vizier/_src/algorithms/designers/gp_ucb_pe.py)
+# ----------------------------------------------------------------------------
+def ucb_threshold(pred_a: Predictive, pred_b: Predictive, ucb_coefficient: float = 1.8) -> float:
+  """_compute_ucb_threshold (:175-218): mean of model A at the point of B's features with max UCB."""
+  mu, sd = predict(pred_a, pred_b.x, pred_b.z)
+  u = np.where(pred_b.row_valid, mu + ucb_coefficient * sd, -np.inf)
+  return float(mu[int(np.argmax(u))])
+
+
+def ucb_pe_score(pred_a: Predictive, pred_b: Predictive, xs, zs=None, *, mode: int, ucb_coefficient=1.8,
+                 explore_coefficient=0.5, penalty_coefficient=10.0, threshold=0.0, tr_dim_mask=None,
+                 tr_rows=None, trust_radius_value=None, use_trust_region=True):
+  """UCBScoreFunction.score_with_aux (:344-381, mode 0) / PEScoreFunction.score_with_aux (:434-492,
+  mode 1), single metric, with the strict trust region of :221-242 over the first tr_rows rows of B."""
+  mu, sd = predict(pred_a, xs, zs)
+  _, sd_all = predict(pred_b, xs, zs)
+  if mode == 0:
+    acq = mu + ucb_coefficient * sd_all
+  else:
+    acq = sd_all + penalty_coefficient * np.minimum(mu + sd * explore_coefficient - threshold, 0.0)
+  if use_trust_region:
+    xs = np.asarray(xs, np.float64)
+    if tr_dim_mask is None:
+      tr_dim_mask = np.ones(xs.shape[-1], bool)
+    n_tr = pred_b.x.shape[0] if tr_rows is None else tr_rows
+    dist = min_linf_distance(xs, pred_b.x[:n_tr], tr_dim_mask)
+    acq = np.where((dist < trust_radius_value) | (trust_radius_value > 0.5), acq, -1e4 - dist)
+  return acq, {'mean': mu, 'stddev': sd, 'stddev_from_all': sd_all}

@@ -135,3 +135,46 @@ def test_all_parameter_types_search_space():
       trials.append(t)
     d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
   assert best > -0.6
+
+
+def test_gp_ucb_pe_designer_batches_and_pending():
+  """Service DEFAULT algorithm (policy_factory.py:40-47): batch suggestions are spread out by the
+  pure-exploration acquisition, pending trials are respected, metadata carries the decision."""
+  from vizier_b200.designers import gp_ucb_pe
+  p = _problem(3, 0.0, 1.0)
+  f = lambda x: -np.sum((x - 0.6) ** 2)
+  opt = vb.VectorizedOptimizerFactory(strategy_factory=vb.VectorizedEagleStrategyFactory(eagle_config=gp_ucb_pe.default_eagle_config),
+                                      max_evaluations=3000, suggestion_batch_size=25)
+  d = gp_ucb_pe.VizierGPUCBPEBandit.from_problem(p, seed=4, acquisition_optimizer_factory=opt)
+  first = d.suggest(1)
+  assert first[0].metadata['seeded'] == 'center'
+  rng = np.random.default_rng(0)
+  tid = 1
+  trials = []
+  for x in rng.uniform(size=(8, 3)):
+    t = vz.Trial(parameters={f'x{j}': float(v) for j, v in enumerate(x)}, id=tid); tid += 1
+    trials.append(t.complete(vz.Measurement({'obj': float(f(x))})))
+  d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  best = max(t.final_measurement.metrics['obj'].value for t in trials)
+  for it in range(5):
+    sugg = d.suggest(3)
+    assert len(sugg) == 3
+    pts = np.array([[s.parameters[f'x{j}'].value for j in range(3)] for s in sugg])
+    assert np.min(np.linalg.norm(pts[:, None] - pts[None], axis=-1) + 10 * np.eye(3)) > 1e-3   # distinct points
+    flags = [s.metadata.ns('google_gp_ucb_pe_bandit').ns('prediction_in_warped_y_space')['use_ucb'] for s in sugg]
+    assert flags[0] in ('True', 'False') and 'False' in flags[1:]       # later members of a batch explore
+    new = []
+    for s in sugg:
+      assert p.search_space.contains(s.parameters)
+      t = s.to_trial(tid); tid += 1
+      x = np.array([t.parameters[f'x{j}'].value for j in range(3)])
+      new.append(t.complete(vz.Measurement({'obj': float(f(x))})))
+      best = max(best, new[-1].final_measurement.metrics['obj'].value)
+    d.update(vz.CompletedTrials(new), vz.ActiveTrials())
+  assert best > -0.05
+  # an ACTIVE (pending) trial steers the next suggestion away from itself
+  pending = vz.Trial(parameters={'x0': 0.6, 'x1': 0.6, 'x2': 0.6}, id=tid)
+  d.update(vz.CompletedTrials([]), vz.ActiveTrials([pending]))
+  s = d.suggest(1)[0]
+  x = np.array([s.parameters[f'x{j}'].value for j in range(3)])
+  assert np.linalg.norm(x - 0.6) > 1e-3

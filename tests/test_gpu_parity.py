@@ -493,3 +493,76 @@ def test_nll_grad_d50_multiblock(dev):
   lm, _, _ = dev.loss_and_grad(xt, yt, _gp().GPHyperParams.from_vector(theta - h * direction, d, 0))
   fd = (lp - lm) / (2 * h)
   assert abs(fd - g0 @ direction) < 1e-4 * max(1.0, abs(fd))
+
+
+def _two_models(dev, n, d, n_pending, seed, high_noise=False):
+  from vizier_b200 import gp
+  x, y, _ = _problem(n, d, seed)
+  xp = np.random.default_rng(seed + 1).uniform(size=(n_pending, d))
+  po, pg = _params(d)
+  pred_a = go.precompute_predictive(po, x, y)
+  xb = np.concatenate([x, xp]); yb = np.concatenate([y, np.zeros(n_pending)])
+  pob = go.GPParams(po.signal_variance, po.continuous_length_scale_squared, 1e-10 if high_noise else po.observation_noise_variance)
+  pgb = gp.GPHyperParams(pob.signal_variance, pob.continuous_length_scale_squared, pob.observation_noise_variance)
+  pred_b = go.precompute_predictive(pob, xb, yb)
+  dev_b = gp.DeviceGP(0, stream=dev.stream)
+  dev.fit(x, y, pg)
+  dev_b.fit(xb, yb, pgb)
+  return x, pred_a, pred_b, dev_b
+
+
+@pytest.mark.parametrize('mode,n,n_pending,tr_rows,high_noise', [(0, 30, 4, None, False), (1, 30, 4, 32, False),
+                                                                (1, 150, 7, 152, True), (0, 150, 0, None, False)])
+def test_ucb_pe_score(dev, mode, n, n_pending, tr_rows, high_noise):
+  """vzgp_score_pe against UCBScoreFunction / PEScoreFunction restated in the oracle
+  (gp_ucb_pe.py:344-381, :434-492, strict trust region :221-242)."""
+  from vizier_b200 import gp
+  d = 4
+  x, pred_a, pred_b, dev_b = _two_models(dev, n, d, n_pending, 81, high_noise)
+  xs = np.random.default_rng(82).uniform(size=(333, d))
+  xs[:3] = x[:3]
+  mask = np.array([True, True, False, True])
+  rows = (n + n_pending) if tr_rows is None else tr_rows
+  radius = go.trust_radius(rows, int(mask.sum()), 0)
+  thr = go.ucb_threshold(pred_a, pred_b, 1.8)
+  want, aux = go.ucb_pe_score(pred_a, pred_b, xs, mode=mode, threshold=thr, tr_dim_mask=mask, tr_rows=rows,
+                              trust_radius_value=radius)
+  pe = gp.UcbPeAcquisition(mode=mode, threshold=thr, trust_radius=radius, tr_dim_mask=mask, tr_rows=0 if tr_rows is None else tr_rows)
+  out = dev.score_pe(dev_b, xs, pe)
+  np.testing.assert_allclose(out['mean'].cpu().numpy(), aux['mean'], atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['stddev'].cpu().numpy(), aux['stddev'], atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['stddev_from_all'].cpu().numpy(), aux['stddev_from_all'], atol=1e-8 if high_noise else TOL, rtol=0)
+  np.testing.assert_allclose(out['score'].cpu().numpy(), want, atol=1e-7 if high_noise else 1e-9, rtol=0)
+  if radius <= 0.5:
+    assert np.any(want < -1e3)
+  dev_b.close()
+
+
+def test_eagle_random_normalisation_with_pe_acquisition(dev):
+  """GP-UCB-PE's optimiser configuration: RANDOM force normalisation (eagle_strategy.py:858-885) and
+  the PE acquisition as scoring function, trajectory against the oracle with shared Philox draws."""
+  from vizier_b200 import _lib, gp
+  n, d, n_pending = 40, 3, 3
+  x, pred_a, pred_b, dev_b = _two_models(dev, n, d, n_pending, 91)
+  mask = np.ones(d, bool)
+  rows = n + n_pending
+  radius = go.trust_radius(rows, d, 0)
+  thr = go.ucb_threshold(pred_a, pred_b, 1.8)
+  cfg_o = eo.EagleConfig(visibility=3.678, gravity=3.028, negative_gravity=0.0304, perturbation=0.2334,
+                         perturbation_lower_bound=7.376e-4, penalize_factor=0.7818, normalization_scale=1.989,
+                         prior_trials_pool_pct=0.4235, mutate_normalization_type=1)
+  pool, batch, steps = 25, 25, 7
+  for mode in (0, 1):
+    score_fn = lambda xc, xz: go.ucb_pe_score(pred_a, pred_b, xc, mode=mode, threshold=thr, tr_dim_mask=mask,
+                                              tr_rows=rows, trust_radius_value=radius)[0]
+    wc, _, wr = eo.run_eagle_optimizer_mixed(score_fn, dim=d, sizes=np.zeros(0, int), pool_size=pool, batch_size=batch,
+                                             max_evaluations=steps * batch, count=2, seed=13, cfg=cfg_o, prior_c=x,
+                                             prior_z=np.zeros((n, 0), np.int32))
+    cfg = _lib.EagleConfig(cfg_o.visibility, cfg_o.gravity, cfg_o.negative_gravity, cfg_o.perturbation,
+                           cfg_o.perturbation_lower_bound, cfg_o.penalize_factor, cfg_o.normalization_scale,
+                           cfg_o.prior_trials_pool_pct, pool, batch, steps * batch, 1.0, 30.0, 0.98, 1)
+    pe = gp.UcbPeAcquisition(mode=mode, threshold=thr, trust_radius=radius, tr_dim_mask=mask)
+    bx, _, br = dev.eagle_run(cfg, pe, 2, 13, prior=x, other=dev_b)
+    np.testing.assert_allclose(br, wr, atol=1e-8)
+    np.testing.assert_allclose(bx, wc, atol=1e-8)
+  dev_b.close()

@@ -43,6 +43,22 @@ class Acq(C.Structure):
       ('use_trust_region', C.c_int),
       ('trust_radius', C.c_double),
       ('tr_dim_mask', C.POINTER(C.c_uint8)),
+      ('tr_rows', C.c_int),
+      ('tr_strict', C.c_int),
+  ]
+
+
+class PeParams(C.Structure):
+  _fields_ = [
+      ('mode', C.c_int),
+      ('ucb_coefficient', C.c_double),
+      ('explore_coefficient', C.c_double),
+      ('penalty_coefficient', C.c_double),
+      ('threshold', C.c_double),
+      ('use_trust_region', C.c_int),
+      ('trust_radius', C.c_double),
+      ('tr_dim_mask', C.POINTER(C.c_uint8)),
+      ('tr_rows', C.c_int),
   ]
 
 
@@ -62,6 +78,7 @@ class EagleConfig(C.Structure):
       ('categorical_perturbation_factor', C.c_double),
       ('pure_categorical_perturbation_factor', C.c_double),
       ('prob_same_category_without_perturbation', C.c_double),
+      ('mutate_normalization_type', C.c_int),
   ]
 
   def __init__(self, *args, **kwargs):
@@ -85,6 +102,7 @@ _pi32 = C.POINTER(C.c_int32)
 _pP = C.POINTER(Params)
 _pA = C.POINTER(Acq)
 _pE = C.POINTER(EagleConfig)
+_pPE = C.POINTER(PeParams)
 
 # name -> (restype, argtypes).  Must list every symbol declared in include/vzgp.h
 # (tests/test_abi.py checks this against the header).
@@ -111,6 +129,8 @@ SIGNATURES = {
     'vzgp_topk': (_i, [_vp, _vp, _i64, _i, _pi64, _pd]),
     'vzgp_score_topk': (_i, [_vp, _vp, _vp, _i, _pA, _i, _vp, _pd, _pd, _pi64]),
     'vzgp_eagle_run': (_i, [_vp, _pE, _pA, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
+    'vzgp_score_pe': (_i, [_vp, _vp, _vp, _vp, _i, _pPE, _vp, _vp, _vp, _vp]),
+    'vzgp_eagle_run_pe': (_i, [_vp, _vp, _pE, _pPE, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
     'vzgp_random_search': (_i, [_vp, _i64, _i64, _pA, _pi32, _i, _u64, _pd, _pi32, _pd, _pi64]),
     'vzgp_random_pool': (_i, [_vp, _i64, _i, _i64, _u64, _vp]),
     'vzgp_random_pool_cat': (_i, [_vp, _i64, _i, _pi32, _i64, _u64, _vp]),

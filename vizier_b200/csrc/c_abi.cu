@@ -180,7 +180,7 @@ int vzgp_destroy(vzgp_handle* h) {
   Guard g(h->device);
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->XT,
-                    &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle})
+                    &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle, &h->pe_tmp})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->copy_stream) {
@@ -522,10 +522,15 @@ int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp
   return 0;
 }
 
-int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq, const double* prior,
-                   const int32_t* prior_z, int n_prior, const int32_t* cat_sizes, int count, uint64_t seed,
-                   double* best_x, int32_t* best_z, double* best_score) {
-  VZ_ARG(h && cfg && acq && best_score, "handle / pointers");
+static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
+                          const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,
+                          const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
+                          double* best_score) {
+  VZ_ARG(h && cfg && (acq || pe) && best_score, "handle / pointers");
+  auto score_batch = [&](const double* xs, const int32_t* zs, int m, double* out) -> int {
+    if (pe) return launch_score_pe(h, hB, xs, zs, m, pe, out, nullptr, nullptr, nullptr);
+    return launch_score(h, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
+  };
   if (!h->fitted) { set_error("vzgp_eagle_run before vzgp_fit"); return VZGP_ERR_STATE; }
   VZ_ARG(best_x != nullptr || h->dc == 0, "best_x");
   VZ_ARG(best_z != nullptr || h->dk == 0, "best_z");
@@ -575,13 +580,13 @@ int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq*
   VZ_TRY(eagle_prepare(e));
   VZ_TRY(launch_eagle_init(h, e));
   if (n_prior > 0) {
-    VZ_TRY(launch_score(h, prior, Dk > 0 ? prior_z : nullptr, n_prior, acq, prior_r, nullptr, nullptr, nullptr));
+    VZ_TRY(score_batch(prior, Dk > 0 ? prior_z : nullptr, n_prior, prior_r));
     VZ_TRY(launch_eagle_seed_priors(h, e, prior, prior_z, prior_r, n_prior, ord, chosen_r));
   }
   const int steps = (cfg->max_evaluations - 1) / B + 1;
   auto one_step = [&]() -> int {
     VZ_TRY(launch_eagle_suggest(h, e));
-    VZ_TRY(launch_score(h, e.batch, Dk > 0 ? e.batch_z : nullptr, B, acq, e.batch_r, nullptr, nullptr, nullptr));
+    VZ_TRY(score_batch(e.batch, Dk > 0 ? e.batch_z : nullptr, B, e.batch_r));
     VZ_TRY(launch_eagle_update(h, e));
     return 0;
   };
@@ -626,6 +631,40 @@ int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq*
   VZ_CUDA(cudaMemcpyAsync(best_score, e.best_r, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
+}
+
+int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq, const double* prior,
+                   const int32_t* prior_z, int n_prior, const int32_t* cat_sizes, int count, uint64_t seed,
+                   double* best_x, int32_t* best_z, double* best_score) {
+  VZ_ARG(acq != nullptr, "acq");
+  return eagle_run_impl(h, nullptr, cfg, acq, nullptr, prior, prior_z, n_prior, cat_sizes, count, seed, best_x,
+                        best_z, best_score);
+}
+
+static int check_pe(vzgp_handle* hA, vzgp_handle* hB, const vzgp_pe_params* pe) {
+  VZ_ARG(hA && hB && pe, "handles / pe");
+  if (!hA->fitted || !hB->fitted) { set_error("GP-UCB-PE scoring needs both models fitted"); return VZGP_ERR_STATE; }
+  VZ_ARG(hA->device == hB->device && hA->stream == hB->stream, "both models must share device and stream");
+  VZ_ARG(hA->dc == hB->dc && hA->dk == hB->dk, "both models must have the same feature dimensions");
+  VZ_ARG(pe->mode == 0 || pe->mode == 1, "mode");
+  return 0;
+}
+
+int vzgp_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
+                  const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all) {
+  VZ_TRY(check_pe(hA, hB, pe));
+  VZ_ARG(M >= 0 && (M == 0 || score != nullptr), "M / score");
+  Guard g(hA->device);
+  return launch_score_pe(hA, hB, Xs, Zs, M, pe, score, mu, sigma, sigma_all);
+}
+
+int vzgp_eagle_run_pe(vzgp_handle* hA, vzgp_handle* hB, const vzgp_eagle_config* cfg,
+                      const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,
+                      const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
+                      double* best_score) {
+  VZ_TRY(check_pe(hA, hB, pe));
+  return eagle_run_impl(hA, hB, cfg, nullptr, pe, prior, prior_z, n_prior, cat_sizes, count, seed, best_x, best_z,
+                        best_score);
 }
 
 int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,

@@ -126,6 +126,7 @@ struct vzgp_handle {
   vzgp::DevBuf xs_dev;  // staging for *_host entry points
   vzgp::DevBuf out_dev;
   vzgp::DevBuf eagle;   // eagle state
+  vzgp::DevBuf pe_tmp;  // GP-UCB-PE: per-candidate pieces of the two models
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaStream_t copy_stream = nullptr;   // H2D staging of vzgp_score_host, overlapped with scoring

@@ -19,7 +19,8 @@
 
 namespace vzgp {
 
-constexpr uint32_t kStreamInitCat = 4, kStreamCatLaplace = 5, kStreamCatGumbel = 6, kStreamTrimCat = 7;
+constexpr uint32_t kStreamInitCat = 4, kStreamCatLaplace = 5, kStreamCatGumbel = 6, kStreamTrimCat = 7,
+                   kStreamPullRand = 9, kStreamPushRand = 10;
 
 __device__ __forceinline__ double laplace_from_uniform(double u) {
   const double v = u - 0.5;
@@ -186,12 +187,37 @@ __global__ void __launch_bounds__(256) k_eagle_suggest(EagleDev e) {
     npush += __shfl_xor_sync(0xffffffffu, npush, o);
   }
   __syncwarp();
-  const double wpull = npull > 0 ? e.cfg.normalization_scale / (double)npull : 0.0;
-  const double wpush = npush > 0 ? e.cfg.normalization_scale / (double)npush : 0.0;
-  // convert the forces to the normalised scale in place
-  for (int j = lane; j < P; j += 32) {
-    const double f = s_f[j];
-    s_f[j] = f > 0.0 ? f * wpull : (f < 0.0 ? f * wpush : 0.0);
+  if (e.cfg.mutate_normalization_type == 1) {
+    // RANDOM normalisation (eagle_strategy.py:858-885): random convex weights over the pulling
+    // flies.  The reference masks BOTH weight matrices with (pull > 0), so pushes end up with zero
+    // weight (reproduced).  Deliberate deviation: a fly that nobody pulls gets 0/0 = NaN weights
+    // in the reference (NaN candidate, NaN best_reward from then on); here its weights are 0.
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = lane; j < P; j += 32) {
+      const double pos = s_f[j] > 0.0 ? 1.0 : 0.0;
+      s1 += philox_uniform(e.seed, kStreamPullRand, (uint32_t)t, (uint64_t)b * P + j) * pos;
+      s2 += philox_uniform(e.seed, kStreamPushRand, (uint32_t)t, (uint64_t)b * P + j) * pos;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    for (int j = lane; j < P; j += 32) {
+      const double f = s_f[j];
+      const double pos = f > 0.0 ? 1.0 : 0.0;
+      const double w1 = s1 > 0.0 ? philox_uniform(e.seed, kStreamPullRand, (uint32_t)t, (uint64_t)b * P + j) * pos / s1 : 0.0;
+      const double w2 = s2 > 0.0 ? philox_uniform(e.seed, kStreamPushRand, (uint32_t)t, (uint64_t)b * P + j) * pos / s2 : 0.0;
+      s_f[j] = e.cfg.normalization_scale * fmax(f, 0.0) * w1 + e.cfg.normalization_scale * fmin(f, 0.0) * w2;
+    }
+  } else {
+    const double wpull = npull > 0 ? e.cfg.normalization_scale / (double)npull : 0.0;
+    const double wpush = npush > 0 ? e.cfg.normalization_scale / (double)npush : 0.0;
+    // convert the forces to the normalised scale in place
+    for (int j = lane; j < P; j += 32) {
+      const double f = s_f[j];
+      s_f[j] = f > 0.0 ? f * wpull : (f < 0.0 ? f * wpush : 0.0);
+    }
   }
   __syncwarp();
   // ---- continuous features: lane handles dims lane and lane+32 ----

@@ -40,6 +40,8 @@ int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int
 
 int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                  double* score, double* mu, double* sigma, double* linf);
+int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
+                    const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
 int launch_random_fill(vzgp_handle* h, double* X, int64_t total, int64_t elem_base, uint64_t seed,
                        uint32_t stream, uint32_t iteration);
 struct ArgMax {

@@ -49,6 +49,8 @@ struct ScoreArgs {
   double sn2;
   double coef;
   int apply_tr;     // trust region modifies the score
+  int tr_rows;      // trusted points = first tr_rows rows of X
+  int tr_strict;    // inside test: dist < radius instead of <=
   double radius;
   uint8_t tr_mask[kMaxDc];
   double* scratch;  // [gridDim.x][64][np]
@@ -130,7 +132,7 @@ __device__ __forceinline__ void emit_score(const ScoreArgs& a, int m, double rs,
   const double sd = sqrt(var);
   double sc = fma(a.coef, sd, mean);
   if (a.apply_tr) {
-    const bool inside = (dist <= a.radius) || (a.radius > 0.5);
+    const bool inside = (a.tr_strict ? (dist < a.radius) : (dist <= a.radius)) || (a.radius > 0.5);
     sc = inside ? sc : (-1e4 - dist);
   }
   a.score[m] = sc;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) k_score(const __grid_constan
           const bool valid = (jb * 64 + cj) < a.n_valid;
           kv[j] = valid ? matern52(d2[i][j], a.kp.sf2) : 0.0;
           mu_part[i] = fma(kv[j], alj[cj], mu_part[i]);
-          if (WITH_LINF && valid) lmin[i] = fmin(lmin[i], lf[i][j]);
+          if (WITH_LINF && (jb * 64 + cj) < a.tr_rows) lmin[i] = fmin(lmin[i], lf[i][j]);
         }
         double* dst = scr + (size_t)GP1::row_of(ty, i) * np + jb * 64;
         *reinterpret_cast<double2*>(dst + GP1::col_of(tx, 0)) = make_double2(kv[0], kv[1]);
@@ -535,6 +537,8 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
   a.kp = h->kp; a.sn2 = h->sn2;
   a.coef = acq->ucb_coefficient;
   a.apply_tr = acq->use_trust_region ? 1 : 0;
+  a.tr_rows = (acq->tr_rows > 0 && acq->tr_rows < h->n_valid) ? acq->tr_rows : h->n_valid;
+  a.tr_strict = acq->tr_strict ? 1 : 0;
   a.radius = acq->trust_radius;
   for (int d = 0; d < kMaxDc; ++d)
     a.tr_mask[d] = (d < h->dc) ? (acq->tr_dim_mask ? (acq->tr_dim_mask[d] ? 1 : 0) : 1) : 0;
@@ -570,6 +574,65 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
     VZ_CHECK_LAUNCH();
     h->launches++;
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// GP-UCB-PE acquisition from the pieces of two models (gp_ucb_pe.py:344-381, :434-492, :221-242).
+// ---------------------------------------------------------------------------
+struct PeCombine {
+  int mode;
+  double ucb, explore, penalty, threshold;
+  int apply_tr;
+  double radius;
+};
+__global__ void k_pe_combine(int M, PeCombine p, const double* __restrict__ mu, const double* __restrict__ sd,
+                             const double* __restrict__ sd_all, const double* __restrict__ linf,
+                             double* __restrict__ score) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double acq;
+  if (p.mode == 0) {
+    acq = fma(p.ucb, sd_all[m], mu[m]);
+  } else {
+    const double explore_ucb = fma(sd[m], p.explore, mu[m]);
+    acq = sd_all[m] + p.penalty * fmin(explore_ucb - p.threshold, 0.0);
+  }
+  if (p.apply_tr) {
+    const double dist = linf[m];
+    const bool inside = (dist < p.radius) || (p.radius > 0.5);
+    acq = inside ? acq : (-1e4 - dist);
+  }
+  score[m] = acq;
+}
+
+int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
+                    const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all) {
+  if (M <= 0) return 0;
+  VZ_TRY(hA->pe_tmp.reserve(sizeof(double) * 6 * (size_t)M));
+  double* t = hA->pe_tmp.as<double>();
+  double* mu_a = mu ? mu : t;
+  double* sd_a = sigma ? sigma : t + M;
+  double* sd_b = sigma_all ? sigma_all : t + 2 * (size_t)M;
+  double* linf_b = t + 3 * (size_t)M;
+  double* dummy_a = t + 4 * (size_t)M;
+  double* dummy_b = t + 5 * (size_t)M;
+  vzgp_acq none;
+  none.ucb_coefficient = 0.0; none.use_trust_region = 0; none.trust_radius = 1.0; none.tr_dim_mask = nullptr;
+  none.tr_rows = 0; none.tr_strict = 0;
+  VZ_TRY(launch_score(hA, Xs, Zs, M, &none, dummy_a, mu_a, sd_a, nullptr));
+  vzgp_acq accb = none;
+  accb.tr_dim_mask = pe->tr_dim_mask;
+  accb.tr_rows = pe->tr_rows;
+  const bool want_tr = pe->use_trust_region && pe->trust_radius <= 0.5;
+  VZ_TRY(launch_score(hB, Xs, Zs, M, &accb, dummy_b, nullptr, sd_b, want_tr ? linf_b : nullptr));
+  PeCombine p;
+  p.mode = pe->mode; p.ucb = pe->ucb_coefficient; p.explore = pe->explore_coefficient;
+  p.penalty = pe->penalty_coefficient; p.threshold = pe->threshold;
+  p.apply_tr = want_tr ? 1 : 0; p.radius = pe->trust_radius;
+  k_pe_combine<<<(M + 255) / 256, 256, 0, hA->stream>>>(M, p, mu_a, sd_a, sd_b, linf_b, score);
+  VZ_CHECK_LAUNCH();
+  hA->launches++;
   return 0;
 }
 

@@ -1,0 +1,298 @@
+"""`VizierGPUCBPEBandit`: GP-UCB with Pure Exploration, the Vizier service's DEFAULT algorithm.
+
+Mirrors vizier/_src/algorithms/designers/gp_ucb_pe.py:609-1445 on the single-metric default
+configuration (`UCBPEConfig()` with `optimize_set_acquisition_for_exploration=False`):
+
+  * ARD: 4 random + 1 fixed initialisation (:828-838), L-BFGS-B maxiter=500, tol=1e-5 (:596-604);
+  * model A = GP on the completed trials (mean, stddev); model B = same hyper-parameters on
+    completed + pending trials (stddev_from_all; noise forced to 1e-10 when the signal-to-noise
+    ratio is low, :996-1004);
+  * per suggestion: UCB (mean_A + 1.8 stddev_B) when trials completed after the newest active
+    trial was created, else PE (stddev_B + 10 min(mean_A + 0.5 stddev_A - threshold, 0)), with the
+    random overwrites of :1017-1046; strict trust region over completed + initially active trials;
+  * batches: every suggestion joins the pending set before the next one is optimised (:1429-1445);
+  * acquisition optimiser: Eagle with the tuned UCB-PE config and RANDOM force normalisation
+    (:678-698).
+
+Everything numeric runs in libvzgp (two handles on one stream, `vzgp_score_pe`,
+`vzgp_eagle_run_pe`).  Not implemented: multi-metric, set-PE batches
+(`optimize_set_acquisition_for_exploration=True`), `prior_acquisition`, linear-kernel mixing,
+ensembles, padding - each raises NotImplementedError.
+"""
+
+from __future__ import annotations
+
+import copy
+import dataclasses
+import datetime
+import json
+import random
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from vizier_b200 import acquisitions as acq_lib
+from vizier_b200 import ard
+from vizier_b200 import converters
+from vizier_b200 import gp
+from vizier_b200 import optimizers as vb
+from vizier_b200 import output_warpers
+from vizier_b200 import profiler
+from vizier_b200 import vz
+from vizier_b200.designers import gp_bandit as _gpb
+
+_MAX_NUM_FEASIBLE_VALUES_FOR_TRUST_REGION = 1000
+
+
+@dataclasses.dataclass(frozen=True)
+class UCBPEConfig:
+  """gp_ucb_pe.py:80-135 (single-metric fields)."""
+
+  ucb_coefficient: float = 1.8
+  explore_region_ucb_coefficient: float = 0.5
+  cb_violation_penalty_coefficient: float = 10.0
+  ucb_overwrite_probability: float = 0.25
+  pe_overwrite_probability: float = 0.1
+  pe_overwrite_probability_in_high_noise: float = 0.7
+  signal_to_noise_threshold: float = 0.7
+  optimize_set_acquisition_for_exploration: bool = False
+
+
+# gp_ucb_pe.py:678-698
+default_eagle_config = vb.EagleStrategyConfig(
+    visibility=3.6782451729470043,
+    gravity=3.028167342024462,
+    negative_gravity=0.03036267153343141,
+    perturbation=0.23337470891647027,
+    categorical_perturbation_factor=9.587350648631066,
+    pure_categorical_perturbation_factor=28.636337967676518,
+    prob_same_category_without_perturbation=0.9744882009359648,
+    perturbation_lower_bound=7.376256294543107e-4,
+    penalize_factor=0.7817632796830948,
+    pool_size_exponent=2.0494446726436744,
+    mutate_normalization_type=1,  # RANDOM
+    normalization_scale=1.9893618760239418,
+    prior_trials_pool_pct=0.423499384081575,
+)
+default_acquisition_optimizer_factory = vb.VectorizedOptimizerFactory(
+    strategy_factory=vb.VectorizedEagleStrategyFactory(eagle_config=default_eagle_config),
+    max_evaluations=75000,
+    suggestion_batch_size=25,
+)
+
+
+def default_ard_optimizer() -> ard.ScipyLbfgsB:
+  """gp_ucb_pe.py:596-604 (the 40-minute wall-clock guard is not needed at GPU speed)."""
+  return ard.ScipyLbfgsB(ard.LbfgsBOptions(num_line_search_steps=20, tol=1e-5, maxiter=500))
+
+
+def _has_new_completed_trials(completed: Sequence[Any], active: Sequence[Any]) -> bool:
+  """gp_ucb_pe.py:142-172."""
+  if not completed:
+    return False
+  if not active:
+    return True
+  done = [t.completion_time for t in completed]
+  made = [t.creation_time for t in active]
+  if not all(done):
+    raise ValueError('All completed trials must have completion times.')
+  if not all(made):
+    raise ValueError('All active trials must have creation times.')
+  return max(done) > max(made)
+
+
+class VizierGPUCBPEBandit:
+  """GP-UCB-PE designer; see module docstring."""
+
+  def __init__(self, problem, *, acquisition_optimizer_factory: vb.VectorizedOptimizerFactory = default_acquisition_optimizer_factory,
+               ensemble_size: Optional[int] = 1, ard_optimizer: Optional[ard.ScipyLbfgsB] = None,
+               ard_random_restarts: int = 4, use_trust_region: bool = True, num_seed_trials: int = 1,
+               config: UCBPEConfig = UCBPEConfig(), rng: Any = None, clear_jax_cache: bool = False,
+               padding_schedule=None, prior_acquisition=None, mixes_linear_kernel: bool = False, device: int = 0):
+    if problem.search_space.is_conditional:
+      raise ValueError(f'{type(self)} does not support conditional search.')
+    if len(problem.metric_information) != 1:
+      raise NotImplementedError('vizier_b200.VizierGPUCBPEBandit implements the single-metric path only.')
+    if config.optimize_set_acquisition_for_exploration:
+      raise NotImplementedError('set-PE batches are not implemented.')
+    if prior_acquisition is not None or mixes_linear_kernel or (ensemble_size or 1) != 1:
+      raise NotImplementedError('prior_acquisition / linear kernel / ensembles are not implemented.')
+    del clear_jax_cache, padding_schedule
+    self._problem = problem
+    self._acquisition_optimizer_factory = acquisition_optimizer_factory
+    self._ard_optimizer = ard_optimizer or default_ard_optimizer()
+    self._ard_random_restarts = ard_random_restarts
+    self._use_trust_region = use_trust_region
+    self._num_seed_trials = num_seed_trials
+    self._config = config
+    self._metadata_ns = 'google_gp_ucb_pe_bandit'
+    self._rng = np.random.default_rng(_gpb._seed_from(rng))
+    self._converter = converters.TrialToModelInputConverter.from_problem(problem)
+    self._halton_offset = int(self._rng.integers(0, 2**16))
+    self._halton_count = 0
+    self._all_completed_trials: list = []
+    self._all_active_trials: Sequence[Any] = []
+    self._output_warper = None
+    self._device_index = device
+    self._dev_a: Optional[gp.DeviceGP] = None
+    self._dev_b: Optional[gp.DeviceGP] = None
+
+  # ------------------------------------------------------------------ API
+  def update(self, completed, all_active) -> None:
+    """gp_ucb_pe.py:740-744."""
+    self._all_completed_trials.extend(copy.deepcopy(list(completed.trials)))
+    self._all_active_trials = copy.deepcopy(list(all_active.trials))
+
+  @classmethod
+  def from_problem(cls, problem, seed: Optional[int] = None, **kwargs) -> 'VizierGPUCBPEBandit':
+    return cls(problem, rng=random.getrandbits(32) if seed is None else seed, **kwargs)
+
+  # ------------------------------------------------------------------ internals
+  def _devices(self):
+    if self._dev_a is None:
+      self._dev_a = gp.DeviceGP(self._device_index)
+      self._dev_b = gp.DeviceGP(self._device_index, stream=self._dev_a.stream)  # same stream: ordered launches
+    return self._dev_a, self._dev_b
+
+  def _generate_seed_trials(self, count: int):
+    """gp_ucb_pe.py:750-787: centre first (if nothing exists yet), quasi-random afterwards."""
+    out = []
+    dc, dk = self._converter.n_continuous, self._converter.n_categorical
+    if not self._all_completed_trials and not self._all_active_trials:
+      params = self._converter.to_parameters(0.5 * np.ones((1, dc)), np.zeros((1, dk), np.int32))[0]
+      out.append(vz.TrialSuggestion(params, metadata=vz.Metadata({'seeded': 'center'})))
+    while len(out) < count:
+      self._halton_count += 1
+      idx = self._halton_offset + self._halton_count
+      cont = np.array([[_gpb._halton(idx, _gpb._PRIMES[j % len(_gpb._PRIMES)]) for j in range(dc)]])
+      cat = np.array([[min(int(_gpb._halton(idx, _gpb._PRIMES[(dc + j) % len(_gpb._PRIMES)]) * s), s - 1)
+                       for j, s in enumerate(self._converter.categorical_sizes)]], np.int32).reshape(1, dk)
+      out.append(vz.TrialSuggestion(self._converter.to_parameters(cont, cat)[0]))
+    return out
+
+  @profiler.record_runtime
+  def _trials_to_data(self, trials):
+    """gp_ucb_pe.py:917-942: a fresh default warper per call."""
+    (cont, cat), labels = self._converter.to_xy(trials)
+    self._output_warper = output_warpers.create_default_warper()
+    warped = self._output_warper.warp(labels[:, 0:1]) if labels.shape[0] else labels[:, 0:1]
+    return cont, cat, warped
+
+  @profiler.record_runtime
+  def _build_gp_model_and_optimize_parameters(self, cont, cat, labels) -> gp.GPHyperParams:
+    """gp_ucb_pe.py:789-894: one fixed + `ard_random_restarts` random initialisations."""
+    dc, dk = cont.shape[1], cat.shape[1]
+    rng = np.random.default_rng(int(self._rng.integers(2**62)))
+    random_inits = ard.log_uniform_init(rng, dc, dk, self._ard_random_restarts)
+    fixed = gp.GPHyperParams(0.039, np.ones(dc), 0.0039, np.ones(dk)).to_vector()[None, :]
+    inits = np.concatenate([fixed, random_inits], axis=0)
+    if cont.shape[0] == 0:
+      # no completed trial yet: the dummy loss makes the optimiser return its first initial point
+      return gp.GPHyperParams.from_vector(inits[0], dc, dk)
+    dev_a, _ = self._devices()
+    import torch  # device-memory handles only
+    xt = torch.from_numpy(np.ascontiguousarray(cont)).to(dev_a.device)
+    yt = torch.from_numpy(np.ascontiguousarray(labels[:, 0])).to(dev_a.device)
+    zt = torch.from_numpy(np.ascontiguousarray(cat)).to(dev_a.device) if dk else None
+    lo, hi = gp.param_bounds(dc, dk)
+
+    def f(theta):
+      loss, grad, _ = dev_a.loss_and_grad(xt, yt, gp.GPHyperParams.from_vector(theta, dc, dk), z=zt)
+      if not np.isfinite(loss):
+        return 1e300, np.zeros_like(theta)
+      return loss, grad
+
+    best, _ = self._ard_optimizer(inits, f, list(zip(lo, hi)), best_n=1)
+    return gp.GPHyperParams.from_vector(best[0], dc, dk)
+
+  def _fit_all_features(self, params: gp.GPHyperParams, cont, cat, labels, pend_c, pend_z, noise_is_high: bool):
+    """_get_predictive_all_features (:944-1004): model B on completed + pending, dummy labels."""
+    _, dev_b = self._devices()
+    xc = np.concatenate([cont, pend_c], axis=0)
+    xz = np.concatenate([cat, pend_z], axis=0)
+    y = np.concatenate([labels[:, 0], np.zeros(pend_c.shape[0])])
+    p = params
+    if noise_is_high:
+      p = gp.GPHyperParams(params.signal_variance, params.continuous_length_scale_squared, 1e-10,
+                           params.categorical_length_scale_squared)
+    dev_b.fit(xc, y, p, z=xz if xz.shape[1] else None)
+    return xc, xz
+
+  @profiler.record_runtime
+  def _suggest_one(self, active_trials, cont, cat, labels, params, mask, radius, n_tr_rows):
+    """gp_ucb_pe.py:1006-1155."""
+    start = datetime.datetime.now()
+    cfg = self._config
+    dev_a, dev_b = self._devices()
+    snr = params.signal_variance / max(params.observation_noise_variance, 1e-12)
+    noise_is_high = snr < cfg.signal_to_noise_threshold
+    pe_overwrite = cfg.pe_overwrite_probability_in_high_noise if noise_is_high else cfg.pe_overwrite_probability
+    u = float(self._rng.uniform())
+    if _has_new_completed_trials(self._all_completed_trials, active_trials):
+      use_ucb = not (u < pe_overwrite)
+    else:
+      use_ucb = len(self._all_completed_trials) > 0 and (u < cfg.ucb_overwrite_probability)
+
+    pend_c, pend_z = self._converter.to_features(active_trials)
+    pend_c = np.nan_to_num(pend_c, nan=0.0)
+    has_model = cont.shape[0] + pend_c.shape[0] > 0
+    xc_all, xz_all = self._fit_all_features(params, cont, cat, labels, pend_c, pend_z, noise_is_high) if has_model else (cont, cat)
+    dk = cat.shape[1]
+    threshold = 0.0
+    if not use_ucb and cont.shape[0] > 0:
+      # _compute_ucb_threshold (:175-218): mean of A at B's feature with the largest UCB_A
+      out = dev_a.score(xc_all, gp.Acquisition(cfg.ucb_coefficient, False, 1.0), zs=xz_all if dk else None, with_aux=True)
+      dev_a.synchronize()
+      mu = out['mean'].cpu().numpy(); sd = out['stddev'].cpu().numpy()
+      threshold = float(mu[int(np.argmax(mu + cfg.ucb_coefficient * sd))])
+    pe = gp.UcbPeAcquisition(
+        mode=0 if use_ucb else 1, ucb_coefficient=cfg.ucb_coefficient,
+        explore_coefficient=cfg.explore_region_ucb_coefficient,
+        penalty_coefficient=cfg.cb_violation_penalty_coefficient, threshold=threshold,
+        use_trust_region=self._use_trust_region, trust_radius=radius, tr_dim_mask=mask, tr_rows=n_tr_rows)
+    optimizer = self._acquisition_optimizer_factory(self._converter)
+    prior = converters.trials_to_sorted_features(self._all_completed_trials, self._converter)
+    seed = int(self._rng.integers(2**62))
+    res = optimizer(dev_a, pe, count=1, prior_features=None if prior is None else prior[0],
+                    prior_categorical=None if prior is None else prior[1], seed=seed, other=dev_b)
+    params_dict = self._converter.to_parameters(res.features[0:1], None if res.categorical is None else res.categorical[0:1])[0]
+    md = vz.Metadata()
+    md.ns('devinfo')['acquisition_optimization'] = json.dumps(
+        {'acquisition': float(res.rewards[0])} | {k: float(v[0]) for k, v in res.aux.items()})
+    pred = md.ns(self._metadata_ns).ns('prediction_in_warped_y_space')
+    pred['mean'] = repr(float(res.aux['mean'][0]))
+    pred['stddev'] = repr(float(res.aux['stddev'][0]))
+    pred['stddev_from_all'] = repr(float(res.aux['stddev_from_all'][0]))
+    pred['acquisition'] = f'{float(res.rewards[0])}'
+    pred['use_ucb'] = f'{use_ucb}'
+    pred['trust_radius'] = f'{radius}'
+    pred['params'] = f'{params}'
+    md.ns(self._metadata_ns).ns('timing')['time'] = f'{datetime.datetime.now() - start}'
+    return vz.TrialSuggestion(params_dict, metadata=md)
+
+  # ------------------------------------------------------------------ suggest
+  @profiler.record_runtime
+  def suggest(self, count: Optional[int] = None):
+    """gp_ucb_pe.py:1356-1445."""
+    count = count or 1
+    if len(self._all_completed_trials) + len(self._all_active_trials) < self._num_seed_trials:
+      return self._generate_seed_trials(count)
+    cont, cat, labels = self._trials_to_data(self._all_completed_trials)
+    params = self._build_gp_model_and_optimize_parameters(cont, cat, labels)
+    dev_a, _ = self._devices()
+    if cont.shape[0] > 0:
+      dev_a.fit(cont, labels[:, 0], params, z=cat if cat.shape[1] else None)
+    else:
+      raise NotImplementedError('suggest() with only ACTIVE trials and no completed trial is not implemented '
+                                '(the reference falls back to a prior-only GP).')
+    act_c, _ = self._converter.to_features(self._all_active_trials)
+    n_tr = cont.shape[0] + act_c.shape[0]   # trust region: completed + initially active trials (:1377-1403)
+    mask = acq_lib.trust_region_dim_mask(self._converter.continuous_feasible_values(_MAX_NUM_FEASIBLE_VALUES_FOR_TRUST_REGION))
+    radius = acq_lib.trust_radius(n_tr, int(mask.sum()), self._converter.n_categorical)
+    active = list(self._all_active_trials)
+    out = []
+    for _ in range(count):
+      s = self._suggest_one(active, cont, cat, labels, params, mask, radius, n_tr)
+      out.append(s)
+      active.append(s.to_trial())
+    return out

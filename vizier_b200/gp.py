@@ -86,12 +86,16 @@ class Acquisition:
   use_trust_region: bool = True
   trust_radius: float = 1.0
   tr_dim_mask: Optional[np.ndarray] = None  # bool [Dc]
+  tr_rows: int = 0          # trusted points = first tr_rows rows of the model's X (0 = all)
+  tr_strict: bool = False   # dist < radius (gp_ucb_pe.py) instead of dist <= radius (acquisitions.py)
 
   def _c(self):
     a = _lib.Acq()
     a.ucb_coefficient = float(self.ucb_coefficient)
     a.use_trust_region = 1 if self.use_trust_region else 0
     a.trust_radius = float(self.trust_radius)
+    a.tr_rows = int(self.tr_rows)
+    a.tr_strict = 1 if self.tr_strict else 0
     keep = None
     if self.tr_dim_mask is not None:
       keep = np.ascontiguousarray(np.asarray(self.tr_dim_mask).astype(np.uint8))
@@ -101,6 +105,39 @@ class Acquisition:
     return a, keep
 
 
+@dataclasses.dataclass
+class UcbPeAcquisition:
+  """GP-UCB-PE acquisition parameters (gp_ucb_pe.py:282-492); see vzgp_pe_params in include/vzgp.h."""
+
+  mode: int = 0                      # 0 = UCB (mean_A + c * stddev_B), 1 = PE
+  ucb_coefficient: float = 1.8
+  explore_coefficient: float = 0.5
+  penalty_coefficient: float = 10.0
+  threshold: float = 0.0
+  use_trust_region: bool = True
+  trust_radius: float = 1.0
+  tr_dim_mask: Optional[np.ndarray] = None
+  tr_rows: int = 0
+
+  def _c(self):
+    p = _lib.PeParams()
+    p.mode = int(self.mode)
+    p.ucb_coefficient = float(self.ucb_coefficient)
+    p.explore_coefficient = float(self.explore_coefficient)
+    p.penalty_coefficient = float(self.penalty_coefficient)
+    p.threshold = float(self.threshold)
+    p.use_trust_region = 1 if self.use_trust_region else 0
+    p.trust_radius = float(self.trust_radius)
+    p.tr_rows = int(self.tr_rows)
+    keep = None
+    if self.tr_dim_mask is not None:
+      keep = np.ascontiguousarray(np.asarray(self.tr_dim_mask).astype(np.uint8))
+      p.tr_dim_mask = keep.ctypes.data_as(C.POINTER(C.c_uint8))
+    else:
+      p.tr_dim_mask = None
+    return p, keep
+
+
 def _ptr(t: Optional[torch.Tensor]):
   return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -108,7 +145,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class DeviceGP:
   """One libvzgp handle = one study's GP on one GPU."""
 
-  def __init__(self, device: int = 0):
+  def __init__(self, device: int = 0, stream: Optional[torch.cuda.Stream] = None):
     self._lib = _lib.load()
     if not torch.cuda.is_available():
       raise RuntimeError('vizier_b200 needs a CUDA device; there is no CPU fallback.')
@@ -116,7 +153,7 @@ class DeviceGP:
     torch.cuda.init()
     with torch.cuda.device(self.device):
       torch.zeros(1, device=self.device)  # make sure the primary context exists
-    self._stream = torch.cuda.Stream(device=self.device)
+    self._stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
     h = C.c_void_p()
     _lib.check('vzgp_create', self._lib.vzgp_create(device, C.c_void_p(self._stream.cuda_stream), C.byref(h)))
     self._h = h
@@ -358,9 +395,28 @@ class DeviceGP:
     del keep
     return bx, bz, bs, bi
 
-  def eagle_run(self, cfg: '_lib.EagleConfig', acq: Acquisition, count: int, seed: int,
-                prior: Optional[Sequence] = None, prior_z: Optional[Sequence] = None, cat_sizes=None):
-    """Returns (best_x [count,Dc], best_z [count,Dk], best_score [count])."""
+  def score_pe(self, other: 'DeviceGP', xs, pe: UcbPeAcquisition, zs=None) -> dict:
+    """GP-UCB-PE score with self = model on completed trials, other = model on completed+pending.
+    Returns device tensors {'score','mean','stddev','stddev_from_all'}; synchronous."""
+    xst, zst = self._xz(xs, zs)
+    m = xst.shape[0]
+    res = {k: torch.empty((m,), dtype=torch.float64, device=self.device) for k in ('score', 'mean', 'stddev', 'stddev_from_all')}
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    p, keep = pe._c()
+    _lib.check('vzgp_score_pe', self._lib.vzgp_score_pe(
+        self._h, other._h, _ptr(xst), _ptr(zst), m, C.byref(p), _ptr(res['score']), _ptr(res['mean']),
+        _ptr(res['stddev']), _ptr(res['stddev_from_all'])))
+    self.synchronize()
+    del keep
+    return res
+
+  def eagle_run(self, cfg: '_lib.EagleConfig', acq, count: int, seed: int,
+                prior: Optional[Sequence] = None, prior_z: Optional[Sequence] = None, cat_sizes=None,
+                other: Optional['DeviceGP'] = None):
+    """Returns (best_x [count,Dc], best_z [count,Dk], best_score [count]).  With `other` and a
+    UcbPeAcquisition the GP-UCB-PE acquisition is optimised (vzgp_eagle_run_pe)."""
+    if isinstance(acq, UcbPeAcquisition):
+      return self._eagle_run_pe(cfg, acq, count, seed, prior, prior_z, cat_sizes, other)
     a, keep = acq._c()
     n_prior = 0 if prior is None else len(prior)
     pt = self._dev(prior, torch.float64) if n_prior > 0 and self.dc > 0 else None
@@ -371,6 +427,23 @@ class DeviceGP:
     sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
     _lib.check('vzgp_eagle_run', self._lib.vzgp_eagle_run(
         self._h, C.byref(cfg), C.byref(a), _ptr(pt), _ptr(pz), n_prior,
+        sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes.size else None, count, seed,
+        bx.ctypes.data_as(C.POINTER(C.c_double)), bz.ctypes.data_as(C.POINTER(C.c_int32)),
+        bs.ctypes.data_as(C.POINTER(C.c_double))))
+    del keep
+    return bx, bz, bs
+
+  def _eagle_run_pe(self, cfg, pe: UcbPeAcquisition, count, seed, prior, prior_z, cat_sizes, other):
+    p, keep = pe._c()
+    n_prior = 0 if prior is None else len(prior)
+    pt = self._dev(prior, torch.float64) if n_prior > 0 and self.dc > 0 else None
+    pz = self._dev(prior_z, torch.int32) if n_prior > 0 and self.dk > 0 else None
+    bx = np.zeros((count, self.dc), np.float64)
+    bz = np.zeros((count, self.dk), np.int32)
+    bs = np.zeros(count, np.float64)
+    sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
+    _lib.check('vzgp_eagle_run_pe', self._lib.vzgp_eagle_run_pe(
+        self._h, other._h, C.byref(cfg), C.byref(p), _ptr(pt), _ptr(pz), n_prior,
         sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes.size else None, count, seed,
         bx.ctypes.data_as(C.POINTER(C.c_double)), bz.ctypes.data_as(C.POINTER(C.c_int32)),
         bs.ctypes.data_as(C.POINTER(C.c_double))))

@@ -37,6 +37,7 @@ class EagleStrategyConfig:
   max_pool_size: int = 100
   normalization_scale: float = 0.5
   prior_trials_pool_pct: float = 0.96
+  mutate_normalization_type: int = 0   # 0 = MEAN (default), 1 = RANDOM (MutateNormalizationType)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -82,11 +83,15 @@ class VectorizedOptimizer:
   max_evaluations: int = 75_000
   categorical_sizes: tuple = ()
 
-  def __call__(self, dev: gp.DeviceGP, acq: gp.Acquisition, *, count: int = 1,
+  def __call__(self, dev: gp.DeviceGP, acq, *, count: int = 1,
                prior_features: Optional[np.ndarray] = None, prior_categorical: Optional[np.ndarray] = None,
-               seed: int = 0) -> VectorizedStrategyResults:
+               seed: int = 0, other: Optional[gp.DeviceGP] = None) -> VectorizedStrategyResults:
+    """acq: gp.Acquisition (UCB + trust region on `dev`) or gp.UcbPeAcquisition (needs `other`)."""
     sizes = list(self.categorical_sizes)
+    is_pe = isinstance(acq, gp.UcbPeAcquisition)
     if isinstance(self.strategy_factory, _RandomStrategyFactory):
+      if is_pe:
+        raise NotImplementedError('random strategy with the GP-UCB-PE acquisition')
       # one uniform batch per step; the device scores all max_evaluations candidates in one pass
       n = (self.max_evaluations - 1) // self.suggestion_batch_size + 1
       m = n * self.suggestion_batch_size
@@ -99,8 +104,13 @@ class VectorizedOptimizer:
                              c.perturbation_lower_bound, c.penalize_factor, c.normalization_scale,
                              c.prior_trials_pool_pct, pool, self.suggestion_batch_size, self.max_evaluations,
                              c.categorical_perturbation_factor, c.pure_categorical_perturbation_factor,
-                             c.prob_same_category_without_perturbation)
-      bx, bz, bs = dev.eagle_run(cfg, acq, count, seed, prior=prior_features, prior_z=prior_categorical, cat_sizes=sizes)
+                             c.prob_same_category_without_perturbation, c.mutate_normalization_type)
+      bx, bz, bs = dev.eagle_run(cfg, acq, count, seed, prior=prior_features, prior_z=prior_categorical,
+                                 cat_sizes=sizes, other=other)
+    if is_pe:
+      out = dev.score_pe(other, bx, acq, zs=bz if self.n_categorical else None)
+      aux = {k: out[k].cpu().numpy() for k in ('mean', 'stddev', 'stddev_from_all')}
+      return VectorizedStrategyResults(bx, bs, aux, categorical=bz)
     # score_with_aux on the winners (vectorized_base.py:504-526)
     out = dev.score(bx, acq, zs=bz if self.n_categorical else None, with_aux=True)
     dev.synchronize()
