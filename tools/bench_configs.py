@@ -39,6 +39,15 @@ out['C1_suggest_s_first_call'] = t1 - t0
 out['C1_suggest_s'] = t3 - t2
 out['C1_breakdown_s'] = {k: sum(v) for k, v in ev.items()}
 
+# ---- GP-UCB-PE (service DEFAULT): batch of 4 suggestions, same 4-D / 50-trial study, default settings
+from vizier_b200.designers import gp_ucb_pe
+d3 = gp_ucb_pe.VizierGPUCBPEBandit.from_problem(p, seed=2)
+d3.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+d3.suggest(1)
+d3.update(vz.CompletedTrials([]), vz.ActiveTrials())
+t2 = time.perf_counter(); d3.suggest(4); t3 = time.perf_counter()
+out['UCBPE_suggest4_N50_D4_s'] = t3 - t2
+
 # ---- fit latency and C3: eagle 1000 fireflies x 200 iterations against the C2 posterior
 import bench
 x, y, th = bench.make_problem()
