@@ -113,109 +113,257 @@ __global__ void k_copy_lower_shift(const double* __restrict__ A, int lda, int n_
 // Inverse of the lower-triangular 64x64 matrix a (shared memory, row stride 66) into x (same
 // layout): column c is owned by 4 adjacent lanes (k-split), combined with two shuffles, so the 64
 // dependent row steps need no block-wide barrier.  256 threads.
-__device__ __forceinline__ void tri_inverse_64(const double* a, double* x) {
+__device__ __forceinline__ void tri_inverse_64(const double* a, double* x, double* rdiag) {
   const int tid = threadIdx.x, c = tid >> 2, q = tid & 3;
+  if (tid < 64) rdiag[tid] = 1.0 / a[tid * 66 + tid];
+  __syncthreads();
   for (int i = 0; i < 64; ++i) {
     double s = 0.0;
     for (int k = c + q; k < i; k += 4) s = fma(a[i * 66 + k], x[k * 66 + c], s);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (q == 0) x[i * 66 + c] = (c <= i) ? ((i == c ? 1.0 : 0.0) - s) / a[i * 66 + i] : 0.0;
+    if (q == 0) x[i * 66 + c] = (c <= i) ? ((i == c ? 1.0 : 0.0) - s) * rdiag[i] : 0.0;
     __syncwarp();
   }
+}
+
+#ifdef VZ_POTF2_TIMING
+__device__ long long g_potf2_t[32];
+#define VZ_TSTAMP(i) do { if (threadIdx.x == 0) g_potf2_t[i] = clock64(); } while (0)
+#else
+#define VZ_TSTAMP(i) do {} while (0)
+#endif
+
+// Correctly rounded quotient c / d from r ~= 1/d without branches: q = c*r; q += (c - q*d)*r.
+__device__ __forceinline__ double div_refined(double c, double d, double r) {
+  const double q = c * r;
+  return fma(fma(-q, d, c), r, q);
 }
 
 // Factor the 64x64 diagonal block kb in place (lower), zero its upper triangle, and write
 // its inverse into the same block of Linv.  flag[0] is set to 1 if a pivot is not a
 // positive finite number (the factor then holds NaN, like jnp.linalg.cholesky).
-// The block lives in registers (thread (ti,tj) owns a 4x4 sub-block); each of the 64 column
-// steps broadcasts the raw pivot column through shared memory and costs one barrier:
-//   a[i][k] -= a[i][j]*a[k][j]/a[j][j]   (k > j),   l[i][j] = a[i][j]/sqrt(a[j][j]).
+//
+// This kernel is a pure latency chain (64 dependent pivots), so it is organised around the
+// critical path rather than throughput:
+//  * four 16-column macro steps; the 16x16 diagonal piece is factored by ONE warp entirely in
+//    registers (lane = row) in the square-root-free LDL^T form: the only long-latency operation on
+//    the pivot-to-pivot chain is one reciprocal, and the column broadcasts (shuffles of the
+//    UNSCALED column) overlap it.  The 16 columns are scaled by 1/sqrt(d_j) once, in parallel,
+//    after the loop.
+//  * the rows below are solved one thread per row (right-looking, 2 dependent ops per column),
+//    the trailing part is updated by the whole CTA with 16-wide register tiles.
+//  * the inverse: the four 16x16 diagonal blocks (one warp each, lane = column) and two
+//    recursive-doubling levels  X21 = -B^-1 (C A^-1)  with fully unrolled dot products.
 __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ L, int ld, int kb,
                                                    double* __restrict__ Linv, int ldi,
                                                    int* __restrict__ flag) {
   extern __shared__ double smem[];
-  double* a = smem;             // [64][66]
-  double* x = smem + 64 * 66;   // [64][66]
-  __shared__ double col[2][64];
+  constexpr int LD = 66;
+  double* a = smem;              // [64][66]
+  double* x = smem + 64 * LD;    // [64][66]
+  double* t = x + 64 * LD;       // [32][34] temporary of the doubling steps
+  __shared__ double rd[64];      // 1 / diagonal of the factor
+  __shared__ int s_bad;
   double* blk = L + (size_t)kb * 64 * ld + kb * 64;
-  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
-  double r[4][4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_bad = 0;
+  VZ_TSTAMP(0);
+  {
+    double2 v[8];
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const double2 v0 = *reinterpret_cast<const double2*>(blk + (size_t)(4 * ti + p) * ld + 4 * tj);
-    const double2 v1 = *reinterpret_cast<const double2*>(blk + (size_t)(4 * ti + p) * ld + 4 * tj + 2);
-    r[p][0] = v0.x; r[p][1] = v0.y; r[p][2] = v1.x; r[p][3] = v1.y;
+    for (int u = 0; u < 8; ++u) {
+      const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
+      v[u] = *reinterpret_cast<const double2*>(blk + (size_t)i * ld + j2);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
+      const bool upper_blk = (j2 >> 4) > (i >> 4);     // 16-blocks strictly above the diagonal
+      *reinterpret_cast<double2*>(a + i * LD + j2) = upper_blk ? make_double2(0.0, 0.0) : v[u];
+      *reinterpret_cast<double2*>(x + i * LD + j2) = make_double2(0.0, 0.0);
+    }
   }
-  bool bad = false;
-  double* lc = x;  // [64] scaled pivot column (x is free until the inverse starts)
-  for (int j = 0; j < 64; ++j) {
-    const int jb = j >> 2, jq = j & 3;
-    double* cb = col[j & 1];
-    if (tj == jb) {
+  __syncthreads();
+  VZ_TSTAMP(1);
+#pragma unroll 1
+  for (int mb = 0; mb < 4; ++mb) {
+    const int c0 = 16 * mb;
+    if (warp == 0) {
+      // ---- 16x16 LDL^T in registers: lane l < 16 owns row c0 + l ----
+      double v[16];
+      const int row = c0 + (lane & 15);
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        double v = r[p][0];
-        if (jq == 1) v = r[p][1];
-        if (jq == 2) v = r[p][2];
-        if (jq == 3) v = r[p][3];
-        cb[4 * ti + p] = v;
+      for (int k = 0; k < 16; k += 2) {
+        const double2 p = *reinterpret_cast<const double2*>(a + row * LD + c0 + k);
+        v[k] = p.x; v[k + 1] = p.y;
       }
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const double d = __shfl_sync(0xffffffffu, v[j], j);
+        if (!(d > 0.0) || !isfinite(d)) bad = true;
+        const double r = 1.0 / d;
+        const double wr = v[j] * r;
+#pragma unroll
+        for (int k = j + 1; k < 16; ++k) {
+          const double wk = __shfl_sync(0xffffffffu, v[j], k);
+          v[k] = fma(-wr, wk, v[k]);
+        }
+      }
+      // lane j: d_j = v[j];  column scale 1/sqrt(d_j)
+      double dj = 0.0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dj = (lane == j) ? v[j] : dj;
+      const double rs = bad ? nan("") : 1.0 / sqrt(dj);
+      if (lane < 16) rd[c0 + lane] = rs;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const double rj = __shfl_sync(0xffffffffu, rs, j);
+        v[j] = (j <= lane) ? v[j] * rj : 0.0;
+      }
+      if (lane < 16) {
+#pragma unroll
+        for (int k = 0; k < 16; k += 2)
+          *reinterpret_cast<double2*>(a + row * LD + c0 + k) = make_double2(v[k], v[k + 1]);
+      }
+      if (bad && lane == 0) s_bad = 1;
     }
     __syncthreads();
-    const double djj = cb[j];
-    if (!(djj > 0.0) || !isfinite(djj)) bad = true;
-    // LAPACK-style arithmetic: l = a / sqrt(d), then a -= l_i * l_k (keeps retry decisions on
-    // exactly singular inputs identical to a host potrf).
-    if (tj == jb) {
-      const double sd = bad ? nan("") : sqrt(djj);
+    VZ_TSTAMP(2 + 3 * mb);
+    const int rem = 48 - c0;                 // rows below this macro block
+    if (tid < rem) {
+      // ---- panel: row r solves x * L11^T = a[r, c0:c0+16], right-looking ----
+      const int r = c0 + 16 + tid;
+      double xr[16];
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int i = 4 * ti + p;
-        const double v = (i == j) ? sd : cb[i] / sd;
-        lc[(j & 1) * 64 + i] = v;
-        if (i >= j) {
-          if (jq == 0) r[p][0] = v;
-          if (jq == 1) r[p][1] = v;
-          if (jq == 2) r[p][2] = v;
-          if (jq == 3) r[p][3] = v;
+      for (int k = 0; k < 16; k += 2) {
+        const double2 p = *reinterpret_cast<const double2*>(a + r * LD + c0 + k);
+        xr[k] = p.x; xr[k + 1] = p.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        xr[j] *= rd[c0 + j];
+#pragma unroll
+        for (int k = j + 1; k < 16; ++k) xr[k] = fma(-xr[j], a[(c0 + k) * LD + c0 + j], xr[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k += 2)
+        *reinterpret_cast<double2*>(a + r * LD + c0 + k) = make_double2(xr[k], xr[k + 1]);
+    }
+    __syncthreads();
+    VZ_TSTAMP(3 + 3 * mb);
+    // ---- trailing update: a[i][k] -= sum_j a[i][c0+j] * a[k][c0+j],  c0+16 <= k <= i ----
+    // thread (ti, tk) owns the entries (ti + 16 p, tk + 16 q) of every 16x16 block (p, q), q <= p
+    {
+      const int ti = tid & 15, tk = tid >> 4;
+      const int nb = rem >> 4;
+      for (int p = 0; p < nb; ++p) {
+        const int i = c0 + 16 + 16 * p + ti;
+        double ai[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const double2 q2 = *reinterpret_cast<const double2*>(a + i * LD + c0 + j);
+          ai[j] = q2.x; ai[j + 1] = q2.y;
+        }
+        for (int q = 0; q <= p; ++q) {
+          const int k = c0 + 16 + 16 * q + tk;
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const double2 q2 = *reinterpret_cast<const double2*>(a + k * LD + c0 + j);
+            s0 = fma(ai[j], q2.x, s0);
+            s1 = fma(ai[j + 1], q2.y, s1);
+          }
+          if (k <= i) a[i * LD + k] -= s0 + s1;
         }
       }
     }
     __syncthreads();
-    if (ti >= tj) {
-      const double* lj = lc + (j & 1) * 64;
-      double li[4], lk[4];
+    VZ_TSTAMP(4 + 3 * mb);
+  }
+  VZ_TSTAMP(14);
+  // ---- inverse, step A: the four 16x16 diagonal blocks, one warp each, lane = column ----
+  if (warp < 4 && lane < 16) {
+    const int b0 = 16 * warp, c = lane;
+    double xc[16];
 #pragma unroll
-      for (int p = 0; p < 4; ++p) { li[p] = lj[4 * ti + p]; lk[p] = lj[4 * tj + p]; }
+    for (int i = 0; i < 16; ++i) xc[i] = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-      for (int p = 0; p < 4; ++p)
+    for (int i = 0; i < 16; ++i) {
+      xc[i] *= rd[b0 + i];
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const int i = 4 * ti + p, k = 4 * tj + qq;
-          if (k > j && i >= k) r[p][qq] = fma(-li[p], lk[qq], r[p][qq]);
-        }
+      for (int k = i + 1; k < 16; ++k) xc[k] = fma(-a[(b0 + k) * LD + b0 + i], xc[i], xc[k]);
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[(b0 + i) * LD + b0 + c] = xc[i];
   }
   __syncthreads();
+  VZ_TSTAMP(15);
+  // ---- step B: 16-level doubling, two pairs; thread = one (row, col) of each pair ----
+  {
+    const int rr = tid >> 4, cc = tid & 15;
+    double acc[2];
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+    for (int pr = 0; pr < 2; ++pr) {
+      const int p0 = 32 * pr;
+      double s0 = 0.0;
 #pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {
-      const int i = 4 * ti + p, k = 4 * tj + qq;
-      a[i * 66 + k] = (k <= i) ? r[p][qq] : 0.0;
+      for (int k = 0; k < 16; ++k) s0 = fma(a[(p0 + 16 + rr) * LD + p0 + k], x[(p0 + k) * LD + p0 + cc], s0);
+      acc[pr] = s0;
     }
+    t[rr * 34 + cc] = acc[0];
+    t[(16 + rr) * 34 + cc] = acc[1];
+    __syncthreads();
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+      const int p0 = 32 * pr;
+      double s0 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s0 = fma(x[(p0 + 16 + rr) * LD + p0 + 16 + k], t[(16 * pr + k) * 34 + cc], s0);
+      acc[pr] = s0;
+    }
+    x[(16 + rr) * LD + cc] = -acc[0];
+    x[(48 + rr) * LD + 32 + cc] = -acc[1];
+  }
   __syncthreads();
-  tri_inverse_64(a, x);
+  VZ_TSTAMP(16);
+  // ---- step C: 32-level doubling; thread = a 2x2 patch of the 32x32 block ----
+  {
+    const int r0 = (tid >> 4) * 2, q0 = (tid & 15) * 2;
+    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const double a0 = a[(32 + r0) * LD + k], a1 = a[(33 + r0) * LD + k];
+      const double2 xv = *reinterpret_cast<const double2*>(x + k * LD + q0);
+      s00 = fma(a0, xv.x, s00); s01 = fma(a0, xv.y, s01);
+      s10 = fma(a1, xv.x, s10); s11 = fma(a1, xv.y, s11);
+    }
+    *reinterpret_cast<double2*>(t + r0 * 34 + q0) = make_double2(s00, s01);
+    *reinterpret_cast<double2*>(t + (r0 + 1) * 34 + q0) = make_double2(s10, s11);
+    __syncthreads();
+    s00 = s01 = s10 = s11 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const double b0v = x[(32 + r0) * LD + 32 + k], b1v = x[(33 + r0) * LD + 32 + k];
+      const double2 tv = *reinterpret_cast<const double2*>(t + k * 34 + q0);
+      s00 = fma(b0v, tv.x, s00); s01 = fma(b0v, tv.y, s01);
+      s10 = fma(b1v, tv.x, s10); s11 = fma(b1v, tv.y, s11);
+    }
+    *reinterpret_cast<double2*>(x + (32 + r0) * LD + q0) = make_double2(-s00, -s01);
+    *reinterpret_cast<double2*>(x + (33 + r0) * LD + q0) = make_double2(-s10, -s11);
+  }
   __syncthreads();
+  VZ_TSTAMP(17);
   double* iblk = Linv + (size_t)kb * 64 * ldi + kb * 64;
-  for (int e = tid; e < 64 * 32; e += 256) {
-    const int i = e >> 5, j2 = (e & 31) * 2;
-    *reinterpret_cast<double2*>(blk + (size_t)i * ld + j2) = make_double2(a[i * 66 + j2], a[i * 66 + j2 + 1]);
-    *reinterpret_cast<double2*>(iblk + (size_t)i * ldi + j2) =
-        make_double2(j2 <= i ? x[i * 66 + j2] : 0.0, j2 + 1 <= i ? x[i * 66 + j2 + 1] : 0.0);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
+    *reinterpret_cast<double2*>(blk + (size_t)i * ld + j2) = *reinterpret_cast<const double2*>(a + i * LD + j2);
+    *reinterpret_cast<double2*>(iblk + (size_t)i * ldi + j2) = *reinterpret_cast<const double2*>(x + i * LD + j2);
   }
-  if (bad && tid == 0) flag[0] = 1;
+  if (tid == 0 && s_bad) flag[0] = 1;
+  VZ_TSTAMP(18);
 }
 
 // Panel solve as a GEMM with the inverted diagonal block:
@@ -489,7 +637,7 @@ int launch_cross_kernel(vzgp_handle* h, const double* Xs, const int32_t* Zs, int
 
 // Factor `L` in place (already holds the shifted lower triangle, np % 64 == 0) and fill the
 // diagonal blocks of Linv.  flag (device int) is raised on a bad pivot.
-constexpr size_t kDiagSmem = sizeof(double) * (2 * 64 * 66);
+constexpr size_t kDiagSmem = sizeof(double) * (2 * 64 * 66 + 32 * 34);
 
 int potrf_blocked(vzgp_handle* h, double* L, int ld, double* Linv, int ldi, int np, int* flag) {
   const int nb = np / 64;
@@ -554,7 +702,8 @@ __global__ void __launch_bounds__(256) k_diag_inv(const double* __restrict__ L, 
   const double* blk = L + (size_t)kb * 64 * ld + kb * 64;
   for (int e = tid; e < 64 * 64; e += 256) a[(e >> 6) * 66 + (e & 63)] = blk[(size_t)(e >> 6) * ld + (e & 63)];
   __syncthreads();
-  tri_inverse_64(a, x);
+  __shared__ double rdiag[64];
+  tri_inverse_64(a, x, rdiag);
   __syncthreads();
   double* iblk = Linv + (size_t)kb * 64 * ldi + kb * 64;
   for (int e = tid; e < 64 * 64; e += 256) {
