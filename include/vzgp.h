@@ -184,6 +184,21 @@ int vzgp_topk(vzgp_handle* h, const double* score, int64_t M, int count, int64_t
 int vzgp_score_topk(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                     int count, double* score_dev, double* best_x, double* best_score, int64_t* best_index);
 
+/* Candidate-pool shards over several GPUs (the reference is single-process, its
+ * counterpart is the arg-partition over ONE pool, vectorized_base.py:575-587).
+ * vzgp_score_topk_pack: score this rank's shard, select its top `count` and write them to the DEVICE
+ * buffer payload_dev[count][Dc+2] as rows [score, index_base + local index, features] (fp64; indices
+ * below 2^53 are exact).  Missing winners (M < count) are [-inf, -1, 0...].  No host synchronisation:
+ * the caller all-gathers the payloads (NCCL, on the handle's stream) and calls
+ * vzgp_merge_topk: rows_dev[n_rows][width] -> out_dev[count][width]: larger score first, NaN as -inf,
+ * ties -> lower global index (every rank computes the identical result).  If host_out != NULL the
+ * merged rows are also copied there asynchronously on the handle's stream (pinned memory; valid
+ * after vzgp_synchronize or an event). */
+int vzgp_score_topk_pack(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                         int count, int64_t index_base, double* score_dev, double* payload_dev);
+int vzgp_merge_topk(vzgp_handle* h, const double* rows_dev, int n_rows, int width, int count,
+                    double* out_dev, double* host_out);
+
 /* ---- acquisition optimisers (device-resident loops) ---------------------- */
 
 /* EagleStrategyConfig (eagle_strategy.py:111-167), continuous features. */

@@ -340,6 +340,55 @@ def test_score_topk_fused_call(dev):
   np.testing.assert_allclose(buf.cpu().numpy(), want, atol=TOL)
 
 
+def test_score_topk_pack_and_device_merge(dev):
+  """The asynchronous shard step (pack rows [score, global index, x]) and the device merge agree with
+  the oracle's top-k and with the host merge used by the gloo test (multi_gpu.merge_topk)."""
+  from vizier_b200 import multi_gpu
+  n, d, m, count = 120, 6, 3000, 4
+  x, y, _ = _problem(n, d, 31)
+  xs, _, _ = _problem(m, d, 32)
+  po, pg = _params(d)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  acq = _gp().Acquisition(1.8, True, go.trust_radius(n, d, 0))
+  xt = torch.from_numpy(xs).cuda()
+  payload = torch.empty((count, d + 2), dtype=torch.float64, device='cuda')
+  base = 7_000_000_000   # > 2^32: global indices of a large sharded pool
+  dev.score_topk_pack(xt, acq, count, base, payload)
+  dev.synchronize()
+  want, _ = go.score_with_aux(pred, xs)
+  order = go.top_k(want, count)
+  p = payload.cpu().numpy()
+  np.testing.assert_array_equal(p[:, 1].astype(np.int64), order + base)
+  np.testing.assert_array_equal(p[:, 2:], xs[order])
+  np.testing.assert_allclose(p[:, 0], want[order], atol=TOL)
+  # merge of "gathered" rows from 3 pretend ranks, with ties, NaN and missing (-1) winners
+  rng = np.random.default_rng(5)
+  rows = np.zeros((3 * count, d + 2))
+  rows[:, 0] = rng.normal(size=3 * count)
+  rows[:, 1] = rng.permutation(3 * count) + 100
+  rows[:, 2:] = rng.uniform(size=(3 * count, d))
+  rows[5, 0] = rows[2, 0]                 # tie -> lower global index wins
+  rows[7, 0] = np.nan                     # NaN ranks as -inf
+  rows[9, :2] = [-np.inf, -1.0]           # rank with fewer than `count` candidates
+  rt = torch.from_numpy(rows).cuda()
+  out = torch.empty((count, d + 2), dtype=torch.float64, device='cuda')
+  host = torch.empty((count, d + 2), dtype=torch.float64).pin_memory()
+  dev.merge_topk(rt, count, out, host)
+  dev.synchronize()
+  valid = rows[:, 1] >= 0
+  wi, wv, wx = multi_gpu.merge_topk(rows[valid, 1].astype(np.int64), rows[valid, 0], rows[valid, 2:], count)
+  np.testing.assert_array_equal(host.numpy()[:, 1].astype(np.int64), wi)
+  np.testing.assert_array_equal(host.numpy()[:, 2:], wx)
+  np.testing.assert_array_equal(out.cpu().numpy(), host.numpy())
+  # world-size-1 exchange object (what bench.py drives): pack -> merge -> pinned host
+  ex = multi_gpu.TopkExchange(None, dev, d, count)
+  ex.step(1, xt, acq, index_base=base)
+  gi, gv, gx = ex.result(1)
+  np.testing.assert_array_equal(gi, order + base)
+  np.testing.assert_array_equal(gx, xs[order])
+
+
 @pytest.mark.parametrize('n,d,m', [(1, 1, 1), (2, 3, 63), (64, 2, 65), (65, 7, 129), (127, 64, 40), (129, 33, 200)])
 def test_score_edge_shapes(dev, n, d, m):
   """Ragged sizes around the 64-row tiles / 128-column blocks, D=1 and the D=64 maximum."""

@@ -729,4 +729,38 @@ int vzgp_score_topk(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
   return 0;
 }
 
+int vzgp_score_topk_pack(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                         int count, int64_t index_base, double* score_dev, double* payload_dev) {
+  VZ_ARG(payload_dev != nullptr, "payload");
+  VZ_ARG(M >= 1, "M >= 1");
+  VZ_ARG(index_base >= 0 && index_base + (int64_t)M < (1LL << 53), "global indices must be exact in fp64");
+  Guard g(h ? h->device : 0);
+  const int dc = h ? h->dc : 0;
+  double* dS = score_dev;
+  if (!dS) {
+    VZ_ARG(h != nullptr, "handle");
+    VZ_TRY(h->out_dev.reserve(sizeof(double) * (size_t)M));
+    dS = h->out_dev.as<double>();
+  }
+  VZ_TRY(check_scoring(h, Xs, Zs, M, acq, dS));
+  VZ_ARG(h->dk == 0, "continuous features only");
+  VZ_TRY(launch_score(h, Xs, Zs, M, acq, dS, nullptr, nullptr, nullptr));
+  long long* d_idx; double* d_val;
+  VZ_TRY(topk_to_device(h, dS, M, count, &d_idx, &d_val));
+  return launch_pack_topk(h, Xs, dc, d_idx, d_val, count, M, index_base, payload_dev);
+}
+
+int vzgp_merge_topk(vzgp_handle* h, const double* rows_dev, int n_rows, int width, int count,
+                    double* out_dev, double* host_out) {
+  VZ_ARG(h && rows_dev && out_dev, "handle / pointers");
+  VZ_ARG(n_rows >= 1 && n_rows <= 2048, "1 <= n_rows <= 2048");
+  VZ_ARG(width >= 2, "width >= 2");
+  VZ_ARG(count >= 1 && count <= kMaxTopk, "1 <= count <= 256");
+  Guard g(h->device);
+  VZ_TRY(launch_merge_topk(h, rows_dev, n_rows, width, count, out_dev));
+  if (host_out)
+    VZ_CUDA(cudaMemcpyAsync(host_out, out_dev, sizeof(double) * (size_t)count * width, cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
 }  // extern "C"

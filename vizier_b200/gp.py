@@ -364,6 +364,28 @@ class DeviceGP:
     del keep
     return bx, bs, bi
 
+  def score_topk_pack(self, xs: torch.Tensor, acq: Acquisition, count: int, index_base: int,
+                      payload: torch.Tensor, score_out: Optional[torch.Tensor] = None) -> None:
+    """Asynchronous shard step: score, local top-`count`, rows [score, global index, features] into the
+    device tensor `payload` [count, Dc+2].  No host synchronisation (multi_gpu.TopkExchange)."""
+    a, keep = acq._c()
+    assert payload.is_cuda and payload.dtype == torch.float64 and payload.shape == (count, self.dc + 2)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    _lib.check('vzgp_score_topk_pack', self._lib.vzgp_score_topk_pack(
+        self._h, _ptr(xs), None, xs.shape[0], C.byref(a), count, int(index_base), _ptr(score_out), _ptr(payload)))
+    del keep
+
+  def merge_topk(self, rows: torch.Tensor, count: int, out: torch.Tensor, host_out: Optional[torch.Tensor] = None) -> None:
+    """Device merge of gathered winner rows [n_rows, width] into out [count, width] (+ async copy to the
+    pinned host tensor `host_out`); runs on the handle's stream, no host synchronisation."""
+    assert rows.is_cuda and rows.dtype == torch.float64 and rows.is_contiguous()
+    assert out.shape == (count, rows.shape[1])
+    if host_out is not None:
+      assert not host_out.is_cuda and host_out.is_pinned() and host_out.shape == out.shape
+    _lib.check('vzgp_merge_topk', self._lib.vzgp_merge_topk(
+        self._h, _ptr(rows), rows.shape[0], rows.shape[1], count, _ptr(out),
+        C.c_void_p(host_out.data_ptr()) if host_out is not None else None))
+
   def random_pool(self, m: int, dc: int, seed: int, index_base: int = 0) -> torch.Tensor:
     out = torch.empty((m, dc), dtype=torch.float64, device=self.device)
     self._stream.wait_stream(torch.cuda.current_stream(self.device))

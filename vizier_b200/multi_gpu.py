@@ -22,42 +22,55 @@ def merge_topk(indices: np.ndarray, values: np.ndarray, features: np.ndarray, co
 
 
 class TopkExchange:
-  """Reusable buffers for the per-suggest collective: one pinned host staging array, one device
-  payload, one device gather target.  Per call: 1 H2D (count*(D+2) doubles), 1 NCCL all-gather,
-  1 D2H of world*count*(D+2) doubles."""
+  """The per-suggest collective on device: every rank's packed winners (`DeviceGP.score_topk_pack`
+  rows [score, global index, features]) are all-gathered with NCCL on the GP handle's stream and
+  merged by the same deterministic kernel on every rank (`DeviceGP.merge_topk`); the merged rows
+  land in a pinned host buffer by an asynchronous copy.  Nothing here blocks the host, so
+  consecutive suggest steps queue back to back; `result(slot)` waits for one step's event.
 
-  def __init__(self, dist, device, dim: int, count: int):
+  Two buffer slots let step i+1 be enqueued while step i's result is still being read.
+  """
+
+  def __init__(self, dist, gp_dev, dim: int, count: int, slots: int = 2):
     import torch
-    self.dist, self.count, self.dim = dist, count, dim
-    self.world = dist.get_world_size()
-    self.host = torch.empty((count, dim + 2), dtype=torch.float64).pin_memory()
-    self.payload = torch.empty((count, dim + 2), dtype=torch.float64, device=device)
-    self.gathered = torch.empty((self.world * count, dim + 2), dtype=torch.float64, device=device)
-    self.host_out = torch.empty((self.world * count, dim + 2), dtype=torch.float64).pin_memory()
+    self.dist, self.dev, self.count, self.dim = dist, gp_dev, count, dim
+    self.world = dist.get_world_size() if dist is not None else 1
+    device = gp_dev.device
+    w = dim + 2
+    self.payload = [torch.empty((count, w), dtype=torch.float64, device=device) for _ in range(slots)]
+    self.gathered = [torch.empty((self.world * count, w), dtype=torch.float64, device=device) for _ in range(slots)]
+    self.merged = [torch.empty((count, w), dtype=torch.float64, device=device) for _ in range(slots)]
+    self.host = [torch.empty((count, w), dtype=torch.float64).pin_memory() for _ in range(slots)]
+    self.done = [torch.cuda.Event() for _ in range(slots)]
+    self.slots = slots
 
-  def __call__(self, idx: np.ndarray, val: np.ndarray, x_host: np.ndarray):
-    h = self.host.numpy()
-    h[:, 0] = val
-    h[:, 1] = idx          # global indices < 2^53 are exact in fp64
-    h[:, 2:] = x_host
-    self.payload.copy_(self.host, non_blocking=True)
-    self.dist.all_gather_into_tensor(self.gathered, self.payload)
-    self.host_out.copy_(self.gathered, non_blocking=False)
-    g = self.host_out.numpy()
-    return merge_topk(g[:, 1].astype(np.int64), g[:, 0], g[:, 2:], self.count)
+  def step(self, slot: int, xs, acq, index_base: int, score_out=None) -> None:
+    """Enqueue score -> local top-k -> all-gather -> merge -> D2H for one pool shard (asynchronous)."""
+    import torch
+    dev = self.dev
+    dev.score_topk_pack(xs, acq, self.count, index_base, self.payload[slot], score_out=score_out)
+    if self.world > 1:
+      with torch.cuda.stream(dev.stream):   # NCCL orders itself against the handle's stream
+        self.dist.all_gather_into_tensor(self.gathered[slot], self.payload[slot])
+      rows = self.gathered[slot]
+    else:
+      rows = self.payload[slot]
+    dev.merge_topk(rows, self.count, self.merged[slot], self.host[slot])
+    self.done[slot].record(dev.stream)
+
+  def result(self, slot: int):
+    """(global indices [count] i64, scores [count], features [count, D]) of the step last enqueued in `slot`."""
+    self.done[slot].synchronize()
+    g = self.host[slot].numpy()
+    return g[:, 1].astype(np.int64), g[:, 0].copy(), g[:, 2:].copy()
 
 
 def global_topk(dist, idx: np.ndarray, val: np.ndarray, x, count: int):
-  """All-gathers each rank's local top-`count` (global indices, scores, feature rows) and merges.
-
-  idx/val: host arrays [count]; x: torch tensor [count, D] (device or host).  Returns host arrays.
-  """
+  """Host-side variant (CPU tensors / gloo): all-gathers each rank's local top-`count` (global indices,
+  scores, feature rows) and merges with `merge_topk`.  Returns host arrays."""
   import torch
-  dev = x.device if x.is_cuda else torch.device('cpu')
-  ex = TopkExchange(dist, dev, x.shape[1], count) if x.is_cuda else None
-  if ex is not None:
-    return ex(np.asarray(idx), np.asarray(val), x.cpu().numpy())
   world = dist.get_world_size()
+  x = x.cpu() if hasattr(x, 'cpu') else torch.as_tensor(x)
   d = x.shape[1]
   payload = torch.empty((count, d + 2), dtype=torch.float64)
   payload[:, 0] = torch.from_numpy(np.asarray(val, np.float64))
