@@ -408,6 +408,44 @@ def test_score_edge_shapes(dev, n, d, m):
   np.testing.assert_allclose(out2['score'].cpu().numpy(), want, atol=TOL, rtol=0)
 
 
+@pytest.mark.parametrize('n,d,m,radius', [(1000, 20, 25, None), (1000, 20, 512, 0.25), (960, 8, 64, 0.1),
+                                          (1500, 12, 130, None)])
+def test_score_small_pool_path(dev, n, d, m, radius):
+  """Acquisition-optimiser batch sizes (<= 8 tiles) take the trial-axis kernels (k_cross_small /
+  k_var_small / k_small_finalize): same oracle, with and without an ACTIVE trust region, and the
+  same bits run to run (fixed-order reductions)."""
+  x, y, _ = _problem(n, d, 61)
+  xs, _, _ = _problem(m, d, 62)
+  rng = np.random.default_rng(63)
+  near = np.arange(0, m, 2)   # every other candidate sits next to a trial (inside a small trust radius)
+  xs[near] = np.clip(x[rng.integers(0, n, near.size)] + rng.uniform(-0.05, 0.05, (near.size, d)), 0.0, 1.0)
+  po, pg = _params(d)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  r = go.trust_radius(n, d, 0) if radius is None else radius
+  acq = _gp().Acquisition(1.8, True, r)
+  mu, sd = go.predict(pred, xs)
+  dist = go.min_linf_distance(xs, pred.x, np.ones(d, bool), pred.row_valid)
+  want = go.apply_trust_region(go.ucb(mu, sd, 1.8), dist, r)
+  aux = {'mean': mu, 'stddev': sd, 'linf_distance': dist}
+  out = dev.score(xs, acq, with_aux=True)
+  dev.synchronize()
+  got = {k: out[k].cpu().numpy().copy() for k in ('score', 'mean', 'stddev', 'linf_distance')}
+  np.testing.assert_allclose(got['score'], want, atol=TOL, rtol=0)
+  np.testing.assert_allclose(got['mean'], aux['mean'], atol=TOL, rtol=0)
+  np.testing.assert_allclose(got['stddev'], aux['stddev'], atol=TOL, rtol=0)
+  np.testing.assert_allclose(got['linf_distance'], aux['linf_distance'], atol=1e-15, rtol=0)
+  if radius is not None:
+    assert (want < -1e3).any() and (want > -1e3).any()   # both sides of the trust region are exercised
+  out2 = dev.score(xs, acq, with_aux=True)
+  dev.synchronize()
+  for k in got:
+    np.testing.assert_array_equal(out2[k].cpu().numpy(), got[k])
+  out3 = dev.score(xs, acq)
+  dev.synchronize()
+  np.testing.assert_allclose(out3['score'].cpu().numpy(), want, atol=TOL, rtol=0)
+
+
 def test_c5_shape_sample_parity(dev):
   """BASELINE C5 per-GPU shape (N=2000, D=50): 20k candidates, 256-sample parity + fit residual."""
   n, d, m = 2000, 50, 20_000
