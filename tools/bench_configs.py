@@ -71,10 +71,22 @@ xt = torch.from_numpy(x4).cuda(); yt = torch.from_numpy(y4).cuda()
 p4 = gp.GPHyperParams(1.0, np.full(dd, 2.0), 1e-2)
 out['C4_nll_grad_N2000_D50_ms'] = 1e3 * sync_time(lambda: dev.loss_and_grad(xt, yt, p4))
 t0 = time.perf_counter()
-best, losses = ard.train_gp(dev, xt, yt, rng=np.random.default_rng(0))
+best, losses = ard.train_gp(dev, xt, yt, rng=np.random.default_rng(0), workers=1)
+out['C4_ard_fit_4x50_sequential_s'] = time.perf_counter() - t0
+ard.train_gp(dev, xt, yt, rng=np.random.default_rng(0))   # creates the worker handles
+t0 = time.perf_counter()
+best4, losses4 = ard.train_gp(dev, xt, yt, rng=np.random.default_rng(0))
 out['C4_ard_fit_4x50_s'] = time.perf_counter() - t0
-out['C4_final_losses'] = [float(v) for v in losses]
+out['C4_final_losses'] = [float(v) for v in losses4]
+out['C4_concurrent_equals_sequential'] = bool(np.array_equal(losses, losses4))
 n, dd = 1000, 20
 xt = torch.from_numpy(x).cuda(); yt = torch.from_numpy(y).cuda()
 out['nll_grad_N1000_D20_ms'] = 1e3 * sync_time(lambda: dev.loss_and_grad(xt, yt, params))
+ard.train_gp(dev, xt, yt, rng=np.random.default_rng(1))
+t0 = time.perf_counter()
+ard.train_gp(dev, xt, yt, rng=np.random.default_rng(1), workers=1)
+out['ard_N1000_D20_4x50_sequential_s'] = time.perf_counter() - t0
+t0 = time.perf_counter()
+ard.train_gp(dev, xt, yt, rng=np.random.default_rng(1))
+out['ard_N1000_D20_4x50_s'] = time.perf_counter() - t0
 print(json.dumps(out, indent=1))

@@ -41,27 +41,82 @@ def log_uniform_init(rng: np.random.Generator, dc: int, dk: int, n: int) -> np.n
 
 @dataclasses.dataclass
 class ScipyLbfgsB:
-  """The reference's default ARD optimiser, driving the CUDA loss."""
+  """The reference's default ARD optimiser, driving the CUDA loss.
+
+  `loss_and_grad` is one callable, or a sequence of equivalent callables (one per libvzgp handle,
+  `loss_functions` below): the restarts are independent, so they then run concurrently, one host
+  thread per handle/stream (ctypes releases the GIL while the device works).  An evaluation at
+  N ~ 1000 is a chain of small latency-bound kernels, so four restarts overlap almost perfectly on
+  one GPU.  Results do not depend on the number of workers.
+  """
 
   options: LbfgsBOptions = LbfgsBOptions()
 
+  def _one(self, fn, t0, bounds):
+    res = sopt.minimize(fn, t0, jac=True, method='L-BFGS-B', bounds=bounds,
+                        options={'maxiter': self.options.maxiter, 'gtol': self.options.tol,
+                                 'maxls': self.options.num_line_search_steps})
+    return res.x, float(res.fun)
+
   def __call__(self, init_thetas: np.ndarray, loss_and_grad, bounds, best_n: int = 1):
-    finals, losses = [], []
-    for t0 in np.atleast_2d(init_thetas):
-      res = sopt.minimize(loss_and_grad, t0, jac=True, method='L-BFGS-B', bounds=bounds,
-                          options={'maxiter': self.options.maxiter, 'gtol': self.options.tol,
-                                   'maxls': self.options.num_line_search_steps})
-      finals.append(res.x)
-      losses.append(float(res.fun))
-    losses = np.asarray(losses)
-    order = np.argsort(losses)[:max(1, best_n)]
+    inits = np.atleast_2d(init_thetas)
+    fns = list(loss_and_grad) if isinstance(loss_and_grad, (list, tuple)) else [loss_and_grad]
+    if len(fns) == 1 or inits.shape[0] == 1:
+      results = [self._one(fns[0], t0, bounds) for t0 in inits]
+    else:
+      import concurrent.futures as cf
+      import queue
+      free = queue.SimpleQueue()
+      for fn in fns:
+        free.put(fn)
+
+      def run(t0):
+        fn = free.get()
+        try:
+          return self._one(fn, t0, bounds)
+        finally:
+          free.put(fn)
+
+      with cf.ThreadPoolExecutor(max_workers=len(fns)) as pool:
+        results = list(pool.map(run, inits))
+    finals = [r[0] for r in results]
+    losses = np.asarray([r[1] for r in results])
+    order = np.argsort(losses, kind='stable')[:max(1, best_n)]
     return [finals[i] for i in order], losses
+
+
+MAX_ARD_WORKERS = 4
+
+
+def loss_functions(dev: gp.DeviceGP, xt, yt, zt, dc: int, dk: int, n_valid: Optional[int] = None,
+                   workers: int = MAX_ARD_WORKERS):
+  """One loss/gradient callable per worker handle (the designer's own handle first; extra handles on
+  their own streams are created once and cached on `dev`)."""
+  workers = max(1, int(workers))
+  pool = getattr(dev, '_ard_workers', None)
+  if pool is None:
+    pool = []
+    dev._ard_workers = pool  # pylint: disable=protected-access
+  while len(pool) < workers - 1:
+    pool.append(gp.DeviceGP(dev.device.index))
+  devs = [dev] + pool[:workers - 1]
+
+  def make(d):
+    def f(theta):
+      p = gp.GPHyperParams.from_vector(theta, dc, dk)
+      loss, grad, _ = d.loss_and_grad(xt, yt, p, z=zt, n_valid=n_valid)
+      if not np.isfinite(loss):
+        return 1e300, np.zeros_like(theta)
+      return loss, grad
+    return f
+
+  return [make(d) for d in devs]
 
 
 def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,
              random_restarts: int = DEFAULT_RANDOM_RESTARTS, ensemble_size: int = 1,
-             optimizer: Optional[ScipyLbfgsB] = None, n_valid: Optional[int] = None
-             ) -> Tuple[List[gp.GPHyperParams], np.ndarray]:
+             optimizer: Optional[ScipyLbfgsB] = None, n_valid: Optional[int] = None,
+             workers: int = MAX_ARD_WORKERS) -> Tuple[List[gp.GPHyperParams], np.ndarray]:
   """Returns the best `ensemble_size` hyper-parameter sets and all final losses.
 
   x [N,Dc] float64, z [N,Dk] int32 or None, y [N]: device tensors or arrays (copied once).
@@ -77,13 +132,6 @@ def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,
   dk = 0 if zt is None else zt.shape[1]
   lo, hi = gp.param_bounds(dc, dk)
   inits = log_uniform_init(rng, dc, dk, random_restarts)
-
-  def f(theta):
-    p = gp.GPHyperParams.from_vector(theta, dc, dk)
-    loss, grad, _ = dev.loss_and_grad(xt, yt, p, z=zt, n_valid=n_valid)
-    if not np.isfinite(loss):
-      return 1e300, np.zeros_like(theta)
-    return loss, grad
-
-  best, losses = optimizer(inits, f, list(zip(lo, hi)), best_n=ensemble_size)
+  fns = loss_functions(dev, xt, yt, zt, dc, dk, n_valid, workers=min(workers, random_restarts))
+  best, losses = optimizer(inits, fns, list(zip(lo, hi)), best_n=ensemble_size)
   return [gp.GPHyperParams.from_vector(t, dc, dk) for t in best], losses

@@ -196,13 +196,8 @@ class VizierGPUCBPEBandit:
     zt = torch.from_numpy(np.ascontiguousarray(cat)).to(dev_a.device) if dk else None
     lo, hi = gp.param_bounds(dc, dk)
 
-    def f(theta):
-      loss, grad, _ = dev_a.loss_and_grad(xt, yt, gp.GPHyperParams.from_vector(theta, dc, dk), z=zt)
-      if not np.isfinite(loss):
-        return 1e300, np.zeros_like(theta)
-      return loss, grad
-
-    best, _ = self._ard_optimizer(inits, f, list(zip(lo, hi)), best_n=1)
+    fns = ard.loss_functions(dev_a, xt, yt, zt, dc, dk, workers=min(ard.MAX_ARD_WORKERS, inits.shape[0]))
+    best, _ = self._ard_optimizer(inits, fns, list(zip(lo, hi)), best_n=1)
     return gp.GPHyperParams.from_vector(best[0], dc, dk)
 
   def _fit_all_features(self, params: gp.GPHyperParams, cont, cat, labels, pend_c, pend_z, noise_is_high: bool):
