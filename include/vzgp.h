@@ -184,6 +184,15 @@ int vzgp_topk(vzgp_handle* h, const double* score, int64_t M, int count, int64_t
 int vzgp_score_topk(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                     int count, double* score_dev, double* best_x, double* best_score, int64_t* best_index);
 
+/* Uniform ensemble of E models (UniformEnsemblePredictive.predict_with_aux,
+ * stochastic_process_model.py:846-868: equal-weight MixtureSameFamily; used when
+ * VizierGPBandit(ensemble_size > 1) keeps the E best ARD restarts, gp_models.py:200-223).
+ * All members must be fitted on the same trials and share device and stream.
+ * mean = avg mu_e;  var = avg(sigma_e^2 + mu_e^2) - mean^2;  score = UCB (+ trust region) of those.
+ * mu / sigma / linf are optional device outputs [M]. */
+int vzgp_score_ensemble(vzgp_handle* const* hs, int E, const double* Xs, const int32_t* Zs, int M,
+                        const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf);
+
 /* Candidate-pool shards over several GPUs (the reference is single-process, its
  * counterpart is the arg-partition over ONE pool, vectorized_base.py:575-587).
  * vzgp_score_topk_pack: score this rank's shard, select its top `count` and write them to the DEVICE
@@ -227,6 +236,10 @@ typedef struct vzgp_eagle_config {
 int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
                    const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
                    int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score);
+/* The same loop against a uniform ensemble (see vzgp_score_ensemble). */
+int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
+                            const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
+                            int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score);
 
 /* GP-UCB-PE scoring of M device candidates with models hA / hB (same device and stream).
  * score [M] required; mu, sigma (model A) and sigma_all (model B) optional; all device. */

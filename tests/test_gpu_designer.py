@@ -92,6 +92,31 @@ def test_minimisation_converges_faster_than_random():
   assert best < 0.02 and best < rand_best
 
 
+def test_ensemble_designer_suggest_sample_predict():
+  """gp_bandit_test.py:128-235 shape: ensemble_size 2 / 3, a padding schedule (no numerical effect
+  here), batches, then sample() / predict() on fresh points."""
+  p = _problem(3)
+  f = lambda x: -np.sum((x - 0.5) ** 2)
+  for ens, batch in ((2, 2), (3, 1)):
+    d = gp_bandit.VizierGPBandit.from_problem(p, seed=1, acquisition_optimizer_factory=small_opt, ensemble_size=ens,
+                                              padding_schedule='POWERS_OF_2', use_trust_region=False)
+    tid = 1
+    for _ in range(4):
+      sugg = d.suggest(batch)
+      assert len(sugg) == batch
+      trials = _complete(sugg, f, tid); tid += len(trials)
+      d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+    assert len(d._last_params) == ens
+    pts = [vz.Trial(parameters={f'x{i}': v for i in range(3)}) for v in (-2.0, 0.5, 3.0)]
+    s = d.sample(pts, num_samples=5)
+    assert s.shape == (5, 3) and np.isfinite(s).all()
+    assert d.sample([], num_samples=5).shape == (5, 0)
+    pr = d.predict(pts)
+    assert len(pr.mean) == 3 and np.isfinite(pr.mean).all() and np.isfinite(pr.stddev).all()
+  with pytest.raises(ValueError):
+    gp_bandit.VizierGPBandit.from_problem(p, ensemble_size=9)
+
+
 def test_random_pool_optimizer_factory():
   # the C2 shape through the designer API: score one M-candidate uniform pool, take the top `count`
   p = _problem(5, 0.0, 1.0)

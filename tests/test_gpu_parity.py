@@ -237,6 +237,79 @@ def test_eagle_run_matches_oracle(dev, n, d, pool, batch, steps):
   np.testing.assert_allclose(bx, wx, atol=1e-9)
 
 
+@pytest.mark.parametrize('n,d,m,members,tr', [(90, 5, 700, 2, True), (40, 3, 64, 3, True), (300, 8, 5000, 2, False)])
+def test_ensemble_score_matches_oracle(n, d, m, members, tr):
+  """Uniform mixture of E GPs (stochastic_process_model.py:846-868) through vzgp_score_ensemble:
+  mean = avg mu_e, var = avg(sd_e^2 + mu_e^2) - mean^2, UCB + trust region on top."""
+  gp = _gp()
+  x, y, _ = _problem(n, d, 71)
+  xs, _, _ = _problem(m, d, 72)
+  rng = np.random.default_rng(73)
+  plist_o, plist_g = [], []
+  for _ in range(members):
+    ls2 = np.exp(rng.uniform(np.log(0.05), np.log(5.0), d))
+    sf2, sn2 = float(np.exp(rng.uniform(-2, 1))), float(np.exp(rng.uniform(-8, -2)))
+    plist_o.append(go.GPParams(sf2, ls2, sn2))
+    plist_g.append(gp.GPHyperParams(sf2, ls2, sn2))
+  preds = [go.precompute_predictive(p, x, y) for p in plist_o]
+  ens = gp.EnsembleGP(0, members)
+  ens.fit(x, y, plist_g)
+  radius = 0.3 if tr else go.trust_radius(n, d, 0)
+  acq = gp.Acquisition(1.8, True, radius)
+  mu, sd = go.predict_ensemble(preds, xs)
+  dist = go.min_linf_distance(xs, x, np.ones(d, bool), np.ones(n, bool))
+  want = go.apply_trust_region(go.ucb(mu, sd, 1.8), dist, radius)
+  out = ens.score(xs, acq, with_aux=True)
+  ens.synchronize()
+  np.testing.assert_allclose(out['mean'].cpu().numpy(), mu, atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['stddev'].cpu().numpy(), sd, atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['score'].cpu().numpy(), want, atol=TOL, rtol=0)
+  out2 = ens.score(xs, acq)
+  ens.synchronize()
+  np.testing.assert_allclose(out2['score'].cpu().numpy(), want, atol=TOL, rtol=0)
+  # one-member "ensemble" == the plain model
+  single = gp.EnsembleGP(0, 1)
+  single.fit(x, y, plist_g[:1])
+  o1 = single.score(xs, acq)
+  single.synchronize()
+  w1 = go.apply_trust_region(go.ucb(*go.predict(preds[0], xs), 1.8), dist, radius)
+  np.testing.assert_allclose(o1['score'].cpu().numpy(), w1, atol=TOL, rtol=0)
+
+
+def test_ensemble_eagle_and_random_search_match_oracle():
+  gp = _gp()
+  n, d, pool, batch, steps = 50, 4, 25, 25, 6
+  x, y, _ = _problem(n, d, 81)
+  plist_o = [go.GPParams(1.0, np.full(d, 0.4), 1e-3), go.GPParams(0.5, np.linspace(0.2, 2.0, d), 1e-2)]
+  plist_g = [gp.GPHyperParams(p.signal_variance, p.continuous_length_scale_squared, p.observation_noise_variance) for p in plist_o]
+  preds = [go.precompute_predictive(p, x, y) for p in plist_o]
+  ens = gp.EnsembleGP(0, 2)
+  ens.fit(x, y, plist_g)
+  radius = go.trust_radius(n, d, 0)
+
+  def score_fn(q):
+    mu, sd = go.predict_ensemble(preds, q)
+    dist = go.min_linf_distance(q, x, np.ones(d, bool), np.ones(n, bool))
+    return go.apply_trust_region(go.ucb(mu, sd, 1.8), dist, radius)
+
+  cfg_o = eo.EagleConfig()
+  wx, wr, _ = eo.run_eagle_optimizer(score_fn, dim=d, pool_size=pool, batch_size=batch,
+                                     max_evaluations=steps * batch, count=3, seed=7, cfg=cfg_o, prior_features=x)
+  from vizier_b200 import _lib
+  cfg = _lib.EagleConfig(cfg_o.visibility, cfg_o.gravity, cfg_o.negative_gravity, cfg_o.perturbation,
+                         cfg_o.perturbation_lower_bound, cfg_o.penalize_factor, cfg_o.normalization_scale,
+                         cfg_o.prior_trials_pool_pct, pool, batch, steps * batch)
+  acq = gp.Acquisition(1.8, True, radius)
+  bx, _, br = ens.eagle_run(cfg, acq, count=3, seed=7, prior=x)
+  np.testing.assert_allclose(br, wr, atol=1e-9)
+  np.testing.assert_allclose(bx, wx, atol=1e-9)
+  wx, ws, wi = eo.run_random_optimizer(score_fn, dim=d, num_candidates=2000, count=3, seed=99)
+  rx, _, rs, ri = ens.random_search(2000, acq, 3, seed=99)
+  np.testing.assert_array_equal(ri, wi)
+  np.testing.assert_allclose(rx, wx, atol=0)
+  np.testing.assert_allclose(rs, ws, atol=TOL)
+
+
 def test_c2_full_size_properties(dev):
   """BASELINE C2 (N=1000, D=20, M=100k): spot parity on a sample + size-independent properties."""
   n, d, m = 1000, 20, 100_000

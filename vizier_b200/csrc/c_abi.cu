@@ -525,10 +525,11 @@ int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp
 static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
                           const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,
                           const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
-                          double* best_score) {
+                          double* best_score, vzgp_handle* const* ens = nullptr, int n_ens = 0) {
   VZ_ARG(h && cfg && (acq || pe) && best_score, "handle / pointers");
   auto score_batch = [&](const double* xs, const int32_t* zs, int m, double* out) -> int {
     if (pe) return launch_score_pe(h, hB, xs, zs, m, pe, out, nullptr, nullptr, nullptr);
+    if (n_ens > 1) return launch_score_ensemble(ens, n_ens, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
     return launch_score(h, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
   };
   if (!h->fitted) { set_error("vzgp_eagle_run before vzgp_fit"); return VZGP_ERR_STATE; }
@@ -665,6 +666,38 @@ int vzgp_eagle_run_pe(vzgp_handle* hA, vzgp_handle* hB, const vzgp_eagle_config*
   VZ_TRY(check_pe(hA, hB, pe));
   return eagle_run_impl(hA, hB, cfg, nullptr, pe, prior, prior_z, n_prior, cat_sizes, count, seed, best_x, best_z,
                         best_score);
+}
+
+static int check_ensemble(vzgp_handle* const* hs, int E) {
+  VZ_ARG(hs != nullptr && E >= 1 && E <= 16, "1 <= E <= 16 handles");
+  for (int e = 0; e < E; ++e) {
+    VZ_ARG(hs[e] != nullptr, "handle");
+    if (!hs[e]->fitted) { set_error("ensemble scoring needs every member fitted"); return VZGP_ERR_STATE; }
+    VZ_ARG(hs[e]->device == hs[0]->device && hs[e]->stream == hs[0]->stream, "members must share device and stream");
+    VZ_ARG(hs[e]->dc == hs[0]->dc && hs[e]->dk == hs[0]->dk && hs[e]->n_valid == hs[0]->n_valid,
+           "members must be fitted on the same trials");
+  }
+  return 0;
+}
+
+int vzgp_score_ensemble(vzgp_handle* const* hs, int E, const double* Xs, const int32_t* Zs, int M,
+                        const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf) {
+  VZ_TRY(check_ensemble(hs, E));
+  VZ_ARG(acq != nullptr, "acq");
+  VZ_ARG(M >= 0 && (M == 0 || score != nullptr), "M / score");
+  VZ_ARG(M == 0 || Xs != nullptr || hs[0]->dc == 0, "Xs");
+  VZ_ARG(M == 0 || Zs != nullptr || hs[0]->dk == 0, "Zs");
+  Guard g(hs[0]->device);
+  return launch_score_ensemble(hs, E, Xs, Zs, M, acq, score, mu, sigma, linf);
+}
+
+int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
+                            const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
+                            int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score) {
+  VZ_TRY(check_ensemble(hs, E));
+  VZ_ARG(acq != nullptr, "acq");
+  return eagle_run_impl(hs[0], nullptr, cfg, acq, nullptr, prior, prior_z, n_prior, cat_sizes, count, seed, best_x,
+                        best_z, best_score, hs, E);
 }
 
 int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,

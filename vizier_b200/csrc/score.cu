@@ -882,6 +882,69 @@ int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const in
 }
 
 // ---------------------------------------------------------------------------
+// Uniform ensemble of E models (UniformEnsemblePredictive, stochastic_process_model.py:846-868:
+// equal-weight MixtureSameFamily): mean = avg mu_e, var = avg(sd_e^2 + mu_e^2) - mean^2.
+// ---------------------------------------------------------------------------
+struct EnsCombine {
+  int E;
+  double coef;
+  int apply_tr, tr_strict;
+  double radius;
+};
+__global__ void k_ensemble_combine(int M, EnsCombine p, const double* __restrict__ mu_e, const double* __restrict__ sd_e,
+                                   const double* __restrict__ linf, double* __restrict__ score,
+                                   double* __restrict__ mu, double* __restrict__ sigma, int* __restrict__ clamp_count) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int e = 0; e < p.E; ++e) {
+    const double a = mu_e[(size_t)e * M + m], b = sd_e[(size_t)e * M + m];
+    s1 += a;
+    s2 += fma(b, b, a * a);
+  }
+  const double mean = s1 / p.E;
+  double var = s2 / p.E - mean * mean;
+  if (var < 0.0) { var = 0.0; atomicAdd(clamp_count, 1); }
+  const double sd = sqrt(var);
+  double sc = fma(p.coef, sd, mean);
+  if (p.apply_tr) {
+    const double dist = linf[m];
+    const bool inside = (p.tr_strict ? (dist < p.radius) : (dist <= p.radius)) || (p.radius > 0.5);
+    sc = inside ? sc : (-1e4 - dist);
+  }
+  score[m] = sc;
+  if (mu) mu[m] = mean;
+  if (sigma) sigma[m] = sd;
+}
+
+int launch_score_ensemble(vzgp_handle* const* hs, int E, const double* Xs, const int32_t* Zs, int M,
+                          const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf) {
+  if (M <= 0) return 0;
+  vzgp_handle* h0 = hs[0];
+  VZ_TRY(h0->pe_tmp.reserve(sizeof(double) * (2 * (size_t)E + 2) * (size_t)M));
+  double* t = h0->pe_tmp.as<double>();
+  double* mu_e = t;
+  double* sd_e = t + (size_t)E * M;
+  double* linf_buf = linf ? linf : t + 2 * (size_t)E * M;
+  double* dummy = t + (2 * (size_t)E + 1) * M;
+  const bool want_tr = acq->use_trust_region && acq->trust_radius <= 0.5;
+  const bool want_linf = want_tr || linf != nullptr;
+  vzgp_acq none;
+  none.ucb_coefficient = 0.0; none.use_trust_region = 0; none.trust_radius = 1.0;
+  none.tr_dim_mask = acq->tr_dim_mask; none.tr_rows = acq->tr_rows; none.tr_strict = 0;
+  for (int e = 0; e < E; ++e)   // all members share the trials: the distance is computed once
+    VZ_TRY(launch_score(hs[e], Xs, Zs, M, &none, dummy, mu_e + (size_t)e * M, sd_e + (size_t)e * M,
+                        (e == 0 && want_linf) ? linf_buf : nullptr));
+  EnsCombine p;
+  p.E = E; p.coef = acq->ucb_coefficient; p.apply_tr = want_tr ? 1 : 0; p.tr_strict = acq->tr_strict ? 1 : 0;
+  p.radius = acq->trust_radius;
+  k_ensemble_combine<<<(M + 255) / 256, 256, 0, h0->stream>>>(M, p, mu_e, sd_e, linf_buf, score, mu, sigma, h0->small.as<int>());
+  VZ_CHECK_LAUNCH();
+  h0->launches++;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Philox candidate pool: X[m, d] = U(seed, STREAM_RANDOM_POOL, 0, (index_base+m)*dc + d)
 // ---------------------------------------------------------------------------
 __global__ void k_random_pool(double* __restrict__ X, int64_t total, int64_t elem_base,

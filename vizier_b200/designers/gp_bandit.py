@@ -10,10 +10,13 @@ same metadata keys, same errors for unsupported search spaces.  What runs where:
                          posterior mean/variance + UCB + trust region, Eagle / random acquisition
                          optimisation, top-k
 
+`ensemble_size > 1` keeps the E best ARD restarts as a uniform mixture (`gp.EnsembleGP`).
 Not implemented (the reference supports them; SURVEY 8f "next"): multi-metric scalarised UCB,
-`ensemble_size > 1`, `linear_coef`, transfer-learning priors (`set_priors`), parallel (q-)
-acquisitions, feature padding schedules.  Categorical parameters ARE supported end to end.  Each raises NotImplementedError / ValueError instead of
-silently doing something else.
+`linear_coef`, transfer-learning priors (`set_priors`), parallel (q-) acquisitions; each raises
+NotImplementedError instead of silently doing something else.  Categorical parameters ARE supported
+end to end.  `padding_schedule` is accepted and has no numerical effect here: the kernels take
+explicit sizes (`n_valid`, Dc, Dk) instead of padded shapes + masks, which is what the reference's
+padding-invariance tests (gp_bandit_test.py:302-370) assert of its own masked implementation.
 """
 
 from __future__ import annotations
@@ -91,8 +94,9 @@ class VizierGPBandit:
       raise NotImplementedError('vizier_b200.VizierGPBandit implements the single-metric path only.')
     if linear_coef is not None:
       raise NotImplementedError('linear_coef (Matern + linear kernel) is not implemented.')
-    if (ensemble_size or 1) != 1:
-      raise NotImplementedError('ensemble_size > 1 is not implemented.')
+    self._ensemble_size = int(ensemble_size or 1)
+    if self._ensemble_size < 1 or self._ensemble_size > ard_random_restarts:
+      raise ValueError('ensemble_size must be in [1, ard_random_restarts].')
     if scoring_function_is_parallel or scoring_function_factory is not None:
       raise NotImplementedError('custom / parallel scoring functions are not implemented (UCB only).')
     del padding_schedule, num_scalarizations, ref_scaling, multitask_type
@@ -113,8 +117,9 @@ class VizierGPBandit:
     self._trials: list = []
     self._incorporated_trials_count = 0
     self._device_index = device
-    self._dev: Optional[gp.DeviceGP] = None
-    self._last_params: Optional[gp.GPHyperParams] = None
+    self._dev = None                       # gp.DeviceGP, or gp.EnsembleGP when ensemble_size > 1
+    self._ard_dev: Optional[gp.DeviceGP] = None
+    self._last_params = None               # GPHyperParams (or a list of them for an ensemble)
 
   # ------------------------------------------------------------------ API
   def update(self, completed, all_active=None) -> None:
@@ -131,9 +136,14 @@ class VizierGPBandit:
     return cls(problem, rng=random.getrandbits(32) if seed is None else seed, **kwargs)
 
   # ------------------------------------------------------------------ internals
-  def _device(self) -> gp.DeviceGP:
+  def _device(self):
     if self._dev is None:
-      self._dev = gp.DeviceGP(self._device_index)
+      if self._ensemble_size > 1:
+        self._dev = gp.EnsembleGP(self._device_index, self._ensemble_size)
+        self._ard_dev = self._dev.members[0]
+      else:
+        self._dev = gp.DeviceGP(self._device_index)
+        self._ard_dev = self._dev
     return self._dev
 
   @profiler.record_runtime
@@ -170,10 +180,15 @@ class VizierGPBandit:
     self._incorporated_trials_count = len(self._trials)
     ard_rng = np.random.default_rng(int(self._rng.integers(2**62)))
     z = cat if cat.shape[1] else None
-    best, _ = ard.train_gp(dev, cont, labels[:, 0], z, rng=ard_rng, random_restarts=self._ard_random_restarts,
-                           ensemble_size=1, optimizer=self._ard_optimizer)
-    self._last_params = best[0]
-    dev.fit(cont, labels[:, 0], self._last_params, z=z)
+    best, _ = ard.train_gp(self._ard_dev, cont, labels[:, 0], z, rng=ard_rng, random_restarts=self._ard_random_restarts,
+                           ensemble_size=self._ensemble_size, optimizer=self._ard_optimizer)
+    if self._ensemble_size > 1:
+      # the E best restarts become the members of a uniform mixture (gp_models.py:200-223)
+      self._last_params = list(best)
+      dev.fit(cont, labels[:, 0], self._last_params, z=z)
+    else:
+      self._last_params = best[0]
+      dev.fit(cont, labels[:, 0], self._last_params, z=z)
     return dev
 
   def _acquisition(self, n_obs: int) -> gp.Acquisition:
@@ -232,15 +247,20 @@ class VizierGPBandit:
     dev = self._update_gp(cont, cat, labels)
     xs, zs = self._converter.to_features(trials)
     xs = np.nan_to_num(xs, nan=0.0)
-    mean, cov = dev.posterior(xs, zs if zs.shape[1] else None, add_noise=True)
-    # Cholesky of the (small) posterior covariance on the device as well; the retry adds a tiny
-    # jitter only if round-off made it indefinite.
-    m = mean.shape[0]
-    chol, _, _ = dev.cholesky_retry(cov, jitter=1e-10, max_iters=8)
-    chol = chol.cpu().numpy()
-    mean = mean.cpu().numpy()
     g = np.random.default_rng(_seed_from(rng) if rng is not None else 0)
-    samples = mean[None, :] + g.standard_normal((num_samples, m)) @ chol.T
+    zq = zs if zs.shape[1] else None
+    comps = dev.posterior(xs, zq, add_noise=True) if self._ensemble_size > 1 else [dev.posterior(xs, zq, add_noise=True)]
+    # Cholesky of each (small) posterior covariance on the device as well; the retry adds a tiny
+    # jitter only if round-off made it indefinite.
+    factors = []
+    for mean, cov in comps:
+      chol, _, _ = self._ard_dev.cholesky_retry(cov, jitter=1e-10, max_iters=8)
+      factors.append((mean.cpu().numpy(), chol.cpu().numpy()))
+    m = factors[0][0].shape[0]
+    normals = g.standard_normal((num_samples, m))
+    # equal-weight mixture: every sample is a joint draw from one uniformly chosen member
+    member = g.integers(0, len(factors), size=num_samples) if len(factors) > 1 else np.zeros(num_samples, int)
+    samples = np.stack([factors[e][0] + normals[i] @ factors[e][1].T for i, e in enumerate(member)])
     return np.vstack([self._output_warper.unwarp(samples[i][:, None]).reshape(-1) for i in range(num_samples)])
 
   @profiler.record_runtime

@@ -471,3 +471,92 @@ class DeviceGP:
         bs.ctypes.data_as(C.POINTER(C.c_double))))
     del keep
     return bx, bz, bs
+
+class EnsembleGP:
+  """Uniform ensemble of E GPs fitted on the same trials with different hyper-parameters
+  (`VizierGPBandit(ensemble_size=E)`: the E best ARD restarts, gp_models.py:200-223; predictive =
+  UniformEnsemblePredictive, stochastic_process_model.py:836-868).  The members are E libvzgp handles on
+  ONE stream; scoring and the Eagle loop run through `vzgp_score_ensemble` / `vzgp_eagle_run_ensemble`.
+  Exposes the subset of the `DeviceGP` interface the acquisition optimiser drives."""
+
+  def __init__(self, device: int, size: int):
+    first = DeviceGP(device)
+    self.members = [first] + [DeviceGP(device, stream=first.stream) for _ in range(size - 1)]
+    self.device = first.device
+    self._lib = first._lib
+    self.n = self.dc = self.dk = 0
+
+  @property
+  def stream(self):
+    return self.members[0].stream
+
+  @property
+  def launch_count(self) -> int:
+    return sum(m.launch_count for m in self.members)
+
+  def synchronize(self):
+    self.members[0].synchronize()
+
+  def _handles(self):
+    arr = (C.c_void_p * len(self.members))(*[m._h for m in self.members])
+    return arr
+
+  def fit(self, x, y, params: Sequence[GPHyperParams], z=None, n_valid=None) -> int:
+    assert len(params) == len(self.members)
+    retries = 0
+    for m, p in zip(self.members, params):
+      retries = max(retries, m.fit(x, y, p, z=z, n_valid=n_valid))
+    f = self.members[0]
+    self.n, self.dc, self.dk = f.n, f.dc, f.dk
+    return retries
+
+  def score(self, xs, acq: Acquisition, zs=None, with_aux: bool = False) -> dict:
+    f = self.members[0]
+    xst, zst = f._xz(xs, zs)
+    m = xst.shape[0]
+    res = {'score': torch.empty((m,), dtype=torch.float64, device=self.device)}
+    if with_aux:
+      for k in ('mean', 'stddev', 'linf_distance'):
+        res[k] = torch.empty((m,), dtype=torch.float64, device=self.device)
+    a, keep = acq._c()
+    _lib.check('vzgp_score_ensemble', self._lib.vzgp_score_ensemble(
+        self._handles(), len(self.members), _ptr(xst), _ptr(zst), m, C.byref(a), _ptr(res['score']),
+        _ptr(res.get('mean')), _ptr(res.get('stddev')), _ptr(res.get('linf_distance'))))
+    res['_inputs'] = (xst, zst, keep)
+    return res
+
+  def eagle_run(self, cfg, acq: Acquisition, count: int, seed: int, prior=None, prior_z=None, cat_sizes=None,
+                other=None):
+    assert other is None
+    f = self.members[0]
+    a, keep = acq._c()
+    n_prior = 0 if prior is None else len(prior)
+    pt = f._dev(prior, torch.float64) if n_prior > 0 and self.dc > 0 else None
+    pz = f._dev(prior_z, torch.int32) if n_prior > 0 and self.dk > 0 else None
+    bx = np.zeros((count, self.dc), np.float64)
+    bz = np.zeros((count, self.dk), np.int32)
+    bs = np.zeros(count, np.float64)
+    sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
+    _lib.check('vzgp_eagle_run_ensemble', self._lib.vzgp_eagle_run_ensemble(
+        self._handles(), len(self.members), C.byref(cfg), C.byref(a), _ptr(pt), _ptr(pz), n_prior,
+        sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes.size else None, count, seed,
+        bx.ctypes.data_as(C.POINTER(C.c_double)), bz.ctypes.data_as(C.POINTER(C.c_int32)),
+        bs.ctypes.data_as(C.POINTER(C.c_double))))
+    del keep
+    return bx, bz, bs
+
+  def random_search(self, m: int, acq: Acquisition, count: int, seed: int, index_base: int = 0, cat_sizes=None):
+    """RandomVectorizedStrategy over the ensemble: Philox pool -> mixture score -> device top-k."""
+    f = self.members[0]
+    xs = f.random_pool(m, self.dc, seed, index_base) if self.dc else torch.zeros((m, 0), dtype=torch.float64, device=self.device)
+    zs = f.random_pool_cat(m, cat_sizes, seed, index_base) if self.dk else None
+    out = self.score(xs, acq, zs=zs)
+    idx, val = f.topk(out['score'], count)
+    it = torch.from_numpy(np.maximum(idx, 0)).to(self.device)
+    bx = xs[it].cpu().numpy()
+    bz = zs[it].cpu().numpy() if zs is not None else np.zeros((count, 0), np.int32)
+    return bx, bz, val, idx + index_base
+
+  def posterior(self, xs, zs=None, add_noise: bool = True):
+    """Per-member joint posteriors [(mean [M], cov [M, M])] (the mixture components)."""
+    return [m.posterior(xs, zs, add_noise) for m in self.members]
