@@ -183,6 +183,47 @@ def test_nll_grad(dev, n, d, dk, nv):
   np.testing.assert_allclose(grad, want_g, atol=1e-8 * max(1.0, np.max(np.abs(want_g))), rtol=0)
 
 
+@pytest.mark.parametrize('n,d,dk,nv', [(1, 1, 0, 1), (7, 2, 1, 7), (50, 4, 0, 50), (64, 20, 3, 64), (64, 64, 0, 57), (33, 5, 2, 20)])
+def test_nll_grad_small_fused_kernel(dev, n, d, dk, nv):
+  """N <= 64 takes the single-launch kernel (k_nll_grad_small): same oracle, same tolerances, and the
+  make_loss_fn closure the ARD driver uses returns the same numbers; the fitted model is untouched."""
+  x, y, z = _problem(n, d, 17, dk)
+  po, pg = _params(d, dk, sf2=0.7, sn2=2e-3)
+  valid = np.arange(n) < nv
+  want_l, want_g = go.loss_and_grad(po.to_vector(), x, y, z, valid)
+  xt = torch.from_numpy(x).cuda(); yt = torch.from_numpy(y).cuda()
+  zt = torch.from_numpy(z).cuda() if z is not None else None
+  dev.fit(x[:nv], y[:nv], pg, z=None if z is None else z[:nv])
+  alpha_before = dev.alpha().cpu().numpy()
+  l0 = dev.launch_count
+  loss, grad, retries = dev.loss_and_grad(xt, yt, pg, z=zt, n_valid=nv)
+  assert dev.launch_count - l0 == 1
+  assert retries == 0
+  assert abs(loss - want_l) < 1e-9 * max(1.0, abs(want_l))
+  np.testing.assert_allclose(grad, want_g, atol=1e-8 * max(1.0, np.max(np.abs(want_g))), rtol=0)
+  f = dev.make_loss_fn(xt, yt, zt, n_valid=nv)
+  l2, g2 = f(pg.to_vector())
+  assert l2 == loss
+  np.testing.assert_array_equal(g2, grad)
+  np.testing.assert_array_equal(dev.alpha().cpu().numpy(), alpha_before)
+
+
+def test_nll_grad_small_near_singular(dev):
+  """Triplicated points at the noise floor (cond ~ 1e10): the in-kernel factorisation + retry loop
+  reports the oracle's retry count and loss (tuned_gp_models.py:272-280)."""
+  rng = np.random.default_rng(19)
+  x = rng.uniform(size=(12, 3)); x[5] = x[2]; x[9] = x[2]
+  y = rng.normal(size=12)
+  po = go.GPParams(1.0, np.full(3, 0.5), 1e-10); pg = _gp().GPHyperParams(1.0, np.full(3, 0.5), 1e-10)
+  ky = go.kernel_matrix(po, x)
+  _, shift, want_retries = go.retrying_cholesky(ky)
+  want_l, want_g = go.loss_and_grad(po.to_vector(), x, y)
+  loss, grad, retries = dev.loss_and_grad(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), pg)
+  assert retries == want_retries
+  if np.isfinite(want_l):
+    assert abs(loss - want_l) < 1e-6 * max(1.0, abs(want_l))
+
+
 def test_topk_ties_nan_and_order(dev):
   rng = np.random.default_rng(11)
   s = rng.normal(size=5000)

@@ -101,16 +101,7 @@ def loss_functions(dev: gp.DeviceGP, xt, yt, zt, dc: int, dk: int, n_valid: Opti
     pool.append(gp.DeviceGP(dev.device.index))
   devs = [dev] + pool[:workers - 1]
 
-  def make(d):
-    def f(theta):
-      p = gp.GPHyperParams.from_vector(theta, dc, dk)
-      loss, grad, _ = d.loss_and_grad(xt, yt, p, z=zt, n_valid=n_valid)
-      if not np.isfinite(loss):
-        return 1e300, np.zeros_like(theta)
-      return loss, grad
-    return f
-
-  return [make(d) for d in devs]
+  return [d.make_loss_fn(xt, yt, zt, n_valid) for d in devs]
 
 
 def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,

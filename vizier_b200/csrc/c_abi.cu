@@ -301,6 +301,46 @@ int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const doubl
                   int Dk, int n_valid, const vzgp_params* p, double* loss_out, double* grad_out) {
   VZ_ARG(h && loss_out && grad_out, "handle / outputs");
   Guard g(h->device);
+  // Regularisers: tuned_gp_models.py:167,180,192,269 -> 0.01*log(x/c)^2, derivative 0.02*log(x/c)/x.
+  auto reg = [](double x, double c) { double l = std::log(x / c); return 0.01 * l * l; };
+  auto dreg = [](double x, double c) { return 0.02 * std::log(x / c) / x; };
+  auto finish = [&](double half_logdet_plus_quad, const double* hostg) {
+    const double sf2 = p->signal_variance, sn2 = p->observation_noise_variance;
+    double loss = half_logdet_plus_quad + 0.5 * n_valid * std::log(2.0 * M_PI);
+    loss += reg(sf2, 0.039) + reg(sn2, 0.0039);
+    for (int k = 0; k < Dk; ++k) {
+      const double l = p->categorical_length_scale_squared[k];
+      loss += reg(l, 0.5);
+      grad_out[k] = -0.5 * hostg[k] / (l * l) + dreg(l, 0.5);
+    }
+    for (int d = 0; d < Dc; ++d) {
+      const double l = p->continuous_length_scale_squared[d];
+      loss += reg(l, 0.5);
+      grad_out[Dk + d] = -0.5 * hostg[Dk + d] / (l * l) + dreg(l, 0.5);
+    }
+    grad_out[Dk + Dc] = 0.5 * hostg[Dk + Dc] + dreg(sn2, 0.0039);
+    grad_out[Dk + Dc + 1] = 0.5 * hostg[Dk + Dc + 1] / sf2 + dreg(sf2, 0.039);
+    *loss_out = loss;
+  };
+  static const bool small_ok = [] { const char* e = getenv("VZGP_NLL_SMALL"); return !(e && e[0] == '0'); }();
+  if (N <= kBlk && small_ok) {
+    // Small studies: the whole evaluation is one single-CTA kernel (nll_small.cu).  The handle's
+    // fitted model is not touched (ARD callers refit with the chosen parameters afterwards).
+    VZ_ARG(N >= 1 && n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
+    VZ_ARG(X != nullptr || Dc == 0, "X");
+    VZ_ARG(Z != nullptr || Dk == 0, "Z");
+    VZ_ARG(y != nullptr, "y");
+    KernelParams kp;
+    VZ_TRY(fill_kernel_params(p, Dc, Dk, &kp));
+    const int nq = Dc + Dk + 2;
+    double* dout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);   // 4 + nq doubles
+    VZ_TRY(launch_nll_grad_small(h, X, Z, y, N, n_valid, kp, p->observation_noise_variance, 1e-4, 5, dout));
+    double host[4 + kMaxDc + kMaxDk + 2];
+    VZ_CUDA(cudaMemcpyAsync(host, dout, sizeof(double) * (4 + nq), cudaMemcpyDeviceToHost, h->stream));
+    VZ_CUDA(cudaStreamSynchronize(h->stream));
+    finish(host[0] + host[1], host + 4);
+    return (int)host[3];
+  }
   double shift = 0.0;
   int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, &shift);
   if (retries < 0) return retries;
@@ -318,25 +358,7 @@ int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const doubl
   VZ_CUDA(cudaMemcpyAsync(host2, out2, sizeof(host2), cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaMemcpyAsync(hostg, gout, sizeof(double) * nq, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaStreamSynchronize(h->stream));
-  // Regularisers: tuned_gp_models.py:167,180,192,269 -> 0.01*log(x/c)^2, derivative 0.02*log(x/c)/x.
-  const double sf2 = p->signal_variance, sn2 = p->observation_noise_variance;
-  auto reg = [](double x, double c) { double l = std::log(x / c); return 0.01 * l * l; };
-  auto dreg = [](double x, double c) { return 0.02 * std::log(x / c) / x; };
-  double loss = host2[1] + host2[0] + 0.5 * n_valid * std::log(2.0 * M_PI);
-  loss += reg(sf2, 0.039) + reg(sn2, 0.0039);
-  for (int k = 0; k < Dk; ++k) {
-    const double l = p->categorical_length_scale_squared[k];
-    loss += reg(l, 0.5);
-    grad_out[k] = -0.5 * hostg[k] / (l * l) + dreg(l, 0.5);
-  }
-  for (int d = 0; d < Dc; ++d) {
-    const double l = p->continuous_length_scale_squared[d];
-    loss += reg(l, 0.5);
-    grad_out[Dk + d] = -0.5 * hostg[Dk + d] / (l * l) + dreg(l, 0.5);
-  }
-  grad_out[Dk + Dc] = 0.5 * hostg[Dk + Dc] + dreg(sn2, 0.0039);
-  grad_out[Dk + Dc + 1] = 0.5 * hostg[Dk + Dc + 1] / sf2 + dreg(sf2, 0.039);
-  *loss_out = loss;
+  finish(host2[1] + host2[0], hostg);
   return retries;
 }
 

@@ -53,6 +53,8 @@ int launch_topk_device(vzgp_handle* h, const double* score, int64_t M, int count
 int launch_gather_rows(vzgp_handle* h, const double* X, int dc, const long long* idx, int count,
                        int64_t M, double* out);
 
+int launch_nll_grad_small(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int n_valid,
+                          const KernelParams& kp, double sn2, double jitter0, int max_iters, double* out);
 int launch_score_ensemble(vzgp_handle* const* hs, int E, const double* Xs, const int32_t* Zs, int M,
                           const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf);
 int launch_pack_topk(vzgp_handle* h, const double* X, int dc, const long long* idx, const double* val,

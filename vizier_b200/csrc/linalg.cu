@@ -130,31 +130,15 @@ __device__ __forceinline__ void tri_inverse_64(const double* a, double* x, doubl
 #ifdef VZ_POTF2_TIMING
 __device__ long long g_potf2_t[32];
 #define VZ_TSTAMP(i) do { if (threadIdx.x == 0) g_potf2_t[i] = clock64(); } while (0)
-#else
-#define VZ_TSTAMP(i) do {} while (0)
 #endif
-
-// Correctly rounded quotient c / d from r ~= 1/d without branches: q = c*r; q += (c - q*d)*r.
-__device__ __forceinline__ double div_refined(double c, double d, double r) {
-  const double q = c * r;
-  return fma(fma(-q, d, c), r, q);
-}
+}  // namespace vzgp
+#include "potf2.cuh"
+namespace vzgp {
 
 // Factor the 64x64 diagonal block kb in place (lower), zero its upper triangle, and write
 // its inverse into the same block of Linv.  flag[0] is set to 1 if a pivot is not a
-// positive finite number (the factor then holds NaN, like jnp.linalg.cholesky).
-//
-// This kernel is a pure latency chain (64 dependent pivots), so it is organised around the
-// critical path rather than throughput:
-//  * four 16-column macro steps; the 16x16 diagonal piece is factored by ONE warp entirely in
-//    registers (lane = row) in the square-root-free LDL^T form: the only long-latency operation on
-//    the pivot-to-pivot chain is one reciprocal, and the column broadcasts (shuffles of the
-//    UNSCALED column) overlap it.  The 16 columns are scaled by 1/sqrt(d_j) once, in parallel,
-//    after the loop.
-//  * the rows below are solved one thread per row (right-looking, 2 dependent ops per column),
-//    the trailing part is updated by the whole CTA with 16-wide register tiles.
-//  * the inverse: the four 16x16 diagonal blocks (one warp each, lane = column) and two
-//    recursive-doubling levels  X21 = -B^-1 (C A^-1)  with fully unrolled dot products.
+// positive finite number (the factor then holds NaN, like jnp.linalg.cholesky).  The work is
+// potf2_inv_64 (potf2.cuh); 102 -> 18 us per block against the first column-by-column version.
 __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ L, int ld, int kb,
                                                    double* __restrict__ Linv, int ldi,
                                                    int* __restrict__ flag) {
@@ -166,7 +150,7 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ L, int l
   __shared__ double rd[64];      // 1 / diagonal of the factor
   __shared__ int s_bad;
   double* blk = L + (size_t)kb * 64 * ld + kb * 64;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   if (tid == 0) s_bad = 0;
   VZ_TSTAMP(0);
   {
@@ -185,176 +169,7 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ L, int l
     }
   }
   __syncthreads();
-  VZ_TSTAMP(1);
-#pragma unroll 1
-  for (int mb = 0; mb < 4; ++mb) {
-    const int c0 = 16 * mb;
-    if (warp == 0) {
-      // ---- 16x16 LDL^T in registers: lane l < 16 owns row c0 + l ----
-      double v[16];
-      const int row = c0 + (lane & 15);
-#pragma unroll
-      for (int k = 0; k < 16; k += 2) {
-        const double2 p = *reinterpret_cast<const double2*>(a + row * LD + c0 + k);
-        v[k] = p.x; v[k + 1] = p.y;
-      }
-      bool bad = false;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const double d = __shfl_sync(0xffffffffu, v[j], j);
-        if (!(d > 0.0) || !isfinite(d)) bad = true;
-        const double r = 1.0 / d;
-        const double wr = v[j] * r;
-#pragma unroll
-        for (int k = j + 1; k < 16; ++k) {
-          const double wk = __shfl_sync(0xffffffffu, v[j], k);
-          v[k] = fma(-wr, wk, v[k]);
-        }
-      }
-      // lane j: d_j = v[j];  column scale 1/sqrt(d_j)
-      double dj = 0.0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) dj = (lane == j) ? v[j] : dj;
-      const double rs = bad ? nan("") : 1.0 / sqrt(dj);
-      if (lane < 16) rd[c0 + lane] = rs;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const double rj = __shfl_sync(0xffffffffu, rs, j);
-        v[j] = (j <= lane) ? v[j] * rj : 0.0;
-      }
-      if (lane < 16) {
-#pragma unroll
-        for (int k = 0; k < 16; k += 2)
-          *reinterpret_cast<double2*>(a + row * LD + c0 + k) = make_double2(v[k], v[k + 1]);
-      }
-      if (bad && lane == 0) s_bad = 1;
-    }
-    __syncthreads();
-    VZ_TSTAMP(2 + 3 * mb);
-    const int rem = 48 - c0;                 // rows below this macro block
-    if (tid < rem) {
-      // ---- panel: row r solves x * L11^T = a[r, c0:c0+16], right-looking ----
-      const int r = c0 + 16 + tid;
-      double xr[16];
-#pragma unroll
-      for (int k = 0; k < 16; k += 2) {
-        const double2 p = *reinterpret_cast<const double2*>(a + r * LD + c0 + k);
-        xr[k] = p.x; xr[k + 1] = p.y;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        xr[j] *= rd[c0 + j];
-#pragma unroll
-        for (int k = j + 1; k < 16; ++k) xr[k] = fma(-xr[j], a[(c0 + k) * LD + c0 + j], xr[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < 16; k += 2)
-        *reinterpret_cast<double2*>(a + r * LD + c0 + k) = make_double2(xr[k], xr[k + 1]);
-    }
-    __syncthreads();
-    VZ_TSTAMP(3 + 3 * mb);
-    // ---- trailing update: a[i][k] -= sum_j a[i][c0+j] * a[k][c0+j],  c0+16 <= k <= i ----
-    // thread (ti, tk) owns the entries (ti + 16 p, tk + 16 q) of every 16x16 block (p, q), q <= p
-    {
-      const int ti = tid & 15, tk = tid >> 4;
-      const int nb = rem >> 4;
-      for (int p = 0; p < nb; ++p) {
-        const int i = c0 + 16 + 16 * p + ti;
-        double ai[16];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const double2 q2 = *reinterpret_cast<const double2*>(a + i * LD + c0 + j);
-          ai[j] = q2.x; ai[j + 1] = q2.y;
-        }
-        for (int q = 0; q <= p; ++q) {
-          const int k = c0 + 16 + 16 * q + tk;
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const double2 q2 = *reinterpret_cast<const double2*>(a + k * LD + c0 + j);
-            s0 = fma(ai[j], q2.x, s0);
-            s1 = fma(ai[j + 1], q2.y, s1);
-          }
-          if (k <= i) a[i * LD + k] -= s0 + s1;
-        }
-      }
-    }
-    __syncthreads();
-    VZ_TSTAMP(4 + 3 * mb);
-  }
-  VZ_TSTAMP(14);
-  // ---- inverse, step A: the four 16x16 diagonal blocks, one warp each, lane = column ----
-  if (warp < 4 && lane < 16) {
-    const int b0 = 16 * warp, c = lane;
-    double xc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) xc[i] = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      xc[i] *= rd[b0 + i];
-#pragma unroll
-      for (int k = i + 1; k < 16; ++k) xc[k] = fma(-a[(b0 + k) * LD + b0 + i], xc[i], xc[k]);
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[(b0 + i) * LD + b0 + c] = xc[i];
-  }
-  __syncthreads();
-  VZ_TSTAMP(15);
-  // ---- step B: 16-level doubling, two pairs; thread = one (row, col) of each pair ----
-  {
-    const int rr = tid >> 4, cc = tid & 15;
-    double acc[2];
-#pragma unroll
-    for (int pr = 0; pr < 2; ++pr) {
-      const int p0 = 32 * pr;
-      double s0 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) s0 = fma(a[(p0 + 16 + rr) * LD + p0 + k], x[(p0 + k) * LD + p0 + cc], s0);
-      acc[pr] = s0;
-    }
-    t[rr * 34 + cc] = acc[0];
-    t[(16 + rr) * 34 + cc] = acc[1];
-    __syncthreads();
-#pragma unroll
-    for (int pr = 0; pr < 2; ++pr) {
-      const int p0 = 32 * pr;
-      double s0 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) s0 = fma(x[(p0 + 16 + rr) * LD + p0 + 16 + k], t[(16 * pr + k) * 34 + cc], s0);
-      acc[pr] = s0;
-    }
-    x[(16 + rr) * LD + cc] = -acc[0];
-    x[(48 + rr) * LD + 32 + cc] = -acc[1];
-  }
-  __syncthreads();
-  VZ_TSTAMP(16);
-  // ---- step C: 32-level doubling; thread = a 2x2 patch of the 32x32 block ----
-  {
-    const int r0 = (tid >> 4) * 2, q0 = (tid & 15) * 2;
-    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const double a0 = a[(32 + r0) * LD + k], a1 = a[(33 + r0) * LD + k];
-      const double2 xv = *reinterpret_cast<const double2*>(x + k * LD + q0);
-      s00 = fma(a0, xv.x, s00); s01 = fma(a0, xv.y, s01);
-      s10 = fma(a1, xv.x, s10); s11 = fma(a1, xv.y, s11);
-    }
-    *reinterpret_cast<double2*>(t + r0 * 34 + q0) = make_double2(s00, s01);
-    *reinterpret_cast<double2*>(t + (r0 + 1) * 34 + q0) = make_double2(s10, s11);
-    __syncthreads();
-    s00 = s01 = s10 = s11 = 0.0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const double b0v = x[(32 + r0) * LD + 32 + k], b1v = x[(33 + r0) * LD + 32 + k];
-      const double2 tv = *reinterpret_cast<const double2*>(t + k * 34 + q0);
-      s00 = fma(b0v, tv.x, s00); s01 = fma(b0v, tv.y, s01);
-      s10 = fma(b1v, tv.x, s10); s11 = fma(b1v, tv.y, s11);
-    }
-    *reinterpret_cast<double2*>(x + (32 + r0) * LD + q0) = make_double2(-s00, -s01);
-    *reinterpret_cast<double2*>(x + (33 + r0) * LD + q0) = make_double2(-s10, -s11);
-  }
-  __syncthreads();
-  VZ_TSTAMP(17);
+  potf2_inv_64(a, x, t, rd, &s_bad);
   double* iblk = Linv + (size_t)kb * 64 * ldi + kb * 64;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {

@@ -288,6 +288,42 @@ class DeviceGP:
         C.byref(p), C.byref(loss), grad.ctypes.data_as(C.POINTER(C.c_double))))
     return float(loss.value), grad, retries
 
+  def make_loss_fn(self, x, y, z=None, n_valid=None):
+    """theta -> (loss, grad) closure for the ARD driver: the device tensors are resolved once and the
+    parameter struct / output buffers are reused, so one evaluation costs a ctypes call (tens of
+    microseconds of host time) instead of a dozen torch calls.  theta is in `GPHyperParams.to_vector`
+    order (categorical ls2, continuous ls2, noise, signal).  Non-finite losses return (1e300, 0)."""
+    xt, zt = self._xz(x, z)
+    yt = self._dev(y, torch.float64).reshape(-1)
+    n, dc = xt.shape
+    dk = 0 if zt is None else zt.shape[1]
+    nv = n if n_valid is None else n_valid
+    ls_k = np.zeros(max(dk, 1), np.float64)
+    ls_c = np.zeros(max(dc, 1), np.float64)
+    grad = np.zeros(dc + dk + 2, np.float64)
+    loss = C.c_double(0.0)
+    p = _lib.Params()
+    p.continuous_length_scale_squared = ls_c.ctypes.data_as(C.POINTER(C.c_double))
+    p.categorical_length_scale_squared = ls_k.ctypes.data_as(C.POINTER(C.c_double)) if dk else None
+    fn, h = self._lib.vzgp_nll_grad, self._h
+    px, pz, py = _ptr(xt), _ptr(zt), _ptr(yt)
+    pp, pl, pg = C.byref(p), C.byref(loss), grad.ctypes.data_as(C.POINTER(C.c_double))
+    keep = (xt, zt, yt, ls_k, ls_c, grad, loss, p)   # referenced by the closure: stays alive with it
+
+    def f(theta, _keep=keep):
+      theta = np.asarray(theta, np.float64)
+      ls_k[:dk] = theta[:dk]
+      ls_c[:dc] = theta[dk:dk + dc]
+      p.observation_noise_variance = float(theta[dk + dc])
+      p.signal_variance = float(theta[dk + dc + 1])
+      _lib.check('vzgp_nll_grad', fn(h, px, pz, py, n, dc, dk, nv, pp, pl, pg))
+      v = loss.value
+      if not np.isfinite(v):
+        return 1e300, np.zeros_like(theta)
+      return v, grad.copy()
+
+    return f
+
   def score(self, xs, acq: Acquisition, zs=None, with_aux: bool = False, out: Optional[dict] = None) -> dict:
     """Asynchronous on self.stream; returns device tensors {'score', ['mean','stddev','linf_distance']}."""
     xst, zst = self._xz(xs, zs)
