@@ -616,6 +616,10 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   // Step 0 runs eagerly (it sizes every workspace); the remaining steps replay one captured
   // CUDA graph of the suggest -> score -> update sequence: the iteration counter and all state
   // live in device memory, so the launches are identical and the host only enqueues graphs.
+  if (!pe && n_ens <= 1 && eagle_persistent_eligible(h, e)) {
+    // small study: the whole loop is one persistent single-CTA kernel
+    VZ_TRY(launch_eagle_persistent64(h, e, acq, steps));
+  } else {
   VZ_TRY(one_step());
   if (steps > 1) {
     const int64_t l0 = h->launches;
@@ -648,6 +652,7 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
       set_error("eagle: cudaGraphLaunch: %s", cudaGetErrorString(ce));
       return VZGP_ERR_CUDA;
     }
+  }
   }
   if (D > 0) VZ_CUDA(cudaMemcpyAsync(best_x, e.best_x, sizeof(double) * (size_t)count * D, cudaMemcpyDeviceToHost, h->stream));
   if (Dk > 0) VZ_CUDA(cudaMemcpyAsync(best_z, e.best_z, sizeof(int32_t) * (size_t)count * Dk, cudaMemcpyDeviceToHost, h->stream));

@@ -145,19 +145,19 @@ __global__ void __launch_bounds__(256) k_eagle_seed_priors(EagleDev e, const dou
 // suggest: one warp per batch fly, 8 flies per CTA.  Dynamic smem: 8*P doubles (forces) +
 // 8*D doubles (the flies' own continuous features) + 8*Dk ints.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_eagle_suggest(EagleDev e) {
-  extern __shared__ double smem[];
+template <int NWARPS>
+__device__ __forceinline__ void eagle_suggest_block(const EagleDev& e, int vblock, double* smem) {
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int P = e.P, B = e.B, D = e.D, Dk = e.Dk;
   const int t = *e.iter;
   const int nb = P / B;
   const int start = (t % nb) * B;
-  const int b = blockIdx.x * 8 + warp;
+  const int b = vblock * NWARPS + warp;
   if (b >= B) return;
   const int i = start + b;
   double* s_f = smem + (size_t)warp * P;
-  double* s_x = smem + (size_t)8 * P + warp * D;
-  int32_t* s_z = reinterpret_cast<int32_t*>(smem + (size_t)8 * P + 8 * D) + warp * Dk;
+  double* s_x = smem + (size_t)NWARPS * P + warp * D;
+  int32_t* s_z = reinterpret_cast<int32_t*>(smem + (size_t)NWARPS * P + NWARPS * D) + warp * Dk;
   for (int d = lane; d < D; d += 32) s_x[d] = e.pool[(size_t)i * D + d];
   for (int d = lane; d < Dk; d += 32) s_z[d] = e.pool_z[(size_t)i * Dk + d];
   __syncwarp();
@@ -277,6 +277,11 @@ __global__ void __launch_bounds__(256) k_eagle_suggest(EagleDev e) {
   }
 }
 
+__global__ void __launch_bounds__(256) k_eagle_suggest(EagleDev e) {
+  extern __shared__ double smem[];
+  eagle_suggest_block<8>(e, blockIdx.x, smem);
+}
+
 // ---------------------------------------------------------------------------
 // update + trim + top-count bookkeeping: single CTA.  Dynamic smem: (B+count) doubles + flags.
 // ---------------------------------------------------------------------------
@@ -284,8 +289,11 @@ __device__ __forceinline__ bool rank_better(double v, long long id, double bv, l
   return (v > bv) || (v == bv && id < bid);
 }
 
-__global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
-  extern __shared__ double smem[];
+// The first 256 threads of the CTA run the update; NAMED = true synchronises only those (named barrier 1)
+// so that the remaining warps of a larger CTA can wait at the next CTA-wide barrier.
+template <bool NAMED>
+__device__ __forceinline__ void eagle_update_block(const EagleDev& e, double* smem) {
+  auto sync = [] { if (NAMED) asm volatile("bar.sync 1, 256;\n" ::: "memory"); else __syncthreads(); };
   __shared__ double sv[256];
   __shared__ long long si[256];
   __shared__ int sp[256];
@@ -298,13 +306,13 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
   double m = -INFINITY;
   for (int b = tid; b < B; b += 256) m = fmax(m, e.batch_r[b]);
   sv[tid] = m;
-  __syncthreads();
+  sync();
   for (int o = 128; o > 0; o >>= 1) {
     if (tid < o) sv[tid] = fmax(sv[tid], sv[tid + o]);
-    __syncthreads();
+    sync();
   }
   const double new_best = fmax(*e.best_reward, sv[0]);
-  __syncthreads();
+  sync();
 
   // ---- top-count merge of (batch U best) into tmp, then copy back ----
   double* cv = smem;                                        // [B+count] ranking values
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
     cv[q] = isnan(v) ? -INFINITY : v;
     used[q] = 0;
   }
-  __syncthreads();
+  sync();
   for (int c = 0; c < count; ++c) {
     double bv = -INFINITY;
     long long bid = LLONG_MAX;
@@ -325,17 +333,17 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
       if (bp < 0 || rank_better(cv[q], id, bv, bid)) { bv = cv[q]; bid = id; bp = q; }
     }
     sv[tid] = bv; si[tid] = bid; sp[tid] = bp;
-    __syncthreads();
+    sync();
     for (int o = 128; o > 0; o >>= 1) {
       if (tid < o && sp[tid + o] >= 0 &&
           (sp[tid] < 0 || rank_better(sv[tid + o], si[tid + o], sv[tid], si[tid]))) {
         sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; sp[tid] = sp[tid + o];
       }
-      __syncthreads();
+      sync();
     }
     const int q = sp[0];
     const long long qid = si[0];
-    __syncthreads();
+    sync();
     if (q >= 0) {
       const double* src = q < B ? e.batch + (size_t)q * D : e.best_x + (size_t)(q - B) * D;
       const int32_t* srcz = q < B ? e.batch_z + (size_t)q * Dk : e.best_z + (size_t)(q - B) * Dk;
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
         used[q] = 1;
       }
     }
-    __syncthreads();
+    sync();
   }
   for (int q = tid; q < count * D; q += 256) e.best_x[q] = e.tmp_x[q];
   for (int q = tid; q < count * Dk; q += 256) e.best_z[q] = e.tmp_z[q];
@@ -384,8 +392,224 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
       e.pert[i] = pert;
     }
   }
-  __syncthreads();
+  sync();
   if (tid == 0) { *e.best_reward = new_best; *e.iter = t + 1; }
+}
+
+__global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
+  extern __shared__ double smem[];
+  eagle_update_block<false>(e, smem);
+}
+
+// ---------------------------------------------------------------------------
+// Small studies (N <= 64 trials, batch <= 64): the WHOLE optimisation loop in one persistent CTA.
+// The default designer runs 3000 sequential suggest -> score -> update iterations of 25 candidates
+// (vectorized_base.py:431-495); as separate launches each iteration costs five kernels (~25 us even
+// from a CUDA graph).  Here the model (L^-1, trial features, alpha) is staged in shared memory once,
+// every iteration calls the same suggest/update code as the stand-alone kernels and scores the batch
+// in place: K* tile -> W = K* L^-T on the DMMA pipe -> sigma^2, UCB, trust region.  Barriers are
+// __syncthreads only; the population state stays in global memory (L1/L2 resident, written and read by
+// this CTA alone).
+// ---------------------------------------------------------------------------
+constexpr int kPLD = 68;    // row stride of the two DMMA operands in smem (8-byte fragment loads conflict-free)
+constexpr int kPXLD = 66;
+
+struct PersistSmem {
+  double* eagle;   // suggest / update scratch
+  double* linv;    // [64][kPLD]
+  double* ks;      // [64][kPLD]
+  double* xt;      // [dc][kPXLD] trial features (unscaled), transposed
+  double* cand;    // [dc][kPXLD] candidates, transposed
+  double* alpha;   // [64]
+  double* mu;      // [64]
+  double* linf;    // [64]
+  double* rs4;     // [4][64] partial row sums of W^2
+  int32_t* z;      // [dk][kPXLD]
+  int32_t* cz;     // [dk][kPXLD]
+};
+
+constexpr int kPThreads = 1024;   // persistent kernel: 32 warps = one warp per batch fly (B <= 32) per pass
+
+__device__ __forceinline__ void score_tile64(const SmallModel& m, const SmallAcq& q, const PersistSmem& sm,
+                                             const double* cand, const int32_t* candz, int B, double* out_score,
+                                             int* clamp_count) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dc = m.kp.dc, dk = m.kp.dk;
+  for (int e = tid; e < 64 * dc; e += kPThreads) {
+    const int r = e / dc, d = e - r * dc;
+    sm.cand[d * kPXLD + r] = r < B ? cand[(size_t)r * dc + d] : 0.0;
+  }
+  for (int e = tid; e < 64 * dk; e += kPThreads) {
+    const int r = e / dk, k = e - r * dk;
+    sm.cz[k * kPXLD + r] = r < B ? candz[(size_t)r * dk + k] : -1;
+  }
+  __syncthreads();
+  // ---- K* tile, mean, trust-region distance: thread = (candidate i, 4 trials) ----
+  {
+    const int i = tid >> 4, j0 = (tid & 15) * 4;
+    double d2[4], lf[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { d2[c] = 0.0; lf[c] = 0.0; }
+    if ((i & ~1) >= B) {              // both candidate rows of this warp are padding
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sm.ks[i * kPLD + j0 + c] = 0.0;
+    } else {
+    if (i < B) {
+      for (int d = 0; d < dc; ++d) {
+        const double av = sm.cand[d * kPXLD + i], w = m.kp.inv_ls2_c[d];
+        const bool in_tr = q.want_linf && q.tr_mask[d];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double df = av - sm.xt[d * kPXLD + j0 + c];
+          d2[c] = fma(df * df, w, d2[c]);
+          if (in_tr) lf[c] = fmax(lf[c], fabs(df));
+        }
+      }
+      for (int k = 0; k < dk; ++k) {
+        const int av = sm.cz[k * kPXLD + i];
+        const double w = m.kp.inv_ls2_k[k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d2[c] += (av != sm.z[k * kPXLD + j0 + c]) ? w : 0.0;
+      }
+    }
+    double mu = 0.0, lmin = INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = j0 + c;
+      const double kv = (i < B && j < m.n_valid) ? matern52(d2[c], m.kp.sf2) : 0.0;
+      sm.ks[i * kPLD + j] = kv;
+      mu = fma(kv, sm.alpha[j], mu);
+      if (j < q.tr_rows) lmin = fmin(lmin, lf[c]);
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      mu += __shfl_xor_sync(0xffffffffu, mu, o);
+      lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    }
+    if ((tid & 15) == 0) { sm.mu[i] = mu; sm.linf[i] = lmin; }
+    }
+  }
+  __syncthreads();
+  // ---- W = K* Linv^T (lower triangular: k <= j), row sums of W^2.  Warp = (8 candidates, 2 column
+  // tiles nt and 7 - nt: balanced triangular work); partial row sums combined through smem ----
+  {
+    const int mt = warp >> 2, pr = warp & 3;          // 8 m-tiles x 4 column-tile pairs
+    if (mt * 8 < B) {
+      const int fr = lane >> 2, fk = lane & 3;
+      const double* Ar = sm.ks + (mt * 8 + fr) * kPLD + fk;
+      double rsum = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nt = h == 0 ? pr : 7 - pr;
+        const double* Br = sm.linv + (nt * 8 + fr) * kPLD + fk;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        for (int ks = 0; ks < 2 * nt + 2; ks += 2) {
+          dmma_8x8x4(a0, a1, Ar[4 * ks], Br[4 * ks]);
+          dmma_8x8x4(b0, b1, Ar[4 * ks + 4], Br[4 * ks + 4]);
+        }
+        const double w0 = a0 + b0, w1 = a1 + b1;
+        rsum = fma(w0, w0, rsum);
+        rsum = fma(w1, w1, rsum);
+      }
+      rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
+      rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
+      if (fk == 0) sm.rs4[pr * 64 + mt * 8 + fr] = rsum;
+    }
+  }
+  __syncthreads();
+  if (tid < B) {
+    const double rs = (sm.rs4[tid] + sm.rs4[64 + tid]) + (sm.rs4[128 + tid] + sm.rs4[192 + tid]);
+    double var = m.kp.sf2 - rs + m.sn2;
+    if (var < 0.0) { var = 0.0; atomicAdd(clamp_count, 1); }
+    const double sd = sqrt(var);
+    double sc = fma(q.coef, sd, sm.mu[tid]);
+    if (q.apply_tr) {
+      const double dist = sm.linf[tid];
+      const bool inside = (q.tr_strict ? (dist < q.radius) : (dist <= q.radius)) || (q.radius > 0.5);
+      sc = inside ? sc : (-1e4 - dist);
+    }
+    out_score[tid] = sc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPThreads) k_eagle_persistent64(const EagleDev eg, SmallModel m, SmallAcq q, int steps,
+                                                                  size_t eagle_scratch_doubles, int* clamp_count) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int dc = m.kp.dc, dk = m.kp.dk;
+  PersistSmem sm;
+  sm.eagle = smem;
+  sm.linv = smem + eagle_scratch_doubles;
+  sm.ks = sm.linv + 64 * kPLD;
+  sm.xt = sm.ks + 64 * kPLD;
+  sm.cand = sm.xt + dc * kPXLD;
+  sm.alpha = sm.cand + dc * kPXLD;
+  sm.mu = sm.alpha + 64;
+  sm.linf = sm.mu + 64;
+  sm.rs4 = sm.linf + 64;
+  sm.z = reinterpret_cast<int32_t*>(sm.rs4 + 256);
+  sm.cz = sm.z + dk * kPXLD;
+  // stage the model once (np == 64)
+  for (int i = tid; i < 64 * 64; i += kPThreads) sm.linv[(i >> 6) * kPLD + (i & 63)] = m.Linv[i];
+  for (int i = tid; i < dc * 64; i += kPThreads) sm.xt[(i >> 6) * kPXLD + (i & 63)] = m.XTu[i];
+  for (int i = tid; i < 64 * dk; i += kPThreads) {
+    const int r = i / dk, k = i - r * dk;
+    sm.z[k * kPXLD + r] = m.Z[i];
+  }
+  if (tid < 64) sm.alpha[tid] = m.alpha[tid];
+  // The population state moves into shared memory for the duration of the loop (generic pointers:
+  // suggest / update run unchanged); every iteration would otherwise pay several dependent L2 round
+  // trips for data this CTA wrote a moment ago.  best_* / tmp_* (touched once per step) stay global.
+  __shared__ EagleDev es;      // the same descriptor with the state pointers redirected to shared memory
+  if (tid == 0) {
+    es = eg;
+    double* p = reinterpret_cast<double*>(sm.cz + dk * kPXLD + ((dk * kPXLD) & 1));
+    es.pool = p; p += (size_t)eg.P * eg.D;
+    es.rewards = p; p += eg.P;
+    es.pert = p; p += eg.P;
+    es.best_reward = p; p += 2;
+    es.batch = p; p += (size_t)eg.B * eg.D;
+    es.batch_r = p; p += eg.B;
+    int32_t* ip = reinterpret_cast<int32_t*>(p);
+    es.iter = ip; ip += 4;
+    es.pool_z = ip; ip += (size_t)eg.P * eg.Dk;
+    es.batch_z = ip;
+  }
+  __syncthreads();
+  const EagleDev& e = es;
+  for (int i = tid; i < e.P * e.D; i += kPThreads) e.pool[i] = eg.pool[i];
+  for (int i = tid; i < e.P; i += kPThreads) { e.rewards[i] = eg.rewards[i]; e.pert[i] = eg.pert[i]; }
+  for (int i = tid; i < e.P * e.Dk; i += kPThreads) e.pool_z[i] = eg.pool_z[i];
+  if (tid == 0) { *e.best_reward = *eg.best_reward; *e.iter = *eg.iter; }
+  __syncthreads();
+  constexpr int kW = kPThreads / 32;
+  const int nvb = (e.B + kW - 1) / kW;
+#ifdef VZ_EAGLE_TIMING
+  long long c_s = 0, c_c = 0, c_u = 0, t0, t1;
+#define VZ_ET(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
+  t0 = clock64();
+#else
+#define VZ_ET(acc) do {} while (0)
+#endif
+  for (int it = 0; it < steps; ++it) {
+    for (int vb = 0; vb < nvb; ++vb) eagle_suggest_block<kW>(e, vb, sm.eagle);
+    __syncthreads();
+    VZ_ET(c_s);
+    score_tile64(m, q, sm, e.batch, e.batch_z, e.B, e.batch_r, clamp_count);
+    VZ_ET(c_c);
+    if (tid < 256) eagle_update_block<true>(e, sm.eagle);
+    __syncthreads();
+    VZ_ET(c_u);
+  }
+  for (int i = tid; i < e.P * e.D; i += kPThreads) eg.pool[i] = e.pool[i];
+  for (int i = tid; i < e.P; i += kPThreads) { eg.rewards[i] = e.rewards[i]; eg.pert[i] = e.pert[i]; }
+  for (int i = tid; i < e.P * e.Dk; i += kPThreads) eg.pool_z[i] = e.pool_z[i];
+  if (tid == 0) { *eg.best_reward = *e.best_reward; *eg.iter = *e.iter; }
+#ifdef VZ_EAGLE_TIMING
+  if (tid == 0) printf("eagle persistent: steps %d, cycles/step suggest %lld score %lld update %lld\n", steps,
+                       c_s / steps, c_c / steps, c_u / steps);
+#endif
 }
 
 // Z[m, k] = uniform category of feature k for candidate index_base+m (RandomVectorizedStrategy).
@@ -446,6 +670,45 @@ int launch_eagle_update(vzgp_handle* h, const EagleDev& e) {
   h->launches++;
   return 0;
 }
+static size_t eagle_persistent_state_bytes(const EagleDev& e) {
+  return sizeof(double) * ((size_t)e.P * e.D + 2 * (size_t)e.P + 2 + (size_t)e.B * e.D + e.B) +
+         sizeof(int32_t) * (4 + (size_t)e.P * e.Dk + (size_t)e.B * e.Dk) + 16;
+}
+
+bool eagle_persistent_eligible(const vzgp_handle* h, const EagleDev& e) {
+  static const bool enabled = [] { const char* v = getenv("VZGP_EAGLE_PERSISTENT"); return !(v && v[0] == '0'); }();
+  return enabled && h->np == 64 && e.B <= 64 && eagle_persistent_state_bytes(e) <= 96 * 1024;
+}
+
+int launch_eagle_persistent64(vzgp_handle* h, const EagleDev& e, const vzgp_acq* acq, int steps) {
+  SmallModel m;
+  m.XTu = h->XT.as<double>() + (size_t)h->dc * h->np;
+  m.Z = h->Z.as<int32_t>();
+  m.Linv = h->Linv.as<double>();
+  m.alpha = h->alpha.as<double>();
+  m.kp = h->kp; m.sn2 = h->sn2; m.n_valid = h->n_valid;
+  SmallAcq q;
+  q.coef = acq->ucb_coefficient;
+  q.radius = acq->trust_radius;
+  q.apply_tr = acq->use_trust_region ? 1 : 0;
+  q.tr_rows = (acq->tr_rows > 0 && acq->tr_rows < h->n_valid) ? acq->tr_rows : h->n_valid;
+  q.tr_strict = acq->tr_strict ? 1 : 0;
+  q.want_linf = (q.apply_tr && q.radius <= 0.5) ? 1 : 0;
+  for (int d = 0; d < kMaxDc; ++d)
+    q.tr_mask[d] = (d < h->dc) ? (acq->tr_dim_mask ? (acq->tr_dim_mask[d] ? 1 : 0) : 1) : 0;
+  const size_t es = sizeof(double) * (size_t)(kPThreads / 32) * (e.P + e.D) + sizeof(int32_t) * (kPThreads / 32) * (size_t)(e.Dk + 2);
+  const size_t eu = eagle_update_smem(e);
+  const size_t scratch = ((es > eu ? es : eu) + 15) / 16 * 2;   // doubles, 16-byte multiple
+  const size_t sm = sizeof(double) * (scratch + 2 * 64 * kPLD + 2 * (size_t)h->dc * kPXLD + 3 * 64 + 256) +
+                    sizeof(int32_t) * (2 * (size_t)h->dk * kPXLD + 2) + eagle_persistent_state_bytes(e);
+  if (sm > 227 * 1024) { set_error("persistent eagle kernel needs %zu bytes of shared memory", sm); return VZGP_ERR_UNSUPPORTED; }
+  VZ_CUDA(cudaFuncSetAttribute(k_eagle_persistent64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_eagle_persistent64<<<1, kPThreads, sm, h->stream>>>(e, m, q, steps, scratch, h->small.as<int>());
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+
 int launch_random_fill_cat(vzgp_handle* h, int32_t* Z, int64_t M, int dk, const int* sizes, int64_t index_base,
                            uint64_t seed, uint32_t stream) {
   const int64_t total = M * dk;

@@ -86,6 +86,25 @@ struct EagleDev {
   vzgp_eagle_config cfg;
   uint64_t seed;
 };
+// Single-CTA persistent Eagle loop for N <= 64 trials (eagle.cu).
+struct SmallModel {
+  const double* XTu;     // [dc][64] unscaled trial features, transposed
+  const int32_t* Z;      // [64][dk]
+  const double* Linv;    // [64][64]
+  const double* alpha;   // [64]
+  KernelParams kp;
+  double sn2;
+  int n_valid;
+};
+struct SmallAcq {
+  double coef, radius;
+  int apply_tr, tr_rows, tr_strict, want_linf;
+  uint8_t tr_mask[kMaxDc];
+};
+bool eagle_persistent_eligible(const vzgp_handle* h, const EagleDev& e);
+int launch_eagle_persistent64(vzgp_handle* h, const EagleDev& e, const vzgp_acq* acq, int steps);
+size_t eagle_suggest_smem(const EagleDev& e);
+size_t eagle_update_smem(const EagleDev& e);
 int launch_eagle_init(vzgp_handle* h, const EagleDev& e);
 int launch_eagle_seed_priors(vzgp_handle* h, const EagleDev& e, const double* prior, const int32_t* prior_z,
                              const double* prior_r, int n, int* ord, double* chosen_r);

@@ -79,14 +79,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
-// D(8x8) += A(8x4, row) * B(4x8, col); lane l holds A[l/4][l%4], B[k=l%4][n=l/4],
-// D[l/4][2*(l%4)+{0,1}]  (PTX ISA, mma.m8n8k4 .f64 fragment layout).
-__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-
 // ---- mbarrier / TMA (cp.async.bulk.tensor) primitives --------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
