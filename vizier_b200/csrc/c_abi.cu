@@ -616,9 +616,9 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   // Step 0 runs eagerly (it sizes every workspace); the remaining steps replay one captured
   // CUDA graph of the suggest -> score -> update sequence: the iteration counter and all state
   // live in device memory, so the launches are identical and the host only enqueues graphs.
-  if (!pe && n_ens <= 1 && eagle_persistent_eligible(h, e)) {
+  if (n_ens <= 1 && eagle_persistent_eligible(h, pe ? hB : nullptr, e)) {
     // small study: the whole loop is one persistent single-CTA kernel
-    VZ_TRY(launch_eagle_persistent64(h, e, acq, steps));
+    VZ_TRY(launch_eagle_persistent64(h, pe ? hB : nullptr, e, acq, pe, steps));
   } else {
   VZ_TRY(one_step());
   if (steps > 1) {

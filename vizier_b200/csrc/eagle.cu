@@ -414,27 +414,41 @@ __global__ void __launch_bounds__(256) k_eagle_update(EagleDev e) {
 constexpr int kPLD = 68;    // row stride of the two DMMA operands in smem (8-byte fragment loads conflict-free)
 constexpr int kPXLD = 66;
 
+constexpr int kPThreads = 1024;   // persistent kernel: 32 warps = one warp per batch fly (B <= 32) per pass
+
+struct ModelSmem {   // one GP staged in shared memory (np == 64)
+  double* linv;    // [64][kPLD]
+  double* xt;      // [dc][kPXLD] trial features (unscaled), transposed
+  double* alpha;   // [64]
+  int32_t* z;      // [dk][kPXLD]
+};
 struct PersistSmem {
   double* eagle;   // suggest / update scratch
-  double* linv;    // [64][kPLD]
-  double* ks;      // [64][kPLD]
-  double* xt;      // [dc][kPXLD] trial features (unscaled), transposed
+  ModelSmem a, b;  // b only with the GP-UCB-PE acquisition
+  double* ks;      // [64][kPLD] K* tile of the model being evaluated
   double* cand;    // [dc][kPXLD] candidates, transposed
-  double* alpha;   // [64]
-  double* mu;      // [64]
-  double* linf;    // [64]
+  double* mu;      // [2][64] posterior mean of model a / b
+  double* sd;      // [2][64] posterior stddev
+  double* linf;    // [64] trust-region distance (model a for UCB, model b for UCB-PE)
   double* rs4;     // [4][64] partial row sums of W^2
-  int32_t* z;      // [dk][kPXLD]
   int32_t* cz;     // [dk][kPXLD]
 };
 
-constexpr int kPThreads = 1024;   // persistent kernel: 32 warps = one warp per batch fly (B <= 32) per pass
+__device__ __forceinline__ void stage_model64(const SmallModel& m, const ModelSmem& ms) {
+  const int tid = threadIdx.x, dc = m.kp.dc, dk = m.kp.dk;
+  for (int i = tid; i < 64 * 64; i += kPThreads) ms.linv[(i >> 6) * kPLD + (i & 63)] = m.Linv[i];
+  for (int i = tid; i < dc * 64; i += kPThreads) ms.xt[(i >> 6) * kPXLD + (i & 63)] = m.XTu[i];
+  for (int i = tid; i < 64 * dk; i += kPThreads) {
+    const int r = i / dk, k = i - r * dk;
+    ms.z[k * kPXLD + r] = m.Z[i];
+  }
+  if (tid < 64) ms.alpha[tid] = m.alpha[tid];
+}
 
-__device__ __forceinline__ void score_tile64(const SmallModel& m, const SmallAcq& q, const PersistSmem& sm,
-                                             const double* cand, const int32_t* candz, int B, double* out_score,
-                                             int* clamp_count) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int dc = m.kp.dc, dk = m.kp.dk;
+// Candidates of the current batch, transposed into shared memory (ends with a barrier).
+__device__ __forceinline__ void stage_candidates64(const PersistSmem& sm, int dc, int dk, const double* cand,
+                                                   const int32_t* candz, int B) {
+  const int tid = threadIdx.x;
   for (int e = tid; e < 64 * dc; e += kPThreads) {
     const int r = e / dc, d = e - r * dc;
     sm.cand[d * kPXLD + r] = r < B ? cand[(size_t)r * dc + d] : 0.0;
@@ -444,6 +458,16 @@ __device__ __forceinline__ void score_tile64(const SmallModel& m, const SmallAcq
     sm.cz[k * kPXLD + r] = r < B ? candz[(size_t)r * dk + k] : -1;
   }
   __syncthreads();
+}
+
+// Posterior of one staged model at the staged candidates: mu_out[i], sd_out[i] and (if linf_out) the
+// trust-region distance to the first tr_rows trials.  Ends with a barrier.
+__device__ __forceinline__ void posterior_tile64(const SmallModel& m, const ModelSmem& ms, const PersistSmem& sm,
+                                                 int B, const SmallAcq& q, double* mu_out, double* sd_out,
+                                                 double* linf_out, int* clamp_count) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dc = m.kp.dc, dk = m.kp.dk;
+  const bool want_linf = linf_out != nullptr;
   // ---- K* tile, mean, trust-region distance: thread = (candidate i, 4 trials) ----
   {
     const int i = tid >> 4, j0 = (tid & 15) * 4;
@@ -454,39 +478,42 @@ __device__ __forceinline__ void score_tile64(const SmallModel& m, const SmallAcq
 #pragma unroll
       for (int c = 0; c < 4; ++c) sm.ks[i * kPLD + j0 + c] = 0.0;
     } else {
-    if (i < B) {
-      for (int d = 0; d < dc; ++d) {
-        const double av = sm.cand[d * kPXLD + i], w = m.kp.inv_ls2_c[d];
-        const bool in_tr = q.want_linf && q.tr_mask[d];
+      if (i < B) {
+        for (int d = 0; d < dc; ++d) {
+          const double av = sm.cand[d * kPXLD + i], w = m.kp.inv_ls2_c[d];
+          const bool in_tr = want_linf && q.tr_mask[d];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double df = av - sm.xt[d * kPXLD + j0 + c];
-          d2[c] = fma(df * df, w, d2[c]);
-          if (in_tr) lf[c] = fmax(lf[c], fabs(df));
+          for (int c = 0; c < 4; ++c) {
+            const double df = av - ms.xt[d * kPXLD + j0 + c];
+            d2[c] = fma(df * df, w, d2[c]);
+            if (in_tr) lf[c] = fmax(lf[c], fabs(df));
+          }
+        }
+        for (int k = 0; k < dk; ++k) {
+          const int av = sm.cz[k * kPXLD + i];
+          const double w = m.kp.inv_ls2_k[k];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) d2[c] += (av != ms.z[k * kPXLD + j0 + c]) ? w : 0.0;
         }
       }
-      for (int k = 0; k < dk; ++k) {
-        const int av = sm.cz[k * kPXLD + i];
-        const double w = m.kp.inv_ls2_k[k];
+      double mu = 0.0, lmin = INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) d2[c] += (av != sm.z[k * kPXLD + j0 + c]) ? w : 0.0;
+      for (int c = 0; c < 4; ++c) {
+        const int j = j0 + c;
+        const double kv = (i < B && j < m.n_valid) ? matern52(d2[c], m.kp.sf2) : 0.0;
+        sm.ks[i * kPLD + j] = kv;
+        mu = fma(kv, ms.alpha[j], mu);
+        if (j < q.tr_rows) lmin = fmin(lmin, lf[c]);
       }
-    }
-    double mu = 0.0, lmin = INFINITY;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int j = j0 + c;
-      const double kv = (i < B && j < m.n_valid) ? matern52(d2[c], m.kp.sf2) : 0.0;
-      sm.ks[i * kPLD + j] = kv;
-      mu = fma(kv, sm.alpha[j], mu);
-      if (j < q.tr_rows) lmin = fmin(lmin, lf[c]);
-    }
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-      mu += __shfl_xor_sync(0xffffffffu, mu, o);
-      lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-    }
-    if ((tid & 15) == 0) { sm.mu[i] = mu; sm.linf[i] = lmin; }
+      for (int o = 1; o < 16; o <<= 1) {
+        mu += __shfl_xor_sync(0xffffffffu, mu, o);
+        lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+      }
+      if ((tid & 15) == 0) {
+        mu_out[i] = mu;
+        if (want_linf) linf_out[i] = lmin;
+      }
     }
   }
   __syncthreads();
@@ -501,7 +528,7 @@ __device__ __forceinline__ void score_tile64(const SmallModel& m, const SmallAcq
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int nt = h == 0 ? pr : 7 - pr;
-        const double* Br = sm.linv + (nt * 8 + fr) * kPLD + fk;
+        const double* Br = ms.linv + (nt * 8 + fr) * kPLD + fk;
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
         for (int ks = 0; ks < 2 * nt + 2; ks += 2) {
           dmma_8x8x4(a0, a1, Ar[4 * ks], Br[4 * ks]);
@@ -521,50 +548,87 @@ __device__ __forceinline__ void score_tile64(const SmallModel& m, const SmallAcq
     const double rs = (sm.rs4[tid] + sm.rs4[64 + tid]) + (sm.rs4[128 + tid] + sm.rs4[192 + tid]);
     double var = m.kp.sf2 - rs + m.sn2;
     if (var < 0.0) { var = 0.0; atomicAdd(clamp_count, 1); }
-    const double sd = sqrt(var);
-    double sc = fma(q.coef, sd, sm.mu[tid]);
-    if (q.apply_tr) {
-      const double dist = sm.linf[tid];
-      const bool inside = (q.tr_strict ? (dist < q.radius) : (dist <= q.radius)) || (q.radius > 0.5);
-      sc = inside ? sc : (-1e4 - dist);
-    }
-    out_score[tid] = sc;
+    sd_out[tid] = sqrt(var);
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kPThreads) k_eagle_persistent64(const EagleDev eg, SmallModel m, SmallAcq q, int steps,
-                                                                  size_t eagle_scratch_doubles, int* clamp_count) {
+// Acquisition of the batch from the staged model(s): UCB + trust region (acquisitions.py:152-225) or the
+// GP-UCB-PE combination of models a (completed trials) and b (completed + pending), gp_ucb_pe.py:344-492.
+__device__ __forceinline__ void score_batch64(const SmallModel& ma, const SmallModel& mb, const SmallAcq& q,
+                                              const PersistSmem& sm, const double* cand, const int32_t* candz, int B,
+                                              double* out_score, int* clamp_count) {
+  const int tid = threadIdx.x;
+  stage_candidates64(sm, ma.kp.dc, ma.kp.dk, cand, candz, B);
+  if (q.pe_mode < 0) {
+    posterior_tile64(ma, sm.a, sm, B, q, sm.mu, sm.sd, q.want_linf ? sm.linf : nullptr, clamp_count);
+    if (tid < B) {
+      double sc = fma(q.coef, sm.sd[tid], sm.mu[tid]);
+      if (q.apply_tr) {
+        const double dist = sm.linf[tid];
+        const bool inside = (q.tr_strict ? (dist < q.radius) : (dist <= q.radius)) || (q.radius > 0.5);
+        sc = inside ? sc : (-1e4 - dist);
+      }
+      out_score[tid] = sc;
+    }
+  } else {
+    posterior_tile64(ma, sm.a, sm, B, q, sm.mu, sm.sd, nullptr, clamp_count);
+    posterior_tile64(mb, sm.b, sm, B, q, sm.mu + 64, sm.sd + 64, q.want_linf ? sm.linf : nullptr, clamp_count);
+    if (tid < B) {
+      double acq;
+      if (q.pe_mode == 0) {
+        acq = fma(q.coef, sm.sd[64 + tid], sm.mu[tid]);
+      } else {
+        const double explore_ucb = fma(sm.sd[tid], q.explore, sm.mu[tid]);
+        acq = sm.sd[64 + tid] + q.penalty * fmin(explore_ucb - q.threshold, 0.0);
+      }
+      if (q.want_linf) {
+        const double dist = sm.linf[tid];
+        const bool inside = (dist < q.radius) || (q.radius > 0.5);
+        acq = inside ? acq : (-1e4 - dist);
+      }
+      out_score[tid] = acq;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPThreads) k_eagle_persistent64(const EagleDev eg, SmallModel m, SmallModel mb,
+                                                                  SmallAcq q, int steps, size_t eagle_scratch_doubles,
+                                                                  int* clamp_count) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int dc = m.kp.dc, dk = m.kp.dk;
+  const bool two = q.pe_mode >= 0;
   PersistSmem sm;
-  sm.eagle = smem;
-  sm.linv = smem + eagle_scratch_doubles;
-  sm.ks = sm.linv + 64 * kPLD;
-  sm.xt = sm.ks + 64 * kPLD;
-  sm.cand = sm.xt + dc * kPXLD;
-  sm.alpha = sm.cand + dc * kPXLD;
-  sm.mu = sm.alpha + 64;
-  sm.linf = sm.mu + 64;
-  sm.rs4 = sm.linf + 64;
-  sm.z = reinterpret_cast<int32_t*>(sm.rs4 + 256);
-  sm.cz = sm.z + dk * kPXLD;
-  // stage the model once (np == 64)
-  for (int i = tid; i < 64 * 64; i += kPThreads) sm.linv[(i >> 6) * kPLD + (i & 63)] = m.Linv[i];
-  for (int i = tid; i < dc * 64; i += kPThreads) sm.xt[(i >> 6) * kPXLD + (i & 63)] = m.XTu[i];
-  for (int i = tid; i < 64 * dk; i += kPThreads) {
-    const int r = i / dk, k = i - r * dk;
-    sm.z[k * kPXLD + r] = m.Z[i];
-  }
-  if (tid < 64) sm.alpha[tid] = m.alpha[tid];
+  double* p = smem;
+  sm.eagle = p; p += eagle_scratch_doubles;
+  sm.a.linv = p; p += 64 * kPLD;
+  sm.a.xt = p; p += dc * kPXLD;
+  sm.a.alpha = p; p += 64;
+  sm.b.linv = p; p += two ? 64 * kPLD : 0;
+  sm.b.xt = p; p += two ? dc * kPXLD : 0;
+  sm.b.alpha = p; p += two ? 64 : 0;
+  sm.ks = p; p += 64 * kPLD;
+  sm.cand = p; p += dc * kPXLD;
+  sm.mu = p; p += 128;
+  sm.sd = p; p += 128;
+  sm.linf = p; p += 64;
+  sm.rs4 = p; p += 256;
+  int32_t* ip0 = reinterpret_cast<int32_t*>(p);
+  sm.a.z = ip0; ip0 += dk * kPXLD;
+  sm.b.z = ip0; ip0 += two ? dk * kPXLD : 0;
+  sm.cz = ip0; ip0 += dk * kPXLD;
+  ip0 += (reinterpret_cast<uintptr_t>(ip0) & 7) ? 1 : 0;
+  stage_model64(m, sm.a);
+  if (two) stage_model64(mb, sm.b);
   // The population state moves into shared memory for the duration of the loop (generic pointers:
   // suggest / update run unchanged); every iteration would otherwise pay several dependent L2 round
   // trips for data this CTA wrote a moment ago.  best_* / tmp_* (touched once per step) stay global.
   __shared__ EagleDev es;      // the same descriptor with the state pointers redirected to shared memory
   if (tid == 0) {
     es = eg;
-    double* p = reinterpret_cast<double*>(sm.cz + dk * kPXLD + ((dk * kPXLD) & 1));
+    double* p = reinterpret_cast<double*>(ip0);
     es.pool = p; p += (size_t)eg.P * eg.D;
     es.rewards = p; p += eg.P;
     es.pert = p; p += eg.P;
@@ -596,7 +660,7 @@ __global__ void __launch_bounds__(kPThreads) k_eagle_persistent64(const EagleDev
     for (int vb = 0; vb < nvb; ++vb) eagle_suggest_block<kW>(e, vb, sm.eagle);
     __syncthreads();
     VZ_ET(c_s);
-    score_tile64(m, q, sm, e.batch, e.batch_z, e.B, e.batch_r, clamp_count);
+    score_batch64(m, mb, q, sm, e.batch, e.batch_z, e.B, e.batch_r, clamp_count);
     VZ_ET(c_c);
     if (tid < 256) eagle_update_block<true>(e, sm.eagle);
     __syncthreads();
@@ -675,35 +739,55 @@ static size_t eagle_persistent_state_bytes(const EagleDev& e) {
          sizeof(int32_t) * (4 + (size_t)e.P * e.Dk + (size_t)e.B * e.Dk) + 16;
 }
 
-bool eagle_persistent_eligible(const vzgp_handle* h, const EagleDev& e) {
+bool eagle_persistent_eligible(const vzgp_handle* h, const vzgp_handle* hB, const EagleDev& e) {
   static const bool enabled = [] { const char* v = getenv("VZGP_EAGLE_PERSISTENT"); return !(v && v[0] == '0'); }();
-  return enabled && h->np == 64 && e.B <= 64 && eagle_persistent_state_bytes(e) <= 96 * 1024;
+  return enabled && h->np == 64 && (hB == nullptr || hB->np == 64) && e.B <= 64 &&
+         eagle_persistent_state_bytes(e) <= 64 * 1024;
 }
 
-int launch_eagle_persistent64(vzgp_handle* h, const EagleDev& e, const vzgp_acq* acq, int steps) {
+static SmallModel small_model_of(const vzgp_handle* h) {
   SmallModel m;
   m.XTu = h->XT.as<double>() + (size_t)h->dc * h->np;
   m.Z = h->Z.as<int32_t>();
   m.Linv = h->Linv.as<double>();
   m.alpha = h->alpha.as<double>();
   m.kp = h->kp; m.sn2 = h->sn2; m.n_valid = h->n_valid;
+  return m;
+}
+
+// acq (UCB on h) or pe (GP-UCB-PE on h = model A and hB = model B): exactly one is non-null.
+int launch_eagle_persistent64(vzgp_handle* h, vzgp_handle* hB, const EagleDev& e, const vzgp_acq* acq,
+                              const vzgp_pe_params* pe, int steps) {
+  const SmallModel m = small_model_of(h);
+  const SmallModel mb = hB ? small_model_of(hB) : m;
+  const vzgp_handle* ht = pe ? hB : h;     // the trust region is measured on this model's trials
   SmallAcq q;
-  q.coef = acq->ucb_coefficient;
-  q.radius = acq->trust_radius;
-  q.apply_tr = acq->use_trust_region ? 1 : 0;
-  q.tr_rows = (acq->tr_rows > 0 && acq->tr_rows < h->n_valid) ? acq->tr_rows : h->n_valid;
-  q.tr_strict = acq->tr_strict ? 1 : 0;
+  memset(&q, 0, sizeof(q));
+  const uint8_t* mask;
+  int tr_rows;
+  if (pe) {
+    q.pe_mode = pe->mode; q.coef = pe->ucb_coefficient; q.explore = pe->explore_coefficient;
+    q.penalty = pe->penalty_coefficient; q.threshold = pe->threshold;
+    q.radius = pe->trust_radius; q.apply_tr = pe->use_trust_region ? 1 : 0; q.tr_strict = 1;
+    mask = pe->tr_dim_mask; tr_rows = pe->tr_rows;
+  } else {
+    q.pe_mode = -1; q.coef = acq->ucb_coefficient;
+    q.radius = acq->trust_radius; q.apply_tr = acq->use_trust_region ? 1 : 0; q.tr_strict = acq->tr_strict ? 1 : 0;
+    mask = acq->tr_dim_mask; tr_rows = acq->tr_rows;
+  }
+  q.tr_rows = (tr_rows > 0 && tr_rows < ht->n_valid) ? tr_rows : ht->n_valid;
   q.want_linf = (q.apply_tr && q.radius <= 0.5) ? 1 : 0;
-  for (int d = 0; d < kMaxDc; ++d)
-    q.tr_mask[d] = (d < h->dc) ? (acq->tr_dim_mask ? (acq->tr_dim_mask[d] ? 1 : 0) : 1) : 0;
+  for (int d = 0; d < kMaxDc; ++d) q.tr_mask[d] = (d < h->dc) ? (mask ? (mask[d] ? 1 : 0) : 1) : 0;
   const size_t es = sizeof(double) * (size_t)(kPThreads / 32) * (e.P + e.D) + sizeof(int32_t) * (kPThreads / 32) * (size_t)(e.Dk + 2);
   const size_t eu = eagle_update_smem(e);
   const size_t scratch = ((es > eu ? es : eu) + 15) / 16 * 2;   // doubles, 16-byte multiple
-  const size_t sm = sizeof(double) * (scratch + 2 * 64 * kPLD + 2 * (size_t)h->dc * kPXLD + 3 * 64 + 256) +
-                    sizeof(int32_t) * (2 * (size_t)h->dk * kPXLD + 2) + eagle_persistent_state_bytes(e);
+  const int nm = pe ? 2 : 1;
+  const size_t sm = sizeof(double) * (scratch + (size_t)(nm + 1) * 64 * kPLD + (size_t)(nm + 1) * h->dc * kPXLD +
+                                      (size_t)nm * 64 + 128 + 128 + 64 + 256) +
+                    sizeof(int32_t) * ((size_t)(nm + 1) * h->dk * kPXLD + 2) + eagle_persistent_state_bytes(e);
   if (sm > 227 * 1024) { set_error("persistent eagle kernel needs %zu bytes of shared memory", sm); return VZGP_ERR_UNSUPPORTED; }
   VZ_CUDA(cudaFuncSetAttribute(k_eagle_persistent64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_eagle_persistent64<<<1, kPThreads, sm, h->stream>>>(e, m, q, steps, scratch, h->small.as<int>());
+  k_eagle_persistent64<<<1, kPThreads, sm, h->stream>>>(e, m, mb, q, steps, scratch, h->small.as<int>());
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;

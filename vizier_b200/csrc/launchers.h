@@ -98,11 +98,14 @@ struct SmallModel {
 };
 struct SmallAcq {
   double coef, radius;
+  double explore, penalty, threshold;   // GP-UCB-PE
+  int pe_mode;                          // -1: UCB on one model; 0 / 1: GP-UCB-PE modes (vzgp_pe_params.mode)
   int apply_tr, tr_rows, tr_strict, want_linf;
   uint8_t tr_mask[kMaxDc];
 };
-bool eagle_persistent_eligible(const vzgp_handle* h, const EagleDev& e);
-int launch_eagle_persistent64(vzgp_handle* h, const EagleDev& e, const vzgp_acq* acq, int steps);
+bool eagle_persistent_eligible(const vzgp_handle* h, const vzgp_handle* hB, const EagleDev& e);
+int launch_eagle_persistent64(vzgp_handle* h, vzgp_handle* hB, const EagleDev& e, const vzgp_acq* acq,
+                              const vzgp_pe_params* pe, int steps);
 size_t eagle_suggest_smem(const EagleDev& e);
 size_t eagle_update_smem(const EagleDev& e);
 int launch_eagle_init(vzgp_handle* h, const EagleDev& e);
