@@ -5,7 +5,7 @@ import numpy as np, torch
 from vizier_b200 import gp, _lib
 from vizier_b200.multi_gpu import trust_radius
 rng = np.random.default_rng(0)
-for n, d in ((50, 4), (60, 20)):
+for n, d in ((50, 4), (60, 20), (1000, 20), (200, 20)):
   x = rng.uniform(size=(n, d)); y = rng.normal(size=n)
   dev = gp.DeviceGP(0)
   dev.fit(x, y, gp.GPHyperParams(1.0, np.full(d, 0.5), 1e-3))

@@ -619,6 +619,9 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   if (n_ens <= 1 && eagle_persistent_eligible(h, pe ? hB : nullptr, e)) {
     // small study: the whole loop is one persistent single-CTA kernel
     VZ_TRY(launch_eagle_persistent64(h, pe ? hB : nullptr, e, acq, pe, steps));
+  } else if (n_ens <= 1 && eagle_grid_eligible(h, pe ? hB : nullptr, e)) {
+    // mid-size study: one cooperative launch, phases separated by grid barriers
+    VZ_TRY(launch_eagle_grid(h, pe ? hB : nullptr, e, acq, pe, steps));
   } else {
   VZ_TRY(one_step());
   if (steps > 1) {

@@ -106,6 +106,10 @@ struct SmallAcq {
 bool eagle_persistent_eligible(const vzgp_handle* h, const vzgp_handle* hB, const EagleDev& e);
 int launch_eagle_persistent64(vzgp_handle* h, vzgp_handle* hB, const EagleDev& e, const vzgp_acq* acq,
                               const vzgp_pe_params* pe, int steps);
+// Multi-CTA persistent Eagle loop (eagle_grid.cu): cooperative launch, batch <= 512 candidates.
+bool eagle_grid_eligible(const vzgp_handle* h, const vzgp_handle* hB, const EagleDev& e);
+int launch_eagle_grid(vzgp_handle* h, vzgp_handle* hB, const EagleDev& e, const vzgp_acq* acq,
+                      const vzgp_pe_params* pe, int steps);
 size_t eagle_suggest_smem(const EagleDev& e);
 size_t eagle_update_smem(const EagleDev& e);
 int launch_eagle_init(vzgp_handle* h, const EagleDev& e);

@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "launchers.h"
+#include "score_small.cuh"
 #include "tiles.cuh"
 
 namespace vzgp {
@@ -31,54 +32,6 @@ using GP1 = GemmCfg<64, 64, 16, 2, 4>;  // phase-1 thread mapping: 512 threads, 
 constexpr int kThreads = 512;        // consumer threads (16 math warps)
 constexpr int kBlockThreads = 544;   // + one TMA producer warp
 
-struct ScoreArgs {
-  // TMA descriptors (must stay first: 64-byte alignment inside the __grid_constant__ parameter).
-  alignas(64) CUtensorMap mapA;  // scratch  as [gridDim.x*64 rows][np], box 64 x 16, SWIZZLE_128B
-  alignas(64) CUtensorMap mapB;  // Linv     as [np rows][np],           box 128 x 16, SWIZZLE_128B
-  const double* Xs;
-  const int32_t* Zs;
-  int M;
-  const double* XT;   // [2][dc][np]: scaled / unscaled transposed trials
-  const int32_t* Z;
-  int np;
-  int n_valid;
-  const double* Linv;
-  int ldi;
-  const double* alpha;
-  KernelParams kp;
-  double sn2;
-  double coef;
-  int apply_tr;     // trust region modifies the score
-  int tr_rows;      // trusted points = first tr_rows rows of X
-  int tr_strict;    // inside test: dist < radius instead of <=
-  double radius;
-  uint8_t tr_mask[kMaxDc];
-  double* scratch;  // [gridDim.x][64][np]
-  int nsplit;       // > 1: output column blocks of one tile are shared by nsplit CTAs (small M)
-  double* part;     // nsplit > 1: [nsplit + 2][Mpad] partial row sums, then mu, then linf
-  int mpad;
-  // small-pool path (k_cross_small / k_var_small / k_small_finalize)
-  double* part_rs;    // [np/16][Mpad] partial row sums of W^2, one row per 16-column block
-  double* part_mu;    // [np/64][Mpad] partial means, one row per 64-trial block
-  double* part_linf;  // [np/64][Mpad] partial trust-region distances
-  double* score;
-  double* mu;
-  double* sigma;
-  double* linf;
-  int* clamp_count;
-};
-
-// ---- cp.async / DMMA primitives -------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
-  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  const int sz = valid ? 16 : 0;  // src-size 0 -> destination is zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
 // ---- mbarrier / TMA (cp.async.bulk.tensor) primitives --------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -108,7 +61,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 32, 3-stage cp.async
 // ring.  16 warps as 4 (M) x 4 (N): each warp owns a 16 x 32 block = 2 x 4 DMMA tiles.
-constexpr int kTM = 64;          // candidates per tile
 constexpr int kBN = 128;         // output columns per pass
 constexpr int kBK = 32;          // k-slab = two TMA boxes of 16 doubles (one 128-byte swizzle atom per row)
 constexpr int kStages = 4;
@@ -118,24 +70,6 @@ constexpr int kAHalf = kTM * 16;                 // doubles
 constexpr int kBHalf = kBN * 16;
 constexpr int kStageDoubles = 2 * (kAHalf + kBHalf);   // 6144 doubles = 48 KB
 constexpr unsigned kStageBytes = kStageDoubles * sizeof(double);
-constexpr int kLD1 = 66;         // phase-1 smem row stride (64 rows/cols + 2)
-
-// Final score from the reduced pieces (shared by the fused epilogue and the split finalize kernel).
-__device__ __forceinline__ void emit_score(const ScoreArgs& a, int m, double rs, double mean, double dist,
-                                           int& clamped) {
-  double var = a.kp.sf2 - rs + a.sn2;
-  if (var < 0.0) { var = 0.0; ++clamped; }
-  const double sd = sqrt(var);
-  double sc = fma(a.coef, sd, mean);
-  if (a.apply_tr) {
-    const bool inside = (a.tr_strict ? (dist < a.radius) : (dist <= a.radius)) || (a.radius > 0.5);
-    sc = inside ? sc : (-1e4 - dist);
-  }
-  a.score[m] = sc;
-  if (a.mu) a.mu[m] = mean;
-  if (a.sigma) a.sigma[m] = sd;
-  if (a.linf) a.linf[m] = dist;
-}
 
 template <bool WITH_LINF>
 __global__ void __launch_bounds__(kBlockThreads, 1) k_score(const __grid_constant__ ScoreArgs a) {
@@ -446,212 +380,26 @@ __global__ void k_score_finalize(const ScoreArgs a) {
   if (clamped) atomicAdd(a.clamp_count, clamped);
 }
 
-// ---------------------------------------------------------------------------
-// Small candidate pools (the acquisition optimiser scores 25..1000 candidates per iteration,
-// vectorized_base.py:431-495).  One persistent CTA per 64-candidate tile leaves the GPU empty there,
-// so the work is cut along the TRIAL axis instead:
-//   k_cross_small  grid (np/64, tiles): K* block [64 cand x 64 trials] -> scratch, partial mean / L-inf
-//   k_var_small    grid (np/16, tiles): W[:, 16 cols] = K*[:, 0:kext] Linv[16 rows, 0:kext]^T on the
-//                  DMMA pipe (cp.async ring), partial row sums of W^2
-//   k_small_finalize: fixed-order sums of the partials -> variance, UCB, trust region.
-// All reductions have a fixed order: results are reproducible run to run.
-// ---------------------------------------------------------------------------
-constexpr int kSmallThreads = 256;
-constexpr int kVarCols = 16;           // output columns per k_var_small CTA
-constexpr int kVarBK = 32;             // k-slab
-constexpr int kVarLD = 40;             // smem row stride (doubles): 16-byte fragment loads are conflict-free
-constexpr int kVarStages = 4;
-constexpr int kVarStageDoubles = (kTM + kVarCols) * kVarLD;
-
+// Stand-alone kernels of the small-pool path (device functions in score_small.cuh).
 template <bool WITH_LINF>
 __global__ void __launch_bounds__(kSmallThreads) k_cross_small(const ScoreArgs a) {
   extern __shared__ double smem_raw[];
-  constexpr int LD = kLD1;
-  const int dc = a.kp.dc, dk = a.kp.dk, np = a.np;
-  double* sa = smem_raw;                 // [dc][LD] candidates (transposed)
-  double* sb = sa + dc * LD;             // [dc][LD] trials
-  int32_t* za = reinterpret_cast<int32_t*>(sb + dc * LD);   // [dk][LD]
-  int32_t* zb = za + dk * LD;
-  const int tid = threadIdx.x;
-  const int jb = blockIdx.x, tile = blockIdx.y, m0 = tile * kTM;
-  const int ty = tid >> 4, tx = tid & 15;       // rows ty + 16 i, columns 4 tx + j
-  for (int e = tid; e < kTM * dc; e += kSmallThreads) {
-    const int r = e / dc, d = e - r * dc;
-    const int gr = m0 + r;
-    const double v = gr < a.M ? __ldg(a.Xs + (size_t)gr * dc + d) : 0.0;
-    sa[d * LD + r] = WITH_LINF ? v : v * a.kp.inv_ls_c[d];
-  }
-  {
-    const double* src = (WITH_LINF ? a.XT + (size_t)dc * np : a.XT) + jb * 64;
-    for (int e = tid; e < dc * 32; e += kSmallThreads) {
-      const int d = e >> 5, q = e & 31;
-      *reinterpret_cast<double2*>(sb + d * LD + 2 * q) = __ldg(reinterpret_cast<const double2*>(src + (size_t)d * np + 2 * q));
-    }
-  }
-  if (dk > 0) {
-    stage_rows_T_i32(a.Zs, a.M, dk, m0, kTM, za, LD, kSmallThreads);
-    stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD, kSmallThreads);
-  }
-  __syncthreads();
-  double d2[4][4], lf[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { d2[i][j] = 0.0; lf[i][j] = 0.0; }
-  for (int d = 0; d < dc; ++d) {
-    double aa[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) aa[i] = sa[d * LD + ty + 16 * i];
-    const double2 b0 = *reinterpret_cast<const double2*>(sb + d * LD + 4 * tx);
-    const double2 b1 = *reinterpret_cast<const double2*>(sb + d * LD + 4 * tx + 2);
-    const double bb[4] = {b0.x, b0.y, b1.x, b1.y};
-    if (WITH_LINF) {
-      const double w = a.kp.inv_ls2_c[d];
-      const bool in_tr = a.tr_mask[d] != 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double df = aa[i] - bb[j];
-          d2[i][j] = fma(df * df, w, d2[i][j]);
-          if (in_tr) lf[i][j] = fmax(lf[i][j], fabs(df));
-        }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double df = aa[i] - bb[j];
-          d2[i][j] = fma(df, df, d2[i][j]);
-        }
-    }
-  }
-  for (int k = 0; k < dk; ++k) {
-    const double w = a.kp.inv_ls2_k[k];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int avz = za[k * LD + ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) d2[i][j] += (avz != zb[k * LD + 4 * tx + j]) ? w : 0.0;
-    }
-  }
-  double* scr = a.scratch + (size_t)tile * kTM * np + jb * 64;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = ty + 16 * i;
-    double kv[4], mu_part = 0.0, lmin = INFINITY;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gc = jb * 64 + 4 * tx + j;
-      kv[j] = gc < a.n_valid ? matern52(d2[i][j], a.kp.sf2) : 0.0;
-      mu_part = fma(kv[j], __ldg(a.alpha + gc), mu_part);
-      if (WITH_LINF && gc < a.tr_rows) lmin = fmin(lmin, lf[i][j]);
-    }
-    *reinterpret_cast<double2*>(scr + (size_t)r * np + 4 * tx) = make_double2(kv[0], kv[1]);
-    *reinterpret_cast<double2*>(scr + (size_t)r * np + 4 * tx + 2) = make_double2(kv[2], kv[3]);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      mu_part += __shfl_xor_sync(0xffffffffu, mu_part, o);
-      if (WITH_LINF) lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-    }
-    if (tx == 0) {
-      a.part_mu[(size_t)jb * a.mpad + m0 + r] = mu_part;
-      a.part_linf[(size_t)jb * a.mpad + m0 + r] = lmin;
-    }
-  }
+  cross_small_block<WITH_LINF>(a, blockIdx.x, blockIdx.y >> 2, blockIdx.y & 3, smem_raw);
 }
-
 __global__ void __launch_bounds__(kSmallThreads) k_var_small(const ScoreArgs a) {
   extern __shared__ double smem_raw[];
-  const int np = a.np;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int fr = lane >> 2, fk = lane & 3;
-  const int b = blockIdx.x, tile = blockIdx.y, m0 = tile * kTM;
-  const int rows = min(kTM, a.M - m0);
-  const int nmt = (rows + 7) >> 3;                 // m-tiles (8 candidates) that hold real rows
-  const int kext = kVarCols * (b + 1);             // Linv[j, k] = 0 for k > j
-  const int nslab = (kext + kVarBK - 1) / kVarBK;
-  const double* Asrc = a.scratch + (size_t)tile * kTM * np;
-  const double* Bsrc = a.Linv + (size_t)b * kVarCols * a.ldi;
-  // 16-byte chunks of one slab: A nmt*8 rows x 16 chunks, then B 16 rows x 16 chunks
-  const int a_chunks = nmt * 8 * (kVarBK / 2), chunks = a_chunks + kVarCols * (kVarBK / 2);
-  auto issue = [&](int ks) {
-    double* stg = smem_raw + (ks % kVarStages) * kVarStageDoubles;
-    const int k0 = ks * kVarBK;
-    for (int c = tid; c < chunks; c += kSmallThreads) {
-      if (c < a_chunks) {
-        const int r = c >> 4, q = c & 15;
-        cp_async16(stg + r * kVarLD + 2 * q, Asrc + (size_t)r * np + k0 + 2 * q, true);
-      } else {
-        const int c2 = c - a_chunks, r = c2 >> 4, q = c2 & 15;
-        cp_async16(stg + (kTM + r) * kVarLD + 2 * q, Bsrc + (size_t)r * a.ldi + k0 + 2 * q, true);
-      }
-    }
-  };
-#pragma unroll
-  for (int s = 0; s < kVarStages - 1; ++s) {
-    if (s < nslab) issue(s);
-    cp_async_commit();
-  }
-  double acc[2][2][2];   // [n-tile][k parity][2]
-#pragma unroll
-  for (int n = 0; n < 2; ++n)
-#pragma unroll
-    for (int q = 0; q < 2; ++q) { acc[n][q][0] = 0.0; acc[n][q][1] = 0.0; }
-  for (int ks = 0; ks < nslab; ++ks) {
-    cp_async_wait<kVarStages - 2>();
-    __syncthreads();                         // slab ks landed for everyone; slab ks-1 fully consumed
-    if (ks + kVarStages - 1 < nslab) issue(ks + kVarStages - 1);
-    cp_async_commit();
-    if (warp < nmt) {
-      const double* stg = smem_raw + (ks % kVarStages) * kVarStageDoubles;
-      const double* Ar = stg + (warp * 8 + fr) * kVarLD + 2 * fk;
-      const double* Br = stg + (kTM + fr) * kVarLD + 2 * fk;
-#pragma unroll
-      for (int h = 0; h < kVarBK / 8; ++h) {
-        const double2 av = *reinterpret_cast<const double2*>(Ar + 8 * h);
-        const double2 b0 = *reinterpret_cast<const double2*>(Br + 8 * h);
-        const double2 b1 = *reinterpret_cast<const double2*>(Br + 8 * kVarLD + 8 * h);
-        dmma_8x8x4(acc[0][0][0], acc[0][0][1], av.x, b0.x);
-        dmma_8x8x4(acc[1][0][0], acc[1][0][1], av.x, b1.x);
-        dmma_8x8x4(acc[0][1][0], acc[0][1][1], av.y, b0.y);
-        dmma_8x8x4(acc[1][1][0], acc[1][1][1], av.y, b1.y);
-      }
-    }
-  }
-  cp_async_wait<0>();
-  if (warp < nmt) {
-    double rs = 0.0;
-#pragma unroll
-    for (int n = 0; n < 2; ++n)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const double w = acc[n][0][e] + acc[n][1][e];
-        rs = fma(w, w, rs);
-      }
-    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-    if (fk == 0) a.part_rs[(size_t)b * a.mpad + m0 + warp * 8 + fr] = rs;
-  }
+  var_small_block(a, blockIdx.x, blockIdx.y, smem_raw);
 }
-
 template <bool WITH_LINF>
-__global__ void k_small_finalize(const ScoreArgs a) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_small_finalize(const ScoreArgs a) {
+  const int m = blockIdx.x * 32 + (threadIdx.x >> 3);
   int clamped = 0;
-  if (m < a.M) {
-    double rs = 0.0, mean = 0.0, dist = INFINITY;
-    const int nvb = a.np / kVarCols, nmb = a.np / 64;
-    const int mt = (m & 63) >> 3;   // rows of m-tiles without real candidates were never written
-    (void)mt;
-    for (int s = 0; s < nvb; ++s) rs += a.part_rs[(size_t)s * a.mpad + m];
-    for (int s = 0; s < nmb; ++s) mean += a.part_mu[(size_t)s * a.mpad + m];
-    if (WITH_LINF)
-      for (int s = 0; s < nmb; ++s) dist = fmin(dist, a.part_linf[(size_t)s * a.mpad + m]);
-    emit_score(a, m, rs, mean, dist, clamped);
-  }
+  small_finalize_8<WITH_LINF>(a, m, threadIdx.x & 7, m < a.M, clamped);
   if (clamped) atomicAdd(a.clamp_count, clamped);
 }
+
+size_t cross_small_smem_bytes(int dc, int dk) { return sizeof(double) * 2 * dc * kLD1 + sizeof(int32_t) * 2 * dk * kLD1; }
+size_t var_small_smem_bytes() { return sizeof(double) * kVarStages * kVarStageDoubles; }
 
 // ---- host side: TMA descriptors ------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -695,29 +443,12 @@ size_t score_smem_bytes(int dc, int dk, bool with_linf) {
          sizeof(int32_t) * dk * 2 * kLD1 + kMaxDc;
 }
 
-int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
-                 double* score, double* mu, double* sigma, double* linf) {
-  if (M <= 0) return 0;
-  const int ntiles = (M + kTM - 1) / kTM;
-  const int nblocks = (h->np + kBN - 1) / kBN;
-  // Small pools cannot fill the GPU with one CTA per tile: share each tile's output column
-  // blocks between nsplit CTAs (each recomputes the cheap K* tile).
-  int nsplit = 1;
-  if (ntiles * 2 <= h->sm_count && nblocks >= 2) nsplit = (nblocks + 1) / 2;
-  const int nwork = ntiles * nsplit;
-  // Pools of a few tiles (acquisition-optimiser batches) take the trial-axis decomposition instead.
-  static const int small_tiles_max = [] {
-    const char* e = getenv("VZGP_SMALL_TILES");   // tuning / test hook; 0 disables the small-pool path
-    return e ? atoi(e) : 8;
-  }();
-  const bool small = ntiles <= small_tiles_max;
-  const int grid = small ? ntiles : (nwork < h->sm_count ? nwork : h->sm_count);
-  const size_t scratch_bytes = (size_t)grid * kTM * h->np * sizeof(double);
+// K* scratch of `bytes` bytes on the handle.  It is written and re-read by the same CTA tile after tile:
+// pin it in L2 (persisting access-policy window) so its dirty lines are overwritten in place instead
+// of being evicted to HBM.  Best effort: failures only cost DRAM write-backs.
+static int ensure_scratch(vzgp_handle* h, size_t scratch_bytes) {
   if (scratch_bytes > h->scratch.bytes || h->scratch_window != h->scratch.ptr) {
     VZ_TRY(h->scratch.reserve(scratch_bytes));
-    // The K* scratch is written and re-read by the same CTA tile after tile: pin it in L2
-    // (persisting access-policy window) so its dirty lines are overwritten in place instead of
-    // being evicted to HBM.  Best effort: failures only cost DRAM write-backs.
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
       size_t want = h->scratch.bytes;
@@ -737,7 +468,13 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
     }
     h->scratch_window = h->scratch.ptr;
   }
-  ScoreArgs a;
+  return 0;
+}
+
+static void fill_score_args(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                            double* score, double* mu, double* sigma, double* linf, ScoreArgs* pa) {
+  ScoreArgs& a = *pa;
+  const int ntiles = (M + kTM - 1) / kTM;
   a.Xs = Xs; a.Zs = Zs; a.M = M;
   a.XT = h->XT.as<double>(); a.Z = h->Z.as<int32_t>();
   a.np = h->np; a.n_valid = h->n_valid;
@@ -753,20 +490,43 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
     a.tr_mask[d] = (d < h->dc) ? (acq->tr_dim_mask ? (acq->tr_dim_mask[d] ? 1 : 0) : 1) : 0;
   a.scratch = h->scratch.as<double>();
   a.mpad = ntiles * kTM;
+  a.nsplit = 1;
   a.part = a.part_rs = a.part_mu = a.part_linf = nullptr;
   a.score = score; a.mu = mu; a.sigma = sigma; a.linf = linf;
   a.clamp_count = h->small.as<int>();  // slot 0
-  if (small) {
+}
+
+int prepare_small_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                        double* score, double* mu, double* sigma, double* linf, ScoreArgs* a, bool* with_linf) {
+  const int ntiles = (M + kTM - 1) / kTM;
+  VZ_TRY(ensure_scratch(h, (size_t)ntiles * kTM * h->np * sizeof(double)));
+  fill_score_args(h, Xs, Zs, M, acq, score, mu, sigma, linf, a);
+  const int nvb = h->np / kVarCols, nmb = h->np / 64;
+  VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)(nvb + 2 * nmb) * a->mpad));
+  a->part_rs = h->Tws.as<double>();
+  a->part_mu = a->part_rs + (size_t)nvb * a->mpad;
+  a->part_linf = a->part_mu + (size_t)nmb * a->mpad;
+  *with_linf = (linf != nullptr) || (a->apply_tr && a->radius <= 0.5);
+  return 0;
+}
+
+int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                 double* score, double* mu, double* sigma, double* linf) {
+  if (M <= 0) return 0;
+  const int ntiles = (M + kTM - 1) / kTM;
+  const int nblocks = (h->np + kBN - 1) / kBN;
+  // Pools of a few tiles (acquisition-optimiser batches) take the trial-axis decomposition.
+  static const int small_tiles_max = [] {
+    const char* e = getenv("VZGP_SMALL_TILES");   // tuning / test hook; 0 disables the small-pool path
+    return e ? atoi(e) : 8;
+  }();
+  ScoreArgs a;
+  if (ntiles <= small_tiles_max) {
+    bool with_linf = false;
+    VZ_TRY(prepare_small_score(h, Xs, Zs, M, acq, score, mu, sigma, linf, &a, &with_linf));
     const int nvb = h->np / kVarCols, nmb = h->np / 64;
-    VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)(nvb + 2 * nmb) * a.mpad));
-    a.part_rs = h->Tws.as<double>();
-    a.part_mu = a.part_rs + (size_t)nvb * a.mpad;
-    a.part_linf = a.part_mu + (size_t)nmb * a.mpad;
-    a.nsplit = 1;
-    const bool with_linf = (linf != nullptr) || (a.apply_tr && a.radius <= 0.5);
-    const size_t sm1 = sizeof(double) * 2 * h->dc * kLD1 + sizeof(int32_t) * 2 * h->dk * kLD1;
-    const size_t sm2 = sizeof(double) * kVarStages * kVarStageDoubles;
-    const dim3 g1(nmb, ntiles), g2(nvb, ntiles);
+    const size_t sm1 = cross_small_smem_bytes(h->dc, h->dk), sm2 = var_small_smem_bytes();
+    const dim3 g1(nmb, ntiles * 4), g2(nvb, ntiles);
     if (with_linf) {
       VZ_CUDA(cudaFuncSetAttribute(k_cross_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
       k_cross_small<true><<<g1, kSmallThreads, sm1, h->stream>>>(a);
@@ -778,12 +538,20 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
     VZ_CUDA(cudaFuncSetAttribute(k_var_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     k_var_small<<<g2, kSmallThreads, sm2, h->stream>>>(a);
     VZ_CHECK_LAUNCH();
-    if (with_linf) k_small_finalize<true><<<(M + 63) / 64, 64, 0, h->stream>>>(a);
-    else k_small_finalize<false><<<(M + 63) / 64, 64, 0, h->stream>>>(a);
+    if (with_linf) k_small_finalize<true><<<(M + 31) / 32, 256, 0, h->stream>>>(a);
+    else k_small_finalize<false><<<(M + 31) / 32, 256, 0, h->stream>>>(a);
     VZ_CHECK_LAUNCH();
     h->launches += 3;
     return 0;
   }
+  // Medium pools cannot fill the GPU with one CTA per tile: share each tile's output column
+  // blocks between nsplit CTAs (each recomputes the cheap K* tile).
+  int nsplit = 1;
+  if (ntiles * 2 <= h->sm_count && nblocks >= 2) nsplit = (nblocks + 1) / 2;
+  const int nwork = ntiles * nsplit;
+  const int grid = nwork < h->sm_count ? nwork : h->sm_count;
+  VZ_TRY(ensure_scratch(h, (size_t)grid * kTM * h->np * sizeof(double)));
+  fill_score_args(h, Xs, Zs, M, acq, score, mu, sigma, linf, &a);
   VZ_TRY(make_map(&a.mapA, a.scratch, (uint64_t)grid * kTM, (uint64_t)h->np, (uint64_t)h->np, kTM));
   VZ_TRY(make_map(&a.mapB, a.Linv, (uint64_t)h->np, (uint64_t)h->np, (uint64_t)h->np, kBN));
   a.nsplit = nsplit;
