@@ -203,8 +203,14 @@ __global__ void __launch_bounds__(256) k_trsm_panel(double* __restrict__ L, int 
     }
 }
 
-// Trailing update: L[i, j] -= L[i, kb] * L[j, kb]^T for kb < j <= i (lower tiles only).
-__global__ void __launch_bounds__(256) k_syrk_trailing(double* __restrict__ L, int ld, int kb) {
+// Trailing update  L[i, j] -= L[i, kb] * L[j, kb]^T  for kb < j <= i (lower tiles only), with
+// look-ahead: the CTA that owns the NEXT
+// diagonal block (kb+1, kb+1) keeps its updated tile in shared memory and factors + inverts it at once
+// (potf2_inv_64), concurrently with the other tiles' updates.  The 64-pivot latency chain of the
+// diagonal block thereby leaves the critical path of the blocked factorisation: per step
+// trsm -> max(trailing update, diagonal factor) instead of factor -> trsm -> update.
+__global__ void __launch_bounds__(256) k_syrk_potf2(double* __restrict__ L, int ld, int kb,
+                                                    double* __restrict__ Linv, int ldi, int* __restrict__ flag) {
   extern __shared__ double smem[];
   const int ib = kb + 1 + blockIdx.y, jb = kb + 1 + blockIdx.x;
   if (jb > ib) return;
@@ -212,17 +218,50 @@ __global__ void __launch_bounds__(256) k_syrk_trailing(double* __restrict__ L, i
   const double* P = L + (size_t)kb * 64;
   gemm_mainloop<64, 64, 16, 4, 4, false, false>(P, ld, ib * 64, P, ld, jb * 64, 0, 64, acc, smem);
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  if (blockIdx.x != 0 || blockIdx.y != 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        double2* p = reinterpret_cast<double2*>(L + (size_t)(ib * 64 + G64::row_of(ty, i)) * ld +
+                                                jb * 64 + G64::col_of(tx, j));
+        double2 v = *p;
+        v.x -= acc[i][j];
+        v.y -= acc[i][j + 1];
+        *p = v;
+      }
+    return;
+  }
+  // ---- the next diagonal block: update in registers -> shared memory -> factor + invert ----
+  constexpr int LD = 66;
+  double* a = smem;              // [64][66]
+  double* x = smem + 64 * LD;    // [64][66]
+  double* t = x + 64 * LD;       // [32][34]
+  __shared__ double rd[64];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  double* blk = L + (size_t)ib * 64 * ld + ib * 64;
+  __syncthreads();               // every warp is done with the GEMM staging buffers
+  if (tid == 0) s_bad = 0;
+  for (int e = tid; e < 64 * LD; e += 256) x[e] = 0.0;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; j += 2) {
-      double2* p = reinterpret_cast<double2*>(L + (size_t)(ib * 64 + G64::row_of(ty, i)) * ld +
-                                              jb * 64 + G64::col_of(tx, j));
-      double2 v = *p;
-      v.x -= acc[i][j];
-      v.y -= acc[i][j + 1];
-      *p = v;
+    for (int j = 0; j < 4; ++j) {
+      const int r = G64::row_of(ty, i), c = G64::col_of(tx, j);
+      const bool upper_blk = (c >> 4) > (r >> 4);
+      a[r * LD + c] = upper_blk ? 0.0 : blk[(size_t)r * ld + c] - acc[i][j];
     }
+  __syncthreads();
+  potf2_inv_64(a, x, t, rd, &s_bad);
+  double* iblk = Linv + (size_t)ib * 64 * ldi + ib * 64;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
+    *reinterpret_cast<double2*>(blk + (size_t)i * ld + j2) = *reinterpret_cast<const double2*>(a + i * LD + j2);
+    *reinterpret_cast<double2*>(iblk + (size_t)i * ldi + j2) = *reinterpret_cast<const double2*>(x + i * LD + j2);
+  }
+  if (tid == 0 && s_bad) flag[0] = 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -458,18 +497,20 @@ int potrf_blocked(vzgp_handle* h, double* L, int ld, double* Linv, int ldi, int 
   const int nb = np / 64;
   VZ_CUDA(cudaFuncSetAttribute(k_potf2_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
   const size_t sm = G64::kSmemBytes;
-  for (int kb = 0; kb < nb; ++kb) {
-    k_potf2_inv<<<1, 256, kDiagSmem, h->stream>>>(L, ld, kb, Linv, ldi, flag);
+  const size_t sm2 = sm > kDiagSmem ? sm : kDiagSmem;
+  VZ_CUDA(cudaFuncSetAttribute(k_syrk_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  // Right-looking with one block of look-ahead: block 0 is factored alone; afterwards the trailing
+  // update of step kb also factors diagonal block kb+1 (k_syrk_potf2).
+  k_potf2_inv<<<1, 256, kDiagSmem, h->stream>>>(L, ld, 0, Linv, ldi, flag);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  for (int kb = 0; kb + 1 < nb; ++kb) {
+    const int rem = nb - kb - 1;
+    k_trsm_panel<<<rem, 256, sm, h->stream>>>(L, ld, kb, Linv, ldi);
     VZ_CHECK_LAUNCH();
-    h->launches++;
-    int rem = nb - kb - 1;
-    if (rem > 0) {
-      k_trsm_panel<<<rem, 256, sm, h->stream>>>(L, ld, kb, Linv, ldi);
-      VZ_CHECK_LAUNCH();
-      k_syrk_trailing<<<dim3(rem, rem), 256, sm, h->stream>>>(L, ld, kb);
-      VZ_CHECK_LAUNCH();
-      h->launches += 2;
-    }
+    k_syrk_potf2<<<dim3(rem, rem), 256, sm2, h->stream>>>(L, ld, kb, Linv, ldi, flag);
+    VZ_CHECK_LAUNCH();
+    h->launches += 2;
   }
   return 0;
 }
