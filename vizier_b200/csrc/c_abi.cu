@@ -345,7 +345,7 @@ int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const doubl
   int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, &shift);
   if (retries < 0) return retries;
   const int np = h->np, nq = Dc + Dk + 2;
-  VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np));
+  VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));   // partial planes of K_y^-1
   double* out2 = reinterpret_cast<double*>(h->small.as<char>() + kOffLogdet);
   double* gout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);
   double* w = h->ypad.as<double>() + np;

@@ -318,23 +318,27 @@ __global__ void __launch_bounds__(256) k_trtri_step2(double* __restrict__ Linv, 
                                   G64::col_of(tx, j)) = make_double2(-acc[i][j], -acc[i][j + 1]);
 }
 
-// Kinv = Linv^T Linv (both triangles written).  Kinv[i,j] = sum_{k >= max(i,j)} Linv[k,i]*Linv[k,j].
+// Kinv = Linv^T Linv, lower tiles only:  Kinv[i,j] = sum_{k >= max(i,j)} Linv[k,i]*Linv[k,j].
+// The tile (0,0) sums over all N rows - a 64-slab latency chain in one CTA - so the k range is cut
+// into kLauumSplit planes: plane z holds the partial sum over k in [z*kc, (z+1)*kc) (only where that
+// range meets k >= 64*ib); the consumer (k_nll_grad_tiles) adds the planes in ascending z.
 __global__ void __launch_bounds__(256) k_lauum(const double* __restrict__ Linv, int ldi,
-                                               double* __restrict__ Kinv, int ldk, int np) {
+                                               double* __restrict__ Kinv, int ldk, int np, int kc) {
   extern __shared__ double smem[];
-  const int ib = blockIdx.y, jb = blockIdx.x;
+  const int ib = blockIdx.y, jb = blockIdx.x, z = blockIdx.z;
   if (jb > ib) return;
+  const int k0 = max(ib * 64, z * kc), k1 = min(np, (z + 1) * kc);
+  if (k0 >= k1) return;
   double acc[4][4] = {};
-  gemm_mainloop<64, 64, 16, 4, 4, true, true>(Linv, ldi, ib * 64, Linv, ldi, jb * 64, ib * 64, np,
-                                              acc, smem);
+  gemm_mainloop<64, 64, 16, 4, 4, true, true>(Linv, ldi, ib * 64, Linv, ldi, jb * 64, k0, k1, acc, smem);
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  double* plane = Kinv + (size_t)z * np * ldk;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int gi = ib * 64 + G64::row_of(ty, i), gj = jb * 64 + G64::col_of(tx, j);
-      Kinv[(size_t)gi * ldk + gj] = acc[i][j];
-      if (ib != jb) Kinv[(size_t)gj * ldk + gi] = acc[i][j];
+    for (int j = 0; j < 4; j += 2) {
+      const int gi = ib * 64 + G64::row_of(ty, i), gj = jb * 64 + G64::col_of(tx, j);
+      *reinterpret_cast<double2*>(plane + (size_t)gi * ldk + gj) = make_double2(acc[i][j], acc[i][j + 1]);
     }
 }
 
@@ -531,9 +535,11 @@ int trtri_doubling(vzgp_handle* h, const double* L, int ld, double* Linv, int ld
   return 0;
 }
 
+int lauum_plane_rows(int np) { return ((np / 64 + kLauumSplit - 1) / kLauumSplit) * 64; }
+
 int launch_lauum(vzgp_handle* h, const double* Linv, int ldi, double* Kinv, int ldk, int np) {
-  int nb = np / 64;
-  k_lauum<<<dim3(nb, nb), 256, G64::kSmemBytes, h->stream>>>(Linv, ldi, Kinv, ldk, np);
+  const int nb = np / 64;
+  k_lauum<<<dim3(nb, nb, kLauumSplit), 256, G64::kSmemBytes, h->stream>>>(Linv, ldi, Kinv, ldk, np, lauum_plane_rows(np));
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;

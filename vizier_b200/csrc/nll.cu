@@ -18,7 +18,7 @@ using G64 = GemmCfg<64, 64, 16, 4, 4>;
 __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict__ X,
                                                         const int32_t* __restrict__ Z, int np,
                                                         int n_valid, KernelParams kp,
-                                                        const double* __restrict__ Kinv, int ldk,
+                                                        const double* __restrict__ Kinv, int ldk, int kc,
                                                         const double* __restrict__ alpha,
                                                         double* __restrict__ partial, int nb) {
   const int bi = blockIdx.y, bj = blockIdx.x;
@@ -51,7 +51,10 @@ __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict
       const int gi = bi * 64 + G64::row_of(ty, i), gj = bj * 64 + G64::col_of(tx, j);
       double g = 0.0, kv = 0.0, ev = 0.0;
       if (gi < n_valid && gj < n_valid) {
-        g = wgt * (Kinv[(size_t)gi * ldk + gj] - alpha[gi] * alpha[gj]);
+        double kinv = 0.0;   // planes of k_lauum that meet k >= 64*bi, ascending
+        for (int z = (bi * 64) / kc; z < kLauumSplit && z * kc < np; ++z)
+          kinv += Kinv[((size_t)z * np + gi) * ldk + gj];
+        g = wgt * (kinv - alpha[gi] * alpha[gj]);
         matern52_with_grad(d2[i][j], kp.sf2, kv, ev);
         if (gi == gj) sum_tr += g;
       }
@@ -116,7 +119,7 @@ int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int
   const int nb = np / 64, nq = kp.dc + kp.dk + 2, ntiles = nb * (nb + 1) / 2;
   size_t sm = sizeof(double) * (kp.dc * 2 * 66 + 8 * nq) + sizeof(int32_t) * kp.dk * 2 * 66;
   VZ_CUDA(cudaFuncSetAttribute(k_nll_grad_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_nll_grad_tiles<<<dim3(nb, nb), 256, sm, h->stream>>>(X, Z, np, n_valid, kp, Kinv, ldk, alpha,
+  k_nll_grad_tiles<<<dim3(nb, nb), 256, sm, h->stream>>>(X, Z, np, n_valid, kp, Kinv, ldk, lauum_plane_rows(np), alpha,
                                                          partial, nb);
   VZ_CHECK_LAUNCH();
   k_reduce_partials<<<nq, 256, 0, h->stream>>>(partial, ntiles, nq, out);
