@@ -117,6 +117,38 @@ def test_ensemble_designer_suggest_sample_predict():
     gp_bandit.VizierGPBandit.from_problem(p, ensemble_size=9)
 
 
+def test_two_studies_concurrently_match_sequential():
+  """Different studies may call suggest() concurrently (vizier_service.py:297 only serialises per study):
+  two designers driven from two threads on one GPU give exactly what they give one after the other."""
+  import concurrent.futures as cf
+  from vizier_b200.designers import gp_ucb_pe
+
+  def run(kind_seed):
+    kind, seed = kind_seed
+    p = _problem(3)
+    f = lambda x: -np.sum((x - 0.7) ** 2)
+    rng = np.random.default_rng(seed)
+    trials = []
+    for i in range(70 if kind == 'bandit' else 30):     # 70 trials: grid-persistent loop, 30: single-CTA loop
+      t = vz.Trial(parameters={f'x{j}': float(v) for j, v in enumerate(rng.uniform(-5, 5, 3))}, id=i + 1)
+      t.complete(vz.Measurement({'obj': float(f(np.array([t.parameters[k].value for k in sorted(t.parameters)])))}))
+      trials.append(t)
+    if kind == 'bandit':
+      d = gp_bandit.VizierGPBandit.from_problem(p, seed=seed, acquisition_optimizer_factory=small_opt)
+    else:
+      d = gp_ucb_pe.VizierGPUCBPEBandit(p, rng=seed, acquisition_optimizer_factory=vb.VectorizedOptimizerFactory(
+          strategy_factory=vb.VectorizedEagleStrategyFactory(eagle_config=gp_ucb_pe.default_eagle_config),
+          max_evaluations=2000, suggestion_batch_size=25))
+    d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+    return [[s.parameters[f'x{j}'].value for j in range(3)] for s in d.suggest(2)]
+
+  jobs = [('bandit', 11), ('ucbpe', 12), ('bandit', 13), ('ucbpe', 14)]
+  sequential = [run(j) for j in jobs]
+  with cf.ThreadPoolExecutor(max_workers=4) as pool:
+    concurrent = list(pool.map(run, jobs))
+  assert concurrent == sequential
+
+
 def test_random_pool_optimizer_factory():
   # the C2 shape through the designer API: score one M-candidate uniform pool, take the top `count`
   p = _problem(5, 0.0, 1.0)
