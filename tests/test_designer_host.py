@@ -73,3 +73,25 @@ def test_seed_trials_centre_then_quasi_random():
   space = _problem().search_space
   for sug in s:
     assert space.contains(sug.parameters)
+
+
+def test_lean_lbfgsb_driver_is_scipy_minimize():
+  """ard._lean_lbfgsb drives the same compiled routine as scipy.optimize.minimize(method='L-BFGS-B'):
+  identical iterates, so identical final point and value (jaxopt_wrappers.py:139-152 uses the latter)."""
+  import scipy.optimize as sopt
+  from vizier_b200 import ard
+  if ard._setulb is None:
+    pytest.skip('scipy.optimize._lbfgsb not importable')
+  rng = np.random.default_rng(3)
+
+  def f(t):
+    return float(np.sum((np.log(t) - 0.3) ** 2) + 1e-3 * np.sum(t ** 4)), 2 * (np.log(t) - 0.3) / t + 4e-3 * t ** 3
+
+  for d, maxiter in ((6, 50), (22, 5), (52, 500)):
+    bounds = [(1e-3, 10.0)] * d
+    x0 = np.exp(rng.uniform(np.log(1e-3), np.log(10.0), d))
+    want = sopt.minimize(f, x0, jac=True, method='L-BFGS-B', bounds=bounds,
+                         options={'maxiter': maxiter, 'gtol': 1e-8, 'maxls': 20})
+    x, fv = ard._lean_lbfgsb(f, x0, bounds, maxiter=maxiter, gtol=1e-8, maxls=20)
+    np.testing.assert_array_equal(x, want.x)
+    assert fv == want.fun

@@ -2,6 +2,7 @@
 #include <climits>
 #include <cstdarg>
 #include <cstring>
+#include <vector>
 
 #include "launchers.h"
 
@@ -128,6 +129,128 @@ static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const d
   return retries;
 }
 
+// ---------------------------------------------------------------------------
+// One NLL + gradient evaluation as a replayed CUDA graph (N > 64).
+// The launch sequence is the one of fit_common + the gradient part with a single factorisation attempt
+// and no host round trip; if the factorisation flags a bad pivot the caller falls back to the eager
+// path with its retry loop.  ~50 launches per evaluation cost more host time than GPU time when several
+// ARD restarts launch from different threads (the driver serialises them); replaying one graph does not.
+// ---------------------------------------------------------------------------
+static int nll_sequence(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int dc, int dk,
+                        int n_valid, const KernelParams& kp, double sn2) {
+  const int np = h->np;
+  double* yp = h->ypad.as<double>();
+  double* w = yp + np;
+  double* r = yp + 2 * np;
+  double* tmp = yp + 3 * np;
+  int* flag = reinterpret_cast<int*>(h->small.as<char>() + kOffFlag);
+  if (dc > 0) VZ_TRY(launch_pad_rows(h, X, N, dc, np, h->X.as<double>()));
+  if (dc > 0) VZ_TRY(launch_transpose_scale(h, h->X.as<double>(), np, dc, kp, h->XT.as<double>()));
+  if (dk > 0) VZ_TRY(launch_pad_rows_i32(h, Z, N, dk, np, h->Z.as<int32_t>()));
+  VZ_TRY(launch_pad_vector(h, y, N, n_valid, np, yp));
+  VZ_TRY(launch_kernel_matrix(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, sn2, h->Kws.as<double>(), np));
+  VZ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+  VZ_CUDA(cudaMemsetAsync(h->Linv.as<double>(), 0, sizeof(double) * (size_t)np * np, h->stream));
+  VZ_TRY(launch_copy_lower_shift(h, h->Kws.as<double>(), np, np, np, 0.0, h->L.as<double>(), np));
+  VZ_TRY(potrf_blocked(h, h->L.as<double>(), np, h->Linv.as<double>(), np, np, flag));
+  VZ_TRY(trtri_doubling(h, h->L.as<double>(), np, h->Linv.as<double>(), np, h->Tws.as<double>(), np, np));
+  double* alpha = h->alpha.as<double>();
+  VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
+  VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, w, alpha));
+  VZ_TRY(launch_residual(h, h->Kws.as<double>(), np, np, yp, alpha, r));
+  VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, r, tmp, 1));
+  VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, tmp, r));
+  VZ_TRY(launch_axpy(h, np, 1.0, r, alpha));
+  double* out2 = reinterpret_cast<double*>(h->small.as<char>() + kOffLogdet);
+  double* gout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);
+  VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, w, out2));
+  VZ_TRY(launch_lauum(h, h->Linv.as<double>(), np, h->Kinv.as<double>(), np, np));
+  VZ_TRY(launch_nll_grad_tiles(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, h->Kinv.as<double>(), np,
+                               alpha, h->Tws.as<double>(), gout));
+  return 0;
+}
+
+static void nll_graph_drop(vzgp_handle* h) {
+  if (h->nll_exec) cudaGraphExecDestroy(h->nll_exec);
+  if (h->nll_graph) cudaGraphDestroy(h->nll_graph);
+  h->nll_exec = nullptr; h->nll_graph = nullptr;
+  h->nll_nodes[0] = h->nll_nodes[1] = h->nll_nodes[2] = nullptr;
+}
+
+// Returns 0 and fills host2 / hostg on success; 1 if the caller must use the eager path (bad pivot or
+// the graph could not be built); < 0 on errors.
+static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int dc, int dk,
+                          int n_valid, const vzgp_params* p, double* host2, double* hostg) {
+  static const bool enabled = [] { const char* e = getenv("VZGP_NLL_GRAPH"); return !(e && e[0] == '0'); }();
+  if (!enabled) return 1;
+  KernelParams kp;
+  VZ_TRY(fill_kernel_params(p, dc, dk, &kp));
+  double sn2 = p->observation_noise_variance;
+  const int np = round_up(N, kBlk), nq = dc + dk + 2;
+  const bool hit = h->nll_exec && h->nll_key[0] == X && h->nll_key[1] == Z && h->nll_key[2] == y &&
+                   h->nll_key_dims[0] == N && h->nll_key_dims[1] == dc && h->nll_key_dims[2] == dk &&
+                   h->nll_key_dims[3] == n_valid;
+  h->fitted = false;
+  if (!hit) {
+    nll_graph_drop(h);
+    VZ_TRY(ensure_model_buffers(h, np, dc, dk));
+    VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));
+    h->n = N; h->np = np; h->dc = dc; h->dk = dk; h->n_valid = n_valid;
+    const int64_t l0 = h->launches;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 1; }
+    const int st = nll_sequence(h, X, Z, y, N, dc, dk, n_valid, kp, sn2);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    h->nll_launches = (int)(h->launches - l0);
+    h->launches = l0;
+    if (st < 0 || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return st < 0 ? st : 1; }
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return 1; }
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    std::vector<cudaGraphNode_t> nodes(nn);
+    cudaGraphGetNodes(graph, nodes.data(), &nn);
+    const void* want[3] = {kernel_matrix_func(), transpose_scale_func(), nll_grad_tiles_func()};
+    cudaGraphNode_t found[3] = {nullptr, nullptr, nullptr};
+    for (size_t i = 0; i < nn; ++i) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      cudaKernelNodeParams kpar;
+      if (cudaGraphKernelNodeGetParams(nodes[i], &kpar) != cudaSuccess) continue;
+      for (int q = 0; q < 3; ++q) if (kpar.func == want[q]) found[q] = nodes[i];
+    }
+    cudaGetLastError();
+    if (!found[0] || (dc > 0 && !found[1]) || !found[2]) { cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); return 1; }
+    h->nll_graph = graph; h->nll_exec = exec;
+    for (int q = 0; q < 3; ++q) h->nll_nodes[q] = found[q];
+    h->nll_key[0] = X; h->nll_key[1] = Z; h->nll_key[2] = y;
+    h->nll_key_dims[0] = N; h->nll_key_dims[1] = dc; h->nll_key_dims[2] = dk; h->nll_key_dims[3] = n_valid;
+  }
+  h->kp = kp; h->sn2 = sn2;
+  // new hyper-parameters: argument 4 (+5) of the kernel matrix, 3 of transpose+scale, 4 of the gradient tiles
+  const int arg_idx[3] = {4, 3, 4};
+  for (int q = 0; q < 3; ++q) {
+    if (!h->nll_nodes[q]) continue;
+    cudaKernelNodeParams kpar;
+    VZ_CUDA(cudaGraphKernelNodeGetParams(h->nll_nodes[q], &kpar));
+    void* args[16];
+    const int nargs = q == 0 ? 8 : (q == 1 ? 5 : 11);
+    for (int a2 = 0; a2 < nargs; ++a2) args[a2] = kpar.kernelParams[a2];
+    args[arg_idx[q]] = &kp;
+    if (q == 0) args[5] = &sn2;
+    kpar.kernelParams = args;
+    VZ_CUDA(cudaGraphExecKernelNodeSetParams(h->nll_exec, h->nll_nodes[q], &kpar));
+  }
+  VZ_CUDA(cudaGraphLaunch(h->nll_exec, h->stream));
+  h->launches += h->nll_launches;
+  int bad = 0;
+  VZ_CUDA(cudaMemcpyAsync(host2, h->small.as<char>() + kOffLogdet, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(hostg, h->small.as<char>() + kOffGrad, sizeof(double) * nq, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(&bad, h->small.as<char>() + kOffFlag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  return bad ? 1 : 0;
+}
+
 }  // namespace vzgp
 
 using namespace vzgp;
@@ -187,6 +310,8 @@ int vzgp_destroy(vzgp_handle* h) {
     for (int i = 0; i < 4; ++i) cudaEventDestroy(h->copy_ev[i]);
     cudaStreamDestroy(h->copy_stream);
   }
+  if (h->nll_exec) cudaGraphExecDestroy(h->nll_exec);
+  if (h->nll_graph) cudaGraphDestroy(h->nll_graph);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -340,6 +465,21 @@ int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const doubl
     VZ_CUDA(cudaStreamSynchronize(h->stream));
     finish(host[0] + host[1], host + 4);
     return (int)host[3];
+  }
+  {
+    // Replayed graph (no retry inside); a flagged pivot or any graph problem falls through to the
+    // eager path below, which has the jitter loop.
+    VZ_ARG(N >= 1 && n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
+    VZ_ARG(X != nullptr || Dc == 0, "X");
+    VZ_ARG(Z != nullptr || Dk == 0, "Z");
+    VZ_ARG(y != nullptr, "y");
+    double g2[2], gg[kMaxDc + kMaxDk + 2];
+    const int st = nll_graph_eval(h, X, Z, y, N, Dc, Dk, n_valid, p, g2, gg);
+    if (st < 0) return st;
+    if (st == 0) {
+      finish(g2[1] + g2[0], gg);
+      return 0;
+    }
   }
   double shift = 0.0;
   int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, &shift);

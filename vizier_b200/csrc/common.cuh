@@ -131,4 +131,13 @@ struct vzgp_handle {
   size_t pinned_bytes = 0;
   cudaStream_t copy_stream = nullptr;   // H2D staging of vzgp_score_host, overlapped with scoring
   cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  // CUDA graph of one NLL + gradient evaluation (c_abi.cu): the ARD loop re-evaluates the same shapes
+  // and buffers hundreds of times with new hyper-parameters; only three kernel nodes take them.
+  cudaGraph_t nll_graph = nullptr;
+  cudaGraphExec_t nll_exec = nullptr;
+  cudaGraphNode_t nll_nodes[3] = {nullptr, nullptr, nullptr};   // kernel matrix, transpose+scale, gradient tiles
+  const void* nll_key[3] = {nullptr, nullptr, nullptr};          // X, Z, y
+  int nll_key_dims[4] = {0, 0, 0, 0};                            // N, dc, dk, n_valid
+  int nll_launches = 0;
 };

@@ -13,6 +13,10 @@ int launch_cross_kernel(vzgp_handle* h, const double* Xs, const int32_t* Zs, int
 int potrf_blocked(vzgp_handle* h, double* L, int ld, double* Linv, int ldi, int np, int* flag);
 int trtri_doubling(vzgp_handle* h, const double* L, int ld, double* Linv, int ldi, double* T, int ldt,
                    int np);
+// Host-side entry addresses of the three kernels whose arguments carry the hyper-parameters (graph node lookup).
+const void* kernel_matrix_func();
+const void* transpose_scale_func();
+const void* nll_grad_tiles_func();
 constexpr int kLauumSplit = 4;   // K_y^-1 is produced as this many partial planes [z][np][ldk] (linalg.cu)
 int lauum_plane_rows(int np);
 int launch_lauum(vzgp_handle* h, const double* Linv, int ldi, double* Kinv, int ldk, int np);

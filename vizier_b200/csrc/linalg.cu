@@ -470,6 +470,9 @@ int fill_kernel_params(const vzgp_params* p, int dc, int dk, KernelParams* kp) {
   return 0;
 }
 
+const void* kernel_matrix_func() { return reinterpret_cast<const void*>(&k_kernel_matrix); }
+const void* transpose_scale_func() { return reinterpret_cast<const void*>(&k_transpose_scale); }
+
 int launch_kernel_matrix(vzgp_handle* h, const double* X, const int32_t* Z, int n, int n_valid,
                          const KernelParams& kp, double diag_add, double* K, int ldk) {
   int nb = (n + 63) / 64;

@@ -113,6 +113,8 @@ __global__ void k_reduce_partials(const double* __restrict__ partial, int ntiles
   if (threadIdx.x == 0) out[q] = s;
 }
 
+const void* nll_grad_tiles_func() { return reinterpret_cast<const void*>(&k_nll_grad_tiles); }
+
 int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
                           const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,
                           double* partial, double* out) {
