@@ -438,6 +438,9 @@ int launch_eagle_seed_priors(vzgp_handle* h, const EagleDev& e, const double* pr
 size_t eagle_suggest_smem(const EagleDev& e) {
   return sizeof(double) * (size_t)8 * (e.P + e.D) + sizeof(int32_t) * 8 * (size_t)(e.Dk + 2);
 }
+size_t eagle_suggest_cta_smem(const EagleDev& e) {
+  return sizeof(double) * ((size_t)e.P + e.D + 8 * (size_t)(e.D + 2) + 4 + 64) + sizeof(int32_t) * (size_t)(e.Dk + 2 + 16) + 16;
+}
 size_t eagle_update_smem(const EagleDev& e) {
   return sizeof(double) * (size_t)(e.B + e.count) + (size_t)(e.B + e.count) + 16;
 }

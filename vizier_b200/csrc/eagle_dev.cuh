@@ -198,6 +198,159 @@ __device__ __forceinline__ void eagle_suggest_block(const EagleDev& e, int vbloc
 }
 
 // ---------------------------------------------------------------------------
+// suggest, one CTA (NT threads) per batch fly: the same arithmetic as eagle_suggest_block with the
+// loops over the pool spread over the CTA (the one-warp-per-fly form is a ~2000-instruction latency
+// chain; in the cooperative grid kernel there are more CTAs than flies).  Sums over the pool are
+// formed per warp and combined in a fixed order.  Dynamic smem: eagle_suggest_cta_smem(e) bytes.
+// ---------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void eagle_suggest_cta(const EagleDev& e, int b, double* smem) {
+  constexpr int NW = NT / 32;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int P = e.P, B = e.B, D = e.D, Dk = e.Dk;
+  const int t = *e.iter;
+  const int nb = P / B;
+  const int i = (t % nb) * B + b;
+  double* s_f = smem;                          // [P]
+  double* s_x = s_f + P;                       // [D]
+  double* s_part = s_x + D;                    // [NW][D + 2]  per-warp partial sums
+  double* s_bc = s_part + NW * (D + 2);        // [4] broadcast scalars
+  double* s_lg = s_bc + 4;                     // [64] categorical logits
+  int32_t* s_z = reinterpret_cast<int32_t*>(s_lg + 64);   // [Dk]
+  int* s_cnt = s_z + Dk + (Dk & 1);            // [2 * NW]
+  for (int d = tid; d < D; d += NT) s_x[d] = e.pool[(size_t)i * D + d];
+  for (int d = tid; d < Dk; d += NT) s_z[d] = e.pool_z[(size_t)i * Dk + d];
+  __syncthreads();
+  double* out = e.batch + (size_t)b * D;
+  int32_t* outz = e.batch_z + (size_t)b * Dk;
+  if (t < nb) {  // still initialising: return the pool features (projected)
+    for (int d = tid; d < D; d += NT) out[d] = fmin(fmax(s_x[d], 0.0), 1.0);
+    for (int d = tid; d < Dk; d += NT) outz[d] = s_z[d];
+    __syncthreads();
+    return;
+  }
+  const double ri = e.rewards[i];
+  const double cexp = -e.cfg.visibility / (double)(D + Dk) * 10.0;
+  int npull = 0, npush = 0;
+  for (int j = tid; j < P; j += NT) {
+    const double d2 = fly_distance(s_x, e.pool + (size_t)j * D, D, s_z, e.pool_z + (size_t)j * Dk, Dk);
+    const double rj = e.rewards[j];
+    const double dir = rj - ri;
+    const double sd = (dir >= 0.0) ? e.cfg.gravity : -e.cfg.negative_gravity;
+    const double f = sd * exp(cexp * d2) * (isfinite(rj) ? 1.0 : 0.0);
+    s_f[j] = f;
+    npull += (f > 0.0);
+    npush += (f < 0.0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    npull += __shfl_xor_sync(0xffffffffu, npull, o);
+    npush += __shfl_xor_sync(0xffffffffu, npush, o);
+  }
+  if (lane == 0) { s_cnt[warp] = npull; s_cnt[NW + warp] = npush; }
+  __syncthreads();
+  npull = npush = 0;
+  for (int w = 0; w < NW; ++w) { npull += s_cnt[w]; npush += s_cnt[NW + w]; }
+  if (e.cfg.mutate_normalization_type == 1) {
+    // RANDOM normalisation (see eagle_suggest_block)
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = tid; j < P; j += NT) {
+      const double pos = s_f[j] > 0.0 ? 1.0 : 0.0;
+      s1 += philox_uniform(e.seed, kStreamPullRand, (uint32_t)t, (uint64_t)b * P + j) * pos;
+      s2 += philox_uniform(e.seed, kStreamPushRand, (uint32_t)t, (uint64_t)b * P + j) * pos;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) { s_part[warp * (D + 2)] = s1; s_part[warp * (D + 2) + 1] = s2; }
+    __syncthreads();
+    s1 = s2 = 0.0;
+    for (int w = 0; w < NW; ++w) { s1 += s_part[w * (D + 2)]; s2 += s_part[w * (D + 2) + 1]; }
+    __syncthreads();
+    for (int j = tid; j < P; j += NT) {
+      const double f = s_f[j];
+      const double pos = f > 0.0 ? 1.0 : 0.0;
+      const double w1 = s1 > 0.0 ? philox_uniform(e.seed, kStreamPullRand, (uint32_t)t, (uint64_t)b * P + j) * pos / s1 : 0.0;
+      const double w2 = s2 > 0.0 ? philox_uniform(e.seed, kStreamPushRand, (uint32_t)t, (uint64_t)b * P + j) * pos / s2 : 0.0;
+      s_f[j] = e.cfg.normalization_scale * fmax(f, 0.0) * w1 + e.cfg.normalization_scale * fmin(f, 0.0) * w2;
+    }
+  } else {
+    const double wpull = npull > 0 ? e.cfg.normalization_scale / (double)npull : 0.0;
+    const double wpush = npush > 0 ? e.cfg.normalization_scale / (double)npush : 0.0;
+    for (int j = tid; j < P; j += NT) {
+      const double f = s_f[j];
+      s_f[j] = f > 0.0 ? f * wpull : (f < 0.0 ? f * wpush : 0.0);
+    }
+  }
+  __syncthreads();
+  // ---- continuous features: warp w sums flies w, w + NW, ...; lane = dimension (and lane + 32) ----
+  {
+    double a0 = 0.0, a1 = 0.0, ss = 0.0;
+    const int d0 = lane, d1 = lane + 32;
+    for (int j = warp; j < P; j += NW) {
+      const double sc = s_f[j];
+      ss += sc;
+      const double* pj = e.pool + (size_t)j * D;
+      if (d0 < D) a0 = fma(sc, pj[d0], a0);
+      if (d1 < D) a1 = fma(sc, pj[d1], a1);
+    }
+    if (d0 < D) s_part[warp * (D + 2) + d0] = a0;
+    if (d1 < D) s_part[warp * (D + 2) + d1] = a1;
+    if (lane == 0) s_part[warp * (D + 2) + D] = ss;
+  }
+  __syncthreads();
+  const double pert = e.pert[i];
+  double ssum = 0.0;
+  for (int w = 0; w < NW; ++w) ssum += s_part[w * (D + 2) + D];
+  for (int d = tid; d < D; d += NT) {
+    double acc = 0.0;
+    for (int w = 0; w < NW; ++w) acc += s_part[w * (D + 2) + d];
+    const double u = philox_uniform(e.seed, kStreamPerturbSign, (uint32_t)t, (uint64_t)b * D + d);
+    const double v = s_x[d] + (acc - s_x[d] * ssum) + (u >= 0.5 ? pert : -pert);
+    out[d] = fmin(fmax(v, 0.0), 1.0);
+  }
+  // ---- categorical features: warp w takes categories w, w + NW, ...; lanes sum over the pool ----
+  if (Dk > 0) {
+    const double factor = D > 0 ? e.cfg.categorical_perturbation_factor : e.cfg.pure_categorical_perturbation_factor;
+    const double log_same = log(e.cfg.prob_same_category_without_perturbation);
+    for (int k = 0; k < Dk; ++k) {
+      const int size = e.sizes[k];
+      __syncthreads();
+      if (size <= 1) {
+        if (tid == 0) outz[k] = 0;
+        continue;
+      }
+      const double log_diff = log((1.0 - e.cfg.prob_same_category_without_perturbation) / ((double)size - 1.0));
+      for (int c = warp; c < size; c += NW) {
+        double lg = 0.0;
+        for (int j = lane; j < P; j += 32) lg += (e.pool_z[(size_t)j * Dk + k] == c) ? s_f[j] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+        if (lane == 0) {
+          lg += log_diff;
+          if (c == s_z[k]) lg += -ssum + log_same - log_diff;
+          const uint64_t el = ((uint64_t)b * Dk + k) * e.smax + c;
+          lg += laplace_from_uniform(philox_uniform(e.seed, kStreamCatLaplace, (uint32_t)t, el)) * factor * pert;
+          lg += gumbel_from_uniform(philox_uniform(e.seed, kStreamCatGumbel, (uint32_t)t, el));
+          s_lg[c] = lg;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double best_v = -INFINITY;
+        int best_c = 0;
+        for (int c = 0; c < size; ++c)
+          if (s_lg[c] > best_v) { best_v = s_lg[c]; best_c = c; }
+        outz[k] = best_c;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
 // update + trim + top-count bookkeeping: single CTA.  Dynamic smem: (B+count) doubles + flags.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ bool rank_better(double v, long long id, double bv, long long bid) {

@@ -8,7 +8,7 @@
 // grid-wide barrier (one atomic per CTA on a monotone counter + acquire spin).  Population state and
 // the K* / partial-sum workspaces stay in global memory (L2 resident).
 //
-//   phase S  CTAs 0..ceil(B/8)-1      eagle_suggest_block            -> batch
+//   phase S  one CTA per batch fly     eagle_suggest_cta              -> batch
 //   phase C  N/64 x tiles work items   cross_small_block (per model)  -> K* scratch, partial mu / L-inf
 //   phase V  N/16 x tiles work items   var_small_block  (per model)   -> partial sum W^2
 //   phase U  CTA 0                     fixed-order finalize (+ GP-UCB-PE combine), eagle_update_block
@@ -52,7 +52,6 @@ __global__ void __launch_bounds__(kSmallThreads) k_eagle_grid(const __grid_const
   unsigned gen = 0;
   const bool two = g.pe_mode >= 0;
   const int ntiles = (e.B + kTM - 1) / kTM;
-  const int nvb_s = (e.B + 7) / 8;
   const int rgs = ntiles == 1 ? (e.B + 15) / 16 : 4;     // 16-candidate row groups per tile
   const int c_a = (g.a.np / 64) * ntiles * rgs, c_b = two ? (g.b.np / 64) * ntiles * rgs : 0;
   const int v_a = (g.a.np / kVarCols) * ntiles, v_b = two ? (g.b.np / kVarCols) * ntiles : 0;
@@ -64,7 +63,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_eagle_grid(const __grid_const
 #endif
   for (int it = 0; it < g.steps; ++it) {
     // ---- S: new batch ----
-    for (int vb = blockIdx.x; vb < nvb_s; vb += nblk) eagle_suggest_block<8>(e, vb, smem);
+    for (int fb = blockIdx.x; fb < e.B; fb += nblk) eagle_suggest_cta<kSmallThreads>(e, fb, smem);   // one CTA per fly
     VZ_GT(0);
     grid_barrier(g.barrier, nblk, gen);
     VZ_GT(1);
@@ -182,7 +181,7 @@ int launch_eagle_grid(vzgp_handle* h, vzgp_handle* hB, const EagleDev& e, const 
     G.apply_tr = want_tr ? 1 : 0;
   }
   // dynamic shared memory = the largest phase
-  size_t sm = eagle_suggest_smem(e);
+  size_t sm = eagle_suggest_cta_smem(e);
   const size_t s_u = eagle_update_smem(e), s_c = cross_small_smem_bytes(h->dc, h->dk), s_v = var_small_smem_bytes();
   if (s_u > sm) sm = s_u;
   if (s_c > sm) sm = s_c;

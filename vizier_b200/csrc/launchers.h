@@ -118,6 +118,7 @@ int launch_eagle_grid(vzgp_handle* h, vzgp_handle* hB, const EagleDev& e, const 
                       const vzgp_pe_params* pe, int steps);
 size_t eagle_suggest_smem(const EagleDev& e);
 size_t eagle_update_smem(const EagleDev& e);
+size_t eagle_suggest_cta_smem(const EagleDev& e);
 int launch_eagle_init(vzgp_handle* h, const EagleDev& e);
 int launch_eagle_seed_priors(vzgp_handle* h, const EagleDev& e, const double* prior, const int32_t* prior_z,
                              const double* prior_r, int n, int* ord, double* chosen_r);
