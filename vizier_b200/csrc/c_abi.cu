@@ -756,13 +756,18 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   // Step 0 runs eagerly (it sizes every workspace); the remaining steps replay one captured
   // CUDA graph of the suggest -> score -> update sequence: the iteration counter and all state
   // live in device memory, so the launches are identical and the host only enqueues graphs.
+  bool done = false;
   if (n_ens <= 1 && eagle_persistent_eligible(h, pe ? hB : nullptr, e)) {
     // small study: the whole loop is one persistent single-CTA kernel
     VZ_TRY(launch_eagle_persistent64(h, pe ? hB : nullptr, e, acq, pe, steps));
+    done = true;
   } else if (n_ens <= 1 && eagle_grid_eligible(h, pe ? hB : nullptr, e)) {
-    // mid-size study: one cooperative launch, phases separated by grid barriers
-    VZ_TRY(launch_eagle_grid(h, pe ? hB : nullptr, e, acq, pe, steps));
-  } else {
+    // mid-size study: one cooperative launch, phases separated by grid barriers.  If the cooperative
+    // launch is refused (nothing has run then) the launch-per-phase loop below takes over.
+    done = launch_eagle_grid(h, pe ? hB : nullptr, e, acq, pe, steps) == 0;
+    if (!done) cudaGetLastError();
+  }
+  if (!done) {
   VZ_TRY(one_step());
   if (steps > 1) {
     const int64_t l0 = h->launches;
