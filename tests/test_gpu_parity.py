@@ -224,6 +224,33 @@ def test_nll_grad_small_near_singular(dev):
     assert abs(loss - want_l) < 1e-6 * max(1.0, abs(want_l))
 
 
+def test_nll_graph_survives_workspace_growth():
+  """The replayed NLL graph points into the handle's workspaces: a later, larger fit reallocates them and
+  the graph must be rebuilt, not replayed (same tensors, same shape -> same cache key)."""
+  gp = _gp()
+  d = gp.DeviceGP(0)
+  x, y, _ = _problem(130, 5, 23)
+  po, pg = _params(5, sf2=0.7, sn2=2e-3)
+  want_l, want_g = go.loss_and_grad(po.to_vector(), x, y)
+  xt = torch.from_numpy(x).cuda(); yt = torch.from_numpy(y).cuda()
+  f = d.make_loss_fn(xt, yt)
+  for _ in range(3):                      # capture + two replays
+    l1, g1 = f(pg.to_vector())
+  xb, yb, _ = _problem(700, 5, 24)
+  d.fit(xb, yb, pg)                       # grows every N x N workspace
+  l2, g2 = f(pg.to_vector())
+  assert l1 == l2
+  np.testing.assert_array_equal(g1, g2)
+  assert abs(l2 - want_l) < 1e-9 * max(1.0, abs(want_l))
+  np.testing.assert_allclose(g2, want_g, atol=1e-8 * max(1.0, np.max(np.abs(want_g))), rtol=0)
+  # and new hyper-parameters through the same graph
+  po2, pg2 = _params(5, sf2=1.3, sn2=5e-2)
+  w2, wg2 = go.loss_and_grad(po2.to_vector(), x, y)
+  l3, g3 = f(pg2.to_vector())
+  assert abs(l3 - w2) < 1e-9 * max(1.0, abs(w2))
+  np.testing.assert_allclose(g3, wg2, atol=1e-8 * max(1.0, np.max(np.abs(wg2))), rtol=0)
+
+
 def test_topk_ties_nan_and_order(dev):
   rng = np.random.default_rng(11)
   s = rng.normal(size=5000)

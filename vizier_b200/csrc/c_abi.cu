@@ -187,9 +187,16 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
   VZ_TRY(fill_kernel_params(p, dc, dk, &kp));
   double sn2 = p->observation_noise_variance;
   const int np = round_up(N, kBlk), nq = dc + dk + 2;
-  const bool hit = h->nll_exec && h->nll_key[0] == X && h->nll_key[1] == Z && h->nll_key[2] == y &&
-                   h->nll_key_dims[0] == N && h->nll_key_dims[1] == dc && h->nll_key_dims[2] == dk &&
-                   h->nll_key_dims[3] == n_valid;
+  auto bufs = [&](const void** o) {
+    const DevBuf* b[11] = {&h->X, &h->XT, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->small};
+    for (int q = 0; q < 11; ++q) o[q] = b[q]->ptr;
+  };
+  const void* cur[11];
+  bufs(cur);
+  bool hit = h->nll_exec && h->nll_key[0] == X && h->nll_key[1] == Z && h->nll_key[2] == y &&
+             h->nll_key_dims[0] == N && h->nll_key_dims[1] == dc && h->nll_key_dims[2] == dk &&
+             h->nll_key_dims[3] == n_valid;
+  for (int q = 0; hit && q < 11; ++q) hit = cur[q] == h->nll_bufs[q];   // a workspace was reallocated since the capture
   h->fitted = false;
   if (!hit) {
     nll_graph_drop(h);
@@ -225,6 +232,7 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
     for (int q = 0; q < 3; ++q) h->nll_nodes[q] = found[q];
     h->nll_key[0] = X; h->nll_key[1] = Z; h->nll_key[2] = y;
     h->nll_key_dims[0] = N; h->nll_key_dims[1] = dc; h->nll_key_dims[2] = dk; h->nll_key_dims[3] = n_valid;
+    bufs(h->nll_bufs);
   }
   h->kp = kp; h->sn2 = sn2;
   // new hyper-parameters: argument 4 (+5) of the kernel matrix, 3 of transpose+scale, 4 of the gradient tiles

@@ -139,5 +139,6 @@ struct vzgp_handle {
   cudaGraphNode_t nll_nodes[3] = {nullptr, nullptr, nullptr};   // kernel matrix, transpose+scale, gradient tiles
   const void* nll_key[3] = {nullptr, nullptr, nullptr};          // X, Z, y
   int nll_key_dims[4] = {0, 0, 0, 0};                            // N, dc, dk, n_valid
+  const void* nll_bufs[11] = {};                                 // handle buffers the graph points into (a growth reallocates them)
   int nll_launches = 0;
 };
