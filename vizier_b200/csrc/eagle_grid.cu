@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_eagle_grid(const __grid_const
       const bool on_b = w >= v_a;
       const ScoreArgs& s = on_b ? g.b : g.a;
       const int q = on_b ? w - v_a : w, nvb = s.np / kVarCols;
-      var_small_block(s, q % nvb, q / nvb, smem);
+      var_small_dispatch(s, q % nvb, q / nvb, smem);
       __syncthreads();
     }
     VZ_GT(4);

@@ -32,33 +32,6 @@ using GP1 = GemmCfg<64, 64, 16, 2, 4>;  // phase-1 thread mapping: 512 threads, 
 constexpr int kThreads = 512;        // consumer threads (16 math warps)
 constexpr int kBlockThreads = 544;   // + one TMA producer warp
 
-// ---- mbarrier / TMA (cp.async.bulk.tensor) primitives --------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// 2-D tile load: box origin (c0 = column / innermost, c1 = row); completion bytes land on `bar`.
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
-
 // Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 32, 3-stage cp.async
 // ring.  16 warps as 4 (M) x 4 (N): each warp owns a 16 x 32 block = 2 x 4 DMMA tiles.
 constexpr int kBN = 128;         // output columns per pass
@@ -386,9 +359,9 @@ __global__ void __launch_bounds__(kSmallThreads) k_cross_small(const ScoreArgs a
   extern __shared__ double smem_raw[];
   cross_small_block<WITH_LINF>(a, blockIdx.x, blockIdx.y >> 2, blockIdx.y & 3, smem_raw);
 }
-__global__ void __launch_bounds__(kSmallThreads) k_var_small(const ScoreArgs a) {
+__global__ void __launch_bounds__(kSmallThreads) k_var_small(const __grid_constant__ ScoreArgs a) {
   extern __shared__ double smem_raw[];
-  var_small_block(a, blockIdx.x, blockIdx.y, smem_raw);
+  var_small_dispatch(a, blockIdx.x, blockIdx.y, smem_raw);
 }
 template <bool WITH_LINF>
 __global__ void __launch_bounds__(256) k_small_finalize(const ScoreArgs a) {
@@ -399,7 +372,10 @@ __global__ void __launch_bounds__(256) k_small_finalize(const ScoreArgs a) {
 }
 
 size_t cross_small_smem_bytes(int dc, int dk) { return sizeof(double) * 2 * dc * kLD1 + sizeof(int32_t) * 2 * dk * kLD1; }
-size_t var_small_smem_bytes() { return sizeof(double) * kVarStages * kVarStageDoubles; }
+size_t var_small_smem_bytes() {
+  const size_t cp = sizeof(double) * kVarStages * kVarStageDoubles, tma = 1024 + sizeof(double) * kVarStages * kVarTmaStageDoubles;
+  return cp > tma ? cp : tma;
+}
 
 // ---- host side: TMA descriptors ------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -491,6 +467,9 @@ static void fill_score_args(vzgp_handle* h, const double* Xs, const int32_t* Zs,
   a.scratch = h->scratch.as<double>();
   a.mpad = ntiles * kTM;
   a.nsplit = 1;
+  a.box_rows = kTM;
+  static const int tma_small = [] { const char* e = getenv("VZGP_SMALL_TMA"); return e ? atoi(e) : 1; }();   // 0: cp.async variant
+  a.use_tma = tma_small;
   a.part = a.part_rs = a.part_mu = a.part_linf = nullptr;
   a.score = score; a.mu = mu; a.sigma = sigma; a.linf = linf;
   a.clamp_count = h->small.as<int>();  // slot 0
@@ -507,6 +486,10 @@ int prepare_small_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int
   a->part_mu = a->part_rs + (size_t)nvb * a->mpad;
   a->part_linf = a->part_mu + (size_t)nmb * a->mpad;
   *with_linf = (linf != nullptr) || (a->apply_tr && a->radius <= 0.5);
+  // TMA boxes of the W phase: K* rows of one tile x 16 doubles, and 8 rows of Linv x 16 doubles.
+  a->box_rows = ntiles == 1 ? ((M + 7) / 8) * 8 : kTM;
+  VZ_TRY(make_map(&a->mapA, a->scratch, (uint64_t)ntiles * kTM, (uint64_t)h->np, (uint64_t)h->np, (uint32_t)a->box_rows));
+  VZ_TRY(make_map(&a->mapB, a->Linv, (uint64_t)h->np, (uint64_t)h->np, (uint64_t)h->np, kVarCols));
   return 0;
 }
 

@@ -42,6 +42,8 @@ struct ScoreArgs {
   double* part_rs;    // [np/16][Mpad] partial row sums of W^2, one row per 16-column block
   double* part_mu;    // [np/64][Mpad] partial means, one row per 64-trial block
   double* part_linf;  // [np/64][Mpad] partial trust-region distances
+  int box_rows;       // rows of the K* TMA box (small-pool W phase)
+  int use_tma;        // small-pool W phase: TMA boxes instead of cp.async
   double* score;
   double* mu;
   double* sigma;
@@ -60,6 +62,33 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// ---- mbarrier / TMA (cp.async.bulk.tensor) primitives --------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 2-D tile load: box origin (c0 = column / innermost, c1 = row); completion bytes land on `bar`.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
 // Final score from the reduced pieces (shared by the fused epilogue and the split finalize kernel).
 __device__ __forceinline__ void emit_score(const ScoreArgs& a, int m, double rs, double mean, double dist,
                                            int& clamped) {
@@ -287,6 +316,83 @@ __device__ __forceinline__ void var_small_block(const ScoreArgs& a, int b, int t
     rs += __shfl_xor_sync(0xffffffffu, rs, 2);
     if (fk == 0) a.part_rs[(size_t)b * a.mpad + m0 + warp * 8 + fr] = rs;
   }
+}
+
+// The same work item with the operands fetched by the TMA unit: per 64-wide slab four K* boxes
+// (box_rows x 16 doubles) and four Linv boxes (8 x 16 doubles), 128-byte swizzle, one elected thread
+// issues them and a per-stage mbarrier counts the bytes; the DMMA warps read the swizzled fragments as in
+// k_score.  No per-thread copy instructions at all.
+constexpr int kVarTmaStageDoubles = (kTM + kVarCols) * kVarBK;    // dense boxes
+__device__ __forceinline__ void var_small_block_tma(const ScoreArgs& a, int b, int tile, double* smem_raw) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int m0 = tile * kTM;
+  const int rows = min(kTM, a.M - m0);
+  const int nmt = (rows + 7) >> 3;
+  const int kext = kVarCols * (b + 1);
+  const int nslab = (kext + kVarBK - 1) / kVarBK;
+  double* base = smem_raw + (((1024u - (static_cast<unsigned>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u) >> 3);
+  const int abox = a.box_rows * 16;                 // doubles per K* box
+  __shared__ uint64_t full_bar[kVarStages];
+  if (tid == 0) {
+    for (int s2 = 0; s2 < kVarStages; ++s2) mbar_init(full_bar + s2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  fence_proxy_async();            // K* was written through the generic proxy (previous phase / kernel)
+  __syncthreads();
+  auto issue = [&](int ks) {      // one thread
+    const int stage = ks % kVarStages;
+    double* stg = base + stage * kVarTmaStageDoubles;
+    mbar_expect_tx(full_bar + stage, (unsigned)((a.box_rows + kVarCols) * kVarBK * sizeof(double)));
+#pragma unroll
+    for (int q = 0; q < kVarBK / 16; ++q) {
+      tma_load_2d(stg + q * abox, &a.mapA, ks * kVarBK + 16 * q, tile * kTM, full_bar + stage);
+      tma_load_2d(stg + 4 * abox + q * kVarCols * 16, &a.mapB, ks * kVarBK + 16 * q, b * kVarCols, full_bar + stage);
+    }
+  };
+  if (tid == 0)
+    for (int s2 = 0; s2 < kVarStages - 1 && s2 < nslab; ++s2) issue(s2);
+  double acc[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+  for (int ks = 0; ks < nslab; ++ks) {
+    if (ks > 0) __syncthreads();             // slab ks-1 consumed by every warp: its stage may be refilled
+    if (tid == 0 && ks + kVarStages - 1 < nslab) issue(ks + kVarStages - 1);
+    if (warp < nmt) {
+      mbar_wait(full_bar + ks % kVarStages, (ks / kVarStages) & 1);
+      const double* stg = base + (ks % kVarStages) * kVarTmaStageDoubles;
+      const double* Ar = stg + (warp * 8 + fr) * 16;
+      const double* Br = stg + 4 * abox + fr * 16;
+#pragma unroll
+      for (int q = 0; q < kVarBK / 16; ++q)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int co = (((hh * 4 + fk) ^ fr) * 2);      // swizzled 16-byte chunk, in doubles
+          const double2 av = *reinterpret_cast<const double2*>(Ar + q * abox + co);
+          const double2 bv = *reinterpret_cast<const double2*>(Br + q * kVarCols * 16 + co);
+          const int c = hh * 2;
+          dmma_8x8x4(acc[c][0], acc[c][1], av.x, bv.x);
+          dmma_8x8x4(acc[c + 1][0], acc[c + 1][1], av.y, bv.y);
+        }
+    }
+  }
+  __syncthreads();                           // nobody still polls the barriers (re-initialised by the next call)
+  if (warp < nmt) {
+    double rs = 0.0;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double w = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]);
+      rs = fma(w, w, rs);
+    }
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    if (fk == 0) a.part_rs[(size_t)b * a.mpad + m0 + warp * 8 + fr] = rs;
+  }
+}
+
+__device__ __forceinline__ void var_small_dispatch(const ScoreArgs& a, int b, int tile, double* smem_raw) {
+  if (a.use_tma) var_small_block_tma(a, b, tile, smem_raw);
+  else var_small_block(a, b, tile, smem_raw);
 }
 
 // EIGHT lanes per candidate m (lane group p = 0..7 sums partials p, p + 8, ... then a fixed shuffle tree):
