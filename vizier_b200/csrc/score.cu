@@ -13,7 +13,8 @@
 //            staged rows; mu = K* alpha and the L-inf trust-region distance are reduced on the
 //            fly; the tile goes to a CTA-private scratch (L2 resident, never re-read by others).
 //   phase 2  W = K* . Linv^T in 64 x 128 blocks on the FP64 tensor pipe (mma.sync m8n8k4 f64;
-//            tcgen05 has no f64 kind), operands staged by a 4-deep cp.async ring, exploiting that
+//            tcgen05 has no f64 kind), operands streamed by a TMA producer warp (cp.async.bulk.tensor,
+//            128-byte swizzle) through a 4-stage ring with full/empty mbarriers, exploiting that
 //            Linv is lower triangular (k <= j, all-zero fragments skipped); each block is squared
 //            and row-summed in registers, W is never stored.
 //   epilogue var = sf2 + sn2 - sum W^2 (clamped at 0), sigma, UCB, trust region, outputs.
@@ -32,8 +33,8 @@ using GP1 = GemmCfg<64, 64, 16, 2, 4>;  // phase-1 thread mapping: 512 threads, 
 constexpr int kThreads = 512;        // consumer threads (16 math warps)
 constexpr int kBlockThreads = 544;   // + one TMA producer warp
 
-// Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 32, 3-stage cp.async
-// ring.  16 warps as 4 (M) x 4 (N): each warp owns a 16 x 32 block = 2 x 4 DMMA tiles.
+// Phase-2 tiling: 64 candidates x 128 output columns per pass, k-slabs of 32, 4-stage TMA ring.
+// 16 warps as 4 (M) x 4 (N): each warp owns a 16 x 32 block = 2 x 4 DMMA tiles.
 constexpr int kBN = 128;         // output columns per pass
 constexpr int kBK = 32;          // k-slab = two TMA boxes of 16 doubles (one 128-byte swizzle atom per row)
 constexpr int kStages = 4;
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) k_score(const __grid_constan
     // ---------------- phase 2: row sums of (K* Linv^T)^2 on the DMMA pipe ----------------
     // Slab (jb, ks): A = scratch[0:64, ks*16 : +16], B = Linv[jb*128 : +128, ks*16 : +16];
     // block jb needs ks < min(np, (jb+1)*128)/16 because Linv is lower triangular.  The slab
-    // stream is flattened over blocks so the cp.async ring never drains between blocks.
+    // stream is flattened over blocks so the TMA ring never drains between blocks.
     // With nsplit > 1 this CTA takes blocks {split, nblocks-1-split} (balanced triangular work).
     double rowsq[2] = {0.0, 0.0};
     for (int q = 0; q < nq; ++q) {
