@@ -142,7 +142,11 @@ int vzgp_get_alpha(vzgp_handle* h, double* alpha);
  * through jaxopt at jaxopt_wrappers.py:139-152): loss = -log N(y;0,K_y) +
  * regularisers; grad in the order [categorical ls2 (Dk), continuous ls2 (Dc),
  * noise variance, signal variance] (jaxopt's sorted-key flattening).
- * loss_out [1], grad_out [Dk+Dc+2] are HOST.  Returns Cholesky retries. */
+ * loss_out [1], grad_out [Dk+Dc+2] are HOST.  Returns Cholesky retries.
+ * The handle's fitted model is NOT valid afterwards (call vzgp_fit with the chosen parameters).
+ * Execution: N <= 64 is one single-CTA kernel; larger N replays a CUDA graph of the launch sequence that
+ * is captured on the first call with a given (X, Z, y, N, Dc, Dk, n_valid) and re-parameterised per
+ * call - keep the buffers alive and unchanged in shape across an optimisation run to benefit. */
 int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
                   int Dk, int n_valid, const vzgp_params* p, double* loss_out, double* grad_out);
 
@@ -232,7 +236,10 @@ typedef struct vzgp_eagle_config {
  * be NULL/0) are the observed trials in creation order.  cat_sizes (host, [Dk])
  * = number of categories of each categorical feature (<= 64).  best_x
  * [count x Dc], best_z [count x Dk], best_score [count] are HOST outputs, best
- * first.  Randomness: Philox4x32-10 keyed by `seed`. */
+ * first.  Randomness: Philox4x32-10 keyed by `seed`.
+ * Execution: the whole loop runs on the device - one persistent single-CTA kernel (N <= 64 trials,
+ * batch <= 64), one cooperative persistent grid (batch <= 512), otherwise a replayed CUDA graph of the
+ * per-step launches; the result does not depend on which. */
 int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
                    const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
                    int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score);
