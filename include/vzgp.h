@@ -239,7 +239,7 @@ typedef struct vzgp_eagle_config {
  * first.  Randomness: Philox4x32-10 keyed by `seed`.
  * Execution: the whole loop runs on the device - one persistent single-CTA kernel (N <= 64 trials,
  * batch <= 64), one cooperative persistent grid (batch <= 512), otherwise a replayed CUDA graph of the
- * per-step launches; the result does not depend on which. */
+ * per-step launches; the forms agree to rounding (sums over the pool are grouped differently). */
 int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
                    const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
                    int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score);
