@@ -117,6 +117,29 @@ def test_ensemble_designer_suggest_sample_predict():
     gp_bandit.VizierGPBandit.from_problem(p, ensemble_size=9)
 
 
+def test_gp_ucb_pe_sample_and_predict():
+  """gp_ucb_pe.py:1262-1354: sample() / predict() shapes, finiteness, and a sane posterior mean."""
+  from vizier_b200.designers import gp_ucb_pe
+  p = _problem(2)
+  f = lambda x: -np.sum((x - 1.0) ** 2)
+  rng = np.random.default_rng(5)
+  trials = []
+  for i in range(25):
+    t = vz.Trial(parameters={f'x{j}': float(v) for j, v in enumerate(rng.uniform(-5, 5, 2))}, id=i + 1)
+    t.complete(vz.Measurement({'obj': float(f(np.array([t.parameters['x0'].value, t.parameters['x1'].value])))}))
+    trials.append(t)
+  d = gp_ucb_pe.VizierGPUCBPEBandit(p, rng=3)
+  d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  pts = [vz.Trial(parameters={'x0': a, 'x1': b}) for a, b in ((1.0, 1.0), (-4.0, 4.0), (0.0, 2.0))]
+  s = d.sample(pts, num_samples=7)
+  assert s.shape == (7, 3) and np.isfinite(s).all()
+  assert d.sample([], num_samples=4).shape == (4, 0)
+  pr = d.predict(pts, num_samples=400)
+  assert len(pr.mean) == 3 and np.isfinite(pr.mean).all() and (pr.stddev >= 0).all()
+  assert pr.mean[0] > pr.mean[1]          # the optimum region predicts higher than a far corner
+  assert abs(pr.mean[0] - f(np.array([1.0, 1.0]))) < 3.0
+
+
 def test_two_studies_concurrently_match_sequential():
   """Different studies may call suggest() concurrently (vizier_service.py:297 only serialises per study):
   two designers driven from two threads on one GPU give exactly what they give one after the other."""

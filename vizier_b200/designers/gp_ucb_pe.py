@@ -15,7 +15,8 @@ configuration (`UCBPEConfig()` with `optimize_set_acquisition_for_exploration=Fa
     (:678-698).
 
 Everything numeric runs in libvzgp (two handles on one stream, `vzgp_score_pe`,
-`vzgp_eagle_run_pe`).  Not implemented: multi-metric, set-PE batches
+`vzgp_eagle_run_pe`); `sample` / `predict` (:1262-1354) draw from the device-computed joint posterior
+like `VizierGPBandit`.  Not implemented: multi-metric, set-PE batches
 (`optimize_set_acquisition_for_exploration=True`), `prior_acquisition`, linear-kernel mixing,
 ensembles, padding - each raises NotImplementedError.
 """
@@ -291,3 +292,31 @@ class VizierGPUCBPEBandit:
       out.append(s)
       active.append(s.to_trial())
     return out
+
+  # ------------------------------------------------------------------ sample / predict
+  @profiler.record_runtime
+  def sample(self, trials: Sequence[Any], rng: Any = None, num_samples: int = 1000) -> np.ndarray:
+    """gp_ucb_pe.py:1262-1329: unwarped joint posterior samples of the model on the COMPLETED trials
+    (re-trained like the reference does), shape (num_samples, num_trials)."""
+    if not trials:
+      return np.zeros((num_samples, 0))
+    cont, cat, labels = self._trials_to_data(self._all_completed_trials)
+    if cont.shape[0] == 0:
+      raise NotImplementedError('sample() before any completed trial is not implemented (prior-only GP).')
+    params = self._build_gp_model_and_optimize_parameters(cont, cat, labels)
+    dev_a, _ = self._devices()
+    dev_a.fit(cont, labels[:, 0], params, z=cat if cat.shape[1] else None)
+    xs, zs = self._converter.to_features(trials)
+    xs = np.nan_to_num(xs, nan=0.0)
+    mean, cov = dev_a.posterior(xs, zs if zs.shape[1] else None, add_noise=True)
+    chol, _, _ = dev_a.cholesky_retry(cov, jitter=1e-10, max_iters=8)
+    g = np.random.default_rng(_gpb._seed_from(rng) if rng is not None else 0)
+    samples = mean.cpu().numpy()[None, :] + g.standard_normal((num_samples, mean.shape[0])) @ chol.cpu().numpy().T
+    return np.vstack([self._output_warper.unwarp(samples[i][:, None]).reshape(-1) for i in range(num_samples)])
+
+  @profiler.record_runtime
+  def predict(self, trials: Sequence[Any], rng: Any = None, num_samples: Optional[int] = 1000):
+    """gp_ucb_pe.py:1331-1354: empirical mean / stddev of the unwarped samples."""
+    s = self.sample(trials, rng, num_samples or 1000)
+    return vz.Prediction(mean=np.mean(s, axis=0), stddev=np.std(s, axis=0))
+
