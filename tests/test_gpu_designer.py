@@ -117,6 +117,35 @@ def test_ensemble_designer_suggest_sample_predict():
     gp_bandit.VizierGPBandit.from_problem(p, ensemble_size=9)
 
 
+def test_gp_ucb_pe_only_active_trials():
+  """Parallel workers at study start: suggestions are requested while the seed trials are still ACTIVE and
+  nothing has completed.  The reference runs its normal code on an empty data set (gp_ucb_pe.py:1356-1445,
+  :1006-1155); here that is pure exploration on the GP conditioned on the pending points."""
+  import datetime
+  from vizier_b200.designers import gp_ucb_pe
+  p = _problem(2, lo=0.0, hi=1.0)
+  d = gp_ucb_pe.VizierGPUCBPEBandit(p, rng=5, acquisition_optimizer_factory=vb.VectorizedOptimizerFactory(
+      strategy_factory=vb.VectorizedEagleStrategyFactory(eagle_config=gp_ucb_pe.default_eagle_config),
+      max_evaluations=3000, suggestion_batch_size=25))
+  seeds = d.suggest(1)
+  active = []
+  for i, sgg in enumerate(seeds):
+    t = sgg.to_trial(i + 1)
+    t.creation_time = datetime.datetime.now()
+    active.append(t)
+  d.update(vz.CompletedTrials([]), vz.ActiveTrials(active))
+  out = d.suggest(3)
+  assert len(out) == 3
+  pts = np.array([[s.parameters['x0'].value, s.parameters['x1'].value] for s in out])
+  pend = np.array([[t.parameters['x0'].value, t.parameters['x1'].value] for t in active])
+  assert ((pts >= 0) & (pts <= 1)).all()
+  every = np.vstack([pend, pts])
+  dist = np.linalg.norm(every[:, None, :] - every[None, :, :], axis=-1) + np.eye(len(every))
+  assert dist.min() > 0.05                                       # exploration: nothing piles up on a pending point
+  info = json.loads(out[0].metadata.ns('devinfo')['acquisition_optimization'])
+  assert info['mean'] == 0.0 and info['stddev_from_all'] <= info['stddev'] + 1e-12
+
+
 def test_gp_ucb_pe_sample_and_predict():
   """gp_ucb_pe.py:1262-1354: sample() / predict() shapes, finiteness, and a sane posterior mean."""
   from vizier_b200.designers import gp_ucb_pe

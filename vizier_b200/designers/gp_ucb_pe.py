@@ -276,11 +276,9 @@ class VizierGPUCBPEBandit:
     cont, cat, labels = self._trials_to_data(self._all_completed_trials)
     params = self._build_gp_model_and_optimize_parameters(cont, cat, labels)
     dev_a, _ = self._devices()
-    if cont.shape[0] > 0:
+    prior_only = cont.shape[0] == 0          # only ACTIVE trials so far (parallel workers at study start)
+    if not prior_only:
       dev_a.fit(cont, labels[:, 0], params, z=cat if cat.shape[1] else None)
-    else:
-      raise NotImplementedError('suggest() with only ACTIVE trials and no completed trial is not implemented '
-                                '(the reference falls back to a prior-only GP).')
     act_c, _ = self._converter.to_features(self._all_active_trials)
     n_tr = cont.shape[0] + act_c.shape[0]   # trust region: completed + initially active trials (:1377-1403)
     mask = acq_lib.trust_region_dim_mask(self._converter.continuous_feasible_values(_MAX_NUM_FEASIBLE_VALUES_FOR_TRUST_REGION))
@@ -288,10 +286,50 @@ class VizierGPUCBPEBandit:
     active = list(self._all_active_trials)
     out = []
     for _ in range(count):
-      s = self._suggest_one(active, cont, cat, labels, params, mask, radius, n_tr)
+      if prior_only:
+        s = self._suggest_one_prior_only(active, params, mask, radius, n_tr)
+      else:
+        s = self._suggest_one(active, cont, cat, labels, params, mask, radius, n_tr)
       out.append(s)
       active.append(s.to_trial())
     return out
+
+  @profiler.record_runtime
+  def _suggest_one_prior_only(self, active_trials, params, mask, radius, n_tr_rows):
+    """No completed trial yet, only pending ones.  The reference then runs the same code on an empty
+    data set (:1006-1155): model A is the GP prior (mean 0, stddev sqrt(sf2 + sn2)), the UCB threshold
+    degenerates to the prior mean 0 (_compute_ucb_threshold over no valid point, :175-218), so both the
+    PE acquisition  stddev_B + 10 min(0 + 0.5 stddev_A - 0, 0)  and the UCB acquisition  0 + 1.8 stddev_B
+    are maximised by the stddev of model B = the GP conditioned on the pending points with dummy labels.
+    That is `vzgp_eagle_run` on model B with a unit UCB coefficient (its mean is exactly 0)."""
+    start = datetime.datetime.now()
+    cfg = self._config
+    _, dev_b = self._devices()
+    snr = params.signal_variance / max(params.observation_noise_variance, 1e-12)
+    noise_is_high = snr < cfg.signal_to_noise_threshold
+    pend_c, pend_z = self._converter.to_features(active_trials)
+    pend_c = np.nan_to_num(pend_c, nan=0.0)
+    empty_c = np.zeros((0, pend_c.shape[1])); empty_z = np.zeros((0, pend_z.shape[1]), np.int32)
+    self._fit_all_features(params, empty_c, empty_z, np.zeros((0, 1)), pend_c, pend_z, noise_is_high)
+    acq = gp.Acquisition(1.0, self._use_trust_region, radius, mask, tr_rows=n_tr_rows, tr_strict=True)
+    optimizer = self._acquisition_optimizer_factory(self._converter)
+    res = optimizer(dev_b, acq, count=1, prior_features=None, prior_categorical=None, seed=int(self._rng.integers(2**62)))
+    params_dict = self._converter.to_parameters(res.features[0:1], None if res.categorical is None else res.categorical[0:1])[0]
+    prior_sd = float(np.sqrt(params.signal_variance + params.observation_noise_variance))
+    sd_all = float(res.aux['stddev'][0]) if 'stddev' in res.aux else float(res.rewards[0])
+    md = vz.Metadata()
+    md.ns('devinfo')['acquisition_optimization'] = json.dumps(
+        {'acquisition': float(res.rewards[0]), 'mean': 0.0, 'stddev': prior_sd, 'stddev_from_all': sd_all})
+    pred = md.ns(self._metadata_ns).ns('prediction_in_warped_y_space')
+    pred['mean'] = repr(0.0)
+    pred['stddev'] = repr(prior_sd)
+    pred['stddev_from_all'] = repr(sd_all)
+    pred['acquisition'] = f'{float(res.rewards[0])}'
+    pred['use_ucb'] = 'False'
+    pred['trust_radius'] = f'{radius}'
+    pred['params'] = f'{params}'
+    md.ns(self._metadata_ns).ns('timing')['time'] = f'{datetime.datetime.now() - start}'
+    return vz.TrialSuggestion(params_dict, metadata=md)
 
   # ------------------------------------------------------------------ sample / predict
   @profiler.record_runtime
