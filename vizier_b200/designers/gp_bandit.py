@@ -223,8 +223,9 @@ class VizierGPBandit:
 
   # ------------------------------------------------------------------ suggest / predict / sample
   @profiler.record_runtime
-  def suggest(self, count: int = 1) -> Sequence[Any]:
+  def suggest(self, count: Optional[int] = 1) -> Sequence[Any]:
     """gp_bandit.py:523-559."""
+    count = count or 1   # Designer.suggest(count=None) means "as many as you like": one (abstractions.py:118-131)
     if len(self._trials) < self._num_seed_trials:
       return self._generate_seed_trials(count)
     start = datetime.datetime.now()
