@@ -95,3 +95,23 @@ def test_lean_lbfgsb_driver_is_scipy_minimize():
     x, fv = ard._lean_lbfgsb(f, x0, bounds, maxiter=maxiter, gtol=1e-8, maxls=20)
     np.testing.assert_array_equal(x, want.x)
     assert fv == want.fun
+
+
+def test_sorted_prior_features_reuse_converted_arrays():
+  """trials_to_sorted_features(trials, converter, features) only permutes already converted arrays
+  (vectorized_base.py:655-665 order: creation time, then insertion)."""
+  import datetime
+  p = vz.ProblemStatement()
+  p.search_space.root.add_float_param('a', 0, 1)
+  p.search_space.root.add_categorical_param('c', ['x', 'y', 'z'])
+  p.metric_information.append(vz.MetricInformation(name='m', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  rng = np.random.default_rng(0)
+  t0 = datetime.datetime(2024, 1, 1)
+  ts = [vz.Trial(parameters={'a': float(rng.uniform()), 'c': ['x', 'y', 'z'][i % 3]}, id=i + 1,
+                 creation_time=t0 + datetime.timedelta(seconds=int(rng.integers(0, 10)))) for i in range(30)]
+  c = converters.TrialToModelInputConverter.from_problem(p)
+  a = converters.trials_to_sorted_features(ts, c)
+  b = converters.trials_to_sorted_features(ts, c, c.to_features(ts))
+  np.testing.assert_array_equal(a[0], b[0])
+  np.testing.assert_array_equal(a[1], b[1])
+  assert converters.trials_to_sorted_features([], c, None) is None

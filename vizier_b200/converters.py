@@ -202,9 +202,16 @@ class TrialToModelInputConverter:
     return res
 
 
-def trials_to_sorted_features(trials: Sequence[Any], converter: TrialToModelInputConverter):
-  """vectorized_base.py:655-665: prior trials ordered by creation time."""
+def trials_to_sorted_features(trials: Sequence[Any], converter: TrialToModelInputConverter, features=None):
+  """vectorized_base.py:655-665: prior trials ordered by creation time.
+
+  `features` = (continuous, categorical) already converted for `trials` in the given order: only the
+  permutation is applied then (the conversion is an O(N*D) Python loop, worth not repeating per suggestion)."""
   if not trials:
     return None
-  ordered = sorted(trials, key=lambda t: (t.creation_time, getattr(t, '_seq', 0)))
-  return converter.to_features(ordered)
+  order = sorted(range(len(trials)), key=lambda i: (trials[i].creation_time, getattr(trials[i], '_seq', 0)))
+  if features is not None:
+    cont, cat = features
+    idx = np.asarray(order, dtype=np.int64)
+    return cont[idx], cat[idx]
+  return converter.to_features([trials[i] for i in order])

@@ -198,9 +198,9 @@ class VizierGPBandit:
         ucb_coefficient=self._ucb_coefficient)
 
   @profiler.record_runtime
-  def _optimize_acquisition(self, dev: gp.DeviceGP, acq: gp.Acquisition, count: int):
+  def _optimize_acquisition(self, dev: gp.DeviceGP, acq: gp.Acquisition, count: int, features=None):
     """gp_bandit.py:482-521 + vectorized_base.best_candidates_to_trials (:591-651)."""
-    prior = converters.trials_to_sorted_features(self._trials, self._converter)
+    prior = converters.trials_to_sorted_features(self._trials, self._converter, features)
     seed = int(self._rng.integers(2**62))
     res = self._acquisition_optimizer(dev, acq, count=count, prior_features=None if prior is None else prior[0],
                                       prior_categorical=None if prior is None else prior[1], seed=seed)
@@ -232,7 +232,7 @@ class VizierGPBandit:
     cont, cat, labels = self._trials_to_data(self._trials)
     dev = self._update_gp(cont, cat, labels)
     acq = self._acquisition(cont.shape[0])
-    best = self._optimize_acquisition(dev, acq, count)
+    best = self._optimize_acquisition(dev, acq, count, features=(cont, cat))
     out = []
     for t in best:
       t.metadata.ns(self._metadata_ns).ns('devinfo')['time_spent'] = f'{datetime.datetime.now() - start}'

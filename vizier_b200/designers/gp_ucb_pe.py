@@ -247,7 +247,7 @@ class VizierGPUCBPEBandit:
         penalty_coefficient=cfg.cb_violation_penalty_coefficient, threshold=threshold,
         use_trust_region=self._use_trust_region, trust_radius=radius, tr_dim_mask=mask, tr_rows=n_tr_rows)
     optimizer = self._acquisition_optimizer_factory(self._converter)
-    prior = converters.trials_to_sorted_features(self._all_completed_trials, self._converter)
+    prior = converters.trials_to_sorted_features(self._all_completed_trials, self._converter, (cont, cat))
     seed = int(self._rng.integers(2**62))
     res = optimizer(dev_a, pe, count=1, prior_features=None if prior is None else prior[0],
                     prior_categorical=None if prior is None else prior[1], seed=seed, other=dev_b)
