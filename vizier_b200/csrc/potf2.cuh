@@ -24,6 +24,18 @@ namespace vzgp {
 //    the trailing part is updated by the whole CTA with 16-wide register tiles.
 //  * the inverse: the four 16x16 diagonal blocks (one warp each, lane = column) and two
 //    recursive-doubling levels  X21 = -B^-1 (C A^-1)  with fully unrolled dot products.
+// 1/d to ~1 ulp without the IEEE division sequence (and its slow-path check): MUFU.RCP64H seed
+// (`rcp.approx.ftz.f64`, ~20 bits) + two Newton steps.  This sits on the pivot-to-pivot chain, 64 times per
+// block.  d is a Cholesky pivot: positive and far from the subnormal / overflow range when it matters.
+__device__ __forceinline__ double rcp_newton(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
 __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, double* rd, int* s_bad) {
   constexpr int LD = 66;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -45,7 +57,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
       for (int j = 0; j < 16; ++j) {
         const double d = __shfl_sync(0xffffffffu, v[j], j);
         if (!(d > 0.0) || !isfinite(d)) bad = true;
-        const double r = 1.0 / d;
+        const double r = rcp_newton(d);
         const double wr = v[j] * r;
 #pragma unroll
         for (int k = j + 1; k < 16; ++k) {
