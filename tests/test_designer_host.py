@@ -115,3 +115,32 @@ def test_sorted_prior_features_reuse_converted_arrays():
   np.testing.assert_array_equal(a[0], b[0])
   np.testing.assert_array_equal(a[1], b[1])
   assert converters.trials_to_sorted_features([], c, None) is None
+
+
+def test_to_xy_cached_equals_to_xy():
+  p = _problem()
+  c = converters.TrialToModelInputConverter.from_problem(p)
+  rng = np.random.default_rng(1)
+  names = [pc.name for pc in p.search_space.parameters]
+  trials = []
+  for i in range(40):
+    params = {}
+    for pc in p.search_space.parameters:
+      tname = getattr(pc.type, 'name', str(pc.type))
+      if tname == 'CATEGORICAL':
+        params[pc.name] = pc.feasible_values[int(rng.integers(len(pc.feasible_values)))]
+      elif tname == 'DOUBLE':
+        params[pc.name] = float(rng.uniform(pc.bounds[0], pc.bounds[1]))
+      else:
+        params[pc.name] = pc.feasible_values[int(rng.integers(len(pc.feasible_values)))]
+    t = vz.Trial(parameters=params, id=i + 1)
+    metric = p.metric_information[0].name if hasattr(p.metric_information, '__getitem__') else list(p.metric_information)[0].name
+    t.complete(vz.Measurement({metric: float(rng.normal())}))
+    trials.append(t)
+  for upto in (10, 25, 40, 40):        # growing study, then an unchanged one
+    (c1, z1), y1 = c.to_xy(trials[:upto])
+    (c2, z2), y2 = c.to_xy_cached(trials[:upto])
+    np.testing.assert_array_equal(c1, c2)
+    np.testing.assert_array_equal(z1, z2)
+    np.testing.assert_array_equal(y1, y2)
+  assert names

@@ -168,7 +168,7 @@ class VizierGPBandit:
 
   @profiler.record_runtime
   def _trials_to_data(self, trials):
-    (cont, cat), labels = self._converter.to_xy(trials)
+    (cont, cat), labels = self._converter.to_xy_cached(trials)   # completed trials: owned deep copies
     return cont, cat, self._warp_labels(labels)
 
   @profiler.record_runtime

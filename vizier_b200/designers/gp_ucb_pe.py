@@ -174,7 +174,7 @@ class VizierGPUCBPEBandit:
   @profiler.record_runtime
   def _trials_to_data(self, trials):
     """gp_ucb_pe.py:917-942: a fresh default warper per call."""
-    (cont, cat), labels = self._converter.to_xy(trials)
+    (cont, cat), labels = self._converter.to_xy_cached(trials)   # completed trials: owned deep copies
     self._output_warper = output_warpers.create_default_warper()
     warped = self._output_warper.warp(labels[:, 0:1]) if labels.shape[0] else labels[:, 0:1]
     return cont, cat, warped
