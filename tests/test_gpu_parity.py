@@ -10,7 +10,7 @@ import pytest
 import scipy.linalg as sla
 
 torch = pytest.importorskip('torch')
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason='no CUDA device')]
 
 from oracle import eagle_oracle as eo  # noqa: E402
 from oracle import gp_oracle as go  # noqa: E402
@@ -285,7 +285,11 @@ def test_random_search_matches_oracle(dev):
   np.testing.assert_allclose(bs, ws, atol=TOL)
 
 
-@pytest.mark.parametrize('n,d,pool,batch,steps', [(30, 4, 25, 25, 6), (60, 5, 20, 5, 14), (130, 3, 50, 25, 7)])
+# The last two rows are BASELINE C3's shape (P = B = 1000 fireflies, N = 1000 trials, D = 20) and a
+# batch-600 case: batches above 512 take the replayed CUDA-graph form of the loop (c_abi.cu,
+# eagle_run_impl) with k_eagle_suggest / k_eagle_update at 1000 flies and the large-pool k_score.
+@pytest.mark.parametrize('n,d,pool,batch,steps', [(30, 4, 25, 25, 6), (60, 5, 20, 5, 14), (130, 3, 50, 25, 7),
+                                                  (1000, 20, 1000, 1000, 6), (700, 12, 1200, 600, 7)])
 def test_eagle_run_matches_oracle(dev, n, d, pool, batch, steps):
   x, y, _ = _problem(n, d, 13)
   po, pg = _params(d)
@@ -419,6 +423,28 @@ def test_c2_full_size_properties(dev):
   # (4) top-k agrees with a host sort
   idx, val = dev.topk(out['score'], 5)
   np.testing.assert_array_equal(idx, go.top_k(sc, 5))
+
+
+def test_c2_full_pool_parity(dev):
+  """BASELINE C2, every one of the 100k candidates against the oracle (~30 s of CPU)."""
+  n, d, m = 1000, 20, 100_000
+  x, y, _ = _problem(n, d, 0)
+  po, pg = _params(d)
+  dev.fit(x, y, pg)
+  xs = dev.random_pool(m, d, seed=77)
+  out = dev.score(xs, _gp().Acquisition(1.8, True, go.trust_radius(n, d, 0)), with_aux=True)
+  dev.synchronize()
+  pred = go.precompute_predictive(po, x, y)
+  want, aux = go.score_with_aux(pred, xs.cpu().numpy())
+  np.testing.assert_allclose(out['score'].cpu().numpy(), want, atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['mean'].cpu().numpy(), aux['mean'], atol=TOL, rtol=0)
+  np.testing.assert_allclose(out['stddev'].cpu().numpy(), aux['stddev'], atol=TOL, rtol=0)
+  np.testing.assert_array_equal(out['linf_distance'].cpu().numpy(), aux['linf_distance'])
+  # the throughput variant (no aux, pre-scaled features) on the same pool
+  fast = dev.score(xs, _gp().Acquisition(1.8, True, go.trust_radius(n, d, 0)))
+  dev.synchronize()
+  np.testing.assert_allclose(fast['score'].cpu().numpy(), want, atol=TOL, rtol=0)
+  np.testing.assert_array_equal(dev.topk(fast['score'], 8)[0], go.top_k(want, 8))
 
 
 def test_ard_fit_matches_oracle_driver(dev):
@@ -728,6 +754,22 @@ def test_nll_grad_d50_multiblock(dev):
   lm, _, _ = dev.loss_and_grad(xt, yt, _gp().GPHyperParams.from_vector(theta - h * direction, d, 0))
   fd = (lp - lm) / (2 * h)
   assert abs(fd - g0 @ direction) < 1e-4 * max(1.0, abs(fd))
+
+
+def test_nll_grad_c4_full_size(dev):
+  """BASELINE C4 (N=2000, D=50, 52 hyper-parameters): loss and the whole gradient against the oracle."""
+  n, d = 2000, 50
+  rng = np.random.default_rng(72)
+  x = rng.uniform(size=(n, d)); y = rng.normal(size=n)
+  ls2 = np.exp(rng.uniform(np.log(0.3), np.log(5.0), size=d))
+  po = go.GPParams(0.9, ls2, 3e-2); pg = _gp().GPHyperParams(0.9, ls2, 3e-2)
+  want_l, want_g = go.loss_and_grad(po.to_vector(), x, y)
+  xt = torch.from_numpy(x).cuda(); yt = torch.from_numpy(y).cuda()
+  for _ in range(2):   # eager capture call, then the replayed graph
+    loss, grad, retries = dev.loss_and_grad(xt, yt, pg)
+    assert retries == 0
+    assert abs(loss - want_l) < 1e-9 * abs(want_l)
+    np.testing.assert_allclose(grad, want_g, atol=1e-8 * np.max(np.abs(want_g)), rtol=0)
 
 
 def _two_models(dev, n, d, n_pending, seed, high_noise=False):

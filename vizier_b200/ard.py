@@ -38,6 +38,12 @@ try:  # SciPy's compiled L-BFGS-B step routine (the one `minimize(method='L-BFGS
   import scipy.optimize._lbfgsb_py as _lbfgsb_py
   _setulb = _lbfgsb_mod.setulb
   _INT = np.int64 if getattr(_lbfgsb_py, 'HAS_ILP64', False) else np.int32
+  # The lean driver below speaks the C translation's calling convention (SciPy >= 1.15: integer `task`
+  # and `ln_task` arrays, no iprint/csave).  The older f2py/Fortran routine takes other arguments and
+  # could misread these, so it is recognised by its docstring and left to `scipy.optimize.minimize`.
+  _doc = _setulb.__doc__ or ''
+  if 'csave' in _doc or 'iprint' in _doc or 'ln_task' not in _doc:
+    _setulb = None
 except Exception:  # pylint: disable=broad-except
   _setulb = None
   _INT = np.int32
@@ -108,7 +114,7 @@ class ScipyLbfgsB:
       try:
         return _lean_lbfgsb(fn, np.asarray(t0, np.float64), bounds, maxiter=self.options.maxiter,
                             gtol=self.options.tol, maxls=self.options.num_line_search_steps)
-      except TypeError:   # private SciPy entry point changed its signature: use the public one
+      except Exception:   # pylint: disable=broad-except  # private SciPy entry point changed: use the public one
         pass
     res = sopt.minimize(fn, t0, jac=True, method='L-BFGS-B', bounds=bounds,
                         options={'maxiter': self.options.maxiter, 'gtol': self.options.tol,

@@ -213,7 +213,8 @@ class VizierGPBandit:
       md = trial.metadata.ns('devinfo')
       aux = {k: float(v[ind]) for k, v in res.aux.items()}
       md['acquisition_optimization'] = json.dumps({'acquisition': float(res.rewards[ind])} | aux)
-      if not np.isfinite([res.rewards[ind], *aux.values()]).all() and np.isnan([res.rewards[ind], *aux.values()]).any():
+      failed_fit = any(getattr(m, 'cholesky_failed', False) for m in getattr(dev, 'members', [dev]))
+      if failed_fit or np.isnan([res.rewards[ind], *aux.values()]).any():
         md['acquisition_optimization_warning'] = (
             'NaNs encountered in acquisition optimization. See the "acquisition_optimization" field in the '
             'metadata for more details.')

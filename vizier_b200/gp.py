@@ -27,6 +27,7 @@ BOUNDARY_EPS = 1e-12
 SIGNAL_VARIANCE_BOUNDS = (1e-3 - BOUNDARY_EPS, 10.0 + BOUNDARY_EPS)
 LENGTH_SCALE_SQUARED_BOUNDS = (1e-2 - BOUNDARY_EPS, 1e2 + BOUNDARY_EPS)
 NOISE_VARIANCE_BOUNDS = (1e-10 - BOUNDARY_EPS, 1.0 + BOUNDARY_EPS)
+CHOLESKY_MAX_RETRIES = 5   # retrying_cholesky(jitter=1e-4, max_iters=5), tuned_gp_models.py:272-280
 
 
 @dataclasses.dataclass
@@ -158,6 +159,7 @@ class DeviceGP:
     _lib.check('vzgp_create', self._lib.vzgp_create(device, C.c_void_p(self._stream.cuda_stream), C.byref(h)))
     self._h = h
     self.dc = self.dk = self.n = 0
+    self.cholesky_failed = False
 
   def close(self):
     if getattr(self, '_h', None):
@@ -258,6 +260,13 @@ class DeviceGP:
         self._h, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, n if n_valid is None else n_valid, C.byref(p)))
     self.synchronize()  # inputs may be freed by the caller after return
     self.n, self.dc, self.dk = n, dc, dk
+    # retrying_cholesky(max_iters=5) exhausted (tuned_gp_models.py:272-280): the factor holds NaN exactly
+    # like the reference's, every score is NaN and top-k treats it as -inf.  Do not stay silent about it.
+    self.cholesky_failed = retries > CHOLESKY_MAX_RETRIES
+    if self.cholesky_failed:
+      import warnings
+      warnings.warn('vzgp_fit: the kernel matrix could not be factored after %d jitter retries; posterior '
+                    'and acquisition values are NaN' % CHOLESKY_MAX_RETRIES, RuntimeWarning)
     return retries
 
   def cholesky(self) -> torch.Tensor:
