@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the GP-Bandit scoring hot path (BASELINE.json metric).
+"""Benchmark of the GP-Bandit suggest() hot path (BASELINE.json metric).
 
-metric   : GP-UCB candidates scored/sec (suggest() acquisition pass)
-workload : C2 -- GP posterior mu/var + UCB (+trust region) over M=100k candidates,
-           N=1000 trials, D=20, fp64, per GPU (weak scaling: every rank scores its own
-           M-candidate shard of one global Philox pool, then one NCCL all-gather picks
-           the global arg-max).
-step     : one pass of the fused scoring kernel over the rank's M candidates + device top-1.
-value    : candidates/s with candidates resident in HBM (CUDA events on the launching stream,
-           max over ranks).
-e2e      : same pass through the C-ABI call with HOST buffers (pinned): H2D of the M x D
-           candidates and D2H of the M scores inside the timed region.
-roofline : the scoring kernel is FP64-pipe bound (2N^2/2 flops per candidate against 8(D+1) bytes),
-           so `achieved` is algorithmic TFLOP/s against the FP64 peak measured on this GPU by
-           tools/fp64_peak.cu (profiles/fp64_peak_r01.json); the HBM view is reported beside it.
-cpu_baseline / --impl reference: the NumPy/SciPy oracle (a port: the reference's JAX/TFP stack is
-           not installable here) on the host cores, on a bounded candidate sample.
+metric   : GP-UCB candidates scored/sec; suggest() latency at N=1000, D=20, M=100k pool
+workload : c2 (default) -- GP posterior mu/var + UCB (+trust region) over M=100k candidates per GPU,
+           N=1000 trials, D=20, fp64 (weak scaling: every rank scores its own M-candidate shard of one
+           global Philox pool, then ONE fused NVLink exchange+merge kernel picks the global arg-max).
+           c5 (--workload c5) -- M=1M candidates split over the ranks, N=2000, D=50 (BASELINE C5).
+step     : one pass of the fused scoring kernel over the rank's candidates + device top-1 + the exchange.
+value    : candidates/s with candidates resident in HBM (CUDA events on the launching stream, max over
+           ranks); per-step event times of every rank are reported (min / median / max) so that a stall
+           is attributable.
+e2e      : the same step through ONE C-ABI call with HOST buffers (`vzgp_suggest_host`): H2D of the M x D
+           candidates, scoring, top-1, exchange+merge across ranks, D2H of all M scores and the winner,
+           host-synchronous - inside the timed region, at every N.
+suggest_e2e (N=1): wall-clock of a whole `VizierGPBandit.suggest(1)` (trial conversion + 4x50 ARD + fit +
+           acquisition optimisation) on 1000 completed 20-D trials after one new trial arrives, with the
+           M=100k random-pool optimiser (the metric's configuration) and with the default Eagle optimiser,
+           next to the same pipeline restated on the CPU (NumPy/SciPy oracle, all host cores).
+roofline : the scoring kernel is FP64-pipe bound (N^2 flops per candidate against 8(D+1) bytes), so
+           `achieved` is algorithmic TFLOP/s against the FP64 DMMA peak measured on this pool's B200 by
+           tools/fp64_peak.cu (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has no fp64 entry); the
+           HBM view is reported beside it.
+cpu_baseline / --impl reference: the NumPy/SciPy oracle (a port: the reference's JAX/TFP stack cannot be
+           installed here) on all host cores, on a bounded candidate sample.
 """
 import argparse
 import json
@@ -30,20 +37,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_TRIALS, DIM, M_POOL = 1000, 20, 100_000
 SEED = 0
+WORKLOADS = {
+    # name: (N trials, D, total candidates (None = per GPU), candidates per GPU (None = total / world), scaling)
+    'c2': dict(n=1000, d=20, m_per_gpu=100_000, m_total=None, scaling='weak'),
+    'c5': dict(n=2000, d=50, m_per_gpu=None, m_total=1_000_000, scaling='strong'),
+}
+N_TRIALS, DIM, M_POOL = 1000, 20, 100_000   # the headline configuration (c2)
 
 
-def make_problem():
+def make_problem(n=N_TRIALS, d=DIM):
   rng = np.random.default_rng(SEED)
-  x = rng.uniform(size=(N_TRIALS, DIM))
-  y = -np.sum((x - 0.3) ** 2, axis=1) + 0.05 * rng.normal(size=N_TRIALS)
-  ls2 = 0.5 * (1 + np.arange(DIM) / DIM)
+  x = rng.uniform(size=(n, d))
+  y = -np.sum((x - 0.3) ** 2, axis=1) + 0.05 * rng.normal(size=n)
+  ls2 = 0.5 * (1 + np.arange(d) / d)
   return x, y, dict(sf2=1.0, ls2=ls2, sn2=1e-3)
 
 
 def algorithmic_flops_per_candidate(n, d):
-  # triangular contraction N^2 (N^2/2 FMA) + kernel row N*(3D+25) + mean 2N  
+  # triangular contraction N^2 (N^2/2 FMA: L^-1 is lower triangular, what the reference's triangular_solve
+  # does as well) + kernel row N*(3D+25) + mean 2N  (SURVEY 8d counts a dense 2N^2)
   return n * n + n * (3 * d + 25) + 2 * n
 
 
@@ -72,6 +85,24 @@ def hbm_peak_gbs():
   return 6650.0, 'fallback'
 
 
+def score_kernel_traffic():
+  """dram__bytes_read.sum + dram__bytes_write.sum of one k_score launch (ncu --set full), newest summary."""
+  for name in ('score_kernel_ncu_r02.json', 'score_kernel_ncu_r01_latest.json'):
+    tp = os.path.join(ROOT, 'profiles', name)
+    if not os.path.exists(tp):
+      continue
+    try:
+      j = json.load(open(tp))
+
+      def _b(k):
+        v, u = float(j[k]['value']), j[k]['unit'].lower()
+        return v * {'gbyte': 1e9, 'mbyte': 1e6, 'kbyte': 1e3, 'byte': 1.0}[u]
+      return _b('dram__bytes_read.sum') + _b('dram__bytes_write.sum'), name
+    except Exception:  # pylint: disable=broad-except
+      continue
+  return None, None
+
+
 class ClockSampler:
   """nvidia-smi clocks/throttle reasons during the timed region."""
 
@@ -87,7 +118,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(
-          ['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20'],
+          ['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50'],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
@@ -122,19 +153,31 @@ class ClockSampler:
             'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def cpu_oracle_rate(sample, reps):
-  """Oracle (NumPy/SciPy) candidates/s on a bounded sample of the C2 workload, using every host
-  core: candidates are split into 1024-row chunks scored concurrently by a thread pool (NumPy
-  releases the GIL), with BLAS pinned to one thread per chunk to avoid oversubscription."""
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on every host core
+# --------------------------------------------------------------------------------------------------
+def _host_cores():
+  try:
+    return max(1, len(os.sched_getaffinity(0)))
+  except AttributeError:
+    return os.cpu_count() or 1
+
+
+def cpu_oracle_rate(reps, n=N_TRIALS, d=DIM, rows_per_worker=512):
+  """Oracle (NumPy/SciPy) candidates/s on a bounded sample of the workload with EVERY host core busy: the
+  sample is `cores` chunks of `rows_per_worker` candidates, one chunk per worker thread (NumPy/LAPACK
+  release the GIL), BLAS pinned to one thread per worker so the workers do not oversubscribe.
+  Returns (candidates/s, seconds per pass, workers used, sample size)."""
   from concurrent.futures import ThreadPoolExecutor
   from oracle import gp_oracle as go
-  x, y, th = make_problem()
+  x, y, th = make_problem(n, d)
   params = go.GPParams(th['sf2'], th['ls2'], th['sn2'])
   pred = go.precompute_predictive(params, x, y)
+  cores = _host_cores()
+  sample = cores * rows_per_worker
   rng = np.random.default_rng(1)
-  xs = rng.uniform(size=(sample, DIM))
-  cores = os.cpu_count() or 1
-  chunks = [xs[i:i + 1024] for i in range(0, sample, 1024)]
+  xs = rng.uniform(size=(sample, d))
+  chunks = [xs[i:i + rows_per_worker] for i in range(0, sample, rows_per_worker)]
 
   def work(c):
     return go.score_with_aux(pred, c)[0]
@@ -145,42 +188,144 @@ def cpu_oracle_rate(sample, reps):
   except Exception:  # pylint: disable=broad-except
     limiter = None
   with ThreadPoolExecutor(max_workers=cores) as ex:
-    list(ex.map(work, chunks[:cores]))  # warm-up
+    list(ex.map(work, chunks))  # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
       list(ex.map(work, chunks))
     dt = (time.perf_counter() - t0) / reps
   if limiter is not None:
     limiter.restore_original_limits()
-  return sample / dt, dt, cores
+  return sample / dt, dt, min(cores, len(chunks)), sample
+
+
+def cpu_suggest_oracle(x, y, budget_s=60.0):
+  """The designer's suggest() pipeline restated on the CPU with the oracle: 4 x 50 L-BFGS-B ARD (restarts
+  one after the other like jaxopt_wrappers.py:139-152, BLAS on all cores), precompute_predictive, score an
+  M=100k random pool + top-1 (rate from `cpu_oracle_rate`, all cores).  ARD is cut off after `budget_s`
+  seconds and extrapolated over the remaining restarts (flagged)."""
+  from oracle import gp_oracle as go
+  from vizier_b200 import output_warpers   # host NumPy label warping, the same as the designer applies
+  y = output_warpers.create_default_warper().warp(np.asarray(y, np.float64)[:, None])[:, 0]
+  rng = np.random.default_rng(7)
+  n, d = x.shape
+  out = {}
+  t0 = time.perf_counter()
+  done, evals = 0, 0
+  best, best_loss = None, np.inf
+
+  def counted(theta, *a):
+    nonlocal evals
+    evals += 1
+    return go.loss_and_grad(theta, *a)
+
+  import scipy.optimize as sopt
+  lo, hi = go.param_bounds(d, 0)
+  for _ in range(4):
+    t_init = go.log_uniform_init(rng, d, 0)
+    res = sopt.minimize(counted, t_init, args=(x, y), jac=True, method='L-BFGS-B', bounds=list(zip(lo, hi)),
+                        options={'maxiter': 50, 'gtol': 1e-8, 'maxls': 20})
+    done += 1
+    if res.fun < best_loss:
+      best, best_loss = res.x, res.fun
+    if time.perf_counter() - t0 > budget_s:
+      break
+  ard_s = time.perf_counter() - t0
+  out['ard_restarts_run'] = done
+  out['ard_evaluations'] = evals
+  out['ard_extrapolated'] = done < 4
+  out['ard_s'] = ard_s * 4 / done
+  t0 = time.perf_counter()
+  go.precompute_predictive(go.GPParams.from_vector(best, d, 0), x, y)
+  out['fit_s'] = time.perf_counter() - t0
+  rate, _, cores, sample = cpu_oracle_rate(2)
+  out['score_100k_s'] = M_POOL / rate
+  out['score_sample'] = sample
+  out['cores'] = cores
+  out['total_s'] = out['ard_s'] + out['fit_s'] + out['score_100k_s']
+  return out
 
 
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  sample = 16384
-  rates = []
-  for _ in range(args.warmup):
-    cpu_oracle_rate(2048, 1)
-  t_all = 0.0
+  for _ in range(max(1, args.warmup)):
+    cpu_oracle_rate(1, rows_per_worker=128)
+  t_all, cand = 0.0, 0
   for _ in range(args.steps):
-    r, dt, cores = cpu_oracle_rate(sample, 1)
-    rates.append(r); t_all += dt
-  v = sample * args.steps / t_all
+    r, dt, cores, sample = cpu_oracle_rate(1)
+    t_all += dt; cand += sample
+  v = cand / t_all
   line = {
       'impl': 'reference', 'metric': 'GP-UCB candidates scored/sec', 'value': v, 'unit': 'candidates/s',
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_all / args.steps,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
       'config': {'workload': f'C2: GP posterior mu/var + UCB, N={N_TRIALS}, D={DIM}, M={M_POOL} (CPU arm: bounded sample of {sample} candidates per step)'},
       'cpu_baseline': {'value': v, 'unit': 'candidates/s', 'cores': cores, 'kind': 'port',
-                       'sample': f'{sample} candidates/step, NumPy/SciPy oracle (reference JAX/TFP build unavailable)'},
+                       'sample': f'{sample} candidates/step = {cores} worker threads x 512 rows, NumPy/SciPy oracle (reference JAX/TFP build unavailable)'},
       'e2e': {'value': v, 'unit': 'candidates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
   print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------
+# suggest() end to end (N = 1): the metric's second half
+# --------------------------------------------------------------------------------------------------
+def suggest_e2e_leg(device_index, reps=3):
+  from vizier_b200 import optimizers as vb
+  from vizier_b200 import profiler, vz
+  from vizier_b200.designers import gp_bandit
+
+  def problem():
+    p = vz.ProblemStatement()
+    for i in range(DIM):
+      p.search_space.root.add_float_param(f'x{i}', 0.0, 1.0)
+    p.metric_information.append(vz.MetricInformation(name='obj', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+    return p
+
+  def trials(xs, ys, first_id):
+    out = []
+    for i, (x, yv) in enumerate(zip(xs, ys)):
+      t = vz.Trial(parameters={f'x{j}': float(x[j]) for j in range(DIM)}, id=first_id + i)
+      t.complete(vz.Measurement({'obj': float(yv)}))
+      out.append(t)
+    return out
+
+  x, y, _ = make_problem()
+  rng = np.random.default_rng(99)
+  res = {}
+  pool_factory = vb.VectorizedOptimizerFactory(strategy_factory=vb.random_strategy_factory, max_evaluations=M_POOL,
+                                               suggestion_batch_size=M_POOL)
+  for name, kwargs in (('random_pool_100k', dict(acquisition_optimizer_factory=pool_factory)), ('eagle_default', {})):
+    d = gp_bandit.VizierGPBandit(problem(), rng=1, device=device_index, **kwargs)
+    d.update(vz.CompletedTrials(trials(x, y, 1)), vz.ActiveTrials())
+    d.suggest(1)                                   # first call: workspaces, worker handles, graphs
+    times, parts = [], []
+    for r in range(reps):
+      xn = rng.uniform(size=(1, DIM))
+      yn = -np.sum((xn - 0.3) ** 2, axis=1) + 0.05 * rng.normal(size=1)
+      d.update(vz.CompletedTrials(trials(xn, yn, N_TRIALS + 1 + r)), vz.ActiveTrials())   # one new trial -> refit
+      with profiler.collect_events() as ev:
+        t0 = time.perf_counter(); d.suggest(1); times.append(time.perf_counter() - t0)
+      parts.append({k.split('.')[-1]: float(np.sum(v)) for k, v in ev.items()})
+    k = int(np.argsort(times)[len(times) // 2])
+    res[name] = {'gpu_s': float(times[k]), 'all_s': [float(t) for t in times],
+                 'breakdown_s': {'convert': parts[k].get('_trials_to_data'), 'ard_and_fit': parts[k].get('_update_gp'),
+                                 'optimize_acquisition': parts[k].get('_optimize_acquisition')}}
+  cpu = cpu_suggest_oracle(x, y)
+  out = {'config': f'VizierGPBandit.suggest(1), {N_TRIALS} completed {DIM}-D trials + 1 new trial, ARD 4 restarts x 50 L-BFGS-B iterations',
+         'gpu_s': res['random_pool_100k']['gpu_s'], 'cpu_s': cpu['total_s'],
+         'speedup': cpu['total_s'] / res['random_pool_100k']['gpu_s'],
+         'breakdown': res['random_pool_100k']['breakdown_s'], 'gpu': res,
+         'cpu': dict(cpu, kind='port', note='NumPy/SciPy oracle restatement of the same pipeline on the host cores; '
+                     'the reference JAX/TFP build is not installable here')}
+  return out
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
 def run_gpu(args):
   import torch
   from vizier_b200 import gp
@@ -195,39 +340,49 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
   torch.cuda.set_device(local)
+  wl = WORKLOADS[args.workload]
+  n_trials, dim = wl['n'], wl['d']
+  m_pool = wl['m_per_gpu'] if wl['m_per_gpu'] else wl['m_total'] // world
   dev = gp.DeviceGP(local)
-  x, y, th = make_problem()
+  x, y, th = make_problem(n_trials, dim)
   params = gp.GPHyperParams(th['sf2'], th['ls2'], th['sn2'])
   dev.fit(x, y, params)  # every rank recomputes the (deterministic) factorisation: no broadcast needed
   from vizier_b200.multi_gpu import trust_radius, TopkExchange
-  acq = gp.Acquisition(1.8, True, trust_radius(N_TRIALS, DIM, 0))
+  acq = gp.Acquisition(1.8, True, trust_radius(n_trials, dim, 0))
 
-  # rotating candidate pools: 10 x 16 MB = 160 MB > 126 MB L2, so no step re-reads inputs from L2
-  n_pools = 10
-  pools = [dev.random_pool(M_POOL, DIM, seed=SEED + 17, index_base=(rank * n_pools + i) * M_POOL)
+  # rotating candidate pools, together larger than the 126 MB L2, so no step re-reads its inputs from L2
+  pool_bytes = m_pool * dim * 8
+  n_pools = max(2, int(np.ceil(160e6 / pool_bytes)))
+  pools = [dev.random_pool(m_pool, dim, seed=SEED + 17, index_base=(rank * n_pools + i) * m_pool)
            for i in range(n_pools)]
-  outs = [{'score': torch.empty(M_POOL, dtype=torch.float64, device=dev.device)} for _ in range(2)]
+  n_slots = 8
+  outs = [torch.empty(m_pool, dtype=torch.float64, device=dev.device) for _ in range(2)]
   stream = dev.stream
-  exchange = TopkExchange(dist, dev, DIM, 1)
-  last = {}
+  exchange = TopkExchange(dist, dev, dim, 1, slots=n_slots)
+  state = {'read': 0}
+
+  def base(i):
+    return (rank * n_pools + i % n_pools) * m_pool
 
   def step(i):
     # one suggest over this rank's shard, all on the handle's stream with no host synchronisation:
-    # fused score -> device top-1 -> pack [score, global index, x] -> NCCL all-gather (N > 1) ->
-    # deterministic merge kernel -> async D2H of the winner.  The host reads step i-1's winner while
-    # step i runs, so the read is inside the timed loop without stalling the GPU.
-    slot = i % 2
-    exchange.step(slot, pools[i % n_pools], acq, index_base=(rank * n_pools + i % n_pools) * M_POOL,
-                  score_out=outs[slot]['score'])
-    if 'slot' in last:
-      last['winner'] = exchange.result(last['slot'])
-    last['slot'] = slot
+    # fused score -> device top-1 -> pack [score, global index, x] -> ONE fused kernel (push to all peers
+    # over NVLink, flags, merge) -> async D2H of the winner.  The host reads winners n_slots-1 steps
+    # behind, so a late host thread does not stall the device (or the other ranks) for up to 7 steps.
+    exchange.step(i % n_slots, pools[i % n_pools], acq, index_base=base(i), score_out=outs[i % 2])
+    if i >= n_slots - 1:
+      state['winner'] = exchange.result((i - (n_slots - 1)) % n_slots)
+      state['read'] += 1
+
+  def drain(total):
+    for j in range(max(0, total - (n_slots - 1)), total):
+      state['winner'] = exchange.result(j % n_slots)
 
   for i in range(args.warmup):
     step(i)
+  drain(args.warmup)
   dev.synchronize()
-  # ---- kernel-only duration of the dominant kernel (events on the launching stream) ----
-  ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+  step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
   if dist is not None:
     dist.barrier()
   torch.cuda.synchronize()
@@ -235,22 +390,26 @@ def run_gpu(args):
   if rank == 0:
     sampler.start()
   l0 = dev.launch_count
-  t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
-  t_start.record(stream)
+  step_ev[0].record(stream)
   for i in range(args.steps):
     step(i)
-  t_end.record(stream)
-  winner = exchange.result(last['slot'])
+    step_ev[i + 1].record(stream)
+  drain(args.steps)
   torch.cuda.synchronize()
   if dist is not None:
     dist.barrier()
   launches = dev.launch_count - l0
-  total_ms = t_start.elapsed_time(t_end)
+  total_ms = step_ev[0].elapsed_time(step_ev[-1])
+  per_step = np.array([step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)])
+  exchange_ok = exchange.peer.status() == 0 if exchange.peer is not None else True
+
   # latency of ONE synchronous suggest (enqueue -> winner on the host), median of 5
   lat = []
   for i in range(5):
+    if dist is not None:
+      dist.barrier()
     t0 = time.perf_counter()
-    exchange.step(0, pools[i % n_pools], acq, index_base=(rank * n_pools + i % n_pools) * M_POOL, score_out=outs[0]['score'])
+    exchange.step(0, pools[i % n_pools], acq, index_base=base(i), score_out=outs[0])
     w_idx, w_val, _ = exchange.result(0)
     lat.append(1e3 * (time.perf_counter() - t0))
   suggest_latency_ms = float(np.median(lat))
@@ -260,86 +419,120 @@ def run_gpu(args):
     allw = torch.empty((world, 2), dtype=torch.float64, device=dev.device)
     dist.all_gather_into_tensor(allw, mine)
     ranks_agree = bool((allw == allw[0]).all().item())
+
   # duration of the dominant kernel alone: CUDA events on the launching stream around each launch
+  ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+  out_k = {'score': outs[0]}
   for i in range(args.steps):
     ev[i][0].record(stream)
-    dev.score(pools[i % n_pools], acq, out=outs[i % 2])
+    dev.score(pools[i % n_pools], acq, out=out_k)
     ev[i][1].record(stream)
   torch.cuda.synchronize()
   kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+  # the trust-region variant k_score<true> (active when the radius is <= 0.5: few trials), same pool size
+  tr_ms = None
+  if args.workload == 'c2' and rank == 0:
+    n_tr = 100
+    dev_tr = gp.DeviceGP(local)
+    dev_tr.fit(x[:n_tr], y[:n_tr], params)
+    acq_tr = gp.Acquisition(1.8, True, trust_radius(n_tr, dim, 0))
+    o_tr = {'score': outs[1]}
+    for _ in range(3):
+      dev_tr.score(pools[0], acq_tr, out=o_tr)
+    dev_tr.synchronize()
+    ts = []
+    for i in range(10):
+      a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a_.record(dev_tr.stream); dev_tr.score(pools[i % n_pools], acq_tr, out=o_tr); b_.record(dev_tr.stream)
+      dev_tr.synchronize(); ts.append(a_.elapsed_time(b_))
+    tr_ms = {'n_trials': n_tr, 'trust_radius': acq_tr.trust_radius, 'kernel': 'k_score<true>', 'ms': float(np.mean(ts)),
+             'candidates_per_s': m_pool / (float(np.mean(ts)) * 1e-3)}
+    dev_tr.close()
 
-  # ---- e2e through the host-buffer C-ABI call ----
-  host_x = [torch.empty((M_POOL, DIM), dtype=torch.float64).pin_memory() for _ in range(2)]
-  host_s = torch.empty(M_POOL, dtype=torch.float64).pin_memory()
+  # ---- e2e: one C-ABI call per step with HOST buffers, the collective included ----
+  host_x = [torch.empty((m_pool, dim), dtype=torch.float64).pin_memory() for _ in range(2)]
+  host_s = torch.empty(m_pool, dtype=torch.float64).pin_memory()
   for i in range(2):
     host_x[i].copy_(pools[i].cpu())
   for i in range(max(1, args.warmup)):
-    dev.score_host(host_x[i % 2], acq, score_out=host_s)
+    dev.suggest_host(host_x[i % 2], acq, 1, base(i), exchange=exchange.peer, score_out=host_s)
   torch.cuda.synchronize()
   if dist is not None:
     dist.barrier()
   t0 = time.perf_counter()
   for i in range(args.steps):
-    dev.score_host(host_x[i % 2], acq, score_out=host_s)
+    dev.suggest_host(host_x[i % 2], acq, 1, base(i), exchange=exchange.peer, score_out=host_s)
   torch.cuda.synchronize()
   e2e_s = time.perf_counter() - t0
   clocks = sampler.stop() if rank == 0 else None
 
+  per_rank = None
   if dist is not None:
     t = torch.tensor([total_ms, kern_ms, e2e_s * 1e3], dtype=torch.float64, device=dev.device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kern_ms, e2e_ms = [float(v) for v in t.cpu()]
     e2e_s = e2e_ms / 1e3
+    mine = torch.tensor([per_step.min(), float(np.median(per_step)), per_step.max(), float(np.argmax(per_step)),
+                         1.0 if exchange_ok else 0.0], dtype=torch.float64, device=dev.device)
+    allp = torch.empty((world, 5), dtype=torch.float64, device=dev.device)
+    dist.all_gather_into_tensor(allp, mine)
+    per_rank = allp.cpu().numpy()
+    exchange_ok = bool(per_rank[:, 4].min() > 0)
   if rank != 0:
     if dist is not None:
       dist.destroy_process_group()
     return
 
-  cand_total = M_POOL * world * args.steps
+  if per_rank is None:
+    per_rank = np.array([[per_step.min(), np.median(per_step), per_step.max(), np.argmax(per_step), 1.0]])
+  worst = int(np.argmax(per_rank[:, 2]))
+  step_stats = {'min': float(per_rank[:, 0].min()), 'median': float(np.median(per_rank[:, 1])),
+                'max': float(per_rank[:, 2].max()), 'max_rank': worst, 'max_step': int(per_rank[worst, 3]),
+                'note': 'CUDA-event time of each step on each rank; min / median-of-medians / max over ranks'}
+  cand_total = m_pool * world * args.steps
   value = cand_total / (total_ms * 1e-3)
-  flops = algorithmic_flops_per_candidate(N_TRIALS, DIM) * M_POOL
+  flops = algorithmic_flops_per_candidate(n_trials, dim) * m_pool
   peak, peak_src = fp64_peak_tflops()
   achieved = flops / (kern_ms * 1e-3) * 1e-12
   hbm_peak, hbm_src = hbm_peak_gbs()
-  hbm_ach = algorithmic_bytes_per_candidate(DIM) * M_POOL / (kern_ms * 1e-3) * 1e-9
-  traffic = None
-  tp = os.path.join(ROOT, 'profiles', 'score_kernel_ncu_r01_latest.json')
-  if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one k_score launch (ncu --set full)
-    try:
-      j = json.load(open(tp))
-      def _b(k):
-        v, u = float(j[k]['value']), j[k]['unit'].lower()
-        return v * {'gbyte': 1e9, 'mbyte': 1e6, 'kbyte': 1e3, 'byte': 1.0}[u]
-      traffic = _b('dram__bytes_read.sum') + _b('dram__bytes_write.sum')
-    except Exception:  # pylint: disable=broad-except
-      pass
-  cpu_v, cpu_dt, cores = (None, None, None)
-  if world == 1:
-    reps = 3
-    cpu_v, cpu_dt, cores = cpu_oracle_rate(16384, reps)
+  hbm_ach = algorithmic_bytes_per_candidate(dim) * m_pool / (kern_ms * 1e-3) * 1e-9
+  traffic, traffic_src = score_kernel_traffic() if args.workload == 'c2' else (None, None)
+  cname = args.workload.upper()
   line = {
       'metric': 'GP-UCB candidates scored/sec', 'value': value, 'unit': 'candidates/s', 'n_gpus': world,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
-      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-      'config': {'workload': f'C2: GP posterior mu/var + UCB + trust region + top-1, N={N_TRIALS}, D={DIM}, M={M_POOL} per GPU',
-                 'l2': f'{n_pools} rotating candidate pools ({n_pools * M_POOL * DIM * 8 / 1e6:.0f} MB > 126 MB L2)',
-                 'parallelism': f'candidate-pool shards x{world}, 1 NCCL all-gather for the global arg-max' if world > 1 else 'single GPU',
-                 'suggest_latency_ms': suggest_latency_ms, 'ranks_agree': ranks_agree,
-                 'pipelining': 'steps are enqueued without host sync; the host reads winner i-1 while step i runs'},
+      'higher_is_better': True, 'scaling': wl['scaling'], 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+      'config': {'workload': f'{cname}: GP posterior mu/var + UCB + trust region + top-1, N={n_trials}, D={dim}, M={m_pool} per GPU'
+                             + (f' ({wl["m_total"]} in total)' if wl['m_total'] else ''),
+                 'l2': f'{n_pools} rotating candidate pools ({n_pools * pool_bytes / 1e6:.0f} MB > 126 MB L2)',
+                 'parallelism': (f'candidate-pool shards x{world}; global arg-max by ONE fused kernel per step (NVLink peer stores + '
+                                 f'release/acquire flags + merge), transport={exchange.transport}') if world > 1 else 'single GPU',
+                 'suggest_latency_ms': suggest_latency_ms, 'ranks_agree': ranks_agree, 'exchange_ok': exchange_ok,
+                 'per_step_ms': step_stats,
+                 'pipelining': f'steps are enqueued without host sync; the host reads winners {n_slots - 1} steps behind',
+                 'k_score_trust_region_variant': tr_ms},
       'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                   'traffic': traffic, 'kernel': 'k_score', 'kernel_ms': kern_ms,
-                   'note': 'fp64: tcgen05 has no f64 kind, the binding roof is the FP64 FMA/DMMA pipe; peak ' + peak_src,
-                   'flops_per_candidate': algorithmic_flops_per_candidate(N_TRIALS, DIM),
+                   'traffic': traffic, 'traffic_source': traffic_src, 'kernel': 'k_score', 'kernel_ms': kern_ms,
+                   'note': 'fp64: tcgen05 has no f64 kind, the binding roof is the FP64 DMMA pipe; peak ' + peak_src,
+                   'flops_per_candidate': algorithmic_flops_per_candidate(n_trials, dim),
                    'hbm': {'achieved': hbm_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_ach / hbm_peak, 'peak_source': hbm_src}},
-      'e2e': {'value': M_POOL * world * args.steps / e2e_s, 'unit': 'candidates/s',
-              'h2d_bytes_per_step': M_POOL * DIM * 8 * world, 'd2h_bytes_per_step': M_POOL * 8 * world,
-              'ms_per_step': 1e3 * e2e_s / args.steps},
+      'e2e': {'value': m_pool * world * args.steps / e2e_s, 'unit': 'candidates/s',
+              'h2d_bytes_per_step': m_pool * dim * 8 * world, 'd2h_bytes_per_step': (m_pool * 8 + (dim + 2) * 8) * world,
+              'ms_per_step': 1e3 * e2e_s / args.steps,
+              'call': 'vzgp_suggest_host: H2D candidates, score, top-1, exchange+merge, D2H scores + winner, host-synchronous'},
       'gpu_launches': int(launches),
       'clocks': clocks,
   }
-  if cpu_v is not None:
+  if world == 1 and args.workload == 'c2':
+    cpu_v, cpu_dt, cores, sample = cpu_oracle_rate(3)
     line['cpu_baseline'] = {'value': cpu_v, 'unit': 'candidates/s', 'cores': cores, 'kind': 'port',
-                            'sample': f'16384 candidates x 3 reps ({cpu_dt:.2f} s each), NumPy/SciPy oracle on the host'}
+                            'sample': f'{sample} candidates x 3 passes ({cpu_dt:.2f} s each): {cores} worker threads x 512 rows, '
+                                      'NumPy/SciPy oracle on the host'}
+    if not args.no_suggest:
+      try:
+        line['suggest_e2e'] = suggest_e2e_leg(local)
+      except Exception as e:  # pylint: disable=broad-except
+        line['suggest_e2e'] = {'error': repr(e)}
   print(json.dumps(line), flush=True)
   if dist is not None:
     dist.destroy_process_group()
@@ -351,6 +544,8 @@ def main():
   ap.add_argument('--steps', type=int, default=50)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+  ap.add_argument('--no-suggest', action='store_true', help='skip the suggest() end-to-end leg (N=1)')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
   if args.impl == 'reference':

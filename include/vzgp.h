@@ -212,6 +212,46 @@ int vzgp_score_topk_pack(vzgp_handle* h, const double* Xs, const int32_t* Zs, in
 int vzgp_merge_topk(vzgp_handle* h, const double* rows_dev, int n_rows, int width, int count,
                     double* out_dev, double* host_out);
 
+/* ---- global top-k over candidate-pool shards (one process per GPU) -------------------------------
+ * the pool shards over the GPUs of one box; after vzgp_score_topk_pack every rank holds
+ * count rows [score, global index, features] and needs the global top-`count` (the reference's
+ * counterpart is the arg-partition over ONE pool, vectorized_base.py:575-587).  A vzgp_exchange owns a
+ * small device buffer that every peer maps (CUDA IPC across processes; plain pointers inside one
+ * process).  vzgp_allgather_topk(use_nccl = 0) is ONE kernel launch on the handle's stream: push the rows
+ * into every peer's buffer over NVLink, publish a sequence flag (st.release.sys), wait for all peers'
+ * flags (ld.acquire.sys, bounded by a timeout), merge deterministically (every rank computes the identical
+ * result).  use_nccl = 1 is the checked fallback: ncclAllGather (libnccl.so.2 through dlopen, communicator
+ * created by vzgp_exchange_nccl_init) + the merge kernel.  No host synchronisation either way; host_out
+ * (pinned, optional) receives the merged rows by an asynchronous copy.  All ranks must call in lock-step. */
+typedef struct vzgp_exchange vzgp_exchange;
+int vzgp_exchange_create(vzgp_handle* h, int rank, int world, int count, int width, vzgp_exchange** out);
+int vzgp_exchange_destroy(vzgp_exchange* x);
+/* 64-byte cudaIpcMemHandle_t of this rank's buffer; all-gather them (any transport) and pass the
+ * [world][64] array, in rank order, to vzgp_exchange_open on every rank. */
+int vzgp_exchange_ipc_handle(vzgp_exchange* x, void* handle_out64);
+int vzgp_exchange_open(vzgp_exchange* x, const void* handles);
+/* Same-process alternative: base pointers (vzgp_exchange_base) of every rank, in rank order. */
+void* vzgp_exchange_base(vzgp_exchange* x);
+int vzgp_exchange_set_peers(vzgp_exchange* x, void* const* bases);
+/* NCCL fallback: rank 0 draws a 128-byte ncclUniqueId, everybody calls _nccl_init with it (collective). */
+int vzgp_nccl_unique_id(void* id_out128);
+int vzgp_exchange_nccl_init(vzgp_exchange* x, const void* id128);
+int vzgp_allgather_topk(vzgp_handle* h, vzgp_exchange* x, const double* payload_dev, double* out_dev,
+                        double* host_out, int use_nccl);
+/* Synchronises the stream; *status_out = 1 if a fused exchange timed out waiting for a peer
+ * (VZGP_EXCHANGE_TIMEOUT_MS, default 10 s; the merged rows of that step are [-inf, -1, 0...]). */
+int vzgp_exchange_status(vzgp_handle* h, vzgp_exchange* x, int* status_out);
+
+/* One sharded suggest from HOST memory in one call (what bench.py's e2e times at every N): Xs [M x Dc]
+ * host candidates of this rank's shard (pinned memory recommended) -> device (copies pipelined against
+ * the scoring, as in vzgp_score_host) -> fused score -> device top-`count` -> rows [score, index_base +
+ * local index, features] -> vzgp_allgather_topk over `x` (NULL: this rank alone) -> best_rows
+ * [count x (Dc+2)] HOST, identical on every rank; score_host (optional, HOST [M]) receives all of this
+ * shard's scores.  Synchronous.  Replaces the body of VectorizedOptimizer.__call__ for the random-pool
+ * strategy on caller-provided candidates (vectorized_base.py:431-495, :575-587). */
+int vzgp_suggest_host(vzgp_handle* h, vzgp_exchange* x, int use_nccl, const double* Xs, int M, const vzgp_acq* acq,
+                      int count, int64_t index_base, double* score_host, double* best_rows);
+
 /* ---- acquisition optimisers (device-resident loops) ---------------------- */
 
 /* EagleStrategyConfig (eagle_strategy.py:111-167), continuous features. */

@@ -132,6 +132,17 @@ SIGNATURES = {
     'vzgp_eagle_run_ensemble': (_i, [C.POINTER(_vp), _i, C.POINTER(EagleConfig), _pA, _vp, _vp, _i, _pi32, _i, C.c_uint64, _pd, _pi32, _pd]),
     'vzgp_score_topk_pack': (_i, [_vp, _vp, _vp, _i, _pA, _i, _i64, _vp, _vp]),
     'vzgp_merge_topk': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    'vzgp_exchange_create': (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    'vzgp_exchange_destroy': (_i, [_vp]),
+    'vzgp_exchange_ipc_handle': (_i, [_vp, _vp]),
+    'vzgp_exchange_open': (_i, [_vp, _vp]),
+    'vzgp_exchange_base': (_vp, [_vp]),
+    'vzgp_exchange_set_peers': (_i, [_vp, C.POINTER(_vp)]),
+    'vzgp_nccl_unique_id': (_i, [_vp]),
+    'vzgp_exchange_nccl_init': (_i, [_vp, _vp]),
+    'vzgp_allgather_topk': (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    'vzgp_exchange_status': (_i, [_vp, _vp, C.POINTER(_i)]),
+    'vzgp_suggest_host': (_i, [_vp, _vp, _i, _vp, _i, _pA, _i, _i64, _vp, _vp]),
     'vzgp_eagle_run': (_i, [_vp, _pE, _pA, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
     'vzgp_score_pe': (_i, [_vp, _vp, _vp, _vp, _i, _pPE, _vp, _vp, _vp, _vp]),
     'vzgp_eagle_run_pe': (_i, [_vp, _vp, _pE, _pPE, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),

@@ -26,7 +26,9 @@ constexpr size_t kOffLogdet = 64;    // double[2]
 constexpr size_t kOffGrad = 128;     // double[<=98]
 constexpr size_t kOffTopIdx = 1024;  // long long[256]
 constexpr size_t kOffTopVal = 3072;  // double[256]
-constexpr size_t kOffPartial = 8192; // ArgMax[<=2048]
+constexpr size_t kOffPartial = 8192; // ArgMax[<=2048] = 32 KiB
+constexpr size_t kOffRows = 40960;   // winner rows of the fused top-k calls (24 KiB)
+constexpr size_t kRowsBytes = kSmallBytes - kOffRows;
 constexpr int kMaxTopk = 256;
 
 struct Guard {
@@ -542,20 +544,19 @@ int vzgp_clamped_count(vzgp_handle* h, int64_t* count_out) {
   return 0;
 }
 
-int vzgp_score_host(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
-                    const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf) {
-  VZ_TRY(check_scoring(h, Xs, Zs, M, acq, score));
-  if (M == 0) return 0;
-  Guard g(h->device);
+// Host candidates -> device staging -> scores in h->out_dev[0..M) (+ mu / sigma / linf planes), all
+// enqueued on the handle's stream, nothing copied back, no synchronisation.  The host->device copy is
+// pipelined against the scoring: candidates go over in up to three chunks sized in whole waves of
+// 64-row tiles (1 wave, 3 waves, rest) on a copy stream, and the score launch of chunk c only waits for
+// the event of chunk c.
+static int score_host_enqueue(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                              bool mu, bool sigma, bool linf, double** dX_out, double** o_out) {
   const size_t xb = sizeof(double) * (size_t)M * h->dc, zb = sizeof(int32_t) * (size_t)M * h->dk;
   VZ_TRY(h->xs_dev.reserve(xb + zb + 64));
   VZ_TRY(h->out_dev.reserve(sizeof(double) * (size_t)M * 4));
   double* dX = h->xs_dev.as<double>();
   int32_t* dZ = reinterpret_cast<int32_t*>(h->xs_dev.as<char>() + ((xb + 15) / 16) * 16);
   double* o = h->out_dev.as<double>();
-  // The host->device copy is pipelined against the scoring: candidates go over in up to three
-  // chunks sized in whole waves of 64-row tiles (1 wave, 3 waves, rest) on a copy stream, and the
-  // score launch of chunk c only waits for the event of chunk c.
   if (!h->copy_stream) {
     VZ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) VZ_CUDA(cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
@@ -584,6 +585,18 @@ int vzgp_score_host(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
     VZ_TRY(launch_score(h, dX + lo * h->dc, h->dk > 0 ? dZ + lo * h->dk : nullptr, n, acq, o + lo, mu ? o + M + lo : nullptr,
                         sigma ? o + 2 * (size_t)M + lo : nullptr, linf ? o + 3 * (size_t)M + lo : nullptr));
   }
+  *dX_out = dX;
+  *o_out = o;
+  return 0;
+}
+
+int vzgp_score_host(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
+                    const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf) {
+  VZ_TRY(check_scoring(h, Xs, Zs, M, acq, score));
+  if (M == 0) return 0;
+  Guard g(h->device);
+  double *dX, *o;
+  VZ_TRY(score_host_enqueue(h, Xs, Zs, M, acq, mu != nullptr, sigma != nullptr, linf != nullptr, &dX, &o));
   const size_t ob = sizeof(double) * (size_t)M;
   VZ_CUDA(cudaMemcpyAsync(score, o, ob, cudaMemcpyDeviceToHost, h->stream));
   if (mu) VZ_CUDA(cudaMemcpyAsync(mu, o + M, ob, cudaMemcpyDeviceToHost, h->stream));
@@ -932,8 +945,8 @@ int vzgp_score_topk(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
   VZ_TRY(launch_score(h, Xs, Zs, M, acq, dS, nullptr, nullptr, nullptr));
   long long* d_idx; double* d_val;
   VZ_TRY(topk_to_device(h, dS, M, count, &d_idx, &d_val));
-  double* dBest = reinterpret_cast<double*>(h->small.as<char>() + 32768);  // count*dc doubles <= 32 KiB
-  VZ_ARG((size_t)count * dc * sizeof(double) <= 32768, "count * Dc too large");
+  double* dBest = reinterpret_cast<double*>(h->small.as<char>() + kOffRows);
+  VZ_ARG((size_t)count * dc * sizeof(double) <= kRowsBytes, "count * Dc too large");
   VZ_TRY(launch_gather_rows(h, Xs, dc, d_idx, count, M, dBest));
   long long hidx[kMaxTopk];
   VZ_CUDA(cudaMemcpyAsync(hidx, d_idx, sizeof(long long) * count, cudaMemcpyDeviceToHost, h->stream));
@@ -976,6 +989,34 @@ int vzgp_merge_topk(vzgp_handle* h, const double* rows_dev, int n_rows, int widt
   VZ_TRY(launch_merge_topk(h, rows_dev, n_rows, width, count, out_dev));
   if (host_out)
     VZ_CUDA(cudaMemcpyAsync(host_out, out_dev, sizeof(double) * (size_t)count * width, cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+int vzgp_suggest_host(vzgp_handle* h, vzgp_exchange* x, int use_nccl, const double* Xs, int M, const vzgp_acq* acq,
+                      int count, int64_t index_base, double* score_host, double* best_rows) {
+  VZ_ARG(best_rows != nullptr, "best_rows");
+  VZ_ARG(M >= 1, "M >= 1");
+  VZ_ARG(index_base >= 0 && index_base + (int64_t)M < (1LL << 53), "global indices must be exact in fp64");
+  static double dummy = 0.0;
+  VZ_TRY(check_scoring(h, Xs, nullptr, M, acq, &dummy));
+  VZ_ARG(h->dk == 0, "continuous features only");
+  Guard g(h->device);
+  const int dc = h->dc, w = dc + 2;
+  VZ_ARG((size_t)2 * count * w * sizeof(double) <= kRowsBytes, "count * (Dc + 2) too large");
+  double *dX, *o;
+  VZ_TRY(score_host_enqueue(h, Xs, nullptr, M, acq, false, false, false, &dX, &o));
+  long long* d_idx; double* d_val;
+  VZ_TRY(topk_to_device(h, o, M, count, &d_idx, &d_val));
+  double* payload = reinterpret_cast<double*>(h->small.as<char>() + kOffRows);   // [count][w], then the merged rows
+  double* merged = payload + (size_t)count * w;
+  VZ_TRY(launch_pack_topk(h, dX, dc, d_idx, d_val, count, M, index_base, payload));
+  if (x != nullptr) {
+    VZ_TRY(vzgp_allgather_topk(h, x, payload, merged, best_rows, use_nccl));
+  } else {
+    VZ_CUDA(cudaMemcpyAsync(best_rows, payload, sizeof(double) * (size_t)count * w, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (score_host) VZ_CUDA(cudaMemcpyAsync(score_host, o, sizeof(double) * (size_t)M, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -25,6 +25,7 @@
 
 #include "launchers.h"
 #include "score_small.cuh"
+#include "topk_merge.cuh"
 #include "tiles.cuh"
 
 namespace vzgp {
@@ -825,52 +826,10 @@ int launch_pack_topk(vzgp_handle* h, const double* X, int dc, const long long* i
   return 0;
 }
 
-// Merge gathered winner rows (n_rows x width, row = [score, global index, features]) into the best
-// `count`: larger score first, NaN as -inf, ties -> lower global index, rows with index < 0 last.
-// One CTA; n_rows <= 2048.  Selection by repeated arg-max (count <= 256, n_rows small).
+// Merge gathered winner rows: merge_topk_block (topk_merge.cuh), one CTA.
 __global__ void __launch_bounds__(256) k_merge_topk(const double* __restrict__ rows, int n_rows, int width,
                                                     int count, double* __restrict__ out) {
-  __shared__ double sv[2048];
-  __shared__ long long si[2048];
-  __shared__ double rv[256];
-  __shared__ long long ri[256];
-  __shared__ int rr[256];
-  const int tid = threadIdx.x;
-  for (int r = tid; r < n_rows; r += 256) {
-    double v = rows[(size_t)r * width];
-    const double gi = rows[(size_t)r * width + 1];
-    if (v != v) v = -INFINITY;
-    sv[r] = v;
-    si[r] = (gi < 0.0) ? LLONG_MAX : (long long)gi;
-  }
-  __syncthreads();
-  for (int c = 0; c < count; ++c) {
-    double bv = -INFINITY; long long bi = LLONG_MAX; int br = -1;
-    for (int r = tid; r < n_rows; r += 256) {
-      const long long i = si[r];
-      if (i == LLONG_MAX - 1) continue;            // already taken
-      const double v = sv[r];
-      if (br < 0 || v > bv || (v == bv && i < bi)) { bv = v; bi = i; br = r; }
-    }
-    rv[tid] = bv; ri[tid] = bi; rr[tid] = br;
-    __syncthreads();
-    for (int s2 = 128; s2 > 0; s2 >>= 1) {
-      if (tid < s2) {
-        const int o = tid + s2;
-        const bool take = rr[o] >= 0 && (rr[tid] < 0 || rv[o] > rv[tid] || (rv[o] == rv[tid] && ri[o] < ri[tid]));
-        if (take) { rv[tid] = rv[o]; ri[tid] = ri[o]; rr[tid] = rr[o]; }
-      }
-      __syncthreads();
-    }
-    const int win = rr[0];
-    if (win >= 0) {
-      for (int d = tid; d < width; d += 256) out[(size_t)c * width + d] = rows[(size_t)win * width + d];
-      if (tid == 0) si[win] = LLONG_MAX - 1;
-    } else {
-      for (int d = tid; d < width; d += 256) out[(size_t)c * width + d] = (d == 0) ? -INFINITY : (d == 1 ? -1.0 : 0.0);
-    }
-    __syncthreads();
-  }
+  merge_topk_block<false>(rows, n_rows, width, count, out);
 }
 
 int launch_merge_topk(vzgp_handle* h, const double* rows, int n_rows, int width, int count, double* out) {

@@ -409,6 +409,28 @@ class DeviceGP:
     del keep
     return bx, bs, bi
 
+  def suggest_host(self, xs_host, acq: Acquisition, count: int, index_base: int = 0, *, exchange=None,
+                   score_out=None):
+    """`vzgp_suggest_host`: one sharded suggest from HOST candidates (torch CPU tensor, ideally pinned, or
+    a NumPy array) in one synchronous C call; `exchange` is a `multi_gpu.PeerExchange` (None = this rank
+    alone).  Returns (global indices [count] i64, scores [count], features [count, Dc]) - the same on
+    every rank."""
+    a, keep = acq._c()
+    m = xs_host.shape[0]
+    rows = np.zeros((count, self.dc + 2), np.float64)
+
+    def hp(arr):
+      if arr is None:
+        return None
+      return C.c_void_p(arr.data_ptr()) if isinstance(arr, torch.Tensor) else C.c_void_p(arr.ctypes.data)
+
+    use_nccl = 1 if (exchange is not None and exchange.transport == 'nccl' and exchange.world > 1) else 0
+    _lib.check('vzgp_suggest_host', self._lib.vzgp_suggest_host(
+        self._h, exchange._x if exchange is not None else None, use_nccl, hp(xs_host), m, C.byref(a), count,
+        int(index_base), hp(score_out), C.c_void_p(rows.ctypes.data)))
+    del keep
+    return rows[:, 1].astype(np.int64), rows[:, 0].copy(), rows[:, 2:].copy()
+
   def score_topk_pack(self, xs: torch.Tensor, acq: Acquisition, count: int, index_base: int,
                       payload: torch.Tensor, score_out: Optional[torch.Tensor] = None) -> None:
     """Asynchronous shard step: score, local top-`count`, rows [score, global index, features] into the
