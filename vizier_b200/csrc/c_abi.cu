@@ -50,6 +50,7 @@ static int ensure_model_buffers(vzgp_handle* h, int np, int dc, int dk) {
   VZ_TRY(h->Z.reserve(sizeof(int32_t) * (size_t)np * (dk > 0 ? dk : 1)));
   VZ_TRY(h->L.reserve(sizeof(double) * (size_t)np * np));
   VZ_TRY(h->Linv.reserve(sizeof(double) * (size_t)np * np));
+  VZ_TRY(h->LinvT.reserve(sizeof(double) * (size_t)np * np));
   VZ_TRY(h->Kws.reserve(sizeof(double) * (size_t)np * np));
   VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)np * np));
   VZ_TRY(h->alpha.reserve(sizeof(double) * (size_t)np));
@@ -57,11 +58,29 @@ static int ensure_model_buffers(vzgp_handle* h, int np, int dc, int dk) {
   return 0;
 }
 
+// Factor the (already shifted) lower matrix in L in place and form L^-1.  With LinvT != nullptr the dataflow
+// kernel (dataflow.cu) does both - plus L^-T and, if Kinv != nullptr, the lower tiles of L^-T L^-1 - in one
+// launch; *used_dataflow tells the caller which form of Kinv exists.  Otherwise (stage-wise entry points,
+// VZGP_DATAFLOW=0, a single 64-block): the panel kernels of linalg.cu + recursive doubling.
+static int factor_invert(vzgp_handle* h, double* L, double* Linv, double* LinvT, double* Kinv, int np, int* flag,
+                         bool* used_dataflow) {
+  *used_dataflow = false;
+  if (LinvT != nullptr) {
+    const int st = chol_dataflow(h, L, Linv, LinvT, Kinv, np, flag);
+    if (st < 0) return st;
+    if (st == 0) { *used_dataflow = true; return 0; }
+  }
+  VZ_TRY(potrf_blocked(h, L, np, Linv, np, np, flag));
+  VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)np * np));
+  VZ_TRY(trtri_doubling(h, L, np, Linv, np, h->Tws.as<double>(), np, np));
+  return 0;
+}
+
 // Factor A (np x np device, lower read) into h-independent buffers with retry semantics.
-// L, Linv: [np x np].  Returns retries, or max_iters+1 on final failure, or <0.
+// L, Linv: [np x np] (Linv complete on return).  Returns retries, or max_iters+1 on final failure, or <0.
 static int cholesky_retry_padded(vzgp_handle* h, const double* A, int lda, int n_src, int np,
                                  double jitter0, int max_iters, double* L, double* Linv,
-                                 double* shift_out) {
+                                 double* shift_out, double* LinvT = nullptr) {
   int* flag = reinterpret_cast<int*>(h->small.as<char>() + kOffFlag);
   double shift = 0.0;
   int attempt = 0;
@@ -69,10 +88,16 @@ static int cholesky_retry_padded(vzgp_handle* h, const double* A, int lda, int n
     VZ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
     VZ_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)np * np, h->stream));
     VZ_TRY(launch_copy_lower_shift(h, A, lda, n_src, np, shift, L, np));
-    VZ_TRY(potrf_blocked(h, L, np, Linv, np, np, flag));
+    bool df = false;
+    VZ_TRY(factor_invert(h, L, Linv, LinvT, nullptr, np, flag, &df));
     int bad = 0;
     VZ_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     VZ_CUDA(cudaStreamSynchronize(h->stream));
+    if (df) {
+      int to = 0;
+      VZ_TRY(chol_dataflow_timed_out(h, &to));
+      if (to) { set_error("dataflow factorisation: a tile wait timed out"); return VZGP_ERR_CUDA; }
+    }
     if (!bad) break;
     if (attempt >= max_iters) {
       if (shift_out) *shift_out = shift;
@@ -115,10 +140,9 @@ static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const d
                               h->Kws.as<double>(), np));
   double shift = 0.0;
   int retries = cholesky_retry_padded(h, h->Kws.as<double>(), np, np, np, 1e-4, 5,
-                                      h->L.as<double>(), h->Linv.as<double>(), &shift);
+                                      h->L.as<double>(), h->Linv.as<double>(), &shift, h->LinvT.as<double>());
   if (retries < 0) return retries;
   if (shift_used) *shift_used = shift;
-  VZ_TRY(trtri_doubling(h, h->L.as<double>(), np, h->Linv.as<double>(), np, h->Tws.as<double>(), np, np));
   // alpha = Linv^T (Linv y), then one step of iterative refinement against K_y (+shift).
   double* alpha = h->alpha.as<double>();
   VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
@@ -154,8 +178,8 @@ static int nll_sequence(vzgp_handle* h, const double* X, const int32_t* Z, const
   VZ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
   VZ_CUDA(cudaMemsetAsync(h->Linv.as<double>(), 0, sizeof(double) * (size_t)np * np, h->stream));
   VZ_TRY(launch_copy_lower_shift(h, h->Kws.as<double>(), np, np, np, 0.0, h->L.as<double>(), np));
-  VZ_TRY(potrf_blocked(h, h->L.as<double>(), np, h->Linv.as<double>(), np, np, flag));
-  VZ_TRY(trtri_doubling(h, h->L.as<double>(), np, h->Linv.as<double>(), np, h->Tws.as<double>(), np, np));
+  bool df = false;   // dataflow kernel: factor, both inverses and K_y^-1 (one plane) in one launch
+  VZ_TRY(factor_invert(h, h->L.as<double>(), h->Linv.as<double>(), h->LinvT.as<double>(), h->Kinv.as<double>(), np, flag, &df));
   double* alpha = h->alpha.as<double>();
   VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
   VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, w, alpha));
@@ -166,9 +190,9 @@ static int nll_sequence(vzgp_handle* h, const double* X, const int32_t* Z, const
   double* out2 = reinterpret_cast<double*>(h->small.as<char>() + kOffLogdet);
   double* gout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);
   VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, w, out2));
-  VZ_TRY(launch_lauum(h, h->Linv.as<double>(), np, h->Kinv.as<double>(), np, np));
+  if (!df) VZ_TRY(launch_lauum(h, h->Linv.as<double>(), np, h->Kinv.as<double>(), np, np));
   VZ_TRY(launch_nll_grad_tiles(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, h->Kinv.as<double>(), np,
-                               alpha, h->Tws.as<double>(), gout));
+                               alpha, h->Tws.as<double>(), gout, df ? np : 0));
   return 0;
 }
 
@@ -190,20 +214,25 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
   double sn2 = p->observation_noise_variance;
   const int np = round_up(N, kBlk), nq = dc + dk + 2;
   auto bufs = [&](const void** o) {
-    const DevBuf* b[11] = {&h->X, &h->XT, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->small};
-    for (int q = 0; q < 11; ++q) o[q] = b[q]->ptr;
+    const DevBuf* b[kNllBufs] = {&h->X, &h->XT, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->small,
+                                 &h->LinvT, &h->df_tasks[1], &h->df_flags, &h->df_S};
+    for (int q = 0; q < kNllBufs; ++q) o[q] = b[q]->ptr;
   };
-  const void* cur[11];
+  const void* cur[kNllBufs];
   bufs(cur);
   bool hit = h->nll_exec && h->nll_key[0] == X && h->nll_key[1] == Z && h->nll_key[2] == y &&
              h->nll_key_dims[0] == N && h->nll_key_dims[1] == dc && h->nll_key_dims[2] == dk &&
              h->nll_key_dims[3] == n_valid;
-  for (int q = 0; hit && q < 11; ++q) hit = cur[q] == h->nll_bufs[q];   // a workspace was reallocated since the capture
+  hit = hit && (h->df_nb[1] == 0 || h->df_nb[1] == np / 64);   // another call re-planned the dataflow tasks
+  for (int q = 0; hit && q < kNllBufs; ++q) hit = cur[q] == h->nll_bufs[q];   // a workspace was reallocated since the capture
   h->fitted = false;
   if (!hit) {
     nll_graph_drop(h);
     VZ_TRY(ensure_model_buffers(h, np, dc, dk));
     VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));
+    VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)np * np));
+    VZ_TRY(chol_dataflow_prepare(h, np, true));   // task list + flags: not capturable
+    bufs(cur);
     h->n = N; h->np = np; h->dc = dc; h->dk = dk; h->n_valid = n_valid;
     const int64_t l0 = h->launches;
     if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 1; }
@@ -313,7 +342,8 @@ int vzgp_destroy(vzgp_handle* h) {
   Guard g(h->device);
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->XT,
-                    &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle, &h->pe_tmp})
+                    &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle, &h->pe_tmp,
+                    &h->LinvT, &h->df_tasks[0], &h->df_tasks[1], &h->df_flags, &h->df_S})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->copy_stream) {

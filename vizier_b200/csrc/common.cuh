@@ -16,6 +16,7 @@ namespace vzgp {
 constexpr int kBlk = 64;       // padding / factorisation block size
 constexpr int kMaxDc = 64;     // continuous feature dims supported by the tile kernels
 constexpr int kMaxDk = 32;     // categorical feature dims
+constexpr int kNllBufs = 15;   // handle buffers a captured NLL graph points into
 
 void set_error(const char* fmt, ...);
 
@@ -96,6 +97,7 @@ struct KernelParams {
 
 }  // namespace vzgp
 
+constexpr int kNllBufsDecl = vzgp::kNllBufs;
 struct vzgp_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -113,6 +115,7 @@ struct vzgp_handle {
   vzgp::DevBuf Z;      // [np x dk] int32
   vzgp::DevBuf L;      // [np x np]
   vzgp::DevBuf Linv;   // [np x np]
+  vzgp::DevBuf LinvT;  // [np x np] L^-T (upper), produced by the dataflow factorisation (dataflow.cu)
   vzgp::DevBuf alpha;  // [np]
   vzgp::DevBuf ypad;   // [np]
 
@@ -139,6 +142,10 @@ struct vzgp_handle {
   cudaGraphNode_t nll_nodes[3] = {nullptr, nullptr, nullptr};   // kernel matrix, transpose+scale, gradient tiles
   const void* nll_key[3] = {nullptr, nullptr, nullptr};          // X, Z, y
   int nll_key_dims[4] = {0, 0, 0, 0};                            // N, dc, dk, n_valid
-  const void* nll_bufs[11] = {};                                 // handle buffers the graph points into (a growth reallocates them)
+  const void* nll_bufs[kNllBufsDecl] = {};                                 // handle buffers the graph points into (a growth reallocates them)
   int nll_launches = 0;
+
+  // Dataflow factorisation (dataflow.cu): task list for the current nb, flags, chain partial sums.
+  vzgp::DevBuf df_tasks[2], df_flags, df_S;     // task lists without / with the K_y^-1 tasks
+  int df_nb[2] = {0, 0}, df_ntasks[2] = {0, 0};
 };

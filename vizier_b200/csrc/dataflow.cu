@@ -1,0 +1,538 @@
+// Blocked Cholesky, L^-1, L^-T and K_y^-1 = L^-T L^-1 as ONE dataflow kernel.
+//
+// Replaces (reference, via TFP / XLA:CPU LAPACK potrf + triangular_solve): retrying_cholesky at
+// vizier/_src/jax/models/tuned_gp_models.py:272-280, the factor inside GaussianProcess.log_prob
+// (vizier/_src/jax/stochastic_process_model.py:940-966) and precompute_predictive (:968-997).
+//
+// Round 1 ran the factorisation as 3 launches per 64-column panel (k_potf2_inv / k_trsm_panel /
+// k_syrk_potf2), then 2 log2(nb) launches of recursive doubling for L^-1 and one k_lauum, all on DFMA
+// register tiles: 0.5 ms of launch-separated latency chain at N = 1000.  Here every 64 x 64 tile of the
+// result is a TASK owned by one CTA; tasks hand tiles over through release/acquire flags in global memory,
+// operands are staged by TMA (64 x 16 boxes, 128-byte swizzle, 4-stage full/empty mbarrier ring) and
+// multiplied on the FP64 tensor pipe (DMMA.8x8x4), so a tile GEMM starts the moment its inputs exist:
+//
+//   chain CTA (ticket 0), for j = 0 .. nb-1            the only sequential part (nb = np / 64)
+//       L[j,j-1] = (A[j,j-1] - S(j,0)) * Linv_{j-1}^T   (Linv_{j-1} is still in shared memory)
+//       D        =  A[j,j]   - S(j,1) - L[j,j-1] L[j,j-1]^T
+//       L_jj, Linv_jj = potf2_inv_64(D)                 (potf2.cuh)
+//   PART(j,w)   S(j,0) = sum_{k<=j-2} L[j,k] L[j-1,k]^T,  S(j,1) = sum_{k<=j-2} L[j,k] L[j,k]^T
+//               (everything of the chain's update that does not depend on the previous panel)
+//   TILE(i,j)   i >= j+2:  L[i,j] = (A[i,j] - sum_{k<j} L[i,k] L[j,k]^T) * Linv_jj^T      (left-looking)
+//   LINV(i,j)   i > j:     Y[j,i] = -(sum_{k=j}^{i-1} Y[j,k] L[i,k]^T) * Linv_ii^T,  Y = L^-T; also stored
+//               transposed as X[i,j] (X = L^-1).  Working with Y makes every product an "NT" GEMM whose
+//               operands are both row-major [row][k] boxes.
+//   KINV(i,j)   i >= j:    Kinv[i,j] = sum_{k>=i} Y[i,k] Y[j,k]^T
+//
+// Scheduling.  Tasks are sorted by the panel step at which their last input appears; every CTA takes a
+// ticket (atomic counter) and runs the task of that rank.  A task only waits for tasks of lower rank and
+// for chain steps that themselves only wait for lower ranks, and tickets are handed out in dispatch
+// order, so the lowest unfinished task is always resident and can finish: no cooperative launch, no
+// co-residency assumption, safe next to other kernels (concurrent ARD restarts on other streams).
+// CTAs that arrive early accumulate the inputs that already exist and then follow the chain; the
+// critical path is  nb x (flag hop + 2 tile GEMMs + potf2_inv_64).  Waits are bounded by a timeout that
+// raises ctrl[1] instead of hanging the GPU.
+#include <cuda.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "async.cuh"
+#include "device.cuh"
+#include "launchers.h"
+
+#ifdef VZ_DF_TIMING
+namespace vzgp { __device__ long long g_df_t[64 * 8]; }
+#define VZ_DFT(j, s) do { if (threadIdx.x == 0 && (j) < 64) g_df_t[(j) * 8 + (s)] = clock64(); } while (0)
+#else
+#define VZ_DFT(j, s) do {} while (0)
+#endif
+#include "potf2.cuh"
+
+namespace vzgp {
+
+constexpr int kDfThreads = 288;   // 8 math warps + 1 TMA producer warp
+constexpr int kDfMath = 256;
+constexpr int kDfStages = 4;
+constexpr int kBoxD = 64 * 16;                 // one TMA box: 64 rows x 16 doubles (8 KB)
+constexpr int kStageD = 2 * kBoxD;             // A box | B box
+constexpr int kRingD = kDfStages * kStageD;    // 64 KB
+constexpr int kTbufD = 4 * kBoxD;              // a whole 64 x 64 operand tile in box layout (32 KB)
+constexpr size_t kDfSmemBytes = 1024 + sizeof(double) * (kRingD + kTbufD) + 256;
+constexpr int kChainLD = 66;                   // potf2_inv_64's row stride
+
+enum { DF_PART = 0, DF_TILE = 1, DF_LINV = 2, DF_KINV = 3 };
+
+struct DfArgs {
+  alignas(64) CUtensorMap mapL;   // [np x np] row-major, boxes 64 x 16, SWIZZLE_128B
+  alignas(64) CUtensorMap mapX;   // L^-1
+  alignas(64) CUtensorMap mapY;   // L^-T
+  double* L;
+  double* X;
+  double* Y;
+  double* S;        // [nb][2][64*64] partial sums for the chain
+  double* Kinv;     // lower tiles of K_y^-1, or nullptr
+  int* ctrl;        // [0] ticket counter, [1] timeout marker
+  int* flagL;       // [nb*nb] tile (i,j) of L final ((j,j): also Linv_jj in X and Y)
+  int* flagY;       // [nb*nb] tile (j,i), j < i, of Y (and X[i,j]) final
+  int* flagS;       // [nb*2]
+  const int4* tasks;
+  int ntasks;
+  int np, nb;
+  int* bad;         // raised on a non-positive / non-finite pivot
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long df_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin until *p != 0.  A producer that never shows up would be a bug (or a device fault upstream): give up
+// after 4 s, mark the run (the host reports an error) and let every later wait fall through.
+__device__ __forceinline__ void df_wait(const int* p, int* ctrl) {
+  if (ld_acquire_gpu(p)) return;
+  const unsigned long long t0 = df_timer_ns();
+  while (!ld_acquire_gpu(p)) {
+    __nanosleep(32);
+    if (*reinterpret_cast<volatile int*>(ctrl + 1)) return;
+    if (df_timer_ns() - t0 > 4000000000ull) { atomicExch(ctrl + 1, 1); return; }
+  }
+}
+
+// acc[f][g][0..1]: rows wm*16 + f*8 + fr, columns wn*32 + g*8 + 2*fk + {0,1}   (DMMA D fragment)
+struct DfFrag {
+  double v[2][4][2];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) v[f][g][0] = v[f][g][1] = 0.0;
+  }
+};
+
+// One 16-wide k slab from swizzled boxes: Abox/Bbox = [64 rows][16 doubles], 16-byte chunk c of row r at
+// chunk c ^ (r & 7).  Lane (fr, fk) reads k = 8h + 2fk, 8h + 2fk + 1: the operands of two DMMA k-steps.
+__device__ __forceinline__ void df_slab(DfFrag& acc, const double* Abox, const double* Bbox, int wm, int wn, int fr, int fk) {
+  const double* Arow0 = Abox + (wm * 16 + fr) * 16;
+  const double* Brow0 = Bbox + (wn * 32 + fr) * 16;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int co = (((h * 4 + fk) ^ fr) * 2);
+    const double2 a0 = *reinterpret_cast<const double2*>(Arow0 + co);
+    const double2 a1 = *reinterpret_cast<const double2*>(Arow0 + 8 * 16 + co);
+    double2 b[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) b[g] = *reinterpret_cast<const double2*>(Brow0 + g * 8 * 16 + co);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      dmma_8x8x4(acc.v[0][g][0], acc.v[0][g][1], a0.x, b[g].x);
+      dmma_8x8x4(acc.v[1][g][0], acc.v[1][g][1], a1.x, b[g].x);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      dmma_8x8x4(acc.v[0][g][0], acc.v[0][g][1], a0.y, b[g].y);
+      dmma_8x8x4(acc.v[1][g][0], acc.v[1][g][1], a1.y, b[g].y);
+    }
+  }
+}
+
+// C = As * Bs^T over k = 0..63, both operands in padded shared memory [64][kChainLD] (chain CTA).
+__device__ __forceinline__ void df_gemm_padded(DfFrag& acc, const double* As, const double* Bs, int wm, int wn, int fr, int fk) {
+  constexpr int LD = kChainLD;
+  const double* Ar = As + (wm * 16 + fr) * LD + 2 * fk;
+  const double* Br = Bs + (wn * 32 + fr) * LD + 2 * fk;
+#pragma unroll 2
+  for (int kk = 0; kk < 64; kk += 8) {
+    const double2 a0 = *reinterpret_cast<const double2*>(Ar + kk);
+    const double2 a1 = *reinterpret_cast<const double2*>(Ar + 8 * LD + kk);
+    double2 b[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) b[g] = *reinterpret_cast<const double2*>(Br + g * 8 * LD + kk);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      dmma_8x8x4(acc.v[0][g][0], acc.v[0][g][1], a0.x, b[g].x);
+      dmma_8x8x4(acc.v[1][g][0], acc.v[1][g][1], a1.x, b[g].x);
+      dmma_8x8x4(acc.v[0][g][0], acc.v[0][g][1], a0.y, b[g].y);
+      dmma_8x8x4(acc.v[1][g][0], acc.v[1][g][1], a1.y, b[g].y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Chain CTA: the sequential part (256 threads).
+// ---------------------------------------------------------------------------------------------------
+__device__ void df_chain(const DfArgs& a, double* sm) {
+  constexpr int LD = kChainLD;
+  double* A_ = sm;                  // [64][66]
+  double* X_ = sm + 64 * LD;        // [64][66]
+  double* T_ = X_ + 64 * LD;        // [32][34]
+  __shared__ double rd[64];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
+  const int np = a.np, nb = a.nb;
+  for (int j = 0; j < nb; ++j) {
+    double* Ljj = a.L + (size_t)j * 64 * np + j * 64;
+    VZ_DFT(j, 0);
+    if (j == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(Ljj + (size_t)i * np + j2);
+        const bool upper_blk = (j2 >> 4) > (i >> 4);
+        *reinterpret_cast<double2*>(A_ + i * LD + j2) = upper_blk ? make_double2(0.0, 0.0) : v;
+        *reinterpret_cast<double2*>(X_ + i * LD + j2) = make_double2(0.0, 0.0);
+      }
+    } else {
+      // ---- L[j,j-1] = (A[j,j-1] - S(j,0)) * Linv_{j-1}^T ; X_ still holds Linv_{j-1} ----
+      if (j >= 2) {
+        if (tid == 0) { df_wait(a.flagS + j * 2, a.ctrl); df_wait(a.flagS + j * 2 + 1, a.ctrl); }
+        __syncthreads();
+      }
+      VZ_DFT(j, 1);
+      double* Lsub = a.L + (size_t)j * 64 * np + (j - 1) * 64;
+      const double* S0 = a.S + (size_t)(j * 2) * 4096;
+      const double* S1 = S0 + 4096;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
+        double2 v = *reinterpret_cast<const double2*>(Lsub + (size_t)i * np + j2);
+        if (j >= 2) {
+          const double2 s = __ldcg(reinterpret_cast<const double2*>(S0 + i * 64 + j2));
+          v.x -= s.x; v.y -= s.y;
+        }
+        *reinterpret_cast<double2*>(A_ + i * LD + j2) = v;
+      }
+      __syncthreads();
+      DfFrag acc;
+      acc.zero();
+      df_gemm_padded(acc, A_, X_, wm, wn, fr, fk);
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
+          *reinterpret_cast<double2*>(Lsub + (size_t)r * np + c) = make_double2(acc.v[f][g][0], acc.v[f][g][1]);
+        }
+      __syncthreads();            // every warp is done reading A_ and X_
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
+          *reinterpret_cast<double2*>(X_ + r * LD + c) = make_double2(acc.v[f][g][0], acc.v[f][g][1]);
+        }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) { fence_proxy_async(); st_release_gpu(a.flagL + j * nb + (j - 1), 1); }   // early release
+      VZ_DFT(j, 2);
+      // ---- D = A[j,j] - S(j,1) - L[j,j-1] L[j,j-1]^T ----
+      acc.zero();
+      df_gemm_padded(acc, X_, X_, wm, wn, fr, fk);
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
+          double2 v = *reinterpret_cast<const double2*>(Ljj + (size_t)r * np + c);
+          if (j >= 2) {
+            const double2 s = __ldcg(reinterpret_cast<const double2*>(S1 + r * 64 + c));
+            v.x -= s.x; v.y -= s.y;
+          }
+          v.x -= acc.v[f][g][0]; v.y -= acc.v[f][g][1];
+          const bool upper_blk = (c >> 4) > (r >> 4);
+          *reinterpret_cast<double2*>(A_ + r * LD + c) = upper_blk ? make_double2(0.0, 0.0) : v;
+        }
+      __syncthreads();            // syrk reads of X_ finished
+      for (int e = tid; e < 64 * LD; e += 256) X_[e] = 0.0;
+    }
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    VZ_DFT(j, 3);
+    potf2_inv_64(A_, X_, T_, rd, &s_bad);
+    VZ_DFT(j, 4);
+    double* Xjj = a.X + (size_t)j * 64 * np + j * 64;
+    double* Yjj = a.Y + (size_t)j * 64 * np + j * 64;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
+      *reinterpret_cast<double2*>(Ljj + (size_t)i * np + j2) = *reinterpret_cast<const double2*>(A_ + i * LD + j2);
+      *reinterpret_cast<double2*>(Xjj + (size_t)i * np + j2) = *reinterpret_cast<const double2*>(X_ + i * LD + j2);
+      // transposed copy: Y[i][j2..j2+1] = X_[j2..j2+1][i]
+      *reinterpret_cast<double2*>(Yjj + (size_t)i * np + j2) = make_double2(X_[j2 * LD + i], X_[(j2 + 1) * LD + i]);
+    }
+    if (tid == 0 && s_bad) *a.bad = 1;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { fence_proxy_async(); st_release_gpu(a.flagL + j * nb + j, 1); }
+    VZ_DFT(j, 5);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Worker CTA: one tile task.
+// ---------------------------------------------------------------------------------------------------
+struct DfPlan {      // how a task's accumulation walks the k tiles (same on producer and consumers)
+  int k0, k1;        // k tiles [k0, k1)
+  int rowA, rowB;    // block rows of the A / B operand
+  int finalB;        // block index of the diagonal inverse used by the final product, or -1
+};
+__device__ __forceinline__ DfPlan df_plan(int type, int i, int j, int nb) {
+  DfPlan p;
+  p.finalB = -1;
+  if (type == DF_TILE) { p.k0 = 0; p.k1 = j; p.rowA = i; p.rowB = j; p.finalB = j; }
+  else if (type == DF_PART) { p.k0 = 0; p.k1 = i - 1; p.rowA = i; p.rowB = j; }         // j = i-1 or i
+  else if (type == DF_LINV) { p.k0 = j; p.k1 = i; p.rowA = j; p.rowB = i; p.finalB = i; }
+  else { p.k0 = i; p.k1 = nb; p.rowA = i; p.rowB = j; }
+  return p;
+}
+
+__device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t* full_bar, uint64_t* empty_bar) {
+  const int type = task.x, ti = task.y, tj = task.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np = a.np, nb = a.nb;
+  double* ring = sm;
+  double* Tbuf = sm + kRingD;
+  const DfPlan p = df_plan(type, ti, tj, nb);
+  if (warp == kDfMath / 32) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      unsigned slab = 0;
+      const CUtensorMap* mA = (type == DF_LINV || type == DF_KINV) ? &a.mapY : &a.mapL;
+      const CUtensorMap* mB = (type == DF_KINV) ? &a.mapY : &a.mapL;
+      for (int k = p.k0; k < p.k1; ++k) {
+        // inputs of this k tile
+        if (type == DF_TILE || type == DF_PART) {
+          df_wait(a.flagL + p.rowA * nb + k, a.ctrl);
+          df_wait(a.flagL + p.rowB * nb + k, a.ctrl);
+        } else if (type == DF_LINV) {
+          df_wait(k == tj ? a.flagL + tj * nb + tj : a.flagY + tj * nb + k, a.ctrl);
+          df_wait(a.flagL + ti * nb + k, a.ctrl);
+        } else {
+          df_wait(k == ti ? a.flagL + ti * nb + ti : a.flagY + ti * nb + k, a.ctrl);
+          df_wait(k == tj ? a.flagL + tj * nb + tj : a.flagY + tj * nb + k, a.ctrl);
+        }
+        fence_proxy_async();   // the tiles were written through the generic proxy by other CTAs
+        for (int ks = 0; ks < 4; ++ks, ++slab) {
+          const int stage = slab % kDfStages;
+          mbar_wait(empty_bar + stage, ((slab / kDfStages) & 1) ^ 1);
+          double* base = ring + stage * kStageD;
+          mbar_expect_tx(full_bar + stage, 2 * kBoxD * sizeof(double));
+          tma_load_2d(base, mA, k * 64 + ks * 16, p.rowA * 64, full_bar + stage);
+          tma_load_2d(base + kBoxD, mB, k * 64 + ks * 16, p.rowB * 64, full_bar + stage);
+        }
+      }
+      if (p.finalB >= 0) {
+        df_wait(a.flagL + p.finalB * nb + p.finalB, a.ctrl);
+        fence_proxy_async();
+        for (int ks = 0; ks < 4; ++ks, ++slab) {
+          const int stage = slab % kDfStages;
+          mbar_wait(empty_bar + stage, ((slab / kDfStages) & 1) ^ 1);
+          double* base = ring + stage * kStageD;
+          mbar_expect_tx(full_bar + stage, kBoxD * sizeof(double));
+          tma_load_2d(base + kBoxD, &a.mapX, p.finalB * 64 + ks * 16, p.finalB * 64, full_bar + stage);
+        }
+      }
+    }
+    return;
+  }
+  // ---------------- math warps ----------------
+  const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
+  auto math_sync = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(kDfMath) : "memory"); };
+  DfFrag acc;
+  acc.zero();
+  unsigned slab = 0;
+  for (int k = p.k0; k < p.k1; ++k) {
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks, ++slab) {
+      const int stage = slab % kDfStages;
+      mbar_wait(full_bar + stage, (slab / kDfStages) & 1);
+      const double* stg = ring + stage * kStageD;
+      df_slab(acc, stg, stg + kBoxD, wm, wn, fr, fk);
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(empty_bar + stage)) : "memory");
+    }
+  }
+  if (p.finalB >= 0) {
+    // T = (A - acc) or (-acc), as the A operand of the final product, in box layout.  TILE reads its own
+    // tile of the matrix being factored here (nobody else writes it; it is overwritten in place below).
+    const double* At = a.L + (size_t)ti * 64 * np + tj * 64;
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
+        double2 v;
+        if (type == DF_TILE) {
+          const double2 o = *reinterpret_cast<const double2*>(At + (size_t)r * np + c);
+          v = make_double2(o.x - acc.v[f][g][0], o.y - acc.v[f][g][1]);
+        } else {
+          v = make_double2(-acc.v[f][g][0], -acc.v[f][g][1]);
+        }
+        const int box = c >> 4, chunk = ((c & 15) >> 1) ^ (r & 7);
+        *reinterpret_cast<double2*>(Tbuf + box * kBoxD + r * 16 + chunk * 2) = v;
+      }
+    math_sync();
+    acc.zero();
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks, ++slab) {
+      const int stage = slab % kDfStages;
+      mbar_wait(full_bar + stage, (slab / kDfStages) & 1);
+      const double* stg = ring + stage * kStageD;
+      df_slab(acc, Tbuf + ks * kBoxD, stg + kBoxD, wm, wn, fr, fk);
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(empty_bar + stage)) : "memory");
+    }
+  }
+  // ---------------- epilogue ----------------
+  double* out;
+  int ldo = np;
+  int* flag = nullptr;
+  if (type == DF_TILE) { out = a.L + (size_t)ti * 64 * np + tj * 64; flag = a.flagL + ti * nb + tj; }
+  else if (type == DF_PART) { out = a.S + (size_t)(ti * 2 + (tj == ti ? 1 : 0)) * 4096; ldo = 64; flag = a.flagS + ti * 2 + (tj == ti ? 1 : 0); }
+  else if (type == DF_LINV) { out = a.Y + (size_t)tj * 64 * np + ti * 64; flag = a.flagY + tj * nb + ti; }
+  else { out = a.Kinv + (size_t)ti * 64 * np + tj * 64; }
+#pragma unroll
+  for (int f = 0; f < 2; ++f)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
+      *reinterpret_cast<double2*>(out + (size_t)r * ldo + c) = make_double2(acc.v[f][g][0], acc.v[f][g][1]);
+    }
+  if (type == DF_LINV) {   // X[i,j] = Y[j,i]^T
+    double* xt = a.X + (size_t)ti * 64 * np + tj * 64;
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
+        xt[(size_t)c * np + r] = acc.v[f][g][0];
+        xt[(size_t)(c + 1) * np + r] = acc.v[f][g][1];
+      }
+  }
+  if (flag != nullptr) {
+    __threadfence();
+    math_sync();
+    if (tid == 0) { fence_proxy_async(); st_release_gpu(flag, 1); }
+  }
+}
+
+__global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const __grid_constant__ DfArgs a) {
+  extern __shared__ double smem_raw[];
+  double* sm = smem_raw + (((1024u - (static_cast<unsigned>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u) >> 3);
+  __shared__ int s_ticket;
+  __shared__ uint64_t bars[2 * kDfStages];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_ticket = atomicAdd(a.ctrl, 1);
+    for (int s = 0; s < kDfStages; ++s) { mbar_init(bars + s, 1); mbar_init(bars + kDfStages + s, kDfMath / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int ticket = s_ticket;
+  if (ticket == 0) {
+    if (tid >= kDfMath) return;
+    df_chain(a, sm);
+    return;
+  }
+  if (ticket - 1 >= a.ntasks) return;
+  const int4 task = a.tasks[ticket - 1];
+  df_worker(a, task, sm, bars, bars + kDfStages);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------
+struct DfTaskHost { int key, type, i, j; };
+
+static void build_tasks(int nb, bool want_kinv, std::vector<int4>* out) {
+  std::vector<DfTaskHost> t;
+  // time of chain step j = 2j; a task's key = time after which its last input exists
+  for (int j = 2; j < nb; ++j) {
+    t.push_back({2 * j - 1, DF_PART, j, j - 1});
+    t.push_back({2 * j - 1, DF_PART, j, j});
+  }
+  for (int j = 0; j < nb; ++j)
+    for (int i = j + 2; i < nb; ++i) t.push_back({2 * j + 1, DF_TILE, i, j});
+  for (int i = 1; i < nb; ++i)
+    for (int j = i - 1; j >= 0; --j) t.push_back({2 * i + 1, DF_LINV, i, j});
+  if (want_kinv)
+    for (int i = nb - 1; i >= 0; --i)
+      for (int j = 0; j <= i; ++j) t.push_back({2 * nb + 1, DF_KINV, i, j});
+  std::stable_sort(t.begin(), t.end(), [](const DfTaskHost& x, const DfTaskHost& y) {
+    if (x.key != y.key) return x.key < y.key;
+    return x.type < y.type;           // PART before TILE before LINV inside one step; then insertion order
+  });
+  out->clear();
+  for (const auto& e : t) out->push_back(make_int4(e.type, e.i, e.j, e.key));
+}
+
+static bool df_enabled() {
+  static const bool enabled = [] { const char* e = getenv("VZGP_DATAFLOW"); return !(e && e[0] == '0'); }();
+  return enabled;
+}
+
+// Allocations and the task-list upload (not capturable): call before a stream capture that will contain
+// chol_dataflow with the same (np, want_kinv).
+int chol_dataflow_prepare(vzgp_handle* h, int np, bool want_kinv) {
+  if (!df_enabled()) return 1;
+  const int nb = np / 64;
+  if (nb < 2 || nb > 256) return 1;
+  const int w = want_kinv ? 1 : 0;
+  if (h->df_nb[w] != nb) {
+    std::vector<int4> tasks;
+    build_tasks(nb, want_kinv, &tasks);
+    VZ_TRY(h->df_tasks[w].reserve(sizeof(int4) * (tasks.size() + 1)));
+    VZ_CUDA(cudaMemcpyAsync(h->df_tasks[w].ptr, tasks.data(), sizeof(int4) * tasks.size(), cudaMemcpyHostToDevice, h->stream));
+    VZ_CUDA(cudaStreamSynchronize(h->stream));   // `tasks` goes out of scope
+    h->df_ntasks[w] = (int)tasks.size();
+    h->df_nb[w] = nb;
+  }
+  const size_t nflags = 8 + 2 * (size_t)nb * nb + 2 * (size_t)nb;
+  VZ_TRY(h->df_flags.reserve(sizeof(int) * nflags));
+  VZ_TRY(h->df_S.reserve(sizeof(double) * (size_t)nb * 2 * 4096));
+  VZ_CUDA(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDfSmemBytes));
+  return 0;
+}
+
+int chol_dataflow(vzgp_handle* h, double* L, double* Linv, double* LinvT, double* Kinv, int np, int* flag) {
+  const int nb = np / 64;
+  const bool want_kinv = Kinv != nullptr;
+  {
+    const int st = chol_dataflow_prepare(h, np, want_kinv);
+    if (st != 0) return st;
+  }
+  const size_t nflags = 8 + 2 * (size_t)nb * nb + 2 * (size_t)nb;
+  DfArgs a;
+  VZ_TRY(make_tensor_map_f64(&a.mapL, L, (uint64_t)np, (uint64_t)np, (uint64_t)np, 64));
+  VZ_TRY(make_tensor_map_f64(&a.mapX, Linv, (uint64_t)np, (uint64_t)np, (uint64_t)np, 64));
+  VZ_TRY(make_tensor_map_f64(&a.mapY, LinvT, (uint64_t)np, (uint64_t)np, (uint64_t)np, 64));
+  a.L = L; a.X = Linv; a.Y = LinvT; a.S = h->df_S.as<double>(); a.Kinv = Kinv;
+  int* f = h->df_flags.as<int>();
+  a.ctrl = f; a.flagL = f + 8; a.flagY = a.flagL + nb * nb; a.flagS = a.flagY + nb * nb;
+  a.tasks = h->df_tasks[want_kinv ? 1 : 0].as<int4>(); a.ntasks = h->df_ntasks[want_kinv ? 1 : 0];
+  a.np = np; a.nb = nb; a.bad = flag;
+  VZ_CUDA(cudaMemsetAsync(f, 0, sizeof(int) * nflags, h->stream));
+  k_chol_dataflow<<<1 + a.ntasks, kDfThreads, kDfSmemBytes, h->stream>>>(a);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+
+// 1 if some wait inside the last dataflow launches timed out (synchronises the stream).
+int chol_dataflow_timed_out(vzgp_handle* h, int* out) {
+  *out = 0;
+  if (!h->df_flags.ptr) return 0;
+  VZ_CUDA(cudaMemcpyAsync(out, h->df_flags.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // namespace vzgp

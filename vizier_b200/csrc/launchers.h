@@ -42,7 +42,18 @@ int launch_cov_update(vzgp_handle* h, const double* W, int ldw, int kdim, int mp
 
 int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
                           const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,
-                          double* partial, double* out);
+                          double* partial, double* out, int plane_rows = 0);
+
+// CUtensorMap (passed as void*) of an fp64 row-major matrix [rows x cols], row pitch ld elements, boxes of
+// box_rows x 16 doubles with the 128-byte swizzle (score.cu).
+int make_tensor_map_f64(void* map, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+// Blocked Cholesky + both triangular inverses (+ K_y^-1) as ONE dataflow kernel (dataflow.cu): L (lower,
+// holds the shifted matrix on entry), Linv = L^-1 (lower), LinvT = L^-T (upper), optional Kinv (lower
+// tiles of L^-T L^-1).  Returns 1 if the dataflow path is unavailable for this call (caller falls back).
+int chol_dataflow(vzgp_handle* h, double* L, double* Linv, double* LinvT, double* Kinv, int np, int* flag);
+int chol_dataflow_prepare(vzgp_handle* h, int np, bool want_kinv);
+int chol_dataflow_timed_out(vzgp_handle* h, int* out);
 
 int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                  double* score, double* mu, double* sigma, double* linf);

@@ -117,11 +117,11 @@ const void* nll_grad_tiles_func() { return reinterpret_cast<const void*>(&k_nll_
 
 int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
                           const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,
-                          double* partial, double* out) {
+                          double* partial, double* out, int plane_rows) {
   const int nb = np / 64, nq = kp.dc + kp.dk + 2, ntiles = nb * (nb + 1) / 2;
   size_t sm = sizeof(double) * (kp.dc * 2 * 66 + 8 * nq) + sizeof(int32_t) * kp.dk * 2 * 66;
   VZ_CUDA(cudaFuncSetAttribute(k_nll_grad_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_nll_grad_tiles<<<dim3(nb, nb), 256, sm, h->stream>>>(X, Z, np, n_valid, kp, Kinv, ldk, lauum_plane_rows(np), alpha,
+  k_nll_grad_tiles<<<dim3(nb, nb), 256, sm, h->stream>>>(X, Z, np, n_valid, kp, Kinv, ldk, plane_rows > 0 ? plane_rows : lauum_plane_rows(np), alpha,
                                                          partial, nb);
   VZ_CHECK_LAUNCH();
   k_reduce_partials<<<nq, 256, 0, h->stream>>>(partial, ntiles, nq, out);

@@ -414,6 +414,10 @@ static int make_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t 
   return 0;
 }
 
+int make_tensor_map_f64(void* map, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_map(static_cast<CUtensorMap*>(map), base, rows, cols, ld, box_rows);
+}
+
 size_t score_smem_bytes(int dc, int dk, bool with_linf) {
   (void)with_linf; (void)dc;
   const size_t big = kStages * kStageDoubles > 3 * kMaxDc * kLD1 ? kStages * kStageDoubles : 3 * kMaxDc * kLD1;
