@@ -122,6 +122,14 @@ int vzgp_cross_kernel(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M
 int vzgp_cholesky_retry(vzgp_handle* h, const double* A, int N, int lda, double jitter0,
                         int max_iters, double* L, int ldl, double* shift_out);
 
+/* The factorisation stage of the fit on its own (no jitter retry): L = chol(A), Linv = L^-1 and, if Kinv !=
+ * NULL, the lower triangle of A^-1 = L^-T L^-1.  A [N x lda] device (lower triangle read); L, Linv, Kinv
+ * [N x ld] device.  N > 64 runs the dataflow kernel (csrc/dataflow.cu: one launch for all three), N <= 64
+ * or VZGP_DATAFLOW=0 the panel kernels.  Returns 1 on a non-positive pivot (outputs hold NaN).
+ * Replaces potrf / triangular_solve inside stochastic_process_model.py:940-997. */
+int vzgp_factor_inverse(vzgp_handle* h, const double* A, int N, int lda, double* L, double* Linv, double* Kinv,
+                        int ld);
+
 /* Linv = L^-1 for lower-triangular L (both [N x ld] device, upper zeroed). */
 int vzgp_tri_inverse(vzgp_handle* h, const double* L, int N, int ldl, double* Linv, int ldi);
 
@@ -133,6 +141,33 @@ int vzgp_tri_inverse(vzgp_handle* h, const double* L, int N, int ldl, double* Li
  * the number of Cholesky retries (>=0). */
 int vzgp_fit(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
              int Dk, int n_valid, const vzgp_params* p);
+
+/* Multi-metric problems: the independent multi-task GP of tuned_gp_models.py:282-288 (tfpke.Independent)
+ * is n_metrics GPs sharing one kernel, one set of hyper-parameters and hence one factor; only alpha differs.
+ * Y is metric-major [n_metrics x N] device (metric m contiguous at Y + m*N); n_metrics <= 8.
+ * vzgp_fit / vzgp_nll_grad are the n_metrics = 1 cases.  The loss is the sum of the per-metric negative
+ * log-likelihoods (+ the regularisers once): grad uses G = M K_y^-1 - sum_m alpha_m alpha_m^T. */
+int vzgp_fit_multi(vzgp_handle* h, const double* X, const int32_t* Z, const double* Y, int N, int Dc,
+                   int Dk, int n_valid, int n_metrics, const vzgp_params* p);
+int vzgp_nll_grad_multi(vzgp_handle* h, const double* X, const int32_t* Z, const double* Y, int N, int Dc,
+                        int Dk, int n_valid, int n_metrics, const vzgp_params* p, double* loss_out,
+                        double* grad_out);
+
+/* Hyper-volume scalarised UCB, the acquisition VizierGPBandit uses for multi-objective problems
+ * (gp_bandit.py:214-242; acquisitions.py:571-625; scalarization.py:85-111):
+ *   u_m = mu_m + ucb_coefficient * sigma            (sigma is shared by the metrics of the independent GP)
+ *   score = mean_s max( (min_m max(u_m - reference_point[m], 0) / weights[s][m]) ^ n_metrics, max_scalarized[s] )
+ * weights [n_scalarizations x n_metrics] (rows of unit L2 norm, positive), reference_point [n_metrics]
+ * (acquisitions.py:132-149), max_scalarized [n_scalarizations] or NULL - all HOST.  No trust region
+ * (gp_bandit.py:241). */
+typedef struct vzgp_scalarization {
+  int n_metrics;
+  int n_scalarizations;          /* <= 4096; the reference default is 1000 */
+  const double* weights;
+  const double* reference_point;
+  const double* max_scalarized;
+  double ucb_coefficient;
+} vzgp_scalarization;
 
 /* Copy the fitted factor / alpha out (device destinations). */
 int vzgp_get_cholesky(vzgp_handle* h, double* L, int ldl);
@@ -160,6 +195,12 @@ int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const doubl
 int vzgp_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                double* score, double* mu, double* sigma, double* linf);
 
+/* Multi-metric counterpart of vzgp_score on a model fitted with vzgp_fit_multi: score [M] (required), mu
+ * [n_metrics x M] metric-major and sigma [M] optional; all device.  Uploads the scalarisation tables
+ * (synchronises once), then asynchronous. */
+int vzgp_score_multi(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_scalarization* sc,
+                     double* score, double* mu, double* sigma);
+
 /* Synchronises, returns the clamp counter accumulated since the last call and resets it. */
 int vzgp_clamped_count(vzgp_handle* h, int64_t* count_out);
 
@@ -174,6 +215,11 @@ int vzgp_score_host(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M,
  * posterior_predictive default).  Asynchronous on the handle's stream. */
 int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,
                    double* mean, double* cov, int ldc);
+
+/* The same for a model fitted with vzgp_fit_multi: mean is [n_metrics x M] metric-major; the covariance is
+ * shared by the metrics. */
+int vzgp_posterior_multi(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,
+                         double* mean, double* cov, int ldc);
 
 /* Top-`count` of score[0..M) (device), descending, ties -> lowest index, NaN
  * treated as -inf (vectorized_base.py:580,598).  idx_out [count] int64 and
@@ -283,6 +329,11 @@ typedef struct vzgp_eagle_config {
 int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
                    const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
                    int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score);
+/* The same loop with the multi-metric scalarised UCB as the scoring function (model fitted with
+ * vzgp_fit_multi). */
+int vzgp_eagle_run_multi(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_scalarization* sc,
+                         const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
+                         int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score);
 /* The same loop against a uniform ensemble (see vzgp_score_ensemble). */
 int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
                             const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,

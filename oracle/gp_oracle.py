@@ -242,17 +242,21 @@ def regularizer(params: GPParams, cont_dim_valid=None, cat_dim_valid=None) -> fl
 def nll(
     params: GPParams, x, y, z=None, row_valid=None, cont_dim_valid=None, cat_dim_valid=None
 ) -> float:
-  """-log N(y; 0, K_y) over the valid rows (no regulariser)."""
-  y = np.asarray(y, np.float64).reshape(-1)
+  """-log N(y; 0, K_y) over the valid rows (no regulariser).  y [N] or, for M metrics, [N, M]: the
+  independent multi-task GP (tuned_gp_models.py:282-288, tfpke.Independent) is M GPs sharing K_y, so
+  the terms simply add up."""
+  y = np.asarray(y, np.float64)
   n = y.shape[0]
+  y2 = y.reshape(n, -1)
   if row_valid is None:
     row_valid = np.ones(n, bool)
-  yv = np.where(row_valid, y, 0.0)
+  yv = np.where(np.asarray(row_valid, bool)[:, None], y2, 0.0)
   ky = kernel_matrix(params, x, z, row_valid, cont_dim_valid, cat_dim_valid)
   l, _, _ = retrying_cholesky(ky)
   w = sla.solve_triangular(l, yv, lower=True)
   nv = int(np.sum(row_valid))
-  return float(0.5 * w @ w + np.sum(np.log(np.diag(l))) + 0.5 * nv * math.log(2 * math.pi))
+  m = y2.shape[1]
+  return float(0.5 * np.sum(w * w) + m * np.sum(np.log(np.diag(l))) + 0.5 * m * nv * math.log(2 * math.pi))
 
 
 def loss(params: GPParams, x, y, z=None, row_valid=None, cont_dim_valid=None, cat_dim_valid=None) -> float:
@@ -266,16 +270,18 @@ def loss_and_grad(
 
   G = K_y^-1 - alpha alpha^T; dNLL/dp = 0.5*sum_ij G_ij dK_ij/dp.
   E_ij = dk/d(d2) = -(5/6)*sf2*(1+s)*exp(-s).
+  y [N, M] (independent multi-task GP, one shared K_y): G = M K_y^-1 - sum_m alpha_m alpha_m^T.
   """
   x = np.asarray(x, np.float64)
-  y = np.asarray(y, np.float64).reshape(-1)
   n, dc = x.shape
+  y = np.asarray(y, np.float64).reshape(n, -1)
+  n_metrics = y.shape[1]
   dk = 0 if z is None else z.shape[1]
   p = GPParams.from_vector(theta, dc, dk)
   if row_valid is None:
     row_valid = np.ones(n, bool)
   row_valid = np.asarray(row_valid, bool)
-  yv = np.where(row_valid, y, 0.0)
+  yv = np.where(row_valid[:, None], y, 0.0)
 
   d2 = scaled_sq_dist(
       x, x, p.continuous_length_scale_squared, z, z, p.categorical_length_scale_squared,
@@ -295,12 +301,12 @@ def loss_and_grad(
   w = sla.solve_triangular(l, yv, lower=True)
   alpha = sla.solve_triangular(l.T, w, lower=False)
   nv = int(np.sum(row_valid))
-  val = 0.5 * w @ w + np.sum(np.log(np.diag(l))) + 0.5 * nv * math.log(2 * math.pi)
+  val = 0.5 * np.sum(w * w) + n_metrics * np.sum(np.log(np.diag(l))) + 0.5 * n_metrics * nv * math.log(2 * math.pi)
   val += regularizer(p)
 
   linv = sla.solve_triangular(l, np.eye(n), lower=True)
   kinv = linv.T @ linv
-  g = kinv - np.outer(alpha, alpha)
+  g = n_metrics * kinv - alpha @ alpha.T
   vm = np.outer(row_valid, row_valid).astype(np.float64)
   g = g * vm  # padded rows/cols carry no dependence on theta
 
@@ -376,14 +382,15 @@ def precompute_predictive(
     params: GPParams, x, y, z=None, row_valid=None, cont_dim_valid=None, cat_dim_valid=None
 ) -> Predictive:
   x = np.asarray(x, np.float64)
-  y = np.asarray(y, np.float64).reshape(-1)
   n = x.shape[0]
+  y = np.asarray(y, np.float64)
+  y = y.reshape(-1) if y.ndim == 1 or y.shape[1] == 1 else y   # [N], or [N, M] for M metrics (alpha [N, M])
   if row_valid is None:
     row_valid = np.ones(n, bool)
   row_valid = np.asarray(row_valid, bool)
   ky = kernel_matrix(params, x, z, row_valid, cont_dim_valid, cat_dim_valid)
   l, _, it = retrying_cholesky(ky)
-  yv = np.where(row_valid, y, 0.0)
+  yv = np.where(row_valid if y.ndim == 1 else row_valid[:, None], y, 0.0)
   w = sla.solve_triangular(l, yv, lower=True)
   alpha = sla.solve_triangular(l.T, w, lower=False)
   return Predictive(params, x, z, l, alpha, row_valid, cont_dim_valid, cat_dim_valid, it)
@@ -542,3 +549,43 @@ def ucb_pe_score(pred_a: Predictive, pred_b: Predictive, xs, zs=None, *, mode: i
     dist = min_linf_distance(xs, pred_b.x[:n_tr], tr_dim_mask)
     acq = np.where((dist < trust_radius_value) | (trust_radius_value > 0.5), acq, -1e4 - dist)
   return acq, {'mean': mu, 'stddev': sd, 'stddev_from_all': sd_all}
+
+
+# ----------------------------------------------------------------------------
+# Multi-metric: hyper-volume scalarised UCB (gp_bandit.py:214-242; acquisitions.py:132-149, 571-625;
+# scalarization.py:85-111).  The scalarisation weights are an input (the reference draws them with
+# jax.random.normal: abs, then rows normalised to unit L2 norm).
+# ----------------------------------------------------------------------------
+def hv_reference_point(labels: np.ndarray, scale: float = 0.01) -> np.ndarray:
+  """worst - scale * (best - worst) per metric (acquisitions.py:132-149; labels are to be maximised)."""
+  labels = np.asarray(labels, np.float64)
+  best, worst = labels.max(axis=0), labels.min(axis=0)
+  return worst - scale * (best - worst)
+
+
+def hv_scalarize(objectives: np.ndarray, weights: np.ndarray, reference_point=None) -> np.ndarray:
+  """HyperVolumeScalarization.__call__ (scalarization.py:95-111): objectives [..., M], weights [S, M]
+  -> [S, ...]:  min_m(max(obj_m - ref_m, 0) / w_sm) ** M."""
+  obj = np.asarray(objectives, np.float64)
+  if reference_point is not None:
+    obj = obj - reference_point
+  obj = np.maximum(obj, 0.0)
+  w = np.asarray(weights, np.float64)
+  prod = obj[None, ...] * (1.0 / w).reshape((w.shape[0],) + (1,) * (obj.ndim - 1) + (w.shape[1],))
+  return np.min(prod, axis=-1) ** obj.shape[-1]
+
+
+def scalarized_ucb(mu: np.ndarray, sd: np.ndarray, weights: np.ndarray, reference_point, max_scalarized=None,
+                   coefficient: float = 1.8) -> np.ndarray:
+  """ScalarizeOverAcquisitions(UCB, HV scalarizer, mean over scalarisations, max with the best observed
+  scalarised label) - mu [B, M], sd [B] (shared by the metrics of the independent multi-task GP)."""
+  u = mu + coefficient * np.asarray(sd, np.float64)[:, None]
+  sc = hv_scalarize(u, weights, reference_point)      # [S, B]
+  if max_scalarized is not None:
+    sc = np.maximum(sc, np.asarray(max_scalarized, np.float64)[:, None])
+  return sc.mean(axis=0)
+
+
+def hv_max_scalarized(labels: np.ndarray, weights: np.ndarray, reference_point) -> np.ndarray:
+  """max over the observed label vectors of the scalarisation, per weight vector (gp_bandit.py:229-232)."""
+  return hv_scalarize(labels, weights, reference_point).max(axis=-1)

@@ -144,3 +144,44 @@ def test_to_xy_cached_equals_to_xy():
     np.testing.assert_array_equal(z1, z2)
     np.testing.assert_array_equal(y1, y2)
   assert names
+
+
+def test_designer_policy_call_sequence():
+  """DesignerPolicy.suggest (designer_policy.py:77-112): factory(problem) -> update(Completed, Active) ->
+  suggest(count), a fresh designer per request, trials split by status."""
+  from vizier_b200 import designer_policy as dp
+  from vizier_b200 import vz
+  calls = []
+
+  class Recorder(vz.Designer):
+    def __init__(self, problem):
+      calls.append(('factory', problem))
+    def update(self, completed, all_active):
+      assert isinstance(completed, vz.CompletedTrials) and isinstance(all_active, vz.ActiveTrials)
+      calls.append(('update', [t.id for t in completed.trials], [t.id for t in all_active.trials]))
+    def suggest(self, count=None):
+      calls.append(('suggest', count))
+      return [vz.TrialSuggestion({'x': 0.5}) for _ in range(count or 1)]
+
+  p = vz.ProblemStatement()
+  p.search_space.root.add_float_param('x', 0.0, 1.0)
+  p.metric_information.append(vz.MetricInformation(name='obj', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  sup = dp.InRamPolicySupporter(p)
+  done = [vz.Trial(parameters={'x': 0.1 * i}).complete(vz.Measurement({'obj': float(i)})) for i in range(3)]
+  sup.AddTrials(done + [vz.Trial(parameters={'x': 0.9})])
+  policy = dp.DesignerPolicy(sup, Recorder)
+  for count in (2, 1):
+    decision = policy.suggest(dp.SuggestRequest(study_config=p, count=count))
+    assert len(decision.suggestions) == count
+  assert [c[0] for c in calls] == ['factory', 'update', 'suggest'] * 2
+  assert calls[1] == ('update', [1, 2, 3], [4]) and calls[2] == ('suggest', 2)
+  with pytest.raises(NotImplementedError):
+    policy.early_stop(None)
+
+
+def test_designers_implement_the_designer_and_predictor_interfaces():
+  from vizier_b200 import vz
+  from vizier_b200.designers import gp_bandit, gp_ucb_pe
+  for cls in (gp_bandit.VizierGPBandit, gp_ucb_pe.VizierGPUCBPEBandit):
+    assert issubclass(cls, vz.Designer) and issubclass(cls, vz.Predictor)
+    assert not getattr(cls, '__abstractmethods__', None), cls.__abstractmethods__

@@ -287,3 +287,22 @@ def test_gp_ucb_pe_designer_batches_and_pending():
   s = d.suggest(1)[0]
   x = np.array([s.parameters[f'x{j}'].value for j in range(3)])
   assert np.linalg.norm(x - 0.6) > 1e-3
+
+
+def test_designer_policy_drives_the_gpu_designer():
+  """The service's path (policy_factory.py:48-53 -> DesignerPolicy.suggest, designer_policy.py:77-112):
+  a fresh VizierGPBandit per request, updated with all COMPLETED + ACTIVE trials, asked for suggestions."""
+  from vizier_b200 import designer_policy as dp
+  p = _problem(3)
+  sup = dp.InRamPolicySupporter(p)
+  policy = dp.DesignerPolicy(sup, lambda problem: gp_bandit.VizierGPBandit.from_problem(problem, seed=3))
+  rng = np.random.default_rng(0)
+  for step in range(4):
+    decision = policy.suggest(dp.SuggestRequest(study_config=p, count=2))
+    assert len(decision.suggestions) == 2
+    for s in decision.suggestions:
+      assert p.search_space.contains(s.parameters)
+      x = np.array([s.parameters[f'x{i}'].value for i in range(3)])
+      sup.AddTrials([vz.Trial(parameters=s.parameters).complete(vz.Measurement({'obj': float(-np.sum((x - 0.3) ** 2))}))])
+  assert len(sup.GetTrials(status_matches=vz.TrialStatus.COMPLETED)) == 8
+  assert 'oss_gp_bandit' in [ns[0] for ns in decision.suggestions[0].metadata.namespaces() if ns]

@@ -5,17 +5,26 @@ rep = sys.argv[1]
 out_json = sys.argv[2] if len(sys.argv) > 2 else None
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+hdr, units, vals = rows[0], rows[1], rows[2 + which]
 d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
 keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'smsp__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'smsp__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tensor.sum', 'smsp__sass_thread_inst_executed_op_dmma_pred_on.sum',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__grid_size', 'launch__block_size',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'sm__cycles_elapsed.max',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum',
         'smsp__inst_executed.sum']
 keys += [k for k in d if k.startswith('smsp__average_warps_issue_stalled') and k.endswith('per_issue_active.ratio')]
+keys += [k for k in d if 'pipe_tensor' in k and k not in keys]
 summ = {k: {'unit': d[k][0], 'value': d[k][1]} for k in keys if k in d}
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))

@@ -62,6 +62,17 @@ class PeParams(C.Structure):
   ]
 
 
+class Scalarization(C.Structure):
+  _fields_ = [
+      ('n_metrics', C.c_int),
+      ('n_scalarizations', C.c_int),
+      ('weights', C.POINTER(C.c_double)),
+      ('reference_point', C.POINTER(C.c_double)),
+      ('max_scalarized', C.POINTER(C.c_double)),
+      ('ucb_coefficient', C.c_double),
+  ]
+
+
 class EagleConfig(C.Structure):
   _fields_ = [
       ('visibility', C.c_double),
@@ -117,8 +128,13 @@ SIGNATURES = {
     'vzgp_kernel_matrix': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _pP, _d, _vp, _i]),
     'vzgp_cross_kernel': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _pP, _vp, _i]),
     'vzgp_cholesky_retry': (_i, [_vp, _vp, _i, _i, _d, _i, _vp, _i, _pd]),
+    'vzgp_factor_inverse': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
     'vzgp_tri_inverse': (_i, [_vp, _vp, _i, _i, _vp, _i]),
     'vzgp_fit': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _pP]),
+    'vzgp_fit_multi': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _pP]),
+    'vzgp_nll_grad_multi': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _pP, _pd, _pd]),
+    'vzgp_score_multi': (_i, [_vp, _vp, _vp, _i, C.POINTER(Scalarization), _vp, _vp, _vp]),
+    'vzgp_eagle_run_multi': (_i, [_vp, _pE, C.POINTER(Scalarization), _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
     'vzgp_get_cholesky': (_i, [_vp, _vp, _i]),
     'vzgp_get_alpha': (_i, [_vp, _vp]),
     'vzgp_nll_grad': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _pP, _pd, _pd]),
@@ -126,6 +142,7 @@ SIGNATURES = {
     'vzgp_clamped_count': (_i, [_vp, _pi64]),
     'vzgp_score_host': (_i, [_vp, _vp, _vp, _i, _pA, _vp, _vp, _vp, _vp]),
     'vzgp_posterior': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i]),
+    'vzgp_posterior_multi': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i]),
     'vzgp_topk': (_i, [_vp, _vp, _i64, _i, _pi64, _pd]),
     'vzgp_score_topk': (_i, [_vp, _vp, _vp, _i, _pA, _i, _vp, _pd, _pd, _pi64]),
     'vzgp_score_ensemble': (_i, [C.POINTER(_vp), _i, _vp, _vp, _i, _pA, _vp, _vp, _vp, _vp]),

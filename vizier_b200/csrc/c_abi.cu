@@ -44,7 +44,7 @@ struct Guard {
   }
 };
 
-static int ensure_model_buffers(vzgp_handle* h, int np, int dc, int dk) {
+static int ensure_model_buffers(vzgp_handle* h, int np, int dc, int dk, int n_metrics = 1) {
   VZ_TRY(h->X.reserve(sizeof(double) * (size_t)np * (dc > 0 ? dc : 1)));
   VZ_TRY(h->XT.reserve(sizeof(double) * 2 * (size_t)np * (dc > 0 ? dc : 1)));
   VZ_TRY(h->Z.reserve(sizeof(int32_t) * (size_t)np * (dk > 0 ? dk : 1)));
@@ -53,8 +53,8 @@ static int ensure_model_buffers(vzgp_handle* h, int np, int dc, int dk) {
   VZ_TRY(h->LinvT.reserve(sizeof(double) * (size_t)np * np));
   VZ_TRY(h->Kws.reserve(sizeof(double) * (size_t)np * np));
   VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)np * np));
-  VZ_TRY(h->alpha.reserve(sizeof(double) * (size_t)np));
-  VZ_TRY(h->ypad.reserve(sizeof(double) * (size_t)np * 4));  // y, w, r, tmp
+  VZ_TRY(h->alpha.reserve(sizeof(double) * (size_t)np * n_metrics));             // [M][np]
+  VZ_TRY(h->ypad.reserve(sizeof(double) * (size_t)np * 4 * n_metrics));  // [M][y, w, r, tmp]
   return 0;
 }
 
@@ -110,32 +110,50 @@ static int cholesky_retry_padded(vzgp_handle* h, const double* A, int lda, int n
   return attempt;
 }
 
+// alpha_m = Linv^T (Linv y_m) plus one step of iterative refinement against K_y (+shift), for every metric
+// (the independent multi-task GP shares the factor: tuned_gp_models.py:282-288).  y is metric-major
+// [M][N] device; ypad is [M][4][np] (y, w = Linv y, r, tmp), alpha [M][np].
+static int solve_alphas(vzgp_handle* h, const double* y, int N, int n_valid, int np, int n_metrics, double shift) {
+  for (int m = 0; m < n_metrics; ++m) {
+    double* yp = h->ypad.as<double>() + (size_t)m * 4 * np;
+    double* w = yp + np;
+    double* r = yp + 2 * np;
+    double* tmp = yp + 3 * np;
+    double* alpha = h->alpha.as<double>() + (size_t)m * np;
+    VZ_TRY(launch_pad_vector(h, y + (size_t)m * N, N, n_valid, np, yp));
+    VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
+    VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, w, alpha));
+    VZ_TRY(launch_residual(h, h->Kws.as<double>(), np, np, yp, alpha, r));
+    if (shift != 0.0) VZ_TRY(launch_axpy(h, np, -shift, alpha, r));
+    VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, r, tmp, 1));
+    VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, tmp, r));
+    VZ_TRY(launch_axpy(h, np, 1.0, r, alpha));
+  }
+  return 0;
+}
+
 // Shared front half of fit / nll_grad: pads inputs, builds K_y, factors, inverts, solves alpha.
 // On return: h->X/Z padded copies, Kws = K_y (unshifted), L, Linv, alpha valid; ypad[0..np) = y,
 // ypad[np..2np) = w = Linv y.
 static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N,
-                      int dc, int dk, int n_valid, const vzgp_params* p, double* shift_used) {
+                      int dc, int dk, int n_valid, const vzgp_params* p, double* shift_used, int n_metrics = 1) {
   VZ_ARG(h != nullptr, "handle");
   VZ_ARG(N >= 1, "N >= 1");
   VZ_ARG(n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
+  VZ_ARG(n_metrics >= 1 && n_metrics <= kMaxMetrics, "1 <= n_metrics <= 8");
   VZ_ARG(X != nullptr || dc == 0, "X");
   VZ_ARG(Z != nullptr || dk == 0, "Z");
   VZ_ARG(y != nullptr, "y");
   KernelParams kp;
   VZ_TRY(fill_kernel_params(p, dc, dk, &kp));
   const int np = round_up(N, kBlk);
-  VZ_TRY(ensure_model_buffers(h, np, dc, dk));
+  VZ_TRY(ensure_model_buffers(h, np, dc, dk, n_metrics));
   h->fitted = false;
-  h->n = N; h->np = np; h->dc = dc; h->dk = dk; h->n_valid = n_valid;
+  h->n = N; h->np = np; h->dc = dc; h->dk = dk; h->n_valid = n_valid; h->n_metrics = n_metrics;
   h->kp = kp; h->sn2 = p->observation_noise_variance;
-  double* yp = h->ypad.as<double>();
-  double* w = yp + np;
-  double* r = yp + 2 * np;
-  double* tmp = yp + 3 * np;
   if (dc > 0) VZ_TRY(launch_pad_rows(h, X, N, dc, np, h->X.as<double>()));
   if (dc > 0) VZ_TRY(launch_transpose_scale(h, h->X.as<double>(), np, dc, kp, h->XT.as<double>()));
   if (dk > 0) VZ_TRY(launch_pad_rows_i32(h, Z, N, dk, np, h->Z.as<int32_t>()));
-  VZ_TRY(launch_pad_vector(h, y, N, n_valid, np, yp));
   VZ_TRY(launch_kernel_matrix(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, h->sn2,
                               h->Kws.as<double>(), np));
   double shift = 0.0;
@@ -143,15 +161,7 @@ static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const d
                                       h->L.as<double>(), h->Linv.as<double>(), &shift, h->LinvT.as<double>());
   if (retries < 0) return retries;
   if (shift_used) *shift_used = shift;
-  // alpha = Linv^T (Linv y), then one step of iterative refinement against K_y (+shift).
-  double* alpha = h->alpha.as<double>();
-  VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
-  VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, w, alpha));
-  VZ_TRY(launch_residual(h, h->Kws.as<double>(), np, np, yp, alpha, r));
-  if (shift != 0.0) VZ_TRY(launch_axpy(h, np, -shift, alpha, r));
-  VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, r, tmp, 1));
-  VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, tmp, r));
-  VZ_TRY(launch_axpy(h, np, 1.0, r, alpha));
+  VZ_TRY(solve_alphas(h, y, N, n_valid, np, n_metrics, shift));
   return retries;
 }
 
@@ -163,36 +173,25 @@ static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const d
 // ARD restarts launch from different threads (the driver serialises them); replaying one graph does not.
 // ---------------------------------------------------------------------------
 static int nll_sequence(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int dc, int dk,
-                        int n_valid, const KernelParams& kp, double sn2) {
+                        int n_valid, const KernelParams& kp, double sn2, int n_metrics) {
   const int np = h->np;
-  double* yp = h->ypad.as<double>();
-  double* w = yp + np;
-  double* r = yp + 2 * np;
-  double* tmp = yp + 3 * np;
   int* flag = reinterpret_cast<int*>(h->small.as<char>() + kOffFlag);
   if (dc > 0) VZ_TRY(launch_pad_rows(h, X, N, dc, np, h->X.as<double>()));
   if (dc > 0) VZ_TRY(launch_transpose_scale(h, h->X.as<double>(), np, dc, kp, h->XT.as<double>()));
   if (dk > 0) VZ_TRY(launch_pad_rows_i32(h, Z, N, dk, np, h->Z.as<int32_t>()));
-  VZ_TRY(launch_pad_vector(h, y, N, n_valid, np, yp));
   VZ_TRY(launch_kernel_matrix(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, sn2, h->Kws.as<double>(), np));
   VZ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
   VZ_CUDA(cudaMemsetAsync(h->Linv.as<double>(), 0, sizeof(double) * (size_t)np * np, h->stream));
   VZ_TRY(launch_copy_lower_shift(h, h->Kws.as<double>(), np, np, np, 0.0, h->L.as<double>(), np));
   bool df = false;   // dataflow kernel: factor, both inverses and K_y^-1 (one plane) in one launch
   VZ_TRY(factor_invert(h, h->L.as<double>(), h->Linv.as<double>(), h->LinvT.as<double>(), h->Kinv.as<double>(), np, flag, &df));
-  double* alpha = h->alpha.as<double>();
-  VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
-  VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, w, alpha));
-  VZ_TRY(launch_residual(h, h->Kws.as<double>(), np, np, yp, alpha, r));
-  VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, r, tmp, 1));
-  VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, tmp, r));
-  VZ_TRY(launch_axpy(h, np, 1.0, r, alpha));
+  VZ_TRY(solve_alphas(h, y, N, n_valid, np, n_metrics, 0.0));
   double* out2 = reinterpret_cast<double*>(h->small.as<char>() + kOffLogdet);
   double* gout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);
-  VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, w, out2));
+  VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, h->ypad.as<double>() + np, out2, 4 * np, n_metrics));
   if (!df) VZ_TRY(launch_lauum(h, h->Linv.as<double>(), np, h->Kinv.as<double>(), np, np));
   VZ_TRY(launch_nll_grad_tiles(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, h->Kinv.as<double>(), np,
-                               alpha, h->Tws.as<double>(), gout, df ? np : 0));
+                               h->alpha.as<double>(), h->Tws.as<double>(), gout, df ? np : 0, n_metrics));
   return 0;
 }
 
@@ -206,7 +205,7 @@ static void nll_graph_drop(vzgp_handle* h) {
 // Returns 0 and fills host2 / hostg on success; 1 if the caller must use the eager path (bad pivot or
 // the graph could not be built); < 0 on errors.
 static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int dc, int dk,
-                          int n_valid, const vzgp_params* p, double* host2, double* hostg) {
+                          int n_valid, int n_metrics, const vzgp_params* p, double* host2, double* hostg) {
   static const bool enabled = [] { const char* e = getenv("VZGP_NLL_GRAPH"); return !(e && e[0] == '0'); }();
   if (!enabled) return 1;
   KernelParams kp;
@@ -222,21 +221,21 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
   bufs(cur);
   bool hit = h->nll_exec && h->nll_key[0] == X && h->nll_key[1] == Z && h->nll_key[2] == y &&
              h->nll_key_dims[0] == N && h->nll_key_dims[1] == dc && h->nll_key_dims[2] == dk &&
-             h->nll_key_dims[3] == n_valid;
+             h->nll_key_dims[3] == n_valid && h->nll_key_dims[4] == n_metrics;
   hit = hit && (h->df_nb[1] == 0 || h->df_nb[1] == np / 64);   // another call re-planned the dataflow tasks
   for (int q = 0; hit && q < kNllBufs; ++q) hit = cur[q] == h->nll_bufs[q];   // a workspace was reallocated since the capture
   h->fitted = false;
   if (!hit) {
     nll_graph_drop(h);
-    VZ_TRY(ensure_model_buffers(h, np, dc, dk));
+    VZ_TRY(ensure_model_buffers(h, np, dc, dk, n_metrics));
     VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));
     VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)np * np));
     VZ_TRY(chol_dataflow_prepare(h, np, true));   // task list + flags: not capturable
     bufs(cur);
-    h->n = N; h->np = np; h->dc = dc; h->dk = dk; h->n_valid = n_valid;
+    h->n = N; h->np = np; h->dc = dc; h->dk = dk; h->n_valid = n_valid; h->n_metrics = n_metrics;
     const int64_t l0 = h->launches;
     if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 1; }
-    const int st = nll_sequence(h, X, Z, y, N, dc, dk, n_valid, kp, sn2);
+    const int st = nll_sequence(h, X, Z, y, N, dc, dk, n_valid, kp, sn2, n_metrics);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
     h->nll_launches = (int)(h->launches - l0);
@@ -263,20 +262,22 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
     for (int q = 0; q < 3; ++q) h->nll_nodes[q] = found[q];
     h->nll_key[0] = X; h->nll_key[1] = Z; h->nll_key[2] = y;
     h->nll_key_dims[0] = N; h->nll_key_dims[1] = dc; h->nll_key_dims[2] = dk; h->nll_key_dims[3] = n_valid;
+    h->nll_key_dims[4] = n_metrics;
     bufs(h->nll_bufs);
   }
   h->kp = kp; h->sn2 = sn2;
-  // new hyper-parameters: argument 4 (+5) of the kernel matrix, 3 of transpose+scale, 4 of the gradient tiles
-  const int arg_idx[3] = {4, 3, 4};
+  // new hyper-parameters, by the argument positions pinned in launchers.h (static_asserted against the kernels)
+  const int arg_idx[3] = {kKernelMatrixKpArg, kTransposeScaleKpArg, kNllGradTilesKpArg};
+  const int arg_cnt[3] = {kKernelMatrixArgs, kTransposeScaleArgs, kNllGradTilesArgs};
   for (int q = 0; q < 3; ++q) {
     if (!h->nll_nodes[q]) continue;
     cudaKernelNodeParams kpar;
     VZ_CUDA(cudaGraphKernelNodeGetParams(h->nll_nodes[q], &kpar));
     void* args[16];
-    const int nargs = q == 0 ? 8 : (q == 1 ? 5 : 11);
+    const int nargs = arg_cnt[q];
     for (int a2 = 0; a2 < nargs; ++a2) args[a2] = kpar.kernelParams[a2];
     args[arg_idx[q]] = &kp;
-    if (q == 0) args[5] = &sn2;
+    if (q == 0) args[kKernelMatrixDiagArg] = &sn2;
     kpar.kernelParams = args;
     VZ_CUDA(cudaGraphExecKernelNodeSetParams(h->nll_exec, h->nll_nodes[q], &kpar));
   }
@@ -343,7 +344,7 @@ int vzgp_destroy(vzgp_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->XT,
                     &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle, &h->pe_tmp,
-                    &h->LinvT, &h->df_tasks[0], &h->df_tasks[1], &h->df_flags, &h->df_S})
+                    &h->LinvT, &h->df_tasks[0], &h->df_tasks[1], &h->df_flags, &h->df_S, &h->scal})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->copy_stream) {
@@ -414,6 +415,43 @@ int vzgp_cholesky_retry(vzgp_handle* h, const double* A, int N, int lda, double 
   return retries;
 }
 
+int vzgp_factor_inverse(vzgp_handle* h, const double* A, int N, int lda, double* L, double* Linv, double* Kinv,
+                        int ld) {
+  VZ_ARG(h && A && L && Linv, "handle / A / L / Linv");
+  VZ_ARG(N >= 1 && lda >= N && ld >= N, "N, lda, ld");
+  Guard g(h->device);
+  const int np = round_up(N, kBlk);
+  VZ_TRY(ensure_model_buffers(h, np, 1, 0));
+  h->fitted = false;
+  const bool want_kinv = Kinv != nullptr;
+  if (want_kinv) VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));
+  int* flag = reinterpret_cast<int*>(h->small.as<char>() + kOffFlag);
+  VZ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+  VZ_CUDA(cudaMemsetAsync(h->Linv.as<double>(), 0, sizeof(double) * (size_t)np * np, h->stream));
+  VZ_TRY(launch_copy_lower_shift(h, A, lda, N, np, 0.0, h->L.as<double>(), np));
+  bool df = false;
+  VZ_TRY(factor_invert(h, h->L.as<double>(), h->Linv.as<double>(), h->LinvT.as<double>(),
+                       want_kinv ? h->Kinv.as<double>() : nullptr, np, flag, &df));
+  if (want_kinv && !df) {
+    // panel-kernel fallback: K^-1 as kLauumSplit partial planes; sum them into plane 0's lower triangle
+    VZ_TRY(launch_lauum(h, h->Linv.as<double>(), np, h->Kinv.as<double>(), np, np));
+    VZ_TRY(launch_sum_planes(h, h->Kinv.as<double>(), np, lauum_plane_rows(np)));
+  }
+  k_unpad_lower<<<dim3((N + 255) / 256, N), 256, 0, h->stream>>>(h->L.as<double>(), np, N, L, ld);
+  k_unpad_lower<<<dim3((N + 255) / 256, N), 256, 0, h->stream>>>(h->Linv.as<double>(), np, N, Linv, ld);
+  if (want_kinv) k_unpad_lower<<<dim3((N + 255) / 256, N), 256, 0, h->stream>>>(h->Kinv.as<double>(), np, N, Kinv, ld);
+  VZ_CHECK_LAUNCH();
+  h->launches += want_kinv ? 3 : 2;
+  int bad = 0, to = 0;
+  VZ_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  if (df) {
+    VZ_TRY(chol_dataflow_timed_out(h, &to));
+    if (to) { set_error("dataflow factorisation: a tile wait timed out"); return VZGP_ERR_CUDA; }
+  }
+  return bad ? 1 : 0;
+}
+
 int vzgp_tri_inverse(vzgp_handle* h, const double* L, int N, int ldl, double* Linv, int ldi) {
   VZ_ARG(h && L && Linv, "handle / L / Linv");
   VZ_ARG(N >= 1 && ldl >= N && ldi >= N, "N, ldl, ldi");
@@ -433,14 +471,19 @@ int vzgp_tri_inverse(vzgp_handle* h, const double* L, int N, int ldl, double* Li
   return 0;
 }
 
-int vzgp_fit(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
-             int Dk, int n_valid, const vzgp_params* p) {
+int vzgp_fit_multi(vzgp_handle* h, const double* X, const int32_t* Z, const double* Y, int N, int Dc,
+                   int Dk, int n_valid, int n_metrics, const vzgp_params* p) {
   VZ_ARG(h != nullptr, "handle");
   Guard g(h->device);
-  int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, nullptr);
+  int retries = fit_common(h, X, Z, Y, N, Dc, Dk, n_valid, p, nullptr, n_metrics);
   if (retries < 0) return retries;
   h->fitted = true;
   return retries;
+}
+
+int vzgp_fit(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
+             int Dk, int n_valid, const vzgp_params* p) {
+  return vzgp_fit_multi(h, X, Z, y, N, Dc, Dk, n_valid, 1, p);
 }
 
 int vzgp_get_cholesky(vzgp_handle* h, double* L, int ldl) {
@@ -464,14 +507,20 @@ int vzgp_get_alpha(vzgp_handle* h, double* alpha) {
 
 int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
                   int Dk, int n_valid, const vzgp_params* p, double* loss_out, double* grad_out) {
+  return vzgp_nll_grad_multi(h, X, Z, y, N, Dc, Dk, n_valid, 1, p, loss_out, grad_out);
+}
+
+int vzgp_nll_grad_multi(vzgp_handle* h, const double* X, const int32_t* Z, const double* y, int N, int Dc,
+                        int Dk, int n_valid, int n_metrics, const vzgp_params* p, double* loss_out, double* grad_out) {
   VZ_ARG(h && loss_out && grad_out, "handle / outputs");
+  VZ_ARG(n_metrics >= 1 && n_metrics <= kMaxMetrics, "1 <= n_metrics <= 8");
   Guard g(h->device);
   // Regularisers: tuned_gp_models.py:167,180,192,269 -> 0.01*log(x/c)^2, derivative 0.02*log(x/c)/x.
   auto reg = [](double x, double c) { double l = std::log(x / c); return 0.01 * l * l; };
   auto dreg = [](double x, double c) { return 0.02 * std::log(x / c) / x; };
   auto finish = [&](double half_logdet_plus_quad, const double* hostg) {
     const double sf2 = p->signal_variance, sn2 = p->observation_noise_variance;
-    double loss = half_logdet_plus_quad + 0.5 * n_valid * std::log(2.0 * M_PI);
+    double loss = half_logdet_plus_quad + 0.5 * n_metrics * n_valid * std::log(2.0 * M_PI);
     loss += reg(sf2, 0.039) + reg(sn2, 0.0039);
     for (int k = 0; k < Dk; ++k) {
       const double l = p->categorical_length_scale_squared[k];
@@ -488,7 +537,7 @@ int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const doubl
     *loss_out = loss;
   };
   static const bool small_ok = [] { const char* e = getenv("VZGP_NLL_SMALL"); return !(e && e[0] == '0'); }();
-  if (N <= kBlk && small_ok) {
+  if (N <= kBlk && small_ok && n_metrics == 1) {
     // Small studies: the whole evaluation is one single-CTA kernel (nll_small.cu).  The handle's
     // fitted model is not touched (ARD callers refit with the chosen parameters afterwards).
     VZ_ARG(N >= 1 && n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
@@ -514,7 +563,7 @@ int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const doubl
     VZ_ARG(Z != nullptr || Dk == 0, "Z");
     VZ_ARG(y != nullptr, "y");
     double g2[2], gg[kMaxDc + kMaxDk + 2];
-    const int st = nll_graph_eval(h, X, Z, y, N, Dc, Dk, n_valid, p, g2, gg);
+    const int st = nll_graph_eval(h, X, Z, y, N, Dc, Dk, n_valid, n_metrics, p, g2, gg);
     if (st < 0) return st;
     if (st == 0) {
       finish(g2[1] + g2[0], gg);
@@ -522,17 +571,17 @@ int vzgp_nll_grad(vzgp_handle* h, const double* X, const int32_t* Z, const doubl
     }
   }
   double shift = 0.0;
-  int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, &shift);
+  int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, &shift, n_metrics);
   if (retries < 0) return retries;
   const int np = h->np, nq = Dc + Dk + 2;
   VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));   // partial planes of K_y^-1
   double* out2 = reinterpret_cast<double*>(h->small.as<char>() + kOffLogdet);
   double* gout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);
   double* w = h->ypad.as<double>() + np;
-  VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, w, out2));
+  VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, w, out2, 4 * np, n_metrics));
   VZ_TRY(launch_lauum(h, h->Linv.as<double>(), np, h->Kinv.as<double>(), np, np));
   VZ_TRY(launch_nll_grad_tiles(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, h->kp,
-                               h->Kinv.as<double>(), np, h->alpha.as<double>(), h->Tws.as<double>(), gout));
+                               h->Kinv.as<double>(), np, h->alpha.as<double>(), h->Tws.as<double>(), gout, 0, n_metrics));
   double host2[2];
   double hostg[kMaxDc + kMaxDk + 2];
   VZ_CUDA(cudaMemcpyAsync(host2, out2, sizeof(host2), cudaMemcpyDeviceToHost, h->stream));
@@ -738,9 +787,11 @@ int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp
 static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
                           const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,
                           const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
-                          double* best_score, vzgp_handle* const* ens = nullptr, int n_ens = 0) {
-  VZ_ARG(h && cfg && (acq || pe) && best_score, "handle / pointers");
+                          double* best_score, vzgp_handle* const* ens = nullptr, int n_ens = 0,
+                          const vzgp_scalarization* scal = nullptr) {
+  VZ_ARG(h && cfg && (acq || pe || scal) && best_score, "handle / pointers");
   auto score_batch = [&](const double* xs, const int32_t* zs, int m, double* out) -> int {
+    if (scal) return launch_score_multi(h, xs, zs, m, out, nullptr, nullptr);
     if (pe) return launch_score_pe(h, hB, xs, zs, m, pe, out, nullptr, nullptr, nullptr);
     if (n_ens > 1) return launch_score_ensemble(ens, n_ens, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
     return launch_score(h, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
@@ -792,6 +843,7 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   e.tmp_z = ip; ip += (size_t)count * Dk;
   e.P = P; e.B = B; e.D = D; e.Dk = Dk; e.count = count; e.cfg = *cfg; e.seed = seed;
   VZ_TRY(eagle_prepare(e));
+  if (scal) VZ_TRY(prepare_scalarization(h, scal));
   VZ_TRY(launch_eagle_init(h, e));
   if (n_prior > 0) {
     VZ_TRY(score_batch(prior, Dk > 0 ? prior_z : nullptr, n_prior, prior_r));
@@ -808,11 +860,11 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   // CUDA graph of the suggest -> score -> update sequence: the iteration counter and all state
   // live in device memory, so the launches are identical and the host only enqueues graphs.
   bool done = false;
-  if (n_ens <= 1 && eagle_persistent_eligible(h, pe ? hB : nullptr, e)) {
+  if (n_ens <= 1 && !scal && eagle_persistent_eligible(h, pe ? hB : nullptr, e)) {
     // small study: the whole loop is one persistent single-CTA kernel
     VZ_TRY(launch_eagle_persistent64(h, pe ? hB : nullptr, e, acq, pe, steps));
     done = true;
-  } else if (n_ens <= 1 && eagle_grid_eligible(h, pe ? hB : nullptr, e)) {
+  } else if (n_ens <= 1 && !scal && eagle_grid_eligible(h, pe ? hB : nullptr, e)) {
     // mid-size study: one cooperative launch, phases separated by grid barriers.  If the cooperative
     // launch is refused (nothing has run then) the launch-per-phase loop below takes over.
     done = launch_eagle_grid(h, pe ? hB : nullptr, e, acq, pe, steps) == 0;
@@ -866,6 +918,26 @@ int vzgp_eagle_run(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_acq*
   VZ_ARG(acq != nullptr, "acq");
   return eagle_run_impl(h, nullptr, cfg, acq, nullptr, prior, prior_z, n_prior, cat_sizes, count, seed, best_x,
                         best_z, best_score);
+}
+
+int vzgp_eagle_run_multi(vzgp_handle* h, const vzgp_eagle_config* cfg, const vzgp_scalarization* sc,
+                         const double* prior, const int32_t* prior_z, int n_prior, const int32_t* cat_sizes,
+                         int count, uint64_t seed, double* best_x, int32_t* best_z, double* best_score) {
+  VZ_ARG(sc != nullptr, "scalarization");
+  return eagle_run_impl(h, nullptr, cfg, nullptr, nullptr, prior, prior_z, n_prior, cat_sizes, count, seed, best_x,
+                        best_z, best_score, nullptr, 0, sc);
+}
+
+int vzgp_score_multi(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_scalarization* sc,
+                     double* score, double* mu, double* sigma) {
+  VZ_ARG(h != nullptr && sc != nullptr, "handle / scalarization");
+  if (!h->fitted) { set_error("vzgp_score_multi before vzgp_fit_multi"); return VZGP_ERR_STATE; }
+  VZ_ARG(M >= 0 && (M == 0 || score != nullptr), "M / score");
+  VZ_ARG(M == 0 || Xs != nullptr || h->dc == 0, "Xs");
+  VZ_ARG(M == 0 || Zs != nullptr || h->dk == 0, "Zs");
+  Guard g(h->device);
+  VZ_TRY(prepare_scalarization(h, sc));
+  return launch_score_multi(h, Xs, Zs, M, score, mu, sigma);
 }
 
 static int check_pe(vzgp_handle* hA, vzgp_handle* hB, const vzgp_pe_params* pe) {
@@ -928,6 +1000,11 @@ int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_conf
 
 int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,
                    double* mean, double* cov, int ldc) {
+  return vzgp_posterior_multi(h, Xs, Zs, M, add_noise, mean, cov, ldc);
+}
+
+int vzgp_posterior_multi(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,
+                         double* mean, double* cov, int ldc) {
   VZ_ARG(h && mean && cov, "handle / outputs");
   if (!h->fitted) { set_error("vzgp_posterior before vzgp_fit"); return VZGP_ERR_STATE; }
   VZ_ARG(M >= 1 && ldc >= M, "M, ldc");
@@ -936,13 +1013,14 @@ int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, i
   const int np = h->np, mp = round_up(M, kBlk);
   // layout in Kinv buffer: Ks [mp x np] | W [mp x np] | C [mp x mp] | Xs padded [mp x dc] | mean [mp]
   const size_t nks = (size_t)mp * np, nc = (size_t)mp * mp, nx = (size_t)mp * (h->dc > 0 ? h->dc : 1);
-  VZ_TRY(h->Kinv.reserve(sizeof(double) * (2 * nks + nc + nx + mp) + sizeof(int32_t) * (size_t)mp * (h->dk > 0 ? h->dk : 1)));
+  const int nm = h->n_metrics;
+  VZ_TRY(h->Kinv.reserve(sizeof(double) * (2 * nks + nc + nx + (size_t)mp * nm) + sizeof(int32_t) * (size_t)mp * (h->dk > 0 ? h->dk : 1)));
   double* Ks = h->Kinv.as<double>();
   double* W = Ks + nks;
   double* C = W + nks;
   double* Xp = C + nc;
   double* mu = Xp + nx;
-  int32_t* Zp = reinterpret_cast<int32_t*>(mu + mp);
+  int32_t* Zp = reinterpret_cast<int32_t*>(mu + (size_t)mp * nm);
   VZ_CUDA(cudaMemsetAsync(Ks, 0, sizeof(double) * nks, h->stream));
   if (h->dc > 0) VZ_TRY(launch_pad_rows(h, Xs, M, h->dc, mp, Xp));
   if (h->dk > 0) VZ_TRY(launch_pad_rows_i32(h, Zs, M, h->dk, mp, Zp));
@@ -950,10 +1028,12 @@ int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, i
   VZ_TRY(launch_cross_kernel(h, Xp, Zp, mp, Xp, Zp, mp, mp, h->kp, C, mp));
   VZ_TRY(launch_gemm_nt_tri(h, Ks, np, mp, h->Linv.as<double>(), np, np, W, np));
   VZ_TRY(launch_cov_update(h, W, np, np, mp, C, mp, add_noise ? h->sn2 : 0.0));
-  VZ_TRY(launch_gemv_rows(h, Ks, np, mp, h->alpha.as<double>(), mu, 0, np));
+  for (int m = 0; m < nm; ++m)
+    VZ_TRY(launch_gemv_rows(h, Ks, np, mp, h->alpha.as<double>() + (size_t)m * np, mu + (size_t)m * mp, 0, np));
   VZ_CUDA(cudaMemcpy2DAsync(cov, sizeof(double) * ldc, C, sizeof(double) * mp, sizeof(double) * M, M,
                             cudaMemcpyDeviceToDevice, h->stream));
-  VZ_CUDA(cudaMemcpyAsync(mean, mu, sizeof(double) * M, cudaMemcpyDeviceToDevice, h->stream));
+  VZ_CUDA(cudaMemcpy2DAsync(mean, sizeof(double) * M, mu, sizeof(double) * mp, sizeof(double) * M, nm,
+                            cudaMemcpyDeviceToDevice, h->stream));
   return 0;
 }
 

@@ -16,6 +16,7 @@ namespace vzgp {
 constexpr int kBlk = 64;       // padding / factorisation block size
 constexpr int kMaxDc = 64;     // continuous feature dims supported by the tile kernels
 constexpr int kMaxDk = 32;     // categorical feature dims
+constexpr int kMaxMetrics = 8; // metrics of the independent multi-task GP (one factor, several alpha)
 constexpr int kNllBufs = 15;   // handle buffers a captured NLL graph points into
 
 void set_error(const char* fmt, ...);
@@ -95,6 +96,13 @@ struct KernelParams {
   double inv_ls2_k[kMaxDk];
 };
 
+// Hyper-volume scalarised UCB parameters (multi.cu); the weight tables live in handle->scal.
+struct ScalArgs {
+  int n_metrics = 0, n_scal = 0, has_max = 0;
+  double coef = 1.8;
+  double ref[kMaxMetrics] = {};
+};
+
 }  // namespace vzgp
 
 constexpr int kNllBufsDecl = vzgp::kNllBufs;
@@ -107,7 +115,7 @@ struct vzgp_handle {
 
   // Fitted model (all padded to np = round_up(n, 64); pad rows are identity/zero).
   bool fitted = false;
-  int n = 0, np = 0, dc = 0, dk = 0, n_valid = 0;
+  int n = 0, np = 0, dc = 0, dk = 0, n_valid = 0, n_metrics = 1;
   vzgp::KernelParams kp;
   double sn2 = 0.0;
   vzgp::DevBuf X;      // [np x dc]
@@ -116,8 +124,8 @@ struct vzgp_handle {
   vzgp::DevBuf L;      // [np x np]
   vzgp::DevBuf Linv;   // [np x np]
   vzgp::DevBuf LinvT;  // [np x np] L^-T (upper), produced by the dataflow factorisation (dataflow.cu)
-  vzgp::DevBuf alpha;  // [np]
-  vzgp::DevBuf ypad;   // [np]
+  vzgp::DevBuf alpha;  // [n_metrics][np]
+  vzgp::DevBuf ypad;   // [n_metrics][4][np]: y, w = Linv y, r, tmp
 
   // Workspaces.
   vzgp::DevBuf Kws;     // [np x np] kernel matrix / temporaries
@@ -130,6 +138,8 @@ struct vzgp_handle {
   vzgp::DevBuf out_dev;
   vzgp::DevBuf eagle;   // eagle state
   vzgp::DevBuf pe_tmp;  // GP-UCB-PE: per-candidate pieces of the two models
+  vzgp::DevBuf scal;    // multi-metric: [S][M] inverse scalarisation weights, then [S] best observed values
+  vzgp::ScalArgs scal_args;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaStream_t copy_stream = nullptr;   // H2D staging of vzgp_score_host, overlapped with scoring
@@ -141,7 +151,7 @@ struct vzgp_handle {
   cudaGraphExec_t nll_exec = nullptr;
   cudaGraphNode_t nll_nodes[3] = {nullptr, nullptr, nullptr};   // kernel matrix, transpose+scale, gradient tiles
   const void* nll_key[3] = {nullptr, nullptr, nullptr};          // X, Z, y
-  int nll_key_dims[4] = {0, 0, 0, 0};                            // N, dc, dk, n_valid
+  int nll_key_dims[5] = {0, 0, 0, 0, 0};                         // N, dc, dk, n_valid, n_metrics
   const void* nll_bufs[kNllBufsDecl] = {};                                 // handle buffers the graph points into (a growth reallocates them)
   int nll_launches = 0;
 

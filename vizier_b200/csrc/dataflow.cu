@@ -8,8 +8,13 @@
 // k_syrk_potf2), then 2 log2(nb) launches of recursive doubling for L^-1 and one k_lauum, all on DFMA
 // register tiles: 0.5 ms of launch-separated latency chain at N = 1000.  Here every 64 x 64 tile of the
 // result is a TASK owned by one CTA; tasks hand tiles over through release/acquire flags in global memory,
-// operands are staged by TMA (64 x 16 boxes, 128-byte swizzle, 4-stage full/empty mbarrier ring) and
-// multiplied on the FP64 tensor pipe (DMMA.8x8x4), so a tile GEMM starts the moment its inputs exist:
+// operands are staged by a producer warp with cp.async (64 x 16 boxes in the 128-byte-swizzle layout of the
+// scoring kernels, 4-stage full/empty mbarrier ring) and multiplied on the FP64 tensor pipe (DMMA.8x8x4),
+// so a tile GEMM starts the moment its inputs exist.  (The first version staged the boxes with TMA.  Tiles
+// written a moment earlier by OTHER CTAs' generic-proxy stores were then occasionally read stale by the
+// async proxy - wrong tiles in 3 of 3 runs at np = 2048, still 1 of 8 with release/acquire flags plus
+// fence.proxy.async in every writing thread and in the reader - so cross-CTA hand-over stays in the generic
+// proxy: cp.async.cg reads L2 like any other load ordered by the acquire.)
 //
 //   chain CTA (ticket 0), for j = 0 .. nb-1            the only sequential part (nb = np / 64)
 //       L[j,j-1] = (A[j,j-1] - S(j,0)) * Linv_{j-1}^T   (Linv_{j-1} is still in shared memory)
@@ -63,10 +68,7 @@ constexpr int kChainLD = 66;                   // potf2_inv_64's row stride
 enum { DF_PART = 0, DF_TILE = 1, DF_LINV = 2, DF_KINV = 3 };
 
 struct DfArgs {
-  alignas(64) CUtensorMap mapL;   // [np x np] row-major, boxes 64 x 16, SWIZZLE_128B
-  alignas(64) CUtensorMap mapX;   // L^-1
-  alignas(64) CUtensorMap mapY;   // L^-T
-  double* L;
+  double* L;        // [np x np] row-major: the shifted matrix on entry (lower tiles), the factor on exit
   double* X;
   double* Y;
   double* S;        // [nb][2][64*64] partial sums for the chain
@@ -141,6 +143,24 @@ __device__ __forceinline__ void df_slab(DfFrag& acc, const double* Abox, const d
       dmma_8x8x4(acc.v[1][g][0], acc.v[1][g][1], a1.y, b[g].y);
     }
   }
+}
+
+// Producer warp: one 64 x 16 box (rows row0.., columns col0..col0+15 of a row-major [np x np] matrix) into
+// the swizzled box layout: 16-byte chunk c of row r at chunk c ^ (r & 7).  512 chunks, 16 per lane.
+__device__ __forceinline__ void df_copy_box(double* box, const double* __restrict__ G, int np, int row0, int col0, int lane) {
+  const int c = lane & 7, r0 = lane >> 3;
+  const double* src = G + (size_t)(row0 + r0) * np + col0 + c * 2;
+  const unsigned dst0 = smem_u32(box);
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const int r = r0 + 4 * t;
+    const unsigned dst = dst0 + (unsigned)(r * 16 + ((c ^ (r & 7)) * 2)) * 8u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + (size_t)4 * t * np) : "memory");
+  }
+}
+// All of this lane's cp.async so far -> one arrival on `bar` when they have landed.
+__device__ __forceinline__ void df_copy_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // C = As * Bs^T over k = 0..63, both operands in padded shared memory [64][kChainLD] (chain CTA).
@@ -231,7 +251,7 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
         }
       __threadfence();
       __syncthreads();
-      if (tid == 0) { fence_proxy_async(); st_release_gpu(a.flagL + j * nb + (j - 1), 1); }   // early release
+      if (tid == 0) st_release_gpu(a.flagL + j * nb + (j - 1), 1);   // early release
       VZ_DFT(j, 2);
       // ---- D = A[j,j] - S(j,1) - L[j,j-1] L[j,j-1]^T ----
       acc.zero();
@@ -271,7 +291,7 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
     if (tid == 0 && s_bad) *a.bad = 1;
     __threadfence();
     __syncthreads();
-    if (tid == 0) { fence_proxy_async(); st_release_gpu(a.flagL + j * nb + j, 1); }
+    if (tid == 0) st_release_gpu(a.flagL + j * nb + j, 1);
     VZ_DFT(j, 5);
   }
 }
@@ -302,13 +322,12 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
   double* Tbuf = sm + kRingD;
   const DfPlan p = df_plan(type, ti, tj, nb);
   if (warp == kDfMath / 32) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      unsigned slab = 0;
-      const CUtensorMap* mA = (type == DF_LINV || type == DF_KINV) ? &a.mapY : &a.mapL;
-      const CUtensorMap* mB = (type == DF_KINV) ? &a.mapY : &a.mapL;
-      for (int k = p.k0; k < p.k1; ++k) {
-        // inputs of this k tile
+    // ---------------- producer warp (cp.async) ----------------
+    unsigned slab = 0;
+    const double* GA = (type == DF_LINV || type == DF_KINV) ? a.Y : a.L;
+    const double* GB = (type == DF_KINV) ? a.Y : a.L;
+    for (int k = p.k0; k < p.k1; ++k) {
+      if (lane == 0) {       // inputs of this k tile
         if (type == DF_TILE || type == DF_PART) {
           df_wait(a.flagL + p.rowA * nb + k, a.ctrl);
           df_wait(a.flagL + p.rowB * nb + k, a.ctrl);
@@ -319,28 +338,29 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
           df_wait(k == ti ? a.flagL + ti * nb + ti : a.flagY + ti * nb + k, a.ctrl);
           df_wait(k == tj ? a.flagL + tj * nb + tj : a.flagY + tj * nb + k, a.ctrl);
         }
-        fence_proxy_async();   // the tiles were written through the generic proxy by other CTAs
-        for (int ks = 0; ks < 4; ++ks, ++slab) {
-          const int stage = slab % kDfStages;
-          mbar_wait(empty_bar + stage, ((slab / kDfStages) & 1) ^ 1);
-          double* base = ring + stage * kStageD;
-          mbar_expect_tx(full_bar + stage, 2 * kBoxD * sizeof(double));
-          tma_load_2d(base, mA, k * 64 + ks * 16, p.rowA * 64, full_bar + stage);
-          tma_load_2d(base + kBoxD, mB, k * 64 + ks * 16, p.rowB * 64, full_bar + stage);
-        }
       }
-      if (p.finalB >= 0) {
-        df_wait(a.flagL + p.finalB * nb + p.finalB, a.ctrl);
-        fence_proxy_async();
-        for (int ks = 0; ks < 4; ++ks, ++slab) {
-          const int stage = slab % kDfStages;
-          mbar_wait(empty_bar + stage, ((slab / kDfStages) & 1) ^ 1);
-          double* base = ring + stage * kStageD;
-          mbar_expect_tx(full_bar + stage, kBoxD * sizeof(double));
-          tma_load_2d(base + kBoxD, &a.mapX, p.finalB * 64 + ks * 16, p.finalB * 64, full_bar + stage);
-        }
+      __syncwarp();          // lane 0's acquire, then the whole warp's loads
+      for (int ks = 0; ks < 4; ++ks, ++slab) {
+        const int stage = slab % kDfStages;
+        mbar_wait(empty_bar + stage, ((slab / kDfStages) & 1) ^ 1);
+        double* base = ring + stage * kStageD;
+        df_copy_box(base, GA, np, p.rowA * 64, k * 64 + ks * 16, lane);
+        df_copy_box(base + kBoxD, GB, np, p.rowB * 64, k * 64 + ks * 16, lane);
+        df_copy_arrive(full_bar + stage);
       }
     }
+    if (p.finalB >= 0) {
+      if (lane == 0) df_wait(a.flagL + p.finalB * nb + p.finalB, a.ctrl);
+      __syncwarp();
+      for (int ks = 0; ks < 4; ++ks, ++slab) {
+        const int stage = slab % kDfStages;
+        mbar_wait(empty_bar + stage, ((slab / kDfStages) & 1) ^ 1);
+        double* base = ring + stage * kStageD;
+        df_copy_box(base + kBoxD, a.X, np, p.finalB * 64, p.finalB * 64 + ks * 16, lane);
+        df_copy_arrive(full_bar + stage);
+      }
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");   // nothing in flight when this warp retires
     return;
   }
   // ---------------- math warps ----------------
@@ -420,11 +440,11 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
   if (flag != nullptr) {
     __threadfence();
     math_sync();
-    if (tid == 0) { fence_proxy_async(); st_release_gpu(flag, 1); }
+    if (tid == 0) st_release_gpu(flag, 1);
   }
 }
 
-__global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const __grid_constant__ DfArgs a) {
+__global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const DfArgs a) {
   extern __shared__ double smem_raw[];
   double* sm = smem_raw + (((1024u - (static_cast<unsigned>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u) >> 3);
   __shared__ int s_ticket;
@@ -432,7 +452,7 @@ __global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const __grid_co
   const int tid = threadIdx.x;
   if (tid == 0) {
     s_ticket = atomicAdd(a.ctrl, 1);
-    for (int s = 0; s < kDfStages; ++s) { mbar_init(bars + s, 1); mbar_init(bars + kDfStages + s, kDfMath / 32); }
+    for (int s = 0; s < kDfStages; ++s) { mbar_init(bars + s, 32); mbar_init(bars + kDfStages + s, kDfMath / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -511,9 +531,6 @@ int chol_dataflow(vzgp_handle* h, double* L, double* Linv, double* LinvT, double
   }
   const size_t nflags = 8 + 2 * (size_t)nb * nb + 2 * (size_t)nb;
   DfArgs a;
-  VZ_TRY(make_tensor_map_f64(&a.mapL, L, (uint64_t)np, (uint64_t)np, (uint64_t)np, 64));
-  VZ_TRY(make_tensor_map_f64(&a.mapX, Linv, (uint64_t)np, (uint64_t)np, (uint64_t)np, 64));
-  VZ_TRY(make_tensor_map_f64(&a.mapY, LinvT, (uint64_t)np, (uint64_t)np, (uint64_t)np, 64));
   a.L = L; a.X = Linv; a.Y = LinvT; a.S = h->df_S.as<double>(); a.Kinv = Kinv;
   int* f = h->df_flags.as<int>();
   a.ctrl = f; a.flagL = f + 8; a.flagY = a.flagL + nb * nb; a.flagS = a.flagY + nb * nb;
@@ -536,3 +553,10 @@ int chol_dataflow_timed_out(vzgp_handle* h, int* out) {
 }
 
 }  // namespace vzgp
+
+#ifdef VZ_DF_TIMING
+// Debug builds only (make EXTRA=-DVZ_DF_TIMING): clock64 stamps of the chain CTA, [step][phase].
+extern "C" int vzgp_debug_df_timing(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, vzgp::g_df_t, sizeof(long long) * (n < 512 ? n : 512)) == cudaSuccess ? 0 : -2;
+}
+#endif

@@ -1,5 +1,8 @@
 // Internal prototypes of the per-file launch helpers (all return 0 or a negative vzgp status).
 #pragma once
+#include <tuple>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vzgp {
@@ -13,12 +16,25 @@ int launch_cross_kernel(vzgp_handle* h, const double* Xs, const int32_t* Zs, int
 int potrf_blocked(vzgp_handle* h, double* L, int ld, double* Linv, int ldi, int np, int* flag);
 int trtri_doubling(vzgp_handle* h, const double* L, int ld, double* Linv, int ldi, double* T, int ldt,
                    int np);
+// The captured NLL graph (c_abi.cu, nll_graph_eval) re-parameterises three kernel nodes per evaluation by
+// ARGUMENT POSITION.  The positions live here, next to the prototypes, and each kernel's translation unit
+// static_asserts them against its real signature (KernelArgs), so a signature change cannot silently write
+// the hyper-parameters into the wrong slot.
+constexpr int kKernelMatrixArgs = 8, kKernelMatrixKpArg = 4, kKernelMatrixDiagArg = 5;
+constexpr int kTransposeScaleArgs = 5, kTransposeScaleKpArg = 3;
+constexpr int kNllGradTilesArgs = 13, kNllGradTilesKpArg = 4;
+template <class F> struct KernelArgs;
+template <class... A> struct KernelArgs<void (*)(A...)> {
+  static constexpr int count = (int)sizeof...(A);
+  template <int I> using arg = typename std::tuple_element<I, std::tuple<A...>>::type;
+};
 // Host-side entry addresses of the three kernels whose arguments carry the hyper-parameters (graph node lookup).
 const void* kernel_matrix_func();
 const void* transpose_scale_func();
 const void* nll_grad_tiles_func();
 constexpr int kLauumSplit = 4;   // K_y^-1 is produced as this many partial planes [z][np][ldk] (linalg.cu)
 int lauum_plane_rows(int np);
+int launch_sum_planes(vzgp_handle* h, double* Kinv, int np, int kc);
 int launch_lauum(vzgp_handle* h, const double* Linv, int ldi, double* Kinv, int ldk, int np);
 int launch_copy_lower_shift(vzgp_handle* h, const double* A, int lda, int n_src, int np, double shift,
                             double* L, int ldl);
@@ -33,7 +49,8 @@ int launch_pad_vector(vzgp_handle* h, const double* src, int n, int n_valid, int
 int launch_pad_rows(vzgp_handle* h, const double* src, int n, int d, int np, double* dst);
 int launch_transpose_scale(vzgp_handle* h, const double* X, int np, int dc, const KernelParams& kp, double* XT);
 int launch_pad_rows_i32(vzgp_handle* h, const int32_t* src, int n, int d, int np, int32_t* dst);
-int launch_logdet_quad(vzgp_handle* h, const double* L, int ld, int n_valid, const double* w, double* out);
+int launch_logdet_quad(vzgp_handle* h, const double* L, int ld, int n_valid, const double* w, double* out,
+                       int wstride = 0, int n_metrics = 1);
 
 int launch_gemm_nt_tri(vzgp_handle* h, const double* A, int lda, int mp, const double* B, int ldb, int np,
                        double* C, int ldc);
@@ -42,7 +59,7 @@ int launch_cov_update(vzgp_handle* h, const double* W, int ldw, int kdim, int mp
 
 int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
                           const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,
-                          double* partial, double* out, int plane_rows = 0);
+                          double* partial, double* out, int plane_rows = 0, int n_metrics = 1);
 
 // CUtensorMap (passed as void*) of an fp64 row-major matrix [rows x cols], row pitch ld elements, boxes of
 // box_rows x 16 doubles with the 128-byte swizzle (score.cu).
@@ -59,6 +76,9 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
                  double* score, double* mu, double* sigma, double* linf);
 int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
                     const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
+int prepare_scalarization(vzgp_handle* h, const vzgp_scalarization* sc);
+int launch_score_multi(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, double* score, double* mu_out,
+                       double* sigma_out);
 int launch_random_fill(vzgp_handle* h, double* X, int64_t total, int64_t elem_base, uint64_t seed,
                        uint32_t stream, uint32_t iteration);
 struct ArgMax {

@@ -430,18 +430,19 @@ __global__ void k_pad_rows_i32(const int32_t* __restrict__ src, int n, int d, in
   dst[e] = e < (size_t)n * d ? src[e] : -1;
 }
 
-// sum_i log L_ii over i < n_valid and  0.5 * sum w_i^2  ->  out[0], out[1]   (single block)
+// n_metrics * sum_i log L_ii over i < n_valid and  0.5 * sum_m sum_i w_m[i]^2  ->  out[0], out[1]
+// (single block; w_m = w + m * wstride: the independent multi-task GP shares one factor).
 __global__ void k_logdet_quad(const double* __restrict__ L, int ld, int n_valid,
-                              const double* __restrict__ w, double* __restrict__ out) {
+                              const double* __restrict__ w, int wstride, int n_metrics, double* __restrict__ out) {
   __shared__ double red[32];
   double a = 0.0, b = 0.0;
   for (int i = threadIdx.x; i < n_valid; i += blockDim.x) {
     a += log(L[(size_t)i * ld + i]);
-    b = fma(w[i], w[i], b);
+    for (int m = 0; m < n_metrics; ++m) { const double v = w[(size_t)m * wstride + i]; b = fma(v, v, b); }
   }
   a = block_sum(a, red);
   b = block_sum(b, red);
-  if (threadIdx.x == 0) { out[0] = a; out[1] = 0.5 * b; }
+  if (threadIdx.x == 0) { out[0] = n_metrics * a; out[1] = 0.5 * b; }
 }
 
 // ---------------------------------------------------------------------------
@@ -470,6 +471,14 @@ int fill_kernel_params(const vzgp_params* p, int dc, int dk, KernelParams* kp) {
   return 0;
 }
 
+// The captured NLL graph re-parameterises these kernels by argument position (c_abi.cu): pin the positions.
+static_assert(KernelArgs<decltype(&k_kernel_matrix)>::count == kKernelMatrixArgs &&
+              std::is_same<KernelArgs<decltype(&k_kernel_matrix)>::arg<kKernelMatrixKpArg>, KernelParams>::value &&
+              std::is_same<KernelArgs<decltype(&k_kernel_matrix)>::arg<kKernelMatrixDiagArg>, double>::value,
+              "k_kernel_matrix signature changed: update kKernelMatrix*Arg in launchers.h");
+static_assert(KernelArgs<decltype(&k_transpose_scale)>::count == kTransposeScaleArgs &&
+              std::is_same<KernelArgs<decltype(&k_transpose_scale)>::arg<kTransposeScaleKpArg>, KernelParams>::value,
+              "k_transpose_scale signature changed: update kTransposeScale*Arg in launchers.h");
 const void* kernel_matrix_func() { return reinterpret_cast<const void*>(&k_kernel_matrix); }
 const void* transpose_scale_func() { return reinterpret_cast<const void*>(&k_transpose_scale); }
 
@@ -543,6 +552,22 @@ int lauum_plane_rows(int np) { return ((np / 64 + kLauumSplit - 1) / kLauumSplit
 int launch_lauum(vzgp_handle* h, const double* Linv, int ldi, double* Kinv, int ldk, int np) {
   const int nb = np / 64;
   k_lauum<<<dim3(nb, nb, kLauumSplit), 256, G64::kSmemBytes, h->stream>>>(Linv, ldi, Kinv, ldk, np, lauum_plane_rows(np));
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+
+// plane 0 (lower tiles) += planes 1..kLauumSplit-1 that meet the tile's k range (see k_lauum)
+__global__ void k_sum_planes(double* __restrict__ Kinv, int np, int kc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j > i || j >= np) return;
+  const int bi = i / 64;
+  double s = 0.0;
+  for (int z = (bi * 64) / kc; z < kLauumSplit && z * kc < np; ++z) s += Kinv[((size_t)z * np + i) * np + j];
+  Kinv[(size_t)i * np + j] = s;
+}
+int launch_sum_planes(vzgp_handle* h, double* Kinv, int np, int kc) {
+  k_sum_planes<<<dim3((np + 255) / 256, np), 256, 0, h->stream>>>(Kinv, np, kc);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;
@@ -643,8 +668,8 @@ int launch_pad_rows_i32(vzgp_handle* h, const int32_t* src, int n, int d, int np
   return 0;
 }
 int launch_logdet_quad(vzgp_handle* h, const double* L, int ld, int n_valid, const double* w,
-                       double* out) {
-  k_logdet_quad<<<1, 256, 0, h->stream>>>(L, ld, n_valid, w, out);
+                       double* out, int wstride, int n_metrics) {
+  k_logdet_quad<<<1, 256, 0, h->stream>>>(L, ld, n_valid, w, wstride, n_metrics, out);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;

@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict
                                                         int n_valid, KernelParams kp,
                                                         const double* __restrict__ Kinv, int ldk, int kc,
                                                         const double* __restrict__ alpha,
-                                                        double* __restrict__ partial, int nb) {
+                                                        double* __restrict__ partial, int nb, int n_metrics,
+                                                        int astride) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj > bi) return;
   extern __shared__ double smem[];
@@ -54,7 +55,9 @@ __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict
         double kinv = 0.0;   // planes of k_lauum that meet k >= 64*bi, ascending
         for (int z = (bi * 64) / kc; z < kLauumSplit && z * kc < np; ++z)
           kinv += Kinv[((size_t)z * np + gi) * ldk + gj];
-        g = wgt * (kinv - alpha[gi] * alpha[gj]);
+        double aa = 0.0;   // independent multi-task GP: G = M K_y^-1 - sum_m alpha_m alpha_m^T
+        for (int m = 0; m < n_metrics; ++m) aa = fma(alpha[(size_t)m * astride + gi], alpha[(size_t)m * astride + gj], aa);
+        g = wgt * (n_metrics * kinv - aa);
         matern52_with_grad(d2[i][j], kp.sf2, kv, ev);
         if (gi == gj) sum_tr += g;
       }
@@ -113,16 +116,19 @@ __global__ void k_reduce_partials(const double* __restrict__ partial, int ntiles
   if (threadIdx.x == 0) out[q] = s;
 }
 
+static_assert(KernelArgs<decltype(&k_nll_grad_tiles)>::count == kNllGradTilesArgs &&
+              std::is_same<KernelArgs<decltype(&k_nll_grad_tiles)>::arg<kNllGradTilesKpArg>, KernelParams>::value,
+              "k_nll_grad_tiles signature changed: update kNllGradTiles*Arg in launchers.h");
 const void* nll_grad_tiles_func() { return reinterpret_cast<const void*>(&k_nll_grad_tiles); }
 
 int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
                           const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,
-                          double* partial, double* out, int plane_rows) {
+                          double* partial, double* out, int plane_rows, int n_metrics) {
   const int nb = np / 64, nq = kp.dc + kp.dk + 2, ntiles = nb * (nb + 1) / 2;
   size_t sm = sizeof(double) * (kp.dc * 2 * 66 + 8 * nq) + sizeof(int32_t) * kp.dk * 2 * 66;
   VZ_CUDA(cudaFuncSetAttribute(k_nll_grad_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   k_nll_grad_tiles<<<dim3(nb, nb), 256, sm, h->stream>>>(X, Z, np, n_valid, kp, Kinv, ldk, plane_rows > 0 ? plane_rows : lauum_plane_rows(np), alpha,
-                                                         partial, nb);
+                                                         partial, nb, n_metrics, np);
   VZ_CHECK_LAUNCH();
   k_reduce_partials<<<nq, 256, 0, h->stream>>>(partial, ntiles, nq, out);
   VZ_CHECK_LAUNCH();

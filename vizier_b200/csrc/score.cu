@@ -400,7 +400,8 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // fp64 matrix [rows x cols] with row pitch ld (elements); box = box_rows x 16 doubles, 128-byte swizzle.
-static int make_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+static int make_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    bool l2_promotion = true) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return VZGP_ERR_CUDA; }
   cuuint64_t gdim[2] = {cols, rows};
@@ -408,14 +409,17 @@ static int make_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t 
   cuuint32_t box[2] = {16, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  l2_promotion ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return VZGP_ERR_CUDA; }
   return 0;
 }
 
 int make_tensor_map_f64(void* map, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  return make_map(static_cast<CUtensorMap*>(map), base, rows, cols, ld, box_rows);
+  // no L2 promotion: the dataflow kernel loads tiles whose NEIGHBOURS are still being written by other CTAs
+  static const bool promo = [] { const char* e = getenv("VZGP_DF_L2PROMO"); return e && e[0] == '1'; }();
+  return make_map(static_cast<CUtensorMap*>(map), base, rows, cols, ld, box_rows, promo);
 }
 
 size_t score_smem_bytes(int dc, int dk, bool with_linf) {

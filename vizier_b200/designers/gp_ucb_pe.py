@@ -102,7 +102,7 @@ def _has_new_completed_trials(completed: Sequence[Any], active: Sequence[Any]) -
   return max(done) > max(made)
 
 
-class VizierGPUCBPEBandit:
+class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
   """GP-UCB-PE designer; see module docstring."""
 
   def __init__(self, problem, *, acquisition_optimizer_factory: vb.VectorizedOptimizerFactory = default_acquisition_optimizer_factory,

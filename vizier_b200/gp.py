@@ -139,6 +139,29 @@ class UcbPeAcquisition:
     return p, keep
 
 
+@dataclasses.dataclass
+class ScalarizedUcbAcquisition:
+  """Hyper-volume scalarised UCB for multi-metric problems (gp_bandit.py:214-242); see vzgp_scalarization
+  in include/vzgp.h.  weights [S, M] positive with unit-norm rows, reference_point [M], max_scalarized [S]."""
+
+  weights: np.ndarray
+  reference_point: np.ndarray
+  max_scalarized: Optional[np.ndarray] = None
+  ucb_coefficient: float = 1.8
+
+  def _c(self):
+    w = np.ascontiguousarray(np.asarray(self.weights, np.float64))
+    r = np.ascontiguousarray(np.asarray(self.reference_point, np.float64).reshape(-1))
+    b = None if self.max_scalarized is None else np.ascontiguousarray(np.asarray(self.max_scalarized, np.float64).reshape(-1))
+    s = _lib.Scalarization()
+    s.n_scalarizations, s.n_metrics = w.shape
+    s.weights = w.ctypes.data_as(C.POINTER(C.c_double))
+    s.reference_point = r.ctypes.data_as(C.POINTER(C.c_double))
+    s.max_scalarized = b.ctypes.data_as(C.POINTER(C.c_double)) if b is not None else None
+    s.ucb_coefficient = float(self.ucb_coefficient)
+    return s, (w, r, b)
+
+
 def _ptr(t: Optional[torch.Tensor]):
   return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -159,6 +182,7 @@ class DeviceGP:
     _lib.check('vzgp_create', self._lib.vzgp_create(device, C.c_void_p(self._stream.cuda_stream), C.byref(h)))
     self._h = h
     self.dc = self.dk = self.n = 0
+    self.n_metrics = 1
     self.cholesky_failed = False
 
   def close(self):
@@ -240,6 +264,16 @@ class DeviceGP:
         self._h, _ptr(at), n, n, float(jitter), int(max_iters), _ptr(out), n, C.byref(shift)))
     return out, float(shift.value), retries
 
+  def factor_inverse(self, a, with_kinv: bool = True):
+    """L = chol(a), L^-1 and (optionally) the lower triangle of a^-1 (vzgp_factor_inverse); device tensors."""
+    at = self._dev(a, torch.float64)
+    n = at.shape[0]
+    outs = [torch.zeros((n, n), dtype=torch.float64, device=self.device) for _ in range(3 if with_kinv else 2)]
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    bad = _lib.check('vzgp_factor_inverse', self._lib.vzgp_factor_inverse(
+        self._h, _ptr(at), n, n, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]) if with_kinv else None, n))
+    return outs, bad
+
   def tri_inverse(self, l) -> torch.Tensor:
     lt = self._dev(l, torch.float64)
     n = lt.shape[0]
@@ -250,14 +284,27 @@ class DeviceGP:
     return out
 
   # -- model ---------------------------------------------------------------
+  def _labels(self, y, n: int):
+    """Labels as a metric-major device tensor [M, N] (the layout of vzgp_fit_multi); y is [N] or [N, M]."""
+    if isinstance(y, torch.Tensor):
+      y2 = y.reshape(n, -1)
+      yt = y2.t().contiguous().to(device=self.device, dtype=torch.float64)
+    else:
+      y2 = np.asarray(y, np.float64).reshape(n, -1)
+      yt = torch.from_numpy(np.ascontiguousarray(y2.T)).to(self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    return yt, y2.shape[1]
+
   def fit(self, x, y, params: GPHyperParams, z=None, n_valid=None) -> int:
+    """y [N] or, for a multi-metric study, [N, M] (independent multi-task GP: one factor, M alphas)."""
     xt, zt = self._xz(x, z)
-    yt = self._dev(np.asarray(y).reshape(-1) if not isinstance(y, torch.Tensor) else y.reshape(-1), torch.float64)
     n, dc = xt.shape
+    yt, n_metrics = self._labels(y, n)
     dk = 0 if zt is None else zt.shape[1]
     p = params._c()
-    retries = _lib.check('vzgp_fit', self._lib.vzgp_fit(
-        self._h, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, n if n_valid is None else n_valid, C.byref(p)))
+    retries = _lib.check('vzgp_fit_multi', self._lib.vzgp_fit_multi(
+        self._h, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, n if n_valid is None else n_valid, n_metrics, C.byref(p)))
+    self.n_metrics = n_metrics
     self.synchronize()  # inputs may be freed by the caller after return
     self.n, self.dc, self.dk = n, dc, dk
     # retrying_cholesky(max_iters=5) exhausted (tuned_gp_models.py:272-280): the factor holds NaN exactly
@@ -286,14 +333,14 @@ class DeviceGP:
   def loss_and_grad(self, x, y, params: GPHyperParams, z=None, n_valid=None):
     """x, y (and z) should be device tensors kept alive by the caller across ARD iterations."""
     xt, zt = self._xz(x, z)
-    yt = self._dev(y, torch.float64).reshape(-1)
     n, dc = xt.shape
+    yt, n_metrics = self._labels(y, n)
     dk = 0 if zt is None else zt.shape[1]
     p = params._c()
     loss = C.c_double(0.0)
     grad = np.zeros(dc + dk + 2, np.float64)
-    retries = _lib.check('vzgp_nll_grad', self._lib.vzgp_nll_grad(
-        self._h, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, n if n_valid is None else n_valid,
+    retries = _lib.check('vzgp_nll_grad_multi', self._lib.vzgp_nll_grad_multi(
+        self._h, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, n if n_valid is None else n_valid, n_metrics,
         C.byref(p), C.byref(loss), grad.ctypes.data_as(C.POINTER(C.c_double))))
     return float(loss.value), grad, retries
 
@@ -303,8 +350,8 @@ class DeviceGP:
     microseconds of host time) instead of a dozen torch calls.  theta is in `GPHyperParams.to_vector`
     order (categorical ls2, continuous ls2, noise, signal).  Non-finite losses return (1e300, 0)."""
     xt, zt = self._xz(x, z)
-    yt = self._dev(y, torch.float64).reshape(-1)
     n, dc = xt.shape
+    yt, n_metrics = self._labels(y, n)
     dk = 0 if zt is None else zt.shape[1]
     nv = n if n_valid is None else n_valid
     ls_k = np.zeros(max(dk, 1), np.float64)
@@ -314,7 +361,7 @@ class DeviceGP:
     p = _lib.Params()
     p.continuous_length_scale_squared = ls_c.ctypes.data_as(C.POINTER(C.c_double))
     p.categorical_length_scale_squared = ls_k.ctypes.data_as(C.POINTER(C.c_double)) if dk else None
-    fn, h = self._lib.vzgp_nll_grad, self._h
+    fn, h = self._lib.vzgp_nll_grad_multi, self._h
     px, pz, py = _ptr(xt), _ptr(zt), _ptr(yt)
     pp, pl, pg = C.byref(p), C.byref(loss), grad.ctypes.data_as(C.POINTER(C.c_double))
     keep = (xt, zt, yt, ls_k, ls_c, grad, loss, p)   # referenced by the closure: stays alive with it
@@ -325,7 +372,7 @@ class DeviceGP:
       ls_c[:dc] = theta[dk:dk + dc]
       p.observation_noise_variance = float(theta[dk + dc])
       p.signal_variance = float(theta[dk + dc + 1])
-      _lib.check('vzgp_nll_grad', fn(h, px, pz, py, n, dc, dk, nv, pp, pl, pg))
+      _lib.check('vzgp_nll_grad_multi', fn(h, px, pz, py, n, dc, dk, nv, n_metrics, pp, pl, pg))
       v = loss.value
       if not np.isfinite(v):
         return 1e300, np.zeros_like(theta)
@@ -349,6 +396,21 @@ class DeviceGP:
         self._h, _ptr(xst), _ptr(zst), m, C.byref(a), _ptr(res['score']), _ptr(res.get('mean')),
         _ptr(res.get('stddev')), _ptr(res.get('linf_distance'))))
     res['_inputs'] = (xst, zst, keep)  # keep alive until the caller synchronises
+    return res
+
+  def score_multi(self, xs, acq: ScalarizedUcbAcquisition, zs=None, with_aux: bool = False) -> dict:
+    """Multi-metric scalarised UCB; returns device tensors {'score' [M], ['mean' [n_metrics, M], 'stddev' [M]]}."""
+    xst, zst = self._xz(xs, zs)
+    m = xst.shape[0]
+    res = {'score': torch.empty((m,), dtype=torch.float64, device=self.device)}
+    if with_aux:
+      res['mean'] = torch.empty((self.n_metrics, m), dtype=torch.float64, device=self.device)
+      res['stddev'] = torch.empty((m,), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    sc, keep = acq._c()
+    _lib.check('vzgp_score_multi', self._lib.vzgp_score_multi(
+        self._h, _ptr(xst), _ptr(zst), m, C.byref(sc), _ptr(res['score']), _ptr(res.get('mean')), _ptr(res.get('stddev'))))
+    res['_inputs'] = (xst, zst, keep)
     return res
 
   def clamped_count(self) -> int:
@@ -377,13 +439,13 @@ class DeviceGP:
     """Joint posterior mean [M] and covariance [M, M] (device tensors)."""
     xst, zst = self._xz(xs, zs)
     m = xst.shape[0]
-    mean = torch.empty((m,), dtype=torch.float64, device=self.device)
+    mean = torch.empty((self.n_metrics, m), dtype=torch.float64, device=self.device)
     cov = torch.empty((m, m), dtype=torch.float64, device=self.device)
     self._stream.wait_stream(torch.cuda.current_stream(self.device))
-    _lib.check('vzgp_posterior', self._lib.vzgp_posterior(
+    _lib.check('vzgp_posterior_multi', self._lib.vzgp_posterior_multi(
         self._h, _ptr(xst), _ptr(zst), m, 1 if add_noise else 0, _ptr(mean), _ptr(cov), m))
     self.synchronize()
-    return mean, cov
+    return (mean[0] if self.n_metrics == 1 else mean), cov
 
   def topk(self, score: torch.Tensor, count: int):
     idx = np.zeros(count, np.int64)
@@ -506,6 +568,7 @@ class DeviceGP:
     UcbPeAcquisition the GP-UCB-PE acquisition is optimised (vzgp_eagle_run_pe)."""
     if isinstance(acq, UcbPeAcquisition):
       return self._eagle_run_pe(cfg, acq, count, seed, prior, prior_z, cat_sizes, other)
+    multi = isinstance(acq, ScalarizedUcbAcquisition)
     a, keep = acq._c()
     n_prior = 0 if prior is None else len(prior)
     pt = self._dev(prior, torch.float64) if n_prior > 0 and self.dc > 0 else None
@@ -514,7 +577,8 @@ class DeviceGP:
     bz = np.zeros((count, self.dk), np.int32)
     bs = np.zeros(count, np.float64)
     sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
-    _lib.check('vzgp_eagle_run', self._lib.vzgp_eagle_run(
+    fn_name = 'vzgp_eagle_run_multi' if multi else 'vzgp_eagle_run'
+    _lib.check(fn_name, getattr(self._lib, fn_name)(
         self._h, C.byref(cfg), C.byref(a), _ptr(pt), _ptr(pz), n_prior,
         sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes.size else None, count, seed,
         bx.ctypes.data_as(C.POINTER(C.c_double)), bz.ctypes.data_as(C.POINTER(C.c_int32)),

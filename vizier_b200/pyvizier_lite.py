@@ -13,6 +13,7 @@ from __future__ import annotations
 import copy
 import dataclasses
 import datetime
+import abc
 import enum
 import math
 from typing import Any, Dict, Iterable, Iterator, List, Mapping, MutableMapping, Optional, Sequence, Tuple, Union
@@ -415,3 +416,33 @@ class Prediction:
   def __post_init__(self):
     if getattr(self.mean, 'shape', None) != getattr(self.stddev, 'shape', None):
       raise ValueError('mean and stddev must have the same shape')
+
+
+class Designer(abc.ABC):
+  """vizier/_src/algorithms/core/abstractions.py:74-149 (`_SuggestionAlgorithm` + `Designer`): the
+  suggest/update contract `DesignerPolicy` drives."""
+
+  @abc.abstractmethod
+  def suggest(self, count: Optional[int] = None) -> Sequence[TrialSuggestion]:
+    """Makes `count` suggestions (None: as many as the algorithm wants)."""
+
+  @abc.abstractmethod
+  def update(self, completed: CompletedTrials, all_active: ActiveTrials) -> None:
+    """Incorporates newly COMPLETED trials and the full list of ACTIVE trials."""
+
+
+class Predictor(abc.ABC):
+  """vizier/_src/algorithms/core/abstractions.py:174-199."""
+
+  @abc.abstractmethod
+  def predict(self, trials: Sequence[TrialSuggestion], rng: Any = None, num_samples: Optional[int] = None) -> Prediction:
+    """Mean and stddev at the given suggestions."""
+
+
+class TrialStatus(enum.Enum):
+  """vizier/_src/pyvizier/shared/trial.py: the statuses DesignerPolicy filters by."""
+  UNKNOWN = 'UNKNOWN'
+  REQUESTED = 'REQUESTED'
+  ACTIVE = 'ACTIVE'
+  COMPLETED = 'COMPLETED'
+  STOPPING = 'STOPPING'

@@ -9,8 +9,10 @@ try:
   CompletedTrials = _vza.CompletedTrials
   ActiveTrials = _vza.ActiveTrials
   Prediction = _vza.Prediction
+  Designer = _vza.Designer
+  Predictor = _vza.Predictor
   USING_REAL_VIZIER = True
 except Exception:  # pylint: disable=broad-except
   from vizier_b200.pyvizier_lite import *  # noqa: F401,F403
-  from vizier_b200.pyvizier_lite import ActiveTrials, CompletedTrials, Prediction  # noqa: F401
+  from vizier_b200.pyvizier_lite import ActiveTrials, CompletedTrials, Designer, Prediction, Predictor  # noqa: F401
   USING_REAL_VIZIER = False
