@@ -185,6 +185,30 @@ __device__ __forceinline__ void df_gemm_padded(DfFrag& acc, const double* As, co
   }
 }
 
+// The same with Bs lower triangular (Bs[n][k] = 0 for k > n): the 8-wide k group q only reaches the column
+// fragments whose last column is >= 8q, i.e. fragment g of warp column wn needs q <= 4 wn + g.  Both warps
+// of a scheduler partition (same wm, wn = 0 / 1) together issue 36 of the 64 group-fragments.
+__device__ __forceinline__ void df_gemm_padded_tri(DfFrag& acc, const double* As, const double* Bs, int wm, int wn, int fr, int fk) {
+  constexpr int LD = kChainLD;
+  const double* Ar = As + (wm * 16 + fr) * LD + 2 * fk;
+  const double* Br = Bs + (wn * 32 + fr) * LD + 2 * fk;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (q > 4 * wn + 3) break;     // warp-uniform
+    const double2 a0 = *reinterpret_cast<const double2*>(Ar + 8 * q);
+    const double2 a1 = *reinterpret_cast<const double2*>(Ar + 8 * LD + 8 * q);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (q > 4 * wn + g) continue;
+      const double2 b = *reinterpret_cast<const double2*>(Br + g * 8 * LD + 8 * q);
+      dmma_8x8x4(acc.v[0][g][0], acc.v[0][g][1], a0.x, b.x);
+      dmma_8x8x4(acc.v[1][g][0], acc.v[1][g][1], a1.x, b.x);
+      dmma_8x8x4(acc.v[0][g][0], acc.v[0][g][1], a0.y, b.y);
+      dmma_8x8x4(acc.v[1][g][0], acc.v[1][g][1], a1.y, b.y);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Chain CTA: the sequential part (256 threads).
 // ---------------------------------------------------------------------------------------------------
@@ -233,7 +257,7 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
       __syncthreads();
       DfFrag acc;
       acc.zero();
-      df_gemm_padded(acc, A_, X_, wm, wn, fr, fk);
+      df_gemm_padded_tri(acc, A_, X_, wm, wn, fr, fk);      // Linv_{j-1} is lower triangular
 #pragma unroll
       for (int f = 0; f < 2; ++f)
 #pragma unroll
@@ -249,9 +273,8 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
           const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
           *reinterpret_cast<double2*>(X_ + r * LD + c) = make_double2(acc.v[f][g][0], acc.v[f][g][1]);
         }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release_gpu(a.flagL + j * nb + (j - 1), 1);   // early release
+      __syncthreads();            // X_ complete; every thread's global stores ordered before thread 0's fence
+      if (tid == 0) { __threadfence(); st_release_gpu(a.flagL + j * nb + (j - 1), 1); }   // early, cumulative release
       VZ_DFT(j, 2);
       // ---- D = A[j,j] - S(j,1) - L[j,j-1] L[j,j-1]^T ----
       acc.zero();
@@ -289,9 +312,8 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
       *reinterpret_cast<double2*>(Yjj + (size_t)i * np + j2) = make_double2(X_[j2 * LD + i], X_[(j2 + 1) * LD + i]);
     }
     if (tid == 0 && s_bad) *a.bad = 1;
-    __threadfence();
     __syncthreads();
-    if (tid == 0) st_release_gpu(a.flagL + j * nb + j, 1);
+    if (tid == 0) { __threadfence(); st_release_gpu(a.flagL + j * nb + j, 1); }
     VZ_DFT(j, 5);
   }
 }
@@ -314,7 +336,8 @@ __device__ __forceinline__ DfPlan df_plan(int type, int i, int j, int nb) {
   return p;
 }
 
-__device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t* full_bar, uint64_t* empty_bar) {
+__device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t* full_bar, uint64_t* empty_bar,
+                          unsigned& slab) {
   const int type = task.x, ti = task.y, tj = task.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = a.np, nb = a.nb;
@@ -323,7 +346,6 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
   const DfPlan p = df_plan(type, ti, tj, nb);
   if (warp == kDfMath / 32) {
     // ---------------- producer warp (cp.async) ----------------
-    unsigned slab = 0;
     const double* GA = (type == DF_LINV || type == DF_KINV) ? a.Y : a.L;
     const double* GB = (type == DF_KINV) ? a.Y : a.L;
     for (int k = p.k0; k < p.k1; ++k) {
@@ -360,7 +382,6 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
         df_copy_arrive(full_bar + stage);
       }
     }
-    asm volatile("cp.async.wait_all;\n" ::: "memory");   // nothing in flight when this warp retires
     return;
   }
   // ---------------- math warps ----------------
@@ -368,7 +389,6 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
   auto math_sync = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(kDfMath) : "memory"); };
   DfFrag acc;
   acc.zero();
-  unsigned slab = 0;
   for (int k = p.k0; k < p.k1; ++k) {
 #pragma unroll 1
     for (int ks = 0; ks < 4; ++ks, ++slab) {
@@ -437,10 +457,12 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
         xt[(size_t)(c + 1) * np + r] = acc.v[f][g][1];
       }
   }
-  if (flag != nullptr) {
+  // All warps are done with this task's tiles (Tbuf may be rewritten by the next task).  The barrier also
+  // orders every thread's stores before thread 0's fence: the release below is cumulative.
+  math_sync();
+  if (flag != nullptr && tid == 0) {
     __threadfence();
-    math_sync();
-    if (tid == 0) st_release_gpu(flag, 1);
+    st_release_gpu(flag, 1);
   }
 }
 
@@ -456,15 +478,25 @@ __global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const DfArgs a)
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  const int ticket = s_ticket;
+  int ticket = s_ticket;
   if (ticket == 0) {
     if (tid >= kDfMath) return;
     df_chain(a, sm);
     return;
   }
-  if (ticket - 1 >= a.ntasks) return;
-  const int4 task = a.tasks[ticket - 1];
-  df_worker(a, task, sm, bars, bars + kDfStages);
+  // Persistent worker: tasks in ticket order until the list is exhausted.  A CTA holds one task at a time
+  // and takes the next ticket only when it is done, so the lowest unfinished task is always held by a
+  // running CTA whatever the number of resident CTAs (see the header comment).
+  unsigned slab = 0;     // ring position, carried across tasks (same sequence on producer and consumers)
+  while (ticket - 1 < a.ntasks) {
+    const int4 task = a.tasks[ticket - 1];
+    df_worker(a, task, sm, bars, bars + kDfStages, slab);
+    __syncthreads();                                   // everybody has read s_ticket and finished the task
+    if (tid == 0) s_ticket = atomicAdd(a.ctrl, 1);
+    __syncthreads();
+    ticket = s_ticket;
+  }
+  if (tid >= kDfMath) asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -537,7 +569,12 @@ int chol_dataflow(vzgp_handle* h, double* L, double* Linv, double* LinvT, double
   a.tasks = h->df_tasks[want_kinv ? 1 : 0].as<int4>(); a.ntasks = h->df_ntasks[want_kinv ? 1 : 0];
   a.np = np; a.nb = nb; a.bad = flag;
   VZ_CUDA(cudaMemsetAsync(f, 0, sizeof(int) * nflags, h->stream));
-  k_chol_dataflow<<<1 + a.ntasks, kDfThreads, kDfSmemBytes, h->stream>>>(a);
+  // Worker CTAs per launch: enough to run a few panel steps ahead of the chain, few enough that the 4-5
+  // concurrent evaluations of an ARD fit (one launch each, on their own streams) are resident together
+  // (2 CTAs per SM x 148 SMs = 296 slots).
+  static const int cap = [] { const char* e = getenv("VZGP_DF_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 56; }();
+  const int workers = a.ntasks < cap ? a.ntasks : cap;
+  k_chol_dataflow<<<1 + workers, kDfThreads, kDfSmemBytes, h->stream>>>(a);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;
