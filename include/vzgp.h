@@ -97,6 +97,10 @@ int vzgp_synchronize(vzgp_handle* h);
 /* Number of kernels this library has launched through `h` so far. */
 int64_t vzgp_launch_count(const vzgp_handle* h);
 
+/* Tuning knobs.  "dataflow_ctas": worker CTAs the dataflow factorisation launches (0 = every resident slot;
+ * callers that run several handles concurrently, like the ARD restarts, give each an equal share). */
+int vzgp_set_int(vzgp_handle* h, const char* key, int value);
+
 /* ---- stage-wise entry points (parity tests call these one by one) -------- */
 
 /* K = K_theta(X,X) + diag_add*I, both triangles, K is [N x ldk] device.

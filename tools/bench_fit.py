@@ -34,15 +34,26 @@ for n, d in ((1000, 20), (2000, 50), (500, 10), (200, 5)):
   fns = ard.loss_functions(dev, xt, yt, None, d, 0, workers=4)
   for g in fns:
     g(th)
-  def chain(g):
+  devs = [dev] + list(getattr(dev, '_ard_workers', []))[:3]
+  gpu_ms = [[] for _ in fns]
+  def chain(i, g):
+    st = devs[i].stream
     for _ in range(30):
-      g(th)
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(st); g(th); e1.record(st); e1.synchronize()
+      gpu_ms[i].append(e0.elapsed_time(e1))
   torch.cuda.synchronize()
   t0 = time.perf_counter()
-  ths = [threading.Thread(target=chain, args=(g,)) for g in fns]
+  ths = [threading.Thread(target=chain, args=(i, g)) for i, g in enumerate(fns)]
   [t.start() for t in ths]; [t.join() for t in ths]
   dt = time.perf_counter() - t0
   out[f'nll_grad_N{n}_D{d}_4_concurrent_ms_per_eval'] = 1e3 * dt / 120
+  out[f'nll_grad_N{n}_D{d}_4_concurrent_gpu_ms_of_one_eval'] = float(np.median(np.concatenate(gpu_ms)))
+  gpu1 = []
+  for _ in range(20):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(dev.stream); f(th); e1.record(dev.stream); e1.synchronize(); gpu1.append(e0.elapsed_time(e1))
+  out[f'nll_grad_N{n}_D{d}_alone_gpu_ms_of_one_eval'] = float(np.median(gpu1))
   t0 = time.perf_counter()
   ard.train_gp(dev, xt, yt, rng=np.random.default_rng(1))
   out[f'ard_4x50_N{n}_D{d}_s'] = time.perf_counter() - t0

@@ -58,3 +58,22 @@ def make_acquisition(num_obs: int, continuous_feasible_values: Optional[Sequence
       raise ValueError(f'{mask.shape[0]} feasible-value lists for {n_continuous} continuous features')
   radius = trust_radius(num_obs, int(mask.sum()), n_categorical)
   return gp.Acquisition(ucb_coefficient, use_trust_region, radius, mask)
+
+
+def hv_reference_point(labels: np.ndarray, scale: float = 0.01) -> np.ndarray:
+  """worst - scale * (best - worst) per metric (acquisitions.py:132-149; labels are maximised)."""
+  labels = np.asarray(labels, np.float64)
+  best, worst = labels.max(axis=0), labels.min(axis=0)
+  return worst - scale * (best - worst)
+
+
+def hv_scalarize(objectives: np.ndarray, weights: np.ndarray, reference_point=None) -> np.ndarray:
+  """HyperVolumeScalarization (scalarization.py:95-111): objectives [N, M], weights [S, M] -> [S, N]:
+  min_m(max(obj_m - ref_m, 0) / w_sm) ** M.  Host NumPy: only the observed labels go through here, the
+  candidates are scalarised on the device (csrc/multi.cu)."""
+  obj = np.asarray(objectives, np.float64)
+  if reference_point is not None:
+    obj = obj - reference_point
+  obj = np.maximum(obj, 0.0)
+  prod = obj[None, :, :] / np.asarray(weights, np.float64)[:, None, :]
+  return np.min(prod, axis=-1) ** obj.shape[-1]

@@ -163,6 +163,11 @@ def loss_functions(dev: gp.DeviceGP, xt, yt, zt, dc: int, dk: int, n_valid: Opti
   while len(pool) < workers - 1:
     pool.append(gp.DeviceGP(dev.device.index))
   devs = [dev] + pool[:workers - 1]
+  # The evaluations of the restarts run concurrently, one dataflow-factorisation launch each: an equal
+  # share of the 2 x 148 resident CTA slots keeps all of them on the GPU at once (csrc/dataflow.cu).
+  share = max(16, 288 // len(devs) - 1) if len(devs) > 1 else 0
+  for d in devs:
+    d.set_int('dataflow_ctas', share)
 
   return [d.make_loss_fn(xt, yt, zt, n_valid) for d in devs]
 
@@ -173,12 +178,17 @@ def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,
              workers: int = MAX_ARD_WORKERS) -> Tuple[List[gp.GPHyperParams], np.ndarray]:
   """Returns the best `ensemble_size` hyper-parameter sets and all final losses.
 
-  x [N,Dc] float64, z [N,Dk] int32 or None, y [N]: device tensors or arrays (copied once).
+  x [N,Dc] float64, z [N,Dk] int32 or None, y [N] or [N, M]: device tensors or arrays (copied once).
   """
   import torch  # device-memory handles only
   optimizer = optimizer or ScipyLbfgsB()
   xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev.device)
-  yt = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(y).reshape(-1), dtype=np.float64)).to(dev.device)
+  if isinstance(y, torch.Tensor):
+    yt = y
+  else:   # [N], or [N, M] for a multi-metric study (independent multi-task GP)
+    ya = np.asarray(y, np.float64)
+    ya = ya.reshape(-1) if ya.ndim == 1 or ya.shape[1] == 1 else ya
+    yt = torch.from_numpy(np.ascontiguousarray(ya)).to(dev.device)
   zt = None
   if z is not None and np.prod(tuple(z.shape)) > 0:
     zt = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z, dtype=np.int32)).to(dev.device)
@@ -187,5 +197,8 @@ def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,
   lo, hi = gp.param_bounds(dc, dk)
   inits = log_uniform_init(rng, dc, dk, random_restarts)
   fns = loss_functions(dev, xt, yt, zt, dc, dk, n_valid, workers=min(workers, random_restarts))
-  best, losses = optimizer(inits, fns, list(zip(lo, hi)), best_n=ensemble_size)
+  try:
+    best, losses = optimizer(inits, fns, list(zip(lo, hi)), best_n=ensemble_size)
+  finally:
+    dev.set_int('dataflow_ctas', 0)     # the fit that follows runs alone: every slot
   return [gp.GPHyperParams.from_vector(t, dc, dk) for t in best], losses

@@ -80,7 +80,7 @@ static int factor_invert(vzgp_handle* h, double* L, double* Linv, double* LinvT,
 // L, Linv: [np x np] (Linv complete on return).  Returns retries, or max_iters+1 on final failure, or <0.
 static int cholesky_retry_padded(vzgp_handle* h, const double* A, int lda, int n_src, int np,
                                  double jitter0, int max_iters, double* L, double* Linv,
-                                 double* shift_out, double* LinvT = nullptr) {
+                                 double* shift_out, double* LinvT = nullptr, bool* used_dataflow = nullptr) {
   int* flag = reinterpret_cast<int*>(h->small.as<char>() + kOffFlag);
   double shift = 0.0;
   int attempt = 0;
@@ -98,6 +98,7 @@ static int cholesky_retry_padded(vzgp_handle* h, const double* A, int lda, int n
       VZ_TRY(chol_dataflow_timed_out(h, &to));
       if (to) { set_error("dataflow factorisation: a tile wait timed out"); return VZGP_ERR_CUDA; }
     }
+    if (used_dataflow) *used_dataflow = df;
     if (!bad) break;
     if (attempt >= max_iters) {
       if (shift_out) *shift_out = shift;
@@ -113,7 +114,13 @@ static int cholesky_retry_padded(vzgp_handle* h, const double* A, int lda, int n
 // alpha_m = Linv^T (Linv y_m) plus one step of iterative refinement against K_y (+shift), for every metric
 // (the independent multi-task GP shares the factor: tuned_gp_models.py:282-288).  y is metric-major
 // [M][N] device; ypad is [M][4][np] (y, w = Linv y, r, tmp), alpha [M][np].
-static int solve_alphas(vzgp_handle* h, const double* y, int N, int n_valid, int np, int n_metrics, double shift) {
+static int solve_alphas(vzgp_handle* h, const double* y, int N, int n_valid, int np, int n_metrics, double shift,
+                        bool have_linvT) {
+  // Linv^T v: a row-wise product with L^-T when the dataflow factorisation produced it (coalesced rows)
+  auto gemv_T = [&](const double* v, double* out) -> int {
+    if (have_linvT) return launch_gemv_rows(h, h->LinvT.as<double>(), np, np, v, out, 2);
+    return launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, v, out);
+  };
   for (int m = 0; m < n_metrics; ++m) {
     double* yp = h->ypad.as<double>() + (size_t)m * 4 * np;
     double* w = yp + np;
@@ -122,11 +129,11 @@ static int solve_alphas(vzgp_handle* h, const double* y, int N, int n_valid, int
     double* alpha = h->alpha.as<double>() + (size_t)m * np;
     VZ_TRY(launch_pad_vector(h, y + (size_t)m * N, N, n_valid, np, yp));
     VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
-    VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, w, alpha));
+    VZ_TRY(gemv_T(w, alpha));
     VZ_TRY(launch_residual(h, h->Kws.as<double>(), np, np, yp, alpha, r));
     if (shift != 0.0) VZ_TRY(launch_axpy(h, np, -shift, alpha, r));
     VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, r, tmp, 1));
-    VZ_TRY(launch_gemv_lower_T(h, h->Linv.as<double>(), np, np, tmp, r));
+    VZ_TRY(gemv_T(tmp, r));
     VZ_TRY(launch_axpy(h, np, 1.0, r, alpha));
   }
   return 0;
@@ -157,11 +164,12 @@ static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const d
   VZ_TRY(launch_kernel_matrix(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, kp, h->sn2,
                               h->Kws.as<double>(), np));
   double shift = 0.0;
+  bool df = false;
   int retries = cholesky_retry_padded(h, h->Kws.as<double>(), np, np, np, 1e-4, 5,
-                                      h->L.as<double>(), h->Linv.as<double>(), &shift, h->LinvT.as<double>());
+                                      h->L.as<double>(), h->Linv.as<double>(), &shift, h->LinvT.as<double>(), &df);
   if (retries < 0) return retries;
   if (shift_used) *shift_used = shift;
-  VZ_TRY(solve_alphas(h, y, N, n_valid, np, n_metrics, shift));
+  VZ_TRY(solve_alphas(h, y, N, n_valid, np, n_metrics, shift, df));
   return retries;
 }
 
@@ -185,7 +193,7 @@ static int nll_sequence(vzgp_handle* h, const double* X, const int32_t* Z, const
   VZ_TRY(launch_copy_lower_shift(h, h->Kws.as<double>(), np, np, np, 0.0, h->L.as<double>(), np));
   bool df = false;   // dataflow kernel: factor, both inverses and K_y^-1 (one plane) in one launch
   VZ_TRY(factor_invert(h, h->L.as<double>(), h->Linv.as<double>(), h->LinvT.as<double>(), h->Kinv.as<double>(), np, flag, &df));
-  VZ_TRY(solve_alphas(h, y, N, n_valid, np, n_metrics, 0.0));
+  VZ_TRY(solve_alphas(h, y, N, n_valid, np, n_metrics, 0.0, df));
   double* out2 = reinterpret_cast<double*>(h->small.as<char>() + kOffLogdet);
   double* gout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);
   VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, h->ypad.as<double>() + np, out2, 4 * np, n_metrics));
@@ -366,6 +374,13 @@ int vzgp_synchronize(vzgp_handle* h) {
 }
 
 int64_t vzgp_launch_count(const vzgp_handle* h) { return h ? h->launches : 0; }
+
+int vzgp_set_int(vzgp_handle* h, const char* key, int value) {
+  VZ_ARG(h && key, "handle / key");
+  if (std::strcmp(key, "dataflow_ctas") == 0) { VZ_ARG(value >= 0, "value >= 0"); h->df_ctas = value; return 0; }
+  set_error("vzgp_set_int: unknown key '%s'", key);
+  return VZGP_ERR_ARG;
+}
 
 int vzgp_kernel_matrix(vzgp_handle* h, const double* X, const int32_t* Z, int N, int Dc, int Dk,
                        int n_valid, const vzgp_params* p, double diag_add, double* K, int ldk) {

@@ -51,19 +51,22 @@ namespace vzgp { __device__ long long g_df_t[64 * 8]; }
 #else
 #define VZ_DFT(j, s) do {} while (0)
 #endif
+#define VZ_POTF2_SYNC() asm volatile("bar.sync 0, 256;\n" ::: "memory")   // the chain's 8 math warps
 #include "potf2.cuh"
 
 namespace vzgp {
 
-constexpr int kDfThreads = 288;   // 8 math warps + 1 TMA producer warp
+constexpr int kDfThreads = 320;   // 8 math warps + producer / publisher warp + (chain only) prefetch warp
 constexpr int kDfMath = 256;
 constexpr int kDfStages = 4;
 constexpr int kBoxD = 64 * 16;                 // one TMA box: 64 rows x 16 doubles (8 KB)
 constexpr int kStageD = 2 * kBoxD;             // A box | B box
 constexpr int kRingD = kDfStages * kStageD;    // 64 KB
 constexpr int kTbufD = 4 * kBoxD;              // a whole 64 x 64 operand tile in box layout (32 KB)
-constexpr size_t kDfSmemBytes = 1024 + sizeof(double) * (kRingD + kTbufD) + 256;
 constexpr int kChainLD = 66;                   // potf2_inv_64's row stride
+constexpr int kChainD = 3 * 64 * kChainLD + 32 * 34;   // chain CTA: A_ | X_ | T_ | staged B' tile
+constexpr size_t kDfWorkerBytes = sizeof(double) * (kRingD + kTbufD), kDfChainBytes = sizeof(double) * kChainD;
+constexpr size_t kDfSmemBytes = 1024 + (kDfWorkerBytes > kDfChainBytes ? kDfWorkerBytes : kDfChainBytes) + 256;
 
 enum { DF_PART = 0, DF_TILE = 1, DF_LINV = 2, DF_KINV = 3 };
 
@@ -210,18 +213,61 @@ __device__ __forceinline__ void df_gemm_padded_tri(DfFrag& acc, const double* As
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Chain CTA: the sequential part (256 threads).
+// Chain CTA: the sequential part.  Warps 0-7 do the arithmetic (barrier 0 with 256 threads), warp 8 publishes
+// (fence + release of the tiles the math warps stored, so that no math thread waits for a fence), warp 9
+// prefetches the next panel's input tile while potf2_inv_64 runs.
+//   PART tasks deliver  B'(j) = A[j,j-1] - sum_{k<=j-2} L[j,k] L[j-1,k]^T   and
+//                       D'(j) = A[j,j]   - sum_{k<=j-2} L[j,k] L[j,k]^T      (flagS[j][0/1]),
+//   step j:  L[j,j-1] = B'(j) Linv_{j-1}^T ;  D = D'(j) - L[j,j-1] L[j,j-1]^T ;  L_jj, Linv_jj = potf2_inv_64(D).
 // ---------------------------------------------------------------------------------------------------
-__device__ void df_chain(const DfArgs& a, double* sm) {
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+
+__device__ void df_chain(const DfArgs& a, double* sm, uint64_t* bars) {
   constexpr int LD = kChainLD;
   double* A_ = sm;                  // [64][66]
   double* X_ = sm + 64 * LD;        // [64][66]
   double* T_ = X_ + 64 * LD;        // [32][34]
+  double* B_ = T_ + 32 * 34;        // [64][66] staged B'(j)
   __shared__ double rd[64];
   __shared__ int s_bad;
+  uint64_t* b_full = bars;          // warp 9's cp.async of B'(j) landed (32 lane arrivals)
+  uint64_t* b_empty = bars + 1;     // the 8 math warps are done reading B_ (T-GEMM of step j)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
   const int np = a.np, nb = a.nb;
+  auto math_sync = [&]() { named_sync(0, 256); };
+  if (warp == 8) {
+    // ---------------- publisher ----------------
+    for (int j = 0; j < nb; ++j) {
+      if (j > 0) {
+        named_sync(2, 288);          // L[j,j-1] stored by the math warps
+        if (lane == 0) { __threadfence(); st_release_gpu(a.flagL + j * nb + (j - 1), 1); }
+      }
+      named_sync(3, 288);            // L_jj, Linv_jj, Linv_jj^T stored
+      if (lane == 0) { __threadfence(); st_release_gpu(a.flagL + j * nb + j, 1); }
+    }
+    return;
+  }
+  if (warp == 9) {
+    // ---------------- prefetcher ----------------
+    for (int j = 1; j < nb; ++j) {
+      mbar_wait(b_empty, ((j - 1) & 1) ^ 1);         // B_ free (first use: passes at once)
+      if (lane == 0) { df_wait(a.flagS + j * 2, a.ctrl); df_wait(a.flagS + j * 2 + 1, a.ctrl); }
+      __syncwarp();
+      const double* Bp = a.S + (size_t)(j * 2) * 4096;     // [64][64] row-major
+      const unsigned dst0 = smem_u32(B_);
+#pragma unroll 4
+      for (int t = 0; t < 64; ++t) {                        // 2048 16-byte chunks, 64 per lane; chunk q: row q / 32
+        const int q = lane + 32 * t, r = q >> 5, c2 = (q & 31) * 2;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + (unsigned)(r * LD + c2) * 8u), "l"(Bp + r * 64 + c2) : "memory");
+      }
+      df_copy_arrive(b_full);
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    return;
+  }
+  // ---------------- math warps ----------------
+  const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
   for (int j = 0; j < nb; ++j) {
     double* Ljj = a.L + (size_t)j * 64 * np + j * 64;
     VZ_DFT(j, 0);
@@ -235,29 +281,16 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
         *reinterpret_cast<double2*>(X_ + i * LD + j2) = make_double2(0.0, 0.0);
       }
     } else {
-      // ---- L[j,j-1] = (A[j,j-1] - S(j,0)) * Linv_{j-1}^T ; X_ still holds Linv_{j-1} ----
-      if (j >= 2) {
-        if (tid == 0) { df_wait(a.flagS + j * 2, a.ctrl); df_wait(a.flagS + j * 2 + 1, a.ctrl); }
-        __syncthreads();
-      }
+      // ---- L[j,j-1] = B'(j) * Linv_{j-1}^T ; X_ still holds Linv_{j-1}, B_ the prefetched B'(j) ----
+      mbar_wait(b_full, (j - 1) & 1);
       VZ_DFT(j, 1);
       double* Lsub = a.L + (size_t)j * 64 * np + (j - 1) * 64;
-      const double* S0 = a.S + (size_t)(j * 2) * 4096;
-      const double* S1 = S0 + 4096;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
-        double2 v = *reinterpret_cast<const double2*>(Lsub + (size_t)i * np + j2);
-        if (j >= 2) {
-          const double2 s = __ldcg(reinterpret_cast<const double2*>(S0 + i * 64 + j2));
-          v.x -= s.x; v.y -= s.y;
-        }
-        *reinterpret_cast<double2*>(A_ + i * LD + j2) = v;
-      }
-      __syncthreads();
+      const double* Dp = a.S + (size_t)(j * 2 + 1) * 4096;     // D'(j): final since flagS[j][1] (seen by warp 9)
       DfFrag acc;
       acc.zero();
-      df_gemm_padded_tri(acc, A_, X_, wm, wn, fr, fk);      // Linv_{j-1} is lower triangular
+      df_gemm_padded_tri(acc, B_, X_, wm, wn, fr, fk);          // Linv_{j-1} is lower triangular
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b_empty)) : "memory");
 #pragma unroll
       for (int f = 0; f < 2; ++f)
 #pragma unroll
@@ -265,7 +298,7 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
           const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
           *reinterpret_cast<double2*>(Lsub + (size_t)r * np + c) = make_double2(acc.v[f][g][0], acc.v[f][g][1]);
         }
-      __syncthreads();            // every warp is done reading A_ and X_
+      math_sync();                // every warp is done reading X_
 #pragma unroll
       for (int f = 0; f < 2; ++f)
 #pragma unroll
@@ -273,10 +306,20 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
           const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
           *reinterpret_cast<double2*>(X_ + r * LD + c) = make_double2(acc.v[f][g][0], acc.v[f][g][1]);
         }
-      __syncthreads();            // X_ complete; every thread's global stores ordered before thread 0's fence
-      if (tid == 0) { __threadfence(); st_release_gpu(a.flagL + j * nb + (j - 1), 1); }   // early, cumulative release
+      named_arrive(2, 288);       // publisher: fence + release of L[j,j-1] (nobody here waits for it)
+      // D'(j) in fragment layout; in flight during the syrk product
+      DfFrag dp;
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(Dp + r * 64 + c));
+          dp.v[f][g][0] = v.x; dp.v[f][g][1] = v.y;
+        }
+      math_sync();                // X_ (= L[j,j-1]) complete
       VZ_DFT(j, 2);
-      // ---- D = A[j,j] - S(j,1) - L[j,j-1] L[j,j-1]^T ----
+      // ---- D = D'(j) - L[j,j-1] L[j,j-1]^T ----
       acc.zero();
       df_gemm_padded(acc, X_, X_, wm, wn, fr, fk);
 #pragma unroll
@@ -284,20 +327,15 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
-          double2 v = *reinterpret_cast<const double2*>(Ljj + (size_t)r * np + c);
-          if (j >= 2) {
-            const double2 s = __ldcg(reinterpret_cast<const double2*>(S1 + r * 64 + c));
-            v.x -= s.x; v.y -= s.y;
-          }
-          v.x -= acc.v[f][g][0]; v.y -= acc.v[f][g][1];
           const bool upper_blk = (c >> 4) > (r >> 4);
-          *reinterpret_cast<double2*>(A_ + r * LD + c) = upper_blk ? make_double2(0.0, 0.0) : v;
+          *reinterpret_cast<double2*>(A_ + r * LD + c) =
+              upper_blk ? make_double2(0.0, 0.0) : make_double2(dp.v[f][g][0] - acc.v[f][g][0], dp.v[f][g][1] - acc.v[f][g][1]);
         }
-      __syncthreads();            // syrk reads of X_ finished
+      math_sync();                // syrk reads of X_ finished
       for (int e = tid; e < 64 * LD; e += 256) X_[e] = 0.0;
     }
     if (tid == 0) s_bad = 0;
-    __syncthreads();
+    math_sync();
     VZ_DFT(j, 3);
     potf2_inv_64(A_, X_, T_, rd, &s_bad);
     VZ_DFT(j, 4);
@@ -312,8 +350,7 @@ __device__ void df_chain(const DfArgs& a, double* sm) {
       *reinterpret_cast<double2*>(Yjj + (size_t)i * np + j2) = make_double2(X_[j2 * LD + i], X_[(j2 + 1) * LD + i]);
     }
     if (tid == 0 && s_bad) *a.bad = 1;
-    __syncthreads();
-    if (tid == 0) { __threadfence(); st_release_gpu(a.flagL + j * nb + j, 1); }
+    named_arrive(3, 288);         // publisher: fence + release of the diagonal tiles
     VZ_DFT(j, 5);
   }
 }
@@ -344,6 +381,7 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
   double* ring = sm;
   double* Tbuf = sm + kRingD;
   const DfPlan p = df_plan(type, ti, tj, nb);
+  if (warp > kDfMath / 32) return;     // the chain CTA's prefetch warp has no job in a worker
   if (warp == kDfMath / 32) {
     // ---------------- producer warp (cp.async) ----------------
     const double* GA = (type == DF_LINV || type == DF_KINV) ? a.Y : a.L;
@@ -439,6 +477,19 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
   else if (type == DF_PART) { out = a.S + (size_t)(ti * 2 + (tj == ti ? 1 : 0)) * 4096; ldo = 64; flag = a.flagS + ti * 2 + (tj == ti ? 1 : 0); }
   else if (type == DF_LINV) { out = a.Y + (size_t)tj * 64 * np + ti * 64; flag = a.flagY + tj * nb + ti; }
   else { out = a.Kinv + (size_t)ti * 64 * np + tj * 64; }
+  if (type == DF_PART) {
+    // B'(j) / D'(j) = (tile of the matrix being factored) - acc: the chain then loads one tile, not two
+    const double* At = a.L + (size_t)ti * 64 * np + tj * 64;
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int r = wm * 16 + f * 8 + fr, c = wn * 32 + g * 8 + 2 * fk;
+        const double2 o = *reinterpret_cast<const double2*>(At + (size_t)r * np + c);
+        acc.v[f][g][0] = o.x - acc.v[f][g][0];
+        acc.v[f][g][1] = o.y - acc.v[f][g][1];
+      }
+  }
 #pragma unroll
   for (int f = 0; f < 2; ++f)
 #pragma unroll
@@ -457,7 +508,7 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
         xt[(size_t)(c + 1) * np + r] = acc.v[f][g][1];
       }
   }
-  // All warps are done with this task's tiles (Tbuf may be rewritten by the next task).  The barrier also
+  // (PART epilogue handled above.)  All warps are done with this task's tiles (Tbuf may be rewritten by the next task).  The barrier also
   // orders every thread's stores before thread 0's fence: the release below is cumulative.
   math_sync();
   if (flag != nullptr && tid == 0) {
@@ -480,8 +531,14 @@ __global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const DfArgs a)
   __syncthreads();
   int ticket = s_ticket;
   if (ticket == 0) {
-    if (tid >= kDfMath) return;
-    df_chain(a, sm);
+    __shared__ uint64_t chain_bars[2];
+    if (tid == 0) {
+      mbar_init(chain_bars, 32);
+      mbar_init(chain_bars + 1, kDfMath / 32);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    df_chain(a, sm, chain_bars);
     return;
   }
   // Persistent worker: tasks in ticket order until the list is exhausted.  A CTA holds one task at a time
@@ -496,7 +553,7 @@ __global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const DfArgs a)
     __syncthreads();
     ticket = s_ticket;
   }
-  if (tid >= kDfMath) asm volatile("cp.async.wait_all;\n" ::: "memory");
+  if (tid >= kDfMath && tid < kDfMath + 32) asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -507,7 +564,7 @@ struct DfTaskHost { int key, type, i, j; };
 static void build_tasks(int nb, bool want_kinv, std::vector<int4>* out) {
   std::vector<DfTaskHost> t;
   // time of chain step j = 2j; a task's key = time after which its last input exists
-  for (int j = 2; j < nb; ++j) {
+  for (int j = 1; j < nb; ++j) {
     t.push_back({2 * j - 1, DF_PART, j, j - 1});
     t.push_back({2 * j - 1, DF_PART, j, j});
   }
@@ -569,10 +626,13 @@ int chol_dataflow(vzgp_handle* h, double* L, double* Linv, double* LinvT, double
   a.tasks = h->df_tasks[want_kinv ? 1 : 0].as<int4>(); a.ntasks = h->df_ntasks[want_kinv ? 1 : 0];
   a.np = np; a.nb = nb; a.bad = flag;
   VZ_CUDA(cudaMemsetAsync(f, 0, sizeof(int) * nflags, h->stream));
-  // Worker CTAs per launch: enough to run a few panel steps ahead of the chain, few enough that the 4-5
-  // concurrent evaluations of an ARD fit (one launch each, on their own streams) are resident together
-  // (2 CTAs per SM x 148 SMs = 296 slots).
-  static const int cap = [] { const char* e = getenv("VZGP_DF_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 56; }();
+  // Worker CTAs per launch.  A lone factorisation (the fit, a single evaluation) may take every slot
+  // (2 CTAs per SM); the 4-5 concurrent evaluations of an ARD fit run one launch each on their own
+  // streams and are given an equal share (vzgp_set_int(h, "dataflow_ctas", n), ard.py) so that all of
+  // them are resident together.
+  static const int env_cap = [] { const char* e = getenv("VZGP_DF_CTAS"); return e ? atoi(e) : 0; }();
+  int cap = h->df_ctas > 0 ? h->df_ctas : (env_cap > 0 ? env_cap : 2 * h->sm_count - 8);
+  if (cap < 8) cap = 8;
   const int workers = a.ntasks < cap ? a.ntasks : cap;
   k_chol_dataflow<<<1 + workers, kDfThreads, kDfSmemBytes, h->stream>>>(a);
   VZ_CHECK_LAUNCH();

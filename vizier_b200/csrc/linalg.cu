@@ -345,15 +345,17 @@ __global__ void __launch_bounds__(256) k_lauum(const double* __restrict__ Linv, 
 // ---------------------------------------------------------------------------
 // Matrix-vector helpers (one warp per row), used for alpha = Linv^T (Linv y) and refinement.
 // ---------------------------------------------------------------------------
-// out[i] = sum_{j in [j_lo(i), j_hi(i))} M[i,j] * v[j];  mode 0: full row [0,np); 1: j <= i.
+// out[i] = sum_{j in [j_lo(i), j_hi(i))} M[i,j] * v[j];  mode 0: full row [0,ncols); 1: j <= i (lower
+// triangular M); 2: j >= i (upper triangular M, e.g. L^-T from the dataflow factorisation).
 __global__ void k_gemv_rows(const double* __restrict__ M, int ld, int nrows, int ncols,
                             const double* __restrict__ v, double* __restrict__ out, int lower_only) {
   int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x & 31;
   if (row >= nrows) return;
-  int hi = lower_only ? row + 1 : ncols;
+  int hi = lower_only == 1 ? row + 1 : ncols;
+  int lo = lower_only == 2 ? (row & ~31) : 0;     // aligned start: the entries left of the diagonal are zero
   double s = 0.0;
-  for (int j = lane; j < hi; j += 32) s = fma(M[(size_t)row * ld + j], v[j], s);
+  for (int j = lo + lane; j < hi; j += 32) s = fma(M[(size_t)row * ld + j], v[j], s);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if (lane == 0) out[row] = s;

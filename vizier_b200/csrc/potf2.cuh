@@ -8,11 +8,16 @@ namespace vzgp {
 #ifndef VZ_TSTAMP
 #define VZ_TSTAMP(i) do {} while (0)
 #endif
+// The barrier between the phases of potf2_inv_64: the whole CTA by default; a CTA that runs it on a subset of
+// its warps (the dataflow chain: 256 of 320 threads) defines its own before including this header.
+#ifndef VZ_POTF2_SYNC
+#define VZ_POTF2_SYNC() __syncthreads()
+#endif
 
 // Factor a (64x64, row stride 66, lower triangle + arbitrary diagonal-16-block upper parts, 16-blocks
 // strictly above the diagonal ZERO) in place and write its inverse into x (must be ZERO on entry).
 // t: [32][34] scratch, rd: [64] reciprocal diagonal, *s_bad is set to 1 on a non-positive / non-finite
-// pivot (the factor then holds NaN).  256 threads, ends with a __syncthreads().
+// pivot (the factor then holds NaN).  256 threads, ends with a VZ_POTF2_SYNC().
 //
 // This is a pure latency chain (64 dependent pivots), organised around the critical path:
 //  * four 16-column macro steps; the 16x16 diagonal piece is factored by ONE warp entirely in
@@ -83,7 +88,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
       }
       if (bad && lane == 0) *s_bad = 1;
     }
-    __syncthreads();
+    VZ_POTF2_SYNC();
     VZ_TSTAMP(2 + 3 * mb);
     const int rem = 48 - c0;                 // rows below this macro block
     if (tid < rem) {
@@ -105,7 +110,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
       for (int k = 0; k < 16; k += 2)
         *reinterpret_cast<double2*>(a + r * LD + c0 + k) = make_double2(xr[k], xr[k + 1]);
     }
-    __syncthreads();
+    VZ_POTF2_SYNC();
     VZ_TSTAMP(3 + 3 * mb);
     // ---- trailing update: a[i][k] -= sum_j a[i][c0+j] * a[k][c0+j],  c0+16 <= k <= i ----
     // thread (ti, tk) owns the entries (ti + 16 p, tk + 16 q) of every 16x16 block (p, q), q <= p
@@ -133,7 +138,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
         }
       }
     }
-    __syncthreads();
+    VZ_POTF2_SYNC();
     VZ_TSTAMP(4 + 3 * mb);
   }
   VZ_TSTAMP(14);
@@ -152,7 +157,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[(b0 + i) * LD + b0 + c] = xc[i];
   }
-  __syncthreads();
+  VZ_POTF2_SYNC();
   VZ_TSTAMP(15);
   // ---- step B: 16-level doubling, two pairs; thread = one (row, col) of each pair ----
   {
@@ -168,7 +173,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
     }
     t[rr * 34 + cc] = acc[0];
     t[(16 + rr) * 34 + cc] = acc[1];
-    __syncthreads();
+    VZ_POTF2_SYNC();
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr) {
       const int p0 = 32 * pr;
@@ -180,7 +185,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
     x[(16 + rr) * LD + cc] = -acc[0];
     x[(48 + rr) * LD + 32 + cc] = -acc[1];
   }
-  __syncthreads();
+  VZ_POTF2_SYNC();
   VZ_TSTAMP(16);
   // ---- step C: 32-level doubling; thread = a 2x2 patch of the 32x32 block ----
   {
@@ -195,7 +200,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
     }
     *reinterpret_cast<double2*>(t + r0 * 34 + q0) = make_double2(s00, s01);
     *reinterpret_cast<double2*>(t + (r0 + 1) * 34 + q0) = make_double2(s10, s11);
-    __syncthreads();
+    VZ_POTF2_SYNC();
     s00 = s01 = s10 = s11 = 0.0;
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
@@ -207,7 +212,7 @@ __device__ __forceinline__ void potf2_inv_64(double* a, double* x, double* t, do
     *reinterpret_cast<double2*>(x + (32 + r0) * LD + q0) = make_double2(-s00, -s01);
     *reinterpret_cast<double2*>(x + (33 + r0) * LD + q0) = make_double2(-s10, -s11);
   }
-  __syncthreads();
+  VZ_POTF2_SYNC();
   VZ_TSTAMP(17);
 }
 

@@ -11,8 +11,11 @@ same metadata keys, same errors for unsupported search spaces.  What runs where:
                          optimisation, top-k
 
 `ensemble_size > 1` keeps the E best ARD restarts as a uniform mixture (`gp.EnsembleGP`).
-Not implemented (the reference supports them; SURVEY 8f "next"): multi-metric scalarised UCB,
-`linear_coef`, transfer-learning priors (`set_priors`), parallel (q-) acquisitions; each raises
+Multi-metric problems use the reference's scalarised UCB (gp_bandit.py:214-242): an independent
+multi-task GP (one factor, one alpha per metric) scored by the mean over `num_scalarizations`
+hyper-volume scalarisations, without a trust region.
+Not implemented (the reference supports them; SURVEY 8f "next"): `linear_coef`, transfer-learning
+priors (`set_priors`), parallel (q-) acquisitions, non-independent multi-task kernels; each raises
 NotImplementedError instead of silently doing something else.  Categorical parameters ARE supported
 end to end.  `padding_schedule` is accepted and has no numerical effect here: the kernels take
 explicit sizes (`n_valid`, Dc, Dk) instead of padded shapes + masks, which is what the reference's
@@ -90,8 +93,11 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
       raise ValueError(f'{type(self)} does not support conditional search.')
     if problem.search_space.num_parameters() == 0:
       raise ValueError('SearchSpace should contain at least one parameter config.')
-    if len(problem.metric_information) != 1:
-      raise NotImplementedError('vizier_b200.VizierGPBandit implements the single-metric path only.')
+    self._n_metrics = len(problem.metric_information)
+    if self._n_metrics > 8:
+      raise NotImplementedError('at most 8 metrics (libvzgp kMaxMetrics).')
+    if self._n_metrics > 1 and multitask_type not in (None, 'INDEPENDENT') and getattr(multitask_type, 'name', '') != 'INDEPENDENT':
+      raise NotImplementedError('only the INDEPENDENT multi-task kernel (the default) is implemented.')
     if linear_coef is not None:
       raise NotImplementedError('linear_coef (Matern + linear kernel) is not implemented.')
     self._ensemble_size = int(ensemble_size or 1)
@@ -99,19 +105,29 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
       raise ValueError('ensemble_size must be in [1, ard_random_restarts].')
     if scoring_function_is_parallel or scoring_function_factory is not None:
       raise NotImplementedError('custom / parallel scoring functions are not implemented (UCB only).')
-    del padding_schedule, num_scalarizations, ref_scaling, multitask_type
+    if self._n_metrics > 1 and self._ensemble_size > 1:
+      raise NotImplementedError('ensembles of multi-metric models are not implemented.')
+    del padding_schedule, multitask_type
+    self._num_scalarizations = int(num_scalarizations)
+    self._ref_scaling = float(ref_scaling)
     self._problem = problem
     self._acquisition_optimizer_factory = acquisition_optimizer_factory
     self._ard_optimizer = ard_optimizer or ard.ScipyLbfgsB()
     self._ard_random_restarts = ard_random_restarts
     self._num_seed_trials = num_seed_trials
-    self._use_trust_region = use_trust_region
+    self._use_trust_region = use_trust_region and self._n_metrics == 1   # gp_bandit.py:241
     self._ucb_coefficient = ucb_coefficient
     self._metadata_ns = 'oss_gp_bandit'
     self._output_warper = output_warper or output_warpers.create_default_warper()
     self._rng = np.random.default_rng(_seed_from(rng))
     self._converter = converters.TrialToModelInputConverter.from_problem(problem)
     self._acquisition_optimizer = acquisition_optimizer_factory(self._converter)
+    # Scalarisation weights are drawn once per designer (gp_bandit.py:217-222: one weights_rng): |N(0,1)|,
+    # rows normalised to unit L2 norm (acquisitions.py:585-589).
+    self._scal_weights = None
+    if self._n_metrics > 1:
+      w = np.abs(np.random.default_rng(int(self._rng.integers(2**62))).standard_normal((self._num_scalarizations, self._n_metrics)))
+      self._scal_weights = w / np.linalg.norm(w, axis=-1, keepdims=True)
     self._halton_offset = int(self._rng.integers(0, 2**16))
     self._halton_count = 0
     self._trials: list = []
@@ -180,18 +196,25 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     self._incorporated_trials_count = len(self._trials)
     ard_rng = np.random.default_rng(int(self._rng.integers(2**62)))
     z = cat if cat.shape[1] else None
-    best, _ = ard.train_gp(self._ard_dev, cont, labels[:, 0], z, rng=ard_rng, random_restarts=self._ard_random_restarts,
+    y = labels[:, 0] if self._n_metrics == 1 else labels     # [N] or [N, M]
+    best, _ = ard.train_gp(self._ard_dev, cont, y, z, rng=ard_rng, random_restarts=self._ard_random_restarts,
                            ensemble_size=self._ensemble_size, optimizer=self._ard_optimizer)
     if self._ensemble_size > 1:
       # the E best restarts become the members of a uniform mixture (gp_models.py:200-223)
       self._last_params = list(best)
-      dev.fit(cont, labels[:, 0], self._last_params, z=z)
+      dev.fit(cont, y, self._last_params, z=z)
     else:
       self._last_params = best[0]
-      dev.fit(cont, labels[:, 0], self._last_params, z=z)
+      dev.fit(cont, y, self._last_params, z=z)
     return dev
 
-  def _acquisition(self, n_obs: int) -> gp.Acquisition:
+  def _acquisition(self, n_obs: int, labels: Optional[np.ndarray] = None):
+    if self._n_metrics > 1:
+      # gp_bandit.py:217-239: HV scalarisation around the reference point of the (warped) labels, floored
+      # at the best scalarised value observed so far
+      ref = acq_lib.hv_reference_point(labels, self._ref_scaling)
+      best = acq_lib.hv_scalarize(labels, self._scal_weights, ref).max(axis=-1)
+      return gp.ScalarizedUcbAcquisition(self._scal_weights, ref, best, self._ucb_coefficient)
     return acq_lib.make_acquisition(
         n_obs, self._converter.continuous_feasible_values(_MAX_NUM_FEASIBLE_VALUES_FOR_TRUST_REGION),
         self._converter.n_continuous, self._converter.n_categorical, use_trust_region=self._use_trust_region,
@@ -232,7 +255,7 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     start = datetime.datetime.now()
     cont, cat, labels = self._trials_to_data(self._trials)
     dev = self._update_gp(cont, cat, labels)
-    acq = self._acquisition(cont.shape[0])
+    acq = self._acquisition(cont.shape[0], labels)
     best = self._optimize_acquisition(dev, acq, count, features=(cont, cat))
     out = []
     for t in best:
@@ -251,6 +274,8 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     xs = np.nan_to_num(xs, nan=0.0)
     g = np.random.default_rng(_seed_from(rng) if rng is not None else 0)
     zq = zs if zs.shape[1] else None
+    if self._n_metrics > 1:
+      return self._sample_multi(dev, xs, zq, g, num_samples)
     comps = dev.posterior(xs, zq, add_noise=True) if self._ensemble_size > 1 else [dev.posterior(xs, zq, add_noise=True)]
     # Cholesky of each (small) posterior covariance on the device as well; the retry adds a tiny
     # jitter only if round-off made it indefinite.
@@ -264,6 +289,19 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     member = g.integers(0, len(factors), size=num_samples) if len(factors) > 1 else np.zeros(num_samples, int)
     samples = np.stack([factors[e][0] + normals[i] @ factors[e][1].T for i, e in enumerate(member)])
     return np.vstack([self._output_warper.unwarp(samples[i][:, None]).reshape(-1) for i in range(num_samples)])
+
+  def _sample_multi(self, dev, xs, zq, g, num_samples: int) -> np.ndarray:
+    """Independent multi-task GP: the metrics share the posterior covariance and differ in the mean.
+    Returns unwarped samples [num_samples, num_trials, num_metrics]."""
+    mean, cov = dev.posterior(xs, zq, add_noise=True)          # mean [M, n]
+    chol, _, _ = self._ard_dev.cholesky_retry(cov, jitter=1e-10, max_iters=8)
+    mean, chol = mean.cpu().numpy(), chol.cpu().numpy()
+    out = np.empty((num_samples, mean.shape[1], self._n_metrics))
+    for m in range(self._n_metrics):
+      z = g.standard_normal((num_samples, mean.shape[1]))
+      warped = mean[m][None, :] + z @ chol.T
+      out[:, :, m] = self._output_warper.unwarp(warped.reshape(-1, 1)).reshape(num_samples, -1)
+    return out
 
   @profiler.record_runtime
   def predict(self, trials: Sequence[Any], rng: Any = None, num_samples: Optional[int] = 1000):

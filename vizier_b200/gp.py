@@ -207,6 +207,9 @@ class DeviceGP:
   def launch_count(self) -> int:
     return int(self._lib.vzgp_launch_count(self._h))
 
+  def set_int(self, key: str, value: int) -> None:
+    _lib.check('vzgp_set_int', self._lib.vzgp_set_int(self._h, key.encode(), int(value)))
+
   # -- helpers -------------------------------------------------------------
   def _dev(self, a, dtype) -> Optional[torch.Tensor]:
     if a is None:

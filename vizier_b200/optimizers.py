@@ -89,7 +89,20 @@ class VectorizedOptimizer:
     """acq: gp.Acquisition (UCB + trust region on `dev`) or gp.UcbPeAcquisition (needs `other`)."""
     sizes = list(self.categorical_sizes)
     is_pe = isinstance(acq, gp.UcbPeAcquisition)
-    if isinstance(self.strategy_factory, _RandomStrategyFactory):
+    is_multi = isinstance(acq, gp.ScalarizedUcbAcquisition)
+    if isinstance(self.strategy_factory, _RandomStrategyFactory) and is_multi:
+      # uniform pool -> scalarised UCB -> device top-k, like vzgp_random_search but with the multi-metric scorer
+      import torch
+      n = (self.max_evaluations - 1) // self.suggestion_batch_size + 1
+      m = n * self.suggestion_batch_size
+      xs = dev.random_pool(m, self.n_continuous, seed) if self.n_continuous else torch.zeros((m, 0), dtype=torch.float64, device=dev.device)
+      zs = dev.random_pool_cat(m, sizes, seed) if self.n_categorical else None
+      out = dev.score_multi(xs, acq, zs=zs)
+      idx, bs = dev.topk(out['score'], count)
+      it = torch.from_numpy(np.maximum(idx, 0)).to(dev.device)
+      bx = xs[it].cpu().numpy()
+      bz = zs[it].cpu().numpy() if zs is not None else np.zeros((count, 0), np.int32)
+    elif isinstance(self.strategy_factory, _RandomStrategyFactory):
       if is_pe:
         raise NotImplementedError('random strategy with the GP-UCB-PE acquisition')
       # one uniform batch per step; the device scores all max_evaluations candidates in one pass
@@ -111,6 +124,8 @@ class VectorizedOptimizer:
       out = dev.score_pe(other, bx, acq, zs=bz if self.n_categorical else None)
       aux = {k: out[k].cpu().numpy() for k in ('mean', 'stddev', 'stddev_from_all')}
       return VectorizedStrategyResults(bx, bs, aux, categorical=bz)
+    if is_multi:   # no trust region -> no aux (acquisitions.py:190-207)
+      return VectorizedStrategyResults(bx, bs, {}, categorical=bz)
     # score_with_aux on the winners (vectorized_base.py:504-526)
     out = dev.score(bx, acq, zs=bz if self.n_categorical else None, with_aux=True)
     dev.synchronize()
