@@ -27,3 +27,16 @@ for j in range(nb):
 tot = {k: int(np.sum([r[k] for r in rows])) for k in rows[0] if k != 'step'}
 print(json.dumps({'n': n, 'nb': nb, 'per_step_cycles': rows[:4] + rows[-2:], 'sum_cycles': tot,
                   'chain_cycles': int(t[nb - 1][5] - t[0][0])}, indent=1))
+
+if hasattr(lib, 'vzgp_debug_la_timing'):
+  b2 = (C.c_longlong * 64)()
+  lib.vzgp_debug_la_timing.restype = C.c_int
+  if lib.vzgp_debug_la_timing(b2) == 0:
+    u = np.array(b2[:], dtype=np.int64)
+    base = u[0]
+    names = {0: 'D start', 1: 'D end', 2: 'UPD passed', 3: 'P end'}
+    for mb in range(4):
+      print('warp0 step', mb, {names[k]: int(u[8 * mb + k] - base) for k in range(4) if u[8 * mb + k]})
+    print('end before final sync', int(u[40] - base), 'after', int(u[41] - base))
+    print('hw6 inverse done', [int(v - base) for v in u[42:46]], 'hw0 panel done', [int(v - base) for v in u[46:50]])
+    print('hw3 after H', [int(v - base) for v in u[50:54]], 'hw3 before UPD', [int(v - base) for v in u[54:58]])

@@ -53,6 +53,7 @@ namespace vzgp { __device__ long long g_df_t[64 * 8]; }
 #endif
 #define VZ_POTF2_SYNC() asm volatile("bar.sync 0, 256;\n" ::: "memory")   // the chain's 8 math warps
 #include "potf2.cuh"
+#include "potf2_la.cuh"
 
 namespace vzgp {
 
@@ -243,7 +244,21 @@ __device__ void df_chain(const DfArgs& a, double* sm, uint64_t* bars) {
         named_sync(2, 288);          // L[j,j-1] stored by the math warps
         if (lane == 0) { __threadfence(); st_release_gpu(a.flagL + j * nb + (j - 1), 1); }
       }
-      named_sync(3, 288);            // L_jj, Linv_jj, Linv_jj^T stored
+      named_sync(3, 288);            // potf2 done: L_jj in A_, Linv_jj in X_
+      // The three diagonal tiles go out from here, so the math warps start the next panel at once.
+      double* Ljj = a.L + (size_t)j * 64 * np + j * 64;
+      double* Xjj = a.X + (size_t)j * 64 * np + j * 64;
+      double* Yjj = a.Y + (size_t)j * 64 * np + j * 64;
+      const int j2 = 2 * lane;
+#pragma unroll 4
+      for (int i = 0; i < 64; ++i) {
+        *reinterpret_cast<double2*>(Ljj + (size_t)i * np + j2) = *reinterpret_cast<const double2*>(A_ + i * LD + j2);
+        *reinterpret_cast<double2*>(Xjj + (size_t)i * np + j2) = *reinterpret_cast<const double2*>(X_ + i * LD + j2);
+        *reinterpret_cast<double2*>(Yjj + (size_t)i * np + j2) = make_double2(X_[j2 * LD + i], X_[(j2 + 1) * LD + i]);   // transposed
+      }
+      if (lane == 0 && s_bad) *a.bad = 1;
+      __syncwarp();
+      if (j + 1 < nb) named_arrive(8, 288);   // A_ / X_ may be overwritten (the math warps wait for this before they do)
       if (lane == 0) { __threadfence(); st_release_gpu(a.flagL + j * nb + j, 1); }
     }
     return;
@@ -269,7 +284,7 @@ __device__ void df_chain(const DfArgs& a, double* sm, uint64_t* bars) {
   // ---------------- math warps ----------------
   const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
   for (int j = 0; j < nb; ++j) {
-    double* Ljj = a.L + (size_t)j * 64 * np + j * 64;
+    const double* Ljj = a.L + (size_t)j * 64 * np + j * 64;
     VZ_DFT(j, 0);
     if (j == 0) {
 #pragma unroll
@@ -299,6 +314,7 @@ __device__ void df_chain(const DfArgs& a, double* sm, uint64_t* bars) {
           *reinterpret_cast<double2*>(Lsub + (size_t)r * np + c) = make_double2(acc.v[f][g][0], acc.v[f][g][1]);
         }
       math_sync();                // every warp is done reading X_
+      named_sync(8, 288);         // ... and so is the publisher (the diagonal tiles of step j-1 are out)
 #pragma unroll
       for (int f = 0; f < 2; ++f)
 #pragma unroll
@@ -337,20 +353,13 @@ __device__ void df_chain(const DfArgs& a, double* sm, uint64_t* bars) {
     if (tid == 0) s_bad = 0;
     math_sync();
     VZ_DFT(j, 3);
+#ifdef VZ_DF_NO_LOOKAHEAD
     potf2_inv_64(A_, X_, T_, rd, &s_bad);
+#else
+    potf2_inv_64_la(A_, X_, T_, rd, &s_bad);
+#endif
     VZ_DFT(j, 4);
-    double* Xjj = a.X + (size_t)j * 64 * np + j * 64;
-    double* Yjj = a.Y + (size_t)j * 64 * np + j * 64;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int e = tid + 256 * u, i = e >> 5, j2 = (e & 31) * 2;
-      *reinterpret_cast<double2*>(Ljj + (size_t)i * np + j2) = *reinterpret_cast<const double2*>(A_ + i * LD + j2);
-      *reinterpret_cast<double2*>(Xjj + (size_t)i * np + j2) = *reinterpret_cast<const double2*>(X_ + i * LD + j2);
-      // transposed copy: Y[i][j2..j2+1] = X_[j2..j2+1][i]
-      *reinterpret_cast<double2*>(Yjj + (size_t)i * np + j2) = make_double2(X_[j2 * LD + i], X_[(j2 + 1) * LD + i]);
-    }
-    if (tid == 0 && s_bad) *a.bad = 1;
-    named_arrive(3, 288);         // publisher: fence + release of the diagonal tiles
+    named_arrive(3, 288);         // publisher: stores L_jj, Linv_jj, Linv_jj^T from A_ / X_, fence, release
     VZ_DFT(j, 5);
   }
 }
@@ -653,6 +662,11 @@ int chol_dataflow_timed_out(vzgp_handle* h, int* out) {
 
 #ifdef VZ_DF_TIMING
 // Debug builds only (make EXTRA=-DVZ_DF_TIMING): clock64 stamps of the chain CTA, [step][phase].
+#ifdef VZ_LA_TIMING
+extern "C" int vzgp_debug_la_timing(long long* out) {
+  return cudaMemcpyFromSymbol(out, vzgp::g_la_t, sizeof(long long) * 64) == cudaSuccess ? 0 : -2;
+}
+#endif
 extern "C" int vzgp_debug_df_timing(long long* out, int n) {
   return cudaMemcpyFromSymbol(out, vzgp::g_df_t, sizeof(long long) * (n < 512 ? n : 512)) == cudaSuccess ? 0 : -2;
 }
