@@ -157,6 +157,18 @@ int vzgp_nll_grad_multi(vzgp_handle* h, const double* X, const int32_t* Z, const
                         int Dk, int n_valid, int n_metrics, const vzgp_params* p, double* loss_out,
                         double* grad_out);
 
+/* R evaluations of vzgp_nll_grad_multi - the restarts of one ARD fit, same data, different hyper-parameters -
+ * in ONE graph launch: hs[r] (distinct handles and streams on one device) holds the workspaces of restart r,
+ * the R launch sequences run as parallel branches of one CUDA graph, results come back through pinned host
+ * memory after a single synchronisation.  ps [R] parameter structs (host), active [R] (0 = skip the update
+ * and the outputs of that restart; NULL = all), loss_out [R], grad_out [R x (Dk+Dc+2)], status_out [R]
+ * (Cholesky retries of the restarts that needed the jitter loop; those fall back to the single-evaluation
+ * path).  N > 64.  This is what the lock-step L-BFGS-B driver (vizier_b200/ard.py) calls once per round, in
+ * place of the reference's sequential restarts (jaxopt_wrappers.py:139-152). */
+int vzgp_nll_grad_batch(vzgp_handle* const* hs, int R, const double* X, const int32_t* Z, const double* Y, int N,
+                        int Dc, int Dk, int n_valid, int n_metrics, const vzgp_params* ps, const uint8_t* active,
+                        double* loss_out, double* grad_out, int* status_out);
+
 /* Hyper-volume scalarised UCB, the acquisition VizierGPBandit uses for multi-objective problems
  * (gp_bandit.py:214-242; acquisitions.py:571-625; scalarization.py:85-111):
  *   u_m = mu_m + ucb_coefficient * sigma            (sigma is shared by the metrics of the independent GP)

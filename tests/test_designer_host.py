@@ -59,8 +59,13 @@ def test_designer_validation_errors_need_no_gpu():
     gp_bandit.VizierGPBandit(vz.ProblemStatement())
   p = _problem()
   p.metric_information.append(vz.MetricInformation(name='m2', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  d = gp_bandit.VizierGPBandit(p, num_scalarizations=16)     # multi-metric: scalarised UCB, no trust region
+  assert d._scal_weights.shape == (16, 2) and not d._use_trust_region
+  np.testing.assert_allclose(np.linalg.norm(d._scal_weights, axis=1), 1.0)
   with pytest.raises(NotImplementedError):
-    gp_bandit.VizierGPBandit(p)
+    gp_bandit.VizierGPBandit(p, ensemble_size=2)
+  with pytest.raises(NotImplementedError):
+    gp_bandit.VizierGPBandit(_problem(), linear_coef=0.1)
 
 
 def test_seed_trials_centre_then_quasi_random():
@@ -185,3 +190,34 @@ def test_designers_implement_the_designer_and_predictor_interfaces():
   for cls in (gp_bandit.VizierGPBandit, gp_ucb_pe.VizierGPUCBPEBandit):
     assert issubclass(cls, vz.Designer) and issubclass(cls, vz.Predictor)
     assert not getattr(cls, '__abstractmethods__', None), cls.__abstractmethods__
+
+
+def test_lockstep_driver_equals_one_restart_at_a_time():
+  """ard._lockstep (all restarts advance together, one batched evaluation per round) gives every restart
+  exactly the iterates it has alone - the batched ARD changes the schedule, not the optimisation."""
+  from vizier_b200 import ard
+  if ard._setulb is None:
+    pytest.skip('SciPy without the C L-BFGS-B step routine')
+  rng = np.random.default_rng(0)
+  a = rng.normal(size=(6, 6)); q = a @ a.T + np.eye(6)
+  c = rng.normal(size=6)
+
+  def f(x):
+    return float(0.5 * x @ q @ x + c @ x + 0.1 * np.sum(np.cos(3 * x))), q @ x + c - 0.3 * np.sin(3 * x)
+
+  bounds = [(-2.0, 2.0)] * 6
+  inits = rng.uniform(-2, 2, size=(5, 6))
+  calls = []
+
+  def batch(indices, points):
+    calls.append(list(indices))
+    out = [f(p) for p in points]
+    return [o[0] for o in out], [o[1] for o in out]
+
+  kw = dict(maxiter=50, gtol=1e-8, maxls=20)
+  together = ard._lockstep(batch, inits, bounds, **kw)
+  for t0, (x, fx) in zip(inits, together):
+    xs, fs = ard._lean_lbfgsb(f, t0, bounds, **kw)
+    np.testing.assert_array_equal(x, xs)
+    assert fx == fs
+  assert calls[0] == [0, 1, 2, 3, 4] and len(calls[-1]) >= 1 and len(calls) < sum(len(c) for c in calls)

@@ -473,6 +473,28 @@ def test_ard_fit_matches_oracle_driver(dev):
   assert abs(l_o - losses.min()) < 1e-8
 
 
+def test_batched_ard_equals_threaded_ard():
+  """The lock-step ARD (one graph launch evaluates all restarts, vzgp_nll_grad_batch) and the round-1 form
+  (one host thread and one graph per restart) run the same optimisations: identical final losses and
+  hyper-parameters; with categorical features and masked rows too."""
+  from vizier_b200 import ard
+  gp = _gp()
+  for n, d, dk, nv in ((150, 4, 0, 150), (260, 6, 2, 250)):
+    x, y, z = _problem(n, d, 31, dk)
+    res = {}
+    for batched in (True, False):
+      ard.BATCHED_ARD = batched
+      try:
+        dev = gp.DeviceGP(0)
+        best, losses = ard.train_gp(dev, x, y, z, rng=np.random.default_rng(5), random_restarts=5, ensemble_size=2,
+                                    n_valid=nv)
+        res[batched] = (np.stack([b.to_vector() for b in best]), losses)
+      finally:
+        ard.BATCHED_ARD = True
+    np.testing.assert_array_equal(res[True][1], res[False][1])
+    np.testing.assert_array_equal(res[True][0], res[False][0])
+
+
 def test_posterior_covariance(dev):
   n, d, m = 150, 5, 70
   x, y, _ = _problem(n, d, 22)

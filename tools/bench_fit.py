@@ -54,8 +54,12 @@ for n, d in ((1000, 20), (2000, 50), (500, 10), (200, 5)):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(dev.stream); f(th); e1.record(dev.stream); e1.synchronize(); gpu1.append(e0.elapsed_time(e1))
   out[f'nll_grad_N{n}_D{d}_alone_gpu_ms_of_one_eval'] = float(np.median(gpu1))
-  t0 = time.perf_counter()
-  ard.train_gp(dev, xt, yt, rng=np.random.default_rng(1))
-  out[f'ard_4x50_N{n}_D{d}_s'] = time.perf_counter() - t0
+  for mode in ('batched', 'threaded'):
+    ard.BATCHED_ARD = mode == 'batched'
+    ard.train_gp(dev, xt, yt, rng=np.random.default_rng(1))      # buffers, graphs
+    t0 = time.perf_counter()
+    ard.train_gp(dev, xt, yt, rng=np.random.default_rng(1))
+    out[f'ard_4x50_N{n}_D{d}_{mode}_s'] = time.perf_counter() - t0
+  ard.BATCHED_ARD = True
   dev.close()
 print(json.dumps(out, indent=1))

@@ -134,6 +134,7 @@ SIGNATURES = {
     'vzgp_fit': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _pP]),
     'vzgp_fit_multi': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _pP]),
     'vzgp_nll_grad_multi': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _pP, _pd, _pd]),
+    'vzgp_nll_grad_batch': (_i, [C.POINTER(_vp), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(Params), C.POINTER(C.c_uint8), _pd, _pd, C.POINTER(_i)]),
     'vzgp_score_multi': (_i, [_vp, _vp, _vp, _i, C.POINTER(Scalarization), _vp, _vp, _vp]),
     'vzgp_eagle_run_multi': (_i, [_vp, _pE, C.POINTER(Scalarization), _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
     'vzgp_get_cholesky': (_i, [_vp, _vp, _i]),

@@ -49,13 +49,14 @@ except Exception:  # pylint: disable=broad-except
   _INT = np.int32
 
 
-def _lean_lbfgsb(fun, x0: np.ndarray, bounds, *, maxiter: int, gtol: float, maxls: int,
-                 ftol: float = 2.220446049250313e-09, maxcor: int = 10, maxfun: int = 15000):
-  """The loop of `scipy.optimize._lbfgsb_py._minimize_lbfgsb` around the same compiled `setulb` routine,
-  without the per-evaluation Python layers (ScalarFunction wrappers, OptimizeResult per iteration):
-  identical iterates and results, ~10 us instead of ~70 us of host time per evaluation.  With several
-  restarts running in threads the host side is what serialises (GIL), so this is what the ARD wall time
-  of small and mid-size studies is made of.  All bounds must be finite (they are: param_bounds)."""
+def _lean_lbfgsb_steps(x0: np.ndarray, bounds, *, maxiter: int, gtol: float, maxls: int,
+                       ftol: float = 2.220446049250313e-09, maxcor: int = 10, maxfun: int = 15000):
+  """The loop of `scipy.optimize._lbfgsb_py._minimize_lbfgsb` around the same compiled `setulb` routine as a
+  GENERATOR: it yields the point it wants evaluated and is sent back (loss, gradient); its return value
+  (StopIteration.value) is (x, f).  Identical iterates and results to `scipy.optimize.minimize`, without the
+  per-evaluation Python layers (ScalarFunction wrappers, OptimizeResult per iteration).  The reverse-
+  communication form is what lets several restarts advance in lock step, one batched device evaluation per
+  round (`_lockstep`).  All bounds must be finite (they are: param_bounds)."""
   n, m = x0.shape[0], maxcor
   low = np.array([b[0] for b in bounds], np.float64)
   up = np.array([b[1] for b in bounds], np.float64)
@@ -75,7 +76,7 @@ def _lean_lbfgsb(fun, x0: np.ndarray, bounds, *, maxiter: int, gtol: float, maxl
   while True:
     _setulb(m, x, low, up, nbd, f, g, factr, gtol, wa, iwa, task, lsave, isave, dsave, maxls, ln_task)
     if task[0] == 3:
-      fv, gv = fun(x)
+      fv, gv = yield x
       nfev += 1
       f = np.array(fv, dtype=np.float64)
       g = np.asarray(gv, np.float64)
@@ -88,6 +89,41 @@ def _lean_lbfgsb(fun, x0: np.ndarray, bounds, *, maxiter: int, gtol: float, maxl
     else:
       break
   return x, float(f)
+
+
+def _lean_lbfgsb(fun, x0: np.ndarray, bounds, **kw):
+  """One restart driven to completion with `fun(x) -> (loss, gradient)`."""
+  steps = _lean_lbfgsb_steps(x0, bounds, **kw)
+  try:
+    x = next(steps)
+    while True:
+      x = steps.send(fun(x))
+  except StopIteration as done:
+    return done.value
+
+
+def _lockstep(batch_fn, inits, bounds, **kw):
+  """All restarts at once: every round collects the point each unfinished restart asks for and evaluates
+  them with ONE call of `batch_fn(indices, points) -> (losses, grads)` (one CUDA graph launch for all
+  restarts, gp.DeviceGP.make_batch_loss_fn).  Each restart's sequence of iterates is exactly the one it
+  would have had alone."""
+  gens = [_lean_lbfgsb_steps(np.asarray(t0, np.float64), bounds, **kw) for t0 in inits]
+  pending, results = {}, {}
+  for i, gen in enumerate(gens):
+    try:
+      pending[i] = next(gen)
+    except StopIteration as done:
+      results[i] = done.value
+  while pending:
+    idx = sorted(pending)
+    losses, grads = batch_fn(idx, [pending[i] for i in idx])
+    for k, i in enumerate(idx):
+      try:
+        pending[i] = gens[i].send((losses[k], grads[k]))
+      except StopIteration as done:
+        results[i] = done.value
+        del pending[i]
+  return [results[i] for i in range(len(gens))]
 
 
 def log_uniform_init(rng: np.random.Generator, dc: int, dk: int, n: int) -> np.ndarray:
@@ -123,6 +159,14 @@ class ScipyLbfgsB:
 
   def __call__(self, init_thetas: np.ndarray, loss_and_grad, bounds, best_n: int = 1):
     inits = np.atleast_2d(init_thetas)
+    if hasattr(loss_and_grad, 'n_restarts') and _setulb is not None and loss_and_grad.n_restarts >= inits.shape[0]:
+      # batched device evaluation: the restarts advance in lock step, one graph launch per round
+      results = _lockstep(loss_and_grad, inits, bounds, maxiter=self.options.maxiter, gtol=self.options.tol,
+                          maxls=self.options.num_line_search_steps)
+      finals = [r[0] for r in results]
+      losses = np.asarray([r[1] for r in results])
+      order = np.argsort(losses, kind='stable')[:max(1, best_n)]
+      return [finals[i] for i in order], losses
     fns = list(loss_and_grad) if isinstance(loss_and_grad, (list, tuple)) else [loss_and_grad]
     if len(fns) == 1 or inits.shape[0] == 1:
       results = [self._one(fns[0], t0, bounds) for t0 in inits]
@@ -172,6 +216,25 @@ def loss_functions(dev: gp.DeviceGP, xt, yt, zt, dc: int, dk: int, n_valid: Opti
   return [d.make_loss_fn(xt, yt, zt, n_valid) for d in devs]
 
 
+def batch_loss_function(dev: gp.DeviceGP, xt, yt, zt, restarts: int, n_valid: Optional[int] = None):
+  """One batched loss/gradient callable for `restarts` concurrent evaluations (worker handles cached on
+  `dev`, as in `loss_functions`), each with an equal share of the dataflow factorisation's CTA slots."""
+  pool = getattr(dev, '_ard_workers', None)
+  if pool is None:
+    pool = []
+    dev._ard_workers = pool  # pylint: disable=protected-access
+  while len(pool) < restarts - 1:
+    pool.append(gp.DeviceGP(dev.device.index))
+  devs = [dev] + pool[:restarts - 1]
+  share = max(16, 288 // len(devs) - 1) if len(devs) > 1 else 0
+  for d in devs:
+    d.set_int('dataflow_ctas', share)
+  return gp.DeviceGP.make_batch_loss_fn(devs, xt, yt, zt, n_valid)
+
+
+BATCHED_ARD = True   # restarts in lock step on one graph launch per round (N > 64); False: one host thread per restart
+
+
 def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,
              random_restarts: int = DEFAULT_RANDOM_RESTARTS, ensemble_size: int = 1,
              optimizer: Optional[ScipyLbfgsB] = None, n_valid: Optional[int] = None,
@@ -196,7 +259,10 @@ def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,
   dk = 0 if zt is None else zt.shape[1]
   lo, hi = gp.param_bounds(dc, dk)
   inits = log_uniform_init(rng, dc, dk, random_restarts)
-  fns = loss_functions(dev, xt, yt, zt, dc, dk, n_valid, workers=min(workers, random_restarts))
+  if BATCHED_ARD and _setulb is not None and xt.shape[0] > 64 and 1 < random_restarts <= 16 and workers > 1:
+    fns = batch_loss_function(dev, xt, yt, zt, random_restarts, n_valid)
+  else:
+    fns = loss_functions(dev, xt, yt, zt, dc, dk, n_valid, workers=min(workers, random_restarts))
   try:
     best, losses = optimizer(inits, fns, list(zip(lo, hi)), best_n=ensemble_size)
   finally:

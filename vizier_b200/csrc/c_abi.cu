@@ -299,6 +299,70 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
   return bad ? 1 : 0;
 }
 
+// loss and gradient from the device sums (regularisers: tuned_gp_models.py:167,180,192,269 ->
+// 0.01 log(x/c)^2, derivative 0.02 log(x/c) / x).  hostg: [Dk cat | Dc cont | trace | sum G K].
+static void finish_loss(const vzgp_params* p, int Dc, int Dk, int n_valid, int n_metrics, double half_logdet_plus_quad,
+                        const double* hostg, double* loss_out, double* grad_out) {
+  auto reg = [](double x, double c) { double l = std::log(x / c); return 0.01 * l * l; };
+  auto dreg = [](double x, double c) { return 0.02 * std::log(x / c) / x; };
+  const double sf2 = p->signal_variance, sn2 = p->observation_noise_variance;
+  double loss = half_logdet_plus_quad + 0.5 * n_metrics * n_valid * std::log(2.0 * M_PI);
+  loss += reg(sf2, 0.039) + reg(sn2, 0.0039);
+  for (int k = 0; k < Dk; ++k) {
+    const double l = p->categorical_length_scale_squared[k];
+    loss += reg(l, 0.5);
+    grad_out[k] = -0.5 * hostg[k] / (l * l) + dreg(l, 0.5);
+  }
+  for (int d = 0; d < Dc; ++d) {
+    const double l = p->continuous_length_scale_squared[d];
+    loss += reg(l, 0.5);
+    grad_out[Dk + d] = -0.5 * hostg[Dk + d] / (l * l) + dreg(l, 0.5);
+  }
+  grad_out[Dk + Dc] = 0.5 * hostg[Dk + Dc] + dreg(sn2, 0.0039);
+  grad_out[Dk + Dc + 1] = 0.5 * hostg[Dk + Dc + 1] / sf2 + dreg(sf2, 0.039);
+  *loss_out = loss;
+}
+
+// ---------------------------------------------------------------------------
+// R evaluations (the ARD restarts, one handle each) as ONE graph launch: the R launch sequences are captured
+// as parallel branches (fork / join by events on the handles' streams), each ending with the copies of its
+// results into that handle's pinned host block.  One cudaGraphLaunch + one synchronisation per round of the
+// lock-step L-BFGS-B driver (ard.py) instead of R host threads contending for the driver lock.
+// ---------------------------------------------------------------------------
+constexpr int kMaxBatch = 16;
+struct BatchGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t nodes[kMaxBatch][3] = {};
+  cudaEvent_t fork = nullptr, join[kMaxBatch] = {};
+  const void* key_ptr[3] = {nullptr, nullptr, nullptr};
+  int key_dims[6] = {0, 0, 0, 0, 0, 0};          // N, dc, dk, n_valid, n_metrics, R
+  const vzgp_handle* hs[kMaxBatch] = {};
+  const void* bufs[kMaxBatch][kNllBufs] = {};
+  int launches = 0;
+};
+
+static void batch_drop(BatchGraph* b) {
+  if (b->exec) cudaGraphExecDestroy(b->exec);
+  if (b->graph) cudaGraphDestroy(b->graph);
+  b->exec = nullptr; b->graph = nullptr;
+}
+
+static void handle_bufs(vzgp_handle* h, const void** o) {
+  const DevBuf* b[kNllBufs] = {&h->X, &h->XT, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->small,
+                               &h->LinvT, &h->df_tasks[1], &h->df_flags, &h->df_S};
+  for (int q = 0; q < kNllBufs; ++q) o[q] = b[q]->ptr;
+}
+
+static int ensure_pinned(vzgp_handle* h, size_t bytes) {
+  if (h->pinned && h->pinned_bytes >= bytes) return 0;
+  if (h->pinned) cudaFreeHost(h->pinned);
+  h->pinned = nullptr; h->pinned_bytes = 0;
+  VZ_CUDA(cudaMallocHost(&h->pinned, bytes));
+  h->pinned_bytes = bytes;
+  return 0;
+}
+
 }  // namespace vzgp
 
 using namespace vzgp;
@@ -361,6 +425,12 @@ int vzgp_destroy(vzgp_handle* h) {
   }
   if (h->nll_exec) cudaGraphExecDestroy(h->nll_exec);
   if (h->nll_graph) cudaGraphDestroy(h->nll_graph);
+  if (h->batch) {
+    BatchGraph* b = static_cast<BatchGraph*>(h->batch);
+    batch_drop(b);
+    if (b->fork) { cudaEventDestroy(b->fork); for (int r = 0; r < kMaxBatch; ++r) cudaEventDestroy(b->join[r]); }
+    delete b;
+  }
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -530,26 +600,8 @@ int vzgp_nll_grad_multi(vzgp_handle* h, const double* X, const int32_t* Z, const
   VZ_ARG(h && loss_out && grad_out, "handle / outputs");
   VZ_ARG(n_metrics >= 1 && n_metrics <= kMaxMetrics, "1 <= n_metrics <= 8");
   Guard g(h->device);
-  // Regularisers: tuned_gp_models.py:167,180,192,269 -> 0.01*log(x/c)^2, derivative 0.02*log(x/c)/x.
-  auto reg = [](double x, double c) { double l = std::log(x / c); return 0.01 * l * l; };
-  auto dreg = [](double x, double c) { return 0.02 * std::log(x / c) / x; };
   auto finish = [&](double half_logdet_plus_quad, const double* hostg) {
-    const double sf2 = p->signal_variance, sn2 = p->observation_noise_variance;
-    double loss = half_logdet_plus_quad + 0.5 * n_metrics * n_valid * std::log(2.0 * M_PI);
-    loss += reg(sf2, 0.039) + reg(sn2, 0.0039);
-    for (int k = 0; k < Dk; ++k) {
-      const double l = p->categorical_length_scale_squared[k];
-      loss += reg(l, 0.5);
-      grad_out[k] = -0.5 * hostg[k] / (l * l) + dreg(l, 0.5);
-    }
-    for (int d = 0; d < Dc; ++d) {
-      const double l = p->continuous_length_scale_squared[d];
-      loss += reg(l, 0.5);
-      grad_out[Dk + d] = -0.5 * hostg[Dk + d] / (l * l) + dreg(l, 0.5);
-    }
-    grad_out[Dk + Dc] = 0.5 * hostg[Dk + Dc] + dreg(sn2, 0.0039);
-    grad_out[Dk + Dc + 1] = 0.5 * hostg[Dk + Dc + 1] / sf2 + dreg(sf2, 0.039);
-    *loss_out = loss;
+    finish_loss(p, Dc, Dk, n_valid, n_metrics, half_logdet_plus_quad, hostg, loss_out, grad_out);
   };
   static const bool small_ok = [] { const char* e = getenv("VZGP_NLL_SMALL"); return !(e && e[0] == '0'); }();
   if (N <= kBlk && small_ok && n_metrics == 1) {
@@ -1011,6 +1063,160 @@ int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_conf
   VZ_ARG(acq != nullptr, "acq");
   return eagle_run_impl(hs[0], nullptr, cfg, acq, nullptr, prior, prior_z, n_prior, cat_sizes, count, seed, best_x,
                         best_z, best_score, hs, E);
+}
+
+int vzgp_nll_grad_batch(vzgp_handle* const* hs, int R, const double* X, const int32_t* Z, const double* Y, int N,
+                        int Dc, int Dk, int n_valid, int n_metrics, const vzgp_params* ps, const uint8_t* active,
+                        double* loss_out, double* grad_out, int* status_out) {
+  VZ_ARG(hs && ps && loss_out && grad_out && status_out, "pointers");
+  VZ_ARG(R >= 1 && R <= kMaxBatch, "1 <= R <= 16");
+  VZ_ARG(N > kBlk, "the batched evaluation is for N > 64 (smaller studies: vzgp_nll_grad per restart)");
+  VZ_ARG(n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
+  VZ_ARG(n_metrics >= 1 && n_metrics <= kMaxMetrics, "1 <= n_metrics <= 8");
+  VZ_ARG(X != nullptr || Dc == 0, "X");
+  VZ_ARG(Z != nullptr || Dk == 0, "Z");
+  VZ_ARG(Y != nullptr, "Y");
+  for (int r = 0; r < R; ++r) {
+    VZ_ARG(hs[r] != nullptr && hs[r]->device == hs[0]->device, "handles must live on one device");
+    for (int q = 0; q < r; ++q) VZ_ARG(hs[q] != hs[r] && hs[q]->stream != hs[r]->stream, "handles need distinct streams");
+  }
+  vzgp_handle* lead = hs[0];
+  Guard g(lead->device);
+  const int np = round_up(N, kBlk), nq = Dc + Dk + 2;
+  const size_t res_bytes = sizeof(double) * (2 + nq) + sizeof(int) * 2;
+  if (!lead->batch) lead->batch = new BatchGraph();
+  BatchGraph* b = static_cast<BatchGraph*>(lead->batch);
+  KernelParams kps[kMaxBatch];
+  for (int r = 0; r < R; ++r) VZ_TRY(fill_kernel_params(&ps[r], Dc, Dk, &kps[r]));
+  // ---- is the captured graph still valid? ----
+  bool hit = b->exec && b->key_ptr[0] == X && b->key_ptr[1] == Z && b->key_ptr[2] == Y && b->key_dims[0] == N &&
+             b->key_dims[1] == Dc && b->key_dims[2] == Dk && b->key_dims[3] == n_valid && b->key_dims[4] == n_metrics &&
+             b->key_dims[5] == R;
+  for (int r = 0; hit && r < R; ++r) {
+    const void* cur[kNllBufs];
+    handle_bufs(hs[r], cur);
+    hit = b->hs[r] == hs[r] && hs[r]->df_nb[1] == np / 64;
+    for (int q = 0; hit && q < kNllBufs; ++q) hit = cur[q] == b->bufs[r][q];
+  }
+  if (!hit) {
+    batch_drop(b);
+    if (!b->fork) {
+      VZ_CUDA(cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming));
+      for (int r = 0; r < kMaxBatch; ++r) VZ_CUDA(cudaEventCreateWithFlags(&b->join[r], cudaEventDisableTiming));
+    }
+    for (int r = 0; r < R; ++r) {
+      vzgp_handle* h = hs[r];
+      VZ_TRY(ensure_model_buffers(h, np, Dc, Dk, n_metrics));
+      VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));
+      VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)np * np));
+      VZ_TRY(chol_dataflow_prepare(h, np, true));
+      VZ_TRY(ensure_pinned(h, res_bytes));
+      h->fitted = false;
+      h->n = N; h->np = np; h->dc = Dc; h->dk = Dk; h->n_valid = n_valid; h->n_metrics = n_metrics;
+      VZ_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    const int64_t l0[kMaxBatch] = {};
+    int64_t before[kMaxBatch];
+    for (int r = 0; r < R; ++r) before[r] = hs[r]->launches;
+    (void)l0;
+    if (cudaStreamBeginCapture(lead->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); set_error("batch capture refused"); return VZGP_ERR_CUDA; }
+    int st = 0;
+    cudaEventRecord(b->fork, lead->stream);
+    for (int r = 1; r < R; ++r) cudaStreamWaitEvent(hs[r]->stream, b->fork, 0);
+    for (int r = 0; r < R && st >= 0; ++r) {
+      vzgp_handle* h = hs[r];
+      st = nll_sequence(h, X, Z, Y, N, Dc, Dk, n_valid, kps[r], ps[r].observation_noise_variance, n_metrics);
+      if (st < 0) break;
+      char* pin = static_cast<char*>(h->pinned);
+      cudaMemcpyAsync(pin, h->small.as<char>() + kOffLogdet, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream);
+      cudaMemcpyAsync(pin + 16, h->small.as<char>() + kOffGrad, sizeof(double) * nq, cudaMemcpyDeviceToHost, h->stream);
+      cudaMemcpyAsync(pin + 16 + sizeof(double) * nq, h->small.as<char>() + kOffFlag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+      if (r > 0) { cudaEventRecord(b->join[r], h->stream); cudaStreamWaitEvent(lead->stream, b->join[r], 0); }
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(lead->stream, &graph);
+    b->launches = 0;
+    for (int r = 0; r < R; ++r) { b->launches += (int)(hs[r]->launches - before[r]); hs[r]->launches = before[r]; }
+    if (st < 0 || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      if (st >= 0) set_error("batch capture failed: %s", cudaGetErrorString(ce));
+      cudaGetLastError();
+      return st < 0 ? st : VZGP_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); set_error("cudaGraphInstantiate (batch)"); return VZGP_ERR_CUDA; }
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    std::vector<cudaGraphNode_t> nodes(nn);
+    cudaGraphGetNodes(graph, nodes.data(), &nn);
+    const void* want[3] = {kernel_matrix_func(), transpose_scale_func(), nll_grad_tiles_func()};
+    const int id_arg[3] = {6, 4, 5};       // output / workspace pointer that tells the R branches apart
+    for (int r = 0; r < R; ++r) for (int q = 0; q < 3; ++q) b->nodes[r][q] = nullptr;
+    for (size_t i = 0; i < nn; ++i) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      cudaKernelNodeParams kpar;
+      if (cudaGraphKernelNodeGetParams(nodes[i], &kpar) != cudaSuccess) continue;
+      for (int q = 0; q < 3; ++q) {
+        if (kpar.func != want[q]) continue;
+        const void* idp = *static_cast<const void* const*>(kpar.kernelParams[id_arg[q]]);
+        for (int r = 0; r < R; ++r) {
+          const void* mine = q == 0 ? hs[r]->Kws.ptr : (q == 1 ? hs[r]->XT.ptr : hs[r]->Kinv.ptr);
+          if (idp == mine) b->nodes[r][q] = nodes[i];
+        }
+      }
+    }
+    cudaGetLastError();
+    for (int r = 0; r < R; ++r)
+      if (!b->nodes[r][0] || (Dc > 0 && !b->nodes[r][1]) || !b->nodes[r][2]) {
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        set_error("batch graph: kernel nodes of restart %d not found", r);
+        return VZGP_ERR_CUDA;
+      }
+    b->graph = graph; b->exec = exec;
+    b->key_ptr[0] = X; b->key_ptr[1] = Z; b->key_ptr[2] = Y;
+    b->key_dims[0] = N; b->key_dims[1] = Dc; b->key_dims[2] = Dk; b->key_dims[3] = n_valid; b->key_dims[4] = n_metrics; b->key_dims[5] = R;
+    for (int r = 0; r < R; ++r) { b->hs[r] = hs[r]; handle_bufs(hs[r], b->bufs[r]); }
+  }
+  // ---- this round's hyper-parameters, launch, wait ----
+  const int arg_idx[3] = {kKernelMatrixKpArg, kTransposeScaleKpArg, kNllGradTilesKpArg};
+  const int arg_cnt[3] = {kKernelMatrixArgs, kTransposeScaleArgs, kNllGradTilesArgs};
+  double sn2s[kMaxBatch];
+  for (int r = 0; r < R; ++r) {
+    if (active && !active[r]) continue;
+    sn2s[r] = ps[r].observation_noise_variance;
+    hs[r]->kp = kps[r]; hs[r]->sn2 = sn2s[r]; hs[r]->fitted = false;
+    for (int q = 0; q < 3; ++q) {
+      if (!b->nodes[r][q]) continue;
+      cudaKernelNodeParams kpar;
+      VZ_CUDA(cudaGraphKernelNodeGetParams(b->nodes[r][q], &kpar));
+      void* args[16];
+      for (int a2 = 0; a2 < arg_cnt[q]; ++a2) args[a2] = kpar.kernelParams[a2];
+      args[arg_idx[q]] = &kps[r];
+      if (q == 0) args[kKernelMatrixDiagArg] = &sn2s[r];
+      kpar.kernelParams = args;
+      VZ_CUDA(cudaGraphExecKernelNodeSetParams(b->exec, b->nodes[r][q], &kpar));
+    }
+  }
+  VZ_CUDA(cudaGraphLaunch(b->exec, lead->stream));
+  lead->launches += b->launches;
+  VZ_CUDA(cudaStreamSynchronize(lead->stream));
+  for (int r = 0; r < R; ++r) {
+    status_out[r] = 0;
+    if (active && !active[r]) continue;
+    const char* pin = static_cast<const char*>(hs[r]->pinned);
+    const double* h2 = reinterpret_cast<const double*>(pin);
+    const double* hg = reinterpret_cast<const double*>(pin + 16);
+    const int bad = *reinterpret_cast<const int*>(pin + 16 + sizeof(double) * nq);
+    if (!bad) {
+      finish_loss(&ps[r], Dc, Dk, n_valid, n_metrics, h2[1] + h2[0], hg, loss_out + r, grad_out + (size_t)r * nq);
+    } else {
+      // a pivot failed without jitter: this restart alone takes the path with the retry loop
+      status_out[r] = vzgp_nll_grad_multi(hs[r], X, Z, Y, N, Dc, Dk, n_valid, n_metrics, &ps[r], loss_out + r, grad_out + (size_t)r * nq);
+      if (status_out[r] < 0) return status_out[r];
+    }
+  }
+  return 0;
 }
 
 int vzgp_posterior(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, int add_noise,

@@ -154,6 +154,7 @@ struct vzgp_handle {
   int nll_key_dims[5] = {0, 0, 0, 0, 0};                         // N, dc, dk, n_valid, n_metrics
   const void* nll_bufs[kNllBufsDecl] = {};                                 // handle buffers the graph points into (a growth reallocates them)
   int nll_launches = 0;
+  void* batch = nullptr;   // BatchGraph (c_abi.cu): this handle leads a batch of concurrent evaluations
 
   // Dataflow factorisation (dataflow.cu): task list for the current nb, flags, chain partial sums.
   vzgp::DevBuf df_tasks[2], df_flags, df_S;     // task lists without / with the K_y^-1 tasks

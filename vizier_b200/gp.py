@@ -383,6 +383,64 @@ class DeviceGP:
 
     return f
 
+  @staticmethod
+  def make_batch_loss_fn(devs: Sequence['DeviceGP'], x, y, z=None, n_valid=None):
+    """(indices, thetas) -> (losses, grads) for the restarts of one ARD fit: restart i is evaluated on
+    `devs[i]`, all of them in ONE graph launch (`vzgp_nll_grad_batch`).  `indices` are the restarts still
+    running, `thetas[k]` the point of restart indices[k] (to_vector order).  Non-finite losses come back as
+    (1e300, 0) like `make_loss_fn`."""
+    lead = devs[0]
+    r_all = len(devs)
+    xt, zt = lead._xz(x, z)
+    n, dc = xt.shape
+    yt, n_metrics = lead._labels(y, n)
+    for d in devs[1:]:   # the inputs were produced on torch's current stream: every branch stream waits for them
+      d._stream.wait_stream(torch.cuda.current_stream(d.device))
+    dk = 0 if zt is None else zt.shape[1]
+    nv = n if n_valid is None else n_valid
+    nq = dc + dk + 2
+    ls_c = np.zeros((r_all, max(dc, 1)), np.float64)
+    ls_k = np.zeros((r_all, max(dk, 1)), np.float64)
+    params = (_lib.Params * r_all)()
+    for r in range(r_all):
+      params[r].continuous_length_scale_squared = ls_c[r].ctypes.data_as(C.POINTER(C.c_double))
+      params[r].categorical_length_scale_squared = ls_k[r].ctypes.data_as(C.POINTER(C.c_double)) if dk else None
+      params[r].signal_variance = 1.0
+      params[r].observation_noise_variance = 1.0
+      ls_c[r, :] = 1.0
+      ls_k[r, :] = 1.0
+    handles = (C.c_void_p * r_all)(*[d._h for d in devs])
+    active = np.zeros(r_all, np.uint8)
+    losses = np.zeros(r_all, np.float64)
+    grads = np.zeros((r_all, nq), np.float64)
+    status = (C.c_int * r_all)()
+    fn = lead._lib.vzgp_nll_grad_batch
+    keep = (xt, zt, yt, ls_c, ls_k, params, handles, active, losses, grads, status, list(devs))
+
+    def f(indices, thetas, _keep=keep):
+      active[:] = 0
+      for i, theta in zip(indices, thetas):
+        theta = np.asarray(theta, np.float64)
+        ls_k[i, :dk] = theta[:dk]
+        ls_c[i, :dc] = theta[dk:dk + dc]
+        params[i].observation_noise_variance = float(theta[dk + dc])
+        params[i].signal_variance = float(theta[dk + dc + 1])
+        active[i] = 1
+      _lib.check('vzgp_nll_grad_batch', fn(
+          handles, r_all, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, nv, n_metrics, params,
+          active.ctypes.data_as(C.POINTER(C.c_uint8)), losses.ctypes.data_as(C.POINTER(C.c_double)),
+          grads.ctypes.data_as(C.POINTER(C.c_double)), status))
+      out_l, out_g = [], []
+      for i in indices:
+        if np.isfinite(losses[i]):
+          out_l.append(float(losses[i])); out_g.append(grads[i].copy())
+        else:
+          out_l.append(1e300); out_g.append(np.zeros(nq))
+      return out_l, out_g
+
+    f.n_restarts = r_all
+    return f
+
   def score(self, xs, acq: Acquisition, zs=None, with_aux: bool = False, out: Optional[dict] = None) -> dict:
     """Asynchronous on self.stream; returns device tensors {'score', ['mean','stddev','linf_distance']}."""
     xst, zst = self._xz(xs, zs)
