@@ -195,6 +195,23 @@ class ScipyLbfgsB:
 MAX_ARD_WORKERS = 8
 
 
+def _cta_share(n_concurrent: int) -> int:
+  """Worker CTAs of the dataflow factorisation per concurrent evaluation (0 = every slot, a lone evaluation).
+  The persistent CTAs of k_chol_dataflow fill an SM's shared memory and registers two by two; the small kernels
+  around the factorisation (kernel matrix, alpha solve, gradient tiles) of the OTHER evaluations need somewhere
+  to run meanwhile, so the restarts together take only part of the 2 x 148 slots."""
+  import os
+  if n_concurrent <= 1:
+    return 0
+  env = os.environ.get('VZGP_ARD_SHARE')
+  if env:
+    return int(env)
+  return max(16, ARD_SLOT_BUDGET // n_concurrent - 1)
+
+
+ARD_SLOT_BUDGET = 192
+
+
 def loss_functions(dev: gp.DeviceGP, xt, yt, zt, dc: int, dk: int, n_valid: Optional[int] = None,
                    workers: int = MAX_ARD_WORKERS):
   """One loss/gradient callable per worker handle (the designer's own handle first; extra handles on
@@ -209,7 +226,7 @@ def loss_functions(dev: gp.DeviceGP, xt, yt, zt, dc: int, dk: int, n_valid: Opti
   devs = [dev] + pool[:workers - 1]
   # The evaluations of the restarts run concurrently, one dataflow-factorisation launch each: an equal
   # share of the 2 x 148 resident CTA slots keeps all of them on the GPU at once (csrc/dataflow.cu).
-  share = max(16, 288 // len(devs) - 1) if len(devs) > 1 else 0
+  share = _cta_share(len(devs))
   for d in devs:
     d.set_int('dataflow_ctas', share)
 
@@ -226,7 +243,7 @@ def batch_loss_function(dev: gp.DeviceGP, xt, yt, zt, restarts: int, n_valid: Op
   while len(pool) < restarts - 1:
     pool.append(gp.DeviceGP(dev.device.index))
   devs = [dev] + pool[:restarts - 1]
-  share = max(16, 288 // len(devs) - 1) if len(devs) > 1 else 0
+  share = _cta_share(len(devs))
   for d in devs:
     d.set_int('dataflow_ctas', share)
   return gp.DeviceGP.make_batch_loss_fn(devs, xt, yt, zt, n_valid)

@@ -158,6 +158,6 @@ struct vzgp_handle {
 
   // Dataflow factorisation (dataflow.cu): task list for the current nb, flags, chain partial sums.
   vzgp::DevBuf df_tasks[2], df_flags, df_S;     // task lists without / with the K_y^-1 tasks
-  int df_nb[2] = {0, 0}, df_ntasks[2] = {0, 0};
+  int df_nb[2] = {0, 0}, df_ntasks[2] = {0, 0}, df_ncrit[2] = {0, 0};
   int df_ctas = 0;                              // worker CTAs per launch (0: all slots); vzgp_set_int
 };

@@ -77,12 +77,14 @@ struct DfArgs {
   double* Y;
   double* S;        // [nb][2][64*64] partial sums for the chain
   double* Kinv;     // lower tiles of K_y^-1, or nullptr
-  int* ctrl;        // [0] ticket counter, [1] timeout marker
+  int* ctrl;        // [0] tickets of the normal queue, [1] timeout marker, [2] tickets of the critical queue, [3] chain election
   int* flagL;       // [nb*nb] tile (i,j) of L final ((j,j): also Linv_jj in X and Y)
   int* flagY;       // [nb*nb] tile (j,i), j < i, of Y (and X[i,j]) final
   int* flagS;       // [nb*2]
-  const int4* tasks;
+  const int4* tasks;   // normal queue, in schedule order: (type, i, j, key)
   int ntasks;
+  const int4* crit;    // critical queue (the PART tasks the chain waits for): (type, i, j, need)
+  int ncrit;
   int np, nb;
   int* bad;         // raised on a non-positive / non-finite pivot
 };
@@ -526,20 +528,46 @@ __device__ void df_worker(const DfArgs& a, const int4 task, double* sm, uint64_t
   }
 }
 
+// Next task for a worker CTA (one thread calls it).  Two queues: the PART tasks feed the chain directly and
+// jump the line - but a critical task is handed out only once every normal task it depends on has been
+// handed out (crit.w = how many normal tickets that takes), so whoever holds a task only ever waits for
+// tasks that are already held by running CTAs (or for the chain, which only waits for critical tasks whose
+// last dependency is held by a CTA that does not wait for that chain step): no deadlock whatever the number
+// of resident CTAs.  Returns type -1 when both queues are exhausted.
+__device__ int4 df_next_task(const DfArgs& a) {
+  for (;;) {
+    const int c = *reinterpret_cast<volatile int*>(a.ctrl + 2);
+    if (c < a.ncrit) {
+      const int4 ct = a.crit[c];
+      if (*reinterpret_cast<volatile int*>(a.ctrl) >= ct.w) {
+        if (atomicCAS(a.ctrl + 2, c, c + 1) == c) return ct;
+        continue;
+      }
+    }
+    if (*reinterpret_cast<volatile int*>(a.ctrl) < a.ntasks) {
+      const int t = atomicAdd(a.ctrl, 1);
+      if (t < a.ntasks) return a.tasks[t];
+    } else if (c >= a.ncrit) {
+      return make_int4(-1, 0, 0, 0);
+    }
+    // normal queue exhausted, critical tasks left: their needs are met now, take them on the next turn
+  }
+}
+
 __global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const DfArgs a) {
   extern __shared__ double smem_raw[];
   double* sm = smem_raw + (((1024u - (static_cast<unsigned>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u) >> 3);
-  __shared__ int s_ticket;
+  __shared__ int4 s_task;
+  __shared__ int s_chain;
   __shared__ uint64_t bars[2 * kDfStages];
   const int tid = threadIdx.x;
   if (tid == 0) {
-    s_ticket = atomicAdd(a.ctrl, 1);
+    s_chain = atomicAdd(a.ctrl + 3, 1) == 0 ? 1 : 0;     // the first CTA to arrive runs the chain
     for (int s = 0; s < kDfStages; ++s) { mbar_init(bars + s, 32); mbar_init(bars + kDfStages + s, kDfMath / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  int ticket = s_ticket;
-  if (ticket == 0) {
+  if (s_chain) {
     __shared__ uint64_t chain_bars[2];
     if (tid == 0) {
       mbar_init(chain_bars, 32);
@@ -550,17 +578,15 @@ __global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const DfArgs a)
     df_chain(a, sm, chain_bars);
     return;
   }
-  // Persistent worker: tasks in ticket order until the list is exhausted.  A CTA holds one task at a time
-  // and takes the next ticket only when it is done, so the lowest unfinished task is always held by a
-  // running CTA whatever the number of resident CTAs (see the header comment).
+  // Persistent worker: one task at a time until both queues are exhausted.
   unsigned slab = 0;     // ring position, carried across tasks (same sequence on producer and consumers)
-  while (ticket - 1 < a.ntasks) {
-    const int4 task = a.tasks[ticket - 1];
-    df_worker(a, task, sm, bars, bars + kDfStages, slab);
-    __syncthreads();                                   // everybody has read s_ticket and finished the task
-    if (tid == 0) s_ticket = atomicAdd(a.ctrl, 1);
+  for (;;) {
+    if (tid == 0) s_task = df_next_task(a);
     __syncthreads();
-    ticket = s_ticket;
+    const int4 task = s_task;
+    if (task.x < 0) break;
+    df_worker(a, task, sm, bars, bars + kDfStages, slab);
+    __syncthreads();                                   // everybody has read s_task and finished the task
   }
   if (tid >= kDfMath && tid < kDfMath + 32) asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
@@ -570,13 +596,9 @@ __global__ void __launch_bounds__(kDfThreads, 2) k_chol_dataflow(const DfArgs a)
 // ---------------------------------------------------------------------------------------------------
 struct DfTaskHost { int key, type, i, j; };
 
-static void build_tasks(int nb, bool want_kinv, std::vector<int4>* out) {
+static void build_tasks(int nb, bool want_kinv, std::vector<int4>* normal, std::vector<int4>* critical) {
   std::vector<DfTaskHost> t;
   // time of chain step j = 2j; a task's key = time after which its last input exists
-  for (int j = 1; j < nb; ++j) {
-    t.push_back({2 * j - 1, DF_PART, j, j - 1});
-    t.push_back({2 * j - 1, DF_PART, j, j});
-  }
   for (int j = 0; j < nb; ++j)
     for (int i = j + 2; i < nb; ++i) t.push_back({2 * j + 1, DF_TILE, i, j});
   for (int i = 1; i < nb; ++i)
@@ -586,10 +608,21 @@ static void build_tasks(int nb, bool want_kinv, std::vector<int4>* out) {
       for (int j = 0; j <= i; ++j) t.push_back({2 * nb + 1, DF_KINV, i, j});
   std::stable_sort(t.begin(), t.end(), [](const DfTaskHost& x, const DfTaskHost& y) {
     if (x.key != y.key) return x.key < y.key;
-    return x.type < y.type;           // PART before TILE before LINV inside one step; then insertion order
+    return x.type < y.type;           // TILE before LINV inside one step; then insertion order
   });
-  out->clear();
-  for (const auto& e : t) out->push_back(make_int4(e.type, e.i, e.j, e.key));
+  normal->clear();
+  for (const auto& e : t) normal->push_back(make_int4(e.type, e.i, e.j, e.key));
+  // Critical queue: PART(j, w) in the order the chain consumes them.  Its last normal dependency is
+  // TILE(j, j-2) (L[j, j-2]; the other inputs come earlier in the schedule or from the chain itself).
+  critical->clear();
+  for (int j = 1; j < nb; ++j) {
+    int need = 0;
+    if (j >= 2)
+      for (size_t q = 0; q < normal->size(); ++q)
+        if ((*normal)[q].x == DF_TILE && (*normal)[q].y == j && (*normal)[q].z == j - 2) { need = (int)q + 1; break; }
+    critical->push_back(make_int4(DF_PART, j, j - 1, need));
+    critical->push_back(make_int4(DF_PART, j, j, need));
+  }
 }
 
 static bool df_enabled() {
@@ -605,12 +638,16 @@ int chol_dataflow_prepare(vzgp_handle* h, int np, bool want_kinv) {
   if (nb < 2 || nb > 256) return 1;
   const int w = want_kinv ? 1 : 0;
   if (h->df_nb[w] != nb) {
-    std::vector<int4> tasks;
-    build_tasks(nb, want_kinv, &tasks);
-    VZ_TRY(h->df_tasks[w].reserve(sizeof(int4) * (tasks.size() + 1)));
-    VZ_CUDA(cudaMemcpyAsync(h->df_tasks[w].ptr, tasks.data(), sizeof(int4) * tasks.size(), cudaMemcpyHostToDevice, h->stream));
-    VZ_CUDA(cudaStreamSynchronize(h->stream));   // `tasks` goes out of scope
+    std::vector<int4> tasks, crit;
+    build_tasks(nb, want_kinv, &tasks, &crit);
+    // one buffer: [normal queue | critical queue]
+    VZ_TRY(h->df_tasks[w].reserve(sizeof(int4) * (tasks.size() + crit.size() + 1)));
+    int4* d = h->df_tasks[w].as<int4>();
+    VZ_CUDA(cudaMemcpyAsync(d, tasks.data(), sizeof(int4) * tasks.size(), cudaMemcpyHostToDevice, h->stream));
+    VZ_CUDA(cudaMemcpyAsync(d + tasks.size(), crit.data(), sizeof(int4) * crit.size(), cudaMemcpyHostToDevice, h->stream));
+    VZ_CUDA(cudaStreamSynchronize(h->stream));   // the vectors go out of scope
     h->df_ntasks[w] = (int)tasks.size();
+    h->df_ncrit[w] = (int)crit.size();
     h->df_nb[w] = nb;
   }
   const size_t nflags = 8 + 2 * (size_t)nb * nb + 2 * (size_t)nb;
@@ -633,6 +670,7 @@ int chol_dataflow(vzgp_handle* h, double* L, double* Linv, double* LinvT, double
   int* f = h->df_flags.as<int>();
   a.ctrl = f; a.flagL = f + 8; a.flagY = a.flagL + nb * nb; a.flagS = a.flagY + nb * nb;
   a.tasks = h->df_tasks[want_kinv ? 1 : 0].as<int4>(); a.ntasks = h->df_ntasks[want_kinv ? 1 : 0];
+  a.crit = a.tasks + a.ntasks; a.ncrit = h->df_ncrit[want_kinv ? 1 : 0];
   a.np = np; a.nb = nb; a.bad = flag;
   VZ_CUDA(cudaMemsetAsync(f, 0, sizeof(int) * nflags, h->stream));
   // Worker CTAs per launch.  A lone factorisation (the fit, a single evaluation) may take every slot
@@ -642,7 +680,7 @@ int chol_dataflow(vzgp_handle* h, double* L, double* Linv, double* LinvT, double
   static const int env_cap = [] { const char* e = getenv("VZGP_DF_CTAS"); return e ? atoi(e) : 0; }();
   int cap = h->df_ctas > 0 ? h->df_ctas : (env_cap > 0 ? env_cap : 2 * h->sm_count - 8);
   if (cap < 8) cap = 8;
-  const int workers = a.ntasks < cap ? a.ntasks : cap;
+  const int workers = a.ntasks + a.ncrit < cap ? a.ntasks + a.ncrit : cap;
   k_chol_dataflow<<<1 + workers, kDfThreads, kDfSmemBytes, h->stream>>>(a);
   VZ_CHECK_LAUNCH();
   h->launches++;
