@@ -163,39 +163,65 @@ def _host_cores():
     return os.cpu_count() or 1
 
 
-def cpu_oracle_rate(reps, n=N_TRIALS, d=DIM, rows_per_worker=512):
-  """Oracle (NumPy/SciPy) candidates/s on a bounded sample of the workload with EVERY host core busy: the
-  sample is `cores` chunks of `rows_per_worker` candidates, one chunk per worker thread (NumPy/LAPACK
-  release the GIL), BLAS pinned to one thread per worker so the workers do not oversubscribe.
-  Returns (candidates/s, seconds per pass, workers used, sample size)."""
-  from concurrent.futures import ThreadPoolExecutor
-  from oracle import gp_oracle as go
-  x, y, th = make_problem(n, d)
-  params = go.GPParams(th['sf2'], th['ls2'], th['sn2'])
-  pred = go.precompute_predictive(params, x, y)
-  cores = _host_cores()
-  sample = cores * rows_per_worker
-  rng = np.random.default_rng(1)
-  xs = rng.uniform(size=(sample, d))
-  chunks = [xs[i:i + rows_per_worker] for i in range(0, sample, rows_per_worker)]
+_CPU_PRED = None
 
-  def work(c):
-    return go.score_with_aux(pred, c)[0]
 
+def _cpu_worker_init(n, d):
+  """Worker process of the CPU arm: BLAS pinned to one thread, the oracle's predictive built once."""
+  global _CPU_PRED
+  for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+    os.environ[k] = '1'
   try:
     from threadpoolctl import threadpool_limits
-    limiter = threadpool_limits(limits=1, user_api='blas')
+    threadpool_limits(limits=1, user_api='blas')
   except Exception:  # pylint: disable=broad-except
-    limiter = None
-  with ThreadPoolExecutor(max_workers=cores) as ex:
-    list(ex.map(work, chunks))  # warm-up
+    pass
+  from oracle import gp_oracle as go
+  x, y, th = make_problem(n, d)
+  _CPU_PRED = go.precompute_predictive(go.GPParams(th['sf2'], th['ls2'], th['sn2']), x, y)
+
+
+def _cpu_worker(chunk):
+  from oracle import gp_oracle as go
+  return float(np.sum(go.score_with_aux(_CPU_PRED, chunk)[0]))
+
+
+class CpuArm:
+  """The oracle (NumPy/SciPy) on EVERY host core: one worker PROCESS per core (spawned: no GIL, no allocator
+  lock shared between workers, no CUDA state), BLAS pinned to one thread per worker.  A pass scores a bounded
+  sample of the workload, `cores` chunks of `rows_per_worker` candidates; pool start-up and one warm-up pass
+  happen in __enter__, outside every timed pass."""
+
+  def __init__(self, n=N_TRIALS, d=DIM, rows_per_worker=512):
+    self.n, self.d, self.rows = n, d, rows_per_worker
+    self.cores = _host_cores()
+    self.sample = self.cores * rows_per_worker
+    xs = np.random.default_rng(1).uniform(size=(self.sample, d))
+    self.chunks = [xs[i:i + rows_per_worker] for i in range(0, self.sample, rows_per_worker)]
+
+  def __enter__(self):
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    self.ex = ProcessPoolExecutor(max_workers=self.cores, mp_context=mp.get_context('spawn'),
+                                  initializer=_cpu_worker_init, initargs=(self.n, self.d))
+    list(self.ex.map(_cpu_worker, self.chunks))   # every worker imports, builds its predictive, scores once
+    return self
+
+  def __exit__(self, *exc):
+    self.ex.shutdown()
+
+  def one_pass(self):
+    """Seconds for one pass over the sample."""
     t0 = time.perf_counter()
-    for _ in range(reps):
-      list(ex.map(work, chunks))
-    dt = (time.perf_counter() - t0) / reps
-  if limiter is not None:
-    limiter.restore_original_limits()
-  return sample / dt, dt, min(cores, len(chunks)), sample
+    list(self.ex.map(_cpu_worker, self.chunks))
+    return time.perf_counter() - t0
+
+
+def cpu_oracle_rate(reps, n=N_TRIALS, d=DIM, rows_per_worker=512):
+  """(candidates/s, seconds per pass, workers used, sample size) of the CPU arm, `reps` timed passes."""
+  with CpuArm(n, d, rows_per_worker) as arm:
+    dt = float(np.mean([arm.one_pass() for _ in range(reps)]))
+    return arm.sample / dt, dt, min(arm.cores, len(arm.chunks)), arm.sample
 
 
 def cpu_suggest_oracle(x, y, budget_s=60.0):
@@ -249,20 +275,19 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  for _ in range(max(1, args.warmup)):
-    cpu_oracle_rate(1, rows_per_worker=128)
-  t_all, cand = 0.0, 0
-  for _ in range(args.steps):
-    r, dt, cores, sample = cpu_oracle_rate(1)
-    t_all += dt; cand += sample
-  v = cand / t_all
+  with CpuArm() as arm:
+    for _ in range(args.warmup):
+      arm.one_pass()
+    t_all = float(np.sum([arm.one_pass() for _ in range(args.steps)]))
+    cores, sample = min(arm.cores, len(arm.chunks)), arm.sample
+  v = sample * args.steps / t_all
   line = {
       'impl': 'reference', 'metric': 'GP-UCB candidates scored/sec', 'value': v, 'unit': 'candidates/s',
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_all / args.steps,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
       'config': {'workload': f'C2: GP posterior mu/var + UCB, N={N_TRIALS}, D={DIM}, M={M_POOL} (CPU arm: bounded sample of {sample} candidates per step)'},
       'cpu_baseline': {'value': v, 'unit': 'candidates/s', 'cores': cores, 'kind': 'port',
-                       'sample': f'{sample} candidates/step = {cores} worker threads x 512 rows, NumPy/SciPy oracle (reference JAX/TFP build unavailable)'},
+                       'sample': f'{sample} candidates/step = {cores} worker processes x 512 rows, NumPy/SciPy oracle (reference JAX/TFP build unavailable)'},
       'e2e': {'value': v, 'unit': 'candidates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
@@ -388,7 +413,7 @@ def run_gpu(args):
   torch.cuda.synchronize()
   sampler = ClockSampler(local)
   if rank == 0:
-    sampler.start()
+    if not args.no_cpu: sampler.start()
   l0 = dev.launch_count
   step_ev[0].record(stream)
   for i in range(args.steps):
@@ -523,11 +548,11 @@ def run_gpu(args):
       'gpu_launches': int(launches),
       'clocks': clocks,
   }
-  if world == 1 and args.workload == 'c2':
+  if world == 1 and args.workload == 'c2' and not args.no_cpu:
     cpu_v, cpu_dt, cores, sample = cpu_oracle_rate(3)
     line['cpu_baseline'] = {'value': cpu_v, 'unit': 'candidates/s', 'cores': cores, 'kind': 'port',
-                            'sample': f'{sample} candidates x 3 passes ({cpu_dt:.2f} s each): {cores} worker threads x 512 rows, '
-                                      'NumPy/SciPy oracle on the host'}
+                            'sample': f'{sample} candidates x 3 passes ({cpu_dt:.2f} s each): {cores} worker processes x 512 rows, '
+                                      'NumPy/SciPy oracle, one process per core'}
     if not args.no_suggest:
       try:
         line['suggest_e2e'] = suggest_e2e_leg(local)
@@ -546,6 +571,8 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
   ap.add_argument('--no-suggest', action='store_true', help='skip the suggest() end-to-end leg (N=1)')
+  ap.add_argument('--no-cpu', action='store_true',
+                  help='skip the cpu_baseline leg and everything that spawns processes (runs under ncu)')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
   if args.impl == 'reference':

@@ -51,6 +51,16 @@ typedef struct vzgp_params {
   double observation_noise_variance;  /* sigma_n^2  in [1e-10, 1]   */
   const double* continuous_length_scale_squared;  /* [Dc], in [1e-2, 1e2] */
   const double* categorical_length_scale_squared; /* [Dk] or NULL         */
+  /* The `linear_coef` variant (tuned_gp_models.py:203-245); linear_coef = 0 switches it off.  The kernel
+   * gains (coef*slope)^2 * sum_d (x_d/l_d - coef*shift)(x'_d/l_d - coef*shift) over the continuous features
+   * and the GP the constant mean coef*mean_constant.  With it the gradient vectors have 3 more entries, in
+   * jaxopt's sorted-key order: [cat ls2 | cont ls2 | linear_shift, linear_slope_amplitude, mean_fn | noise |
+   * signal].  Such models run the general launch sequences (no captured graph, no fused small-study or
+   * persistent Eagle kernels, explicit K* for the scoring). */
+  double linear_coef;
+  double linear_slope_amplitude;  /* in [1e-3, 10] */
+  double linear_shift;            /* unbounded */
+  double mean_constant;           /* unbounded */
 } vzgp_params;
 
 /* Acquisition + trust-region parameters (acquisitions.py:213-225, :152-174,
@@ -86,7 +96,7 @@ typedef struct vzgp_pe_params {
 } vzgp_pe_params;
 
 const char* vzgp_last_error(void);       /* thread-local message of the last failure */
-int vzgp_version(void);                  /* ABI version, currently 1 */
+int vzgp_version(void);                  /* ABI version, currently 2 (1: without the linear_* fields of vzgp_params) */
 int vzgp_device_count(void);
 
 /* device: CUDA ordinal.  stream: a cudaStream_t cast to void*, or NULL for a

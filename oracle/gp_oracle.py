@@ -52,6 +52,19 @@ REG_WEIGHT = 0.01
 
 
 @dataclasses.dataclass
+class LinearParams:
+  """The `linear_coef` variant (tuned_gp_models.py:203-245): the kernel gains
+  tfpk.Linear(slope_amplitude = coef * slope, shift = coef * shift) on the length-scaled CONTINUOUS
+  features [T: k(x, y) = slope_amplitude^2 * sum_d (x_d/l_d - shift)(y_d/l_d - shift), no bias term], and
+  the GP a constant mean coef * mean_constant."""
+
+  coef: float
+  slope_amplitude: float      # in [1e-3, 10], regulariser 0.01 log(x/0.039)^2
+  shift: float                # unbounded, regulariser 0.5 x^2
+  mean_constant: float        # unbounded, regulariser 0.5 x^2
+
+
+@dataclasses.dataclass
 class GPParams:
   """theta of VizierGaussianProcess (tuned_gp_models.py:161-271)."""
 
@@ -59,6 +72,7 @@ class GPParams:
   continuous_length_scale_squared: np.ndarray  # [Dc]
   observation_noise_variance: float
   categorical_length_scale_squared: Optional[np.ndarray] = None  # [Dk]
+  linear: Optional[LinearParams] = None
 
   def __post_init__(self):
     self.continuous_length_scale_squared = np.asarray(
@@ -73,16 +87,29 @@ class GPParams:
   # Flattening order = jaxopt's sorted-key pytree order:
   # categorical_ls2, continuous_ls2, observation_noise_variance, signal_variance
   def to_vector(self) -> np.ndarray:
+    lin = [] if self.linear is None else [self.linear.shift, self.linear.slope_amplitude, self.linear.mean_constant]
+    # with the linear part the sorted keys are: categorical_ls2, continuous_ls2, linear_shift,
+    # linear_slope_amplitude, mean_fn, observation_noise_variance, signal_variance
     return np.concatenate([
         self.categorical_length_scale_squared,
         self.continuous_length_scale_squared,
+        lin,
         [self.observation_noise_variance],
         [self.signal_variance],
     ])
 
   @classmethod
-  def from_vector(cls, v: np.ndarray, dc: int, dk: int) -> 'GPParams':
+  def from_vector(cls, v: np.ndarray, dc: int, dk: int, linear_coef: Optional[float] = None) -> 'GPParams':
     v = np.asarray(v, dtype=np.float64)
+    if linear_coef is not None:
+      o = dk + dc
+      return cls(
+          categorical_length_scale_squared=v[:dk].copy(),
+          continuous_length_scale_squared=v[dk : dk + dc].copy(),
+          linear=LinearParams(float(linear_coef), slope_amplitude=float(v[o + 1]), shift=float(v[o]), mean_constant=float(v[o + 2])),
+          observation_noise_variance=float(v[o + 3]),
+          signal_variance=float(v[o + 4]),
+      )
     return cls(
         categorical_length_scale_squared=v[:dk].copy(),
         continuous_length_scale_squared=v[dk : dk + dc].copy(),
@@ -105,6 +132,16 @@ def param_bounds(dc: int, dk: int) -> tuple[np.ndarray, np.ndarray]:
       [NOISE_VARIANCE_BOUNDS[1]],
       [SIGNAL_VARIANCE_BOUNDS[1]],
   ])
+  return lo, hi
+
+
+def param_bounds_linear(dc: int, dk: int) -> tuple[np.ndarray, np.ndarray]:
+  """Bounds in to_vector() order with the linear part: shift and mean are unbounded (no constraint in
+  tuned_gp_models.py:216-245 -> +-inf in jaxopt_wrappers._get_bounds), the slope has the amplitude bounds."""
+  lo, hi = param_bounds(dc, dk)
+  o = dk + dc
+  lo = np.concatenate([lo[:o], [-np.inf, SIGNAL_VARIANCE_BOUNDS[0], -np.inf], lo[o:]])
+  hi = np.concatenate([hi[:o], [np.inf, SIGNAL_VARIANCE_BOUNDS[1], np.inf], hi[o:]])
   return lo, hi
 
 
@@ -181,7 +218,29 @@ def kernel(
       cont_dim_valid,
       cat_dim_valid,
   )
-  return matern52_from_d2(d2, params.signal_variance)
+  k = matern52_from_d2(d2, params.signal_variance)
+  if params.linear is not None:
+    k += linear_kernel(params, x1, x2, cont_dim_valid)
+  return k
+
+
+def linear_features(params: GPParams, x, cont_dim_valid=None) -> np.ndarray:
+  """u_id = x_id / l_d - coef * shift  (masked dimensions are zeroed BEFORE the kernel: u = -coef*shift)."""
+  x = np.asarray(x, np.float64)
+  if cont_dim_valid is not None:
+    x = np.where(np.asarray(cont_dim_valid, bool)[None, :], x, 0.0)
+  lin = params.linear
+  return x / np.sqrt(params.continuous_length_scale_squared)[None, :] - lin.coef * lin.shift
+
+
+def linear_kernel(params: GPParams, x1, x2, cont_dim_valid=None) -> np.ndarray:
+  lin = params.linear
+  a = (lin.coef * lin.slope_amplitude) ** 2
+  return a * (linear_features(params, x1, cont_dim_valid) @ linear_features(params, x2, cont_dim_valid).T)
+
+
+def prior_mean(params: GPParams) -> float:
+  return 0.0 if params.linear is None else params.linear.coef * params.linear.mean_constant
 
 
 def kernel_matrix(
@@ -236,6 +295,9 @@ def regularizer(params: GPParams, cont_dim_valid=None, cat_dim_valid=None) -> fl
   r += float(np.sum(REG_WEIGHT * np.log(params.continuous_length_scale_squared / REG_CENTER_LENGTH) ** 2))
   r += float(np.sum(REG_WEIGHT * np.log(params.categorical_length_scale_squared / REG_CENTER_LENGTH) ** 2))
   r += REG_WEIGHT * math.log(params.observation_noise_variance / REG_CENTER_NOISE) ** 2
+  if params.linear is not None:   # tuned_gp_models.py:214, 219, 242
+    r += REG_WEIGHT * math.log(params.linear.slope_amplitude / REG_CENTER_SIGNAL) ** 2
+    r += 0.5 * params.linear.shift ** 2 + 0.5 * params.linear.mean_constant ** 2
   return r
 
 
@@ -250,7 +312,7 @@ def nll(
   y2 = y.reshape(n, -1)
   if row_valid is None:
     row_valid = np.ones(n, bool)
-  yv = np.where(np.asarray(row_valid, bool)[:, None], y2, 0.0)
+  yv = np.where(np.asarray(row_valid, bool)[:, None], y2 - prior_mean(params), 0.0)
   ky = kernel_matrix(params, x, z, row_valid, cont_dim_valid, cat_dim_valid)
   l, _, _ = retrying_cholesky(ky)
   w = sla.solve_triangular(l, yv, lower=True)
@@ -264,7 +326,8 @@ def loss(params: GPParams, x, y, z=None, row_valid=None, cont_dim_valid=None, ca
 
 
 def loss_and_grad(
-    theta: np.ndarray, x, y, z=None, row_valid=None, cont_dim_valid=None, cat_dim_valid=None
+    theta: np.ndarray, x, y, z=None, row_valid=None, cont_dim_valid=None, cat_dim_valid=None,
+    linear_coef: Optional[float] = None,
 ) -> tuple[float, np.ndarray]:
   """loss(theta) and d loss / d theta in GPParams.to_vector() order (A.3).
 
@@ -277,11 +340,11 @@ def loss_and_grad(
   y = np.asarray(y, np.float64).reshape(n, -1)
   n_metrics = y.shape[1]
   dk = 0 if z is None else z.shape[1]
-  p = GPParams.from_vector(theta, dc, dk)
+  p = GPParams.from_vector(theta, dc, dk, linear_coef)
   if row_valid is None:
     row_valid = np.ones(n, bool)
   row_valid = np.asarray(row_valid, bool)
-  yv = np.where(row_valid[:, None], y, 0.0)
+  yv = np.where(row_valid[:, None], y - prior_mean(p), 0.0)
 
   d2 = scaled_sq_dist(
       x, x, p.continuous_length_scale_squared, z, z, p.categorical_length_scale_squared,
@@ -292,6 +355,11 @@ def loss_and_grad(
   kmat = p.signal_variance * (1.0 + s + s * s / 3.0) * es
   e = -(5.0 / 6.0) * p.signal_variance * (1.0 + s) * es
   ky = kmat.copy()
+  if p.linear is not None:
+    u = linear_features(p, x, cont_dim_valid)                 # [N, Dc]
+    lin_a = (p.linear.coef * p.linear.slope_amplitude) ** 2
+    uu = u @ u.T
+    ky += lin_a * uu
   ky[np.diag_indices(n)] += p.observation_noise_variance
   inv = ~row_valid
   ky[inv, :] = 0.0
@@ -328,12 +396,28 @@ def loss_and_grad(
     else:
       diff = x[:, d][:, None] - x[:, d][None, :]
       dterm = 0.5 * np.sum(ge * (-(diff * diff) / ld**2))
+      if p.linear is not None:
+        # K_lin = A sum_d u_id u_jd, u_id = x_id w_d - b, w_d = ld^-1/2: dK_lin/d ld = A (x_id u_jd + x_jd u_id) (-w_d^3 / 2)
+        w3 = ld ** -1.5
+        dterm += 0.5 * np.sum(g * lin_a * (np.outer(x[:, d], u[:, d]) + np.outer(u[:, d], x[:, d]))) * (-0.5 * w3)
     grad_cont[d] = dterm + 2 * REG_WEIGHT * math.log(ld / REG_CENTER_LENGTH) / ld
   sn2 = p.observation_noise_variance
   sf2 = p.signal_variance
   g_noise = 0.5 * np.sum(np.diag(g)) + 2 * REG_WEIGHT * math.log(sn2 / REG_CENTER_NOISE) / sn2
   g_signal = 0.5 * np.sum(g * kmat) / sf2 + 2 * REG_WEIGHT * math.log(sf2 / REG_CENTER_SIGNAL) / sf2
-  grad = np.concatenate([grad_cat, grad_cont, [g_noise], [g_signal]])
+  lin_grads = []
+  if p.linear is not None:
+    lp = p.linear
+    su = u.sum(axis=1)                                           # sum_d u_id
+    # d/d shift: b = coef*shift, d(u_i.u_j)/db = -(su_i + su_j)
+    g_shift = 0.5 * np.sum(g * (-(su[:, None] + su[None, :]))) * lin_a * lp.coef + lp.shift
+    # d/d slope: A = (coef*slope)^2
+    g_slope = 0.5 * np.sum(g * uu) * 2.0 * lp.coef**2 * lp.slope_amplitude \
+        + 2 * REG_WEIGHT * math.log(lp.slope_amplitude / REG_CENTER_SIGNAL) / lp.slope_amplitude
+    # d/d mean_constant: mu = coef*m on the valid rows, dNLL/dmu_i = -alpha_i (summed over metrics)
+    g_mean = -lp.coef * float(np.sum(alpha[row_valid])) + lp.mean_constant
+    lin_grads = [g_shift, g_slope, g_mean]
+  grad = np.concatenate([grad_cat, grad_cont, lin_grads, [g_noise], [g_signal]])
   return float(val), grad
 
 
@@ -390,7 +474,7 @@ def precompute_predictive(
   row_valid = np.asarray(row_valid, bool)
   ky = kernel_matrix(params, x, z, row_valid, cont_dim_valid, cat_dim_valid)
   l, _, it = retrying_cholesky(ky)
-  yv = np.where(row_valid if y.ndim == 1 else row_valid[:, None], y, 0.0)
+  yv = np.where(row_valid if y.ndim == 1 else row_valid[:, None], y - prior_mean(params), 0.0)
   w = sla.solve_triangular(l, yv, lower=True)
   alpha = sla.solve_triangular(l.T, w, lower=False)
   return Predictive(params, x, z, l, alpha, row_valid, cont_dim_valid, cat_dim_valid, it)
@@ -405,9 +489,13 @@ def predict(pred: Predictive, xs, zs=None) -> tuple[np.ndarray, np.ndarray]:
   """
   ks = kernel(pred.params, xs, pred.x, zs, pred.z, pred.cont_dim_valid, pred.cat_dim_valid)
   ks = ks * pred.row_valid[None, :]
-  mu = ks @ pred.alpha
+  mu = ks @ pred.alpha + prior_mean(pred.params)
   v = sla.solve_triangular(pred.chol, ks.T, lower=True)
-  var = pred.params.signal_variance - np.sum(v * v, axis=0) + pred.params.observation_noise_variance
+  kss = pred.params.signal_variance
+  if pred.params.linear is not None:   # k(x*, x*) is no longer constant
+    us = linear_features(pred.params, xs, pred.cont_dim_valid)
+    kss = kss + (pred.params.linear.coef * pred.params.linear.slope_amplitude) ** 2 * np.sum(us * us, axis=1)
+  var = kss - np.sum(v * v, axis=0) + pred.params.observation_noise_variance
   return mu, np.sqrt(np.maximum(var, 0.0))
 
 

@@ -64,8 +64,9 @@ def test_designer_validation_errors_need_no_gpu():
   np.testing.assert_allclose(np.linalg.norm(d._scal_weights, axis=1), 1.0)
   with pytest.raises(NotImplementedError):
     gp_bandit.VizierGPBandit(p, ensemble_size=2)
+  assert gp_bandit.VizierGPBandit(_problem(), linear_coef=0.1)._linear_coef == 0.1
   with pytest.raises(NotImplementedError):
-    gp_bandit.VizierGPBandit(_problem(), linear_coef=0.1)
+    gp_bandit.VizierGPBandit(p, linear_coef=0.1)     # linear kernel + several metrics
 
 
 def test_seed_trials_centre_then_quasi_random():
@@ -221,3 +222,22 @@ def test_lockstep_driver_equals_one_restart_at_a_time():
     np.testing.assert_array_equal(x, xs)
     assert fx == fs
   assert calls[0] == [0, 1, 2, 3, 4] and len(calls[-1]) >= 1 and len(calls) < sum(len(c) for c in calls)
+
+
+def test_lean_lbfgsb_with_unbounded_variables():
+  """The linear_coef model has unconstrained parameters (+-inf bounds): the lean driver must tell setulb so
+  (nbd codes) and still reproduce scipy.optimize.minimize."""
+  import scipy.optimize as sopt
+  from vizier_b200 import ard
+  if ard._setulb is None:
+    pytest.skip('SciPy without the C L-BFGS-B step routine')
+
+  def f(x):
+    return float(np.sum((x - np.array([0.3, -2.0, 5.0])) ** 2) + 0.1 * x[0] * x[1]), 2 * (x - np.array([0.3, -2.0, 5.0])) + 0.1 * np.array([x[1], x[0], 0.0])
+
+  bounds = [(0.0, 1.0), (-np.inf, np.inf), (-np.inf, 4.0)]
+  x0 = np.array([0.9, 0.0, 0.0])
+  x, fx = ard._lean_lbfgsb(f, x0, bounds, maxiter=50, gtol=1e-8, maxls=20)
+  ref = sopt.minimize(f, x0, jac=True, method='L-BFGS-B', bounds=bounds, options={'maxiter': 50, 'gtol': 1e-8, 'maxls': 20})
+  np.testing.assert_array_equal(x, ref.x)
+  assert fx == ref.fun

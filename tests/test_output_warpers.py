@@ -50,3 +50,17 @@ def test_infeasible_are_worst_and_mean_shift():
   y = np.array([[1.0], [2.0], [np.nan], [4.0]])
   z = ow.InfeasibleWarperComponent().warp(y)
   assert z[2, 0] < z[[0, 1, 3], 0].min()
+
+
+def test_vectorised_half_rank_unwarp_equals_the_scalar_form():
+  from vizier_b200 import output_warpers as ow
+  rng = np.random.default_rng(0)
+  for n in (3, 10, 57):
+    labels = rng.normal(size=(n, 1)) * 3
+    labels[rng.integers(0, n, size=2)] = labels[0]          # ties
+    w = ow.HalfRankComponent()
+    warped = w.warp(labels.copy())
+    q = np.concatenate([warped.flatten(), rng.normal(size=200) * 4, [warped.min() - 1.0, warped.max() + 1.0]])
+    want = np.array([w._unwarp_one(v) for v in q])
+    np.testing.assert_array_equal(w._unwarp_many(q), want)
+    np.testing.assert_array_equal(w.unwarp(q[:, None]).flatten(), want)

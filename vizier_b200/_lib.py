@@ -34,6 +34,10 @@ class Params(C.Structure):
       ('observation_noise_variance', C.c_double),
       ('continuous_length_scale_squared', C.POINTER(C.c_double)),
       ('categorical_length_scale_squared', C.POINTER(C.c_double)),
+      ('linear_coef', C.c_double),
+      ('linear_slope_amplitude', C.c_double),
+      ('linear_shift', C.c_double),
+      ('mean_constant', C.c_double),
   ]
 
 

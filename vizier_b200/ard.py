@@ -60,7 +60,9 @@ def _lean_lbfgsb_steps(x0: np.ndarray, bounds, *, maxiter: int, gtol: float, max
   n, m = x0.shape[0], maxcor
   low = np.array([b[0] for b in bounds], np.float64)
   up = np.array([b[1] for b in bounds], np.float64)
-  nbd = np.full(n, 2, dtype=_INT)
+  # SciPy's codes: 0 unbounded, 1 lower only, 2 both, 3 upper only (the linear_coef model has free parameters)
+  fl, fu = np.isfinite(low), np.isfinite(up)
+  nbd = np.where(fl & fu, 2, np.where(fl, 1, np.where(fu, 3, 0))).astype(_INT)
   x = np.clip(np.array(x0, dtype=np.float64), low, up)
   f = np.array(0.0, dtype=np.float64)
   g = np.zeros(n, np.float64)
@@ -126,10 +128,16 @@ def _lockstep(batch_fn, inits, bounds, **kw):
   return [results[i] for i in range(len(gens))]
 
 
-def log_uniform_init(rng: np.random.Generator, dc: int, dk: int, n: int) -> np.ndarray:
+def log_uniform_init(rng: np.random.Generator, dc: int, dk: int, n: int, linear: bool = False) -> np.ndarray:
   lo, hi = gp.param_bounds(dc, dk)
   u = rng.uniform(size=(n, lo.shape[0]))
-  return np.exp(u * np.log(hi / lo) + np.log(lo))
+  th = np.exp(u * np.log(hi / lo) + np.log(lo))
+  if linear:   # slope: log-uniform in the amplitude bounds; shift and mean: standard normal (tuned_gp_models.py:209-240)
+    o = dk + dc
+    slo, shi = gp.SIGNAL_VARIANCE_BOUNDS
+    slope = np.exp(rng.uniform(size=(n, 1)) * np.log(shi / slo) + np.log(slo))
+    th = np.concatenate([th[:, :o], rng.standard_normal((n, 1)), slope, rng.standard_normal((n, 1)), th[:, o:]], axis=1)
+  return th
 
 
 @dataclasses.dataclass
@@ -213,7 +221,7 @@ ARD_SLOT_BUDGET = 192
 
 
 def loss_functions(dev: gp.DeviceGP, xt, yt, zt, dc: int, dk: int, n_valid: Optional[int] = None,
-                   workers: int = MAX_ARD_WORKERS):
+                   workers: int = MAX_ARD_WORKERS, linear_coef: Optional[float] = None):
   """One loss/gradient callable per worker handle (the designer's own handle first; extra handles on
   their own streams are created once and cached on `dev`)."""
   workers = max(1, int(workers))
@@ -230,7 +238,7 @@ def loss_functions(dev: gp.DeviceGP, xt, yt, zt, dc: int, dk: int, n_valid: Opti
   for d in devs:
     d.set_int('dataflow_ctas', share)
 
-  return [d.make_loss_fn(xt, yt, zt, n_valid) for d in devs]
+  return [d.make_loss_fn(xt, yt, zt, n_valid, linear_coef=linear_coef) for d in devs]
 
 
 def batch_loss_function(dev: gp.DeviceGP, xt, yt, zt, restarts: int, n_valid: Optional[int] = None):
@@ -255,7 +263,7 @@ BATCHED_ARD = True   # restarts in lock step on one graph launch per round (N > 
 def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,
              random_restarts: int = DEFAULT_RANDOM_RESTARTS, ensemble_size: int = 1,
              optimizer: Optional[ScipyLbfgsB] = None, n_valid: Optional[int] = None,
-             workers: int = MAX_ARD_WORKERS) -> Tuple[List[gp.GPHyperParams], np.ndarray]:
+             workers: int = MAX_ARD_WORKERS, linear_coef: Optional[float] = None) -> Tuple[List[gp.GPHyperParams], np.ndarray]:
   """Returns the best `ensemble_size` hyper-parameter sets and all final losses.
 
   x [N,Dc] float64, z [N,Dk] int32 or None, y [N] or [N, M]: device tensors or arrays (copied once).
@@ -274,14 +282,14 @@ def train_gp(dev: gp.DeviceGP, x, y, z=None, *, rng: np.random.Generator,
     zt = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z, dtype=np.int32)).to(dev.device)
   dc = xt.shape[1]
   dk = 0 if zt is None else zt.shape[1]
-  lo, hi = gp.param_bounds(dc, dk)
-  inits = log_uniform_init(rng, dc, dk, random_restarts)
-  if BATCHED_ARD and _setulb is not None and xt.shape[0] > 64 and 1 < random_restarts <= 16 and workers > 1:
+  lo, hi = gp.param_bounds(dc, dk, linear=bool(linear_coef))
+  inits = log_uniform_init(rng, dc, dk, random_restarts, linear=bool(linear_coef))
+  if BATCHED_ARD and _setulb is not None and xt.shape[0] > 64 and 1 < random_restarts <= 16 and workers > 1 and not linear_coef:
     fns = batch_loss_function(dev, xt, yt, zt, random_restarts, n_valid)
   else:
-    fns = loss_functions(dev, xt, yt, zt, dc, dk, n_valid, workers=min(workers, random_restarts))
+    fns = loss_functions(dev, xt, yt, zt, dc, dk, n_valid, workers=min(workers, random_restarts), linear_coef=linear_coef)
   try:
     best, losses = optimizer(inits, fns, list(zip(lo, hi)), best_n=ensemble_size)
   finally:
     dev.set_int('dataflow_ctas', 0)     # the fit that follows runs alone: every slot
-  return [gp.GPHyperParams.from_vector(t, dc, dk) for t in best], losses
+  return [gp.GPHyperParams.from_vector(t, dc, dk, linear_coef) for t in best], losses

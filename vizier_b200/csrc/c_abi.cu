@@ -22,8 +22,9 @@ void set_error(const char* fmt, ...) {
 constexpr size_t kSmallBytes = 65536;
 constexpr size_t kOffClamp = 0;      // int
 constexpr size_t kOffFlag = 8;       // int
-constexpr size_t kOffLogdet = 64;    // double[2]
-constexpr size_t kOffGrad = 128;     // double[<=98]
+constexpr size_t kOffLogdet = 64;    // double[3]: M sum log L_ii, quadratic form / 2, sum alpha
+constexpr size_t kOffGrad = 5120;    // double[<= 2 kMaxDc + kMaxDk + 8] (the free 3 KiB below kOffPartial)
+constexpr int kMaxGrad = 2 * kMaxDc + kMaxDk + 8;
 constexpr size_t kOffTopIdx = 1024;  // long long[256]
 constexpr size_t kOffTopVal = 3072;  // double[256]
 constexpr size_t kOffPartial = 8192; // ArgMax[<=2048] = 32 KiB
@@ -127,7 +128,7 @@ static int solve_alphas(vzgp_handle* h, const double* y, int N, int n_valid, int
     double* r = yp + 2 * np;
     double* tmp = yp + 3 * np;
     double* alpha = h->alpha.as<double>() + (size_t)m * np;
-    VZ_TRY(launch_pad_vector(h, y + (size_t)m * N, N, n_valid, np, yp));
+    VZ_TRY(launch_pad_vector(h, y + (size_t)m * N, N, n_valid, np, yp, h->mean_const));
     VZ_TRY(launch_gemv_rows(h, h->Linv.as<double>(), np, np, yp, w, 1));
     VZ_TRY(gemv_T(w, alpha));
     VZ_TRY(launch_residual(h, h->Kws.as<double>(), np, np, yp, alpha, r));
@@ -155,9 +156,11 @@ static int fit_common(vzgp_handle* h, const double* X, const int32_t* Z, const d
   VZ_TRY(fill_kernel_params(p, dc, dk, &kp));
   const int np = round_up(N, kBlk);
   VZ_TRY(ensure_model_buffers(h, np, dc, dk, n_metrics));
-  h->fitted = false;
+  h->fitted = false; h->i8_ready = false;
   h->n = N; h->np = np; h->dc = dc; h->dk = dk; h->n_valid = n_valid; h->n_metrics = n_metrics;
   h->kp = kp; h->sn2 = p->observation_noise_variance;
+  h->mean_const = p->linear_coef != 0.0 ? p->linear_coef * p->mean_constant : 0.0;
+  VZ_ARG(!kp.use_linear || n_metrics == 1, "linear_coef with several metrics is not implemented");
   if (dc > 0) VZ_TRY(launch_pad_rows(h, X, N, dc, np, h->X.as<double>()));
   if (dc > 0) VZ_TRY(launch_transpose_scale(h, h->X.as<double>(), np, dc, kp, h->XT.as<double>()));
   if (dk > 0) VZ_TRY(launch_pad_rows_i32(h, Z, N, dk, np, h->Z.as<int32_t>()));
@@ -232,7 +235,7 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
              h->nll_key_dims[3] == n_valid && h->nll_key_dims[4] == n_metrics;
   hit = hit && (h->df_nb[1] == 0 || h->df_nb[1] == np / 64);   // another call re-planned the dataflow tasks
   for (int q = 0; hit && q < kNllBufs; ++q) hit = cur[q] == h->nll_bufs[q];   // a workspace was reallocated since the capture
-  h->fitted = false;
+  h->fitted = false; h->i8_ready = false;
   if (!hit) {
     nll_graph_drop(h);
     VZ_TRY(ensure_model_buffers(h, np, dc, dk, n_metrics));
@@ -273,7 +276,7 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
     h->nll_key_dims[4] = n_metrics;
     bufs(h->nll_bufs);
   }
-  h->kp = kp; h->sn2 = sn2;
+  h->kp = kp; h->sn2 = sn2; h->mean_const = 0.0;
   // new hyper-parameters, by the argument positions pinned in launchers.h (static_asserted against the kernels)
   const int arg_idx[3] = {kKernelMatrixKpArg, kTransposeScaleKpArg, kNllGradTilesKpArg};
   const int arg_cnt[3] = {kKernelMatrixArgs, kTransposeScaleArgs, kNllGradTilesArgs};
@@ -302,10 +305,12 @@ static int nll_graph_eval(vzgp_handle* h, const double* X, const int32_t* Z, con
 // loss and gradient from the device sums (regularisers: tuned_gp_models.py:167,180,192,269 ->
 // 0.01 log(x/c)^2, derivative 0.02 log(x/c) / x).  hostg: [Dk cat | Dc cont | trace | sum G K].
 static void finish_loss(const vzgp_params* p, int Dc, int Dk, int n_valid, int n_metrics, double half_logdet_plus_quad,
-                        const double* hostg, double* loss_out, double* grad_out) {
+                        const double* hostg, double* loss_out, double* grad_out, double sum_alpha = 0.0) {
   auto reg = [](double x, double c) { double l = std::log(x / c); return 0.01 * l * l; };
   auto dreg = [](double x, double c) { return 0.02 * std::log(x / c) / x; };
   const double sf2 = p->signal_variance, sn2 = p->observation_noise_variance;
+  const bool lin = p->linear_coef != 0.0;
+  const int o = Dk + Dc, tail = o + (lin ? 3 : 0);            // position of [noise, signal] in the output
   double loss = half_logdet_plus_quad + 0.5 * n_metrics * n_valid * std::log(2.0 * M_PI);
   loss += reg(sf2, 0.039) + reg(sn2, 0.0039);
   for (int k = 0; k < Dk; ++k) {
@@ -313,13 +318,24 @@ static void finish_loss(const vzgp_params* p, int Dc, int Dk, int n_valid, int n
     loss += reg(l, 0.5);
     grad_out[k] = -0.5 * hostg[k] / (l * l) + dreg(l, 0.5);
   }
+  const double c = p->linear_coef, s = p->linear_slope_amplitude, lin_a = (c * s) * (c * s);
   for (int d = 0; d < Dc; ++d) {
     const double l = p->continuous_length_scale_squared[d];
     loss += reg(l, 0.5);
-    grad_out[Dk + d] = -0.5 * hostg[Dk + d] / (l * l) + dreg(l, 0.5);
+    double gd = -0.5 * hostg[Dk + d] / (l * l);
+    // K_lin = A sum_d u_id u_jd, u = x w - b, w = l^-1/2:  dK_lin/dl = A (x_i u_j + x_j u_i) (-w^3 / 2)
+    if (lin) gd += 0.5 * lin_a * hostg[o + 2 + d] * (-0.5 / (l * std::sqrt(l)));
+    grad_out[Dk + d] = gd + dreg(l, 0.5);
   }
-  grad_out[Dk + Dc] = 0.5 * hostg[Dk + Dc] + dreg(sn2, 0.0039);
-  grad_out[Dk + Dc + 1] = 0.5 * hostg[Dk + Dc + 1] / sf2 + dreg(sf2, 0.039);
+  if (lin) {   // tuned_gp_models.py:203-245: slope in the amplitude bounds, shift and mean with 0.5 x^2
+    const double q = hostg[o + 2 + Dc], hs = hostg[o + 2 + Dc + 1], h = p->linear_shift, m = p->mean_constant;
+    loss += reg(s, 0.039) + 0.5 * h * h + 0.5 * m * m;
+    grad_out[o] = 0.5 * (-hs) * lin_a * c + h;                       // d/d shift
+    grad_out[o + 1] = 0.5 * q * 2.0 * c * c * s + dreg(s, 0.039);    // d/d slope amplitude
+    grad_out[o + 2] = -c * sum_alpha + m;                            // d/d mean constant
+  }
+  grad_out[tail] = 0.5 * hostg[o] + dreg(sn2, 0.0039);
+  grad_out[tail + 1] = 0.5 * hostg[o + 1] / sf2 + dreg(sf2, 0.039);
   *loss_out = loss;
 }
 
@@ -370,7 +386,7 @@ using namespace vzgp;
 extern "C" {
 
 const char* vzgp_last_error(void) { return g_err; }
-int vzgp_version(void) { return 1; }
+int vzgp_version(void) { return 2; }
 
 int vzgp_device_count(void) {
   int n = 0;
@@ -416,7 +432,8 @@ int vzgp_destroy(vzgp_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->Z, &h->L, &h->Linv, &h->alpha, &h->ypad, &h->Kws, &h->Tws, &h->Kinv, &h->XT,
                     &h->scratch, &h->small, &h->xs_dev, &h->out_dev, &h->eagle, &h->pe_tmp,
-                    &h->LinvT, &h->df_tasks[0], &h->df_tasks[1], &h->df_flags, &h->df_S, &h->scal})
+                    &h->LinvT, &h->df_tasks[0], &h->df_tasks[1], &h->df_flags, &h->df_S, &h->scal, &h->gen,
+                    &h->i8_planes, &h->i8_scale, &h->i8_kdig})
     b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->copy_stream) {
@@ -448,6 +465,7 @@ int64_t vzgp_launch_count(const vzgp_handle* h) { return h ? h->launches : 0; }
 int vzgp_set_int(vzgp_handle* h, const char* key, int value) {
   VZ_ARG(h && key, "handle / key");
   if (std::strcmp(key, "dataflow_ctas") == 0) { VZ_ARG(value >= 0, "value >= 0"); h->df_ctas = value; return 0; }
+  if (std::strcmp(key, "score_i8") == 0) { VZ_ARG(value >= -1 && value <= 1, "value in {-1, 0, 1}"); h->score_i8 = value; return 0; }
   set_error("vzgp_set_int: unknown key '%s'", key);
   return VZGP_ERR_ARG;
 }
@@ -507,7 +525,7 @@ int vzgp_factor_inverse(vzgp_handle* h, const double* A, int N, int lda, double*
   Guard g(h->device);
   const int np = round_up(N, kBlk);
   VZ_TRY(ensure_model_buffers(h, np, 1, 0));
-  h->fitted = false;
+  h->fitted = false; h->i8_ready = false;
   const bool want_kinv = Kinv != nullptr;
   if (want_kinv) VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));
   int* flag = reinterpret_cast<int*>(h->small.as<char>() + kOffFlag);
@@ -604,7 +622,9 @@ int vzgp_nll_grad_multi(vzgp_handle* h, const double* X, const int32_t* Z, const
     finish_loss(p, Dc, Dk, n_valid, n_metrics, half_logdet_plus_quad, hostg, loss_out, grad_out);
   };
   static const bool small_ok = [] { const char* e = getenv("VZGP_NLL_SMALL"); return !(e && e[0] == '0'); }();
-  if (N <= kBlk && small_ok && n_metrics == 1) {
+  const bool lin = p->linear_coef != 0.0;
+  VZ_ARG(!lin || n_metrics == 1, "linear_coef with several metrics is not implemented");
+  if (N <= kBlk && small_ok && n_metrics == 1 && !lin) {
     // Small studies: the whole evaluation is one single-CTA kernel (nll_small.cu).  The handle's
     // fitted model is not touched (ARD callers refit with the chosen parameters afterwards).
     VZ_ARG(N >= 1 && n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
@@ -616,20 +636,20 @@ int vzgp_nll_grad_multi(vzgp_handle* h, const double* X, const int32_t* Z, const
     const int nq = Dc + Dk + 2;
     double* dout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);   // 4 + nq doubles
     VZ_TRY(launch_nll_grad_small(h, X, Z, y, N, n_valid, kp, p->observation_noise_variance, 1e-4, 5, dout));
-    double host[4 + kMaxDc + kMaxDk + 2];
+    double host[4 + kMaxGrad];
     VZ_CUDA(cudaMemcpyAsync(host, dout, sizeof(double) * (4 + nq), cudaMemcpyDeviceToHost, h->stream));
     VZ_CUDA(cudaStreamSynchronize(h->stream));
     finish(host[0] + host[1], host + 4);
     return (int)host[3];
   }
-  {
+  if (!lin) {
     // Replayed graph (no retry inside); a flagged pivot or any graph problem falls through to the
     // eager path below, which has the jitter loop.
     VZ_ARG(N >= 1 && n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
     VZ_ARG(X != nullptr || Dc == 0, "X");
     VZ_ARG(Z != nullptr || Dk == 0, "Z");
     VZ_ARG(y != nullptr, "y");
-    double g2[2], gg[kMaxDc + kMaxDk + 2];
+    double g2[2], gg[kMaxGrad];
     const int st = nll_graph_eval(h, X, Z, y, N, Dc, Dk, n_valid, n_metrics, p, g2, gg);
     if (st < 0) return st;
     if (st == 0) {
@@ -640,21 +660,21 @@ int vzgp_nll_grad_multi(vzgp_handle* h, const double* X, const int32_t* Z, const
   double shift = 0.0;
   int retries = fit_common(h, X, Z, y, N, Dc, Dk, n_valid, p, &shift, n_metrics);
   if (retries < 0) return retries;
-  const int np = h->np, nq = Dc + Dk + 2;
+  const int np = h->np, nq = Dc + Dk + 2 + (lin ? Dc + 2 : 0);
   VZ_TRY(h->Kinv.reserve(sizeof(double) * (size_t)np * np * kLauumSplit));   // partial planes of K_y^-1
   double* out2 = reinterpret_cast<double*>(h->small.as<char>() + kOffLogdet);
   double* gout = reinterpret_cast<double*>(h->small.as<char>() + kOffGrad);
   double* w = h->ypad.as<double>() + np;
-  VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, w, out2, 4 * np, n_metrics));
+  VZ_TRY(launch_logdet_quad(h, h->L.as<double>(), np, n_valid, w, out2, 4 * np, n_metrics, h->alpha.as<double>()));
   VZ_TRY(launch_lauum(h, h->Linv.as<double>(), np, h->Kinv.as<double>(), np, np));
   VZ_TRY(launch_nll_grad_tiles(h, h->X.as<double>(), h->Z.as<int32_t>(), np, n_valid, h->kp,
                                h->Kinv.as<double>(), np, h->alpha.as<double>(), h->Tws.as<double>(), gout, 0, n_metrics));
-  double host2[2];
-  double hostg[kMaxDc + kMaxDk + 2];
+  double host2[3];
+  double hostg[kMaxGrad];
   VZ_CUDA(cudaMemcpyAsync(host2, out2, sizeof(host2), cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaMemcpyAsync(hostg, gout, sizeof(double) * nq, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaStreamSynchronize(h->stream));
-  finish(host2[1] + host2[0], hostg);
+  finish_loss(p, Dc, Dk, n_valid, n_metrics, host2[1] + host2[0], hostg, loss_out, grad_out, host2[2]);
   return retries;
 }
 
@@ -1071,6 +1091,7 @@ int vzgp_nll_grad_batch(vzgp_handle* const* hs, int R, const double* X, const in
   VZ_ARG(hs && ps && loss_out && grad_out && status_out, "pointers");
   VZ_ARG(R >= 1 && R <= kMaxBatch, "1 <= R <= 16");
   VZ_ARG(N > kBlk, "the batched evaluation is for N > 64 (smaller studies: vzgp_nll_grad per restart)");
+  for (int r = 0; r < R; ++r) VZ_ARG(ps[r].linear_coef == 0.0, "linear_coef models take vzgp_nll_grad per restart");
   VZ_ARG(n_valid >= 1 && n_valid <= N, "1 <= n_valid <= N");
   VZ_ARG(n_metrics >= 1 && n_metrics <= kMaxMetrics, "1 <= n_metrics <= 8");
   VZ_ARG(X != nullptr || Dc == 0, "X");
@@ -1111,7 +1132,7 @@ int vzgp_nll_grad_batch(vzgp_handle* const* hs, int R, const double* X, const in
       VZ_TRY(h->Tws.reserve(sizeof(double) * (size_t)np * np));
       VZ_TRY(chol_dataflow_prepare(h, np, true));
       VZ_TRY(ensure_pinned(h, res_bytes));
-      h->fitted = false;
+      h->fitted = false; h->i8_ready = false;
       h->n = N; h->np = np; h->dc = Dc; h->dk = Dk; h->n_valid = n_valid; h->n_metrics = n_metrics;
       VZ_CUDA(cudaStreamSynchronize(h->stream));
     }
@@ -1185,7 +1206,7 @@ int vzgp_nll_grad_batch(vzgp_handle* const* hs, int R, const double* X, const in
   for (int r = 0; r < R; ++r) {
     if (active && !active[r]) continue;
     sn2s[r] = ps[r].observation_noise_variance;
-    hs[r]->kp = kps[r]; hs[r]->sn2 = sn2s[r]; hs[r]->fitted = false;
+    hs[r]->kp = kps[r]; hs[r]->sn2 = sn2s[r]; hs[r]->mean_const = 0.0; hs[r]->fitted = false; hs[r]->i8_ready = false;
     for (int q = 0; q < 3; ++q) {
       if (!b->nodes[r][q]) continue;
       cudaKernelNodeParams kpar;
@@ -1251,6 +1272,7 @@ int vzgp_posterior_multi(vzgp_handle* h, const double* Xs, const int32_t* Zs, in
   VZ_TRY(launch_cov_update(h, W, np, np, mp, C, mp, add_noise ? h->sn2 : 0.0));
   for (int m = 0; m < nm; ++m)
     VZ_TRY(launch_gemv_rows(h, Ks, np, mp, h->alpha.as<double>() + (size_t)m * np, mu + (size_t)m * mp, 0, np));
+  if (h->mean_const != 0.0) VZ_TRY(launch_add_scalar(h, (int)((size_t)mp * nm), h->mean_const, mu));
   VZ_CUDA(cudaMemcpy2DAsync(cov, sizeof(double) * ldc, C, sizeof(double) * mp, sizeof(double) * M, M,
                             cudaMemcpyDeviceToDevice, h->stream));
   VZ_CUDA(cudaMemcpy2DAsync(mean, sizeof(double) * M, mu, sizeof(double) * mp, sizeof(double) * M, nm,

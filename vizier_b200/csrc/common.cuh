@@ -94,6 +94,9 @@ struct KernelParams {
   double inv_ls2_c[kMaxDc];
   double inv_ls_c[kMaxDc];   // sqrt(inv_ls2_c): the reference's FeatureScaled divides by the length scale
   double inv_ls2_k[kMaxDk];
+  // linear_coef variant: k += lin_a * sum_d (x_d inv_ls_c[d] - lin_b)(x'_d inv_ls_c[d] - lin_b)
+  int use_linear;
+  double lin_a, lin_b;
 };
 
 // Hyper-volume scalarised UCB parameters (multi.cu); the weight tables live in handle->scal.
@@ -118,6 +121,7 @@ struct vzgp_handle {
   int n = 0, np = 0, dc = 0, dk = 0, n_valid = 0, n_metrics = 1;
   vzgp::KernelParams kp;
   double sn2 = 0.0;
+  double mean_const = 0.0;   // constant prior mean (linear_coef variant), 0 otherwise
   vzgp::DevBuf X;      // [np x dc]
   vzgp::DevBuf XT;     // [2][dc x np]: transposed trials, scaled by 1/ls (first) and unscaled (second)
   vzgp::DevBuf Z;      // [np x dk] int32
@@ -138,6 +142,7 @@ struct vzgp_handle {
   vzgp::DevBuf out_dev;
   vzgp::DevBuf eagle;   // eagle state
   vzgp::DevBuf pe_tmp;  // GP-UCB-PE: per-candidate pieces of the two models
+  vzgp::DevBuf gen;     // general scoring path: explicit K* and W chunks
   vzgp::DevBuf scal;    // multi-metric: [S][M] inverse scalarisation weights, then [S] best observed values
   vzgp::ScalArgs scal_args;
   void* pinned = nullptr;
@@ -160,4 +165,9 @@ struct vzgp_handle {
   vzgp::DevBuf df_tasks[2], df_flags, df_S;     // task lists without / with the K_y^-1 tasks
   int df_nb[2] = {0, 0}, df_ntasks[2] = {0, 0}, df_ncrit[2] = {0, 0};
   int df_ctas = 0;                              // worker CTAs per launch (0: all slots); vzgp_set_int
+
+  // Integer-split scoring on tcgen05 (score_i8.cu): digit planes of Linv, their row scales, K* digit scratch.
+  int score_i8 = -1;                            // -1: environment VZGP_SCORE_I8 (default off), 0 / 1: vzgp_set_int
+  bool i8_ready = false;                        // the digit planes describe the current Linv
+  vzgp::DevBuf i8_planes, i8_scale, i8_kdig;
 };

@@ -470,7 +470,8 @@ static size_t eagle_persistent_state_bytes(const EagleDev& e) {
 
 bool eagle_persistent_eligible(const vzgp_handle* h, const vzgp_handle* hB, const EagleDev& e) {
   static const bool enabled = [] { const char* v = getenv("VZGP_EAGLE_PERSISTENT"); return !(v && v[0] == '0'); }();
-  return enabled && h->np == 64 && (hB == nullptr || hB->np == 64) && e.B <= 64 &&
+  const bool linear = h->kp.use_linear || (hB != nullptr && hB->kp.use_linear);   // in-kernel scoring knows Matern only
+  return enabled && !linear && h->np == 64 && (hB == nullptr || hB->np == 64) && e.B <= 64 &&
          eagle_persistent_state_bytes(e) <= 64 * 1024;
 }
 

@@ -142,8 +142,8 @@ bool eagle_grid_eligible(const vzgp_handle* h, const vzgp_handle* hB, const Eagl
   static const bool enabled = [] { const char* v = getenv("VZGP_EAGLE_GRID"); return !(v && v[0] == '0'); }();
   int coop = 0;
   if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device) != cudaSuccess) coop = 0;
-  (void)hB;
-  return enabled && coop && e.B <= 8 * kTM;
+  const bool linear = h->kp.use_linear || (hB != nullptr && hB->kp.use_linear);   // in-kernel scoring knows Matern only
+  return enabled && coop && !linear && e.B <= 8 * kTM;
 }
 
 // acq (UCB on h) or pe (GP-UCB-PE on h = model A and hB = model B): exactly one is non-null.

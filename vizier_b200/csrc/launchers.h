@@ -45,12 +45,13 @@ int launch_gemv_lower_T(vzgp_handle* h, const double* M, int ld, int np, const d
 int launch_residual(vzgp_handle* h, const double* Ky, int ld, int np, const double* y, const double* a,
                     double* r);
 int launch_axpy(vzgp_handle* h, int n, double a, const double* x, double* y);
-int launch_pad_vector(vzgp_handle* h, const double* src, int n, int n_valid, int np, double* dst);
+int launch_add_scalar(vzgp_handle* h, int n, double a, double* y);
+int launch_pad_vector(vzgp_handle* h, const double* src, int n, int n_valid, int np, double* dst, double offset = 0.0);
 int launch_pad_rows(vzgp_handle* h, const double* src, int n, int d, int np, double* dst);
 int launch_transpose_scale(vzgp_handle* h, const double* X, int np, int dc, const KernelParams& kp, double* XT);
 int launch_pad_rows_i32(vzgp_handle* h, const int32_t* src, int n, int d, int np, int32_t* dst);
 int launch_logdet_quad(vzgp_handle* h, const double* L, int ld, int n_valid, const double* w, double* out,
-                       int wstride = 0, int n_metrics = 1);
+                       int wstride = 0, int n_metrics = 1, const double* alpha = nullptr);
 
 int launch_gemm_nt_tri(vzgp_handle* h, const double* A, int lda, int mp, const double* B, int ldb, int np,
                        double* C, int ldc);
@@ -74,6 +75,13 @@ int chol_dataflow_timed_out(vzgp_handle* h, int* out);
 
 int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                  double* score, double* mu, double* sigma, double* linf);
+// tcgen05 / TMEM integer-split variant of the large-pool scoring kernel (score_i8.cu).
+bool score_i8_eligible(const vzgp_handle* h, int M);
+int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                    double* score, double* mu, double* sigma, double* linf);
+// CUtensorMap (void*) of a u8 tensor of `rank` <= 3 dims (innermost first), byte strides of dims 1.., 128-byte swizzle.
+int make_tensor_map_u8(void* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                       const uint32_t* box);
 int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
                     const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
 int prepare_scalarization(vzgp_handle* h, const vzgp_scalarization* sc);

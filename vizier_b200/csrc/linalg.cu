@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) k_kernel_matrix(const double* __restrict_
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
   double d2[4][4], unused[4][4];
   tile_d2<G64, 4, 4, false>(sa, LD, sb, LD, za, LD, zb, LD, kp, nullptr, ty, tx, d2, unused);
+  if (kp.use_linear) tile_lin<G64, 4, 4>(sa, LD, sb, LD, kp, ty, tx, unused);   // `unused` now holds the linear term
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) k_kernel_matrix(const double* __restrict_
         v = (gi == gj) ? 1.0 : 0.0;
       } else {
         v = matern52(d2[i][j], kp.sf2);
+        if (kp.use_linear) v = fma(kp.lin_a, unused[i][j], v);
         if (gi == gj) v += diag_add;
       }
       K[(size_t)gi * ldk + gj] = v;
@@ -83,13 +85,16 @@ __global__ void __launch_bounds__(256) k_cross_kernel(const double* __restrict__
   double d2[8][4], unused[8][4];
   tile_d2<G128x64, 8, 4, false>(sa, LDA, sb, LDB, za, LDA, zb, LDB, kp, nullptr, ty, tx, d2,
                                 unused);
+  if (kp.use_linear) tile_lin<G128x64, 8, 4>(sa, LDA, sb, LDB, kp, ty, tx, unused);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int gi = m0 + G128x64::row_of(ty, i), gj = j0 + G128x64::col_of(tx, j);
       if (gi >= M || gj >= n) continue;
-      Ks[(size_t)gi * ldks + gj] = gj < n_valid ? matern52(d2[i][j], kp.sf2) : 0.0;
+      double v = matern52(d2[i][j], kp.sf2);
+      if (kp.use_linear) v = fma(kp.lin_a, unused[i][j], v);
+      Ks[(size_t)gi * ldks + gj] = gj < n_valid ? v : 0.0;
     }
 }
 
@@ -402,9 +407,9 @@ __global__ void k_axpy(int n, double a, const double* __restrict__ x, double* __
 }
 
 __global__ void k_pad_vector(const double* __restrict__ src, int n, int n_valid, int np,
-                             double* __restrict__ dst) {
+                             double* __restrict__ dst, double offset) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < np) dst[i] = (i < n && i < n_valid) ? src[i] : 0.0;
+  if (i < np) dst[i] = (i < n && i < n_valid) ? src[i] - offset : 0.0;   // offset: constant prior mean
 }
 
 __global__ void k_pad_rows(const double* __restrict__ src, int n, int d, int np,
@@ -434,17 +439,21 @@ __global__ void k_pad_rows_i32(const int32_t* __restrict__ src, int n, int d, in
 
 // n_metrics * sum_i log L_ii over i < n_valid and  0.5 * sum_m sum_i w_m[i]^2  ->  out[0], out[1]
 // (single block; w_m = w + m * wstride: the independent multi-task GP shares one factor).
+// out[2] = sum_i alpha[i] over the valid rows (gradient of the constant mean of the linear_coef model).
 __global__ void k_logdet_quad(const double* __restrict__ L, int ld, int n_valid,
-                              const double* __restrict__ w, int wstride, int n_metrics, double* __restrict__ out) {
+                              const double* __restrict__ w, int wstride, int n_metrics, double* __restrict__ out,
+                              const double* __restrict__ alpha) {
   __shared__ double red[32];
-  double a = 0.0, b = 0.0;
+  double a = 0.0, b = 0.0, c = 0.0;
   for (int i = threadIdx.x; i < n_valid; i += blockDim.x) {
     a += log(L[(size_t)i * ld + i]);
     for (int m = 0; m < n_metrics; ++m) { const double v = w[(size_t)m * wstride + i]; b = fma(v, v, b); }
+    if (alpha) c += alpha[i];
   }
   a = block_sum(a, red);
   b = block_sum(b, red);
-  if (threadIdx.x == 0) { out[0] = n_metrics * a; out[1] = 0.5 * b; }
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) { out[0] = n_metrics * a; out[1] = 0.5 * b; out[2] = c; }
 }
 
 // ---------------------------------------------------------------------------
@@ -470,6 +479,9 @@ int fill_kernel_params(const vzgp_params* p, int dc, int dk, KernelParams* kp) {
   }
   for (int d = 0; d < kMaxDk; ++d)
     kp->inv_ls2_k[d] = d < dk ? 1.0 / p->categorical_length_scale_squared[d] : 0.0;
+  kp->use_linear = p->linear_coef != 0.0 ? 1 : 0;
+  kp->lin_a = kp->use_linear ? (p->linear_coef * p->linear_slope_amplitude) * (p->linear_coef * p->linear_slope_amplitude) : 0.0;
+  kp->lin_b = kp->use_linear ? p->linear_coef * p->linear_shift : 0.0;
   return 0;
 }
 
@@ -638,8 +650,18 @@ int launch_axpy(vzgp_handle* h, int n, double a, const double* x, double* y) {
   h->launches++;
   return 0;
 }
-int launch_pad_vector(vzgp_handle* h, const double* src, int n, int n_valid, int np, double* dst) {
-  k_pad_vector<<<(np + 255) / 256, 256, 0, h->stream>>>(src, n, n_valid, np, dst);
+__global__ void k_add_scalar(int n, double a, double* __restrict__ y) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a;
+}
+int launch_add_scalar(vzgp_handle* h, int n, double a, double* y) {
+  k_add_scalar<<<(n + 255) / 256, 256, 0, h->stream>>>(n, a, y);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+int launch_pad_vector(vzgp_handle* h, const double* src, int n, int n_valid, int np, double* dst, double offset) {
+  k_pad_vector<<<(np + 255) / 256, 256, 0, h->stream>>>(src, n, n_valid, np, dst, offset);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;
@@ -670,8 +692,8 @@ int launch_pad_rows_i32(vzgp_handle* h, const int32_t* src, int n, int d, int np
   return 0;
 }
 int launch_logdet_quad(vzgp_handle* h, const double* L, int ld, int n_valid, const double* w,
-                       double* out, int wstride, int n_metrics) {
-  k_logdet_quad<<<1, 256, 0, h->stream>>>(L, ld, n_valid, w, wstride, n_metrics, out);
+                       double* out, int wstride, int n_metrics, const double* alpha) {
+  k_logdet_quad<<<1, 256, 0, h->stream>>>(L, ld, n_valid, w, wstride, n_metrics, out, alpha);
   VZ_CHECK_LAUNCH();
   h->launches++;
   return 0;

@@ -14,7 +14,9 @@ using G64 = GemmCfg<64, 64, 16, 4, 4>;
 
 // One CTA per lower-triangular 64x64 tile (off-diagonal tiles count twice).  Writes
 // partial[tile][0..dk) = sum G*E*neq_k, [dk..dk+dc) = sum G*E*diff_d^2, [dk+dc] = trace part of G,
-// [dk+dc+1] = sum G*K.
+// [dk+dc+1] = sum G*K_matern; with the linear_coef model (kp.use_linear) three more groups follow:
+// [dk+dc+2 .. +dc) = sum G (x_id u_jd + x_jd u_id), then sum G sum_d u_id u_jd, then sum G sum_d (u_id + u_jd),
+// u_id = x_id / l_d - coef*shift  (the pieces of dK_lin/d ls2_d, d/d slope, d/d shift).
 __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict__ X,
                                                         const int32_t* __restrict__ Z, int np,
                                                         int n_valid, KernelParams kp,
@@ -26,7 +28,7 @@ __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict
   if (bj > bi) return;
   extern __shared__ double smem[];
   constexpr int LD = 66;
-  const int dc = kp.dc, dk = kp.dk, np_out = dc + dk + 2;
+  const int dc = kp.dc, dk = kp.dk, np_out = dc + dk + 2 + (kp.use_linear ? dc + 2 : 0);
   double* sa = smem;
   double* sb = sa + dc * LD;
   double* s_part = sb + dc * LD;                                   // [8 warps][np_out]
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16, warp = tid / 32, lane = tid % 32;
   double d2[4][4], unused[4][4];
   tile_d2<G64, 4, 4, false>(sa, LD, sb, LD, za, LD, zb, LD, kp, nullptr, ty, tx, d2, unused);
-  double ge[4][4];
+  double ge[4][4], gg[4][4];
   double sum_gk = 0.0, sum_tr = 0.0;
   const double wgt = (bi == bj) ? 1.0 : 2.0;
 #pragma unroll
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict
         if (gi == gj) sum_tr += g;
       }
       ge[i][j] = g * ev;
+      gg[i][j] = g;
       sum_gk = fma(g, kv, sum_gk);
     }
   auto warp_store = [&](double v, int slot) {
@@ -94,6 +97,29 @@ __global__ void __launch_bounds__(256) k_nll_grad_tiles(const double* __restrict
   }
   warp_store(sum_tr, dk + dc);
   warp_store(sum_gk, dk + dc + 1);
+  if (kp.use_linear) {
+    double q = 0.0, hs = 0.0;
+    for (int d = 0; d < dc; ++d) {
+      const double w = kp.inv_ls_c[d];
+      double xi[4], ui[4], xj[4], uj[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xi[i] = sa[d * LD + G64::row_of(ty, i)]; ui[i] = fma(xi[i], w, -kp.lin_b); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xj[j] = sb[d * LD + G64::col_of(tx, j)]; uj[j] = fma(xj[j], w, -kp.lin_b); }
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          t = fma(gg[i][j], fma(xi[i], uj[j], xj[j] * ui[i]), t);
+          q = fma(gg[i][j], ui[i] * uj[j], q);
+          hs = fma(gg[i][j], ui[i] + uj[j], hs);
+        }
+      warp_store(t, dk + dc + 2 + d);
+    }
+    warp_store(q, dk + dc + 2 + dc);
+    warp_store(hs, dk + dc + 2 + dc + 1);
+  }
   __syncthreads();
   // tile index in row-major lower-triangular enumeration
   const int tile = bi * (bi + 1) / 2 + bj;
@@ -124,7 +150,7 @@ const void* nll_grad_tiles_func() { return reinterpret_cast<const void*>(&k_nll_
 int launch_nll_grad_tiles(vzgp_handle* h, const double* X, const int32_t* Z, int np, int n_valid,
                           const KernelParams& kp, const double* Kinv, int ldk, const double* alpha,
                           double* partial, double* out, int plane_rows, int n_metrics) {
-  const int nb = np / 64, nq = kp.dc + kp.dk + 2, ntiles = nb * (nb + 1) / 2;
+  const int nb = np / 64, nq = kp.dc + kp.dk + 2 + (kp.use_linear ? kp.dc + 2 : 0), ntiles = nb * (nb + 1) / 2;
   size_t sm = sizeof(double) * (kp.dc * 2 * 66 + 8 * nq) + sizeof(int32_t) * kp.dk * 2 * 66;
   VZ_CUDA(cudaFuncSetAttribute(k_nll_grad_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   k_nll_grad_tiles<<<dim3(nb, nb), 256, sm, h->stream>>>(X, Z, np, n_valid, kp, Kinv, ldk, plane_rows > 0 ? plane_rows : lauum_plane_rows(np), alpha,

@@ -422,6 +422,21 @@ int make_tensor_map_f64(void* map, const double* base, uint64_t rows, uint64_t c
   return make_map(static_cast<CUtensorMap*>(map), base, rows, cols, ld, box_rows, promo);
 }
 
+int make_tensor_map_u8(void* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                       const uint32_t* box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return VZGP_ERR_CUDA; }
+  cuuint64_t gdim[3], gstride[2];
+  cuuint32_t bx[3], estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides[i];
+  CUresult r = fn(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base),
+                  gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (u8) failed with CUresult %d", (int)r); return VZGP_ERR_CUDA; }
+  return 0;
+}
+
 size_t score_smem_bytes(int dc, int dk, bool with_linf) {
   (void)with_linf; (void)dc;
   const size_t big = kStages * kStageDoubles > 3 * kMaxDc * kLD1 ? kStages * kStageDoubles : 3 * kMaxDc * kLD1;
@@ -503,9 +518,115 @@ int prepare_small_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// General scoring path: explicit K* and W = K* Linv^T, then one warp per candidate.  Taken by models the
+// fused kernels do not cover - today the `linear_coef` variant (tuned_gp_models.py:203-245), whose kernel
+// is Matern + feature-scaled linear (so k(x*, x*) is not constant) and whose GP has a constant mean.
+// Same results contract as k_score; ~3x the HBM/L2 traffic and DFMA instead of DMMA (k_gemm_nt_tri).
+// ---------------------------------------------------------------------------
+struct GeneralArgs {
+  const double* Xs;      // [mp x dc] padded candidates of this chunk
+  const double* Ks;      // [mp x np]
+  const double* W;       // [mp x np]
+  const double* X;       // [np x dc] trials
+  const double* alpha;
+  int mc, np, n_valid, dc;
+  KernelParams kp;
+  double sn2, mean_const, coef, radius;
+  int apply_tr, tr_rows, tr_strict, want_linf;
+  uint8_t tr_mask[kMaxDc];
+  double* score; double* mu; double* sigma; double* linf;
+  int* clamp_count;
+};
+
+__global__ void __launch_bounds__(256) k_general_finalize(GeneralArgs a) {
+  const int m = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+  if (m >= a.mc) return;
+  const double* ks = a.Ks + (size_t)m * a.np;
+  const double* w = a.W + (size_t)m * a.np;
+  double mean = 0.0, rs = 0.0;
+  for (int j = lane; j < a.n_valid; j += 32) mean = fma(ks[j], a.alpha[j], mean);
+  for (int j = lane; j < a.np; j += 32) rs = fma(w[j], w[j], rs);
+  double dist = INFINITY;
+  if (a.want_linf) {
+    for (int n = lane; n < a.tr_rows; n += 32) {
+      double mx = 0.0;
+      for (int d = 0; d < a.dc; ++d)
+        if (a.tr_mask[d]) mx = fmax(mx, fabs(a.Xs[(size_t)m * a.dc + d] - a.X[(size_t)n * a.dc + d]));
+      dist = fmin(dist, mx);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mean += __shfl_xor_sync(0xffffffffu, mean, o);
+    rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    dist = fmin(dist, __shfl_xor_sync(0xffffffffu, dist, o));
+  }
+  if (lane != 0) return;
+  double kss = a.kp.sf2;
+  if (a.kp.use_linear) {
+    double uu = 0.0;
+    for (int d = 0; d < a.dc; ++d) {
+      const double u = fma(a.Xs[(size_t)m * a.dc + d], a.kp.inv_ls_c[d], -a.kp.lin_b);
+      uu = fma(u, u, uu);
+    }
+    kss = fma(a.kp.lin_a, uu, kss);
+  }
+  mean += a.mean_const;
+  double var = kss - rs + a.sn2;
+  if (var < 0.0) { var = 0.0; atomicAdd(a.clamp_count, 1); }
+  const double sd = sqrt(var);
+  double sc = fma(a.coef, sd, mean);
+  if (a.apply_tr) {
+    const bool inside = (a.tr_strict ? (dist < a.radius) : (dist <= a.radius)) || (a.radius > 0.5);
+    sc = inside ? sc : (-1e4 - dist);
+  }
+  a.score[m] = sc;
+  if (a.mu) a.mu[m] = mean;
+  if (a.sigma) a.sigma[m] = sd;
+  if (a.linf) a.linf[m] = dist;
+}
+
+static int launch_score_general(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
+                                double* score, double* mu, double* sigma, double* linf) {
+  const int np = h->np, dc = h->dc, dk = h->dk;
+  constexpr int kChunk = 4096;
+  const size_t nks = (size_t)kChunk * np, nx = (size_t)kChunk * (dc > 0 ? dc : 1);
+  VZ_TRY(h->gen.reserve(sizeof(double) * (2 * nks + nx) + sizeof(int32_t) * (size_t)kChunk * (dk > 0 ? dk : 1)));
+  double* Ks = h->gen.as<double>();
+  double* W = Ks + nks;
+  double* Xp = W + nks;
+  int32_t* Zp = reinterpret_cast<int32_t*>(Xp + nx);
+  GeneralArgs a;
+  a.Ks = Ks; a.W = W; a.Xs = Xp; a.X = h->X.as<double>(); a.alpha = h->alpha.as<double>();
+  a.np = np; a.n_valid = h->n_valid; a.dc = dc; a.kp = h->kp; a.sn2 = h->sn2; a.mean_const = h->mean_const;
+  a.coef = acq->ucb_coefficient; a.radius = acq->trust_radius;
+  a.apply_tr = acq->use_trust_region ? 1 : 0;
+  a.tr_rows = (acq->tr_rows > 0 && acq->tr_rows < h->n_valid) ? acq->tr_rows : h->n_valid;
+  a.tr_strict = acq->tr_strict ? 1 : 0;
+  a.want_linf = (linf != nullptr) || (a.apply_tr && a.radius <= 0.5);
+  for (int d = 0; d < kMaxDc; ++d) a.tr_mask[d] = (d < dc) ? (acq->tr_dim_mask ? (acq->tr_dim_mask[d] ? 1 : 0) : 1) : 0;
+  a.clamp_count = h->small.as<int>();
+  for (int m0 = 0; m0 < M; m0 += kChunk) {
+    const int mc = M - m0 < kChunk ? M - m0 : kChunk, mp = round_up(mc, 64);
+    if (dc > 0) VZ_TRY(launch_pad_rows(h, Xs + (size_t)m0 * dc, mc, dc, mp, Xp));
+    if (dk > 0) VZ_TRY(launch_pad_rows_i32(h, Zs + (size_t)m0 * dk, mc, dk, mp, Zp));
+    VZ_TRY(launch_cross_kernel(h, Xp, Zp, mp, h->X.as<double>(), h->Z.as<int32_t>(), np, h->n_valid, h->kp, Ks, np));
+    VZ_TRY(launch_gemm_nt_tri(h, Ks, np, mp, h->Linv.as<double>(), np, np, W, np));
+    a.mc = mc;
+    a.score = score + m0; a.mu = mu ? mu + m0 : nullptr; a.sigma = sigma ? sigma + m0 : nullptr;
+    a.linf = linf ? linf + m0 : nullptr;
+    k_general_finalize<<<(mc + 7) / 8, 256, 0, h->stream>>>(a);
+    VZ_CHECK_LAUNCH();
+    h->launches++;
+  }
+  return 0;
+}
+
 int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, const vzgp_acq* acq,
                  double* score, double* mu, double* sigma, double* linf) {
   if (M <= 0) return 0;
+  if (h->kp.use_linear) return launch_score_general(h, Xs, Zs, M, acq, score, mu, sigma, linf);
   const int ntiles = (M + kTM - 1) / kTM;
   const int nblocks = (h->np + kBN - 1) / kBN;
   // Pools of a few tiles (acquisition-optimiser batches) take the trial-axis decomposition.
@@ -536,6 +657,11 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
     VZ_CHECK_LAUNCH();
     h->launches += 3;
     return 0;
+  }
+  {
+    static const int env_i8 = [] { const char* e = getenv("VZGP_SCORE_I8"); return e ? atoi(e) : 0; }();
+    const int want = h->score_i8 >= 0 ? h->score_i8 : env_i8;
+    if (want && score_i8_eligible(h, M)) return launch_score_i8(h, Xs, Zs, M, acq, score, mu, sigma, linf);
   }
   // Medium pools cannot fill the GPU with one CTA per tile: share each tile's output column
   // blocks between nsplit CTAs (each recomputes the cheap K* tile).

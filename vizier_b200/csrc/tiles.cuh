@@ -83,4 +83,33 @@ __device__ __forceinline__ void tile_d2(const double* sa, int lda, const double*
   }
 }
 
+// lin[i][j] = sum_d (a_i[d] w_d - b)(b_j[d] w_d - b),  w_d = 1/length scale, b = coef*shift: the feature-scaled
+// tfpk.Linear term of the `linear_coef` model (tuned_gp_models.py:220-230), a / b staged by stage_rows_T.
+template <typename Cfg, int TTM, int TTN>
+__device__ __forceinline__ void tile_lin(const double* sa, int lda, const double* sb, int ldb, const KernelParams& kp,
+                                         int ty, int tx, double (&lin)[TTM][TTN]) {
+#pragma unroll
+  for (int i = 0; i < TTM; ++i)
+#pragma unroll
+    for (int j = 0; j < TTN; ++j) lin[i][j] = 0.0;
+  for (int d = 0; d < kp.dc; ++d) {
+    const double w = kp.inv_ls_c[d];
+    double a[TTM], b[TTN];
+#pragma unroll
+    for (int i = 0; i < TTM; i += 2) {
+      double2 t = *reinterpret_cast<const double2*>(sa + d * lda + Cfg::row_of(ty, i));
+      a[i] = fma(t.x, w, -kp.lin_b); a[i + 1] = fma(t.y, w, -kp.lin_b);
+    }
+#pragma unroll
+    for (int j = 0; j < TTN; j += 2) {
+      double2 t = *reinterpret_cast<const double2*>(sb + d * ldb + Cfg::col_of(tx, j));
+      b[j] = fma(t.x, w, -kp.lin_b); b[j + 1] = fma(t.y, w, -kp.lin_b);
+    }
+#pragma unroll
+    for (int i = 0; i < TTM; ++i)
+#pragma unroll
+      for (int j = 0; j < TTN; ++j) lin[i][j] = fma(a[i], b[j], lin[i][j]);
+  }
+}
+
 }  // namespace vzgp

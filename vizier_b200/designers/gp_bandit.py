@@ -14,7 +14,9 @@ same metadata keys, same errors for unsupported search spaces.  What runs where:
 Multi-metric problems use the reference's scalarised UCB (gp_bandit.py:214-242): an independent
 multi-task GP (one factor, one alpha per metric) scored by the mean over `num_scalarizations`
 hyper-volume scalarisations, without a trust region.
-Not implemented (the reference supports them; SURVEY 8f "next"): `linear_coef`, transfer-learning
+`linear_coef` adds the feature-scaled linear kernel and the constant mean of tuned_gp_models.py:203-245
+(general launch sequences: no captured graph, explicit K* for the scoring).
+Not implemented (the reference supports them; SURVEY 8f "next"): transfer-learning
 priors (`set_priors`), parallel (q-) acquisitions, non-independent multi-task kernels; each raises
 NotImplementedError instead of silently doing something else.  Categorical parameters ARE supported
 end to end.  `padding_schedule` is accepted and has no numerical effect here: the kernels take
@@ -98,8 +100,9 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
       raise NotImplementedError('at most 8 metrics (libvzgp kMaxMetrics).')
     if self._n_metrics > 1 and multitask_type not in (None, 'INDEPENDENT') and getattr(multitask_type, 'name', '') != 'INDEPENDENT':
       raise NotImplementedError('only the INDEPENDENT multi-task kernel (the default) is implemented.')
-    if linear_coef is not None:
-      raise NotImplementedError('linear_coef (Matern + linear kernel) is not implemented.')
+    self._linear_coef = float(linear_coef) if linear_coef else None   # Matern + feature-scaled linear kernel, constant mean
+    if self._linear_coef and self._n_metrics > 1:
+      raise NotImplementedError('linear_coef with several metrics is not implemented.')
     self._ensemble_size = int(ensemble_size or 1)
     if self._ensemble_size < 1 or self._ensemble_size > ard_random_restarts:
       raise ValueError('ensemble_size must be in [1, ard_random_restarts].')
@@ -198,7 +201,7 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     z = cat if cat.shape[1] else None
     y = labels[:, 0] if self._n_metrics == 1 else labels     # [N] or [N, M]
     best, _ = ard.train_gp(self._ard_dev, cont, y, z, rng=ard_rng, random_restarts=self._ard_random_restarts,
-                           ensemble_size=self._ensemble_size, optimizer=self._ard_optimizer)
+                           ensemble_size=self._ensemble_size, optimizer=self._ard_optimizer, linear_coef=self._linear_coef)
     if self._ensemble_size > 1:
       # the E best restarts become the members of a uniform mixture (gp_models.py:200-223)
       self._last_params = list(best)
@@ -288,7 +291,8 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     # equal-weight mixture: every sample is a joint draw from one uniformly chosen member
     member = g.integers(0, len(factors), size=num_samples) if len(factors) > 1 else np.zeros(num_samples, int)
     samples = np.stack([factors[e][0] + normals[i] @ factors[e][1].T for i, e in enumerate(member)])
-    return np.vstack([self._output_warper.unwarp(samples[i][:, None]).reshape(-1) for i in range(num_samples)])
+    # one vectorised unwarp of all num_samples x num_trials values (the warpers act element-wise)
+    return self._output_warper.unwarp(samples.reshape(-1, 1)).reshape(samples.shape)
 
   def _sample_multi(self, dev, xs, zq, g, num_samples: int) -> np.ndarray:
     """Independent multi-task GP: the metrics share the posterior covariance and differ in the mean.

@@ -197,8 +197,16 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     zt = torch.from_numpy(np.ascontiguousarray(cat)).to(dev_a.device) if dk else None
     lo, hi = gp.param_bounds(dc, dk)
 
-    fns = ard.loss_functions(dev_a, xt, yt, zt, dc, dk, workers=min(ard.MAX_ARD_WORKERS, inits.shape[0]))
-    best, _ = self._ard_optimizer(inits, fns, list(zip(lo, hi)), best_n=1)
+    # all initial points advance in lock step, one CUDA-graph launch per round (ard.batch_loss_function); small
+    # studies (one fused kernel per evaluation) keep one host thread per point
+    if ard.BATCHED_ARD and ard._setulb is not None and xt.shape[0] > 64 and inits.shape[0] <= 16:   # pylint: disable=protected-access
+      fns = ard.batch_loss_function(dev_a, xt, yt, zt, inits.shape[0])
+    else:
+      fns = ard.loss_functions(dev_a, xt, yt, zt, dc, dk, workers=min(ard.MAX_ARD_WORKERS, inits.shape[0]))
+    try:
+      best, _ = self._ard_optimizer(inits, fns, list(zip(lo, hi)), best_n=1)
+    finally:
+      dev_a.set_int('dataflow_ctas', 0)
     return gp.GPHyperParams.from_vector(best[0], dc, dk)
 
   def _fit_all_features(self, params: gp.GPHyperParams, cont, cat, labels, pend_c, pend_z, noise_is_high: bool):
@@ -350,7 +358,7 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     chol, _, _ = dev_a.cholesky_retry(cov, jitter=1e-10, max_iters=8)
     g = np.random.default_rng(_gpb._seed_from(rng) if rng is not None else 0)
     samples = mean.cpu().numpy()[None, :] + g.standard_normal((num_samples, mean.shape[0])) @ chol.cpu().numpy().T
-    return np.vstack([self._output_warper.unwarp(samples[i][:, None]).reshape(-1) for i in range(num_samples)])
+    return self._output_warper.unwarp(samples.reshape(-1, 1)).reshape(samples.shape)
 
   @profiler.record_runtime
   def predict(self, trials: Sequence[Any], rng: Any = None, num_samples: Optional[int] = 1000):

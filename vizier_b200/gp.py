@@ -36,6 +36,12 @@ class GPHyperParams:
   continuous_length_scale_squared: np.ndarray
   observation_noise_variance: float
   categorical_length_scale_squared: Optional[np.ndarray] = None
+  # `linear_coef` variant (tuned_gp_models.py:203-245): None = plain Matern model.  With it the kernel gains
+  # (coef*slope)^2 sum_d (x_d/l_d - coef*shift)(x'_d/l_d - coef*shift) and the GP the mean coef*mean_constant.
+  linear_coef: Optional[float] = None
+  linear_slope_amplitude: float = 1.0
+  linear_shift: float = 0.0
+  mean_constant: float = 0.0
 
   def __post_init__(self):
     self.continuous_length_scale_squared = np.ascontiguousarray(
@@ -47,13 +53,20 @@ class GPHyperParams:
 
   # jaxopt's sorted-key flattening: categorical ls2, continuous ls2, noise, signal.
   def to_vector(self) -> np.ndarray:
+    lin = [] if not self.linear_coef else [self.linear_shift, self.linear_slope_amplitude, self.mean_constant]
     return np.concatenate([
-        self.categorical_length_scale_squared, self.continuous_length_scale_squared,
+        self.categorical_length_scale_squared, self.continuous_length_scale_squared, lin,
         [self.observation_noise_variance], [self.signal_variance]])
 
   @classmethod
-  def from_vector(cls, v: np.ndarray, dc: int, dk: int) -> 'GPHyperParams':
+  def from_vector(cls, v: np.ndarray, dc: int, dk: int, linear_coef: Optional[float] = None) -> 'GPHyperParams':
     v = np.asarray(v, np.float64)
+    if linear_coef:   # sorted keys: ..., linear_shift, linear_slope_amplitude, mean_fn, noise, signal
+      o = dk + dc
+      return cls(signal_variance=float(v[o + 4]), continuous_length_scale_squared=v[dk:o].copy(),
+                 observation_noise_variance=float(v[o + 3]), categorical_length_scale_squared=v[:dk].copy(),
+                 linear_coef=float(linear_coef), linear_slope_amplitude=float(v[o + 1]), linear_shift=float(v[o]),
+                 mean_constant=float(v[o + 2]))
     return cls(signal_variance=float(v[dk + dc + 1]),
                continuous_length_scale_squared=v[dk:dk + dc].copy(),
                observation_noise_variance=float(v[dk + dc]),
@@ -68,10 +81,19 @@ class GPHyperParams:
     p.categorical_length_scale_squared = (
         self.categorical_length_scale_squared.ctypes.data_as(C.POINTER(C.c_double))
         if self.categorical_length_scale_squared.size else None)
+    p.linear_coef = float(self.linear_coef or 0.0)
+    p.linear_slope_amplitude = float(self.linear_slope_amplitude)
+    p.linear_shift = float(self.linear_shift)
+    p.mean_constant = float(self.mean_constant)
     return p
 
 
-def param_bounds(dc: int, dk: int) -> tuple[np.ndarray, np.ndarray]:
+def param_bounds(dc: int, dk: int, linear: bool = False) -> tuple[np.ndarray, np.ndarray]:
+  if linear:   # shift and mean are unconstrained (+-inf, jaxopt_wrappers._get_bounds), the slope has the amplitude bounds
+    lo, hi = param_bounds(dc, dk)
+    o = dk + dc
+    return (np.concatenate([lo[:o], [-np.inf, SIGNAL_VARIANCE_BOUNDS[0], -np.inf], lo[o:]]),
+            np.concatenate([hi[:o], [np.inf, SIGNAL_VARIANCE_BOUNDS[1], np.inf], hi[o:]]))
   lo = np.concatenate([np.full(dk, LENGTH_SCALE_SQUARED_BOUNDS[0]), np.full(dc, LENGTH_SCALE_SQUARED_BOUNDS[0]),
                        [NOISE_VARIANCE_BOUNDS[0]], [SIGNAL_VARIANCE_BOUNDS[0]]])
   hi = np.concatenate([np.full(dk, LENGTH_SCALE_SQUARED_BOUNDS[1]), np.full(dc, LENGTH_SCALE_SQUARED_BOUNDS[1]),
@@ -341,13 +363,13 @@ class DeviceGP:
     dk = 0 if zt is None else zt.shape[1]
     p = params._c()
     loss = C.c_double(0.0)
-    grad = np.zeros(dc + dk + 2, np.float64)
+    grad = np.zeros(dc + dk + 2 + (3 if params.linear_coef else 0), np.float64)
     retries = _lib.check('vzgp_nll_grad_multi', self._lib.vzgp_nll_grad_multi(
         self._h, _ptr(xt), _ptr(zt), _ptr(yt), n, dc, dk, n if n_valid is None else n_valid, n_metrics,
         C.byref(p), C.byref(loss), grad.ctypes.data_as(C.POINTER(C.c_double))))
     return float(loss.value), grad, retries
 
-  def make_loss_fn(self, x, y, z=None, n_valid=None):
+  def make_loss_fn(self, x, y, z=None, n_valid=None, linear_coef: Optional[float] = None):
     """theta -> (loss, grad) closure for the ARD driver: the device tensors are resolved once and the
     parameter struct / output buffers are reused, so one evaluation costs a ctypes call (tens of
     microseconds of host time) instead of a dozen torch calls.  theta is in `GPHyperParams.to_vector`
@@ -359,9 +381,11 @@ class DeviceGP:
     nv = n if n_valid is None else n_valid
     ls_k = np.zeros(max(dk, 1), np.float64)
     ls_c = np.zeros(max(dc, 1), np.float64)
-    grad = np.zeros(dc + dk + 2, np.float64)
+    lin = 3 if linear_coef else 0
+    grad = np.zeros(dc + dk + 2 + lin, np.float64)
     loss = C.c_double(0.0)
     p = _lib.Params()
+    p.linear_coef = float(linear_coef or 0.0)
     p.continuous_length_scale_squared = ls_c.ctypes.data_as(C.POINTER(C.c_double))
     p.categorical_length_scale_squared = ls_k.ctypes.data_as(C.POINTER(C.c_double)) if dk else None
     fn, h = self._lib.vzgp_nll_grad_multi, self._h
@@ -373,8 +397,10 @@ class DeviceGP:
       theta = np.asarray(theta, np.float64)
       ls_k[:dk] = theta[:dk]
       ls_c[:dc] = theta[dk:dk + dc]
-      p.observation_noise_variance = float(theta[dk + dc])
-      p.signal_variance = float(theta[dk + dc + 1])
+      if lin:
+        p.linear_shift, p.linear_slope_amplitude, p.mean_constant = (float(t) for t in theta[dk + dc:dk + dc + 3])
+      p.observation_noise_variance = float(theta[dk + dc + lin])
+      p.signal_variance = float(theta[dk + dc + lin + 1])
       _lib.check('vzgp_nll_grad_multi', fn(h, px, pz, py, n, dc, dk, nv, n_metrics, pp, pl, pg))
       v = loss.value
       if not np.isfinite(v):

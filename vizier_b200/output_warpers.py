@@ -87,7 +87,39 @@ class HalfRankComponent:
     y = _validate_labels(labels).flatten()
     if np.isnan(y).any():
       raise ValueError('unwarp does not support nan values.')
-    return np.array([self._unwarp_one(v) for v in y])[:, None]
+    return self._unwarp_many(y)[:, None]
+
+  def _unwarp_many(self, y: np.ndarray) -> np.ndarray:
+    """`_unwarp_one` for a whole array at once (`sample()` unwarps num_samples x num_trials values): the same
+    branches in the same order, evaluated with masks; `tests/test_output_warpers.py` pins it to the scalar form."""
+    orig, warped = self._orig, self._warped
+    nw = len(warped)
+    out = y.astype(np.float64).copy()
+    todo = y < self._orig_median
+    if not todo.any():
+      return out
+    lab = y[todo]
+    idx = np.searchsorted(warped, lab)
+    lo_c = np.maximum(0, idx - 1)
+    hi_c = np.minimum(nw, idx + 1)                      # candidates warped[lo_c:hi_c], one or two values
+    d0 = np.abs(warped[lo_c] - lab)
+    has2 = hi_c - lo_c > 1
+    d1 = np.where(has2, np.abs(warped[np.minimum(lo_c + 1, nw - 1)] - lab), np.inf)
+    best = np.where(d1 < d0, 1, 0)                      # argmin inside the candidate window ...
+    best = np.minimum(best, nw - 1)
+    close = np.isclose(warped[best], lab)               # ... used, as in the reference, as an index into `warped`
+    res = np.empty_like(lab)
+    res[close] = orig[best[close]]
+    below = ~close & (lab < np.min(warped))
+    if below.any():
+      res[below] = orig[0] - (np.abs(lab[below] - warped[0]) / (warped[-1] - warped[0])) * (orig[-1] - orig[0])
+    mid = ~close & ~below
+    if mid.any():
+      lower = np.searchsorted(warped, lab[mid]) - 1
+      upper = lower + 1
+      res[mid] = orig[lower] + (lab[mid] - warped[lower]) * (orig[upper] - orig[lower]) / (warped[upper] - warped[lower])
+    out[todo] = res
+    return out
 
 
 class LogWarperComponent:
