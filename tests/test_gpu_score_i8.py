@@ -66,8 +66,8 @@ def test_i8_scores_match_oracle_and_dmma(dev, n, d, sf2):
   np.testing.assert_allclose(out['stddev'].cpu().numpy()[sel], aux['stddev'], atol=TOL, rtol=0)
   np.testing.assert_allclose(out['mean'].cpu().numpy()[sel], aux['mean'], atol=TOL, rtol=0)
   np.testing.assert_allclose(out['score'].cpu().numpy()[sel], want, atol=TOL, rtol=0)
-  # the two device kernels on the whole pool: the mean is the same arithmetic, sigma agrees far below TOL
-  np.testing.assert_array_equal(out['mean'].cpu().numpy(), ref['mean'].cpu().numpy())
+  # the two device kernels on the whole pool: the mean differs by its summation order only, sigma agrees far below TOL
+  np.testing.assert_allclose(out['mean'].cpu().numpy(), ref['mean'].cpu().numpy(), atol=1e-11, rtol=0)
   np.testing.assert_array_equal(out['linf_distance'].cpu().numpy(), ref['linf_distance'].cpu().numpy())
   np.testing.assert_allclose(out['stddev'].cpu().numpy(), ref['stddev'].cpu().numpy(), atol=1e-11, rtol=0)
   # throughput variant (no aux, pre-scaled features)

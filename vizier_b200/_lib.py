@@ -12,7 +12,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libvzgp.so')
+# VZGP_LIB: an alternative build of the same library (instrumented debug builds, tools/i8_timing.py)
+LIB_PATH = os.environ.get('VZGP_LIB') or os.path.join(_HERE, '_lib', 'libvzgp.so')
 
 VZGP_ERR_ARG = -1
 VZGP_ERR_CUDA = -2

@@ -35,13 +35,24 @@
 #include "score_small.cuh"
 #include "tiles.cuh"
 
+#ifdef VZ_I8_TIMING
+namespace vzgp { __device__ long long g_i8_t[16]; }
+#define VZ_I8T_DECL long long t_a = 0, t_b = 0; (void)t_a; (void)t_b
+#define VZ_I8T_START(v) do { v = clock64(); } while (0)
+#define VZ_I8T_ADD(slot, v) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_i8_t[slot] += clock64() - (v); } while (0)
+#else
+#define VZ_I8T_DECL do {} while (0)
+#define VZ_I8T_START(v) do {} while (0)
+#define VZ_I8T_ADD(slot, v) do {} while (0)
+#endif
+
 namespace vzgp {
 
 namespace {
 
-using GP1 = GemmCfg<64, 64, 16, 2, 4>;
-constexpr int kWorkers = 512;                 // 16 worker warps: phase 1 + epilogue
-constexpr int kI8Threads = kWorkers + 64;     // + TMA producer warp + MMA issuer warp
+constexpr int kKWarps = 16;                   // K* warps (phase 1); 22 warps in all -> 80 registers per thread
+constexpr int kEWarps = 4;                    // epilogue warps: one per TMEM lane quarter
+constexpr int kI8Threads = (kKWarps + kEWarps + 2) * 32;     // + TMA producer warp + MMA issuer warp
 constexpr int kDigits = 7;
 constexpr int kGroups = 7;                    // g = s + t - 2 in [0, 6]
 constexpr int kJT = 128;                      // Linv rows per j tile = MMA M
@@ -57,7 +68,9 @@ struct I8Args {
   alignas(64) CUtensorMap mapK;   // K* digit scratch as u8 [grid*7*64 rows][np], box 64 x 128, SWIZZLE_128B
   alignas(64) CUtensorMap mapL;   // Linv digit planes as u8 [7][np][np], box 1 x 128 x 128, SWIZZLE_128B
   ScoreArgs s;                    // candidates, model, outputs (mapA / mapB / scratch unused)
-  uint8_t* kdig;                  // [grid][7][64][np]
+  uint8_t* kdig;                  // [grid][nbuf][7][64][np]
+  int nbuf;                       // 2: phase 1 of the next tile overlaps phase 2; 1: back to back (large Dc)
+  int misc_bytes;                 // shared memory between the operand ring and the (nbuf = 2) phase-1 staging
   const double* lscale;           // [np]  2^(ea + eb_j - 32)
   double kscale;                  // 2^(56 - ea)
 };
@@ -82,9 +95,10 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity
   }
 }
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_3d_elect(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(smem_u32(smem_dst)),
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n\t}\n" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
@@ -111,15 +125,34 @@ __host__ __device__ inline int balanced_scale_exp(double m) {
   const double f = frexp(m, &e);
   return f < 0.996 ? e + 1 : e + 2;
 }
+// The issuing warps run their loops with warp-uniform control flow and elect the issuing lane INSIDE the asm
+// statement: ptxas then keeps descriptors and addresses in uniform registers.  (Issuing from an `if (lane == 0)`
+// region costs an ELECT + R2UR round trip per instruction: 131 cycles per MMA instead of 48, tools/umma_rate.cu.)
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, unsigned bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -130,6 +163,19 @@ __device__ __forceinline__ void tmem_ld4(uint32_t addr, int32_t (&v)[4]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+__device__ __forceinline__ void g_i8_t_tiles() {
+#ifdef VZ_I8_TIMING
+  g_i8_t[15] += 1;
+#endif
+}
+
+// Warp roles: 8 K* warps (phase 1 of tile n+1 while tile n is in phase 2), 8 epilogue warps, one TMA producer
+// warp, one MMA issuer warp.  Hand-over by mbarriers only:
+//   kready[b]  K* warps -> producer + epilogue: digit planes / mu / L-inf of the tile in buffer b are complete
+//   kfree[b]   epilogue -> K* warps: the tile that used buffer b is finished (all its TMA reads are consumed)
+//   bfull/bempty, afull/aempty   TMA <-> MMA operand buffers;  tfull/tempty   MMA <-> epilogue accumulators
+// nbuf = 2 overlaps the phases (digit scratch and phase-1 staging have their own memory); nbuf = 1 (large Dc:
+// the staging does not fit next to the operand ring) runs them back to back with the staging aliased onto the ring.
 template <bool WITH_LINF>
 __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constant__ I8Args ia) {
   const ScoreArgs& a = ia.s;
@@ -137,40 +183,43 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>(smem_raw) +
                   ((1024u - (static_cast<unsigned>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u);
   constexpr int LD = kLD1;
-  const int dc = a.kp.dc, dk = a.kp.dk, np = a.np;
-  // phase 2 buffers; phase 1 staging aliases them (the phases do not overlap in time)
+  const int dc = a.kp.dc, dk = a.kp.dk, np = a.np, nbuf = ia.nbuf;
   uint8_t* bbuf = smem;                                  // [2][7][64][128]
   uint8_t* aring = smem + 2 * kBBufBytes;                // [kASlots][128][128]
-  double* sa = reinterpret_cast<double*>(smem);          // [dc][LD]     candidates (transposed)
-  double* sb = sa + dc * LD;                             // [2][dc][LD]  trials, double buffered
   double* s_alpha = reinterpret_cast<double*>(smem + kRingBytes);   // [2][64]
-  double* s_mu = s_alpha + 128;                          // [64]
-  double* s_linf = s_mu + 64;                            // [64]
-  double* s_red = s_linf + 64;                           // [4][64] row sums of the four TMEM lane quarters
+  double* s_mu = s_alpha + 128;                          // [2][64]
+  double* s_linf = s_mu + 128;                           // [2][64]
+  double* s_red = s_linf + 128;                          // [4][64] row sums of the four TMEM lane quarters
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 256);
   uint64_t* bfull = bars;              // [2]
   uint64_t* bempty = bars + 2;         // [2]
   uint64_t* afull = bars + 4;          // [kASlots]
   uint64_t* aempty = bars + 4 + kASlots;
   uint64_t* tfull = bars + 4 + 2 * kASlots;     // accumulators of a j tile complete
-  uint64_t* tempty = tfull + 1;                 // ... drained by the 16 worker warps
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 1);
+  uint64_t* tempty = tfull + 1;                 // ... drained by the epilogue warps
+  uint64_t* kready = tempty + 1;                // [2]
+  uint64_t* kfree = kready + 2;                 // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(kfree + 2);
   int32_t* za = reinterpret_cast<int32_t*>(s_tmem + 2);  // [dk][LD]
   int32_t* zb = za + dk * LD;                            // [dk][LD]
   uint8_t* s_mask = reinterpret_cast<uint8_t*>(zb + dk * LD);  // [kMaxDc]
+  // phase-1 staging: behind everything else (nbuf = 2) or aliased onto the operand ring (nbuf = 1)
+  double* stage = nbuf == 2 ? reinterpret_cast<double*>(smem + ((kRingBytes + ia.misc_bytes + 15) & ~15)) : reinterpret_cast<double*>(smem);
+  double* sa = stage;                                    // [dc][LD]     candidates (transposed)
+  double* sb = sa + dc * LD;                             // [2][dc][LD]  trials, double buffered
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ty = tid / 16, tx = tid % 16;      // phase-1 mapping (32 x 16 threads), workers only
-  const bool is_worker = warp < kWorkers / 32;
-  const bool is_producer = warp == kWorkers / 32;
-  const bool is_mma = warp == kWorkers / 32 + 1;
-  uint8_t* kd = ia.kdig + (size_t)blockIdx.x * kDigits * kTM * np;
+  const bool is_kwarp = warp < kKWarps;
+  const bool is_epi = warp >= kKWarps && warp < kKWarps + kEWarps;
+  const bool is_producer = warp == kKWarps + kEWarps;
+  const bool is_mma = warp == kKWarps + kEWarps + 1;
   if (tid < kMaxDc) s_mask[tid] = a.tr_mask[tid];
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(bfull + i, 1); mbar_init(bempty + i, 1); }
     for (int i = 0; i < kASlots; ++i) { mbar_init(afull + i, 1); mbar_init(aempty + i, 1); }
     mbar_init(tfull, 1);
-    mbar_init(tempty, kWorkers / 32);
+    mbar_init(tempty, kEWarps);
+    for (int i = 0; i < 2; ++i) { mbar_init(kready + i, kKWarps * 32); mbar_init(kfree + i, kEWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (is_mma) {
@@ -181,253 +230,332 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
-  int clamped = 0;
-  auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(kWorkers) : "memory"); };
 
   const int ntiles = (a.M + kTM - 1) / kTM;
   const int njt = (np + kJT - 1) / kJT;
-  const double* XTs = a.XT;
-  const double* XTu = a.XT + (size_t)dc * np;
-  unsigned b_n = 0, a_n = 0, jt_n = 0;   // B buffers / A slots / j tiles issued (producer), consumed (MMA thread, workers)
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int m0 = tile * kTM;
-    if (is_producer) {
-      __syncthreads();   // phase 1 of this tile is complete: the digit scratch is visible, the staging smem is free
-      if (lane == 0) {
-        for (int jt = 0; jt < njt; ++jt) {
-          for (int kc = 0; kc <= jt; ++kc) {
-            const int buf = b_n & 1;
-            mbar_wait_bounded(bempty + buf, ((b_n >> 1) & 1) ^ 1);
-            mbar_expect_tx(bfull + buf, kBBufBytes);
-            for (int s = 0; s < kDigits; ++s)
-              tma_load_2d(bbuf + buf * kBBufBytes + s * kBPlaneBytes, &ia.mapK, kc * kKC,
-                          ((int)blockIdx.x * kDigits + s) * kTM, bfull + buf);
-            ++b_n;
-            for (int t = 0; t < kDigits; ++t) {
-              const int slot = a_n % kASlots;
-              mbar_wait_bounded(aempty + slot, ((a_n / kASlots) & 1) ^ 1);
-              mbar_expect_tx(afull + slot, kASlotBytes);
-              tma_load_3d(aring + slot * kASlotBytes, &ia.mapL, kc * kKC, jt * kJT, t, afull + slot);
-              ++a_n;
-            }
+  if (is_producer) {
+    // ================= TMA producer warp (uniform control flow, elected issue) =================
+    unsigned b_n = 0, a_n = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int kb = it % nbuf;
+      VZ_I8T_DECL;
+      VZ_I8T_START(t_a);
+      mbar_wait_bounded(kready + kb, (it / nbuf) & 1);     // the tile's digit planes are complete and fenced
+      VZ_I8T_ADD(11, t_a);
+      VZ_I8T_START(t_a);
+      const int krow0 = ((int)blockIdx.x * nbuf + kb) * kDigits * kTM;
+      for (int jt = 0; jt < njt; ++jt) {
+        for (int kc = 0; kc <= jt; ++kc) {
+          const int buf = b_n & 1;
+          VZ_I8T_START(t_b);
+          mbar_wait_bounded(bempty + buf, ((b_n >> 1) & 1) ^ 1);
+          VZ_I8T_ADD(8, t_b);
+          mbar_expect_tx_elect(bfull + buf, kBBufBytes);
+          for (int s = 0; s < kDigits; ++s)
+            tma_load_2d_elect(bbuf + buf * kBBufBytes + s * kBPlaneBytes, &ia.mapK, kc * kKC, krow0 + s * kTM, bfull + buf);
+          ++b_n;
+          for (int t = 0; t < kDigits; ++t) {
+            const int slot = a_n % kASlots;
+            VZ_I8T_START(t_b);
+            mbar_wait_bounded(aempty + slot, ((a_n / kASlots) & 1) ^ 1);
+            VZ_I8T_ADD(9, t_b);
+            mbar_expect_tx_elect(afull + slot, kASlotBytes);
+            tma_load_3d_elect(aring + slot * kASlotBytes, &ia.mapL, kc * kKC, jt * kJT, t, afull + slot);
+            ++a_n;
           }
         }
       }
-      __syncwarp();
-      continue;
+      VZ_I8T_ADD(10, t_a);
     }
-    if (is_mma) {
-      __syncthreads();
-      if (lane == 0) {
-        for (int jt = 0; jt < njt; ++jt) {
-          mbar_wait_bounded(tempty, (jt_n & 1) ^ 1);   // the previous j tile's accumulators have been read
-          tc_fence_after();
-          unsigned touched = 0;
-          for (int kc = 0; kc <= jt; ++kc) {
-            const int buf = b_n & 1;
-            mbar_wait_bounded(bfull + buf, (b_n >> 1) & 1);
-            ++b_n;
-            const int ksteps = (np - kc * kKC) >= kKC ? 4 : (np - kc * kKC + 31) / 32;   // the last chunk may be half
-            const uint32_t bbase = smem_u32(bbuf + buf * kBBufBytes);
-            for (int t = 0; t < kDigits; ++t) {
-              const int slot = a_n % kASlots;
-              mbar_wait_bounded(afull + slot, (a_n / kASlots) & 1);
-              ++a_n;
-              tc_fence_after();
-              const uint64_t da = umma_desc_sw128(smem_u32(aring + slot * kASlotBytes));
-              constexpr uint32_t idesc = umma_idesc_i8();
-              for (int s = 0; s + t < kGroups; ++s) {     // digit pair (s+1, t+1): group g = s + t
-                const int g = s + t;
-                const uint64_t db = umma_desc_sw128(bbase + s * kBPlaneBytes);
-                for (int kk = 0; kk < ksteps; ++kk) {
-                  umma_i8(tmem + g * kTM, da + 2 * kk, db + 2 * kk, idesc, (touched >> g) & 1u);
-                  touched |= 1u << g;
-                }
+  } else if (is_mma) {
+    // ================= MMA issuer warp (uniform control flow, elected issue) =================
+    unsigned b_n = 0, a_n = 0, jt_n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      VZ_I8T_DECL;
+      VZ_I8T_START(t_a);
+      for (int jt = 0; jt < njt; ++jt) {
+        VZ_I8T_START(t_b);
+        mbar_wait_bounded(tempty, (jt_n & 1) ^ 1);   // the previous j tile's accumulators have been read
+        VZ_I8T_ADD(4, t_b);
+        tc_fence_after();
+        unsigned touched = 0;
+        for (int kc = 0; kc <= jt; ++kc) {
+          const int buf = b_n & 1;
+          VZ_I8T_START(t_b);
+          mbar_wait_bounded(bfull + buf, (b_n >> 1) & 1);
+          VZ_I8T_ADD(5, t_b);
+          ++b_n;
+          const int ksteps = (np - kc * kKC) >= kKC ? 4 : (np - kc * kKC + 31) / 32;   // the last chunk may be half
+          const uint32_t bbase = smem_u32(bbuf + buf * kBBufBytes);
+          for (int t = 0; t < kDigits; ++t) {
+            const int slot = a_n % kASlots;
+            VZ_I8T_START(t_b);
+            mbar_wait_bounded(afull + slot, (a_n / kASlots) & 1);
+            VZ_I8T_ADD(6, t_b);
+            ++a_n;
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(aring + slot * kASlotBytes));
+            constexpr uint32_t idesc = umma_idesc_i8();
+            // (The A-operand collector - collector::a::fill/use/lastuse over the MMAs that share a Linv plane and
+            // k step - was tried: correct, but the MMAs then no longer overlap their operand fetches: 99 instead of
+            // 84 cycles per MMA in this loop, 92 against 83 in tools/umma_rate.cu.)
+            for (int s = 0; s + t < kGroups; ++s) {     // digit pair (s+1, t+1): group g = s + t
+              const int g = s + t;
+              const uint64_t db = umma_desc_sw128(bbase + s * kBPlaneBytes);
+              for (int kk = 0; kk < ksteps; ++kk) {
+                umma_i8(tmem + g * kTM, da + 2 * kk, db + 2 * kk, idesc, (touched >> g) & 1u);
+                touched |= 1u << g;
               }
-              umma_commit(aempty + slot);   // slot reusable once these MMAs have read it
             }
-            umma_commit(bempty + buf);
+            umma_commit(aempty + slot);   // slot reusable once these MMAs have read it
           }
-          umma_commit(tfull);
-          ++jt_n;
+          umma_commit(bempty + buf);
         }
+        umma_commit(tfull);
+        ++jt_n;
       }
-      __syncwarp();
-      continue;
+      VZ_I8T_ADD(7, t_a);
     }
-    // ================= worker warps =================
-    consumer_sync();  // previous tile fully consumed by the workers (sa, s_mu, s_red)
-    for (int e = tid; e < kTM * dc; e += kWorkers) {
-      const int r = e / dc, d = e - r * dc;
-      const int gr = m0 + r;
-      const double v = gr < a.M ? __ldg(a.Xs + (size_t)gr * dc + d) : 0.0;
-      sa[d * LD + r] = WITH_LINF ? v : v * a.kp.inv_ls_c[d];
-    }
-    if (dk > 0) stage_rows_T_i32(a.Zs, a.M, dk, m0, kTM, za, LD, kWorkers);
-
-    // ---------------- phase 1: K* tile -> digits, mean, trust-region distance ----------------
-    auto stage_trials = [&](int jb, int buf) {
-      double* dst = sb + buf * dc * LD;
-      const double* src = WITH_LINF ? XTu : XTs;
-      for (int c = tid; c < dc * 32; c += kWorkers) {       // dc rows x 32 chunks of 16 B
-        const int d = c >> 5, q = c & 31;
-        cp_async16(dst + d * LD + q * 2, src + (size_t)d * np + jb * 64 + q * 2, true);
-      }
-      if (tid < 32) cp_async16(s_alpha + buf * 64 + tid * 2, a.alpha + jb * 64 + tid * 2, true);
+  } else if (is_kwarp) {
+    // ================= K* warps: phase 1 of every tile, one tile ahead of phase 2 =================
+    // 512 threads, 2 x 4 outputs each on the 64 x 64 block: rows 2 ty + i, columns (j/2) 32 + 2 tx + j%2
+    // (ty = tid / 16, tx = tid % 16)
+    struct GP {
+      __device__ static int row_of(int ty, int i) { return ty * 2 + i; }
+      __device__ static int col_of(int tx, int j) { return (j >> 1) * 32 + tx * 2 + (j & 1); }
     };
-    double mu_part[2], lmin[2];
+    constexpr int kKT = kKWarps * 32;
+    auto ksync = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(kKT) : "memory"); };
+    const int ty = tid / 16, tx = tid % 16;
+    const double* XTs = a.XT;
+    const double* XTu = a.XT + (size_t)dc * np;
+    unsigned it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int m0 = tile * kTM;
+      const int kb = it % nbuf;
+      VZ_I8T_DECL;
+      VZ_I8T_START(t_a);
+      mbar_wait_bounded(kfree + kb, ((it / nbuf) & 1) ^ 1);   // the tile that used this buffer is finished
+      if (tid == 0) { VZ_I8T_ADD(12, t_a); }
+      VZ_I8T_START(t_a);
+      uint8_t* kd = ia.kdig + ((size_t)blockIdx.x * nbuf + kb) * kDigits * kTM * np;
+      for (int e = tid; e < kTM * dc; e += kKT) {
+        const int r = e / dc, d = e - r * dc;
+        const int gr = m0 + r;
+        const double v = gr < a.M ? __ldg(a.Xs + (size_t)gr * dc + d) : 0.0;
+        sa[d * LD + r] = WITH_LINF ? v : v * a.kp.inv_ls_c[d];
+      }
+      if (dk > 0) stage_rows_T_i32(a.Zs, a.M, dk, m0, kTM, za, LD, kKT);
+      auto stage_trials = [&](int jb, int buf) {
+        double* dst = sb + buf * dc * LD;
+        const double* src = WITH_LINF ? XTu : XTs;
+        for (int c = tid; c < dc * 32; c += kKT) {       // dc rows x 32 chunks of 16 B
+          const int d = c >> 5, q = c & 31;
+          cp_async16(dst + d * LD + q * 2, src + (size_t)d * np + jb * 64 + q * 2, true);
+        }
+        if (tid < 32) cp_async16(s_alpha + buf * 64 + tid * 2, a.alpha + jb * 64 + tid * 2, true);
+      };
+      double mu_part[2], lmin[2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) { mu_part[i] = 0.0; lmin[i] = INFINITY; }
-    const int nj = np / 64;
-    stage_trials(0, 0);
-    cp_async_commit();
-    for (int jb = 0; jb < nj; ++jb) {
-      const int buf = jb & 1;
-      if (jb + 1 < nj) stage_trials(jb + 1, buf ^ 1);
+      for (int i = 0; i < 2; ++i) { mu_part[i] = 0.0; lmin[i] = INFINITY; }
+      const int nj = np / 64;
+      stage_trials(0, 0);
       cp_async_commit();
-      cp_async_wait<1>();
-      consumer_sync();
-      if (dk > 0) {
-        stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD, kWorkers);
-        consumer_sync();
-      }
-      const double* sbj = sb + buf * dc * LD;
-      const double* alj = s_alpha + buf * 64;
-      double d2[2][4], lf[2][4];
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { d2[i][j] = 0.0; lf[i][j] = 0.0; }
-      for (int d = 0; d < dc; ++d) {
-        const double2 av = *reinterpret_cast<const double2*>(sa + d * LD + GP1::row_of(ty, 0));
-        const double2 b0 = *reinterpret_cast<const double2*>(sbj + d * LD + GP1::col_of(tx, 0));
-        const double2 b1 = *reinterpret_cast<const double2*>(sbj + d * LD + GP1::col_of(tx, 2));
-        const double aa[2] = {av.x, av.y}, bb[4] = {b0.x, b0.y, b1.x, b1.y};
-        if (WITH_LINF) {
-          const double w = a.kp.inv_ls2_c[d];
-          const bool in_tr = s_mask[d] != 0;
+      for (int jb = 0; jb < nj; ++jb) {
+        const int buf = jb & 1;
+        if (jb + 1 < nj) stage_trials(jb + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        ksync();
+        if (dk > 0) {
+          stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD, kKT);
+          ksync();
+        }
+        {
+          constexpr int zoff = 0;
+          const double* sbj = sb + buf * dc * LD + zoff;
+          const double* alj = s_alpha + buf * 64 + zoff;
+          double d2[2][4], lf[2][4];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const double df = aa[i] - bb[j];
-              d2[i][j] = fma(df * df, w, d2[i][j]);
-              if (in_tr) lf[i][j] = fmax(lf[i][j], fabs(df));
+            for (int j = 0; j < 4; ++j) { d2[i][j] = 0.0; lf[i][j] = 0.0; }
+          for (int d = 0; d < dc; ++d) {
+            const double2 av = *reinterpret_cast<const double2*>(sa + d * LD + GP::row_of(ty, 0));
+            const double2 b0 = *reinterpret_cast<const double2*>(sbj + d * LD + GP::col_of(tx, 0));
+            const double2 b1 = *reinterpret_cast<const double2*>(sbj + d * LD + GP::col_of(tx, 2));
+            const double aa[2] = {av.x, av.y}, bb[4] = {b0.x, b0.y, b1.x, b1.y};
+            if (WITH_LINF) {
+              const double w = a.kp.inv_ls2_c[d];
+              const bool in_tr = s_mask[d] != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const double df = aa[i] - bb[j];
+                  d2[i][j] = fma(df * df, w, d2[i][j]);
+                  if (in_tr) lf[i][j] = fmax(lf[i][j], fabs(df));
+                }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const double df = aa[i] - bb[j];
+                  d2[i][j] = fma(df, df, d2[i][j]);
+                }
             }
-        } else {
+          }
+          for (int k = 0; k < dk; ++k) {
+            const double w = a.kp.inv_ls2_k[k];
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 2; ++i) {
+              const int avz = za[k * LD + GP::row_of(ty, i)];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) d2[i][j] += (avz != zb[k * LD + zoff + GP::col_of(tx, j)]) ? w : 0.0;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            long long q[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const double df = aa[i] - bb[j];
-              d2[i][j] = fma(df, df, d2[i][j]);
+              const int cj = zoff + GP::col_of(tx, j);
+              const bool valid = (jb * 64 + cj) < a.n_valid;
+              const double kv = valid ? matern52(d2[i][j], a.kp.sf2) : 0.0;
+              mu_part[i] = fma(kv, alj[GP::col_of(tx, j)], mu_part[i]);
+              if (WITH_LINF && (jb * 64 + cj) < a.tr_rows) lmin[i] = fmin(lmin[i], lf[i][j]);
+              q[j] = __double2ll_rn(kv * ia.kscale);    // |q| < 2^55
             }
-        }
-      }
-      for (int k = 0; k < dk; ++k) {
-        const double w = a.kp.inv_ls2_k[k];
+            uint8_t* row = kd + (size_t)GP::row_of(ty, i) * np + jb * 64 + zoff;
+            // balanced base-256 digits, least significant first: digit = low byte (two's complement), carry (q + 128) >> 8
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int avz = za[k * LD + GP1::row_of(ty, i)];
+            for (int s = kDigits - 1; s >= 0; --s) {
+              uint8_t* p = row + (size_t)s * kTM * np;
+              *reinterpret_cast<uint16_t*>(p + GP::col_of(tx, 0)) = (uint16_t)((q[0] & 255ll) | ((q[1] & 255ll) << 8));
+              *reinterpret_cast<uint16_t*>(p + GP::col_of(tx, 2)) = (uint16_t)((q[2] & 255ll) | ((q[3] & 255ll) << 8));
 #pragma unroll
-          for (int j = 0; j < 4; ++j) d2[i][j] += (avz != zb[k * LD + GP1::col_of(tx, j)]) ? w : 0.0;
+              for (int j = 0; j < 4; ++j) q[j] = (q[j] + 128) >> 8;
+            }
+          }
         }
+        ksync();
       }
+      cp_async_wait<0>();
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        long long q[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cj = GP1::col_of(tx, j);
-          const bool valid = (jb * 64 + cj) < a.n_valid;
-          const double kv = valid ? matern52(d2[i][j], a.kp.sf2) : 0.0;
-          mu_part[i] = fma(kv, alj[cj], mu_part[i]);
-          if (WITH_LINF && (jb * 64 + cj) < a.tr_rows) lmin[i] = fmin(lmin[i], lf[i][j]);
-          q[j] = __double2ll_rn(kv * ia.kscale);    // |q| < 2^55
+        for (int o = 8; o > 0; o >>= 1) {
+          mu_part[i] += __shfl_xor_sync(0xffffffffu, mu_part[i], o);
+          if (WITH_LINF) lmin[i] = fmin(lmin[i], __shfl_xor_sync(0xffffffffu, lmin[i], o));
         }
-        uint8_t* row = kd + (size_t)GP1::row_of(ty, i) * np + jb * 64;
-        // balanced base-256 digits, least significant first: digit = low byte (two's complement), carry (q + 128) >> 8
-#pragma unroll
-        for (int s = kDigits - 1; s >= 0; --s) {
-          uint8_t* p = row + (size_t)s * kTM * np;
-          *reinterpret_cast<uint16_t*>(p + GP1::col_of(tx, 0)) = (uint16_t)((q[0] & 255ll) | ((q[1] & 255ll) << 8));
-          *reinterpret_cast<uint16_t*>(p + GP1::col_of(tx, 2)) = (uint16_t)((q[2] & 255ll) | ((q[3] & 255ll) << 8));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) q[j] = (q[j] + 128) >> 8;
+        if (tx == 0) {
+          s_mu[kb * 64 + GP::row_of(ty, i)] = mu_part[i];
+          s_linf[kb * 64 + GP::row_of(ty, i)] = lmin[i];
         }
       }
-      consumer_sync();
+      fence_proxy_async();  // generic-proxy writes (digit scratch, aliased smem) before async-proxy (TMA) accesses
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(kready + kb)) : "memory");
+      if (tid == 0) { VZ_I8T_ADD(0, t_a); }
     }
-    cp_async_wait<0>();
+  } else if (is_epi) {
+    // ================= epilogue warps: TMEM -> sum_j W[i,j]^2 -> scores =================
+    // warp e reads TMEM lanes 32 (e % 4) .. +31 (Linv rows j), all 64 columns (candidates)
+    constexpr int kET = kEWarps * 32;
+    auto esync = [&]() { asm volatile("bar.sync 2, %0;\n" ::"n"(kET) : "memory"); };
+    const int etid = tid - kKWarps * 32;
+    const int quarter = warp & 3;
+    int clamped = 0;
+    unsigned jt_n = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int m0 = tile * kTM;
+      const int kb = it % nbuf;
+      VZ_I8T_DECL;
+      VZ_I8T_START(t_a);
+      // acc[grp]: this warp's sum over its 32 Linv rows (and over the j tiles) for candidate 8 grp + c(lane),
+      // c(lane) = 4 bit4 + 2 bit3 + bit2 - the 32 x 8 -> 8 reduce-scatter below leaves it replicated on 4 lanes
+      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int jt = 0; jt < njt; ++jt) {
+        VZ_I8T_START(t_b);
+        mbar_wait_bounded(tfull, jt_n & 1);
+        if (etid == 0) { VZ_I8T_ADD(1, t_b); }
+        VZ_I8T_START(t_b);
+        ++jt_n;
+        tc_fence_after();
+        const int j = jt * kJT + quarter * 32 + lane;
+        const double sc = j < np ? __ldg(ia.lscale + j) : 0.0;
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+        for (int grp = 0; grp < 8; ++grp) {
+          double v[8];
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        mu_part[i] += __shfl_xor_sync(0xffffffffu, mu_part[i], o);
-        if (WITH_LINF) lmin[i] = fmin(lmin[i], __shfl_xor_sync(0xffffffffu, lmin[i], o));
+          for (int c4 = 0; c4 < 2; ++c4) {
+            int32_t G[kGroups][4];
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) tmem_ld4(taddr + g * kTM + grp * 8 + c4 * 4, G[g]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              // sum_g G_g 2^(-8(g+2)) = 2^-32 (hi + lo 2^-32),  hi = G0 2^16 + G1 2^8 + G2,  lo = G3 2^24 + ... + G6
+              const long long hi = ((long long)G[0][c] << 16) + ((long long)G[1][c] << 8) + (long long)G[2][c];
+              const long long lo = ((long long)G[3][c] << 24) + ((long long)G[4][c] << 16) + ((long long)G[5][c] << 8) +
+                                   (long long)G[6][c];
+              const double w = sc * fma((double)lo, 0x1p-32, (double)hi);
+              v[c4 * 4 + c] = w * w;
+            }
+          }
+          // reduce-scatter over the lanes (fixed order): keep the half of the values selected by the lane bit
+          {
+            const bool up = lane & 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const double send = up ? v[c] : v[c + 4], keep = up ? v[c + 4] : v[c];
+              v[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          }
+          {
+            const bool up = lane & 8;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const double send = up ? v[c] : v[c + 2], keep = up ? v[c + 2] : v[c];
+              v[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+          }
+          {
+            const bool up = lane & 4;
+            const double send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+          v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+          acc[grp] += v[0];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(tempty)) : "memory");
+        if (etid == 0) { VZ_I8T_ADD(2, t_b); }
       }
-      if (tx == 0) {
-        s_mu[GP1::row_of(ty, i)] = mu_part[i];
-        s_linf[GP1::row_of(ty, i)] = lmin[i];
+      if ((lane & 3) == 0) {
+        const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+        for (int grp = 0; grp < 8; ++grp) s_red[quarter * 64 + grp * 8 + c] = acc[grp];
       }
-    }
-    fence_proxy_async();  // generic-proxy writes (digit scratch, aliased smem) before async-proxy (TMA) accesses
-    __syncthreads();      // this CTA's digit scratch is complete and visible
-
-    // ---------------- epilogue of every j tile: TMEM -> sum_j W[i,j]^2 ----------------
-    // warp w reads TMEM lanes 32 (w % 4) .. +31 (Linv rows j) and columns 16 (w / 4) .. +15 (candidates)
-    const int quarter = warp & 3, cblock = warp >> 2;
-    double rowsq[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) rowsq[c] = 0.0;
-    for (int jt = 0; jt < njt; ++jt) {
-      mbar_wait_bounded(tfull, jt_n & 1);
-      ++jt_n;
-      tc_fence_after();
-      const int j = jt * kJT + quarter * 32 + lane;
-      const double sc = j < np ? __ldg(ia.lscale + j) : 0.0;
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + cblock * 16;
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        int32_t G[kGroups][4];
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) tmem_ld4(taddr + g * kTM + c4 * 4, G[g]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          // sum_g G_g 2^(-8(g+2)) = 2^-32 (hi + lo 2^-32),  hi = G0 2^16 + G1 2^8 + G2,  lo = G3 2^24 + ... + G6
-          const long long hi = ((long long)G[0][c] << 16) + ((long long)G[1][c] << 8) + (long long)G[2][c];
-          const long long lo = ((long long)G[3][c] << 24) + ((long long)G[4][c] << 16) + ((long long)G[5][c] << 8) +
-                               (long long)G[6][c];
-          const double w = sc * fma((double)lo, 0x1p-32, (double)hi);
-          rowsq[c4 * 4 + c] = fma(w, w, rowsq[c4 * 4 + c]);
+      mbar_wait_bounded(kready + kb, (it / nbuf) & 1);     // mu / L-inf of this tile (long since complete)
+      esync();
+      if (etid < kTM) {
+        const int r = etid, m = m0 + r;
+        if (m < a.M) {
+          const double rs = (s_red[r] + s_red[64 + r]) + (s_red[128 + r] + s_red[192 + r]);
+          emit_score(a, m, rs, s_mu[kb * 64 + r], s_linf[kb * 64 + r], clamped);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(tempty)) : "memory");
+      esync();             // s_red and s_mu[kb] are consumed
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(kfree + kb)) : "memory");
+      if (etid == 0) { VZ_I8T_ADD(3, t_a); if (blockIdx.x == 0) g_i8_t_tiles(); }
     }
-    // sum over the 32 lanes (rows j) in a fixed order, then over the four lane quarters through smem
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rowsq[c] += __shfl_xor_sync(0xffffffffu, rowsq[c], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c) s_red[quarter * 64 + cblock * 16 + c] = rowsq[c];
-    }
-    consumer_sync();
-    if (tid < kTM) {
-      const int r = tid, m = m0 + r;
-      if (m < a.M) {
-        const double rs = (s_red[r] + s_red[64 + r]) + (s_red[128 + r] + s_red[192 + r]);
-        emit_score(a, m, rs, s_mu[r], s_linf[r], clamped);
-      }
-    }
+    if (clamped) atomicAdd(a.clamp_count, clamped);
   }
-  if (clamped) atomicAdd(a.clamp_count, clamped);
   tc_fence_before();
   __syncthreads();
   if (is_mma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((uint32_t)kTmemCols));
@@ -460,16 +588,21 @@ __global__ void __launch_bounds__(128) k_slice_linv(const double* __restrict__ L
   if (tid == 0) lscale[j] = ldexp(1.0, ea + eb - 32);
 }
 
-size_t score_i8_smem_bytes(int dk) {
-  return 1024 + kRingBytes + sizeof(double) * (128 + 64 * 2 + 256) + sizeof(uint64_t) * (4 + 2 * kASlots + 2) + 16 +
+// shared memory behind the operand ring: alpha, mu, L-inf, reduction, barriers, TMEM pointer, categorical rows, mask
+size_t score_i8_misc_bytes(int dk) {
+  return sizeof(double) * (128 + 128 + 128 + 256) + sizeof(uint64_t) * (4 + 2 * kASlots + 2 + 4) + 16 +
          sizeof(int32_t) * dk * 2 * kLD1 + kMaxDc;
+}
+size_t score_i8_stage_bytes(int dc) { return sizeof(double) * 3 * dc * kLD1; }
+size_t score_i8_smem_bytes(int dc, int dk, int nbuf) {
+  return 1024 + kRingBytes + ((score_i8_misc_bytes(dk) + 15) & ~size_t(15)) + (nbuf == 2 ? score_i8_stage_bytes(dc) : 0);
 }
 
 }  // namespace
 
 bool score_i8_eligible(const vzgp_handle* h, int M) {
   if (h->kp.use_linear || h->np < kJT || h->np > 4096) return false;
-  if ((size_t)3 * h->dc * kLD1 * sizeof(double) > (size_t)kRingBytes) return false;
+  if (score_i8_stage_bytes(h->dc) > (size_t)kRingBytes) return false;
   const int ntiles = (M + kTM - 1) / kTM;
   return ntiles >= h->sm_count;          // enough tiles for one CTA per SM (no column split on this path)
 }
@@ -488,7 +621,8 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
     h->launches++;
     h->i8_ready = true;
   }
-  VZ_TRY(h->i8_kdig.reserve((size_t)grid * kDigits * kTM * np));
+  const int nbuf = score_i8_smem_bytes(h->dc, h->dk, 2) <= 227 * 1024 ? 2 : 1;
+  VZ_TRY(h->i8_kdig.reserve((size_t)grid * nbuf * kDigits * kTM * np));
   I8Args ia;
   memset(&ia, 0, sizeof(ia));
   ScoreArgs& a = ia.s;
@@ -512,8 +646,10 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
   ia.kdig = h->i8_kdig.as<uint8_t>();
   ia.lscale = h->i8_scale.as<double>();
   ia.kscale = ldexp(1.0, 56 - ea);
+  ia.nbuf = nbuf;
+  ia.misc_bytes = (int)score_i8_misc_bytes(h->dk);
   {
-    const uint64_t dims[2] = {(uint64_t)np, (uint64_t)grid * kDigits * kTM};
+    const uint64_t dims[2] = {(uint64_t)np, (uint64_t)grid * nbuf * kDigits * kTM};
     const uint64_t strides[1] = {(uint64_t)np};
     const uint32_t box[2] = {(uint32_t)kKC, (uint32_t)kTM};
     VZ_TRY(make_tensor_map_u8(&ia.mapK, ia.kdig, 2, dims, strides, box));
@@ -525,7 +661,7 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
     VZ_TRY(make_tensor_map_u8(&ia.mapL, h->i8_planes.as<uint8_t>(), 3, dims, strides, box));
   }
   const bool need_linf = (linf != nullptr) || (a.apply_tr && a.radius <= 0.5);
-  const size_t sm = score_i8_smem_bytes(h->dk);
+  const size_t sm = score_i8_smem_bytes(h->dc, h->dk, nbuf);
   if (sm > 227 * 1024) { set_error("k_score_i8 needs %zu bytes of shared memory", sm); return VZGP_ERR_UNSUPPORTED; }
   if (need_linf) {
     VZ_CUDA(cudaFuncSetAttribute(k_score_i8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -540,3 +676,18 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
 }
 
 }  // namespace vzgp
+
+#ifdef VZ_I8_TIMING
+// Debug builds only (make EXTRA=-DVZ_I8_TIMING): clock64 sums of CTA 0.  [0] phase 1, [1] epilogue waiting for the
+// accumulators, [2] epilogue, [3] whole tile (worker), [4] MMA thread waiting for the epilogue, [5] ... for K* planes,
+// [6] ... for Linv planes, [7] MMA thread total, [8] / [9] producer waiting for a free B buffer / A slot, [10] producer
+// total, [15] tiles.  reset != 0 clears the counters.
+extern "C" int vzgp_debug_i8_timing(long long* out, int reset) {
+  if (cudaMemcpyFromSymbol(out, vzgp::g_i8_t, sizeof(long long) * 16) != cudaSuccess) return -2;
+  if (reset) {
+    long long z[16] = {};
+    if (cudaMemcpyToSymbol(vzgp::g_i8_t, z, sizeof(z)) != cudaSuccess) return -2;
+  }
+  return 0;
+}
+#endif
