@@ -75,6 +75,25 @@ def fp64_peak_tflops():
   return 37.0, 'nominal B200 FP64 (no measurement found)'
 
 
+def int8_peak_tops():
+  """Dense int8 tensor roof.  tcgen05 kind::i8 runs at the fp8 rate = 2 x bf16 (tools/umma_rate.cu: identical cycles per
+  MMA for i8 and f8f6f4 at equal bytes); MEASURED_PEAKS.json carries the measured bf16 figure - the sustained one, the
+  kernel is timed inside a long step."""
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    try:
+      j = json.load(open(p))
+      return 2.0 * float(j.get('bf16_tflops_sustained', j['bf16_tflops'])), '2 x measured sustained dense bf16 (MEASURED_PEAKS.json)'
+    except Exception:  # pylint: disable=broad-except
+      pass
+  return 2.0 * 1590.0, '2 x the fallback dense bf16 figure of B200_PROFILING.md (1.59 PFLOP/s)'
+
+
+def i8_ops_per_candidate(n):
+  # 28 digit-pair products (7 x 7 balanced base-256 digits, s + t <= 8) of the triangular contraction: n(n+1)/2 MACs each
+  return 28 * n * (n + 1)
+
+
 def hbm_peak_gbs():
   p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(p):
@@ -85,9 +104,9 @@ def hbm_peak_gbs():
   return 6650.0, 'fallback'
 
 
-def score_kernel_traffic():
+def score_kernel_traffic(i8=False):
   """dram__bytes_read.sum + dram__bytes_write.sum of one k_score launch (ncu --set full), newest summary."""
-  for name in ('score_kernel_ncu_r02.json', 'score_kernel_ncu_r01_latest.json'):
+  for name in (('score_i8_kernel_ncu_r02.json',) if i8 else ('score_kernel_ncu_r02.json', 'score_kernel_ncu_r01_latest.json')):
     tp = os.path.join(ROOT, 'profiles', name)
     if not os.path.exists(tp):
       continue
@@ -454,6 +473,23 @@ def run_gpu(args):
     ev[i][1].record(stream)
   torch.cuda.synchronize()
   kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+  # which kernel that was: the tcgen05 integer-split kernel (default for pools of this size) or the FP64 DMMA kernel
+  i8_before = dev.get_int('score_i8_launches')
+  dev.score(pools[0], acq, out=out_k)
+  used_i8 = dev.get_int('score_i8_launches') > i8_before
+  dmma_ms = kern_ms
+  if used_i8:   # the DMMA kernel on the same pools, for the record (round 1's dominant kernel)
+    dev.set_int('score_i8', 0)
+    for i in range(3):
+      dev.score(pools[i % n_pools], acq, out=out_k)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 10))]
+    for i, (a_, b_) in enumerate(ev2):
+      a_.record(stream)
+      dev.score(pools[i % n_pools], acq, out=out_k)
+      b_.record(stream)
+    torch.cuda.synchronize()
+    dmma_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in ev2]))
+    dev.set_int('score_i8', -1)
   # the trust-region variant k_score<true> (active when the radius is <= 0.5: few trials), same pool size
   tr_ms = None
   if args.workload == 'c2' and rank == 0:
@@ -493,9 +529,9 @@ def run_gpu(args):
 
   per_rank = None
   if dist is not None:
-    t = torch.tensor([total_ms, kern_ms, e2e_s * 1e3], dtype=torch.float64, device=dev.device)
+    t = torch.tensor([total_ms, kern_ms, e2e_s * 1e3, dmma_ms], dtype=torch.float64, device=dev.device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms, e2e_ms = [float(v) for v in t.cpu()]
+    total_ms, kern_ms, e2e_ms, dmma_ms = [float(v) for v in t.cpu()]
     e2e_s = e2e_ms / 1e3
     mine = torch.tensor([per_step.min(), float(np.median(per_step)), per_step.max(), float(np.argmax(per_step)),
                          1.0 if exchange_ok else 0.0], dtype=torch.float64, device=dev.device)
@@ -518,15 +554,37 @@ def run_gpu(args):
   value = cand_total / (total_ms * 1e-3)
   flops = algorithmic_flops_per_candidate(n_trials, dim) * m_pool
   peak, peak_src = fp64_peak_tflops()
-  achieved = flops / (kern_ms * 1e-3) * 1e-12
+  achieved = flops / (dmma_ms * 1e-3) * 1e-12
   hbm_peak, hbm_src = hbm_peak_gbs()
   hbm_ach = algorithmic_bytes_per_candidate(dim) * m_pool / (kern_ms * 1e-3) * 1e-9
-  traffic, traffic_src = score_kernel_traffic() if args.workload == 'c2' else (None, None)
+  traffic, traffic_src = score_kernel_traffic(used_i8) if args.workload == 'c2' else (None, None)
+  dmma_roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+               'kernel': 'k_score', 'kernel_ms': dmma_ms,
+               'note': 'the FP64 DMMA kernel (mma.sync m8n8k4 f64) on the same pools; peak ' + peak_src}
+  if used_i8:
+    i8_peak, i8_src = int8_peak_tops()
+    i8_ach = i8_ops_per_candidate(n_trials) * m_pool / (kern_ms * 1e-3) * 1e-12
+    roofline = {'bound': 'tensor', 'achieved': i8_ach, 'peak': i8_peak, 'unit': 'TOP/s', 'frac': i8_ach / i8_peak,
+                'traffic': traffic, 'traffic_source': traffic_src, 'kernel': 'k_score_i8', 'kernel_ms': kern_ms,
+                'note': 'tcgen05.mma kind::i8 (s8 x s8 -> s32 in TMEM): W = K* Linv^T as 28 exact products of balanced base-256 '
+                        'digit planes, recombined in fp64; peak = ' + i8_src + '.  M = 128, N = 64 MMAs (7 accumulator groups x 64 '
+                        'columns fill TMEM) read 6 KB of shared memory per 32-cycle MMA: the operand bandwidth bounds them at 48 '
+                        'cycles = 0.67 of the tensor peak (tools/umma_rate.cu)',
+                'int8_ops_per_candidate': i8_ops_per_candidate(n_trials),
+                'fp64_equivalent': {'tflops': flops / (kern_ms * 1e-3) * 1e-12, 'of_fp64_dmma_peak': flops / (kern_ms * 1e-3) * 1e-12 / peak,
+                                    'flops_per_candidate': algorithmic_flops_per_candidate(n_trials, dim)},
+                'fp64_dmma_kernel': dmma_roof,
+                'hbm': {'achieved': hbm_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_ach / hbm_peak, 'peak_source': hbm_src}}
+  else:
+    roofline = dict(dmma_roof, traffic=traffic, traffic_source=traffic_src,
+                    note='fp64: tcgen05 has no f64 kind, the binding roof is the FP64 DMMA pipe; peak ' + peak_src,
+                    flops_per_candidate=algorithmic_flops_per_candidate(n_trials, dim),
+                    hbm={'achieved': hbm_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_ach / hbm_peak, 'peak_source': hbm_src})
   cname = args.workload.upper()
   line = {
       'metric': 'GP-UCB candidates scored/sec', 'value': value, 'unit': 'candidates/s', 'n_gpus': world,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
-      'higher_is_better': True, 'scaling': wl['scaling'], 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+      'higher_is_better': True, 'scaling': wl['scaling'], 'vs_baseline': None, 'dtype': 'f64 (W = K* Linv^T as exact s8 digit products on tcgen05)' if used_i8 else 'f64', 'data': 'synthetic',
       'config': {'workload': f'{cname}: GP posterior mu/var + UCB + trust region + top-1, N={n_trials}, D={dim}, M={m_pool} per GPU'
                              + (f' ({wl["m_total"]} in total)' if wl['m_total'] else ''),
                  'l2': f'{n_pools} rotating candidate pools ({n_pools * pool_bytes / 1e6:.0f} MB > 126 MB L2)',
@@ -536,11 +594,7 @@ def run_gpu(args):
                  'per_step_ms': step_stats,
                  'pipelining': f'steps are enqueued without host sync; the host reads winners {n_slots - 1} steps behind',
                  'k_score_trust_region_variant': tr_ms},
-      'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                   'traffic': traffic, 'traffic_source': traffic_src, 'kernel': 'k_score', 'kernel_ms': kern_ms,
-                   'note': 'fp64: tcgen05 has no f64 kind, the binding roof is the FP64 DMMA pipe; peak ' + peak_src,
-                   'flops_per_candidate': algorithmic_flops_per_candidate(n_trials, dim),
-                   'hbm': {'achieved': hbm_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_ach / hbm_peak, 'peak_source': hbm_src}},
+      'roofline': roofline,
       'e2e': {'value': m_pool * world * args.steps / e2e_s, 'unit': 'candidates/s',
               'h2d_bytes_per_step': m_pool * dim * 8 * world, 'd2h_bytes_per_step': (m_pool * 8 + (dim + 2) * 8) * world,
               'ms_per_step': 1e3 * e2e_s / args.steps,

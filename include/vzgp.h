@@ -108,8 +108,13 @@ int vzgp_synchronize(vzgp_handle* h);
 int64_t vzgp_launch_count(const vzgp_handle* h);
 
 /* Tuning knobs.  "dataflow_ctas": worker CTAs the dataflow factorisation launches (0 = every resident slot;
- * callers that run several handles concurrently, like the ARD restarts, give each an equal share). */
+ * callers that run several handles concurrently, like the ARD restarts, give each an equal share).
+ * "score_i8": 1 = large candidate pools (>= one 64-candidate tile per SM, 128 <= padded N <= 4096, no linear
+ * kernel) are scored by the tcgen05 integer-split kernel, 0 = always the FP64 DMMA kernel, -1 = the process
+ * default (environment VZGP_SCORE_I8, default 1). */
 int vzgp_set_int(vzgp_handle* h, const char* key, int value);
+/* Counters.  "launches" (= vzgp_launch_count), "score_i8_launches": launches of the tcgen05 scoring kernel. */
+int vzgp_get_int(const vzgp_handle* h, const char* key, int64_t* value);
 
 /* ---- stage-wise entry points (parity tests call these one by one) -------- */
 

@@ -46,9 +46,12 @@ def _pool(dev, m, d, seed):
   return dev.random_pool(m, d, seed=seed)
 
 
-@pytest.mark.parametrize('n,d,sf2', [(1000, 20, 1.0), (520, 7, 2.7), (192, 3, 0.31), (1030, 12, 1.0)])
+@pytest.mark.parametrize('n,d,sf2', [(1000, 20, 1.0), (520, 7, 2.7), (192, 3, 0.31), (1030, 12, 1.0), (300, 40, 1.0),
+                                     (2000, 50, 0.9999999)])
 def test_i8_scores_match_oracle_and_dmma(dev, n, d, sf2):
-  """np = 1024 / 576 (a half k chunk and a half j tile) / 192 / 1088; sf2 off a power of two."""
+  """np = 1024 / 576 (a half k chunk and a half j tile) / 192 / 1088; sf2 off a power of two; Dc = 40 and 50: the
+  phase-1 staging no longer fits next to the operand ring (nbuf = 1, phases back to back); C4's N = 2000 with sf2
+  just below a power of two (the balanced top digit needs the extra scale bit)."""
   m = 148 * 64 + 37
   x, y, _ = _problem(n, d, n)
   po, pg = _params(d, sf2=sf2)

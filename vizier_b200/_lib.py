@@ -131,6 +131,7 @@ SIGNATURES = {
     'vzgp_synchronize': (_i, [_vp]),
     'vzgp_launch_count': (_i64, [_vp]),
     'vzgp_set_int': (_i, [_vp, C.c_char_p, _i]),
+    'vzgp_get_int': (_i, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
     'vzgp_kernel_matrix': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _pP, _d, _vp, _i]),
     'vzgp_cross_kernel': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _pP, _vp, _i]),
     'vzgp_cholesky_retry': (_i, [_vp, _vp, _i, _i, _d, _i, _vp, _i, _pd]),

@@ -470,6 +470,14 @@ int vzgp_set_int(vzgp_handle* h, const char* key, int value) {
   return VZGP_ERR_ARG;
 }
 
+int vzgp_get_int(const vzgp_handle* h, const char* key, int64_t* value) {
+  VZ_ARG(h && key && value, "handle / key / value");
+  if (std::strcmp(key, "launches") == 0) { *value = h->launches; return 0; }
+  if (std::strcmp(key, "score_i8_launches") == 0) { *value = h->i8_launches; return 0; }
+  set_error("vzgp_get_int: unknown key '%s'", key);
+  return VZGP_ERR_ARG;
+}
+
 int vzgp_kernel_matrix(vzgp_handle* h, const double* X, const int32_t* Z, int N, int Dc, int Dk,
                        int n_valid, const vzgp_params* p, double diag_add, double* K, int ldk) {
   VZ_ARG(h && K, "handle / K");

@@ -167,7 +167,8 @@ struct vzgp_handle {
   int df_ctas = 0;                              // worker CTAs per launch (0: all slots); vzgp_set_int
 
   // Integer-split scoring on tcgen05 (score_i8.cu): digit planes of Linv, their row scales, K* digit scratch.
-  int score_i8 = -1;                            // -1: environment VZGP_SCORE_I8 (default off), 0 / 1: vzgp_set_int
+  int score_i8 = -1;                            // -1: environment VZGP_SCORE_I8 (default on), 0 / 1: vzgp_set_int
   bool i8_ready = false;                        // the digit planes describe the current Linv
+  int64_t i8_launches = 0;
   vzgp::DevBuf i8_planes, i8_scale, i8_kdig;
 };

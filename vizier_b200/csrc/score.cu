@@ -659,7 +659,7 @@ int launch_score(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, con
     return 0;
   }
   {
-    static const int env_i8 = [] { const char* e = getenv("VZGP_SCORE_I8"); return e ? atoi(e) : 0; }();
+    static const int env_i8 = [] { const char* e = getenv("VZGP_SCORE_I8"); return e ? atoi(e) : 1; }();
     const int want = h->score_i8 >= 0 ? h->score_i8 : env_i8;
     if (want && score_i8_eligible(h, M)) return launch_score_i8(h, Xs, Zs, M, acq, score, mu, sigma, linf);
   }

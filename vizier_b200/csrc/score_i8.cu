@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
   double* sa = stage;                                    // [dc][LD]     candidates (transposed)
   double* sb = sa + dc * LD;                             // [2][dc][LD]  trials, double buffered
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and
+  // the issuing warps keep their descriptors in uniform registers
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const bool is_kwarp = warp < kKWarps;
   const bool is_epi = warp >= kKWarps && warp < kKWarps + kEWarps;
   const bool is_producer = warp == kKWarps + kEWarps;
@@ -672,6 +674,7 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
   }
   VZ_CHECK_LAUNCH();
   h->launches++;
+  h->i8_launches++;
   return 0;
 }
 

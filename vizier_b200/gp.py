@@ -232,6 +232,11 @@ class DeviceGP:
   def set_int(self, key: str, value: int) -> None:
     _lib.check('vzgp_set_int', self._lib.vzgp_set_int(self._h, key.encode(), int(value)))
 
+  def get_int(self, key: str) -> int:
+    v = C.c_int64(0)
+    _lib.check('vzgp_get_int', self._lib.vzgp_get_int(self._h, key.encode(), C.byref(v)))
+    return int(v.value)
+
   # -- helpers -------------------------------------------------------------
   def _dev(self, a, dtype) -> Optional[torch.Tensor]:
     if a is None:
