@@ -625,6 +625,10 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
   }
   const int nbuf = score_i8_smem_bytes(h->dc, h->dk, 2) <= 227 * 1024 ? 2 : 1;
   VZ_TRY(h->i8_kdig.reserve((size_t)grid * nbuf * kDigits * kTM * np));
+  // (A persisting L2 access-policy window over the digit scratch, as k_score uses for its fp64 scratch, changes
+  // nothing here: the two buffers are 136 MB at C2 against 126 MB of L2, the freshly written tile is the LRU victim
+  // while the current one is re-read, so every digit goes through HBM once - 0.7 GB written + 0.8 GB read per launch,
+  // 9 % of the HBM bandwidth, ncu: profiles/score_i8_kernel_ncu_r02.json.)
   I8Args ia;
   memset(&ia, 0, sizeof(ia));
   ScoreArgs& a = ia.s;
