@@ -375,6 +375,19 @@ int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_conf
 int vzgp_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
                   const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
 
+/* Host-stepped form of the same optimiser: identical device-resident state and kernels, but the CALLER scores every
+ * batch - for acquisitions libvzgp cannot evaluate by itself, e.g. one with a user-supplied `prior_acquisition` term
+ * (gp_ucb_pe.py:286-381, :589-592; the reference calls `acquisition_optimizer(scoring_fn.score, ...)` with an arbitrary
+ * callable, vectorized_base.py:431-495).  begin -> [write n_prior prior rewards to *prior_rewards_dev, seed] ->
+ * repeat { ask: batch features [B x Dc] / [B x Dk] on the device and where to put the B rewards; tell } -> end
+ * (winners to the host; synchronises).  Everything else is asynchronous on the handle's stream. */
+int vzgp_eagle_begin(vzgp_handle* h, const vzgp_eagle_config* cfg, const int32_t* cat_sizes, int count, uint64_t seed,
+                     int n_prior, double** prior_rewards_dev);
+int vzgp_eagle_seed(vzgp_handle* h, const double* prior, const int32_t* prior_z);
+int vzgp_eagle_ask(vzgp_handle* h, const double** batch_x_dev, const int32_t** batch_z_dev, double** batch_rewards_dev);
+int vzgp_eagle_tell(vzgp_handle* h);
+int vzgp_eagle_end(vzgp_handle* h, double* best_x, int32_t* best_z, double* best_score);
+
 /* vzgp_eagle_run with the GP-UCB-PE acquisition as the scoring function (gp_ucb_pe.py:1006-1155). */
 int vzgp_eagle_run_pe(vzgp_handle* hA, vzgp_handle* hB, const vzgp_eagle_config* cfg,
                       const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,

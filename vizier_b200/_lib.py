@@ -171,6 +171,11 @@ SIGNATURES = {
     'vzgp_eagle_run': (_i, [_vp, _pE, _pA, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
     'vzgp_score_pe': (_i, [_vp, _vp, _vp, _vp, _i, _pPE, _vp, _vp, _vp, _vp]),
     'vzgp_eagle_run_pe': (_i, [_vp, _vp, _pE, _pPE, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
+    'vzgp_eagle_begin': (_i, [_vp, _pE, _pi32, _i, _u64, _i, C.POINTER(C.c_void_p)]),
+    'vzgp_eagle_seed': (_i, [_vp, _vp, _vp]),
+    'vzgp_eagle_ask': (_i, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    'vzgp_eagle_tell': (_i, [_vp]),
+    'vzgp_eagle_end': (_i, [_vp, _pd, _pi32, _pd]),
     'vzgp_random_search': (_i, [_vp, _i64, _i64, _pA, _pi32, _i, _u64, _pd, _pi32, _pd, _pi64]),
     'vzgp_random_pool': (_i, [_vp, _i64, _i, _i64, _u64, _vp]),
     'vzgp_random_pool_cat': (_i, [_vp, _i64, _i, _pi32, _i64, _u64, _vp]),

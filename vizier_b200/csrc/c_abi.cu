@@ -426,6 +426,8 @@ int vzgp_create(int device, void* stream, vzgp_handle** out) {
   return 0;
 }
 
+static void eagle_step_free(vzgp_handle* h);
+
 int vzgp_destroy(vzgp_handle* h) {
   if (!h) return 0;
   Guard g(h->device);
@@ -435,6 +437,7 @@ int vzgp_destroy(vzgp_handle* h) {
                     &h->LinvT, &h->df_tasks[0], &h->df_tasks[1], &h->df_flags, &h->df_S, &h->scal, &h->gen,
                     &h->i8_planes, &h->i8_scale, &h->i8_kdig})
     b->release();
+  eagle_step_free(h);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->copy_stream) {
     for (int i = 0; i < 4; ++i) cudaEventDestroy(h->copy_ev[i]);
@@ -879,33 +882,16 @@ int vzgp_random_search(vzgp_handle* h, int64_t M, int64_t index_base, const vzgp
   return 0;
 }
 
-static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
-                          const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,
-                          const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
-                          double* best_score, vzgp_handle* const* ens = nullptr, int n_ens = 0,
-                          const vzgp_scalarization* scal = nullptr) {
-  VZ_ARG(h && cfg && (acq || pe || scal) && best_score, "handle / pointers");
-  auto score_batch = [&](const double* xs, const int32_t* zs, int m, double* out) -> int {
-    if (scal) return launch_score_multi(h, xs, zs, m, out, nullptr, nullptr);
-    if (pe) return launch_score_pe(h, hB, xs, zs, m, pe, out, nullptr, nullptr, nullptr);
-    if (n_ens > 1) return launch_score_ensemble(ens, n_ens, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
-    return launch_score(h, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
-  };
-  if (!h->fitted) { set_error("vzgp_eagle_run before vzgp_fit"); return VZGP_ERR_STATE; }
-  VZ_ARG(best_x != nullptr || h->dc == 0, "best_x");
-  VZ_ARG(best_z != nullptr || h->dk == 0, "best_z");
-  VZ_ARG(cfg->pool_size >= 1 && cfg->batch_size >= 1, "pool/batch size");
-  VZ_ARG(cfg->pool_size % cfg->batch_size == 0, "pool_size must be a multiple of batch_size");
-  VZ_ARG(cfg->pool_size <= 3000, "pool_size <= 3000");
-  VZ_ARG(cfg->batch_size <= 8192, "batch_size <= 8192");
-  VZ_ARG(count >= 1 && count <= kMaxTopk, "count");
-  VZ_ARG(cfg->max_evaluations >= 1, "max_evaluations");
-  VZ_ARG(n_prior >= 0, "n_prior");
-  VZ_ARG(n_prior == 0 || prior != nullptr || h->dc == 0, "prior");
-  VZ_ARG(n_prior == 0 || prior_z != nullptr || h->dk == 0, "prior_z");
-  Guard g(h->device);
+// Carves handle->eagle into the device-resident optimiser state for (cfg, count) on `h`.
+struct EagleScratch {
+  double* prior_r;    // [max(n_prior, 1)] rewards of the prior trials
+  double* chosen_r;   // [P]
+  int* ord;           // [max(n_prior, 1)]
+};
+static int eagle_setup(vzgp_handle* h, const vzgp_eagle_config* cfg, const int32_t* cat_sizes, int count, uint64_t seed,
+                       int n_prior, EagleDev* pe_, EagleScratch* sc) {
+  EagleDev& e = *pe_;
   const int P = cfg->pool_size, B = cfg->batch_size, D = h->dc, Dk = h->dk;
-  EagleDev e;
   VZ_TRY(check_cat_sizes(h, cat_sizes, e.sizes, &e.smax));
   // carve the eagle buffer: doubles | long longs | ints
   const size_t np1 = (size_t)(n_prior > 0 ? n_prior : 1);
@@ -924,20 +910,59 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   e.best_r = p; p += count;
   e.tmp_x = p; p += (size_t)count * D;
   e.tmp_r = p; p += count;
-  double* prior_r = p; p += np1;
-  double* chosen_r = p; p += P;
+  sc->prior_r = p; p += np1;
+  sc->chosen_r = p; p += P;
   long long* lp = reinterpret_cast<long long*>(p);
   e.best_id = lp; lp += count;
   e.tmp_id = lp; lp += count;
   int32_t* ip = reinterpret_cast<int32_t*>(lp);
   e.iter = ip; ip += 16;
-  int* ord = ip; ip += np1;
+  sc->ord = ip; ip += np1;
   e.pool_z = ip; ip += (size_t)P * Dk;
   e.batch_z = ip; ip += (size_t)B * Dk;
   e.best_z = ip; ip += (size_t)count * Dk;
   e.tmp_z = ip; ip += (size_t)count * Dk;
   e.P = P; e.B = B; e.D = D; e.Dk = Dk; e.count = count; e.cfg = *cfg; e.seed = seed;
-  VZ_TRY(eagle_prepare(e));
+  return eagle_prepare(e);
+}
+static int eagle_check_config(const vzgp_handle* h, const vzgp_eagle_config* cfg, int count) {
+  VZ_ARG(cfg->pool_size >= 1 && cfg->batch_size >= 1, "pool/batch size");
+  VZ_ARG(cfg->pool_size % cfg->batch_size == 0, "pool_size must be a multiple of batch_size");
+  VZ_ARG(cfg->pool_size <= 3000, "pool_size <= 3000");
+  VZ_ARG(cfg->batch_size <= 8192, "batch_size <= 8192");
+  VZ_ARG(count >= 1 && count <= kMaxTopk, "count");
+  VZ_ARG(cfg->max_evaluations >= 1, "max_evaluations");
+  (void)h;
+  return 0;
+}
+
+static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_config* cfg, const vzgp_acq* acq,
+                          const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,
+                          const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
+                          double* best_score, vzgp_handle* const* ens = nullptr, int n_ens = 0,
+                          const vzgp_scalarization* scal = nullptr) {
+  VZ_ARG(h && cfg && (acq || pe || scal) && best_score, "handle / pointers");
+  auto score_batch = [&](const double* xs, const int32_t* zs, int m, double* out) -> int {
+    if (scal) return launch_score_multi(h, xs, zs, m, out, nullptr, nullptr);
+    if (pe) return launch_score_pe(h, hB, xs, zs, m, pe, out, nullptr, nullptr, nullptr);
+    if (n_ens > 1) return launch_score_ensemble(ens, n_ens, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
+    return launch_score(h, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
+  };
+  if (!h->fitted) { set_error("vzgp_eagle_run before vzgp_fit"); return VZGP_ERR_STATE; }
+  VZ_ARG(best_x != nullptr || h->dc == 0, "best_x");
+  VZ_ARG(best_z != nullptr || h->dk == 0, "best_z");
+  VZ_TRY(eagle_check_config(h, cfg, count));
+  VZ_ARG(n_prior >= 0, "n_prior");
+  VZ_ARG(n_prior == 0 || prior != nullptr || h->dc == 0, "prior");
+  VZ_ARG(n_prior == 0 || prior_z != nullptr || h->dk == 0, "prior_z");
+  Guard g(h->device);
+  const int B = cfg->batch_size, D = h->dc, Dk = h->dk;
+  EagleDev e;
+  EagleScratch es;
+  VZ_TRY(eagle_setup(h, cfg, cat_sizes, count, seed, n_prior, &e, &es));
+  double* prior_r = es.prior_r;
+  double* chosen_r = es.chosen_r;
+  int* ord = es.ord;
   if (scal) VZ_TRY(prepare_scalarization(h, scal));
   VZ_TRY(launch_eagle_init(h, e));
   if (n_prior > 0) {
@@ -1004,6 +1029,88 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   if (Dk > 0) VZ_CUDA(cudaMemcpyAsync(best_z, e.best_z, sizeof(int32_t) * (size_t)count * Dk, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaMemcpyAsync(best_score, e.best_r, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
   VZ_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- host-stepped Eagle loop: same state and kernels, the caller scores every batch -----------------
+struct EagleStepState {
+  EagleDev e;
+  EagleScratch es;
+  int n_prior = 0;
+  bool seeded = false, asked = false;
+};
+static EagleStepState* step_state(vzgp_handle* h) { return static_cast<EagleStepState*>(h->eagle_step); }
+static void eagle_step_free(vzgp_handle* h) {
+  if (h->eagle_step) { delete step_state(h); h->eagle_step = nullptr; }
+}
+
+int vzgp_eagle_begin(vzgp_handle* h, const vzgp_eagle_config* cfg, const int32_t* cat_sizes, int count, uint64_t seed,
+                     int n_prior, double** prior_rewards_dev) {
+  VZ_ARG(h && cfg, "handle / cfg");
+  VZ_ARG(h->dc + h->dk > 0, "the handle needs its feature dimensions (fit a model first)");
+  VZ_TRY(eagle_check_config(h, cfg, count));
+  VZ_ARG(n_prior >= 0, "n_prior");
+  Guard g(h->device);
+  if (h->eagle_step) { delete step_state(h); h->eagle_step = nullptr; }
+  EagleStepState* st = new EagleStepState();
+  int rc = eagle_setup(h, cfg, cat_sizes, count, seed, n_prior, &st->e, &st->es);
+  if (rc == 0) rc = launch_eagle_init(h, st->e);
+  if (rc < 0) { delete st; return rc; }
+  st->n_prior = n_prior;
+  h->eagle_step = st;
+  if (prior_rewards_dev) *prior_rewards_dev = st->es.prior_r;
+  return 0;
+}
+
+int vzgp_eagle_seed(vzgp_handle* h, const double* prior, const int32_t* prior_z) {
+  VZ_ARG(h && h->eagle_step, "vzgp_eagle_begin first");
+  EagleStepState* st = step_state(h);
+  VZ_ARG(st->n_prior > 0 && !st->seeded && !st->asked, "seeding happens once, before the first ask, with n_prior > 0");
+  VZ_ARG(prior != nullptr || h->dc == 0, "prior");
+  VZ_ARG(prior_z != nullptr || h->dk == 0, "prior_z");
+  Guard g(h->device);
+  VZ_TRY(launch_eagle_seed_priors(h, st->e, prior, prior_z, st->es.prior_r, st->n_prior, st->es.ord, st->es.chosen_r));
+  st->seeded = true;
+  return 0;
+}
+
+int vzgp_eagle_ask(vzgp_handle* h, const double** batch_x_dev, const int32_t** batch_z_dev, double** batch_rewards_dev) {
+  VZ_ARG(h && h->eagle_step, "vzgp_eagle_begin first");
+  EagleStepState* st = step_state(h);
+  VZ_ARG(!st->asked, "vzgp_eagle_tell the previous batch first");
+  Guard g(h->device);
+  VZ_TRY(launch_eagle_suggest(h, st->e));
+  st->asked = true;
+  if (batch_x_dev) *batch_x_dev = st->e.batch;
+  if (batch_z_dev) *batch_z_dev = st->e.batch_z;
+  if (batch_rewards_dev) *batch_rewards_dev = st->e.batch_r;
+  return 0;
+}
+
+int vzgp_eagle_tell(vzgp_handle* h) {
+  VZ_ARG(h && h->eagle_step, "vzgp_eagle_begin first");
+  EagleStepState* st = step_state(h);
+  VZ_ARG(st->asked, "vzgp_eagle_ask first");
+  Guard g(h->device);
+  VZ_TRY(launch_eagle_update(h, st->e));
+  st->asked = false;
+  return 0;
+}
+
+int vzgp_eagle_end(vzgp_handle* h, double* best_x, int32_t* best_z, double* best_score) {
+  VZ_ARG(h && h->eagle_step && best_score, "vzgp_eagle_begin first / best_score");
+  EagleStepState* st = step_state(h);
+  VZ_ARG(best_x != nullptr || h->dc == 0, "best_x");
+  VZ_ARG(best_z != nullptr || h->dk == 0, "best_z");
+  Guard g(h->device);
+  const EagleDev& e = st->e;
+  const int count = e.count, D = e.D, Dk = e.Dk;
+  if (D > 0) VZ_CUDA(cudaMemcpyAsync(best_x, e.best_x, sizeof(double) * (size_t)count * D, cudaMemcpyDeviceToHost, h->stream));
+  if (Dk > 0) VZ_CUDA(cudaMemcpyAsync(best_z, e.best_z, sizeof(int32_t) * (size_t)count * Dk, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaMemcpyAsync(best_score, e.best_r, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  VZ_CUDA(cudaStreamSynchronize(h->stream));
+  delete st;
+  h->eagle_step = nullptr;
   return 0;
 }
 

@@ -141,6 +141,7 @@ struct vzgp_handle {
   vzgp::DevBuf xs_dev;  // staging for *_host entry points
   vzgp::DevBuf out_dev;
   vzgp::DevBuf eagle;   // eagle state
+  void* eagle_step = nullptr;   // EagleStepState (c_abi.cu) of a host-stepped optimiser run
   vzgp::DevBuf pe_tmp;  // GP-UCB-PE: per-candidate pieces of the two models
   vzgp::DevBuf gen;     // general scoring path: explicit K* and W chunks
   vzgp::DevBuf scal;    // multi-metric: [S][M] inverse scalarisation weights, then [S] best observed values

@@ -603,7 +603,7 @@ size_t score_i8_smem_bytes(int dc, int dk, int nbuf) {
 }  // namespace
 
 bool score_i8_eligible(const vzgp_handle* h, int M) {
-  if (h->kp.use_linear || h->np < kJT || h->np > 4096) return false;
+  if (h->kp.use_linear || h->np < kJT || h->np > 4096 || h->dc < 1) return false;
   if (score_i8_stage_bytes(h->dc) > (size_t)kRingBytes) return false;
   const int ntiles = (M + kTM - 1) / kTM;
   return ntiles >= h->sm_count;          // enough tiles for one CTA per SM (no column split on this path)

@@ -16,9 +16,10 @@ configuration (`UCBPEConfig()` with `optimize_set_acquisition_for_exploration=Fa
 
 Everything numeric runs in libvzgp (two handles on one stream, `vzgp_score_pe`,
 `vzgp_eagle_run_pe`); `sample` / `predict` (:1262-1354) draw from the device-computed joint posterior
-like `VizierGPBandit`.  Not implemented: multi-metric, set-PE batches
-(`optimize_set_acquisition_for_exploration=True`), `prior_acquisition`, linear-kernel mixing,
-ensembles, padding - each raises NotImplementedError.
+like `VizierGPBandit`.  `prior_acquisition` (a callable on NumPy features) is added to both acquisitions through the
+host-stepped Eagle loop (`gp.SteppedEagle`).  Not implemented: multi-metric, set-PE batches
+(`optimize_set_acquisition_for_exploration=True`), linear-kernel mixing, ensembles - each raises
+NotImplementedError.
 """
 
 from __future__ import annotations
@@ -116,9 +117,12 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
       raise NotImplementedError('vizier_b200.VizierGPUCBPEBandit implements the single-metric path only.')
     if config.optimize_set_acquisition_for_exploration:
       raise NotImplementedError('set-PE batches are not implemented.')
-    if prior_acquisition is not None or mixes_linear_kernel or (ensemble_size or 1) != 1:
-      raise NotImplementedError('prior_acquisition / linear kernel / ensembles are not implemented.')
+    if mixes_linear_kernel or (ensemble_size or 1) != 1:
+      raise NotImplementedError('linear kernel / ensembles are not implemented for GP-UCB-PE.')
     del clear_jax_cache, padding_schedule
+    # prior_acquisition(continuous [m, Dc], categorical [m, Dk]) -> [m]: added to the UCB / PE acquisition
+    # (gp_ucb_pe.py:286-381, :487-490); NumPy arrays instead of the reference's JAX ModelInput.
+    self._prior_acquisition = prior_acquisition
     self._problem = problem
     self._acquisition_optimizer_factory = acquisition_optimizer_factory
     self._ard_optimizer = ard_optimizer or default_ard_optimizer()
@@ -258,7 +262,8 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     prior = converters.trials_to_sorted_features(self._all_completed_trials, self._converter, (cont, cat))
     seed = int(self._rng.integers(2**62))
     res = optimizer(dev_a, pe, count=1, prior_features=None if prior is None else prior[0],
-                    prior_categorical=None if prior is None else prior[1], seed=seed, other=dev_b)
+                    prior_categorical=None if prior is None else prior[1], seed=seed, other=dev_b,
+                    prior_acquisition=self._prior_acquisition)
     params_dict = self._converter.to_parameters(res.features[0:1], None if res.categorical is None else res.categorical[0:1])[0]
     md = vz.Metadata()
     md.ns('devinfo')['acquisition_optimization'] = json.dumps(
@@ -271,6 +276,8 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     pred['use_ucb'] = f'{use_ucb}'
     pred['trust_radius'] = f'{radius}'
     pred['params'] = f'{params}'
+    if 'prior_acq_values' in res.aux:
+      md.ns(self._metadata_ns).ns('prior_acquisition')['value'] = f'{float(res.aux["prior_acq_values"][0])}'
     md.ns(self._metadata_ns).ns('timing')['time'] = f'{datetime.datetime.now() - start}'
     return vz.TrialSuggestion(params_dict, metadata=md)
 

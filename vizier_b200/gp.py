@@ -695,6 +695,66 @@ class DeviceGP:
     del keep
     return bx, bz, bs
 
+class _DevView:
+  """A raw device pointer as a `__cuda_array_interface__` object (zero-copy torch view of library-owned memory)."""
+
+  def __init__(self, ptr: int, shape, typestr: str):
+    self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
+class SteppedEagle:
+  """Host-stepped Eagle loop (vzgp_eagle_begin / seed / ask / tell / end): the device-resident optimiser state and
+  kernels of `DeviceGP.eagle_run`, with the batch scored by the caller - used for acquisitions that include a
+  host-side term (`prior_acquisition`, gp_ucb_pe.py:286-381)."""
+
+  def __init__(self, dev: 'DeviceGP', cfg: '_lib.EagleConfig', count: int, seed: int, n_prior: int = 0, cat_sizes=None):
+    self.dev, self.count, self.batch_size = dev, count, int(cfg.batch_size)
+    self.n_prior = int(n_prior)
+    sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
+    pr = C.c_void_p(0)
+    _lib.check('vzgp_eagle_begin', dev._lib.vzgp_eagle_begin(
+        dev._h, C.byref(cfg), sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes.size else None, count, seed,
+        self.n_prior, C.byref(pr)))
+    self._prior_rewards = pr.value
+
+  def _view(self, ptr, shape, typestr):
+    return torch.as_tensor(_DevView(ptr, shape, typestr), device=self.dev.device)
+
+  def seed(self, prior, prior_z, rewards) -> None:
+    """prior [n_prior, Dc] / prior_z [n_prior, Dk] features and their acquisition values [n_prior]."""
+    d = self.dev
+    with torch.cuda.stream(d._stream):
+      self._view(self._prior_rewards, (self.n_prior,), '<f8').copy_(torch.as_tensor(rewards, dtype=torch.float64, device=d.device))
+    pt = d._dev(prior, torch.float64) if d.dc > 0 else None
+    pz = d._dev(prior_z, torch.int32) if d.dk > 0 else None
+    d._stream.wait_stream(torch.cuda.current_stream(d.device))
+    _lib.check('vzgp_eagle_seed', d._lib.vzgp_eagle_seed(d._h, _ptr(pt), _ptr(pz)))
+    self._keep = (pt, pz)
+
+  def ask(self):
+    """Next batch: (xs [B, Dc] device view, zs [B, Dk] device view or None, rewards [B] device view to fill)."""
+    d = self.dev
+    px, pz, pr = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
+    _lib.check('vzgp_eagle_ask', d._lib.vzgp_eagle_ask(d._h, C.byref(px), C.byref(pz), C.byref(pr)))
+    b = self.batch_size
+    xs = self._view(px.value, (b, d.dc), '<f8') if d.dc > 0 else torch.zeros((b, 0), dtype=torch.float64, device=d.device)
+    zs = self._view(pz.value, (b, d.dk), '<i4') if d.dk > 0 else None
+    return xs, zs, self._view(pr.value, (b,), '<f8')
+
+  def tell(self) -> None:
+    _lib.check('vzgp_eagle_tell', self.dev._lib.vzgp_eagle_tell(self.dev._h))
+
+  def end(self):
+    d = self.dev
+    bx = np.zeros((self.count, d.dc), np.float64)
+    bz = np.zeros((self.count, d.dk), np.int32)
+    bs = np.zeros(self.count, np.float64)
+    _lib.check('vzgp_eagle_end', d._lib.vzgp_eagle_end(
+        d._h, bx.ctypes.data_as(C.POINTER(C.c_double)), bz.ctypes.data_as(C.POINTER(C.c_int32)),
+        bs.ctypes.data_as(C.POINTER(C.c_double))))
+    return bx, bz, bs
+
+
 class EnsembleGP:
   """Uniform ensemble of E GPs fitted on the same trials with different hyper-parameters
   (`VizierGPBandit(ensemble_size=E)`: the E best ARD restarts, gp_models.py:200-223; predictive =

@@ -83,13 +83,70 @@ class VectorizedOptimizer:
   max_evaluations: int = 75_000
   categorical_sizes: tuple = ()
 
+  def _eagle_config(self):
+    f = self.strategy_factory
+    pool = f.pool_size(self.n_continuous + self.n_categorical, self.suggestion_batch_size)
+    c = f.eagle_config
+    return _lib.EagleConfig(c.visibility, c.gravity, c.negative_gravity, c.perturbation,
+                            c.perturbation_lower_bound, c.penalize_factor, c.normalization_scale,
+                            c.prior_trials_pool_pct, pool, self.suggestion_batch_size, self.max_evaluations,
+                            c.categorical_perturbation_factor, c.pure_categorical_perturbation_factor,
+                            c.prob_same_category_without_perturbation, c.mutate_normalization_type)
+
+  def _stepped_eagle(self, dev, acq, count, prior_features, prior_categorical, seed, other, prior_acquisition):
+    """Eagle with the batch scored here: device acquisition + the caller's `prior_acquisition(continuous [m, Dc],
+    categorical [m, Dk]) -> [m]` evaluated on the host (gp_ucb_pe.py:376-379, :487-490).  One D2H + H2D round trip
+    per iteration; state, suggest and update stay on the device (gp.SteppedEagle)."""
+    import torch
+    is_pe = isinstance(acq, gp.UcbPeAcquisition)
+    has_cat = self.n_categorical > 0
+
+    def score(xs, zs):
+      with torch.cuda.stream(dev._stream):
+        out = dev.score_pe(other, xs, acq, zs=zs if has_cat else None) if is_pe else dev.score(xs, acq, zs=zs if has_cat else None)
+        xh = xs.cpu().numpy()
+        zh = zs.cpu().numpy() if (has_cat and zs is not None) else np.zeros((xh.shape[0], 0), np.int32)
+        vals = np.asarray(prior_acquisition(xh, zh), np.float64).reshape(-1)
+        return out['score'] + torch.as_tensor(vals, dtype=torch.float64, device=dev.device)
+
+    n_prior = 0 if prior_features is None else len(prior_features)
+    se = gp.SteppedEagle(dev, self._eagle_config(), count, seed, n_prior, list(self.categorical_sizes))
+    if n_prior > 0:
+      pt = dev._dev(prior_features, torch.float64)
+      pz = dev._dev(prior_categorical, torch.int32) if has_cat else None
+      se.seed(prior_features, prior_categorical, score(pt, pz))
+    steps = (self.max_evaluations - 1) // self.suggestion_batch_size + 1
+    for _ in range(steps):
+      xs, zs, rewards = se.ask()
+      r = score(xs, zs)
+      with torch.cuda.stream(dev._stream):
+        rewards.copy_(r)
+      se.tell()
+    return se.end()
+
   def __call__(self, dev: gp.DeviceGP, acq, *, count: int = 1,
                prior_features: Optional[np.ndarray] = None, prior_categorical: Optional[np.ndarray] = None,
-               seed: int = 0, other: Optional[gp.DeviceGP] = None) -> VectorizedStrategyResults:
+               seed: int = 0, other: Optional[gp.DeviceGP] = None,
+               prior_acquisition: Optional[Callable] = None) -> VectorizedStrategyResults:
     """acq: gp.Acquisition (UCB + trust region on `dev`) or gp.UcbPeAcquisition (needs `other`)."""
     sizes = list(self.categorical_sizes)
     is_pe = isinstance(acq, gp.UcbPeAcquisition)
     is_multi = isinstance(acq, gp.ScalarizedUcbAcquisition)
+    if prior_acquisition is not None:
+      if is_multi or isinstance(self.strategy_factory, _RandomStrategyFactory):
+        raise NotImplementedError('prior_acquisition is supported with the Eagle strategy on single-metric acquisitions')
+      bx, bz, bs = self._stepped_eagle(dev, acq, count, prior_features, prior_categorical, seed, other, prior_acquisition)
+      zsel = bz if self.n_categorical else None
+      prior_vals = np.asarray(prior_acquisition(bx, bz), np.float64).reshape(-1)
+      if is_pe:
+        out = dev.score_pe(other, bx, acq, zs=zsel)
+        aux = {k: out[k].cpu().numpy() for k in ('mean', 'stddev', 'stddev_from_all')}
+      else:
+        out = dev.score(bx, acq, zs=zsel, with_aux=True)
+        dev.synchronize()
+        aux = {'mean': out['mean'].cpu().numpy(), 'stddev': out['stddev'].cpu().numpy()}
+      aux['prior_acq_values'] = prior_vals
+      return VectorizedStrategyResults(bx, bs, aux, categorical=bz)
     if isinstance(self.strategy_factory, _RandomStrategyFactory) and is_multi:
       # uniform pool -> scalarised UCB -> device top-k, like vzgp_random_search but with the multi-metric scorer
       import torch
@@ -110,14 +167,7 @@ class VectorizedOptimizer:
       m = n * self.suggestion_batch_size
       bx, bz, bs, _ = dev.random_search(m, acq, count, seed, cat_sizes=sizes)
     else:
-      f = self.strategy_factory
-      pool = f.pool_size(self.n_continuous + self.n_categorical, self.suggestion_batch_size)
-      c = f.eagle_config
-      cfg = _lib.EagleConfig(c.visibility, c.gravity, c.negative_gravity, c.perturbation,
-                             c.perturbation_lower_bound, c.penalize_factor, c.normalization_scale,
-                             c.prior_trials_pool_pct, pool, self.suggestion_batch_size, self.max_evaluations,
-                             c.categorical_perturbation_factor, c.pure_categorical_perturbation_factor,
-                             c.prob_same_category_without_perturbation, c.mutate_normalization_type)
+      cfg = self._eagle_config()
       bx, bz, bs = dev.eagle_run(cfg, acq, count, seed, prior=prior_features, prior_z=prior_categorical,
                                  cat_sizes=sizes, other=other)
     if is_pe:
