@@ -1,0 +1,141 @@
+"""Host-stepped Eagle loop (vzgp_eagle_begin / seed / ask / tell / end) and `prior_acquisition`.
+
+The stepped loop shares state, kernels and Philox draws with `vzgp_eagle_run`; the caller scores each batch.  With
+the library's own acquisition as the scorer it must reproduce `vzgp_eagle_run`; with an extra host-side term it is
+compared with the oracle's optimiser driven by the same composite score function (gp_ucb_pe.py:376-379, :487-490).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason='no CUDA device')]
+
+from oracle import eagle_oracle as eo  # noqa: E402
+from oracle import gp_oracle as go  # noqa: E402
+
+
+@pytest.fixture()
+def dev():
+  from vizier_b200 import gp
+  d = gp.DeviceGP(0)
+  yield d
+  d.close()
+
+
+def _problem(n, d, seed):
+  rng = np.random.default_rng(seed)
+  x = rng.uniform(size=(n, d))
+  y = -np.sum((x - 0.3) ** 2, axis=1) + 0.05 * rng.normal(size=n)
+  return x, y
+
+
+def _cfg(cfg_o, pool, batch, steps):
+  from vizier_b200 import _lib
+  return _lib.EagleConfig(cfg_o.visibility, cfg_o.gravity, cfg_o.negative_gravity, cfg_o.perturbation,
+                          cfg_o.perturbation_lower_bound, cfg_o.penalize_factor, cfg_o.normalization_scale,
+                          cfg_o.prior_trials_pool_pct, pool, batch, steps * batch)
+
+
+def _prior_term(xc):
+  """A smooth user prior over the features (what `prior_acquisition` would return)."""
+  return -0.7 * np.sum((np.asarray(xc) - 0.8) ** 2, axis=1)
+
+
+@pytest.mark.parametrize('n,d,pool,batch,steps', [(120, 4, 50, 25, 12), (300, 6, 100, 50, 6)])
+def test_stepped_loop_reproduces_eagle_run_and_oracle_with_prior_term(dev, n, d, pool, batch, steps):
+  from vizier_b200 import gp
+  x, y = _problem(n, d, 31)
+  ls2 = 0.5 * (1 + np.arange(d) / d)
+  po, pg = go.GPParams(1.0, ls2, 1e-3), gp.GPHyperParams(1.0, ls2, 1e-3)
+  pred = go.precompute_predictive(po, x, y)
+  dev.fit(x, y, pg)
+  radius = go.trust_radius(n, d, 0)
+  acq = gp.Acquisition(1.8, True, radius)
+  cfg_o = eo.EagleConfig()
+  cfg = _cfg(cfg_o, pool, batch, steps)
+
+  def run_stepped(extra):
+    se = gp.SteppedEagle(dev, cfg, 3, 7, n_prior=n)
+
+    def score(xs):
+      out = dev.score(xs, acq)['score']
+      if extra:
+        with torch.cuda.stream(dev._stream):
+          out = out + torch.as_tensor(_prior_term(xs.cpu().numpy()), device=dev.device)
+      return out
+
+    se.seed(x, None, score(torch.from_numpy(x).cuda()))
+    for _ in range(steps):
+      xs, _, rewards = se.ask()
+      r = score(xs)
+      with torch.cuda.stream(dev._stream):
+        rewards.copy_(r)
+      se.tell()
+    return se.end()
+
+  # 1. the library's acquisition as the scorer: the same run as vzgp_eagle_run (graph / cooperative forms)
+  bx0, _, br0 = dev.eagle_run(cfg, acq, count=3, seed=7, prior=x)
+  bx1, _, br1 = run_stepped(False)
+  np.testing.assert_allclose(br1, br0, atol=1e-9)
+  np.testing.assert_allclose(bx1, bx0, atol=1e-9)
+  # 2. with the host-side prior term: the oracle's optimiser on the composite score
+  score_fn = lambda q: go.score_with_aux(pred, q)[0] + _prior_term(q)
+  wx, wr, _ = eo.run_eagle_optimizer(score_fn, dim=d, pool_size=pool, batch_size=batch, max_evaluations=steps * batch,
+                                     count=3, seed=7, cfg=cfg_o, prior_features=x)
+  bx2, _, br2 = run_stepped(True)
+  np.testing.assert_allclose(br2, wr, atol=1e-9)
+  np.testing.assert_allclose(bx2, wx, atol=1e-9)
+  assert not np.allclose(bx2, bx0)     # the prior term moved the optimum
+
+
+def test_stepped_loop_rejects_out_of_order_calls(dev):
+  from vizier_b200 import _lib, gp
+  x, y = _problem(40, 3, 5)
+  dev.fit(x, y, gp.GPHyperParams(1.0, np.full(3, 0.5), 1e-3))
+  cfg = _cfg(eo.EagleConfig(), 50, 25, 2)
+  se = gp.SteppedEagle(dev, cfg, 1, 3)
+  with pytest.raises(_lib.VzgpError):
+    se.tell()                       # nothing asked yet
+  se.ask()
+  with pytest.raises(_lib.VzgpError):
+    se.ask()                        # the previous batch has not been told
+  se.tell()
+  se.end()
+  with pytest.raises(_lib.VzgpError):
+    se.tell()                       # the run is over
+
+
+def test_ucb_pe_designer_with_prior_acquisition(dev):
+  """`VizierGPUCBPEBandit(prior_acquisition=...)`: suggestions are pulled towards the prior's optimum and carry the
+  prior value in their metadata (gp_ucb_pe.py:1147-1150)."""
+  del dev
+  from vizier_b200 import vz
+  from vizier_b200.designers import gp_ucb_pe
+  from vizier_b200 import optimizers as vb
+  p = vz.ProblemStatement()
+  for i in range(3):
+    p.search_space.root.add_float_param(f'x{i}', 0.0, 1.0)
+  p.metric_information.append(vz.MetricInformation(name='obj', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  rng = np.random.default_rng(0)
+  trials = []
+  for i in range(30):
+    xv = rng.uniform(size=3)
+    t = vz.Trial(parameters={f'x{j}': float(xv[j]) for j in range(3)}, id=i + 1)
+    t.complete(vz.Measurement({'obj': float(-np.sum((xv - 0.3) ** 2))}))
+    trials.append(t)
+  fac = vb.VectorizedOptimizerFactory(strategy_factory=vb.VectorizedEagleStrategyFactory(eagle_config=gp_ucb_pe.default_eagle_config),
+                                      max_evaluations=2500, suggestion_batch_size=25)
+  strong_prior = lambda xc, xz: -50.0 * np.sum((xc - 0.9) ** 2, axis=1)
+
+  def suggest(prior):
+    d = gp_ucb_pe.VizierGPUCBPEBandit(p, acquisition_optimizer_factory=fac, prior_acquisition=prior, rng=1)
+    d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+    return d.suggest(1)[0]
+
+  s0, s1 = suggest(None), suggest(strong_prior)
+  x0 = np.array([s0.parameters[f'x{j}'].value for j in range(3)])
+  x1 = np.array([s1.parameters[f'x{j}'].value for j in range(3)])
+  assert np.sum((x1 - 0.9) ** 2) < np.sum((x0 - 0.9) ** 2)
+  assert np.max(np.abs(x1 - 0.9)) < 0.25
+  val = float(s1.metadata.ns('google_gp_ucb_pe_bandit').ns('prior_acquisition')['value'])
+  np.testing.assert_allclose(val, strong_prior(x1[None, :], None)[0], rtol=1e-6, atol=1e-6)
