@@ -345,6 +345,11 @@ typedef struct vzgp_eagle_config {
   double prob_same_category_without_perturbation; /* 0.98 */
   int mutate_normalization_type;  /* 0 = MEAN (default), 1 = RANDOM (eagle_strategy.py:858-885; the
                                      GP-UCB-PE default, gp_ucb_pe.py:678-692) */
+  int n_parallel;       /* 0 / 1: a fly is one point.  q > 1 (host-stepped loop only, continuous features, q*Dc <= 64):
+                           a fly is a SET of q points [q x Dc] scored together (set acquisitions, gp_ucb_pe.py:510-594;
+                           vectorized_base.py:331-377): distances and moves over all q*Dc coordinates, forces normalised by
+                           Dc, Laplace perturbations normalised over the q members of each coordinate
+                           (eagle_strategy.py:1013-1046). */
 } vzgp_eagle_config;
 
 /* VectorizedOptimizer.__call__ with VectorizedEagleStrategy
@@ -374,6 +379,14 @@ int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_conf
  * score [M] required; mu, sigma (model A) and sigma_all (model B) optional; all device. */
 int vzgp_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
                   const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
+
+/* Set-PE acquisition of GP-UCB-PE batches (SetPEScoreFunction, gp_ucb_pe.py:510-594): Xs holds n_sets sets of q points
+ * ([n_sets * q x Dc] device, continuous features, q <= 16).  score[s] = logdet of the q x q joint predictive covariance
+ * under model B (completed + pending trials) + penalty * sum_i min(mean_A + explore * stddev_A - threshold, 0)
+ * (+ the set trust-region term, :245-269); -inf when the covariance block is not positive definite (:495-507).
+ * mu / sigma (model A) and sigma_all (sqrt of the diagonal of B's covariance), each [n_sets * q], are optional. */
+int vzgp_score_set_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, int n_sets, int q, const vzgp_pe_params* pe,
+                      double* score, double* mu, double* sigma, double* sigma_all);
 
 /* Host-stepped form of the same optimiser: identical device-resident state and kernels, but the CALLER scores every
  * batch - for acquisitions libvzgp cannot evaluate by itself, e.g. one with a user-supplied `prior_acquisition` term

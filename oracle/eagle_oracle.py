@@ -77,6 +77,7 @@ STREAM_TRIM_CAT = 7        # categorical features of re-seeded flies
 STREAM_RANDOM_POOL_CAT = 8
 STREAM_PULL_RAND = 9        # RANDOM force normalisation weights (eagle_strategy.py:862-877)
 STREAM_PUSH_RAND = 10
+STREAM_SET_LAPLACE = 11      # continuous perturbations of set flies (n_parallel > 1)
 
 
 def philox4x32(counter: np.ndarray, key: np.ndarray) -> np.ndarray:
@@ -198,13 +199,14 @@ def init_state(
 
 def create_features(
     pool: np.ndarray, rewards: np.ndarray, batch: np.ndarray, rewards_batch: np.ndarray,
-    perturbations: np.ndarray, cfg: EagleConfig,
+    perturbations: np.ndarray, cfg: EagleConfig, norm_dim: Optional[int] = None,
 ) -> np.ndarray:
   """eagle_strategy.py:784-952, MEAN normalisation, ADDITIVE perturbation.
 
-  perturbations [B, D] already = sign * perturbation_i.
+  perturbations [B, D] already = sign * perturbation_i.  norm_dim: the number of feature dimensions of ONE point
+  (eagle_strategy.py:830-837); differs from the flattened width for set flies (n_parallel > 1).
   """
-  n_features = pool.shape[1]
+  n_features = pool.shape[1] if norm_dim is None else norm_dim
   dists = features_dist_squared(batch, pool)
   with np.errstate(invalid='ignore'):
     directions = rewards[None, :] - rewards_batch[:, None]
@@ -223,7 +225,8 @@ def create_features(
   return batch + change + perturbations
 
 
-def suggest(state: EagleState, batch_size: int, signs: np.ndarray, cfg: EagleConfig) -> np.ndarray:
+def suggest(state: EagleState, batch_size: int, signs: np.ndarray, cfg: EagleConfig,
+            norm_dim: Optional[int] = None) -> np.ndarray:
   """eagle_strategy.py:720-782 incl. DefaultProjection clip to [0,1] (:257-268)."""
   pool_size = state.features.shape[0]
   nb = pool_size // batch_size
@@ -234,7 +237,7 @@ def suggest(state: EagleState, batch_size: int, signs: np.ndarray, cfg: EagleCon
   else:
     rb = state.rewards[start : start + batch_size]
     pb = state.perturbations[start : start + batch_size]
-    new = create_features(state.features, state.rewards, fb, rb, signs * pb[:, None], cfg)
+    new = create_features(state.features, state.rewards, fb, rb, signs * pb[:, None], cfg, norm_dim)
   return np.clip(new, 0.0, 1.0)
 
 
@@ -480,3 +483,51 @@ def run_eagle_optimizer_mixed(score_fn, *, dim: int, sizes, pool_size: int, batc
     order = np.lexsort((ii, -np.where(np.isnan(rr), -np.inf, rr)))[:count]
     best_c, best_z, best_r, best_id = f[order], z[order], rr[order], ii[order]
   return best_c, best_z, best_r
+
+
+# ----------------------------------------------------------------------------
+# Set flies (n_parallel > 1): a fly is a set of q points scored together (vectorized_base.py:331-377, :108-122;
+# eagle_strategy.py:1013-1046).  Flattened to [*, q * D]; distances and moves over all coordinates, forces normalised
+# by D, perturbations = Laplace noise divided by its largest magnitude over the q members of each feature.
+# ----------------------------------------------------------------------------
+def set_perturbation_directions(seed: int, iteration: int, batch_size: int, q: int, dim: int) -> np.ndarray:
+  """[B, q * D] normalised Laplace directions; element numbering b * q * D + m * D + f (shared with csrc/eagle_dev.cuh)."""
+  u = philox_uniform(seed, STREAM_SET_LAPLACE, iteration, batch_size * q * dim).reshape(batch_size, q, dim)
+  lap = laplace_from_uniform(u)
+  big = np.max(np.abs(lap), axis=1, keepdims=True)
+  with np.errstate(invalid='ignore', divide='ignore'):
+    out = np.where(big > 0.0, lap / big, 0.0)
+  return out.reshape(batch_size, q * dim)
+
+
+def run_eagle_optimizer_sets(
+    score_fn: Callable[[np.ndarray], np.ndarray], *, dim: int, n_parallel: int, pool_size: int, batch_size: int,
+    max_evaluations: int, count: int, seed: int, cfg: EagleConfig = EagleConfig(),
+    prior_features: Optional[np.ndarray] = None,
+):
+  """VectorizedOptimizer.__call__(n_parallel=q) with the eagle strategy and Philox draws.
+
+  score_fn([B, q, D]) -> [B].  prior_features [n, D] are grouped into n // q consecutive sets
+  (`_reshape_to_parallel_batches`, vectorized_base.py:108-122).  Returns (best sets [count, q, D], rewards, state).
+  """
+  q, width = n_parallel, n_parallel * dim
+  prior_sets = prior_rewards = None
+  if prior_features is not None and prior_features.shape[0] >= q:
+    n_sets = prior_features.shape[0] // q
+    prior_sets = prior_features[: n_sets * q].reshape(n_sets, width)
+    prior_rewards = score_fn(prior_sets.reshape(n_sets, q, dim))
+  random_pool = philox_uniform(seed, STREAM_INIT_POOL, 0, pool_size * width).reshape(pool_size, width)
+  state = init_state(random_pool, cfg, prior_sets, prior_rewards)
+  best_f = np.zeros((count, width))
+  best_r = np.full(count, -np.inf)
+  best_id = np.full(count, np.iinfo(np.int64).max, dtype=np.int64)
+  n_steps = (max_evaluations - 1) // batch_size + 1
+  for t in range(n_steps):
+    dirs = set_perturbation_directions(seed, t, batch_size, q, dim)
+    x = suggest(state, batch_size, dirs, cfg, norm_dim=dim)
+    r = score_fn(x.reshape(batch_size, q, dim))
+    rnd = philox_uniform(seed, STREAM_TRIM, t, batch_size * width).reshape(batch_size, width)
+    state = update(state, batch_size, x, r, rnd, cfg)
+    ids = np.arange(batch_size, dtype=np.int64) + t * batch_size
+    best_f, best_r, best_id = update_best(best_f, best_r, best_id, x, r, ids, count)
+  return best_f.reshape(count, q, dim), best_r, state

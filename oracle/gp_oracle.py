@@ -639,6 +639,49 @@ def ucb_pe_score(pred_a: Predictive, pred_b: Predictive, xs, zs=None, *, mode: i
   return acq, {'mean': mu, 'stddev': sd, 'stddev_from_all': sd_all}
 
 
+def predictive_covariance(pred: Predictive, xs) -> np.ndarray:
+  """Joint posterior predictive covariance at xs [m, D]: K** - V^T V + sn2 I (the GPRM of
+  stochastic_process_model.py:800-868 with predictive noise = observation noise [T])."""
+  xs = np.asarray(xs, np.float64)
+  ks = kernel(pred.params, xs, pred.x, None, pred.z, pred.cont_dim_valid, pred.cat_dim_valid)
+  ks = ks * pred.row_valid[None, :]
+  v = sla.solve_triangular(pred.chol, ks.T, lower=True)
+  kss = kernel(pred.params, xs, xs, None, None, pred.cont_dim_valid, pred.cat_dim_valid)
+  return kss - v.T @ v + pred.params.observation_noise_variance * np.eye(xs.shape[0])
+
+
+def set_pe_score(pred_a: Predictive, pred_b: Predictive, xs_sets, *, explore_coefficient=0.5, penalty_coefficient=10.0,
+                 threshold=0.0, tr_dim_mask=None, tr_rows=None, trust_radius_value=None, use_trust_region=True):
+  """SetPEScoreFunction.score_with_aux (gp_ucb_pe.py:510-594) for xs_sets [S, q, D]: logdet of the joint predictive
+  covariance under model B (-inf if not positive definite, :495-507) + penalty * sum_i min(mean_A + explore *
+  stddev_A - threshold, 0) + the set trust-region term (:245-269: sum_i (dist_i > r) & (r <= 0.5) * (-1e4 - dist_i))."""
+  xs_sets = np.asarray(xs_sets, np.float64)
+  n_sets, q, d = xs_sets.shape
+  flat = xs_sets.reshape(n_sets * q, d)
+  mu, sd = predict(pred_a, flat)
+  acq = np.zeros(n_sets)
+  sd_all = np.zeros(n_sets * q)
+  for s in range(n_sets):
+    cov = predictive_covariance(pred_b, xs_sets[s])
+    sd_all[s * q:(s + 1) * q] = np.sqrt(np.maximum(np.diag(cov), 0.0))
+    try:
+      chol = np.linalg.cholesky(cov)
+      logdet = 2.0 * np.sum(np.log(np.diag(chol)))
+      if not np.isfinite(logdet):
+        logdet = -np.inf
+    except np.linalg.LinAlgError:
+      logdet = -np.inf
+    viol = np.minimum(mu[s * q:(s + 1) * q] + explore_coefficient * sd[s * q:(s + 1) * q] - threshold, 0.0)
+    acq[s] = logdet + penalty_coefficient * np.sum(viol)
+  if use_trust_region:
+    if tr_dim_mask is None:
+      tr_dim_mask = np.ones(d, bool)
+    n_tr = pred_b.x.shape[0] if tr_rows is None else tr_rows
+    dist = min_linf_distance(flat, pred_b.x[:n_tr], tr_dim_mask).reshape(n_sets, q)
+    acq = acq + np.sum(((dist > trust_radius_value) & (trust_radius_value <= 0.5)) * (-1e4 - dist), axis=1)
+  return acq, {'mean': mu, 'stddev': sd, 'stddev_from_all': sd_all}
+
+
 # ----------------------------------------------------------------------------
 # Multi-metric: hyper-volume scalarised UCB (gp_bandit.py:214-242; acquisitions.py:132-149, 571-625;
 # scalarization.py:85-111).  The scalarisation weights are an input (the reference draws them with

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
   assert sorted(_lib.SIGNATURES) == syms, 'ctypes table and header disagree'
   for s in syms:
     assert hasattr(lib, s), f'{s} not exported by libvzgp.so'
-  assert lib.vzgp_version() == 2
+  assert lib.vzgp_version() == 3
   assert isinstance(lib.vzgp_device_count(), int)
 
 

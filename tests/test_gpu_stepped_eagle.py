@@ -139,3 +139,115 @@ def test_ucb_pe_designer_with_prior_acquisition(dev):
   assert np.max(np.abs(x1 - 0.9)) < 0.25
   val = float(s1.metadata.ns('google_gp_ucb_pe_bandit').ns('prior_acquisition')['value'])
   np.testing.assert_allclose(val, strong_prior(x1[None, :], None)[0], rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Set-PE batches (gp_ucb_pe.py:510-594, :1157-1260): set scorer, n_parallel Eagle, designer
+# ---------------------------------------------------------------------------------------------------------------------
+def _two_models(n_done, n_pend, d, seed, sn2=1e-3):
+  from vizier_b200 import gp
+  rng = np.random.default_rng(seed)
+  x = rng.uniform(size=(n_done + n_pend, d))
+  y = -np.sum((x[:n_done] - 0.3) ** 2, axis=1) + 0.05 * rng.normal(size=n_done)
+  ls2 = 0.3 * (1 + np.arange(d) / d)
+  po, pg = go.GPParams(1.1, ls2, sn2), gp.GPHyperParams(1.1, ls2, sn2)
+  pred_a = go.precompute_predictive(po, x[:n_done], y)
+  y_all = np.r_[y, np.zeros(n_pend)]
+  pred_b = go.precompute_predictive(po, x, y_all)
+  dev_a = gp.DeviceGP(0)
+  dev_b = gp.DeviceGP(0, stream=dev_a.stream)     # both models on one stream (vzgp_score_set_pe requires it)
+  return x, y, y_all, pg, pred_a, pred_b, dev_a, dev_b
+
+
+@pytest.mark.parametrize('n_done,n_pend,d,q,radius', [(60, 5, 4, 3, 0.25), (150, 0, 6, 5, 0.9), (40, 8, 2, 8, 0.3)])
+def test_set_pe_score_matches_oracle(n_done, n_pend, d, q, radius):
+  from vizier_b200 import gp
+  x, y, y_all, pg, pred_a, pred_b, dev_a, dev_b = _two_models(n_done, n_pend, d, 3)
+  dev_a.fit(x[:n_done], y, pg)
+  dev_b.fit(x, y_all, pg)
+  rng = np.random.default_rng(9)
+  sets = rng.uniform(size=(37, q, d))
+  sets[3, 1] = sets[3, 0]                      # a duplicated point: covariance singular up to the noise
+  sets[5] = x[:q]                              # a set of observed points
+  pe = gp.UcbPeAcquisition(mode=1, explore_coefficient=0.5, penalty_coefficient=10.0, threshold=-0.2,
+                           use_trust_region=True, trust_radius=radius, tr_rows=n_done + max(n_pend - 2, 0))
+  out = dev_a.score_set_pe(dev_b, sets.reshape(-1, d), q, pe)
+  dev_a.synchronize()
+  want, aux = go.set_pe_score(pred_a, pred_b, sets, explore_coefficient=0.5, penalty_coefficient=10.0, threshold=-0.2,
+                              tr_rows=n_done + max(n_pend - 2, 0), trust_radius_value=radius)
+  np.testing.assert_allclose(out['mean'].cpu().numpy(), aux['mean'], atol=1e-10)
+  np.testing.assert_allclose(out['stddev'].cpu().numpy(), aux['stddev'], atol=1e-10)
+  np.testing.assert_allclose(out['stddev_from_all'].cpu().numpy(), aux['stddev_from_all'], atol=1e-9)
+  np.testing.assert_allclose(out['score'].cpu().numpy(), want, rtol=1e-9, atol=1e-7)
+  dev_a.close(); dev_b.close()
+
+
+def test_eagle_sets_trajectory_matches_oracle():
+  """The n_parallel form of the optimiser (set flies) through the stepped loop against the oracle's, same Philox draws."""
+  from vizier_b200 import gp
+  n_done, n_pend, d, q, pool, batch, steps = 50, 4, 3, 4, 50, 25, 10
+  x, y, y_all, pg, pred_a, pred_b, dev_a, dev_b = _two_models(n_done, n_pend, d, 5)
+  dev_a.fit(x[:n_done], y, pg)
+  dev_b.fit(x, y_all, pg)
+  radius = 0.35
+  pe = gp.UcbPeAcquisition(mode=1, explore_coefficient=0.5, penalty_coefficient=10.0, threshold=-0.1,
+                           use_trust_region=True, trust_radius=radius, tr_rows=n_done + n_pend)
+  cfg_o = eo.EagleConfig()
+  cfg = _cfg(cfg_o, pool, batch, steps)
+  cfg.n_parallel = q
+  n_sets = n_done // q
+  prior_sets = x[: n_sets * q].reshape(n_sets, q * d)
+  score = lambda xs: dev_a.score_set_pe(dev_b, xs.reshape(-1, d), q, pe)['score']
+  se = gp.SteppedEagle(dev_a, cfg, 2, 11, n_prior=n_sets)
+  se.seed(prior_sets, None, score(torch.from_numpy(prior_sets).cuda()))
+  for _ in range(steps):
+    xs, _, rewards = se.ask()
+    r = score(xs)
+    with torch.cuda.stream(dev_a._stream):
+      rewards.copy_(r)
+    se.tell()
+  bx, _, br = se.end()
+  score_fn = lambda s: go.set_pe_score(pred_a, pred_b, s, explore_coefficient=0.5, penalty_coefficient=10.0, threshold=-0.1,
+                                       tr_rows=n_done + n_pend, trust_radius_value=radius)[0]
+  wx, wr, _ = eo.run_eagle_optimizer_sets(score_fn, dim=d, n_parallel=q, pool_size=pool, batch_size=batch,
+                                          max_evaluations=steps * batch, count=2, seed=11, cfg=cfg_o, prior_features=x[:n_done])
+  np.testing.assert_allclose(br, wr, rtol=1e-8, atol=1e-6)
+  np.testing.assert_allclose(bx.reshape(2, q, d), wx, atol=1e-8)
+  dev_a.close(); dev_b.close()
+
+
+def test_ucb_pe_designer_set_batches(dev):
+  """`optimize_set_acquisition_for_exploration=True`: a batch of 4 = one UCB/PE suggestion + a set of 3 (or a set of 4
+  when nothing completed since the last suggestion); points of a set are spread out (log-det acquisition)."""
+  del dev
+  from vizier_b200 import vz
+  from vizier_b200.designers import gp_ucb_pe
+  from vizier_b200 import optimizers as vb
+  import dataclasses
+  p = vz.ProblemStatement()
+  for i in range(3):
+    p.search_space.root.add_float_param(f'x{i}', 0.0, 1.0)
+  p.metric_information.append(vz.MetricInformation(name='obj', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  rng = np.random.default_rng(0)
+  trials = []
+  for i in range(40):
+    xv = rng.uniform(size=3)
+    t = vz.Trial(parameters={f'x{j}': float(xv[j]) for j in range(3)}, id=i + 1)
+    t.complete(vz.Measurement({'obj': float(-np.sum((xv - 0.3) ** 2))}))
+    trials.append(t)
+  fac = vb.VectorizedOptimizerFactory(strategy_factory=vb.VectorizedEagleStrategyFactory(eagle_config=gp_ucb_pe.default_eagle_config),
+                                      max_evaluations=3000, suggestion_batch_size=25)
+  cfg = dataclasses.replace(gp_ucb_pe.UCBPEConfig(), optimize_set_acquisition_for_exploration=True)
+  d = gp_ucb_pe.VizierGPUCBPEBandit(p, acquisition_optimizer_factory=fac, config=cfg, rng=2)
+  d.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  sugg = d.suggest(4)
+  assert len(sugg) == 4
+  pts = np.array([[s.parameters[f'x{j}'].value for j in range(3)] for s in sugg])
+  assert np.all((pts >= 0) & (pts <= 1))
+  ns = 'google_gp_ucb_pe_bandit'
+  flags = [s.metadata.ns(ns).ns('prediction_in_warped_y_space')['use_ucb'] for s in sugg]
+  assert flags[1:] == ['False'] * 3                     # the set part is pure exploration
+  acqs = {s.metadata.ns(ns).ns('prediction_in_warped_y_space')['acquisition'] for s in sugg[1:]}
+  assert len(acqs) == 1                                 # one acquisition value for the whole set
+  dmin = min(np.linalg.norm(pts[i] - pts[j]) for i in range(1, 4) for j in range(i + 1, 4))
+  assert dmin > 0.05                                    # log-det repels the members from each other

@@ -95,6 +95,7 @@ class EagleConfig(C.Structure):
       ('pure_categorical_perturbation_factor', C.c_double),
       ('prob_same_category_without_perturbation', C.c_double),
       ('mutate_normalization_type', C.c_int),
+      ('n_parallel', C.c_int),
   ]
 
   def __init__(self, *args, **kwargs):
@@ -171,6 +172,7 @@ SIGNATURES = {
     'vzgp_eagle_run': (_i, [_vp, _pE, _pA, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
     'vzgp_score_pe': (_i, [_vp, _vp, _vp, _vp, _i, _pPE, _vp, _vp, _vp, _vp]),
     'vzgp_eagle_run_pe': (_i, [_vp, _vp, _pE, _pPE, _vp, _vp, _i, _pi32, _i, _u64, _pd, _pi32, _pd]),
+    'vzgp_score_set_pe': (_i, [_vp, _vp, _vp, _i, _i, _pPE, _vp, _vp, _vp, _vp]),
     'vzgp_eagle_begin': (_i, [_vp, _pE, _pi32, _i, _u64, _i, C.POINTER(C.c_void_p)]),
     'vzgp_eagle_seed': (_i, [_vp, _vp, _vp]),
     'vzgp_eagle_ask': (_i, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

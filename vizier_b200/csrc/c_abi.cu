@@ -386,7 +386,7 @@ using namespace vzgp;
 extern "C" {
 
 const char* vzgp_last_error(void) { return g_err; }
-int vzgp_version(void) { return 2; }
+int vzgp_version(void) { return 3; }
 
 int vzgp_device_count(void) {
   int n = 0;
@@ -891,8 +891,12 @@ struct EagleScratch {
 static int eagle_setup(vzgp_handle* h, const vzgp_eagle_config* cfg, const int32_t* cat_sizes, int count, uint64_t seed,
                        int n_prior, EagleDev* pe_, EagleScratch* sc) {
   EagleDev& e = *pe_;
-  const int P = cfg->pool_size, B = cfg->batch_size, D = h->dc, Dk = h->dk;
+  const int q = cfg->n_parallel > 1 ? cfg->n_parallel : 1;
+  VZ_ARG(q == 1 || (h->dk == 0 && h->dc * q <= kMaxDc), "n_parallel > 1 needs continuous features only and n_parallel * Dc <= 64");
+  const int P = cfg->pool_size, B = cfg->batch_size, D = h->dc * q, Dk = h->dk;
   VZ_TRY(check_cat_sizes(h, cat_sizes, e.sizes, &e.smax));
+  e.q = q;
+  e.norm_dim = h->dc + h->dk;
   // carve the eagle buffer: doubles | long longs | ints
   const size_t np1 = (size_t)(n_prior > 0 ? n_prior : 1);
   const size_t nd = (size_t)P * D + 2 * (size_t)P + 8 + (size_t)B * D + B + 2 * ((size_t)count * D + count) + np1 + P;
@@ -952,6 +956,7 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   VZ_ARG(best_x != nullptr || h->dc == 0, "best_x");
   VZ_ARG(best_z != nullptr || h->dk == 0, "best_z");
   VZ_TRY(eagle_check_config(h, cfg, count));
+  VZ_ARG(cfg->n_parallel <= 1, "n_parallel > 1 runs through the host-stepped loop (vzgp_eagle_begin ...)");
   VZ_ARG(n_prior >= 0, "n_prior");
   VZ_ARG(n_prior == 0 || prior != nullptr || h->dc == 0, "prior");
   VZ_ARG(n_prior == 0 || prior_z != nullptr || h->dk == 0, "prior_z");
@@ -1157,6 +1162,41 @@ int vzgp_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int3
   VZ_ARG(M >= 0 && (M == 0 || score != nullptr), "M / score");
   Guard g(hA->device);
   return launch_score_pe(hA, hB, Xs, Zs, M, pe, score, mu, sigma, sigma_all);
+}
+
+int vzgp_score_set_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, int n_sets, int q, const vzgp_pe_params* pe,
+                      double* score, double* mu, double* sigma, double* sigma_all) {
+  VZ_TRY(check_pe(hA, hB, pe));
+  VZ_ARG(hA->dk == 0, "set acquisitions: continuous features only");
+  VZ_ARG(n_sets >= 0 && q >= 1 && q <= 16, "n_sets >= 0, 1 <= q <= 16");
+  VZ_ARG(n_sets == 0 || (Xs != nullptr && score != nullptr), "Xs / score");
+  if (n_sets == 0) return 0;
+  Guard g(hA->device);
+  const int M = n_sets * q;
+  // pe_tmp of A: mu_a | sd_a | linf_b | dummy_a | dummy_b | sd_b [6 M]  then  cov [M x M]  then  mean_b [M]
+  VZ_TRY(hA->pe_tmp.reserve(sizeof(double) * (7 * (size_t)M + (size_t)M * M)));
+  double* t = hA->pe_tmp.as<double>();
+  double* mu_a = mu ? mu : t;
+  double* sd_a = sigma ? sigma : t + M;
+  double* linf_b = t + 2 * (size_t)M;
+  double* dummy_a = t + 3 * (size_t)M;
+  double* dummy_b = t + 4 * (size_t)M;
+  double* sd_b = t + 5 * (size_t)M;
+  double* mean_b = t + 6 * (size_t)M;
+  double* cov = t + 7 * (size_t)M;
+  vzgp_acq none;
+  none.ucb_coefficient = 0.0; none.use_trust_region = 0; none.trust_radius = 1.0; none.tr_dim_mask = nullptr;
+  none.tr_rows = 0; none.tr_strict = 0;
+  VZ_TRY(launch_score(hA, Xs, nullptr, M, &none, dummy_a, mu_a, sd_a, nullptr));
+  const bool want_tr = pe->use_trust_region && pe->trust_radius <= 0.5;
+  if (want_tr) {
+    vzgp_acq accb = none;
+    accb.tr_dim_mask = pe->tr_dim_mask;
+    accb.tr_rows = pe->tr_rows;
+    VZ_TRY(launch_score(hB, Xs, nullptr, M, &accb, dummy_b, nullptr, sd_b, linf_b));
+  }
+  VZ_TRY(vzgp_posterior_multi(hB, Xs, nullptr, M, 1, mean_b, cov, M));
+  return launch_set_pe_combine(hA, n_sets, q, pe, cov, M, mu_a, sd_a, want_tr ? linf_b : nullptr, score, sigma_all);
 }
 
 int vzgp_eagle_run_pe(vzgp_handle* hA, vzgp_handle* hB, const vzgp_eagle_config* cfg,

@@ -10,7 +10,7 @@
 namespace vzgp {
 
 constexpr uint32_t kStreamInitCat = 4, kStreamCatLaplace = 5, kStreamCatGumbel = 6, kStreamTrimCat = 7,
-                   kStreamPullRand = 9, kStreamPushRand = 10;
+                   kStreamPullRand = 9, kStreamPushRand = 10, kStreamSetLaplace = 11;
 
 __device__ __forceinline__ double laplace_from_uniform(double u) {
   const double v = u - 0.5;
@@ -18,6 +18,24 @@ __device__ __forceinline__ double laplace_from_uniform(double u) {
   return v > 0.0 ? l : (v < 0.0 ? -l : 0.0);
 }
 __device__ __forceinline__ double gumbel_from_uniform(double u) { return -log(-log(fmax(u, 1e-300))); }
+// Continuous perturbation of coordinate d of batch fly b (eagle_strategy.py:1013-1046): Laplace noise divided by its
+// largest magnitude over the q members of the same feature.  q = 1: the quotient is +-1 and one sign bit is drawn
+// (stream kStreamPerturbSign); q > 1: coordinate d = m * Dm + f, uniforms of stream kStreamSetLaplace.
+__device__ __forceinline__ double eagle_perturbation(const EagleDev& e, int t, int b, int d, double pert) {
+  if (e.q <= 1) {
+    const double u = philox_uniform(e.seed, kStreamPerturbSign, (uint32_t)t, (uint64_t)b * e.D + d);
+    return u >= 0.5 ? pert : -pert;
+  }
+  const int dm = e.D / e.q, f = d % dm;
+  double mine = 0.0, big = 0.0;
+  for (int m = 0; m < e.q; ++m) {
+    const int dd = m * dm + f;
+    const double l = laplace_from_uniform(philox_uniform(e.seed, kStreamSetLaplace, (uint32_t)t, (uint64_t)b * e.D + dd));
+    big = fmax(big, fabs(l));
+    if (dd == d) mine = l;
+  }
+  return big > 0.0 ? mine / big * pert : 0.0;
+}
 __device__ __forceinline__ int uniform_category(double u, int size) {
   const int c = (int)(u * (double)size);
   return c < size - 1 ? c : size - 1;
@@ -63,7 +81,7 @@ __device__ __forceinline__ void eagle_suggest_block(const EagleDev& e, int vbloc
     return;
   }
   const double ri = e.rewards[i];
-  const double cexp = -e.cfg.visibility / (double)(D + Dk) * 10.0;
+  const double cexp = -e.cfg.visibility / (double)e.norm_dim * 10.0;
   int npull = 0, npush = 0;
   for (int j = lane; j < P; j += 32) {
     const double d2 = fly_distance(s_x, e.pool + (size_t)j * D, D, s_z, e.pool_z + (size_t)j * Dk, Dk);
@@ -152,13 +170,11 @@ __device__ __forceinline__ void eagle_suggest_block(const EagleDev& e, int vbloc
   }
   const double pert = e.pert[i];
   if (d0 < D) {
-    const double u = philox_uniform(e.seed, kStreamPerturbSign, (uint32_t)t, (uint64_t)b * D + d0);
-    const double v = s_x[d0] + (acc0 - s_x[d0] * ssum) + (u >= 0.5 ? pert : -pert);
+    const double v = s_x[d0] + (acc0 - s_x[d0] * ssum) + eagle_perturbation(e, t, b, d0, pert);
     out[d0] = fmin(fmax(v, 0.0), 1.0);
   }
   if (d1 < D) {
-    const double u = philox_uniform(e.seed, kStreamPerturbSign, (uint32_t)t, (uint64_t)b * D + d1);
-    const double v = s_x[d1] + (acc1 - s_x[d1] * ssum) + (u >= 0.5 ? pert : -pert);
+    const double v = s_x[d1] + (acc1 - s_x[d1] * ssum) + eagle_perturbation(e, t, b, d1, pert);
     out[d1] = fmin(fmax(v, 0.0), 1.0);
   }
   // ---- categorical features (eagle_strategy.py:936-1011): lane = category (and lane+32) ----
@@ -230,7 +246,7 @@ __device__ __forceinline__ void eagle_suggest_cta(const EagleDev& e, int b, doub
     return;
   }
   const double ri = e.rewards[i];
-  const double cexp = -e.cfg.visibility / (double)(D + Dk) * 10.0;
+  const double cexp = -e.cfg.visibility / (double)e.norm_dim * 10.0;
   int npull = 0, npush = 0;
   for (int j = tid; j < P; j += NT) {
     const double d2 = fly_distance(s_x, e.pool + (size_t)j * D, D, s_z, e.pool_z + (size_t)j * Dk, Dk);

@@ -84,6 +84,8 @@ int make_tensor_map_u8(void* map, const void* base, int rank, const uint64_t* di
                        const uint32_t* box);
 int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
                     const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
+int launch_set_pe_combine(vzgp_handle* h, int n_sets, int q, const vzgp_pe_params* pe, const double* cov, int ldc,
+                          const double* mu_a, const double* sd_a, const double* linf, double* score, double* sd_all);
 int prepare_scalarization(vzgp_handle* h, const vzgp_scalarization* sc);
 int launch_score_multi(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, double* score, double* mu_out,
                        double* sigma_out);
@@ -127,6 +129,8 @@ struct EagleDev {
   int32_t* best_z;   // [count x Dk]
   int32_t* tmp_z;    // [count x Dk]
   int P, B, D, Dk, smax, count;
+  int norm_dim;   // feature dimensions of ONE point (Dc + Dk of the model): normalises the force exponent
+  int q;          // points per fly (n_parallel); D = q * Dc
   int sizes[kMaxDk];
   vzgp_eagle_config cfg;
   uint64_t seed;

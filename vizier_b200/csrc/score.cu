@@ -761,6 +761,69 @@ int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const in
 }
 
 // ---------------------------------------------------------------------------
+// Set-PE acquisition (SetPEScoreFunction, gp_ucb_pe.py:510-594): per set of q points
+//   logdet(joint predictive covariance under model B)  +  penalty * sum_i min(mean_A + explore * stddev_A - threshold, 0)
+//   [+ sum_i (dist_i > radius and radius <= 0.5) * (-1e4 - dist_i)      _apply_trust_region_to_set, :245-269]
+// One warp per set: the q x q block of the [M x M] covariance is factored in shared memory (q <= 16); a pivot that is
+// not positive gives -inf like the reference's NaN -> -inf rule (:495-507).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_set_pe_combine(int n_sets, int q, PeCombine p, const double* __restrict__ cov, int ldc,
+                                                       const double* __restrict__ mu_a, const double* __restrict__ sd_a,
+                                                       const double* __restrict__ linf, double* __restrict__ score,
+                                                       double* __restrict__ sd_all) {
+  __shared__ double c[16][17];
+  const int s = blockIdx.x, lane = threadIdx.x;
+  if (s >= n_sets) return;
+  const int r0 = s * q;
+  for (int e = lane; e < q * q; e += 32) c[e / q][e % q] = cov[(size_t)(r0 + e / q) * ldc + r0 + e % q];
+  __syncwarp();
+  if (sd_all && lane < q) sd_all[r0 + lane] = sqrt(fmax(c[lane][lane], 0.0));
+  double logdet = 0.0;
+  bool bad = false;
+  for (int k = 0; k < q; ++k) {
+    const double d = c[k][k];
+    if (!(d > 0.0) || !isfinite(d)) { bad = true; break; }
+    logdet += log(d);
+    __syncwarp();
+    const double inv = 1.0 / d;
+    // right-looking LDL^T step on the trailing block: lane = row i > k
+    for (int i = k + 1 + lane; i < q; i += 32) {
+      const double lik = c[i][k] * inv;
+      for (int j = k + 1; j <= i; ++j) c[i][j] -= lik * c[j][k];
+    }
+    __syncwarp();
+    // keep the block symmetric for the next pivot column reads (c[j][k] with j > k is the lower part: already there)
+  }
+  double pen = 0.0, tr = 0.0;
+  for (int i = lane; i < q; i += 32) {
+    pen += fmin(mu_a[r0 + i] + p.explore * sd_a[r0 + i] - p.threshold, 0.0);
+    if (p.apply_tr) {
+      const double dist = linf[r0 + i];
+      if (dist > p.radius) tr += -1e4 - dist;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pen += __shfl_xor_sync(0xffffffffu, pen, o);
+    tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  }
+  if (lane == 0) score[s] = (bad ? -INFINITY : logdet) + p.penalty * pen + tr;
+}
+
+int launch_set_pe_combine(vzgp_handle* h, int n_sets, int q, const vzgp_pe_params* pe, const double* cov, int ldc,
+                          const double* mu_a, const double* sd_a, const double* linf, double* score, double* sd_all) {
+  PeCombine p;
+  p.mode = 1; p.ucb = pe->ucb_coefficient; p.explore = pe->explore_coefficient;
+  p.penalty = pe->penalty_coefficient; p.threshold = pe->threshold;
+  p.apply_tr = (pe->use_trust_region && pe->trust_radius <= 0.5 && linf != nullptr) ? 1 : 0;
+  p.radius = pe->trust_radius;
+  k_set_pe_combine<<<n_sets, 32, 0, h->stream>>>(n_sets, q, p, cov, ldc, mu_a, sd_a, linf, score, sd_all);
+  VZ_CHECK_LAUNCH();
+  h->launches++;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Uniform ensemble of E models (UniformEnsemblePredictive, stochastic_process_model.py:846-868:
 // equal-weight MixtureSameFamily): mean = avg mu_e, var = avg(sd_e^2 + mu_e^2) - mean^2.
 // ---------------------------------------------------------------------------

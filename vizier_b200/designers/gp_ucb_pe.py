@@ -17,8 +17,9 @@ configuration (`UCBPEConfig()` with `optimize_set_acquisition_for_exploration=Fa
 Everything numeric runs in libvzgp (two handles on one stream, `vzgp_score_pe`,
 `vzgp_eagle_run_pe`); `sample` / `predict` (:1262-1354) draw from the device-computed joint posterior
 like `VizierGPBandit`.  `prior_acquisition` (a callable on NumPy features) is added to both acquisitions through the
-host-stepped Eagle loop (`gp.SteppedEagle`).  Not implemented: multi-metric, set-PE batches
-(`optimize_set_acquisition_for_exploration=True`), linear-kernel mixing, ensembles - each raises
+host-stepped Eagle loop (`gp.SteppedEagle`); `optimize_set_acquisition_for_exploration=True` optimises the rest of a
+batch as ONE set for the set-PE acquisition (`vzgp_score_set_pe`, the optimiser's n_parallel form; continuous search
+spaces with count * Dc <= 64).  Not implemented: multi-metric, linear-kernel mixing, ensembles - each raises
 NotImplementedError.
 """
 
@@ -115,8 +116,6 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
       raise ValueError(f'{type(self)} does not support conditional search.')
     if len(problem.metric_information) != 1:
       raise NotImplementedError('vizier_b200.VizierGPUCBPEBandit implements the single-metric path only.')
-    if config.optimize_set_acquisition_for_exploration:
-      raise NotImplementedError('set-PE batches are not implemented.')
     if mixes_linear_kernel or (ensemble_size or 1) != 1:
       raise NotImplementedError('linear kernel / ensembles are not implemented for GP-UCB-PE.')
     del clear_jax_cache, padding_schedule
@@ -281,6 +280,50 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     md.ns(self._metadata_ns).ns('timing')['time'] = f'{datetime.datetime.now() - start}'
     return vz.TrialSuggestion(params_dict, metadata=md)
 
+  @profiler.record_runtime
+  def _suggest_batch_with_exploration(self, count, active_trials, cont, cat, labels, params, mask, radius, n_tr_rows):
+    """gp_ucb_pe.py:1157-1260: `count` suggestions as one set maximising the set-PE acquisition (log-determinant of
+    the joint predictive covariance given completed + pending trials, penalised below the UCB threshold)."""
+    start = datetime.datetime.now()
+    cfg = self._config
+    dev_a, dev_b = self._devices()
+    snr = params.signal_variance / max(params.observation_noise_variance, 1e-12)
+    noise_is_high = snr < cfg.signal_to_noise_threshold
+    pend_c, pend_z = self._converter.to_features(active_trials)
+    pend_c = np.nan_to_num(pend_c, nan=0.0)
+    xc_all, xz_all = self._fit_all_features(params, cont, cat, labels, pend_c, pend_z, noise_is_high)
+    dk = cat.shape[1]
+    out = dev_a.score(xc_all, gp.Acquisition(cfg.ucb_coefficient, False, 1.0), zs=xz_all if dk else None, with_aux=True)
+    dev_a.synchronize()
+    mu = out['mean'].cpu().numpy(); sd = out['stddev'].cpu().numpy()
+    threshold = float(mu[int(np.argmax(mu + cfg.ucb_coefficient * sd))])
+    pe = gp.UcbPeAcquisition(
+        mode=1, ucb_coefficient=cfg.ucb_coefficient, explore_coefficient=cfg.explore_region_ucb_coefficient,
+        penalty_coefficient=cfg.cb_violation_penalty_coefficient, threshold=threshold,
+        use_trust_region=self._use_trust_region, trust_radius=radius, tr_dim_mask=mask, tr_rows=n_tr_rows)
+    optimizer = self._acquisition_optimizer_factory(self._converter)
+    prior = converters.trials_to_sorted_features(self._all_completed_trials, self._converter, (cont, cat))
+    res = optimizer.optimize_sets(dev_a, dev_b, pe, n_parallel=count, prior_features=None if prior is None else prior[0],
+                                  seed=int(self._rng.integers(2**62)), prior_acquisition=self._prior_acquisition)
+    params_list = self._converter.to_parameters(res.features, None)
+    end = datetime.datetime.now()
+    suggestions = []
+    for i, params_dict in enumerate(params_list):
+      md = vz.Metadata()
+      pred = md.ns(self._metadata_ns).ns('prediction_in_warped_y_space')
+      pred['mean'] = repr(float(res.aux['mean'][i]))
+      pred['stddev'] = repr(float(res.aux['stddev'][i]))
+      pred['stddev_from_all'] = repr(float(res.aux['stddev_from_all'][i]))
+      pred['acquisition'] = f'{float(res.rewards[0])}'
+      pred['use_ucb'] = 'False'
+      pred['trust_radius'] = f'{radius}'
+      pred['params'] = f'{params}'
+      if 'prior_acq_values' in res.aux:
+        md.ns(self._metadata_ns).ns('prior_acquisition')['value'] = f'{float(res.aux["prior_acq_values"][0])}'
+      md.ns(self._metadata_ns).ns('timing')['time'] = f'{end - start}'
+      suggestions.append(vz.TrialSuggestion(params_dict, metadata=md))
+    return suggestions
+
   # ------------------------------------------------------------------ suggest
   @profiler.record_runtime
   def suggest(self, count: Optional[int] = None):
@@ -300,6 +343,13 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     radius = acq_lib.trust_radius(n_tr, int(mask.sum()), self._converter.n_categorical)
     active = list(self._all_active_trials)
     out = []
+    if count > 1 and self._config.optimize_set_acquisition_for_exploration and not prior_only:
+      # gp_ucb_pe.py:1423-1434: one UCB / PE suggestion if trials completed since the newest active one, then the
+      # rest of the batch as ONE set optimised for the set-PE acquisition
+      if _has_new_completed_trials(self._all_completed_trials, active):
+        out.append(self._suggest_one(active, cont, cat, labels, params, mask, radius, n_tr))
+        active.append(out[-1].to_trial())
+      return out + self._suggest_batch_with_exploration(count - len(out), active, cont, cat, labels, params, mask, radius, n_tr)
     for _ in range(count):
       if prior_only:
         s = self._suggest_one_prior_only(active, params, mask, radius, n_tr)

@@ -653,6 +653,25 @@ class DeviceGP:
     del keep
     return res
 
+  def score_set_pe(self, other: 'DeviceGP', xs_sets, q: int, pe: UcbPeAcquisition) -> dict:
+    """Set-PE acquisition (gp_ucb_pe.py:510-594) of n_sets sets of q points: xs_sets [n_sets * q, Dc] (or
+    [n_sets, q * Dc]).  self = model on completed trials, other = model on completed + pending trials.  Returns
+    device tensors {'score' [n_sets], 'mean', 'stddev', 'stddev_from_all' [n_sets * q]}; asynchronous."""
+    xst = self._dev(xs_sets, torch.float64).reshape(-1, self.dc)
+    m = xst.shape[0]
+    assert m % q == 0
+    n_sets = m // q
+    res = {'score': torch.empty((n_sets,), dtype=torch.float64, device=self.device)}
+    for k in ('mean', 'stddev', 'stddev_from_all'):
+      res[k] = torch.empty((m,), dtype=torch.float64, device=self.device)
+    self._stream.wait_stream(torch.cuda.current_stream(self.device))
+    p, keep = pe._c()
+    _lib.check('vzgp_score_set_pe', self._lib.vzgp_score_set_pe(
+        self._h, other._h, _ptr(xst), n_sets, int(q), C.byref(p), _ptr(res['score']), _ptr(res['mean']),
+        _ptr(res['stddev']), _ptr(res['stddev_from_all'])))
+    res['_inputs'] = (xst, keep)
+    return res
+
   def eagle_run(self, cfg: '_lib.EagleConfig', acq, count: int, seed: int,
                 prior: Optional[Sequence] = None, prior_z: Optional[Sequence] = None, cat_sizes=None,
                 other: Optional['DeviceGP'] = None):
@@ -710,6 +729,8 @@ class SteppedEagle:
   def __init__(self, dev: 'DeviceGP', cfg: '_lib.EagleConfig', count: int, seed: int, n_prior: int = 0, cat_sizes=None):
     self.dev, self.count, self.batch_size = dev, count, int(cfg.batch_size)
     self.n_prior = int(n_prior)
+    self.q = max(1, int(cfg.n_parallel))          # points per fly (set acquisitions)
+    self.fly_dim = dev.dc * self.q
     sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
     pr = C.c_void_p(0)
     _lib.check('vzgp_eagle_begin', dev._lib.vzgp_eagle_begin(
@@ -725,7 +746,7 @@ class SteppedEagle:
     d = self.dev
     with torch.cuda.stream(d._stream):
       self._view(self._prior_rewards, (self.n_prior,), '<f8').copy_(torch.as_tensor(rewards, dtype=torch.float64, device=d.device))
-    pt = d._dev(prior, torch.float64) if d.dc > 0 else None
+    pt = d._dev(prior, torch.float64).reshape(self.n_prior, self.fly_dim).contiguous() if d.dc > 0 else None
     pz = d._dev(prior_z, torch.int32) if d.dk > 0 else None
     d._stream.wait_stream(torch.cuda.current_stream(d.device))
     _lib.check('vzgp_eagle_seed', d._lib.vzgp_eagle_seed(d._h, _ptr(pt), _ptr(pz)))
@@ -737,7 +758,7 @@ class SteppedEagle:
     px, pz, pr = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
     _lib.check('vzgp_eagle_ask', d._lib.vzgp_eagle_ask(d._h, C.byref(px), C.byref(pz), C.byref(pr)))
     b = self.batch_size
-    xs = self._view(px.value, (b, d.dc), '<f8') if d.dc > 0 else torch.zeros((b, 0), dtype=torch.float64, device=d.device)
+    xs = self._view(px.value, (b, self.fly_dim), '<f8') if d.dc > 0 else torch.zeros((b, 0), dtype=torch.float64, device=d.device)
     zs = self._view(pz.value, (b, d.dk), '<i4') if d.dk > 0 else None
     return xs, zs, self._view(pr.value, (b,), '<f8')
 
@@ -746,7 +767,7 @@ class SteppedEagle:
 
   def end(self):
     d = self.dev
-    bx = np.zeros((self.count, d.dc), np.float64)
+    bx = np.zeros((self.count, self.fly_dim), np.float64)
     bz = np.zeros((self.count, d.dk), np.int32)
     bs = np.zeros(self.count, np.float64)
     _lib.check('vzgp_eagle_end', d._lib.vzgp_eagle_end(

@@ -124,6 +124,53 @@ class VectorizedOptimizer:
       se.tell()
     return se.end()
 
+  def optimize_sets(self, dev: gp.DeviceGP, other: gp.DeviceGP, pe: gp.UcbPeAcquisition, *, n_parallel: int,
+                    prior_features: Optional[np.ndarray] = None, seed: int = 0,
+                    prior_acquisition: Optional[Callable] = None) -> VectorizedStrategyResults:
+    """`acquisition_optimizer(scoring_fn.score, ..., count=1, n_parallel=q)` with the set-PE acquisition
+    (gp_ucb_pe.py:1178-1202; vectorized_base.py:331-377): a fly is a set of q points, scored by `vzgp_score_set_pe`;
+    the Eagle state and kernels run in their n_parallel form through the host-stepped loop.  prior_features [n, Dc]
+    are grouped into n // q consecutive sets (vectorized_base.py:108-122).  `prior_acquisition`, if given, is called
+    with (continuous [B, q, Dc], categorical [B, q, 0]) and returns [B].  Returns the best set: features [q, Dc],
+    rewards [q] (the set's acquisition value repeated), aux per point."""
+    import torch
+    q, d = int(n_parallel), self.n_continuous
+    if isinstance(self.strategy_factory, _RandomStrategyFactory) or self.n_categorical > 0 or q * d > 64 or q > 16:
+      raise NotImplementedError('set acquisitions need the Eagle strategy, continuous features, n_parallel * Dc <= 64 '
+                                'and n_parallel <= 16')
+    cfg = self._eagle_config()
+    cfg.n_parallel = q
+
+    def score(xs_flat):          # [B, q * Dc] device -> [B] device
+      with torch.cuda.stream(dev._stream):
+        out = dev.score_set_pe(other, xs_flat.reshape(-1, d), q, pe)['score']
+        if prior_acquisition is not None:
+          xh = xs_flat.cpu().numpy().reshape(-1, q, d)
+          vals = np.asarray(prior_acquisition(xh, np.zeros((xh.shape[0], q, 0), np.int32)), np.float64).reshape(-1)
+          out = out + torch.as_tensor(vals, dtype=torch.float64, device=dev.device)
+        return out
+
+    n_sets = 0 if prior_features is None else len(prior_features) // q
+    se = gp.SteppedEagle(dev, cfg, 1, seed, n_sets)
+    if n_sets > 0:
+      ps = np.ascontiguousarray(np.asarray(prior_features, np.float64)[: n_sets * q].reshape(n_sets, q * d))
+      se.seed(ps, None, score(dev._dev(ps, torch.float64)))
+    steps = (self.max_evaluations - 1) // self.suggestion_batch_size + 1
+    for _ in range(steps):
+      xs, _, rewards = se.ask()
+      r = score(xs)
+      with torch.cuda.stream(dev._stream):
+        rewards.copy_(r)
+      se.tell()
+    bx, _, bs = se.end()
+    best = bx[0].reshape(q, d)
+    out = dev.score_set_pe(other, best, q, pe)
+    dev.synchronize()
+    aux = {k: out[k].cpu().numpy() for k in ('mean', 'stddev', 'stddev_from_all')}
+    if prior_acquisition is not None:
+      aux['prior_acq_values'] = np.asarray(prior_acquisition(best[None], np.zeros((1, q, 0), np.int32)), np.float64).reshape(-1)
+    return VectorizedStrategyResults(best, np.full(q, bs[0]), aux, categorical=np.zeros((q, 0), np.int32))
+
   def __call__(self, dev: gp.DeviceGP, acq, *, count: int = 1,
                prior_features: Optional[np.ndarray] = None, prior_categorical: Optional[np.ndarray] = None,
                seed: int = 0, other: Optional[gp.DeviceGP] = None,
