@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in i8timing i8t_STORES i8t_MATERN; do
-VZGP_LIB=$PWD/vizier_b200/_lib/libvzgp_$v.so timeout 200 python tools/i8_timing.py > gpurun_out/i8_timing_$v.log 2>&1; echo "$v exit $?"; tail -1 gpurun_out/i8_timing_$v.log
-done
+timeout 300 python -m pytest tests/test_gpu_score_i8.py -x -q > gpurun_out/pytest_i8.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_i8.log
+timeout 200 python tools/bench_i8.py > gpurun_out/bench_i8.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench_i8.log
+timeout 200 python tools/bench_i8.py 2000 50 > gpurun_out/bench_i8_c4.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench_i8_c4.log

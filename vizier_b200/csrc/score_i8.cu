@@ -51,7 +51,9 @@ namespace vzgp {
 namespace {
 
 constexpr int kKWarps = 16;                   // K* warps (phase 1); 22 warps in all -> 80 registers per thread
-constexpr int kEWarps = 4;                    // epilogue warps: one per TMEM lane quarter
+constexpr int kEWarps = 4;                    // epilogue warps: 4 TMEM lane quarters x kEWarps / 4 column blocks (8 warps:
+                                              // 72 registers, same 2.48 ms - the shorter epilogue buys nothing)
+constexpr int kEGroups = 8 / (kEWarps / 4);   // 8-candidate column groups per epilogue warp
 constexpr int kI8Threads = (kKWarps + kEWarps + 2) * 32;     // + TMA producer warp + MMA issuer warp
 constexpr int kDigits = 7;
 constexpr int kGroups = 7;                    // g = s + t - 2 in [0, 6]
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
     constexpr int kET = kEWarps * 32;
     auto esync = [&]() { asm volatile("bar.sync 2, %0;\n" ::"n"(kET) : "memory"); };
     const int etid = tid - kKWarps * 32;
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, cbase = ((warp - kKWarps) >> 2) * (kEGroups * 8);   // first candidate column of this warp
     int clamped = 0;
     unsigned jt_n = 0, it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -477,7 +479,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
       VZ_I8T_START(t_a);
       // acc[grp]: this warp's sum over its 32 Linv rows (and over the j tiles) for candidate 8 grp + c(lane),
       // c(lane) = 4 bit4 + 2 bit3 + bit2 - the 32 x 8 -> 8 reduce-scatter below leaves it replicated on 4 lanes
-      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      double acc[kEGroups];
+#pragma unroll
+      for (int grp = 0; grp < kEGroups; ++grp) acc[grp] = 0.0;
       for (int jt = 0; jt < njt; ++jt) {
         VZ_I8T_START(t_b);
         mbar_wait_bounded(tfull, jt_n & 1);
@@ -487,9 +491,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
         tc_fence_after();
         const int j = jt * kJT + quarter * 32 + lane;
         const double sc = j < np ? __ldg(ia.lscale + j) : 0.0;
-        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + cbase;
 #pragma unroll
-        for (int grp = 0; grp < 8; ++grp) {
+        for (int grp = 0; grp < kEGroups; ++grp) {
           double v[8];
 #pragma unroll
           for (int c4 = 0; c4 < 2; ++c4) {
@@ -541,7 +545,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
       if ((lane & 3) == 0) {
         const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
 #pragma unroll
-        for (int grp = 0; grp < 8; ++grp) s_red[quarter * 64 + grp * 8 + c] = acc[grp];
+        for (int grp = 0; grp < kEGroups; ++grp) s_red[quarter * 64 + cbase + grp * 8 + c] = acc[grp];
       }
       mbar_wait_bounded(kready + kb, (it / nbuf) & 1);     // mu / L-inf of this tile (long since complete)
       esync();
