@@ -380,6 +380,20 @@ int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_conf
 int vzgp_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
                   const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
 
+/* Transfer learning: a stack of residual GPs (StackedResidualGP, gp/gp_models.py:91-140, :245-300; VizierGPBandit.
+ * set_priors, gp_bandit.py:289-318).  hs[0] is fitted on the first prior study, every further hs[e] on the residuals
+ * y - (sum of the means of the levels below) of the next study, hs[E-1] on the current study.  Combined prediction
+ * (gp/transfer_learning.py:62-152): mean = sum_e mean_e;  stddev: s = sd_0, then s = sd_e^alphas[e] * s^(1 - alphas[e])
+ * for e = 1 .. E-1 (alphas[0] unused; the caller derives them from the levels' degrees of freedom).  UCB / trust
+ * region as in vzgp_score, the trust region measured against the trials of hs[E-1].  All levels share device, stream
+ * and feature dimensions. */
+int vzgp_score_stack(vzgp_handle* const* hs, int E, const double* alphas, const double* Xs, const int32_t* Zs, int M,
+                     const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf);
+int vzgp_eagle_run_stack(vzgp_handle* const* hs, int E, const double* alphas, const vzgp_eagle_config* cfg,
+                         const vzgp_acq* acq, const double* prior, const int32_t* prior_z, int n_prior,
+                         const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
+                         double* best_score);
+
 /* Set-PE acquisition of GP-UCB-PE batches (SetPEScoreFunction, gp_ucb_pe.py:510-594): Xs holds n_sets sets of q points
  * ([n_sets * q x Dc] device, continuous features, q <= 16).  score[s] = logdet of the q x q joint predictive covariance
  * under model B (completed + pending trials) + penalty * sum_i min(mean_A + explore * stddev_A - threshold, 0)

@@ -639,6 +639,44 @@ def ucb_pe_score(pred_a: Predictive, pred_b: Predictive, xs, zs=None, *, mode: i
   return acq, {'mean': mu, 'stddev': sd, 'stddev_from_all': sd_all}
 
 
+# ----------------------------------------------------------------------------
+# Transfer learning: stacked residual GPs (gp/gp_models.py:91-140, :245-300; gp/transfer_learning.py:38-152)
+# ----------------------------------------------------------------------------
+def transfer_dof(n: int, num_hyperparameters: int) -> float:
+  """_compute_dof (gp/transfer_learning.py:38-59)."""
+  return max(n - num_hyperparameters, n / (1 + num_hyperparameters))
+
+
+def transfer_alpha(n_top: int, n_base: int, num_hyperparameters: int, expected_base_stddev_mismatch: float = 1.0) -> float:
+  """combine_predictions_with_aux (gp/transfer_learning.py:96-118): weight of the top stddev in the geometric mean."""
+  dof_base, dof_top = transfer_dof(n_base, num_hyperparameters), transfer_dof(n_top, num_hyperparameters)
+  beta_squared = (dof_top / dof_base) * (1 + dof_base + expected_base_stddev_mismatch ** 2)
+  return beta_squared / (1 + beta_squared)
+
+
+def predict_stack(preds: Sequence[Predictive], xs, zs=None):
+  """StackedResidualGP.predict_with_aux, recursively (gp/gp_models.py:110-140): preds[0] is the first prior study's GP,
+  preds[e] was trained on the residuals of study e against preds[:e]; the last one belongs to the current study.
+  mean = sum of the means; stddev = stddev_e^alpha_e * (stddev of the stack below)^(1 - alpha_e), bottom-up, with
+  alpha_e from the training-set sizes of levels e and e-1 and D + 2 hyper-parameters (gp/gp_models.py:77-88)."""
+  mean, sd = predict(preds[0], xs, zs)
+  for e in range(1, len(preds)):
+    p = preds[e]
+    h = p.x.shape[1] + (0 if p.z is None else p.z.shape[1]) + 2
+    alpha = transfer_alpha(int(np.sum(p.row_valid)), int(np.sum(preds[e - 1].row_valid)), h)
+    mu_e, sd_e = predict(p, xs, zs)
+    mean = mean + mu_e
+    sd = sd_e ** alpha * sd ** (1.0 - alpha)
+  return mean, sd
+
+
+def stack_residual_labels(preds: Sequence[Predictive], x, y, z=None) -> np.ndarray:
+  """Labels of the next level: y minus the mean of the stack built so far (gp/gp_models.py:268-283)."""
+  if not preds:
+    return np.asarray(y, np.float64)
+  return np.asarray(y, np.float64) - predict_stack(preds, x, z)[0]
+
+
 def predictive_covariance(pred: Predictive, xs) -> np.ndarray:
   """Joint posterior predictive covariance at xs [m, D]: K** - V^T V + sn2 I (the GPRM of
   stochastic_process_model.py:800-868 with predictive noise = observation noise [T])."""

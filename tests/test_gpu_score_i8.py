@@ -133,3 +133,36 @@ def test_i8_refit_invalidates_digit_planes(dev):
     _, aux = go.score_with_aux(pred, xs.cpu().numpy()[:500])
     np.testing.assert_allclose(out['stddev'].cpu().numpy()[:500], aux['stddev'], atol=TOL, rtol=0)
     np.testing.assert_allclose(small['stddev'].cpu().numpy()[:500], aux['stddev'], atol=TOL, rtol=0)
+
+
+def test_i8_two_handles_on_two_streams_concurrently():
+  """Two models scoring large pools at the same time from two host threads (separate handles and streams): the
+  kernels take turns on the SMs (one CTA per SM: shared memory and the 512 TMEM columns); results equal the serial ones."""
+  import threading
+  gp = _gp()
+  devs, pools, want = [], [], []
+  for k in range(2):
+    n, d = 400 + 300 * k, 6 + 4 * k
+    x, y, _ = _problem(n, d, 40 + k)
+    _, pg = _params(d, sf2=1.0 + k)
+    dv = gp.DeviceGP(0)
+    dv.set_int('score_i8', 1)
+    dv.fit(x, y, pg)
+    xs = dv.random_pool(148 * 64 * 3, d, seed=k)
+    ref = dv.score(xs, gp.Acquisition(1.8, False, 0.0), with_aux=True)
+    dv.synchronize()
+    devs.append(dv); pools.append(xs); want.append(ref['stddev'].clone())
+  got = [None, None]
+
+  def run(k):
+    for _ in range(5):
+      out = devs[k].score(pools[k], gp.Acquisition(1.8, False, 0.0), with_aux=True)
+    devs[k].synchronize()
+    got[k] = out['stddev']
+
+  ts = [threading.Thread(target=run, args=(k,)) for k in range(2)]
+  [t.start() for t in ts]; [t.join() for t in ts]
+  for k in range(2):
+    assert devs[k].get_int('score_i8_launches') >= 6
+    np.testing.assert_array_equal(got[k].cpu().numpy(), want[k].cpu().numpy())
+    devs[k].close()

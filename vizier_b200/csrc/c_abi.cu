@@ -944,11 +944,12 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
                           const vzgp_pe_params* pe, const double* prior, const int32_t* prior_z, int n_prior,
                           const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
                           double* best_score, vzgp_handle* const* ens = nullptr, int n_ens = 0,
-                          const vzgp_scalarization* scal = nullptr) {
+                          const vzgp_scalarization* scal = nullptr, const double* stack_alphas = nullptr) {
   VZ_ARG(h && cfg && (acq || pe || scal) && best_score, "handle / pointers");
   auto score_batch = [&](const double* xs, const int32_t* zs, int m, double* out) -> int {
     if (scal) return launch_score_multi(h, xs, zs, m, out, nullptr, nullptr);
     if (pe) return launch_score_pe(h, hB, xs, zs, m, pe, out, nullptr, nullptr, nullptr);
+    if (stack_alphas) return launch_score_stack(ens, n_ens, stack_alphas, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
     if (n_ens > 1) return launch_score_ensemble(ens, n_ens, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
     return launch_score(h, xs, zs, m, acq, out, nullptr, nullptr, nullptr);
   };
@@ -985,11 +986,11 @@ static int eagle_run_impl(vzgp_handle* h, vzgp_handle* hB, const vzgp_eagle_conf
   // CUDA graph of the suggest -> score -> update sequence: the iteration counter and all state
   // live in device memory, so the launches are identical and the host only enqueues graphs.
   bool done = false;
-  if (n_ens <= 1 && !scal && eagle_persistent_eligible(h, pe ? hB : nullptr, e)) {
+  if (n_ens <= 1 && !scal && !stack_alphas && eagle_persistent_eligible(h, pe ? hB : nullptr, e)) {
     // small study: the whole loop is one persistent single-CTA kernel
     VZ_TRY(launch_eagle_persistent64(h, pe ? hB : nullptr, e, acq, pe, steps));
     done = true;
-  } else if (n_ens <= 1 && !scal && eagle_grid_eligible(h, pe ? hB : nullptr, e)) {
+  } else if (n_ens <= 1 && !scal && !stack_alphas && eagle_grid_eligible(h, pe ? hB : nullptr, e)) {
     // mid-size study: one cooperative launch, phases separated by grid barriers.  If the cooperative
     // launch is refused (nothing has run then) the launch-per-phase loop below takes over.
     done = launch_eagle_grid(h, pe ? hB : nullptr, e, acq, pe, steps) == 0;
@@ -1238,6 +1239,39 @@ int vzgp_eagle_run_ensemble(vzgp_handle* const* hs, int E, const vzgp_eagle_conf
   VZ_ARG(acq != nullptr, "acq");
   return eagle_run_impl(hs[0], nullptr, cfg, acq, nullptr, prior, prior_z, n_prior, cat_sizes, count, seed, best_x,
                         best_z, best_score, hs, E);
+}
+
+static int check_stack(vzgp_handle* const* hs, int E, const double* alphas) {
+  VZ_ARG(hs != nullptr && alphas != nullptr && E >= 1 && E <= 16, "1 <= E <= 16 handles, alphas");
+  for (int e = 0; e < E; ++e) {
+    VZ_ARG(hs[e] != nullptr, "handle");
+    if (!hs[e]->fitted) { set_error("stacked scoring needs every level fitted"); return VZGP_ERR_STATE; }
+    VZ_ARG(hs[e]->device == hs[0]->device && hs[e]->stream == hs[0]->stream, "levels must share device and stream");
+    VZ_ARG(hs[e]->dc == hs[0]->dc && hs[e]->dk == hs[0]->dk, "levels must have the same feature dimensions");
+    VZ_ARG(e == 0 || (alphas[e] >= 0.0 && alphas[e] <= 1.0), "0 <= alpha <= 1");
+  }
+  return 0;
+}
+
+int vzgp_score_stack(vzgp_handle* const* hs, int E, const double* alphas, const double* Xs, const int32_t* Zs, int M,
+                     const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf) {
+  VZ_TRY(check_stack(hs, E, alphas));
+  VZ_ARG(acq != nullptr, "acq");
+  VZ_ARG(M >= 0 && (M == 0 || score != nullptr), "M / score");
+  VZ_ARG(M == 0 || Xs != nullptr || hs[0]->dc == 0, "Xs");
+  VZ_ARG(M == 0 || Zs != nullptr || hs[0]->dk == 0, "Zs");
+  Guard g(hs[0]->device);
+  return launch_score_stack(hs, E, alphas, Xs, Zs, M, acq, score, mu, sigma, linf);
+}
+
+int vzgp_eagle_run_stack(vzgp_handle* const* hs, int E, const double* alphas, const vzgp_eagle_config* cfg,
+                         const vzgp_acq* acq, const double* prior, const int32_t* prior_z, int n_prior,
+                         const int32_t* cat_sizes, int count, uint64_t seed, double* best_x, int32_t* best_z,
+                         double* best_score) {
+  VZ_TRY(check_stack(hs, E, alphas));
+  VZ_ARG(acq != nullptr, "acq");
+  return eagle_run_impl(hs[E - 1], nullptr, cfg, acq, nullptr, prior, prior_z, n_prior, cat_sizes, count, seed, best_x,
+                        best_z, best_score, hs, E, nullptr, alphas);
 }
 
 int vzgp_nll_grad_batch(vzgp_handle* const* hs, int R, const double* X, const int32_t* Z, const double* Y, int N,

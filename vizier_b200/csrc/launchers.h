@@ -84,6 +84,8 @@ int make_tensor_map_u8(void* map, const void* base, int rank, const uint64_t* di
                        const uint32_t* box);
 int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const int32_t* Zs, int M,
                     const vzgp_pe_params* pe, double* score, double* mu, double* sigma, double* sigma_all);
+int launch_score_stack(vzgp_handle* const* hs, int E, const double* alphas, const double* Xs, const int32_t* Zs, int M,
+                       const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf);
 int launch_set_pe_combine(vzgp_handle* h, int n_sets, int q, const vzgp_pe_params* pe, const double* cov, int ldc,
                           const double* mu_a, const double* sd_a, const double* linf, double* score, double* sd_all);
 int prepare_scalarization(vzgp_handle* h, const vzgp_scalarization* sc);

@@ -761,6 +761,70 @@ int launch_score_pe(vzgp_handle* hA, vzgp_handle* hB, const double* Xs, const in
 }
 
 // ---------------------------------------------------------------------------
+// Stacked residual GPs of transfer learning (StackedResidualGP, gp/gp_models.py:91-140; combine_predictions_with_aux,
+// gp/transfer_learning.py:62-152): level 0 is the first prior study's GP, every further level is trained on the
+// residuals of the stack below it, the last level on the current study.  mean = sum of the level means; the stddevs
+// are combined bottom-up by weighted geometric means  s <- sd_e^alpha_e * s^(1 - alpha_e)  (alpha_e from the degrees
+// of freedom of the two levels, computed by the caller).  UCB and the trust region (distances to the TOP level's
+// trials) on the combined prediction.
+// ---------------------------------------------------------------------------
+struct StackCombine {
+  int E;
+  double alpha[16];
+  double coef;
+  int apply_tr, tr_strict;
+  double radius;
+};
+__global__ void k_stack_combine(int M, StackCombine p, const double* __restrict__ mu_e, const double* __restrict__ sd_e,
+                                const double* __restrict__ linf, double* __restrict__ score, double* __restrict__ mu,
+                                double* __restrict__ sigma) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double mean = mu_e[m], sd = sd_e[m];
+  for (int e = 1; e < p.E; ++e) {
+    mean += mu_e[(size_t)e * M + m];
+    sd = pow(sd_e[(size_t)e * M + m], p.alpha[e]) * pow(sd, 1.0 - p.alpha[e]);
+  }
+  double sc = fma(p.coef, sd, mean);
+  if (p.apply_tr) {
+    const double dist = linf[m];
+    const bool inside = (p.tr_strict ? (dist < p.radius) : (dist <= p.radius)) || (p.radius > 0.5);
+    sc = inside ? sc : (-1e4 - dist);
+  }
+  score[m] = sc;
+  if (mu) mu[m] = mean;
+  if (sigma) sigma[m] = sd;
+}
+
+int launch_score_stack(vzgp_handle* const* hs, int E, const double* alphas, const double* Xs, const int32_t* Zs, int M,
+                       const vzgp_acq* acq, double* score, double* mu, double* sigma, double* linf) {
+  if (M <= 0) return 0;
+  vzgp_handle* top = hs[E - 1];
+  VZ_TRY(top->pe_tmp.reserve(sizeof(double) * (2 * (size_t)E + 2) * (size_t)M));
+  double* t = top->pe_tmp.as<double>();
+  double* mu_e = t;
+  double* sd_e = t + (size_t)E * M;
+  double* linf_buf = linf ? linf : t + 2 * (size_t)E * M;
+  double* dummy = t + (2 * (size_t)E + 1) * M;
+  const bool want_tr = acq->use_trust_region && acq->trust_radius <= 0.5;
+  const bool want_linf = want_tr || linf != nullptr;
+  vzgp_acq none;
+  none.ucb_coefficient = 0.0; none.use_trust_region = 0; none.trust_radius = 1.0;
+  none.tr_dim_mask = acq->tr_dim_mask; none.tr_rows = acq->tr_rows; none.tr_strict = 0;
+  for (int e = 0; e < E; ++e)   // the trust region is measured against the trials of the top level (the current study)
+    VZ_TRY(launch_score(hs[e], Xs, Zs, M, &none, dummy, mu_e + (size_t)e * M, sd_e + (size_t)e * M,
+                        (e == E - 1 && want_linf) ? linf_buf : nullptr));
+  StackCombine p;
+  p.E = E; p.coef = acq->ucb_coefficient; p.apply_tr = want_tr ? 1 : 0; p.tr_strict = acq->tr_strict ? 1 : 0;
+  p.radius = acq->trust_radius;
+  for (int e = 0; e < 16; ++e) p.alpha[e] = e < E ? alphas[e] : 0.0;
+  k_stack_combine<<<(M + 255) / 256, 256, 0, top->stream>>>(M, p, mu_e, sd_e, linf_buf, score, mu, sigma);
+  VZ_CHECK_LAUNCH();
+  top->launches++;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Set-PE acquisition (SetPEScoreFunction, gp_ucb_pe.py:510-594): per set of q points
 //   logdet(joint predictive covariance under model B)  +  penalty * sum_i min(mean_A + explore * stddev_A - threshold, 0)
 //   [+ sum_i (dist_i > radius and radius <= 0.5) * (-1e4 - dist_i)      _apply_trust_region_to_set, :245-269]

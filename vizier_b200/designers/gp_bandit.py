@@ -16,9 +16,11 @@ multi-task GP (one factor, one alpha per metric) scored by the mean over `num_sc
 hyper-volume scalarisations, without a trust region.
 `linear_coef` adds the feature-scaled linear kernel and the constant mean of tuned_gp_models.py:203-245
 (general launch sequences: no captured graph, explicit K* for the scoring).
-Not implemented (the reference supports them; SURVEY 8f "next"): transfer-learning
-priors (`set_priors`), parallel (q-) acquisitions, non-independent multi-task kernels; each raises
-NotImplementedError instead of silently doing something else.  Categorical parameters ARE supported
+`set_priors` trains a stack of residual GPs, one level per prior study plus the current study on top (gp_bandit.py:289-318;
+gp/gp_models.py:91-140, :245-300; gp/transfer_learning.py), scored through `vzgp_score_stack` (`gp.StackedGP`).
+Not implemented (the reference supports them; SURVEY 8f "next"): parallel (q-) acquisitions / custom scoring functions,
+non-independent multi-task kernels, priors for multi-metric or ensemble models; each raises NotImplementedError
+instead of silently doing something else.  Categorical parameters ARE supported
 end to end.  `padding_schedule` is accepted and has no numerical effect here: the kernels take
 explicit sizes (`n_valid`, Dc, Dk) instead of padded shapes + masks, which is what the reference's
 padding-invariance tests (gp_bandit_test.py:302-370) assert of its own masked implementation.
@@ -138,6 +140,8 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     self._device_index = device
     self._dev = None                       # gp.DeviceGP, or gp.EnsembleGP when ensemble_size > 1
     self._ard_dev: Optional[gp.DeviceGP] = None
+    self._stack: Optional[gp.StackedGP] = None   # transfer learning: prior levels (+ the current study's level on top)
+    self._n_prior_levels = 0
     self._last_params = None               # GPHyperParams (or a list of them for an ensemble)
 
   # ------------------------------------------------------------------ API
@@ -147,7 +151,39 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     self._trials.extend(copy.deepcopy(list(completed.trials)))
 
   def set_priors(self, prior_studies) -> None:
-    raise NotImplementedError('transfer-learning priors are not implemented (reference tests skip them too).')
+    """gp_bandit.py:289-318: one prior GP per study, stacked in the order received - the first on its study's (warped)
+    labels, each further one on the residuals of its study against the stack below (gp/gp_models.py:245-300).  The
+    current study's GP is later trained on ITS residuals against the whole prior stack (`_update_gp`).  Each call
+    retrains the prior stack from scratch on what it is given."""
+    if self._n_metrics != 1 or self._ensemble_size != 1 or self._linear_coef:
+      raise NotImplementedError('transfer-learning priors: single-metric, single-model Matern GPs only.')
+    if self._stack is not None:
+      self._stack.close()
+    self._stack = gp.StackedGP(self._device_index)
+    for study in prior_studies:
+      trials = list(study.trials)
+      if not trials:
+        continue
+      (cont, cat), labels = self._converter.to_xy(trials)
+      labels = self._warp_labels(labels)
+      self._push_level(cont, cat, labels[:, 0])
+    self._n_prior_levels = len(self._stack.levels)
+    if self._n_prior_levels == 0:
+      self._stack = None
+    self._last_params = None               # the top level must be retrained against the new priors
+    self._incorporated_trials_count = -1
+
+  def _push_level(self, cont, cat, y):
+    """Trains one more level of the stack on the residuals of (cont, cat, y) against the levels below."""
+    z = cat if cat.shape[1] else None
+    resid = y - self._stack.mean(cont, z)
+    level = self._stack.new_level()
+    ard_rng = np.random.default_rng(int(self._rng.integers(2**62)))
+    best, _ = ard.train_gp(level, cont, resid, z, rng=ard_rng, random_restarts=self._ard_random_restarts,
+                           ensemble_size=1, optimizer=self._ard_optimizer)
+    level.fit(cont, resid, best[0], z=z)
+    self._stack.push(level, cont.shape[0])
+    return best[0]
 
   @classmethod
   def from_problem(cls, problem, seed: Optional[int] = None, **kwargs) -> 'VizierGPBandit':
@@ -193,6 +229,14 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
   @profiler.record_runtime
   def _update_gp(self, cont, cat, labels) -> gp.DeviceGP:
     """gp_bandit.py:449-479: ARD + precompute, skipped when no new trial arrived."""
+    if self._stack is not None:
+      # transfer learning (gp_bandit.py:470-476): the current study's GP on the residuals against the prior stack
+      if len(self._trials) == self._incorporated_trials_count and self._last_params is not None:
+        return self._stack
+      self._incorporated_trials_count = len(self._trials)
+      self._stack.truncate(self._n_prior_levels)
+      self._last_params = self._push_level(cont, cat, labels[:, 0])
+      return self._stack
     dev = self._device()
     if len(self._trials) == self._incorporated_trials_count and self._last_params is not None:
       return dev
@@ -279,6 +323,13 @@ class VizierGPBandit(vz.Designer, vz.Predictor):
     zq = zs if zs.shape[1] else None
     if self._n_metrics > 1:
       return self._sample_multi(dev, xs, zq, g, num_samples)
+    if self._stack is not None:
+      # the combined prediction is a diagonal normal (gp/transfer_learning.py:150-152)
+      out = dev.score(xs, gp.Acquisition(0.0, False, 1.0), zs=zq, with_aux=True)
+      dev.synchronize()
+      mean, sd = out['mean'].cpu().numpy(), out['stddev'].cpu().numpy()
+      samples = mean[None, :] + g.standard_normal((num_samples, mean.shape[0])) * sd[None, :]
+      return self._output_warper.unwarp(samples.reshape(-1, 1)).reshape(samples.shape)
     comps = dev.posterior(xs, zq, add_noise=True) if self._ensemble_size > 1 else [dev.posterior(xs, zq, add_noise=True)]
     # Cholesky of each (small) posterior covariance on the device as well; the retry adds a tiny
     # jitter only if round-off made it indefinite.

@@ -714,6 +714,138 @@ class DeviceGP:
     del keep
     return bx, bz, bs
 
+def transfer_dof(n: int, num_hyperparameters: int) -> float:
+  """gp/transfer_learning.py:38-59 (_compute_dof)."""
+  return max(n - num_hyperparameters, n / (1.0 + num_hyperparameters))
+
+
+def transfer_alpha(n_top: int, n_base: int, num_hyperparameters: int, expected_base_stddev_mismatch: float = 1.0) -> float:
+  """Weight of the top level's stddev in the geometric mean (gp/transfer_learning.py:96-118)."""
+  dof_base, dof_top = transfer_dof(n_base, num_hyperparameters), transfer_dof(n_top, num_hyperparameters)
+  beta2 = (dof_top / dof_base) * (1.0 + dof_base + expected_base_stddev_mismatch ** 2)
+  return beta2 / (1.0 + beta2)
+
+
+class StackedGP:
+  """Stack of residual GPs for transfer learning (`VizierGPBandit.set_priors`, gp_bandit.py:289-318; StackedResidualGP,
+  gp/gp_models.py:91-140, :245-300): level 0 is fitted on the first prior study, each further level on the residuals
+  of the next study against the stack below it, the last level on the current study.  The levels are libvzgp handles
+  on ONE stream; scoring and the Eagle loop run through `vzgp_score_stack` / `vzgp_eagle_run_stack`.  Exposes the
+  subset of the `DeviceGP` interface the acquisition optimiser drives."""
+
+  def __init__(self, device: int):
+    self._device_index = device
+    self.levels: list = []          # DeviceGP per level, base first
+    self.counts: list = []          # training points per level
+    self.alphas: list = []          # alphas[e]: weight of level e's stddev against the stack below (alphas[0] unused)
+    self.device = None
+    self.dc = self.dk = self.n = 0
+
+  @property
+  def top(self) -> 'DeviceGP':
+    return self.levels[-1]
+
+  @property
+  def stream(self):
+    return self.levels[0].stream
+
+  @property
+  def launch_count(self) -> int:
+    return sum(m.launch_count for m in self.levels)
+
+  def synchronize(self):
+    self.levels[0].synchronize()
+
+  def close(self):
+    for m in self.levels:
+      m.close()
+    self.levels = []
+
+  def truncate(self, n_levels: int) -> None:
+    """Keeps the first n_levels levels (the prior stack) and drops the rest (a new top level follows)."""
+    for m in self.levels[n_levels:]:
+      m.close()
+    del self.levels[n_levels:], self.counts[n_levels:], self.alphas[n_levels:]
+
+  def new_level(self) -> 'DeviceGP':
+    m = DeviceGP(self._device_index) if not self.levels else DeviceGP(self._device_index, stream=self.levels[0].stream)
+    return m
+
+  def mean(self, xs, zs=None) -> np.ndarray:
+    """Mean of the stack built so far at xs (0 for an empty stack): the quantity the next level's labels are reduced by
+    (`_pred_mean`, gp/gp_models.py:268-283)."""
+    n = len(xs)
+    if not self.levels:
+      return np.zeros(n)
+    out = self.score(xs, Acquisition(0.0, False, 1.0), zs=zs, with_aux=True)
+    self.synchronize()
+    return out['mean'].cpu().numpy()
+
+  def push(self, level: 'DeviceGP', n_points: int) -> None:
+    """Adds a fitted level on top of the stack."""
+    h = level.dc + level.dk + 2           # GPState.num_hyperparameters (gp/gp_models.py:77-88)
+    self.alphas.append(0.0 if not self.levels else transfer_alpha(n_points, self.counts[-1], h))
+    self.levels.append(level)
+    self.counts.append(int(n_points))
+    self.device, self.dc, self.dk, self.n = level.device, level.dc, level.dk, level.n
+
+  def _handles(self):
+    return (C.c_void_p * len(self.levels))(*[m._h for m in self.levels])
+
+  def _alphas(self):
+    return (C.c_double * len(self.levels))(*self.alphas)
+
+  def score(self, xs, acq: Acquisition, zs=None, with_aux: bool = False) -> dict:
+    f = self.levels[-1]
+    xst, zst = f._xz(xs, zs)
+    m = xst.shape[0]
+    res = {'score': torch.empty((m,), dtype=torch.float64, device=f.device)}
+    if with_aux:
+      for k in ('mean', 'stddev', 'linf_distance'):
+        res[k] = torch.empty((m,), dtype=torch.float64, device=f.device)
+    f._stream.wait_stream(torch.cuda.current_stream(f.device))
+    a, keep = acq._c()
+    _lib.check('vzgp_score_stack', f._lib.vzgp_score_stack(
+        self._handles(), len(self.levels), self._alphas(), _ptr(xst), _ptr(zst), m, C.byref(a), _ptr(res['score']),
+        _ptr(res.get('mean')), _ptr(res.get('stddev')), _ptr(res.get('linf_distance'))))
+    res['_inputs'] = (xst, zst, keep)
+    return res
+
+  def eagle_run(self, cfg, acq: Acquisition, count: int, seed: int, prior=None, prior_z=None, cat_sizes=None, other=None):
+    assert other is None
+    f = self.levels[-1]
+    a, keep = acq._c()
+    n_prior = 0 if prior is None else len(prior)
+    pt = f._dev(prior, torch.float64) if n_prior > 0 and self.dc > 0 else None
+    pz = f._dev(prior_z, torch.int32) if n_prior > 0 and self.dk > 0 else None
+    bx = np.zeros((count, self.dc), np.float64)
+    bz = np.zeros((count, self.dk), np.int32)
+    bs = np.zeros(count, np.float64)
+    sizes = np.ascontiguousarray(np.asarray(cat_sizes if cat_sizes is not None else [], np.int32))
+    _lib.check('vzgp_eagle_run_stack', f._lib.vzgp_eagle_run_stack(
+        self._handles(), len(self.levels), self._alphas(), C.byref(cfg), C.byref(a), _ptr(pt), _ptr(pz), n_prior,
+        sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes.size else None, count, seed,
+        bx.ctypes.data_as(C.POINTER(C.c_double)), bz.ctypes.data_as(C.POINTER(C.c_int32)),
+        bs.ctypes.data_as(C.POINTER(C.c_double))))
+    del keep
+    return bx, bz, bs
+
+  def random_search(self, m: int, acq: Acquisition, count: int, seed: int, index_base: int = 0, cat_sizes=None):
+    """RandomVectorizedStrategy over the stack: Philox pool -> combined score -> device top-k."""
+    f = self.levels[-1]
+    xs = f.random_pool(m, self.dc, seed, index_base) if self.dc else torch.zeros((m, 0), dtype=torch.float64, device=f.device)
+    zs = f.random_pool_cat(m, cat_sizes, seed, index_base) if self.dk else None
+    out = self.score(xs, acq, zs=zs)
+    idx, val = f.topk(out['score'], count)
+    it = torch.from_numpy(np.maximum(idx, 0)).to(f.device)
+    bx = xs[it].cpu().numpy()
+    bz = zs[it].cpu().numpy() if zs is not None else np.zeros((count, 0), np.int32)
+    return bx, bz, val, idx + index_base
+
+  def topk(self, score, count: int):
+    return self.levels[-1].topk(score, count)
+
+
 class _DevView:
   """A raw device pointer as a `__cuda_array_interface__` object (zero-copy torch view of library-owned memory)."""
 
