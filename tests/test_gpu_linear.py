@@ -13,6 +13,11 @@ from oracle import gp_oracle as go  # noqa: E402
 COEF = 0.7
 
 
+def _gp():
+  from vizier_b200 import gp
+  return gp
+
+
 def _setup(n, d, dk=0, seed=0):
   rng = np.random.default_rng(seed)
   x = rng.uniform(size=(n, d))
@@ -147,3 +152,56 @@ def test_linear_designer_runs_and_predicts():
   pred = d.predict(trials[:6], rng=1, num_samples=300)
   truth = np.array([t.final_measurement.metrics['obj'].value for t in trials[:6]])
   assert np.max(np.abs(pred.mean - truth)) < 0.15
+
+
+def test_ucb_pe_with_linear_kernel():
+  """GP-UCB-PE `mixes_linear_kernel=True` (gp_ucb_pe.py:805-809, :844-853): the PE / UCB acquisition over two models
+  with the Matern + linear kernel and constant mean against the oracle, and the designer end to end."""
+  from vizier_b200 import vz
+  from vizier_b200.designers import gp_ucb_pe
+  from vizier_b200 import optimizers as vb
+  gp = _gp()
+  rng = np.random.default_rng(4)
+  n, n_pend, d, m = 60, 5, 4, 300
+  x = rng.uniform(size=(n + n_pend, d))
+  y = 2.0 * x[:n, 0] - np.sum((x[:n] - 0.4) ** 2, axis=1) + 0.02 * rng.normal(size=n)
+  ls2 = 0.4 * (1 + np.arange(d) / d)
+  lin = go.LinearParams(1.0, 0.7, 0.2, 0.3)
+  po = go.GPParams(0.9, ls2, 2e-3, None, lin)
+  pg = gp.GPHyperParams(0.9, ls2, 2e-3, None, linear_coef=1.0, linear_slope_amplitude=0.7, linear_shift=0.2, mean_constant=0.3)
+  pred_a = go.precompute_predictive(po, x[:n], y)
+  y_all = np.r_[y, np.zeros(n_pend)]
+  pred_b = go.precompute_predictive(po, x, y_all)
+  dev_a = gp.DeviceGP(0)
+  dev_b = gp.DeviceGP(0, stream=dev_a.stream)
+  dev_a.fit(x[:n], y, pg)
+  dev_b.fit(x, y_all, pg)
+  xs = rng.uniform(size=(m, d))
+  for mode in (0, 1):
+    pe = gp.UcbPeAcquisition(mode=mode, threshold=0.1, use_trust_region=True, trust_radius=0.3, tr_rows=n + 2)
+    out = dev_a.score_pe(dev_b, xs, pe)
+    want, aux = go.ucb_pe_score(pred_a, pred_b, xs, mode=mode, threshold=0.1, tr_rows=n + 2, trust_radius_value=0.3)
+    np.testing.assert_allclose(out['score'].cpu().numpy(), want, atol=1e-9)
+    np.testing.assert_allclose(out['stddev_from_all'].cpu().numpy(), aux['stddev_from_all'], atol=1e-9)
+  dev_a.close(); dev_b.close()
+
+  p = vz.ProblemStatement()
+  for i in range(3):
+    p.search_space.root.add_float_param(f'x{i}', 0.0, 1.0)
+  p.metric_information.append(vz.MetricInformation(name='obj', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  trials = []
+  for i in range(25):
+    xv = rng.uniform(size=3)
+    t = vz.Trial(parameters={f'x{j}': float(xv[j]) for j in range(3)}, id=i + 1)
+    t.complete(vz.Measurement({'obj': float(3.0 * xv[0] + xv[1] - 0.5 * xv[2])}))
+    trials.append(t)
+  fac = vb.VectorizedOptimizerFactory(strategy_factory=vb.VectorizedEagleStrategyFactory(eagle_config=gp_ucb_pe.default_eagle_config),
+                                      max_evaluations=2500, suggestion_batch_size=25)
+  des = gp_ucb_pe.VizierGPUCBPEBandit(p, acquisition_optimizer_factory=fac, mixes_linear_kernel=True, rng=3)
+  des.update(vz.CompletedTrials(trials), vz.ActiveTrials())
+  sugg = des.suggest(2)
+  assert len(sugg) == 2
+  params_txt = sugg[0].metadata.ns('google_gp_ucb_pe_bandit').ns('prediction_in_warped_y_space')['params']
+  assert 'linear_coef=1.0' in params_txt
+  pred = des.predict(trials[:5])
+  assert np.all(np.isfinite(pred.mean)) and np.all(pred.stddev > 0)

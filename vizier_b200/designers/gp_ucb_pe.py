@@ -19,7 +19,8 @@ Everything numeric runs in libvzgp (two handles on one stream, `vzgp_score_pe`,
 like `VizierGPBandit`.  `prior_acquisition` (a callable on NumPy features) is added to both acquisitions through the
 host-stepped Eagle loop (`gp.SteppedEagle`); `optimize_set_acquisition_for_exploration=True` optimises the rest of a
 batch as ONE set for the set-PE acquisition (`vzgp_score_set_pe`, the optimiser's n_parallel form; continuous search
-spaces with count * Dc <= 64).  Not implemented: multi-metric, linear-kernel mixing, ensembles - each raises
+spaces with count * Dc <= 64); `mixes_linear_kernel=True` uses the Matern + linear kernel with a constant mean
+(`linear_coef = 1`, libvzgp's general scoring path).  Not implemented: multi-metric, ensembles - each raises
 NotImplementedError.
 """
 
@@ -116,8 +117,11 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
       raise ValueError(f'{type(self)} does not support conditional search.')
     if len(problem.metric_information) != 1:
       raise NotImplementedError('vizier_b200.VizierGPUCBPEBandit implements the single-metric path only.')
-    if mixes_linear_kernel or (ensemble_size or 1) != 1:
-      raise NotImplementedError('linear kernel / ensembles are not implemented for GP-UCB-PE.')
+    if (ensemble_size or 1) != 1:
+      raise NotImplementedError('ensembles are not implemented for GP-UCB-PE.')
+    # mixes_linear_kernel: the Matern + feature-scaled linear kernel with a constant mean, linear_coef = 1
+    # (gp_ucb_pe.py:805-809, :844-853; tuned_gp_models.py:203-245)
+    self._linear_coef = 1.0 if mixes_linear_kernel else None
     del clear_jax_cache, padding_schedule
     # prior_acquisition(continuous [m, Dc], categorical [m, Dk]) -> [m]: added to the UCB / PE acquisition
     # (gp_ucb_pe.py:286-381, :487-490); NumPy arrays instead of the reference's JAX ModelInput.
@@ -187,30 +191,34 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     """gp_ucb_pe.py:789-894: one fixed + `ard_random_restarts` random initialisations."""
     dc, dk = cont.shape[1], cat.shape[1]
     rng = np.random.default_rng(int(self._rng.integers(2**62)))
-    random_inits = ard.log_uniform_init(rng, dc, dk, self._ard_random_restarts)
-    fixed = gp.GPHyperParams(0.039, np.ones(dc), 0.0039, np.ones(dk)).to_vector()[None, :]
+    lin = self._linear_coef
+    random_inits = ard.log_uniform_init(rng, dc, dk, self._ard_random_restarts, linear=bool(lin))
+    fixed = gp.GPHyperParams(0.039, np.ones(dc), 0.0039, np.ones(dk), linear_coef=lin, linear_slope_amplitude=0.0,
+                             linear_shift=0.0, mean_constant=0.0).to_vector()[None, :]    # :833-853
     inits = np.concatenate([fixed, random_inits], axis=0)
     if cont.shape[0] == 0:
       # no completed trial yet: the dummy loss makes the optimiser return its first initial point
-      return gp.GPHyperParams.from_vector(inits[0], dc, dk)
+      return gp.GPHyperParams.from_vector(inits[0], dc, dk, lin)
     dev_a, _ = self._devices()
     import torch  # device-memory handles only
     xt = torch.from_numpy(np.ascontiguousarray(cont)).to(dev_a.device)
     yt = torch.from_numpy(np.ascontiguousarray(labels[:, 0])).to(dev_a.device)
     zt = torch.from_numpy(np.ascontiguousarray(cat)).to(dev_a.device) if dk else None
-    lo, hi = gp.param_bounds(dc, dk)
+    lo, hi = gp.param_bounds(dc, dk, bool(lin))
+    if lin:
+      inits = np.clip(inits, lo, hi)     # the fixed slope 0 sits below its lower bound: L-BFGS-B starts from the projection
 
     # all initial points advance in lock step, one CUDA-graph launch per round (ard.batch_loss_function); small
     # studies (one fused kernel per evaluation) keep one host thread per point
-    if ard.BATCHED_ARD and ard._setulb is not None and xt.shape[0] > 64 and inits.shape[0] <= 16:   # pylint: disable=protected-access
+    if not lin and ard.BATCHED_ARD and ard._setulb is not None and xt.shape[0] > 64 and inits.shape[0] <= 16:   # pylint: disable=protected-access
       fns = ard.batch_loss_function(dev_a, xt, yt, zt, inits.shape[0])
     else:
-      fns = ard.loss_functions(dev_a, xt, yt, zt, dc, dk, workers=min(ard.MAX_ARD_WORKERS, inits.shape[0]))
+      fns = ard.loss_functions(dev_a, xt, yt, zt, dc, dk, workers=min(ard.MAX_ARD_WORKERS, inits.shape[0]), linear_coef=lin)
     try:
       best, _ = self._ard_optimizer(inits, fns, list(zip(lo, hi)), best_n=1)
     finally:
       dev_a.set_int('dataflow_ctas', 0)
-    return gp.GPHyperParams.from_vector(best[0], dc, dk)
+    return gp.GPHyperParams.from_vector(best[0], dc, dk, lin)
 
   def _fit_all_features(self, params: gp.GPHyperParams, cont, cat, labels, pend_c, pend_z, noise_is_high: bool):
     """_get_predictive_all_features (:944-1004): model B on completed + pending, dummy labels."""
@@ -220,8 +228,7 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     y = np.concatenate([labels[:, 0], np.zeros(pend_c.shape[0])])
     p = params
     if noise_is_high:
-      p = gp.GPHyperParams(params.signal_variance, params.continuous_length_scale_squared, 1e-10,
-                           params.categorical_length_scale_squared)
+      p = dataclasses.replace(params, observation_noise_variance=1e-10)
     dev_b.fit(xc, y, p, z=xz if xz.shape[1] else None)
     return xc, xz
 
