@@ -60,7 +60,7 @@ constexpr int kGroups = 7;                    // g = s + t - 2 in [0, 6]
 constexpr int kJT = 128;                      // Linv rows per j tile = MMA M
 constexpr int kKC = 128;                      // bytes (= k values) per chunk: one 128-byte swizzle atom per row
 constexpr int kASlotBytes = kJT * kKC;        // 16 KB: one digit plane of a j tile x k chunk
-constexpr int kASlots = 4;
+constexpr int kASlots = 4;                   // most; large Dc trades slots for the phase-1 staging (I8Args::n_aslots)
 constexpr int kBPlaneBytes = kTM * kKC;       // 8 KB
 constexpr int kBBufBytes = kDigits * kBPlaneBytes;   // 56 KB: all digit planes of the candidates' k chunk
 constexpr int kRingBytes = 2 * kBBufBytes + kASlots * kASlotBytes;   // 176 KB
@@ -73,6 +73,8 @@ struct I8Args {
   uint8_t* kdig;                  // [grid][nbuf][7][64][np]
   int nbuf;                       // 2: phase 1 of the next tile overlaps phase 2; 1: back to back (large Dc)
   int misc_bytes;                 // shared memory between the operand ring and the (nbuf = 2) phase-1 staging
+  int n_aslots;                   // Linv plane slots in the ring (2 .. kASlots)
+  int sb_bufs;                    // trial staging buffers of phase 1: 2 (copy of step jb + 1 under the math of jb) or 1
   const double* lscale;           // [np]  2^(ea + eb_j - 32)
   double kscale;                  // 2^(56 - ea)
 };
@@ -188,7 +190,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
   const int dc = a.kp.dc, dk = a.kp.dk, np = a.np, nbuf = ia.nbuf;
   uint8_t* bbuf = smem;                                  // [2][7][64][128]
   uint8_t* aring = smem + 2 * kBBufBytes;                // [kASlots][128][128]
-  double* s_alpha = reinterpret_cast<double*>(smem + kRingBytes);   // [2][64]
+  const int ring_bytes = 2 * kBBufBytes + ia.n_aslots * kASlotBytes;
+  double* s_alpha = reinterpret_cast<double*>(smem + ring_bytes);   // [2][64]
   double* s_mu = s_alpha + 128;                          // [2][64]
   double* s_linf = s_mu + 128;                           // [2][64]
   double* s_red = s_linf + 128;                          // [4][64] row sums of the four TMEM lane quarters
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
   int32_t* zb = za + dk * LD;                            // [dk][LD]
   uint8_t* s_mask = reinterpret_cast<uint8_t*>(zb + dk * LD);  // [kMaxDc]
   // phase-1 staging: behind everything else (nbuf = 2) or aliased onto the operand ring (nbuf = 1)
-  double* stage = nbuf == 2 ? reinterpret_cast<double*>(smem + ((kRingBytes + ia.misc_bytes + 15) & ~15)) : reinterpret_cast<double*>(smem);
+  double* stage = nbuf == 2 ? reinterpret_cast<double*>(smem + ((ring_bytes + ia.misc_bytes + 15) & ~15)) : reinterpret_cast<double*>(smem);
   double* sa = stage;                                    // [dc][LD]     candidates (transposed)
   double* sb = sa + dc * LD;                             // [2][dc][LD]  trials, double buffered
 
@@ -240,7 +243,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
 
   if (is_producer) {
     // ================= TMA producer warp (uniform control flow, elected issue) =================
-    unsigned b_n = 0, a_n = 0, it = 0;
+    unsigned b_n = 0, it = 0;
+    int slot = 0;
+    unsigned aph = 0;                  // parity of the current pass over the A slots
+    const int n_aslots = ia.n_aslots;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int kb = it % nbuf;
       VZ_I8T_DECL;
@@ -260,13 +266,12 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
             tma_load_2d_elect(bbuf + buf * kBBufBytes + s * kBPlaneBytes, &ia.mapK, kc * kKC, krow0 + s * kTM, bfull + buf);
           ++b_n;
           for (int t = 0; t < kDigits; ++t) {
-            const int slot = a_n % kASlots;
             VZ_I8T_START(t_b);
-            mbar_wait_bounded(aempty + slot, ((a_n / kASlots) & 1) ^ 1);
+            mbar_wait_bounded(aempty + slot, aph ^ 1);
             VZ_I8T_ADD(9, t_b);
             mbar_expect_tx_elect(afull + slot, kASlotBytes);
             tma_load_3d_elect(aring + slot * kASlotBytes, &ia.mapL, kc * kKC, jt * kJT, t, afull + slot);
-            ++a_n;
+            if (++slot == n_aslots) { slot = 0; aph ^= 1; }
           }
         }
       }
@@ -274,7 +279,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
     }
   } else if (is_mma) {
     // ================= MMA issuer warp (uniform control flow, elected issue) =================
-    unsigned b_n = 0, a_n = 0, jt_n = 0;
+    unsigned b_n = 0, jt_n = 0;
+    int slot = 0;
+    unsigned aph = 0;
+    const int n_aslots = ia.n_aslots;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       VZ_I8T_DECL;
       VZ_I8T_START(t_a);
@@ -293,13 +301,13 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
           const int ksteps = (np - kc * kKC) >= kKC ? 4 : (np - kc * kKC + 31) / 32;   // the last chunk may be half
           const uint32_t bbase = smem_u32(bbuf + buf * kBBufBytes);
           for (int t = 0; t < kDigits; ++t) {
-            const int slot = a_n % kASlots;
             VZ_I8T_START(t_b);
-            mbar_wait_bounded(afull + slot, (a_n / kASlots) & 1);
+            mbar_wait_bounded(afull + slot, aph);
             VZ_I8T_ADD(6, t_b);
-            ++a_n;
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(smem_u32(aring + slot * kASlotBytes));
+            uint64_t* const slot_empty = aempty + slot;
+            if (++slot == n_aslots) { slot = 0; aph ^= 1; }
             constexpr uint32_t idesc = umma_idesc_i8();
             // (The A-operand collector - collector::a::fill/use/lastuse over the MMAs that share a Linv plane and
             // k step - was tried: correct, but the MMAs then no longer overlap their operand fetches: 99 instead of
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
                 touched |= 1u << g;
               }
             }
-            umma_commit(aempty + slot);   // slot reusable once these MMAs have read it
+            umma_commit(slot_empty);   // slot reusable once these MMAs have read it
           }
           umma_commit(bempty + buf);
         }
@@ -364,13 +372,18 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
 #pragma unroll
       for (int i = 0; i < 2; ++i) { mu_part[i] = 0.0; lmin[i] = INFINITY; }
       const int nj = np / 64;
+      const bool dbl = ia.sb_bufs == 2;
       stage_trials(0, 0);
       cp_async_commit();
       for (int jb = 0; jb < nj; ++jb) {
-        const int buf = jb & 1;
-        if (jb + 1 < nj) stage_trials(jb + 1, buf ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
+        const int buf = dbl ? (jb & 1) : 0;
+        if (dbl) {
+          if (jb + 1 < nj) stage_trials(jb + 1, buf ^ 1);
+          cp_async_commit();
+          cp_async_wait<1>();
+        } else {                       // one staging buffer (large Dc): the copy of step jb was issued after step jb - 1
+          cp_async_wait<0>();
+        }
         ksync();
         if (dk > 0) {
           stage_rows_T_i32(a.Z, np, dk, jb * 64, 64, zb, LD, kKT);
@@ -445,6 +458,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
           }
         }
         ksync();
+        if (!dbl && jb + 1 < nj) {     // everybody is done with the buffer: refill it (latency exposed, large Dc only)
+          stage_trials(jb + 1, 0);
+          cp_async_commit();
+        }
       }
       cp_async_wait<0>();
 #pragma unroll
@@ -599,9 +616,19 @@ size_t score_i8_misc_bytes(int dk) {
   return sizeof(double) * (128 + 128 + 128 + 256) + sizeof(uint64_t) * (4 + 2 * kASlots + 2 + 4) + 16 +
          sizeof(int32_t) * dk * 2 * kLD1 + kMaxDc;
 }
-size_t score_i8_stage_bytes(int dc) { return sizeof(double) * 3 * dc * kLD1; }
-size_t score_i8_smem_bytes(int dc, int dk, int nbuf) {
-  return 1024 + kRingBytes + ((score_i8_misc_bytes(dk) + 15) & ~size_t(15)) + (nbuf == 2 ? score_i8_stage_bytes(dc) : 0);
+size_t score_i8_stage_bytes(int dc, int sb_bufs = 2) { return sizeof(double) * (1 + sb_bufs) * dc * kLD1; }
+size_t score_i8_smem_bytes(int dc, int dk, int nbuf, int n_aslots = kASlots, int sb_bufs = 2) {
+  return 1024 + 2 * kBBufBytes + (size_t)n_aslots * kASlotBytes + ((score_i8_misc_bytes(dk) + 15) & ~size_t(15)) +
+         (nbuf == 2 ? score_i8_stage_bytes(dc, sb_bufs) : 0);
+}
+// Shared-memory plan: overlap the phases (nbuf = 2) whenever the phase-1 staging fits next to the operand ring, giving
+// up Linv slots and the second trial buffer for large Dc; otherwise back to back with the staging aliased onto the ring.
+struct I8Plan { int nbuf, n_aslots, sb_bufs; };
+I8Plan score_i8_plan(int dc, int dk) {
+  const int tries[4][2] = {{4, 2}, {3, 2}, {3, 1}, {2, 1}};
+  for (const auto& t : tries)
+    if (score_i8_smem_bytes(dc, dk, 2, t[0], t[1]) <= 227 * 1024) return {2, t[0], t[1]};
+  return {1, kASlots, 2};
 }
 
 }  // namespace
@@ -627,7 +654,8 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
     h->launches++;
     h->i8_ready = true;
   }
-  const int nbuf = score_i8_smem_bytes(h->dc, h->dk, 2) <= 227 * 1024 ? 2 : 1;
+  const I8Plan plan = score_i8_plan(h->dc, h->dk);
+  const int nbuf = plan.nbuf;
   VZ_TRY(h->i8_kdig.reserve((size_t)grid * nbuf * kDigits * kTM * np));
   // (A persisting L2 access-policy window over the digit scratch, as k_score uses for its fp64 scratch, changes
   // nothing here: the two buffers are 136 MB at C2 against 126 MB of L2, the freshly written tile is the LRU victim
@@ -657,6 +685,8 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
   ia.lscale = h->i8_scale.as<double>();
   ia.kscale = ldexp(1.0, 56 - ea);
   ia.nbuf = nbuf;
+  ia.n_aslots = plan.n_aslots;
+  ia.sb_bufs = plan.sb_bufs;
   ia.misc_bytes = (int)score_i8_misc_bytes(h->dk);
   {
     const uint64_t dims[2] = {(uint64_t)np, (uint64_t)grid * nbuf * kDigits * kTM};
@@ -671,7 +701,7 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
     VZ_TRY(make_tensor_map_u8(&ia.mapL, h->i8_planes.as<uint8_t>(), 3, dims, strides, box));
   }
   const bool need_linf = (linf != nullptr) || (a.apply_tr && a.radius <= 0.5);
-  const size_t sm = score_i8_smem_bytes(h->dc, h->dk, nbuf);
+  const size_t sm = score_i8_smem_bytes(h->dc, h->dk, nbuf, plan.n_aslots, plan.sb_bufs);
   if (sm > 227 * 1024) { set_error("k_score_i8 needs %zu bytes of shared memory", sm); return VZGP_ERR_UNSUPPORTED; }
   if (need_linf) {
     VZ_CUDA(cudaFuncSetAttribute(k_score_i8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
