@@ -94,7 +94,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000ull) __trap();
+      else if (t - t0 > 20000000000ull) __trap();   // 20 s: far beyond any wait of a healthy run, time-sliced GPUs included
     }
   }
 }
