@@ -3,6 +3,8 @@
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r02.log 2>&1; echo "pytest exit $?"; tail -6 gpurun_out/pytest_gpu_r02.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -2
+# the FP64 DMMA kernel on the large pools as well (it stays the reference implementation of the tcgen05 kernel)
+VZGP_SCORE_I8=0 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k 'c2_full_pool or score' 2>&1 | tail -2
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r02_1gpu.json 2> gpurun_out/bench_r02_1gpu.err; echo "bench exit $?"; python - <<'PY'
 import json
 j=json.loads(open('gpurun_out/bench_r02_1gpu.json').read().strip().splitlines()[-1])
