@@ -96,7 +96,8 @@ typedef struct vzgp_pe_params {
 } vzgp_pe_params;
 
 const char* vzgp_last_error(void);       /* thread-local message of the last failure */
-int vzgp_version(void);                  /* ABI version, currently 2 (1: without the linear_* fields of vzgp_params) */
+int vzgp_version(void);                  /* ABI version, currently 3 (1: without the linear_* fields of vzgp_params;
+                                            2: without vzgp_eagle_config.n_parallel) */
 int vzgp_device_count(void);
 
 /* device: CUDA ordinal.  stream: a cudaStream_t cast to void*, or NULL for a
