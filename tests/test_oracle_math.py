@@ -137,3 +137,68 @@ def test_ard_fit_weak_pin_tuned_gp_models_dataset():
 def test_top_k_ordering():
   s = np.array([1.0, 3.0, 3.0, -np.inf, 2.0])
   assert go.top_k(s, 3).tolist() == [1, 2, 4]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Round-2 restatements: transfer-learning stacks, set-PE, set flies (checked against closed forms / each other)
+# ---------------------------------------------------------------------------------------------------------------------
+def _toy_pred(n, d, seed, sn2=1e-3):
+  rng = np.random.default_rng(seed)
+  x = rng.uniform(size=(n, d))
+  y = np.sin(3 * x[:, 0]) + 0.1 * rng.normal(size=n)
+  return x, y, go.precompute_predictive(go.GPParams(1.2, np.full(d, 0.4), sn2), x, y)
+
+
+def test_transfer_alpha_and_single_level_stack():
+  # gp/transfer_learning.py:38-59, :96-118 by hand: n_top = 30, n_base = 100, h = 6
+  dof_base, dof_top = max(100 - 6, 100 / 7), max(30 - 6, 30 / 7)
+  beta2 = dof_top / dof_base * (1 + dof_base + 1.0)
+  assert abs(go.transfer_alpha(30, 100, 6) - beta2 / (1 + beta2)) < 1e-15
+  assert go.transfer_dof(4, 6) == 4 / 7                       # fewer points than hyper-parameters
+  assert 0 < go.transfer_alpha(5, 500, 6) < go.transfer_alpha(50, 500, 6) < 1
+  x, y, pred = _toy_pred(25, 3, 0)
+  xs = np.random.default_rng(1).uniform(size=(7, 3))
+  np.testing.assert_array_equal(go.predict_stack([pred], xs)[0], go.predict(pred, xs)[0])
+  np.testing.assert_array_equal(go.predict_stack([pred], xs)[1], go.predict(pred, xs)[1])
+  # a second level trained on exactly-zero residuals of the same data adds (almost) nothing to the mean
+  resid = go.stack_residual_labels([pred], x, go.predict(pred, x)[0])
+  np.testing.assert_allclose(resid, 0.0, atol=1e-12)
+  from vizier_b200 import gp as _gp_mod   # host-side helper of the product: same formula
+  assert abs(_gp_mod.transfer_alpha(30, 100, 6) - go.transfer_alpha(30, 100, 6)) < 1e-15
+
+
+def test_set_pe_score_closed_forms():
+  xa, ya, pa = _toy_pred(20, 2, 3)
+  rng = np.random.default_rng(4)
+  xb = np.concatenate([xa, rng.uniform(size=(4, 2))])
+  pb = go.precompute_predictive(pa.params, xb, np.r_[ya, np.zeros(4)])
+  pts = rng.uniform(size=(6, 1, 2))
+  # q = 1: log of the predictive variance under B + the penalty of that one point
+  acq, aux = go.set_pe_score(pa, pb, pts, threshold=0.3, use_trust_region=False)
+  mu, sd = go.predict(pa, pts[:, 0])
+  _, sdb = go.predict(pb, pts[:, 0])
+  np.testing.assert_allclose(acq, 2 * np.log(sdb) + 10.0 * np.minimum(mu + 0.5 * sd - 0.3, 0.0), atol=1e-10)
+  np.testing.assert_allclose(aux['stddev_from_all'], sdb, atol=1e-12)
+  # a set with a repeated point: cov = [[v, v - sn2], [v - sn2, v]] (v includes the noise) -> det = sn2 (2 v - sn2)
+  two = rng.uniform(size=(1, 2, 2))
+  twin = np.repeat(two[:, :1], 2, axis=1)
+  v = go.predict(pb, twin[0, :1])[1][0] ** 2
+  sn2 = pa.params.observation_noise_variance
+  got = go.set_pe_score(pa, pb, twin, penalty_coefficient=0.0, use_trust_region=False)[0][0]
+  np.testing.assert_allclose(got, np.log(sn2 * (2 * v - sn2)), rtol=1e-9)
+  assert got < go.set_pe_score(pa, pb, two, penalty_coefficient=0.0, use_trust_region=False)[0][0]
+  # set trust region: every member outside the radius costs -1e4 - dist
+  far = np.full((1, 2, 2), 0.999)
+  base = go.set_pe_score(pa, pb, far, use_trust_region=False)[0][0]
+  dist = go.min_linf_distance(far[0], xb, np.ones(2, bool))
+  with_tr = go.set_pe_score(pa, pb, far, trust_radius_value=1e-3)[0][0]
+  np.testing.assert_allclose(with_tr, base + np.sum(-1e4 - dist), rtol=1e-12)
+
+
+def test_set_fly_perturbation_directions():
+  from oracle import eagle_oracle as eo
+  d = eo.set_perturbation_directions(seed=5, iteration=3, batch_size=4, q=3, dim=5).reshape(4, 3, 5)
+  np.testing.assert_allclose(np.max(np.abs(d), axis=1), 1.0)        # the largest member of every feature is +-1
+  assert np.all(np.abs(d) <= 1.0)
+  d1 = eo.set_perturbation_directions(seed=5, iteration=3, batch_size=4, q=1, dim=5)
+  assert set(np.unique(d1)) <= {-1.0, 1.0}                          # q = 1 degenerates to signs (eagle_strategy.py:1033-1044)
