@@ -566,7 +566,9 @@ def run_gpu(args):
     i8_ach = i8_ops_per_candidate(n_trials) * m_pool / (kern_ms * 1e-3) * 1e-12
     roofline = {'bound': 'tensor', 'achieved': i8_ach, 'peak': i8_peak, 'unit': 'TOP/s', 'frac': i8_ach / i8_peak,
                 'traffic': traffic, 'traffic_source': traffic_src, 'kernel': 'k_score_i8', 'kernel_ms': kern_ms,
-                'note': 'tcgen05.mma kind::i8 (s8 x s8 -> s32 in TMEM): W = K* Linv^T as 28 exact products of balanced base-256 '
+                'note': 'frac is against the INT8 tensor roof of the kernel that now runs; measured against round 1\'s FP64 DMMA roof '
+                        '(frac 0.755 then) the same work is fp64_equivalent.of_fp64_dmma_peak.  '
+                        'tcgen05.mma kind::i8 (s8 x s8 -> s32 in TMEM): W = K* Linv^T as 28 exact products of balanced base-256 '
                         'digit planes, recombined in fp64; peak = ' + i8_src + '.  M = 128, N = 64 MMAs (7 accumulator groups x 64 '
                         'columns fill TMEM) read 6 KB of shared memory per 32-cycle MMA: the operand bandwidth bounds them at 48 '
                         'cycles = 0.67 of the tensor peak (tools/umma_rate.cu)',
