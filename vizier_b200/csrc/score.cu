@@ -423,7 +423,7 @@ int make_tensor_map_f64(void* map, const double* base, uint64_t rows, uint64_t c
 }
 
 int make_tensor_map_u8(void* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                       const uint32_t* box) {
+                       const uint32_t* box, bool promote_256) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return VZGP_ERR_CUDA; }
   cuuint64_t gdim[3], gstride[2];
@@ -432,7 +432,8 @@ int make_tensor_map_u8(void* map, const void* base, int rank, const uint64_t* di
   for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides[i];
   CUresult r = fn(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base),
                   gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  promote_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (u8) failed with CUresult %d", (int)r); return VZGP_ERR_CUDA; }
   return 0;
 }

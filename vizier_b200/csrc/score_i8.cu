@@ -165,6 +165,9 @@ __device__ __forceinline__ void tmem_ld4(uint32_t addr, int32_t (&v)[4]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                : "r"(addr));
 }
+__device__ __forceinline__ void st_u16_keep(void* p, uint16_t v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;\n" ::"l"(p), "h"(v), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 __device__ __forceinline__ void g_i8_t_tiles() {
@@ -255,7 +258,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
       VZ_I8T_ADD(11, t_a);
       VZ_I8T_START(t_a);
       const int krow0 = ((int)blockIdx.x * nbuf + kb) * kDigits * kTM;
-      for (int jt = 0; jt < njt; ++jt) {
+      for (int jj = 0; jj < njt; ++jj) {
+        const int jt = njt - 1 - jj;     // descending: k chunk kc is last needed by j tile kc, so the digit scratch dies front to back
         for (int kc = 0; kc <= jt; ++kc) {
           const int buf = b_n & 1;
           VZ_I8T_START(t_b);
@@ -286,7 +290,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       VZ_I8T_DECL;
       VZ_I8T_START(t_a);
-      for (int jt = 0; jt < njt; ++jt) {
+      for (int jj = 0; jj < njt; ++jj) {
+        const int jt = njt - 1 - jj;     // descending: k chunk kc is last needed by j tile kc, so the digit scratch dies front to back
         VZ_I8T_START(t_b);
         mbar_wait_bounded(tempty, (jt_n & 1) ^ 1);   // the previous j tile's accumulators have been read
         VZ_I8T_ADD(4, t_b);
@@ -340,6 +345,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
     constexpr int kKT = kKWarps * 32;
     auto ksync = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(kKT) : "memory"); };
     const int ty = tid / 16, tx = tid % 16;
+    // the digits are written a tile ahead of their use: ask L2 to evict them last (the dead ones are discarded by the
+    // epilogue warps), so that they are still resident when phase 2 streams them
+    uint64_t keep_policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(keep_policy));
     const double* XTs = a.XT;
     const double* XTu = a.XT + (size_t)dc * np;
     unsigned it = 0;
@@ -450,8 +459,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
 #pragma unroll
             for (int s = kDigits - 1; s >= 0; --s) {
               uint8_t* p = row + (size_t)s * kTM * np;
-              *reinterpret_cast<uint16_t*>(p + GP::col_of(tx, 0)) = (uint16_t)((q[0] & 255ll) | ((q[1] & 255ll) << 8));
-              *reinterpret_cast<uint16_t*>(p + GP::col_of(tx, 2)) = (uint16_t)((q[2] & 255ll) | ((q[3] & 255ll) << 8));
+              st_u16_keep(p + GP::col_of(tx, 0), (uint16_t)((q[0] & 255ll) | ((q[1] & 255ll) << 8)), keep_policy);
+              st_u16_keep(p + GP::col_of(tx, 2), (uint16_t)((q[2] & 255ll) | ((q[3] & 255ll) << 8)), keep_policy);
 #pragma unroll
               for (int j = 0; j < 4; ++j) q[j] = (q[j] + 128) >> 8;
             }
@@ -489,9 +498,11 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
     const int quarter = warp & 3, cbase = ((warp - kKWarps) >> 2) * (kEGroups * 8);   // first candidate column of this warp
     int clamped = 0;
     unsigned jt_n = 0, it = 0;
+    const bool can_discard = (np % kKC) == 0;    // discard.L2 wants 128-byte aligned lines
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int m0 = tile * kTM;
       const int kb = it % nbuf;
+      const uint8_t* kdt = ia.kdig + ((size_t)blockIdx.x * nbuf + kb) * kDigits * kTM * np;
       VZ_I8T_DECL;
       VZ_I8T_START(t_a);
       // acc[grp]: this warp's sum over its 32 Linv rows (and over the j tiles) for candidate 8 grp + c(lane),
@@ -499,7 +510,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
       double acc[kEGroups];
 #pragma unroll
       for (int grp = 0; grp < kEGroups; ++grp) acc[grp] = 0.0;
-      for (int jt = 0; jt < njt; ++jt) {
+      for (int jj = 0; jj < njt; ++jj) {
+        const int jt = njt - 1 - jj;     // descending: k chunk kc is last needed by j tile kc, so the digit scratch dies front to back
         VZ_I8T_START(t_b);
         mbar_wait_bounded(tfull, jt_n & 1);
         if (etid == 0) { VZ_I8T_ADD(1, t_b); }
@@ -557,6 +569,14 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_score_i8(const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(tempty)) : "memory");
+        if (can_discard) {
+          // All MMAs of j tile jt are done, and with the j tiles in descending order that was the last use of k chunk
+          // jt of this tile's K* digits: drop its lines from L2 without writing them back.  The scratch is written
+          // one tile ahead and exceeds L2 otherwise (2 x 68 MB at C2): every digit then went through HBM once, 0.7 GB
+          // out + 0.8 GB in per launch.  (Ordered before the next owner's stores by the release on kfree below.)
+          for (int i = etid; i < kDigits * kTM; i += kET)
+            asm volatile("discard.global.L2 [%0], 128;\n" ::"l"(kdt + (size_t)i * np + (size_t)jt * kKC) : "memory");
+        }
         if (etid == 0) { VZ_I8T_ADD(2, t_b); }
       }
       if ((lane & 3) == 0) {
@@ -692,7 +712,8 @@ int launch_score_i8(vzgp_handle* h, const double* Xs, const int32_t* Zs, int M, 
     const uint64_t dims[2] = {(uint64_t)np, (uint64_t)grid * nbuf * kDigits * kTM};
     const uint64_t strides[1] = {(uint64_t)np};
     const uint32_t box[2] = {(uint32_t)kKC, (uint32_t)kTM};
-    VZ_TRY(make_tensor_map_u8(&ia.mapK, ia.kdig, 2, dims, strides, box));
+    // 128-byte L2 promotion: a 256-byte one would pull the neighbouring k chunk's (already discarded) line back in
+    VZ_TRY(make_tensor_map_u8(&ia.mapK, ia.kdig, 2, dims, strides, box, false));
   }
   {
     const uint64_t dims[3] = {(uint64_t)np, (uint64_t)np, (uint64_t)kDigits};
