@@ -251,3 +251,66 @@ def test_ucb_pe_designer_set_batches(dev):
   assert len(acqs) == 1                                 # one acquisition value for the whole set
   dmin = min(np.linalg.norm(pts[i] - pts[j]) for i in range(1, 4) for j in range(i + 1, 4))
   assert dmin > 0.05                                    # log-det repels the members from each other
+
+
+@pytest.mark.parametrize('set_pe', [False, True])
+def test_prior_acquisition_like_the_reference_test(set_pe):
+  """gp_ucb_pe_test.py:476-607 (test_prior_acquisition), same configuration and assertions: a constant prior
+  acquisition of 12345 appears in every suggestion's metadata; the first suggestion of a batch is UCB with
+  acquisition = mean + 10 stddev + prior; the others are PE - per point  stddev_from_all (+ a non-positive penalty)
+  + prior, or, with set optimisation, ONE value log det(cov) + prior for the whole set whose geometric mean of
+  eigenvalues is below the arithmetic mean of the predictive variances."""
+  import dataclasses
+  from vizier_b200 import vz
+  from vizier_b200.designers import gp_ucb_pe
+  from vizier_b200 import optimizers as vb
+  p = vz.ProblemStatement()
+  for i in range(3):
+    p.search_space.root.add_float_param(f'x{i}', -1.0 * (i + 1), 2.0 * (i + 1))
+  p.metric_information.append(vz.MetricInformation(name='metric', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  fac = vb.VectorizedOptimizerFactory(strategy_factory=vb.VectorizedEagleStrategyFactory(), max_evaluations=100)
+  cfg = gp_ucb_pe.UCBPEConfig(ucb_coefficient=10.0, explore_region_ucb_coefficient=0.5, cb_violation_penalty_coefficient=10.0,
+                              ucb_overwrite_probability=0.0, pe_overwrite_probability=0.0, signal_to_noise_threshold=0.0,
+                              optimize_set_acquisition_for_exploration=set_pe)
+  ns = 'gp_ucb_pe_bandit_test'
+  des = gp_ucb_pe.VizierGPUCBPEBandit(p, acquisition_optimizer_factory=fac, metadata_ns=ns, num_seed_trials=1, config=cfg,
+                                      prior_acquisition=lambda xc, xz: np.ones(xc.shape[0]) * 12345.0, rng=1)
+  rng = np.random.default_rng(1)
+  batch, iters, trial_id, all_trials = 3, 2, 1, []
+  for _ in range(iters):
+    sugg = des.suggest(count=batch)
+    assert len(sugg) == batch
+    done = []
+    for s in sugg:
+      trial_id += 1
+      t = s.to_trial(trial_id)
+      t.complete(vz.Measurement({'metric': float(rng.uniform(-10.0, 10.0))}))
+      done.append(t)
+    all_trials.extend(done)
+    des.update(vz.CompletedTrials(done), vz.ActiveTrials())
+  assert len(all_trials) == iters * batch
+  set_acq, sd_all = None, []
+  for idx, t in enumerate(all_trials):
+    if idx < batch:
+      continue                      # seed suggestions
+    md = t.metadata.ns(ns)
+    pred = md.ns('prediction_in_warped_y_space')
+    mean, sd, sda, acq = (float(pred[k]) for k in ('mean', 'stddev', 'stddev_from_all', 'acquisition'))
+    prior = float(md.ns('prior_acquisition')['value'])
+    assert prior == 12345.0
+    if idx % batch == 0:
+      assert pred['use_ucb'] == 'True'
+      np.testing.assert_allclose(mean + 10.0 * sda + prior, acq, rtol=1e-9)
+    else:
+      assert pred['use_ucb'] == 'False'
+      if set_pe:
+        assert acq > 10000.0
+        sd_all.append(sda)
+        if set_acq is None:
+          set_acq = acq - prior
+        else:
+          np.testing.assert_allclose(set_acq, acq - prior, rtol=1e-9)
+      else:
+        assert acq <= sda + prior + 1e-9      # PE: stddev_from_all + (penalty <= 0) + prior
+  if set_pe:
+    assert np.exp(set_acq / (batch - 1)) <= np.mean(np.square(sd_all)) + 1e-12

@@ -112,7 +112,8 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
                ensemble_size: Optional[int] = 1, ard_optimizer: Optional[ard.ScipyLbfgsB] = None,
                ard_random_restarts: int = 4, use_trust_region: bool = True, num_seed_trials: int = 1,
                config: UCBPEConfig = UCBPEConfig(), rng: Any = None, clear_jax_cache: bool = False,
-               padding_schedule=None, prior_acquisition=None, mixes_linear_kernel: bool = False, device: int = 0):
+               padding_schedule=None, prior_acquisition=None, mixes_linear_kernel: bool = False,
+               metadata_ns: str = 'google_gp_ucb_pe_bandit', device: int = 0):
     if problem.search_space.is_conditional:
       raise ValueError(f'{type(self)} does not support conditional search.')
     if len(problem.metric_information) != 1:
@@ -133,7 +134,7 @@ class VizierGPUCBPEBandit(vz.Designer, vz.Predictor):
     self._use_trust_region = use_trust_region
     self._num_seed_trials = num_seed_trials
     self._config = config
-    self._metadata_ns = 'google_gp_ucb_pe_bandit'
+    self._metadata_ns = metadata_ns
     self._rng = np.random.default_rng(_gpb._seed_from(rng))
     self._converter = converters.TrialToModelInputConverter.from_problem(problem)
     self._halton_offset = int(self._rng.integers(0, 2**16))
