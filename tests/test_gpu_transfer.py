@@ -130,3 +130,68 @@ def test_designer_with_priors_predicts_better_from_few_trials():
     errs[with_prior] = float(np.sqrt(np.mean((pred.mean - truth) ** 2)))
     assert np.all(pred.stddev > 0)
   assert errs[True] < 0.6 * errs[False], errs
+
+
+def _lambda_search(f, num_trials, seed):
+  """gp_bandit_test.py:64-105 (_setup_lambda_search): 1-D problem on [-5, 5), `num_trials` evaluated trials of f."""
+  from vizier_b200 import vz
+  from vizier_b200.designers import gp_bandit
+  from vizier_b200 import optimizers as vb
+  p = vz.ProblemStatement()
+  p.search_space.root.add_float_param('x0', -5.0, 5.0)
+  p.metric_information.append(vz.MetricInformation(name='obj', goal=vz.ObjectiveMetricGoal.MAXIMIZE))
+  xs = np.random.default_rng(seed).uniform(-5.0, 5.0, num_trials)
+  trials = []
+  for i, xv in enumerate(xs):
+    t = vz.Trial(parameters={'x0': float(xv)}, id=i + 1)
+    t.complete(vz.Measurement({'obj': float(f(xv))}))
+    trials.append(t)
+  fac = vb.VectorizedOptimizerFactory(strategy_factory=vb.VectorizedEagleStrategyFactory(), max_evaluations=1000,
+                                      suggestion_batch_size=25)
+  return gp_bandit.VizierGPBandit(p, acquisition_optimizer_factory=fac, rng=1), trials, p
+
+
+@pytest.mark.xfail(strict=False, reason="skipped upstream too ('The current transfer learning seems broken and test failing', "
+                   "gp_bandit_test.py:546-547): each study's labels are warped on their own scale, so the residuals of "
+                   "a linearly transformed study against the prior are not small; this port reproduces that behaviour "
+                   "(measured: MSE 0.139 with the prior against 0.004 without)")
+def test_prior_warping_like_the_reference_test():
+  """gp_bandit_test.py:550-595 (test_prior_warping): the prior study samples f, the current study the linearly
+  transformed 3 f + 10; upstream expects the designer with the prior to predict the transformed function better."""
+  from vizier_b200 import vz
+  f = lambda x: -((x / 5.0 - 0.5) ** 2)
+  g = lambda x: 3.0 * f(x) + 10.0
+  x_test = np.random.default_rng(1).uniform(-5.0, 5.0, 100)
+  y_test = np.array([g(x) for x in x_test])
+  test_trials = [vz.Trial(parameters={'x0': float(x)}) for x in x_test]
+  with_prior, prior_trials, _ = _lambda_search(f, 100, 11)
+  with_prior.set_priors([vz.CompletedTrials(prior_trials)])
+  no_prior, obs, _ = _lambda_search(g, 20, 12)
+  no_prior.update(vz.CompletedTrials(obs), vz.ActiveTrials())
+  with_prior.update(vz.CompletedTrials(obs), vz.ActiveTrials())
+  mse = lambda d: float(np.mean((d.predict(test_trials, rng=2, num_samples=300).mean - y_test) ** 2))
+  assert mse(with_prior) < mse(no_prior)
+
+
+@pytest.mark.parametrize('iters,batch_size', [(3, 5), (5, 1)])
+def test_run_with_priors_like_the_reference_test(iters, batch_size):
+  """gp_bandit_test.py:597-621 (test_run_with_priors): a designer with a prior study survives a suggest / complete /
+  update loop with random metrics; every suggestion lies in the search space."""
+  from vizier_b200 import vz
+  des, prior_trials, p = _lambda_search(lambda x: -((x / 5.0 - 0.5) ** 2), 100, 21)
+  des.set_priors([vz.CompletedTrials(prior_trials)])
+  rng = np.random.default_rng(1)
+  n, tid = 0, 1000
+  for _ in range(iters):
+    sugg = des.suggest(batch_size)
+    assert len(sugg) == batch_size
+    done = []
+    for s in sugg:
+      assert -5.0 <= s.parameters['x0'].value <= 5.0
+      tid += 1
+      t = s.to_trial(tid)
+      t.complete(vz.Measurement({'obj': float(rng.uniform(-1.0, 1.0))}))
+      done.append(t)
+    n += len(done)
+    des.update(vz.CompletedTrials(done), vz.ActiveTrials())
+  assert n == iters * batch_size

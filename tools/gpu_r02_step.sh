@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_stepped_eagle.py -x -q -k "like_the_reference or designer" > gpurun_out/pytest_step.log 2>&1; echo "pytest exit $?"; tail -30 gpurun_out/pytest_step.log
+timeout 300 python -m pytest tests/test_gpu_transfer.py -q -k "like_the_reference" > gpurun_out/pytest_step.log 2>&1; echo "pytest exit $?"; tail -8 gpurun_out/pytest_step.log
